@@ -1,0 +1,165 @@
+/* polycracker_b200 -- C ABI of the B200-native polyCRACKER hot path.
+ *
+ * The reference (jlevy44/PolyCRACKER-Unofficial-Mirror) has no FFI: its hot path is a chain of click
+ * sub-commands that shell out to kmercountexact.sh / jellyfish / bbmap.sh / bedtools and glue the results with
+ * CPython.  Each entry point below replaces one of those stages; the comment on each cites
+ * the reference lines it stands in for (paths relative to /root/reference/polycracker/).  The Python side
+ * (polycracker_b200/binding.py) binds exactly these symbols with ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 (PC_OK) or a negative PC_E* code; pc_last_error() gives the message
+ *     (the reference ignores tool failures, polycracker.py:204-207; this library fails loudly instead).
+ *   - plain pointers and sizes only.  `loc` says where a caller-owned buffer lives: PC_HOST or PC_DEVICE
+ *     (a torch tensor's data_ptr()).  Sizes are queried first (pc_*_info), buffers are caller-owned.
+ *   - one pc_ctx per GPU, one host thread per pc_ctx.  All work is issued on the ctx stream (pc_set_stream lets a
+ *     caller hand in torch's current stream).
+ *   - k-mers are uint64: first base in the most significant of the low 2k bits, A=0 C=1 G=2 T=3, canonical =
+ *     min(k-mer, reverse complement) (jellyfish -C orientation, polycracker.py:203).  Integer order == the
+ *     Python string order the reference sorts its columns by (polycracker.py:295).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns PC_ECUDA.
+ */
+#ifndef POLYCRACKER_B200_H
+#define POLYCRACKER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PC_OK        0
+#define PC_EINVAL   -1   /* bad argument / unsupported mode (k > 32, perfect_mode = 0, ...) */
+#define PC_ECUDA    -2   /* CUDA runtime error (including "no device") */
+#define PC_ESTATE   -3   /* stage called out of order */
+#define PC_ENOMEM   -4   /* table would not fit / probe limit hit */
+#define PC_EIO      -5   /* file error (host helpers) */
+
+#define PC_HOST      0
+#define PC_DEVICE    1
+
+typedef struct pc_ctx pc_ctx;
+
+/* ---- library ------------------------------------------------------------------------------------------- */
+int         pc_version(void);
+const char* pc_last_error(void);
+int         pc_device_count(void);
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+int pc_create(int device, pc_ctx** out);
+int pc_destroy(pc_ctx* ctx);
+int pc_set_stream(pc_ctx* ctx, void* cuda_stream);       /* NULL -> the ctx's own stream */
+int pc_sync(pc_ctx* ctx);
+
+/* ---- a1  splitFasta geometry (polycracker.py:129-156), host-side integer work ------------------------------
+ * For every sequence length L: windows [i*C,(i+1)*C) for consecutive pairs of arange(0,L,C) when L > C, then the
+ * tail [last, L).  Zero-length sequences yield nothing.  Output order: input sequence order, start ascending
+ * (the caller applies `bedtools sort` / Python sorted() to names).  pc_chunk_count returns the number of chunks. */
+int64_t pc_chunk_count(const int64_t* seq_len, int64_t n_seqs, int64_t chunk_size);
+int     pc_chunk_table(const int64_t* seq_len, int64_t n_seqs, int64_t chunk_size,
+                       int64_t* chunk_seq, int64_t* chunk_start, int64_t* chunk_end);
+
+/* ---- K1  2-bit packing + N-mask (replaces `bedtools getfasta` + FASTA parsing, polycracker.py:170) ----------
+ * ascii: newline-free sequence bytes (n_bytes), host or device.  Chunk c is ascii[chunk_begin[c], chunk_end[c])
+ * (host arrays, ascending, non-overlapping).  Anything but acgtACGT is masked.  Each chunk is an independent
+ * record: no k-mer spans two chunks. */
+int pc_load_sequences(pc_ctx* ctx, const uint8_t* ascii, int64_t n_bytes, int loc,
+                      const int64_t* chunk_begin, const int64_t* chunk_end, int64_t n_chunks);
+/* device-resident staging buffer (>= n_bytes) a caller may fill itself before pc_load_sequences(ascii=that ptr,
+ * loc=PC_DEVICE); avoids a copy when the genome is produced on the GPU. */
+int pc_ascii_buffer(pc_ctx* ctx, int64_t n_bytes, uint8_t** dev_ptr);
+/* copy the packed representation out (tests): words[n_words] uint64, nmask[n_words] uint32, chunk_word0[n_chunks+1] */
+int pc_packed_info(pc_ctx* ctx, int64_t* n_words, int64_t* n_chunks);
+int pc_packed_get(pc_ctx* ctx, uint64_t* words, uint32_t* nmask, int64_t* chunk_word0, int loc);
+
+/* ---- K2+K3  canonical k-mer counting (replaces kmercountexact.sh / jellyfish count -C, polycracker.py:199,203)
+ * capacity = 0 -> sized from the number of windows.  1 <= k <= 32. */
+int pc_count(pc_ctx* ctx, int k, int64_t capacity);
+/* info[0]=capacity info[1]=distinct k-mers info[2]=valid windows info[3]=table bytes info[4]=max probe length */
+int pc_count_info(pc_ctx* ctx, int64_t info[8]);
+/* dump (kmer, count) with min_count <= count <= max_count (the .kcount file: `mincount=3` for k<=31,
+ * polycracker.py:199).  keys == NULL -> only *n is written.  Unordered, like the tools' dumps. */
+int pc_dump_counts(pc_ctx* ctx, uint32_t min_count, uint32_t max_count,
+                   uint64_t* keys, uint32_t* counts, int64_t cap, int loc, int64_t* n);
+/* multi-GPU exchange: all (kmer,count) pairs of the local table grouped by owner rank
+ * (owner = hash(kmer) % world); offsets[world+1] is a host array.  keys/counts are device buffers of
+ * capacity >= distinct k-mers.  pc_merge_counts adds received pairs into the ctx table (creating it with
+ * `capacity` slots when *fresh* != 0). */
+int pc_export_by_owner(pc_ctx* ctx, int world, uint64_t* keys_dev, uint32_t* counts_dev, int64_t cap,
+                       int64_t* offsets);
+int pc_merge_counts(pc_ctx* ctx, const uint64_t* keys_dev, const uint32_t* counts_dev, int64_t n,
+                    int k, int64_t capacity, int fresh);
+
+/* ---- K4  repeat-k-mer selection (replaces kmer2Fasta, polycracker.py:220-238) ------------------------------
+ * keep count >= low (and <= high when use_high); sort ascending; keep every `sampling`-th survivor
+ * (sorted-order sampling: declared deviation, the reference samples in the counter's dump order). */
+int pc_select(pc_ctx* ctx, uint32_t low, uint32_t high, int use_high, int64_t sampling, int64_t* n_selected);
+int pc_selected_get(pc_ctx* ctx, uint64_t* keys, int loc);             /* n_selected keys, ascending */
+/* install an externally chosen repeat set (the separately invoked blast_kmers stage reads it from the k-mer
+ * FASTA, polycracker.py:244; the multi-GPU path installs the all-gathered set).  Keys need not be sorted or
+ * canonical-unique on entry; they are canonicalised, sorted and de-duplicated; *n_unique is returned. */
+int pc_set_selected(pc_ctx* ctx, const uint64_t* keys, int64_t n, int k, int loc, int64_t* n_unique);
+
+/* ---- K5+K6  exact matching + occurrence matrix (replaces bbmap.sh perfectmode=t, blast2bed's sort/merge and
+ * generate_Kmer_Matrix's Counter/dok/tocsc, polycracker.py:252, 268-280, 343-355) --------------------------
+ * chunk_row[c] = row index of chunk c in the matrix or -1 when the chunk is filtered out
+ * (polycracker.py:322-327).  Result: CSR (n_rows x n_selected), entry = number of windows of chunk i whose
+ * canonical k-mer is repeat k-mer j.  Column indices ascending within a row. */
+int pc_build_matrix(pc_ctx* ctx, const int32_t* chunk_row, int64_t n_rows, int64_t* nnz);
+int pc_csr_get(pc_ctx* ctx, int64_t* indptr, int32_t* indices, float* data, int loc);
+int pc_df_get(pc_ctx* ctx, int32_t* df, int loc);                      /* stored entries per column */
+
+/* ---- K7  TF-IDF + L2 rows (replaces sklearn TfidfTransformer().fit_transform, polycracker.py:395-396) -------
+ * idf_j = ln((1+n)/(1+df_j)) + 1 in float32; rows divided by their L2 norm (double accumulation), zero rows
+ * untouched.  n_rows_global / df_global (device or host, may be NULL = use local) let ranks share a global idf. */
+int pc_tfidf(pc_ctx* ctx, int64_t n_rows_global, const int32_t* df_global, int df_loc);
+int pc_tfidf_get(pc_ctx* ctx, float* data, int loc);                   /* nnz values, CSR order */
+
+/* ---- measurement ------------------------------------------------------------------------------------------
+ * CUDA-event time (ms) of the last run of each stage on the ctx stream.  Index: 0 h2d, 1 pack, 2 table-init,
+ * 3 count, 4 select(scan), 5 sort, 6 repeat-table, 7 probe, 8 row-sort, 9 emit, 10 tfidf, 11 d2h.
+ * launches: kernels launched by this ctx since the last pc_reset_counters. */
+#define PC_N_STAGES 16
+int pc_timings(pc_ctx* ctx, float ms[PC_N_STAGES]);
+int pc_launch_count(pc_ctx* ctx, int64_t* launches);
+int pc_reset_counters(pc_ctx* ctx);
+
+/* ---- host helpers (no GPU) -------------------------------------------------------------------------------- */
+/* pack one 32-base word on the host with the exact device routine (unit tests) */
+int pc_host_pack_word(const uint8_t* bases, int n, uint64_t* word, uint32_t* nmask);
+int pc_host_canonical(uint64_t kmer, int k, uint64_t* out);
+/* kmer <-> text */
+int pc_kmer_decode(const uint64_t* keys, int64_t n, int k, char* out /* n*k bytes, no separators */);
+int pc_kmer_encode(const char* text, int64_t n, int k, uint64_t* keys /* ~0 when not acgtACGT */);
+/* FASTA reader: two-call protocol.  pc_fasta_scan fills n_seqs / total bases / name bytes; pc_fasta_read fills
+ * seq (newline-free), offsets[n_seqs+1], names ('\n'-joined first tokens of the headers). */
+int pc_fasta_scan(const char* path, int64_t* n_seqs, int64_t* n_bases, int64_t* name_bytes);
+int pc_fasta_read(const char* path, uint8_t* seq, int64_t* offsets, char* names);
+/* text writers: "KMER\tCOUNT\n" (.kcount) and ">KMER\nKMER\n" (.kcount.fa) */
+int pc_write_kcount(const char* path, const uint64_t* keys, const uint32_t* counts, int64_t n, int k, int append);
+int pc_write_kmer_fasta(const char* path, const uint64_t* keys, int64_t n, int k, int rc_labels);
+
+/* deterministic synthetic polyploid genome (bench + tests).  See csrc/synth.cpp. */
+typedef struct pc_synth_params {
+    uint64_t seed;
+    int64_t  genome_size;        /* total bases over all chromosomes */
+    int32_t  n_subgenomes;       /* 2 = allotetraploid, 3 = hexaploid */
+    int32_t  n_chrom;            /* chromosomes per subgenome */
+    double   divergence;         /* homoeolog substitution divergence (0.08) */
+    double   repeat_fraction;    /* target fraction of bases under repeats (0.60) */
+    int32_t  n_shared_families;  /* 200 */
+    int32_t  n_specific_families;/* 300 (split round-robin over subgenomes) */
+    int32_t  min_family_len, max_family_len;   /* 500..8000 */
+    double   max_copy_mutation;  /* U[0, 0.10] */
+    double   n_fraction;         /* 0.001 */
+    int32_t  min_n_run, max_n_run;             /* 100..10000 */
+    double   softmask_fraction;  /* 0.10 */
+} pc_synth_params;
+int64_t pc_synth_n_chrom(const pc_synth_params* p);
+int     pc_synth_chrom_len(const pc_synth_params* p, int64_t chrom, int64_t* len, char name[64]);
+int     pc_synth_chrom(const pc_synth_params* p, int64_t chrom, uint8_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

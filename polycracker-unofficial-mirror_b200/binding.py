@@ -1,0 +1,363 @@
+"""ctypes binding of ``include/polycracker_b200.h`` -- the only way Python reaches the CUDA kernels.
+
+There is no CPU fallback: if ``libpolycracker_b200.so`` is missing the import of this module raises, and every
+compute call raises :class:`PolycrackerError` when no CUDA device is present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+PC_HOST, PC_DEVICE = 0, 1
+PC_N_STAGES = 16
+STAGE_NAMES = ["h2d", "pack", "table_init", "count", "select", "sort", "rep_table", "probe", "row_sort", "emit",
+               "tfidf", "d2h", "export", "merge"]
+
+
+class PolycrackerError(RuntimeError):
+    pass
+
+
+class SynthParams(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("genome_size", C.c_int64), ("n_subgenomes", C.c_int32),
+                ("n_chrom", C.c_int32), ("divergence", C.c_double), ("repeat_fraction", C.c_double),
+                ("n_shared_families", C.c_int32), ("n_specific_families", C.c_int32),
+                ("min_family_len", C.c_int32), ("max_family_len", C.c_int32), ("max_copy_mutation", C.c_double),
+                ("n_fraction", C.c_double), ("min_n_run", C.c_int32), ("max_n_run", C.c_int32),
+                ("softmask_fraction", C.c_double)]
+
+
+def _load():
+    path = _build.LIB
+    if not os.path.exists(path):
+        # on the dev box nvcc is present: build in-tree; on a GPU box the prebuilt .so travels with the snapshot
+        try:
+            _build.build()
+        except Exception as exc:  # pragma: no cover
+            raise ImportError("libpolycracker_b200.so is missing and could not be built: %s "
+                              "(the CUDA extension is mandatory, there is no CPU fallback)" % exc)
+    return C.CDLL(path)
+
+
+lib = _load()
+
+_vp, _i64, _i32, _u32, _u64 = C.c_void_p, C.c_int64, C.c_int32, C.c_uint32, C.c_uint64
+_P = C.POINTER
+_SIGS = {
+    "pc_version": (C.c_int, []),
+    "pc_last_error": (C.c_char_p, []),
+    "pc_device_count": (C.c_int, []),
+    "pc_create": (C.c_int, [C.c_int, _P(_vp)]),
+    "pc_destroy": (C.c_int, [_vp]),
+    "pc_set_stream": (C.c_int, [_vp, _vp]),
+    "pc_sync": (C.c_int, [_vp]),
+    "pc_chunk_count": (_i64, [_vp, _i64, _i64]),
+    "pc_chunk_table": (C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp]),
+    "pc_load_sequences": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _vp, _i64]),
+    "pc_ascii_buffer": (C.c_int, [_vp, _i64, _P(_vp)]),
+    "pc_packed_info": (C.c_int, [_vp, _P(_i64), _P(_i64)]),
+    "pc_packed_get": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int]),
+    "pc_count": (C.c_int, [_vp, C.c_int, _i64]),
+    "pc_count_info": (C.c_int, [_vp, _vp]),
+    "pc_dump_counts": (C.c_int, [_vp, _u32, _u32, _vp, _vp, _i64, C.c_int, _P(_i64)]),
+    "pc_export_by_owner": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _vp]),
+    "pc_merge_counts": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, _i64, C.c_int]),
+    "pc_select": (C.c_int, [_vp, _u32, _u32, C.c_int, _i64, _P(_i64)]),
+    "pc_selected_get": (C.c_int, [_vp, _vp, C.c_int]),
+    "pc_set_selected": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, _P(_i64)]),
+    "pc_build_matrix": (C.c_int, [_vp, _vp, _i64, _P(_i64)]),
+    "pc_csr_get": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int]),
+    "pc_df_get": (C.c_int, [_vp, _vp, C.c_int]),
+    "pc_tfidf": (C.c_int, [_vp, _i64, _vp, C.c_int]),
+    "pc_tfidf_get": (C.c_int, [_vp, _vp, C.c_int]),
+    "pc_timings": (C.c_int, [_vp, _vp]),
+    "pc_launch_count": (C.c_int, [_vp, _P(_i64)]),
+    "pc_reset_counters": (C.c_int, [_vp]),
+    "pc_host_pack_word": (C.c_int, [_vp, C.c_int, _P(_u64), _P(_u32)]),
+    "pc_host_canonical": (C.c_int, [_u64, C.c_int, _P(_u64)]),
+    "pc_kmer_decode": (C.c_int, [_vp, _i64, C.c_int, _vp]),
+    "pc_kmer_encode": (C.c_int, [_vp, _i64, C.c_int, _vp]),
+    "pc_fasta_scan": (C.c_int, [C.c_char_p, _P(_i64), _P(_i64), _P(_i64)]),
+    "pc_fasta_read": (C.c_int, [C.c_char_p, _vp, _vp, _vp]),
+    "pc_write_kcount": (C.c_int, [C.c_char_p, _vp, _vp, _i64, C.c_int, C.c_int]),
+    "pc_write_kmer_fasta": (C.c_int, [C.c_char_p, _vp, _i64, C.c_int, C.c_int]),
+    "pc_synth_n_chrom": (_i64, [_P(SynthParams)]),
+    "pc_synth_chrom_len": (C.c_int, [_P(SynthParams), _i64, _P(_i64), C.c_char_p]),
+    "pc_synth_chrom": (C.c_int, [_P(SynthParams), _i64, _vp]),
+}
+EXPORTED = sorted(_SIGS)
+for _name, (_res, _args) in _SIGS.items():
+    _fn = getattr(lib, _name)          # AttributeError here = header and library disagree
+    _fn.restype, _fn.argtypes = _res, _args
+
+
+def last_error():
+    return (lib.pc_last_error() or b"").decode("utf-8", "replace")
+
+
+def check(rc, what=""):
+    if rc != 0:
+        raise PolycrackerError("%s failed (%d): %s" % (what or "polycracker_b200 call", rc, last_error()))
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def ptr(x):
+    """(address, location) of a numpy array (host) or torch tensor (host or device)."""
+    if x is None:
+        return None, PC_HOST
+    if _is_torch(x):
+        if not x.is_contiguous():
+            raise ValueError("tensor must be contiguous")
+        return x.data_ptr(), (PC_DEVICE if x.is_cuda else PC_HOST)
+    a = np.ascontiguousarray(x)
+    if a is not x:
+        raise ValueError("array must be C-contiguous")
+    return a.ctypes.data, PC_HOST
+
+
+def device_count():
+    return int(lib.pc_device_count())
+
+
+# ------------------------------------------------------------------------------------------------ host helpers
+def chunk_table(seq_len, chunk_size):
+    """a1 geometry (polycracker.py:129-147): returns (chunk_seq, chunk_start, chunk_end) int64 arrays."""
+    seq_len = np.ascontiguousarray(seq_len, dtype=np.int64)
+    n = lib.pc_chunk_count(seq_len.ctypes.data, len(seq_len), int(chunk_size))
+    if n < 0:
+        raise PolycrackerError("bad chunk_size")
+    cs, st, en = (np.empty(n, np.int64) for _ in range(3))
+    check(lib.pc_chunk_table(seq_len.ctypes.data, len(seq_len), int(chunk_size), cs.ctypes.data, st.ctypes.data,
+                             en.ctypes.data), "pc_chunk_table")
+    return cs, st, en
+
+
+def kmer_decode(keys, k):
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    out = np.empty(len(keys) * k, np.uint8)
+    check(lib.pc_kmer_decode(keys.ctypes.data, len(keys), k, out.ctypes.data), "pc_kmer_decode")
+    if len(keys) == 0:
+        return []
+    return out.view("S%d" % k).astype(str).tolist()
+
+
+def kmer_encode(kmers, k):
+    if len(kmers) == 0:
+        return np.empty(0, np.uint64)
+    buf = np.frombuffer("".join(kmers).encode(), dtype=np.uint8)
+    if len(buf) != len(kmers) * k:
+        raise ValueError("all k-mers must have length %d" % k)
+    out = np.empty(len(kmers), np.uint64)
+    check(lib.pc_kmer_encode(buf.ctypes.data, len(kmers), k, out.ctypes.data), "pc_kmer_encode")
+    return out
+
+
+def read_fasta(path):
+    """Returns (seq uint8[n_bases] newline-free, offsets int64[n_seqs+1], names list[str])."""
+    ns, nb, nn = _i64(), _i64(), _i64()
+    check(lib.pc_fasta_scan(path.encode(), C.byref(ns), C.byref(nb), C.byref(nn)), "pc_fasta_scan(%s)" % path)
+    seq = np.empty(nb.value, np.uint8)
+    offsets = np.empty(ns.value + 1, np.int64)
+    names = np.empty(max(nn.value, 1), np.uint8)
+    check(lib.pc_fasta_read(path.encode(), seq.ctypes.data, offsets.ctypes.data, names.ctypes.data), "pc_fasta_read")
+    name_list = names[:nn.value].tobytes().decode().split("\n")[:ns.value]
+    return seq, offsets, name_list
+
+
+def write_kcount(path, keys, counts, k, append=False):
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    counts = np.ascontiguousarray(counts, dtype=np.uint32)
+    check(lib.pc_write_kcount(path.encode(), keys.ctypes.data, counts.ctypes.data, len(keys), k, int(append)),
+          "pc_write_kcount")
+
+
+def write_kmer_fasta(path, keys, k, rc_labels=False):
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    check(lib.pc_write_kmer_fasta(path.encode(), keys.ctypes.data, len(keys), k, int(rc_labels)),
+          "pc_write_kmer_fasta")
+
+
+def host_pack_word(bases):
+    b = np.frombuffer(bases if isinstance(bases, bytes) else bases.encode(), dtype=np.uint8)
+    w, m = _u64(), _u32()
+    check(lib.pc_host_pack_word(b.ctypes.data, len(b), C.byref(w), C.byref(m)), "pc_host_pack_word")
+    return w.value, m.value
+
+
+def host_canonical(kmer, k):
+    out = _u64()
+    check(lib.pc_host_canonical(int(kmer), k, C.byref(out)), "pc_host_canonical")
+    return out.value
+
+
+# ------------------------------------------------------------------------------------------------ GPU context
+class Context:
+    """One per GPU.  Thin object wrapper over the pc_* entry points; no logic of its own."""
+
+    def __init__(self, device=0):
+        h = _vp()
+        check(lib.pc_create(int(device), C.byref(h)), "pc_create")
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib.pc_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_stream(self, cuda_stream):
+        check(lib.pc_set_stream(self._h, _vp(cuda_stream or 0)), "pc_set_stream")
+
+    def sync(self):
+        check(lib.pc_sync(self._h), "pc_sync")
+
+    # K1
+    def load_sequences(self, ascii_buf, chunk_begin, chunk_end, n_bytes=None):
+        p, loc = ptr(ascii_buf)
+        nb = int(n_bytes if n_bytes is not None else (ascii_buf.numel() if _is_torch(ascii_buf) else ascii_buf.size))
+        cb = np.ascontiguousarray(chunk_begin, dtype=np.int64)
+        ce = np.ascontiguousarray(chunk_end, dtype=np.int64)
+        check(lib.pc_load_sequences(self._h, p, nb, loc, cb.ctypes.data, ce.ctypes.data, len(cb)), "pc_load_sequences")
+
+    def ascii_buffer(self, n_bytes):
+        out = _vp()
+        check(lib.pc_ascii_buffer(self._h, int(n_bytes), C.byref(out)), "pc_ascii_buffer")
+        return out.value
+
+    def load_from_ascii_buffer(self, dev_ptr, n_bytes, chunk_begin, chunk_end):
+        cb = np.ascontiguousarray(chunk_begin, dtype=np.int64)
+        ce = np.ascontiguousarray(chunk_end, dtype=np.int64)
+        check(lib.pc_load_sequences(self._h, dev_ptr, int(n_bytes), PC_DEVICE, cb.ctypes.data, ce.ctypes.data, len(cb)),
+              "pc_load_sequences")
+
+    def packed(self):
+        nw, nc = _i64(), _i64()
+        check(lib.pc_packed_info(self._h, C.byref(nw), C.byref(nc)), "pc_packed_info")
+        words = np.empty(nw.value, np.uint64); nmask = np.empty(nw.value, np.uint32)
+        w0 = np.empty(nc.value + 1, np.int64)
+        check(lib.pc_packed_get(self._h, words.ctypes.data, nmask.ctypes.data, w0.ctypes.data, PC_HOST), "pc_packed_get")
+        return words, nmask, w0
+
+    # K3
+    def count(self, k, capacity=0):
+        check(lib.pc_count(self._h, int(k), int(capacity)), "pc_count")
+
+    def count_info(self):
+        info = np.zeros(8, np.int64)
+        check(lib.pc_count_info(self._h, info.ctypes.data), "pc_count_info")
+        return dict(capacity=int(info[0]), distinct=int(info[1]), valid_windows=int(info[2]),
+                    table_bytes=int(info[3]), max_probe=int(info[4]), k=int(info[5]))
+
+    def dump_counts(self, min_count=1, max_count=0xFFFFFFFF):
+        n = _i64()
+        check(lib.pc_dump_counts(self._h, min_count, max_count, None, None, 0, PC_HOST, C.byref(n)), "pc_dump_counts")
+        keys = np.empty(n.value, np.uint64); counts = np.empty(n.value, np.uint32)
+        if n.value:
+            check(lib.pc_dump_counts(self._h, min_count, max_count, keys.ctypes.data, counts.ctypes.data, n.value,
+                                     PC_HOST, C.byref(n)), "pc_dump_counts")
+        return keys, counts
+
+    def export_by_owner(self, world, keys_t, counts_t):
+        """keys_t (int64/uint64 view) and counts_t (int32) are torch CUDA tensors with >= distinct elements."""
+        offsets = np.zeros(world + 1, np.int64)
+        check(lib.pc_export_by_owner(self._h, int(world), keys_t.data_ptr(), counts_t.data_ptr(), keys_t.numel(),
+                                     offsets.ctypes.data), "pc_export_by_owner")
+        return offsets
+
+    def merge_counts(self, keys_t, counts_t, n, k, capacity=0, fresh=True):
+        check(lib.pc_merge_counts(self._h, keys_t.data_ptr() if n else None, counts_t.data_ptr() if n else None,
+                                  int(n), int(k), int(capacity), int(bool(fresh))), "pc_merge_counts")
+
+    # K4
+    def select(self, low, high=2000000, use_high=False, sampling=1):
+        n = _i64()
+        check(lib.pc_select(self._h, int(low), int(high), int(bool(use_high)), int(sampling), C.byref(n)), "pc_select")
+        return n.value
+
+    def selected(self, n):
+        keys = np.empty(n, np.uint64)
+        if n:
+            check(lib.pc_selected_get(self._h, keys.ctypes.data, PC_HOST), "pc_selected_get")
+        return keys
+
+    def selected_into(self, tensor):
+        p, loc = ptr(tensor)
+        check(lib.pc_selected_get(self._h, p, loc), "pc_selected_get")
+
+    def set_selected(self, keys, k, n=None):
+        p, loc = ptr(keys)
+        n = int(n if n is not None else (keys.numel() if _is_torch(keys) else len(keys)))
+        out = _i64()
+        check(lib.pc_set_selected(self._h, p if n else None, n, int(k), loc, C.byref(out)), "pc_set_selected")
+        return out.value
+
+    # K5 + K6
+    def build_matrix(self, chunk_row, n_rows):
+        cr = np.ascontiguousarray(chunk_row, dtype=np.int32)
+        nnz = _i64()
+        check(lib.pc_build_matrix(self._h, cr.ctypes.data, int(n_rows), C.byref(nnz)), "pc_build_matrix")
+        return nnz.value
+
+    def csr(self, n_rows, nnz):
+        indptr = np.empty(n_rows + 1, np.int64); indices = np.empty(nnz, np.int32); data = np.empty(nnz, np.float32)
+        check(lib.pc_csr_get(self._h, indptr.ctypes.data, indices.ctypes.data, data.ctypes.data, PC_HOST), "pc_csr_get")
+        return indptr, indices, data
+
+    def csr_into(self, indptr=None, indices=None, data=None):
+        locs = {ptr(x)[1] for x in (indptr, indices, data) if x is not None}
+        if len(locs) > 1:
+            raise ValueError("all CSR outputs must live in the same place")
+        check(lib.pc_csr_get(self._h, ptr(indptr)[0], ptr(indices)[0], ptr(data)[0], locs.pop() if locs else PC_HOST),
+              "pc_csr_get")
+
+    def df(self, n_cols):
+        out = np.empty(n_cols, np.int32)
+        if n_cols:
+            check(lib.pc_df_get(self._h, out.ctypes.data, PC_HOST), "pc_df_get")
+        return out
+
+    def df_into(self, tensor):
+        p, loc = ptr(tensor)
+        check(lib.pc_df_get(self._h, p, loc), "pc_df_get")
+
+    # K7
+    def tfidf(self, n_rows_global=0, df_global=None):
+        p, loc = ptr(df_global)
+        check(lib.pc_tfidf(self._h, int(n_rows_global), p, loc), "pc_tfidf")
+
+    def tfidf_values(self, nnz):
+        out = np.empty(nnz, np.float32)
+        if nnz:
+            check(lib.pc_tfidf_get(self._h, out.ctypes.data, PC_HOST), "pc_tfidf_get")
+        return out
+
+    def tfidf_into(self, tensor):
+        p, loc = ptr(tensor)
+        check(lib.pc_tfidf_get(self._h, p, loc), "pc_tfidf_get")
+
+    # measurement
+    def timings(self):
+        ms = np.zeros(PC_N_STAGES, np.float32)
+        check(lib.pc_timings(self._h, ms.ctypes.data), "pc_timings")
+        return {name: float(ms[i]) for i, name in enumerate(STAGE_NAMES)}
+
+    def launch_count(self):
+        n = _i64()
+        check(lib.pc_launch_count(self._h, C.byref(n)), "pc_launch_count")
+        return n.value
+
+    def reset_counters(self):
+        check(lib.pc_reset_counters(self._h), "pc_reset_counters")

@@ -1,0 +1,700 @@
+// C ABI of the B200 hot path (include/polycracker_b200.h): host orchestration of the kernels in kernels.cuh.
+// No CPU fallback lives here: every compute entry point needs a CUDA device and says so when there is none.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/polycracker_b200.h"
+#include "kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (expr);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(PC_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_)); \
+    } while (0)
+
+enum Stage { ST_H2D = 0, ST_PACK, ST_TABLE_INIT, ST_COUNT, ST_SELECT, ST_SORT, ST_REPTABLE, ST_PROBE,
+             ST_ROWSORT, ST_EMIT, ST_TFIDF, ST_D2H, ST_EXPORT, ST_MERGE, ST_N };
+static_assert(ST_N <= PC_N_STAGES, "stage table too small");
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr; size_t n = 0;
+    int alloc(size_t count) {
+        if (count <= n && p) return PC_OK;
+        release();
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e != cudaSuccess) { p = nullptr; n = 0; return fail(PC_ENOMEM, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e)); }
+        n = count;
+        return PC_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+}  // namespace
+
+struct pc_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev[ST_N][2];
+    bool ev_used[ST_N];
+    int64_t launches = 0;
+
+    // sequences
+    DevBuf<uint8_t> ascii; int64_t ascii_padded = 0;
+    std::vector<int64_t> h_word0, h_begin, h_len;
+    DevBuf<int64_t> d_word0, d_begin, d_len;
+    int64_t n_chunks = 0, n_words = 0;           // n_words = data words (a guard word follows)
+    DevBuf<uint64_t> words; DevBuf<uint32_t> nmask;
+    bool loaded = false;
+
+    // count table
+    int k = 0;
+    DevBuf<pc::CountSlot> table; uint64_t capacity = 0;
+    DevBuf<pc::CountStats> d_stats; pc::CountStats h_stats{};
+    bool counted = false;
+
+    // selection
+    DevBuf<uint64_t> sel_a, sel_b; uint64_t* sel = nullptr; int64_t n_sel = 0;
+    DevBuf<unsigned int> rs_hist;
+    DevBuf<unsigned long long> d_counter;
+    DevBuf<pc::RepSlot> rtable; uint64_t rcap = 0;
+    bool selected = false;
+
+    // matrix
+    DevBuf<int32_t> d_chunk_row; DevBuf<int64_t> d_row_base; DevBuf<unsigned int> d_row_cursor;
+    DevBuf<int32_t> hits_a, hits_b; DevBuf<int64_t> d_row_nnz, d_indptr;
+    DevBuf<int32_t> d_indices; DevBuf<float> d_data, d_idf, d_tfidf; DevBuf<int> d_df, d_df_global;
+    int64_t n_rows = 0, nnz = 0;
+    bool built = false, tfidf_done = false;
+};
+
+namespace {
+
+struct StageTimer {
+    pc_ctx* c; int st;
+    StageTimer(pc_ctx* c_, int st_) : c(c_), st(st_) { cudaEventRecord(c->ev[st][0], c->stream); }
+    ~StageTimer() { cudaEventRecord(c->ev[st][1], c->stream); c->ev_used[st] = true; }
+};
+
+#define LAUNCH(ctx, kernel, grid, block, ...)                                                      \
+    do {                                                                                           \
+        kernel<<<(grid), (block), 0, (ctx)->stream>>>(__VA_ARGS__);                                \
+        (ctx)->launches++;                                                                         \
+        CU(cudaGetLastError());                                                                    \
+    } while (0)
+
+inline unsigned int blocks_for(int64_t n, int per) { return (unsigned int)std::max<int64_t>(1, (n + per - 1) / per); }
+
+int use_device(pc_ctx* c) {
+    if (!c) return fail(PC_EINVAL, "null context");
+    CU(cudaSetDevice(c->device));
+    return PC_OK;
+}
+
+int copy_out(pc_ctx* c, void* dst, const void* src_dev, size_t bytes, int loc) {
+    if (bytes == 0) return PC_OK;
+    CU(cudaMemcpyAsync(dst, src_dev, bytes, loc == PC_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+    if (loc == PC_HOST) CU(cudaStreamSynchronize(c->stream));
+    return PC_OK;
+}
+
+// stable LSD radix sort of n uint64 keys over `bits` low bits; result pointer returned in *out (a or b)
+constexpr int RS_WARPS = 8;
+int radix_sort_u64(pc_ctx* c, uint64_t* a, uint64_t* b, int64_t n, int bits, uint64_t** out) {
+    *out = a;
+    if (n <= 1) return PC_OK;
+    int n_ctas = (int)std::min<int64_t>(296, std::max<int64_t>(1, n / (RS_WARPS * 32 * 16)));
+    int NW = n_ctas * RS_WARPS;
+    int64_t ipw = (((n + NW - 1) / NW) + 31) & ~(int64_t)31;
+    int rc = c->rs_hist.alloc((size_t)256 * NW);
+    if (rc) return rc;
+    uint64_t* src = a; uint64_t* dst = b;
+    for (int shift = 0; shift < bits; shift += 8) {
+        LAUNCH(c, (pc::k_rs_hist<uint64_t, RS_WARPS>), n_ctas, RS_WARPS * 32, src, n, ipw, shift, c->rs_hist.p, NW);
+        LAUNCH(c, pc::k_rs_scan, 1, 1024, c->rs_hist.p, (int64_t)256 * NW);
+        LAUNCH(c, (pc::k_rs_scatter<uint64_t, RS_WARPS, false>), n_ctas, RS_WARPS * 32, src, dst,
+               (const uint32_t*)nullptr, (uint32_t*)nullptr, n, ipw, shift, c->rs_hist.p, NW);
+        std::swap(src, dst);
+    }
+    *out = src;
+    return PC_OK;
+}
+
+int build_rep_table(pc_ctx* c) {
+    StageTimer t(c, ST_REPTABLE);
+    c->rcap = std::max<uint64_t>(64, (uint64_t)c->n_sel * 2);
+    int rc = c->rtable.alloc(c->rcap);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(c->rtable.p, 0, c->rcap * sizeof(pc::RepSlot), c->stream));
+    if (c->n_sel > 0)
+        LAUNCH(c, pc::k_rep_build, blocks_for(c->n_sel, 256), 256, c->sel, c->n_sel, c->rtable.p, c->rcap);
+    return PC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pc_version(void) { return 100; }
+const char* pc_last_error(void) { return g_err.c_str(); }
+
+int pc_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int pc_create(int device, pc_ctx** out) {
+    if (!out) return fail(PC_EINVAL, "out is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(PC_ECUDA, "no CUDA device: polycracker_b200 has no CPU fallback (%s)", cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return fail(PC_EINVAL, "device %d out of range (have %d)", device, n);
+    CU(cudaSetDevice(device));
+    pc_ctx* c = new pc_ctx();
+    c->device = device;
+    CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    for (int i = 0; i < ST_N; ++i) {
+        CU(cudaEventCreate(&c->ev[i][0])); CU(cudaEventCreate(&c->ev[i][1])); c->ev_used[i] = false;
+    }
+    int rc = c->d_stats.alloc(1); if (rc) { delete c; return rc; }
+    rc = c->d_counter.alloc(64); if (rc) { delete c; return rc; }
+    *out = c;
+    return PC_OK;
+}
+
+int pc_destroy(pc_ctx* c) {
+    if (!c) return PC_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->ascii.release(); c->d_word0.release(); c->d_begin.release(); c->d_len.release();
+    c->words.release(); c->nmask.release(); c->table.release(); c->d_stats.release();
+    c->sel_a.release(); c->sel_b.release(); c->rs_hist.release(); c->d_counter.release(); c->rtable.release();
+    c->d_chunk_row.release(); c->d_row_base.release(); c->d_row_cursor.release(); c->hits_a.release();
+    c->hits_b.release(); c->d_row_nnz.release(); c->d_indptr.release(); c->d_indices.release();
+    c->d_data.release(); c->d_idf.release(); c->d_tfidf.release(); c->d_df.release(); c->d_df_global.release();
+    for (int i = 0; i < ST_N; ++i) { cudaEventDestroy(c->ev[i][0]); cudaEventDestroy(c->ev[i][1]); }
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+    return PC_OK;
+}
+
+int pc_set_stream(pc_ctx* c, void* s) {
+    if (!c) return fail(PC_EINVAL, "null context");
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return PC_OK;
+}
+
+int pc_sync(pc_ctx* c) {
+    int rc = use_device(c); if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    return PC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- a1
+int64_t pc_chunk_count(const int64_t* seq_len, int64_t n_seqs, int64_t C) {
+    if (!seq_len || C <= 0) return -1;
+    int64_t n = 0;
+    for (int64_t s = 0; s < n_seqs; ++s) {
+        int64_t L = seq_len[s];
+        if (L <= 0) continue;
+        n += (L + C - 1) / C;                 // len(arange(0, L, C)) chunks: pairs + tail
+    }
+    return n;
+}
+
+int pc_chunk_table(const int64_t* seq_len, int64_t n_seqs, int64_t C, int64_t* chunk_seq, int64_t* chunk_start,
+                   int64_t* chunk_end) {
+    if (!seq_len || !chunk_seq || !chunk_start || !chunk_end || C <= 0) return fail(PC_EINVAL, "bad chunk_table arguments");
+    int64_t n = 0;
+    for (int64_t s = 0; s < n_seqs; ++s) {
+        int64_t L = seq_len[s];
+        if (L <= 0) continue;
+        for (int64_t p = 0; p < L; p += C) {
+            chunk_seq[n] = s; chunk_start[n] = p; chunk_end[n] = std::min(L, p + C); ++n;
+        }
+    }
+    return PC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- K1
+int pc_ascii_buffer(pc_ctx* c, int64_t n_bytes, uint8_t** dev_ptr) {
+    int rc = use_device(c); if (rc) return rc;
+    if (n_bytes < 0 || !dev_ptr) return fail(PC_EINVAL, "bad ascii buffer request");
+    int64_t padded = ((n_bytes + 255) & ~(int64_t)255) + 256;
+    rc = c->ascii.alloc((size_t)padded); if (rc) return rc;
+    c->ascii_padded = padded;
+    *dev_ptr = c->ascii.p;
+    return PC_OK;
+}
+
+int pc_load_sequences(pc_ctx* c, const uint8_t* ascii, int64_t n_bytes, int loc, const int64_t* chunk_begin,
+                      const int64_t* chunk_end, int64_t n_chunks) {
+    int rc = use_device(c); if (rc) return rc;
+    if (n_bytes < 0 || n_chunks < 0 || (n_bytes > 0 && !ascii) || (n_chunks > 0 && (!chunk_begin || !chunk_end)))
+        return fail(PC_EINVAL, "bad load_sequences arguments");
+    c->loaded = c->counted = c->selected = c->built = c->tfidf_done = false;
+    c->h_word0.assign(n_chunks + 1, 0); c->h_begin.assign(std::max<int64_t>(n_chunks, 1), 0); c->h_len.assign(std::max<int64_t>(n_chunks, 1), 0);
+    int64_t prev_end = 0, wsum = 0;
+    for (int64_t i = 0; i < n_chunks; ++i) {
+        int64_t b = chunk_begin[i], e = chunk_end[i];
+        if (b < prev_end || e < b || e > n_bytes) return fail(PC_EINVAL, "chunk %lld [%lld,%lld) is out of order or out of range", (long long)i, (long long)b, (long long)e);
+        prev_end = e;
+        c->h_begin[i] = b; c->h_len[i] = e - b; c->h_word0[i] = wsum;
+        wsum += (e - b) / 32 + 1;             // >= 1 padding base after every chunk
+    }
+    c->h_word0[n_chunks] = wsum;
+    c->n_chunks = n_chunks; c->n_words = wsum;
+
+    const uint8_t* src_dev = nullptr; int64_t src_padded = 0;
+    {
+        StageTimer t(c, ST_H2D);
+        if (loc == PC_HOST) {
+            uint8_t* dptr = nullptr;
+            rc = pc_ascii_buffer(c, n_bytes, &dptr); if (rc) return rc;
+            if (n_bytes) CU(cudaMemcpyAsync(dptr, ascii, (size_t)n_bytes, cudaMemcpyHostToDevice, c->stream));
+            src_dev = dptr; src_padded = c->ascii_padded;
+        } else if (ascii == c->ascii.p && c->ascii.p) {
+            src_dev = c->ascii.p; src_padded = c->ascii_padded;
+        } else {
+            src_dev = ascii; src_padded = n_bytes;                // caller-owned: no slack assumed
+        }
+        rc = c->d_word0.alloc(n_chunks + 1); if (rc) return rc;
+        rc = c->d_begin.alloc(n_chunks); if (rc) return rc;
+        rc = c->d_len.alloc(n_chunks); if (rc) return rc;
+        CU(cudaMemcpyAsync(c->d_word0.p, c->h_word0.data(), (n_chunks + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        if (n_chunks) {
+            CU(cudaMemcpyAsync(c->d_begin.p, c->h_begin.data(), n_chunks * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(c->d_len.p, c->h_len.data(), n_chunks * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        }
+    }
+    rc = c->words.alloc(wsum + 1); if (rc) return rc;
+    rc = c->nmask.alloc(wsum + 1); if (rc) return rc;
+    {
+        StageTimer t(c, ST_PACK);
+        LAUNCH(c, pc::k_pack, blocks_for(wsum + 1, 256), 256, src_dev, src_padded, c->d_word0.p, c->d_begin.p,
+               c->d_len.p, n_chunks, wsum + 1, c->words.p, c->nmask.p);
+    }
+    // the h_* vectors are re-used by later host code; the async copies above read them now
+    CU(cudaStreamSynchronize(c->stream));
+    c->loaded = true;
+    return PC_OK;
+}
+
+int pc_packed_info(pc_ctx* c, int64_t* n_words, int64_t* n_chunks) {
+    if (!c || !c->loaded) return fail(PC_ESTATE, "no sequences loaded");
+    if (n_words) *n_words = c->n_words;
+    if (n_chunks) *n_chunks = c->n_chunks;
+    return PC_OK;
+}
+
+int pc_packed_get(pc_ctx* c, uint64_t* words, uint32_t* nmask, int64_t* chunk_word0, int loc) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!c->loaded) return fail(PC_ESTATE, "no sequences loaded");
+    if (words) { rc = copy_out(c, words, c->words.p, c->n_words * sizeof(uint64_t), loc); if (rc) return rc; }
+    if (nmask) { rc = copy_out(c, nmask, c->nmask.p, c->n_words * sizeof(uint32_t), loc); if (rc) return rc; }
+    if (chunk_word0) { rc = copy_out(c, chunk_word0, c->d_word0.p, (c->n_chunks + 1) * sizeof(int64_t), loc); if (rc) return rc; }
+    return PC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- K3
+static int table_prepare(pc_ctx* c, int k, int64_t capacity) {
+    if (k < 1 || k > 32) return fail(PC_EINVAL, "k = %d unsupported: this path handles 1 <= k <= 32 (uint64 k-mers)", k);
+    if (capacity < 64) capacity = 64;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    size_t need = (size_t)capacity * sizeof(pc::CountSlot);
+    if (need > free_b + c->table.n * sizeof(pc::CountSlot))
+        return fail(PC_ENOMEM, "count table of %lld slots (%.1f GB) does not fit in free HBM (%.1f GB): shard the genome over more GPUs",
+                    (long long)capacity, need / 1e9, free_b / 1e9);
+    int rc = c->table.alloc((size_t)capacity); if (rc) return rc;
+    c->capacity = (uint64_t)capacity; c->k = k;
+    StageTimer t(c, ST_TABLE_INIT);
+    CU(cudaMemsetAsync(c->table.p, 0, (size_t)capacity * sizeof(pc::CountSlot), c->stream));
+    CU(cudaMemsetAsync(c->d_stats.p, 0, sizeof(pc::CountStats), c->stream));
+    return PC_OK;
+}
+
+static int fetch_stats(pc_ctx* c) {
+    CU(cudaMemcpyAsync(&c->h_stats, c->d_stats.p, sizeof(pc::CountStats), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->h_stats.overflow)
+        return fail(PC_ENOMEM, "count table overflow: %llu insertions hit the probe limit (capacity %llu)",
+                    c->h_stats.overflow, (unsigned long long)c->capacity);
+    return PC_OK;
+}
+
+int pc_count(pc_ctx* c, int k, int64_t capacity) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!c->loaded) return fail(PC_ESTATE, "pc_count before pc_load_sequences");
+    if (k < 1 || k > 32) return fail(PC_EINVAL, "k = %d unsupported: this path handles 1 <= k <= 32 (uint64 k-mers)", k);
+    c->counted = c->selected = c->built = c->tfidf_done = false;
+    if (capacity <= 0) {
+        int64_t windows = 0;
+        for (int64_t i = 0; i < c->n_chunks; ++i) windows += std::max<int64_t>(0, c->h_len[i] - k + 1);
+        // distinct canonical k-mers <= windows and <= 4^k (palindrome-aware bound not needed: it is an upper bound)
+        double space = k >= 31 ? 9.3e18 : (double)(1ull << (2 * k));
+        double bound = std::min((double)windows, space);
+        capacity = (int64_t)(bound / 0.6) + 1024;
+    }
+    rc = table_prepare(c, k, capacity); if (rc) return rc;
+    {
+        StageTimer t(c, ST_COUNT);
+        if (c->n_words > 0)
+            LAUNCH(c, (pc::k_count<8>), blocks_for(c->n_words, 256), 256, c->words.p, c->nmask.p, c->n_words, k,
+                   c->table.p, c->capacity, c->d_stats.p);
+    }
+    rc = fetch_stats(c); if (rc) return rc;
+    c->counted = true;
+    return PC_OK;
+}
+
+int pc_count_info(pc_ctx* c, int64_t info[8]) {
+    if (!c || !c->counted) return fail(PC_ESTATE, "no count table");
+    memset(info, 0, 8 * sizeof(int64_t));
+    info[0] = (int64_t)c->capacity; info[1] = (int64_t)c->h_stats.distinct; info[2] = (int64_t)c->h_stats.valid_windows;
+    info[3] = (int64_t)(c->capacity * sizeof(pc::CountSlot)); info[4] = (int64_t)c->h_stats.max_probe; info[5] = c->k;
+    return PC_OK;
+}
+
+// runs k_select into (keys_dev, counts_dev); returns the number of survivors
+static int select_into(pc_ctx* c, uint32_t low, uint32_t high, uint64_t* keys_dev, uint32_t* counts_dev, int64_t cap,
+                       int64_t* n_out) {
+    CU(cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned long long), c->stream));
+    unsigned int grid = (unsigned int)std::min<uint64_t>((c->capacity + 255) / 256, 148ull * 16);
+    LAUNCH(c, pc::k_select, grid, 256, c->table.p, c->capacity, low, high, keys_dev, counts_dev,
+           (unsigned long long)cap, c->d_counter.p);
+    unsigned long long n = 0;
+    CU(cudaMemcpyAsync(&n, c->d_counter.p, sizeof n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *n_out = (int64_t)n;
+    return PC_OK;
+}
+
+int pc_dump_counts(pc_ctx* c, uint32_t min_count, uint32_t max_count, uint64_t* keys, uint32_t* counts, int64_t cap,
+                   int loc, int64_t* n) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!c->counted) return fail(PC_ESTATE, "pc_dump_counts before pc_count");
+    if (!n) return fail(PC_EINVAL, "n is null");
+    if (!keys) return select_into(c, min_count, max_count, nullptr, nullptr, 0, n);
+    if (loc == PC_DEVICE) {
+        rc = select_into(c, min_count, max_count, keys, counts, cap, n); if (rc) return rc;
+        if (*n > cap) return fail(PC_EINVAL, "dump buffer too small: need %lld", (long long)*n);
+        return PC_OK;
+    }
+    DevBuf<uint64_t> dk; DevBuf<uint32_t> dc;
+    rc = dk.alloc(cap); if (rc) return rc;
+    rc = dc.alloc(cap); if (rc) { dk.release(); return rc; }
+    rc = select_into(c, min_count, max_count, dk.p, dc.p, cap, n);
+    if (!rc && *n > cap) rc = fail(PC_EINVAL, "dump buffer too small: need %lld", (long long)*n);
+    if (!rc) rc = copy_out(c, keys, dk.p, *n * sizeof(uint64_t), PC_HOST);
+    if (!rc && counts) rc = copy_out(c, counts, dc.p, *n * sizeof(uint32_t), PC_HOST);
+    dk.release(); dc.release();
+    return rc;
+}
+
+int pc_export_by_owner(pc_ctx* c, int world, uint64_t* keys_dev, uint32_t* counts_dev, int64_t cap, int64_t* offsets) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!c->counted) return fail(PC_ESTATE, "pc_export_by_owner before pc_count");
+    if (world < 1 || world > 64 || !keys_dev || !counts_dev || !offsets) return fail(PC_EINVAL, "bad export arguments");
+    if (cap < (int64_t)c->h_stats.distinct) return fail(PC_EINVAL, "export buffer too small: need %llu", c->h_stats.distinct);
+    StageTimer t(c, ST_EXPORT);
+    CU(cudaMemsetAsync(c->d_counter.p, 0, 64 * sizeof(unsigned long long), c->stream));
+    unsigned int grid = (unsigned int)std::min<uint64_t>((c->capacity + 255) / 256, 148ull * 16);
+    LAUNCH(c, pc::k_owner_hist, grid, 256, c->table.p, c->capacity, (unsigned int)world, c->d_counter.p);
+    unsigned long long hist[64];
+    CU(cudaMemcpyAsync(hist, c->d_counter.p, world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    unsigned long long start[64]; offsets[0] = 0;
+    for (int r = 0; r < world; ++r) { start[r] = (unsigned long long)offsets[r]; offsets[r + 1] = offsets[r] + (int64_t)hist[r]; }
+    CU(cudaMemcpyAsync(c->d_counter.p, start, world * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, pc::k_owner_scatter, grid, 256, c->table.p, c->capacity, (unsigned int)world, c->d_counter.p, keys_dev, counts_dev);
+    CU(cudaStreamSynchronize(c->stream));
+    return PC_OK;
+}
+
+int pc_merge_counts(pc_ctx* c, const uint64_t* keys_dev, const uint32_t* counts_dev, int64_t n, int k, int64_t capacity,
+                    int fresh) {
+    int rc = use_device(c); if (rc) return rc;
+    if (n < 0 || (n > 0 && (!keys_dev || !counts_dev))) return fail(PC_EINVAL, "bad merge arguments");
+    if (fresh) {
+        if (capacity <= 0) capacity = (int64_t)(n / 0.6) + 1024;
+        rc = table_prepare(c, k, capacity); if (rc) return rc;
+        c->selected = c->built = c->tfidf_done = false;
+    } else if (!c->counted || c->k != k) {
+        return fail(PC_ESTATE, "pc_merge_counts(fresh=0) needs an existing table with the same k");
+    }
+    {
+        StageTimer t(c, ST_MERGE);
+        if (n > 0) LAUNCH(c, pc::k_merge, blocks_for(n, 256), 256, keys_dev, counts_dev, n, c->table.p, c->capacity, c->d_stats.p);
+    }
+    rc = fetch_stats(c); if (rc) return rc;
+    c->counted = true;
+    return PC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- K4
+int pc_select(pc_ctx* c, uint32_t low, uint32_t high, int use_high, int64_t sampling, int64_t* n_selected) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!c->counted) return fail(PC_ESTATE, "pc_select before pc_count");
+    if (sampling < 1) sampling = 1;                            // polycracker.py:220-221
+    if (!use_high) high = 0xFFFFFFFFu;
+    if (low == 0) low = 1;                                     // absent k-mers are never selected
+    c->selected = c->built = c->tfidf_done = false;
+    int64_t cap = std::min<int64_t>((int64_t)c->h_stats.distinct, (int64_t)1 << 26);
+    cap = std::max<int64_t>(cap, 1024);
+    int64_t n = 0;
+    {
+        StageTimer t(c, ST_SELECT);
+        rc = c->sel_a.alloc(cap); if (rc) return rc;
+        rc = select_into(c, low, high, c->sel_a.p, nullptr, cap, &n); if (rc) return rc;
+        if (n > cap) {                                         // rare: more survivors than the first guess
+            cap = n;
+            rc = c->sel_a.alloc(cap); if (rc) return rc;
+            rc = select_into(c, low, high, c->sel_a.p, nullptr, cap, &n); if (rc) return rc;
+        }
+    }
+    {
+        StageTimer t(c, ST_SORT);
+        rc = c->sel_b.alloc(std::max<int64_t>(n, 1)); if (rc) return rc;
+        uint64_t* sorted = nullptr;
+        rc = radix_sort_u64(c, c->sel_a.p, c->sel_b.p, n, 2 * c->k, &sorted); if (rc) return rc;
+        if (sampling > 1 && n > 0) {
+            int64_t n_out = (n + sampling - 1) / sampling;     // survivors 0, s, 2s, ... (count % s == 0)
+            uint64_t* other = (sorted == c->sel_a.p) ? c->sel_b.p : c->sel_a.p;
+            LAUNCH(c, pc::k_stride_gather, blocks_for(n_out, 256), 256, sorted, n_out, sampling, other);
+            sorted = other; n = n_out;
+        }
+        c->sel = sorted; c->n_sel = n;
+    }
+    rc = build_rep_table(c); if (rc) return rc;
+    c->selected = true;
+    if (n_selected) *n_selected = n;
+    return PC_OK;
+}
+
+int pc_selected_get(pc_ctx* c, uint64_t* keys, int loc) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!c->selected) return fail(PC_ESTATE, "no repeat set selected");
+    return copy_out(c, keys, c->sel, c->n_sel * sizeof(uint64_t), loc);
+}
+
+int pc_set_selected(pc_ctx* c, const uint64_t* keys, int64_t n, int k, int loc, int64_t* n_unique) {
+    int rc = use_device(c); if (rc) return rc;
+    if (k < 1 || k > 32) return fail(PC_EINVAL, "k = %d unsupported: this path handles 1 <= k <= 32 (uint64 k-mers)", k);
+    if (n < 0 || (n > 0 && !keys)) return fail(PC_EINVAL, "bad set_selected arguments");
+    if (c->counted && c->k != k) return fail(PC_EINVAL, "k = %d differs from the count table's k = %d", k, c->k);
+    c->k = k;
+    c->selected = c->built = c->tfidf_done = false;
+    StageTimer t(c, ST_SORT);
+    rc = c->sel_a.alloc(std::max<int64_t>(n, 1)); if (rc) return rc;
+    rc = c->sel_b.alloc(std::max<int64_t>(n, 1)); if (rc) return rc;
+    if (n) CU(cudaMemcpyAsync(c->sel_a.p, keys, n * sizeof(uint64_t), loc == PC_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    if (n) LAUNCH(c, pc::k_canonicalize, blocks_for(n, 256), 256, c->sel_a.p, n, k);
+    uint64_t* sorted = nullptr;
+    rc = radix_sort_u64(c, c->sel_a.p, c->sel_b.p, n, 2 * k, &sorted); if (rc) return rc;
+    uint64_t* other = (sorted == c->sel_a.p) ? c->sel_b.p : c->sel_a.p;
+    unsigned long long nu = 0;
+    if (n > 0) {
+        LAUNCH(c, pc::k_unique_sorted_single, 1, 1024, sorted, n, other, c->d_counter.p);
+        CU(cudaMemcpyAsync(&nu, c->d_counter.p, sizeof nu, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    c->sel = other; c->n_sel = (int64_t)nu;
+    rc = build_rep_table(c); if (rc) return rc;
+    c->selected = true;
+    if (n_unique) *n_unique = c->n_sel;
+    return PC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- K5 + K6
+int pc_build_matrix(pc_ctx* c, const int32_t* chunk_row, int64_t n_rows, int64_t* nnz) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!c->loaded || !c->selected) return fail(PC_ESTATE, "pc_build_matrix needs loaded sequences and a repeat set");
+    if (n_rows < 0 || (c->n_chunks > 0 && !chunk_row)) return fail(PC_EINVAL, "bad build_matrix arguments");
+    if (n_rows > 0x7FFFFFFF) return fail(PC_EINVAL, "too many rows");
+    c->built = c->tfidf_done = false;
+    const int k = c->k;
+    std::vector<int64_t> row_base(n_rows + 1, 0), row_windows(std::max<int64_t>(n_rows, 1), -1);
+    for (int64_t i = 0; i < c->n_chunks; ++i) {
+        int32_t r = chunk_row[i];
+        if (r < 0) continue;
+        if (r >= n_rows) return fail(PC_EINVAL, "chunk_row[%lld] = %d >= n_rows", (long long)i, r);
+        if (row_windows[r] >= 0) return fail(PC_EINVAL, "row %d is assigned to two chunks", r);
+        row_windows[r] = std::max<int64_t>(0, c->h_len[i] - k + 1);
+    }
+    for (int64_t r = 0; r < n_rows; ++r) {
+        int64_t wnd = std::max<int64_t>(0, row_windows[r]);
+        if (wnd > 0xFFFFFFFFll) return fail(PC_EINVAL, "chunk too long for 32-bit hit cursors");
+        row_base[r + 1] = row_base[r] + wnd;
+    }
+    int64_t total_windows = row_base[n_rows];
+    rc = c->d_chunk_row.alloc(c->n_chunks); if (rc) return rc;
+    rc = c->d_row_base.alloc(n_rows + 1); if (rc) return rc;
+    rc = c->d_row_cursor.alloc(n_rows); if (rc) return rc;
+    rc = c->d_row_nnz.alloc(n_rows); if (rc) return rc;
+    rc = c->d_indptr.alloc(n_rows + 1); if (rc) return rc;
+    rc = c->hits_a.alloc(total_windows); if (rc) return rc;
+    rc = c->hits_b.alloc(total_windows); if (rc) return rc;
+    rc = c->d_df.alloc(std::max<int64_t>(c->n_sel, 1)); if (rc) return rc;
+    if (c->n_chunks) CU(cudaMemcpyAsync(c->d_chunk_row.p, chunk_row, c->n_chunks * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_row_base.p, row_base.data(), (n_rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(c->d_row_cursor.p, 0, std::max<int64_t>(n_rows, 1) * sizeof(unsigned int), c->stream));
+    CU(cudaMemsetAsync(c->d_df.p, 0, std::max<int64_t>(c->n_sel, 1) * sizeof(int), c->stream));
+    CU(cudaMemsetAsync(c->d_indptr.p, 0, (n_rows + 1) * sizeof(int64_t), c->stream));
+    {
+        StageTimer t(c, ST_PROBE);
+        if (c->n_words > 0 && n_rows > 0 && c->n_sel > 0)
+            LAUNCH(c, (pc::k_probe<8>), blocks_for(c->n_words, 256), 256, c->words.p, c->nmask.p, c->n_words, k,
+                   c->d_word0.p, c->n_chunks, c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, c->hits_a.p,
+                   c->d_row_cursor.p);
+    }
+    int bits = 1; while (((int64_t)1 << bits) < c->n_sel) ++bits;
+    int n_passes = std::max(1, (bits + 7) / 8);
+    int32_t* sorted = (n_passes & 1) ? c->hits_b.p : c->hits_a.p;
+    c->nnz = 0;
+    if (n_rows > 0) {
+        {
+            StageTimer t(c, ST_ROWSORT);
+            LAUNCH(c, (pc::k_row_sort<16>), (unsigned int)n_rows, 512, c->hits_a.p, c->hits_b.p, c->d_row_base.p,
+                   c->d_row_cursor.p, n_passes, c->d_row_nnz.p);
+            LAUNCH(c, pc::k_indptr, 1, 1024, c->d_row_nnz.p, n_rows, c->d_indptr.p);
+        }
+        int64_t total = 0;
+        CU(cudaMemcpyAsync(&total, c->d_indptr.p + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->nnz = total;
+        rc = c->d_indices.alloc(std::max<int64_t>(total, 1)); if (rc) return rc;
+        rc = c->d_data.alloc(std::max<int64_t>(total, 1)); if (rc) return rc;
+        StageTimer t(c, ST_EMIT);
+        LAUNCH(c, (pc::k_row_emit<256>), (unsigned int)n_rows, 256, sorted, c->d_row_base.p, c->d_row_cursor.p,
+               c->d_indptr.p, c->d_indices.p, c->d_data.p, c->d_df.p);
+    }
+    CU(cudaStreamSynchronize(c->stream));                      // row_base (host vector) no longer needed
+    c->n_rows = n_rows;
+    c->built = true;
+    if (nnz) *nnz = c->nnz;
+    return PC_OK;
+}
+
+int pc_csr_get(pc_ctx* c, int64_t* indptr, int32_t* indices, float* data, int loc) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!c->built) return fail(PC_ESTATE, "no matrix built");
+    StageTimer t(c, ST_D2H);
+    if (indptr) { rc = copy_out(c, indptr, c->d_indptr.p, (c->n_rows + 1) * sizeof(int64_t), loc); if (rc) return rc; }
+    if (indices) { rc = copy_out(c, indices, c->d_indices.p, c->nnz * sizeof(int32_t), loc); if (rc) return rc; }
+    if (data) { rc = copy_out(c, data, c->d_data.p, c->nnz * sizeof(float), loc); if (rc) return rc; }
+    return PC_OK;
+}
+
+int pc_df_get(pc_ctx* c, int32_t* df, int loc) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!c->built) return fail(PC_ESTATE, "no matrix built");
+    return copy_out(c, df, c->d_df.p, c->n_sel * sizeof(int32_t), loc);
+}
+
+// ---------------------------------------------------------------------------------------------- K7
+int pc_tfidf(pc_ctx* c, int64_t n_rows_global, const int32_t* df_global, int df_loc) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!c->built) return fail(PC_ESTATE, "pc_tfidf before pc_build_matrix");
+    if (n_rows_global <= 0) n_rows_global = c->n_rows;
+    c->tfidf_done = false;
+    rc = c->d_idf.alloc(std::max<int64_t>(c->n_sel, 1)); if (rc) return rc;
+    rc = c->d_tfidf.alloc(std::max<int64_t>(c->nnz, 1)); if (rc) return rc;
+    const int* df = c->d_df.p;
+    if (df_global) {
+        if (df_loc == PC_DEVICE) df = df_global;
+        else {
+            rc = c->d_df_global.alloc(std::max<int64_t>(c->n_sel, 1)); if (rc) return rc;
+            if (c->n_sel) CU(cudaMemcpyAsync(c->d_df_global.p, df_global, c->n_sel * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+            df = c->d_df_global.p;
+        }
+    }
+    {
+        StageTimer t(c, ST_TFIDF);
+        if (c->n_sel > 0) LAUNCH(c, pc::k_idf, blocks_for(c->n_sel, 256), 256, df, c->n_sel, (float)(n_rows_global + 1), c->d_idf.p);
+        if (c->n_rows > 0 && c->nnz > 0)
+            LAUNCH(c, (pc::k_tfidf<256>), (unsigned int)c->n_rows, 256, c->d_indptr.p, c->d_indices.p, c->d_data.p, c->d_idf.p, c->d_tfidf.p);
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    c->tfidf_done = true;
+    return PC_OK;
+}
+
+int pc_tfidf_get(pc_ctx* c, float* data, int loc) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!c->tfidf_done) return fail(PC_ESTATE, "no tf-idf computed");
+    StageTimer t(c, ST_D2H);
+    return copy_out(c, data, c->d_tfidf.p, c->nnz * sizeof(float), loc);
+}
+
+// ---------------------------------------------------------------------------------------------- measurement
+int pc_timings(pc_ctx* c, float ms[PC_N_STAGES]) {
+    int rc = use_device(c); if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < PC_N_STAGES; ++i) ms[i] = 0.f;
+    for (int i = 0; i < ST_N; ++i)
+        if (c->ev_used[i]) { float v = 0.f; if (cudaEventElapsedTime(&v, c->ev[i][0], c->ev[i][1]) == cudaSuccess) ms[i] = v; else cudaGetLastError(); }
+    return PC_OK;
+}
+
+int pc_launch_count(pc_ctx* c, int64_t* launches) {
+    if (!c || !launches) return fail(PC_EINVAL, "bad arguments");
+    *launches = c->launches;
+    return PC_OK;
+}
+
+int pc_reset_counters(pc_ctx* c) {
+    if (!c) return fail(PC_EINVAL, "null context");
+    c->launches = 0;
+    for (int i = 0; i < ST_N; ++i) c->ev_used[i] = false;
+    return PC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- host unit-test hooks
+int pc_host_pack_word(const uint8_t* bases, int n, uint64_t* word, uint32_t* nmask) {
+    if (!bases || n < 0 || n > 32 || !word || !nmask) return fail(PC_EINVAL, "bad pack_word arguments");
+    uint8_t tmp[32];
+    for (int i = 0; i < 32; ++i) tmp[i] = i < n ? bases[i] : (uint8_t)'N';
+    uint64_t w = 0; uint32_t nm = 0;
+    for (int i = 0; i < 8; ++i) {
+        uint32_t v = (uint32_t)tmp[4 * i] | ((uint32_t)tmp[4 * i + 1] << 8) | ((uint32_t)tmp[4 * i + 2] << 16) | ((uint32_t)tmp[4 * i + 3] << 24);
+        w |= (uint64_t)pc::pack4_codes(v) << (56 - 8 * i);
+        nm |= pc::pack4_invalid(v) << (28 - 4 * i);
+    }
+    for (int j = 0; j < 32; ++j) if ((nm >> (31 - j)) & 1u) w &= ~(3ull << (62 - 2 * j));
+    *word = w; *nmask = nm;
+    return PC_OK;
+}
+
+int pc_host_canonical(uint64_t kmer, int k, uint64_t* out) {
+    if (k < 1 || k > 32 || !out) return fail(PC_EINVAL, "bad canonical arguments");
+    uint64_t x = kmer & pc::kmer_mask(k), rc = pc::revcomp_bits(x, k);
+    *out = x < rc ? x : rc;
+    return PC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,773 @@
+// Hand-written sm_100a kernels of the polyCRACKER hot path (K1..K7 of SURVEY.md section 7).
+// Everything here is HBM / L2 / atomic bound integer work: no tensor cores, no library calls.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "kmer_device.cuh"
+
+namespace pc {
+
+// ------------------------------------------------------------------------------------------------ tables
+// Count table slot (K3).  skey = ~kmer so that a zeroed table is empty (the all-ones pattern is never a
+// canonical-min k-mer: its reverse complement, all A, is smaller).  16-byte slots keep key and count in one
+// 32-byte DRAM sector: one sector read per probe instead of two with a split layout.
+struct __align__(16) CountSlot {
+    unsigned long long skey;
+    unsigned int count;
+    unsigned int pad;
+};
+// Repeat table slot (K5): selected k-mer -> column id.
+struct __align__(16) RepSlot {
+    unsigned long long skey;
+    int col;
+    int pad;
+};
+
+struct CountStats {
+    unsigned long long valid_windows;
+    unsigned long long distinct;
+    unsigned long long overflow;      // != 0 when a probe sequence hit the limit (table too small)
+    unsigned long long max_probe;
+};
+
+__device__ __forceinline__ unsigned long long ldcg_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ldcg_u4(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ldnc_u4(const void* p) {   // streaming read-only, do not pollute L1
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+
+// largest c in [0, n) with a[c] <= x   (a ascending, a[0] <= x)
+__device__ __forceinline__ int64_t find_le(const int64_t* __restrict__ a, int64_t n, int64_t x) {
+    int64_t lo = 0, hi = n;            // invariant a[lo] <= x < a[hi] (a[n] = +inf)
+    while (hi - lo > 1) {
+        int64_t mid = (lo + hi) >> 1;
+        if (__ldg(a + mid) <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------------ K1 pack
+// One thread = one packed word = 32 bases.  A warp reads 1 KiB of contiguous ASCII with 128-bit loads
+// (three aligned uint4 per lane, funnel-shifted to the chunk's byte phase) and writes 256 B of codes + 128 B
+// of mask, fully coalesced.  chunk_word0[c] is the first word of chunk c; chunk_word0[n_chunks] the total.
+// ascii_lo/ascii_hi bound the bytes that may be touched by the aligned over-read (the staging buffer is padded).
+template <int WS>
+__device__ __forceinline__ void realign8(const uint32_t (&r)[12], int bs, uint32_t (&o)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = __funnelshift_r(r[WS + i], r[WS + i + 1], bs);
+}
+
+__global__ void __launch_bounds__(256)
+k_pack(const uint8_t* __restrict__ ascii, int64_t ascii_bytes_padded,
+       const int64_t* __restrict__ chunk_word0, const int64_t* __restrict__ chunk_begin,
+       const int64_t* __restrict__ chunk_len, int64_t n_chunks, int64_t n_words_total,
+       uint64_t* __restrict__ words, uint32_t* __restrict__ nmask)
+{
+    int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_words_total) return;
+    int64_t data_words = __ldg(chunk_word0 + n_chunks);
+    if (w >= data_words) {             // trailing guard word(s): all padding
+        words[w] = 0ull; nmask[w] = 0xFFFFFFFFu; return;
+    }
+    int64_t c = find_le(chunk_word0, n_chunks, w);
+    int64_t off = (w - __ldg(chunk_word0 + c)) * 32;
+    int64_t remaining = __ldg(chunk_len + c) - off;         // may be <= 0: pure padding word
+    uint64_t word = 0ull; uint32_t nm = 0xFFFFFFFFu;
+    if (remaining > 0) {
+        int64_t src = __ldg(chunk_begin + c) + off;          // byte offset into ascii
+        int sh = (int)((reinterpret_cast<uintptr_t>(ascii) + (uintptr_t)src) & 15);
+        int64_t a0 = src - sh;                                // 16-byte aligned (ascii itself is 256-aligned)
+        uint32_t o[8];
+        if (a0 >= 0 && a0 + 48 <= ascii_bytes_padded) {
+            const uint8_t* p = ascii + a0;
+            uint4 q0 = ldnc_u4(p), q1 = ldnc_u4(p + 16), q2 = ldnc_u4(p + 32);
+            uint32_t r[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+            int bs = (sh & 3) * 8;
+            switch (sh >> 2) {
+                case 0: realign8<0>(r, bs, o); break;
+                case 1: realign8<1>(r, bs, o); break;
+                case 2: realign8<2>(r, bs, o); break;
+                default: realign8<3>(r, bs, o); break;
+            }
+        } else {                                              // caller-owned device buffer without slack
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                uint32_t v = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    int64_t idx = src + 4 * i + b;
+                    uint32_t ch = (4 * i + b < remaining && idx < ascii_bytes_padded) ? ascii[idx] : (uint32_t)'N';
+                    v |= ch << (8 * b);
+                }
+                o[i] = v;
+            }
+        }
+        nm = 0u;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            word |= (uint64_t)pack4_codes(o[i]) << (56 - 8 * i);
+            nm |= pack4_invalid(o[i]) << (28 - 4 * i);
+        }
+        if (remaining < 32) {                                 // bases past the chunk end are padding
+            nm |= 0xFFFFFFFFu >> (int)remaining;
+            word &= ~(~0ull >> (2 * (int)remaining));
+        }
+        // invalid bases carry code 0 so the packed words are deterministic
+        // (spread the 32 mask bits to 64 code bits: bit (31-j) -> bits (63-2j, 62-2j))
+        uint64_t m64 = nm;
+        m64 = (m64 | (m64 << 16)) & 0x0000FFFF0000FFFFull;
+        m64 = (m64 | (m64 << 8)) & 0x00FF00FF00FF00FFull;
+        m64 = (m64 | (m64 << 4)) & 0x0F0F0F0F0F0F0F0Full;
+        m64 = (m64 | (m64 << 2)) & 0x3333333333333333ull;
+        m64 = (m64 | (m64 << 1)) & 0x5555555555555555ull;
+        word &= ~(m64 | (m64 << 1));
+    }
+    words[w] = word;
+    nmask[w] = nm;
+}
+
+// ------------------------------------------------------------------------------------------------ K2 extraction
+// One lane = one packed word = 32 window starts; the (k-1)-base overlap comes from the next lane's word by
+// warp shuffle (lane 31 loads it), so every packed word is read from HBM once.
+struct WordPair {
+    uint64_t w0, w1; uint32_t m0, m1;
+};
+__device__ __forceinline__ WordPair load_word_pair(const uint64_t* __restrict__ words,
+                                                   const uint32_t* __restrict__ nmask,
+                                                   int64_t w, int64_t n_words /* data words; word n_words is a guard */)
+{
+    WordPair p;
+    bool in = w < n_words;
+    p.w0 = in ? __ldg(words + w) : 0ull;
+    p.m0 = in ? __ldg(nmask + w) : 0xFFFFFFFFu;
+    p.w1 = __shfl_down_sync(0xFFFFFFFFu, p.w0, 1);
+    p.m1 = __shfl_down_sync(0xFFFFFFFFu, p.m0, 1);
+    if ((threadIdx.x & 31) == 31) {
+        bool in1 = (w + 1) < n_words;
+        p.w1 = in1 ? __ldg(words + w + 1) : 0ull;
+        p.m1 = in1 ? __ldg(nmask + w + 1) : 0xFFFFFFFFu;
+    }
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------------ K3 count
+#define PC_PROBE_LIMIT (1u << 22)
+
+__device__ __forceinline__ void count_insert(CountSlot* __restrict__ table, uint64_t capacity, uint64_t slot,
+                                             unsigned long long skey, unsigned long long cur,
+                                             unsigned int& new_keys, unsigned int& max_probe,
+                                             CountStats* stats)
+{
+    // `cur` is the (possibly stale-empty) key already loaded from table[slot]
+    unsigned int probes = 0;
+    for (;;) {
+        if (cur == 0ull) {
+            cur = atomicCAS(&table[slot].skey, 0ull, skey);
+            if (cur == 0ull) { ++new_keys; cur = skey; }
+        }
+        if (cur == skey) {
+            atomicAdd(&table[slot].count, 1u);                // result unused -> RED
+            break;
+        }
+        if (++probes > PC_PROBE_LIMIT) { atomicAdd(&stats->overflow, 1ull); break; }
+        if (++slot == capacity) slot = 0;
+        cur = ldcg_u64(&table[slot].skey);
+    }
+    max_probe = max(max_probe, probes);
+}
+
+template <int BATCH>
+__global__ void __launch_bounds__(256)
+k_count(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, int64_t n_words, int k,
+        CountSlot* __restrict__ table, uint64_t capacity, CountStats* __restrict__ stats)
+{
+    int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    WordPair p = load_word_pair(words, nmask, w, n_words);
+    unsigned int nvalid = 0, new_keys = 0, max_probe = 0;
+    if (p.m0 != 0xFFFFFFFFu) {
+        Roller r; r.init(p.w0, p.w1, p.m0, p.m1, k);
+#pragma unroll 1
+        for (int b0 = 0; b0 < 32; b0 += BATCH) {
+            unsigned long long skey[BATCH]; uint64_t slot[BATCH]; unsigned long long cur[BATCH];
+            unsigned int vmask = 0;
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j) {
+                int b = b0 + j;
+                uint64_t key = r.canonical();
+                bool v = r.valid(b);
+                vmask |= (unsigned int)v << j;
+                skey[j] = ~key;
+                slot[j] = slot_of(mix64(key), capacity);
+                if (b < 31) r.step(b);
+            }
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j)                    // all probes of the batch in flight together
+                cur[j] = ((vmask >> j) & 1u) ? ldcg_u64(&table[slot[j]].skey) : 0ull;
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j)
+                if ((vmask >> j) & 1u)
+                    count_insert(table, capacity, slot[j], skey[j], cur[j], new_keys, max_probe, stats);
+            nvalid += __popc(vmask);
+        }
+    }
+    // per-warp statistics: 2-3 atomics per 1024 windows
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        nvalid += __shfl_xor_sync(0xFFFFFFFFu, nvalid, o);
+        new_keys += __shfl_xor_sync(0xFFFFFFFFu, new_keys, o);
+        max_probe = max(max_probe, __shfl_xor_sync(0xFFFFFFFFu, max_probe, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (nvalid) atomicAdd(&stats->valid_windows, (unsigned long long)nvalid);
+        if (new_keys) atomicAdd(&stats->distinct, (unsigned long long)new_keys);
+        if (max_probe > 8) atomicMax(&stats->max_probe, (unsigned long long)max_probe);
+    }
+}
+
+// merge (kmer, count) pairs received from other ranks into the owner's table (multi-GPU)
+__global__ void __launch_bounds__(256)
+k_merge(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, int64_t n,
+        CountSlot* __restrict__ table, uint64_t capacity, CountStats* __restrict__ stats)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t key = keys[i];
+    unsigned int add = counts[i];
+    unsigned long long skey = ~key;
+    uint64_t slot = slot_of(mix64(key), capacity);
+    unsigned int probes = 0;
+    for (;;) {
+        unsigned long long cur = ldcg_u64(&table[slot].skey);
+        if (cur == 0ull) {
+            cur = atomicCAS(&table[slot].skey, 0ull, skey);
+            if (cur == 0ull) { atomicAdd(&stats->distinct, 1ull); cur = skey; }
+        }
+        if (cur == skey) { atomicAdd(&table[slot].count, add); break; }
+        if (++probes > PC_PROBE_LIMIT) { atomicAdd(&stats->overflow, 1ull); break; }
+        if (++slot == capacity) slot = 0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K4 select
+// Streaming scan of the table; survivors appended with one atomic per warp.  out_keys may be null (count only).
+__global__ void __launch_bounds__(256)
+k_select(const CountSlot* __restrict__ table, uint64_t capacity, unsigned int low, unsigned int high,
+         uint64_t* __restrict__ out_keys, uint32_t* __restrict__ out_counts, unsigned long long out_cap,
+         unsigned long long* __restrict__ n_out)
+{
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    uint64_t cap_round = (capacity + 31) & ~31ull;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap_round; i += stride) {
+        bool keep = false; unsigned long long skey = 0; unsigned int cnt = 0;
+        if (i < capacity) {
+            uint4 s = ldnc_u4(table + i);
+            skey = ((unsigned long long)s.y << 32) | s.x; cnt = s.z;
+            keep = skey != 0ull && cnt >= low && cnt <= high;
+        }
+        unsigned int bal = __ballot_sync(0xFFFFFFFFu, keep);
+        if (bal) {
+            int lane = threadIdx.x & 31;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(n_out, (unsigned long long)__popc(bal));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (keep && out_keys) {
+                unsigned long long pos = base + __popc(bal & ((1u << lane) - 1u));
+                if (pos < out_cap) {
+                    out_keys[pos] = ~skey;
+                    if (out_counts) out_counts[pos] = cnt;
+                }
+            }
+        }
+    }
+}
+
+// owner histogram + scatter for the multi-GPU exchange
+__global__ void __launch_bounds__(256)
+k_owner_hist(const CountSlot* __restrict__ table, uint64_t capacity, unsigned int world,
+             unsigned long long* __restrict__ hist /* world */)
+{
+    __shared__ unsigned int sh[64];
+    if (threadIdx.x < 64) sh[threadIdx.x] = 0;
+    __syncthreads();
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < capacity; i += stride) {
+        uint4 s = ldnc_u4(table + i);
+        unsigned long long skey = ((unsigned long long)s.y << 32) | s.x;
+        if (skey != 0ull) atomicAdd(&sh[owner_of(~skey, world)], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < world && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
+}
+__global__ void __launch_bounds__(256)
+k_owner_scatter(const CountSlot* __restrict__ table, uint64_t capacity, unsigned int world,
+                unsigned long long* __restrict__ cursor /* world, pre-set to bucket starts */,
+                uint64_t* __restrict__ out_keys, uint32_t* __restrict__ out_counts)
+{
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < capacity; i += stride) {
+        uint4 s = ldnc_u4(table + i);
+        unsigned long long skey = ((unsigned long long)s.y << 32) | s.x;
+        if (skey != 0ull) {
+            unsigned int o = owner_of(~skey, world);
+            unsigned int peers = __match_any_sync(__activemask(), o);
+            int lane = threadIdx.x & 31;
+            int leader = __ffs(peers) - 1;
+            unsigned long long base = 0;
+            if (lane == leader) base = atomicAdd(&cursor[o], (unsigned long long)__popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            unsigned long long pos = base + __popc(peers & ((1u << lane) - 1u));
+            out_keys[pos] = ~skey; out_counts[pos] = s.z;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ radix sort
+// Stable LSD radix sort, 8-bit digits, warp-blocked ranges: warp gw owns the contiguous range
+// [gw*ipw, (gw+1)*ipw).  hist is digit-major (hist[d*NW + gw]) so one exclusive scan over the flat array yields
+// every (digit, warp) output base.  Ranking inside a warp uses match.any, no smem atomics in the scatter.
+template <typename K>
+__device__ __forceinline__ unsigned int digit_of(K key, int shift) { return (unsigned int)(key >> shift) & 0xFFu; }
+
+template <typename K, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_rs_hist(const K* __restrict__ src, int64_t n, int64_t ipw, int shift, unsigned int* __restrict__ hist, int NW)
+{
+    __shared__ unsigned int h[WARPS][256];
+    int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < WARPS * 256; i += WARPS * 32) (&h[0][0])[i] = 0;
+    __syncthreads();
+    int gw = blockIdx.x * WARPS + wid;
+    int64_t beg = (int64_t)gw * ipw, end = min(n, beg + ipw);
+    for (int64_t i = beg + lane; i < end; i += 32) atomicAdd(&h[wid][digit_of(src[i], shift)], 1u);
+    __syncthreads();
+    for (int d = lane; d < 256; d += 32) hist[(int64_t)d * NW + gw] = h[wid][d];
+}
+
+// single-CTA exclusive scan of `m` counters (m = 256*NW, a few 1e5)
+__global__ void __launch_bounds__(1024)
+k_rs_scan(unsigned int* __restrict__ hist, int64_t m)
+{
+    __shared__ unsigned int part[1024];
+    int t = threadIdx.x;
+    int64_t per = (m + 1023) / 1024;
+    int64_t beg = (int64_t)t * per, end = min(m, beg + per);
+    unsigned int s = 0;
+    for (int64_t i = beg; i < end; ++i) s += hist[i];
+    part[t] = s;
+    __syncthreads();
+    // Hillis-Steele inclusive scan over 1024 partials
+    for (int o = 1; o < 1024; o <<= 1) {
+        unsigned int v = (t >= o) ? part[t - o] : 0u;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    unsigned int run = part[t] - s;                          // exclusive
+    for (int64_t i = beg; i < end; ++i) { unsigned int v = hist[i]; hist[i] = run; run += v; }
+}
+
+template <typename K, int WARPS, bool HAS_VAL>
+__global__ void __launch_bounds__(WARPS * 32)
+k_rs_scatter(const K* __restrict__ src, K* __restrict__ dst, const uint32_t* __restrict__ vsrc,
+             uint32_t* __restrict__ vdst, int64_t n, int64_t ipw, int shift,
+             const unsigned int* __restrict__ hist, int NW)
+{
+    __shared__ unsigned int off[WARPS][256];
+    int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int gw = blockIdx.x * WARPS + wid;
+    for (int d = lane; d < 256; d += 32) off[wid][d] = hist[(int64_t)d * NW + gw];
+    __syncwarp();
+    int64_t beg = (int64_t)gw * ipw, end = min(n, beg + ipw);
+    for (int64_t i0 = beg; i0 < end; i0 += 32) {
+        int64_t i = i0 + lane;
+        bool act = i < end;
+        unsigned int amask = __ballot_sync(0xFFFFFFFFu, act);
+        if (act) {
+            K key = src[i];
+            unsigned int d = digit_of(key, shift);
+            unsigned int peers = __match_any_sync(amask, d);
+            unsigned int rank = __popc(peers & ((1u << lane) - 1u));
+            unsigned int base = off[wid][d];
+            __syncwarp(amask);
+            if (rank == 0) off[wid][d] = base + __popc(peers);
+            __syncwarp(amask);
+            dst[base + rank] = key;
+            if (HAS_VAL) vdst[base + rank] = vsrc[i];
+        }
+    }
+}
+
+// drop consecutive duplicates of a sorted array (pc_set_selected); flags -> positions via one atomic per warp
+// would break order, so this is a two-kernel exact compaction: per-CTA counts, host-free scan, scatter.
+__global__ void __launch_bounds__(1024)
+k_unique_sorted_single(const uint64_t* __restrict__ src, int64_t n, uint64_t* __restrict__ dst,
+                       unsigned long long* __restrict__ n_out)
+{
+    // single CTA, ordered: used only for repeat sets (a few 1e6 keys at most per call)
+    __shared__ unsigned int wsum[32];
+    __shared__ unsigned long long carry;
+    int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    if (t == 0) carry = 0;
+    __syncthreads();
+    for (int64_t i0 = 0; i0 < n; i0 += 1024) {
+        int64_t i = i0 + t;
+        bool flag = false; uint64_t v = 0;
+        if (i < n) { v = src[i]; flag = (i == 0) || (src[i - 1] != v); }
+        unsigned int bal = __ballot_sync(0xFFFFFFFFu, flag);
+        if (lane == 0) wsum[wid] = __popc(bal);
+        __syncthreads();
+        unsigned int before = 0, total = 0;
+        for (int x = 0; x < 32; ++x) { unsigned int c = wsum[x]; if (x < wid) before += c; total += c; }
+        unsigned long long base = carry;
+        if (flag) dst[base + before + __popc(bal & ((1u << lane) - 1u))] = v;
+        __syncthreads();
+        if (t == 0) carry = base + total;
+        __syncthreads();
+    }
+    if (t == 0) *n_out = carry;
+}
+
+__global__ void __launch_bounds__(256)
+k_canonicalize(uint64_t* __restrict__ keys, int64_t n, int k)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t x = keys[i] & kmer_mask(k);
+    uint64_t rc = revcomp_bits(x, k);
+    keys[i] = x < rc ? x : rc;
+}
+
+__global__ void __launch_bounds__(256)
+k_stride_gather(const uint64_t* __restrict__ src, int64_t n_out, int64_t stride, uint64_t* __restrict__ dst)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_out) dst[i] = src[i * stride];
+}
+
+// ------------------------------------------------------------------------------------------------ K5 repeat table + probe
+__global__ void __launch_bounds__(256)
+k_rep_build(const uint64_t* __restrict__ sorted_keys, int64_t n, RepSlot* __restrict__ table, uint64_t capacity)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t key = sorted_keys[i];
+    unsigned long long skey = ~key;
+    uint64_t slot = slot_of(mix64(key), capacity);
+    for (;;) {                                               // keys are unique and capacity >= 2n: terminates
+        unsigned long long cur = atomicCAS(&table[slot].skey, 0ull, skey);
+        if (cur == 0ull) { table[slot].col = (int)i; break; }
+        if (++slot == capacity) slot = 0;
+    }
+}
+
+// chunk of a packed word: chunk_word0 ascending.  Warp-uniform binary search for lane 0, then a short walk.
+__device__ __forceinline__ int64_t chunk_of_word(const int64_t* __restrict__ chunk_word0, int64_t n_chunks,
+                                                 int64_t w, int64_t w_lane0)
+{
+    int64_t c = find_le(chunk_word0, n_chunks, w_lane0);
+    while (c + 1 < n_chunks && __ldg(chunk_word0 + c + 1) <= w) ++c;
+    return c;
+}
+
+// Streams the packed genome once; every valid window probes the repeat table (one 32-byte sector, normally an
+// L2 hit) and hits (column ids) are appended to the row's private region of `hits`.
+template <int BATCH>
+__global__ void __launch_bounds__(256)
+k_probe(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, int64_t n_words, int k,
+        const int64_t* __restrict__ chunk_word0, int64_t n_chunks, const int32_t* __restrict__ chunk_row,
+        const int64_t* __restrict__ row_hit_base, const RepSlot* __restrict__ rtable, uint64_t rcap,
+        int32_t* __restrict__ hits, unsigned int* __restrict__ row_cursor)
+{
+    int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int lane = threadIdx.x & 31;
+    WordPair p = load_word_pair(words, nmask, w, n_words);
+    int64_t w_lane0 = w - lane;
+    if (w_lane0 >= n_words) return;                           // whole warp past the end
+    int row = -1;
+    if (w < n_words && p.m0 != 0xFFFFFFFFu) {
+        int64_t c = chunk_of_word(chunk_word0, n_chunks, w, w_lane0);
+        row = __ldg(chunk_row + c);
+    }
+    bool lane_on = row >= 0;
+    unsigned int on_mask = __ballot_sync(0xFFFFFFFFu, lane_on);
+    if (on_mask == 0u) return;
+    int row0 = __shfl_sync(0xFFFFFFFFu, row, __ffs(on_mask) - 1);
+    bool uniform = __all_sync(0xFFFFFFFFu, !lane_on || row == row0);
+
+    Roller r;
+    if (lane_on) r.init(p.w0, p.w1, p.m0, p.m1, k);
+#pragma unroll 1
+    for (int b0 = 0; b0 < 32; b0 += BATCH) {
+        int cols[BATCH];
+        unsigned int hmask = 0;                               // bit j: window b0+j hit repeat k-mer cols[j]
+        if (lane_on) {
+            unsigned long long skey[BATCH]; uint64_t slot[BATCH]; uint4 cur[BATCH];
+            unsigned int vmask = 0;
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j) {
+                int b = b0 + j;
+                uint64_t key = r.canonical();
+                vmask |= (unsigned int)r.valid(b) << j;
+                skey[j] = ~key;
+                slot[j] = slot_of(mix64(key), rcap);
+                if (b < 31) r.step(b);
+            }
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j)
+                cur[j] = ((vmask >> j) & 1u) ? __ldg(reinterpret_cast<const uint4*>(rtable + slot[j])) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j) {
+                cols[j] = 0;
+                if (!((vmask >> j) & 1u)) continue;
+                unsigned long long ck = ((unsigned long long)cur[j].y << 32) | cur[j].x;
+                int col = (int)cur[j].z;
+                uint64_t s = slot[j];
+                while (ck != 0ull && ck != skey[j]) {          // linear probing until empty or found
+                    if (++s == rcap) s = 0;
+                    uint4 c2 = __ldg(reinterpret_cast<const uint4*>(rtable + s));
+                    ck = ((unsigned long long)c2.y << 32) | c2.x; col = (int)c2.z;
+                }
+                if (ck != 0ull) { cols[j] = col; hmask |= 1u << j; }
+            }
+        }
+        int nh = __popc(hmask);
+        // append this batch's hits: one atomic per warp when the warp sits in one row (the normal case)
+        unsigned int any = __ballot_sync(0xFFFFFFFFu, nh > 0);
+        if (any == 0u) continue;
+        int32_t* dst = nullptr;
+        if (uniform) {
+            int incl = nh;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(&row_cursor[row0], (unsigned int)total);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (nh > 0) dst = hits + __ldg(row_hit_base + row0) + base + (incl - nh);
+        } else if (nh > 0) {
+            unsigned int base = atomicAdd(&row_cursor[row], (unsigned int)nh);
+            dst = hits + __ldg(row_hit_base + row) + base;
+        }
+        if (nh > 0) {
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j)
+                if ((hmask >> j) & 1u) dst[__popc(hmask & ((1u << j) - 1u))] = cols[j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K6 rows -> CSR
+// One CTA per matrix row.  The row's hits (column ids, unordered, with multiplicity) are sorted with the same
+// stable LSD scheme, CTA-local: warp wq owns a contiguous slice, hist[wq][256] lives in shared memory, data
+// ping-pongs between the row's slices of two global buffers (L2 resident: a 75 kb chunk is <= 300 KB).
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+k_row_sort(int32_t* buf_a, int32_t* buf_b, const int64_t* __restrict__ row_hit_base,
+           const unsigned int* __restrict__ row_cursor, int n_passes, int64_t* __restrict__ row_nnz)
+{
+    __shared__ unsigned int h[WARPS][256];
+    __shared__ unsigned int tot[256];
+    __shared__ unsigned int red[WARPS];
+    int row = blockIdx.x;
+    int t = threadIdx.x, wid = t >> 5, lane = t & 31;
+    unsigned int n = row_cursor[row];
+    int64_t base = row_hit_base[row];
+    int32_t* src = buf_a + base;
+    int32_t* dst = buf_b + base;
+    unsigned int ipw = ((n + WARPS - 1) / WARPS + 31u) & ~31u;
+    unsigned int beg = min(n, wid * ipw), end = min(n, beg + ipw);
+    for (int pass = 0; pass < n_passes; ++pass) {
+        int shift = 8 * pass;
+        for (int i = t; i < WARPS * 256; i += WARPS * 32) (&h[0][0])[i] = 0;
+        __syncthreads();
+        for (unsigned int i = beg + lane; i < end; i += 32)
+            atomicAdd(&h[wid][((unsigned int)src[i] >> shift) & 0xFFu], 1u);
+        __syncthreads();
+        if (t < 256) {                                        // per digit: exclusive scan over warps
+            unsigned int s = 0;
+#pragma unroll
+            for (int q = 0; q < WARPS; ++q) { unsigned int v = h[q][t]; h[q][t] = s; s += v; }
+            tot[t] = s;
+        }
+        __syncthreads();
+        if (wid == 0) {                                       // exclusive scan of the 256 digit totals
+            unsigned int carry = 0;
+            for (int d0 = 0; d0 < 256; d0 += 32) {
+                unsigned int v = tot[d0 + lane], incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    unsigned int u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (lane >= o) incl += u;
+                }
+                tot[d0 + lane] = carry + incl - v;
+                carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+            }
+        }
+        __syncthreads();
+        for (int d = lane; d < 256; d += 32) h[wid][d] += tot[d];
+        __syncwarp();
+        for (unsigned int i0 = beg; i0 < end; i0 += 32) {
+            unsigned int i = i0 + lane;
+            bool act = i < end;
+            unsigned int amask = __ballot_sync(0xFFFFFFFFu, act);
+            if (act) {
+                int32_t key = src[i];
+                unsigned int d = ((unsigned int)key >> shift) & 0xFFu;
+                unsigned int peers = __match_any_sync(amask, d);
+                unsigned int rank = __popc(peers & ((1u << lane) - 1u));
+                unsigned int ob = h[wid][d];
+                __syncwarp(amask);
+                if (rank == 0) h[wid][d] = ob + __popc(peers);
+                __syncwarp(amask);
+                dst[ob + rank] = key;
+            }
+        }
+        __syncthreads();                                      // dst complete and visible to the whole CTA
+        int32_t* tmp = src; src = dst; dst = tmp;
+    }
+    // number of distinct columns in the sorted row
+    unsigned int cnt = 0;
+    for (unsigned int i = t; i < n; i += WARPS * 32) cnt += (i == 0 || src[i] != src[i - 1]) ? 1u : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+    if (lane == 0) red[wid] = cnt;
+    __syncthreads();
+    if (t == 0) {
+        unsigned int s = 0;
+        for (int q = 0; q < WARPS; ++q) s += red[q];
+        row_nnz[row] = (int64_t)s;
+    }
+}
+
+// exclusive scan of row_nnz -> indptr (R+1).  Single CTA; R is at most a few 1e5.
+__global__ void __launch_bounds__(1024)
+k_indptr(const int64_t* __restrict__ row_nnz, int64_t n_rows, int64_t* __restrict__ indptr)
+{
+    __shared__ unsigned long long part[1024];
+    int t = threadIdx.x;
+    int64_t per = (n_rows + 1023) / 1024;
+    int64_t beg = (int64_t)t * per, end = min(n_rows, beg + per);
+    unsigned long long s = 0;
+    for (int64_t i = beg; i < end; ++i) s += (unsigned long long)row_nnz[i];
+    part[t] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        unsigned long long v = (t >= o) ? part[t - o] : 0ull;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    unsigned long long run = part[t] - s;
+    for (int64_t i = beg; i < end; ++i) { indptr[i] = (int64_t)run; run += (unsigned long long)row_nnz[i]; }
+    if (t == 1023) indptr[n_rows] = (int64_t)part[1023];
+}
+
+// run-length encode each sorted row into CSR (indices ascending, data = multiplicity) and accumulate the
+// column document frequency df (= stored entries per column, what TfidfTransformer calls df).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_row_emit(const int32_t* __restrict__ sorted, const int64_t* __restrict__ row_hit_base,
+           const unsigned int* __restrict__ row_cursor, const int64_t* __restrict__ indptr,
+           int32_t* __restrict__ indices, float* __restrict__ data, int* __restrict__ df)
+{
+    __shared__ unsigned int wsum[THREADS / 32];
+    __shared__ unsigned int carry_s;
+    int row = blockIdx.x;
+    int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    unsigned int n = row_cursor[row];
+    const int32_t* a = sorted + row_hit_base[row];
+    int64_t out0 = indptr[row];
+    if (t == 0) carry_s = 0;
+    __syncthreads();
+    for (unsigned int i0 = 0; i0 < n; i0 += THREADS) {
+        unsigned int i = i0 + t;
+        bool flag = false; int32_t v = 0;
+        if (i < n) { v = a[i]; flag = (i == 0) || (a[i - 1] != v); }
+        unsigned int bal = __ballot_sync(0xFFFFFFFFu, flag);
+        if (lane == 0) wsum[wid] = __popc(bal);
+        __syncthreads();
+        unsigned int before = 0, total = 0;
+#pragma unroll
+        for (int x = 0; x < THREADS / 32; ++x) { unsigned int c = wsum[x]; if (x < wid) before += c; total += c; }
+        unsigned int base = carry_s;
+        if (flag) {
+            // run end: short linear look-ahead, then binary search (runs are usually 1-3 long)
+            unsigned int e = i + 1;
+            int steps = 0;
+            while (e < n && steps < 4 && a[e] == v) { ++e; ++steps; }
+            if (e < n && a[e] == v) {
+                unsigned int lo = e, hi = n;                  // a[lo] == v, find first index with a[] != v
+                while (hi - lo > 1) { unsigned int mid = lo + ((hi - lo) >> 1); if (a[mid] == v) lo = mid; else hi = mid; }
+                e = hi;
+            }
+            int64_t pos = out0 + base + before + __popc(bal & ((1u << lane) - 1u));
+            indices[pos] = v;
+            data[pos] = (float)(e - i);
+            atomicAdd(&df[v], 1);
+        }
+        __syncthreads();
+        if (t == 0) carry_s = base + total;
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K7 tf-idf
+// idf_j = ln(float32(n+1) / float32(df_j+1)) + 1, all float32 like sklearn with float32 input
+// (text.py: df.astype(dtype); full_like/df; np.log; += 1).
+__global__ void __launch_bounds__(256)
+k_idf(const int* __restrict__ df, int64_t n_cols, float n_plus_1, float* __restrict__ idf)
+{
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_cols) return;
+    float q = __fdiv_rn(n_plus_1, (float)df[j] + 1.0f);
+    idf[j] = (float)log((double)q) + 1.0f;                   // correctly rounded float32 log, then float32 add
+}
+
+// One CTA per row: x = count*idf (float32), sum of float32 squares accumulated in double, x /= sqrt(sum) in
+// double and rounded once (sparsefuncs_fast.pyx:_inplace_csr_row_normalize_l2).  Zero rows stay zero.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_tfidf(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ data,
+        const float* __restrict__ idf, float* __restrict__ out)
+{
+    __shared__ double red[THREADS / 32];
+    __shared__ double norm_s;
+    int row = blockIdx.x;
+    int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    int64_t beg = indptr[row], end = indptr[row + 1];
+    double acc = 0.0;
+    for (int64_t i = beg + t; i < end; i += THREADS) {
+        float x = __fmul_rn(data[i], __ldg(idf + indices[i]));
+        out[i] = x;
+        acc += (double)__fmul_rn(x, x);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, o);
+    if (lane == 0) red[wid] = acc;
+    __syncthreads();
+    if (t == 0) {
+        double s = 0.0;
+        for (int q = 0; q < THREADS / 32; ++q) s += red[q];
+        norm_s = sqrt(s);
+    }
+    __syncthreads();
+    double nrm = norm_s;
+    if (nrm == 0.0) return;
+    for (int64_t i = beg + t; i < end; i += THREADS) out[i] = (float)((double)out[i] / nrm);
+}
+
+}  // namespace pc

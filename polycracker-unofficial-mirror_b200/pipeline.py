@@ -1,0 +1,129 @@
+"""In-memory hot path: split -> count -> select -> exact match -> CSR -> TF-IDF, all compute on the GPU through
+the C ABI.  The file-based stage functions (stages.py / cli.py) and bench.py are thin callers of this module.
+
+Host code here is integer bookkeeping only (chunk names, row order, row filter: polycracker.py:129-156, 284-287,
+322-327); it never touches a base or a k-mer.
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import binding
+
+
+class ChunkLayout:
+    """a1 + a6: chunk geometry, names, bed order, row universe (polycracker.py:129-156, 284-287)."""
+
+    def __init__(self, names, seq_offsets, chunk_size):
+        self.seq_names = list(names)
+        self.seq_offsets = np.ascontiguousarray(seq_offsets, dtype=np.int64)
+        self.chunk_size = int(chunk_size)
+        seq_len = np.diff(self.seq_offsets)
+        self.chunk_seq, self.chunk_start, self.chunk_end = binding.chunk_table(seq_len, self.chunk_size)
+        base = self.seq_offsets[self.chunk_seq] if len(self.chunk_seq) else np.zeros(0, np.int64)
+        self.chunk_begin_abs = base + self.chunk_start
+        self.chunk_end_abs = base + self.chunk_end
+        self.chunk_names = ["%s_%d_%d" % (self.seq_names[s], a, b)
+                            for s, a, b in zip(self.chunk_seq.tolist(), self.chunk_start.tolist(),
+                                               self.chunk_end.tolist())]
+
+    @property
+    def n_chunks(self):
+        return len(self.chunk_names)
+
+    def bed_rows(self):
+        """correspondence.bed rows in `bedtools sort` order (chrom bytewise, start numeric; pc.py:154)."""
+        rows = [(self.seq_names[s], a, b, n) for s, a, b, n in
+                zip(self.chunk_seq.tolist(), self.chunk_start.tolist(), self.chunk_end.tolist(), self.chunk_names)]
+        rows.sort(key=lambda r: (r[0].encode(), r[1]))
+        return rows
+
+    def original_scaffolds(self):
+        return sorted(self.chunk_names)                       # findScaffolds, pc.py:284-287
+
+    def rows(self, remove_non_chunk=1, min_chunk_threshold=0, min_chunk_size=0, prefilter=0, keep_names=None):
+        """Row universe after the filter of polycracker.py:322-327 -> (scaffolds, chunk_row int32).
+        keep_names (optional set) restricts rows further (a correspondence.bed that was pre-filtered)."""
+        clen = np.abs(self.chunk_end - self.chunk_start)
+        if remove_non_chunk and prefilter == 0:
+            keep = clen == self.chunk_size
+        elif min_chunk_threshold and prefilter == 0:
+            keep = clen >= int(min_chunk_size)
+        else:
+            keep = np.ones(self.n_chunks, bool)
+        idx = [i for i in np.flatnonzero(keep).tolist() if keep_names is None or self.chunk_names[i] in keep_names]
+        idx.sort(key=lambda i: self.chunk_names[i])
+        chunk_row = np.full(self.n_chunks, -1, np.int32)
+        chunk_row[idx] = np.arange(len(idx), dtype=np.int32)
+        return [self.chunk_names[i] for i in idx], chunk_row
+
+
+@dataclass
+class HotPathResult:
+    layout: ChunkLayout
+    k: int
+    scaffolds: list            # row labels (scaffolds.p)
+    kmer_keys: np.ndarray      # uint64, ascending == sorted k-mer strings (kmers.p)
+    indptr: object             # CSR of raw counts (numpy, or torch CUDA tensors when device_out)
+    indices: object
+    data: object
+    tfidf: object              # TF-IDF values in CSR order (or None)
+    df: object = None
+    stats: dict = field(default_factory=dict)
+    timings: dict = field(default_factory=dict)
+
+    @property
+    def shape(self):
+        return (len(self.scaffolds), len(self.kmer_keys))
+
+    def kmers(self, orientation="min"):
+        """Column labels.  'max' relabels every k-mer by its reverse complement (BBTools orientation);
+        note the reference would then also sort by those labels -- see stages.relabel_max."""
+        names = binding.kmer_decode(self.kmer_keys, self.k)
+        if orientation == "max":
+            comp = str.maketrans("ACGT", "TGCA")
+            names = [n.translate(comp)[::-1] for n in names]
+        return names
+
+    def csr_matrix(self, values="counts"):
+        import scipy.sparse as sps
+        d = self.data if values == "counts" else self.tfidf
+        idt = np.int32 if (len(self.indices) < 2**31 - 1) else np.int64
+        return sps.csr_matrix((np.asarray(d), np.asarray(self.indices).astype(idt, copy=False),
+                               np.asarray(self.indptr).astype(idt, copy=False)), shape=self.shape)
+
+
+def effective_low_count(k, kmer_low_count):
+    """kmer2Fasta only ever sees what writeKmerCount dumped: `mincount=3` for k <= 31 (polycracker.py:199),
+    everything for k > 31 (jellyfish dump without -L, polycracker.py:203)."""
+    return max(int(kmer_low_count), 3 if k <= 31 else 1)
+
+
+def run_hot_path(ctx, seq, seq_offsets, names, chunk_size=75000, k=23, kmer_low_count=100, high_bool=0,
+                 kmer_high_count=2000000, sampling_sensitivity=1, remove_non_chunk=1, min_chunk_threshold=0,
+                 min_chunk_size=0, prefilter=0, tfidf=True, table_capacity=0, fetch=True, layout=None):
+    """One pass of the hot path on one GPU.
+
+    seq: newline-free ASCII bases, numpy uint8 (pageable or pinned) or a torch uint8 tensor (CPU pinned or CUDA).
+    Returns a HotPathResult; with fetch=False the CSR stays on the device and only sizes are returned.
+    """
+    if layout is None:
+        layout = ChunkLayout(names, seq_offsets, chunk_size)
+    scaffolds, chunk_row = layout.rows(remove_non_chunk, min_chunk_threshold, min_chunk_size, prefilter)
+    ctx.load_sequences(seq, layout.chunk_begin_abs, layout.chunk_end_abs)
+    ctx.count(k, table_capacity)
+    n_sel = ctx.select(effective_low_count(k, kmer_low_count), kmer_high_count, bool(high_bool),
+                       sampling_sensitivity)
+    nnz = ctx.build_matrix(chunk_row, len(scaffolds))
+    if tfidf:
+        ctx.tfidf(len(scaffolds))
+    stats = ctx.count_info()
+    stats.update(n_selected=n_sel, nnz=nnz, n_rows=len(scaffolds), n_chunks=layout.n_chunks)
+    if not fetch:
+        return HotPathResult(layout, k, scaffolds, np.empty(0, np.uint64), None, None, None, None, None, stats,
+                             ctx.timings())
+    keys = ctx.selected(n_sel)
+    indptr, indices, data = ctx.csr(len(scaffolds), nnz)
+    tf = ctx.tfidf_values(nnz) if tfidf else None
+    df = ctx.df(n_sel)
+    return HotPathResult(layout, k, scaffolds, keys, indptr, indices, data, tf, df, stats, ctx.timings())
