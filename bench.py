@@ -1,0 +1,340 @@
+#!/usr/bin/env python
+"""bench.py -- matrix-build Gbp/s at k=23 (BASELINE.json metric) on 1..8 B200, next to the host-CPU reference.
+
+    python bench.py --gpus N --steps K --warmup W              # the CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W      # the CPU restatement of the reference path
+
+A "step" is one pass of the hot path (2-bit pack -> count -> select -> exact match -> CSR -> TF-IDF) over the
+synthetic genome of BASELINE.json configs[1] (500 Mbp allotetraploid, k=23, 75 kb chunks, threshold 30); with N GPUs
+every rank gets one 500 Mbp share of an N x 500 Mbp genome of the same shape (weak scaling) and the count exchange
+(all-to-all), repeat-set all-gather and df all-reduce run inside the step.
+
+One JSON line on stdout (rank 0).  `value` = genome bases / step time with the ASCII genome already resident in HBM;
+`e2e` = the same through the public API with pinned HOST buffers, H2D of the genome and D2H of the CSR + TF-IDF inside
+the timed region; `roofline` is for the dominant kernel (k_count) from its CUDA-event time; `cpu_baseline` is the C
+oracle (oracle/oracle.c, a port: the reference's own tool chain cannot run) on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "matrix_build_gbp_per_s_k23"
+UNIT = "Gbp/s"
+WORKLOAD = "cfg2_500Mbp_allotetraploid"
+FALLBACK_HBM_GBS = 6650.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--genome-size", type=int, default=0, help="override bases per GPU (testing only)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="override the CPU-baseline sample size in bases")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.proc, self.lines, self.gpu = None, [], gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [s for s in sm if s > 0.5 * max(mx + [1])] or sm
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def workload_params(n_gpus, genome_size_override):
+    from polycracker_b200 import synth
+    cfg = dict(synth.CONFIGS[WORKLOAD])
+    per_gpu = genome_size_override or cfg["genome_size"]
+    params = synth.make_params(cfg["seed"], per_gpu * n_gpus, n_subgenomes=cfg["n_subgenomes"])
+    return cfg, params, per_gpu
+
+
+def algorithmic_bytes_count(n_bases_packed, n_windows):
+    """0.375 B per packed base (2-bit codes + 1-bit mask) + 24 B per k-mer instance (one 12-byte
+    slot read-modify-write)."""
+    return 0.375 * n_bases_packed + 24.0 * n_windows
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_pass(seq, off, names, cfg):
+    """The C restatement of the reference path (oracle/oracle.c) over one in-memory genome; returns seconds."""
+    from oracle import c_oracle
+    from tests import util
+    t0 = time.perf_counter()
+    out = util.c_oracle_path(seq, off, names, cfg["chunk_size"], cfg["k"], cfg["kmer_low_count"])
+    dt = time.perf_counter() - t0
+    return dt, out
+
+
+def cpu_sample(params, target_bases):
+    from polycracker_b200 import synth
+    lay = synth.layout(params)
+    chroms, total = [], 0
+    for c, (_, ln) in enumerate(lay):
+        if total >= target_bases:
+            break
+        chroms.append(c); total += ln
+    seq, off, names = synth.generate(params, chroms=chroms, threads=8)
+    if total > target_bases and len(chroms) == 1:          # a single huge chromosome: cut it
+        seq = seq[:target_bases].copy(); off = np.array([0, target_bases], np.int64)
+    return seq, off, names
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle import c_oracle
+    cfg, params, per_gpu = workload_params(1, args.genome_size)
+    sample_bases = args.cpu_sample or min(per_gpu, 72_000_000)
+    seq, off, names = cpu_sample(params, sample_bases)
+    times = []
+    for i in range(args.warmup + args.steps):
+        dt, out = cpu_reference_pass(seq, off, names, cfg)
+        if i >= args.warmup:
+            times.append(dt)
+    sec = float(np.mean(times))
+    val = len(seq) / sec / 1e9
+    cores = c_oracle.threads()
+    sample = "%d bp (first %d chromosomes of the %s genome), full path count->select->match->CSR->TF-IDF" % (
+        len(seq), len(names), WORKLOAD)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "k": cfg["k"], "chunk_size": cfg["chunk_size"],
+                       "kmer_low_count": cfg["kmer_low_count"], "sample_bases": int(len(seq))},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "oracle/oracle.c (C+OpenMP restatement): the reference's kmercountexact/bbmap/bedtools/py2 chain "
+                    "cannot run here (SURVEY.md F8)"}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_b200_arm(args):
+    import torch
+    from polycracker_b200 import binding, synth
+    from polycracker_b200.pipeline import ChunkLayout, HostArena, run_hot_path
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit("--gpus %d but WORLD_SIZE=%d" % (args.gpus, world))
+    if not torch.cuda.is_available() or binding.device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device: polycracker_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+    cfg, params, per_gpu = workload_params(world, args.genome_size)
+    k, chunk, low = cfg["k"], cfg["chunk_size"], cfg["kmer_low_count"]
+    lay_all = synth.layout(params)
+    names_all = [n for n, _ in lay_all]
+    offs_all = np.concatenate([[0], np.cumsum([l for _, l in lay_all])]).astype(np.int64)
+    genome_bases = int(offs_all[-1])
+    layout = ChunkLayout(names_all, offs_all, chunk)
+
+    ctx = binding.Context(local_rank)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    # ---- stage this rank's share of the genome in pinned host memory -----------------------------------------
+    if world == 1:
+        pinned = torch.empty(genome_bases, dtype=torch.uint8, pin_memory=True)
+        synth.generate(params, out=pinned.numpy(), threads=8)
+        ids = np.arange(layout.n_chunks)
+        begins, ends = layout.chunk_begin_abs, layout.chunk_end_abs
+        local_bases = genome_bases
+    else:
+        from polycracker_b200 import distributed as pcd
+        blocks = pcd.shard_chunks(layout, world)
+        ids, begins, ends, local_bases = pcd.local_buffer_plan(layout, blocks[rank])
+        pinned = torch.empty(max(local_bases, 1), dtype=torch.uint8, pin_memory=True)
+        host = pinned.numpy()
+        need = sorted(set(layout.chunk_seq[ids].tolist()))
+        for c in need:
+            chrom, _, _ = synth.generate(params, chroms=[c], threads=4)
+            for j in np.flatnonzero(layout.chunk_seq[ids] == c).tolist():
+                i = ids[j]
+                host[begins[j]:ends[j]] = chrom[layout.chunk_start[i]:layout.chunk_end[i]]
+            del chrom
+    # device-resident copy for the `value` loop (staged outside the timed region); K1 reads it in place
+    dev_genome = pinned[:max(local_bases, 1)].to(device, non_blocking=False)
+    arena = HostArena()
+
+    def step(resident, fetch):
+        src = dev_genome[:local_bases] if resident else pinned[:local_bases]
+        if world == 1:
+            return run_hot_path(ctx, src, offs_all, names_all, chunk_size=chunk, k=k, kmer_low_count=low,
+                                fetch=fetch, layout=layout, arena=arena)
+        return pcd.run_hot_path_distributed(ctx, layout, None, device, chunk_size=chunk, k=k, kmer_low_count=low,
+                                            fetch=fetch, staged=(src, ids, begins, ends), arena=arena)
+
+    layout.rows()                                          # host-side row order: cached, reused by every step
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(n_steps, resident, fetch, collect=None):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        last = None
+        for _ in range(n_steps):
+            last = step(resident, fetch)
+            if collect is not None:
+                collect.append(ctx.timings())
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, last
+
+    # ---- device-resident throughput (`value`) ------------------------------------------------------------------
+    timed(args.warmup, True, False)
+    ctx.reset_counters()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    per_step_timings = []
+    ms_total, _ = timed(args.steps, True, False, per_step_timings)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.launch_count()
+    ms_per_step = ms_total / args.steps
+    value = genome_bases / (ms_per_step * 1e-3) / 1e9
+    info = ctx.count_info()
+
+    # ---- end to end through the public API with host buffers (`e2e`) -------------------------------------------
+    e2e = None
+    res = None
+    if not args.no_e2e:
+        timed(1, False, True)
+        ms_e2e, res = timed(args.steps, False, True)
+        h2d = local_bases
+        d2h = int(res.indptr.nbytes + res.indices.nbytes + res.data.nbytes + (res.tfidf.nbytes if res.tfidf is not None else 0)
+                  + res.kmer_keys.nbytes)
+        e2e = {"value": genome_bases / (ms_e2e / args.steps * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+               "note": "pinned host genome -> pc_load_sequences (H2D) ... pc_csr_get/pc_tfidf_get (D2H) per step"
+                       + (", per rank" if world > 1 else "")}
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier(); dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel, from the CUDA-event time of its launches ------------------------------
+    peak, peak_src = hbm_peak()
+    stage_ms = {name: float(np.mean([t[name] for t in per_step_timings])) for name in per_step_timings[0]}
+    dom = max((n for n in stage_ms if n not in ("h2d", "d2h")), key=lambda n: stage_ms[n])
+    n_words = sum(int((e - b) // 32 + 1) for b, e in zip(begins.tolist(), ends.tolist()))
+    count_bytes = algorithmic_bytes_count(n_words * 32, info["valid_windows"])
+    count_ms = stage_ms["count"]
+    achieved = count_bytes / (count_ms * 1e-3) / 1e9 if count_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_count", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": count_bytes, "launch_ms": count_ms,
+                "dominant_stage_by_time": dom, "stage_ms": stage_ms,
+                "model": "0.375 B/packed base + 24 B/k-mer instance (SURVEY.md 8d K3), per rank"}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        from oracle import c_oracle
+        sample_bases = args.cpu_sample or min(per_gpu, 72_000_000)
+        s_seq, s_off, s_names = cpu_sample(workload_params(1, args.genome_size)[1], sample_bases)
+        dt, _ = cpu_reference_pass(s_seq, s_off, s_names, cfg)
+        cpu_baseline = {"value": len(s_seq) / dt / 1e9, "unit": UNIT, "cores": c_oracle.threads(), "kind": "port",
+                        "sample": "%d bp (first %d chromosomes of the 1-GPU %s genome), full path, %.1f s wall" % (
+                            len(s_seq), len(s_names), WORKLOAD, dt)}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "genome_bases": genome_bases, "bases_per_gpu": per_gpu, "k": k,
+                       "chunk_size": chunk, "kmer_low_count": low, "n_subgenomes": cfg["n_subgenomes"],
+                       "l2_policy": "inputs larger than L2 (ASCII %.0f MB, count table %.1f GB per rank)" % (
+                           local_bases / 1e6, info["table_bytes"] / 1e9),
+                       "parallelism": "chunks sharded over %d rank(s); all-to-all of (kmer,count) by owner, "
+                                      "all-gather of the repeat set, all-reduce of df" % world},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks,
+            "result": {"distinct_kmers_rank0": info["distinct"], "valid_windows_rank0": info["valid_windows"],
+                       "table_capacity": info["capacity"], "load_factor": info["distinct"] / max(1, info["capacity"]),
+                       "n_selected": (res.stats["n_selected"] if res is not None else None),
+                       "nnz_rank0": (res.stats["nnz"] if res is not None else None),
+                       "rows_rank0": (res.stats["n_rows"] if res is not None else None)}}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier(); dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    sys.exit(run_reference_arm(a) if a.impl == "reference" else run_b200_arm(a))

@@ -128,6 +128,11 @@ int pc_reset_counters(pc_ctx* ctx);
 /* pack one 32-base word on the host with the exact device routine (unit tests) */
 int pc_host_pack_word(const uint8_t* bases, int n, uint64_t* word, uint32_t* nmask);
 int pc_host_canonical(uint64_t kmer, int k, uint64_t* out);
+/* host emulation of K1's layout rules and of the device k-mer roller (unit tests; same inline routines) */
+int pc_host_pack_chunks(const uint8_t* ascii, const int64_t* chunk_begin, const int64_t* chunk_end, int64_t n_chunks,
+                        uint64_t* words, uint32_t* nmask, int64_t* chunk_word0, int64_t cap_words, int64_t* n_words);
+int pc_host_extract(const uint64_t* words, const uint32_t* nmask, int64_t n_words, int k, uint64_t* keys,
+                    uint8_t* valid);
 /* kmer <-> text */
 int pc_kmer_decode(const uint64_t* keys, int64_t n, int k, char* out /* n*k bytes, no separators */);
 int pc_kmer_encode(const char* text, int64_t n, int k, uint64_t* keys /* ~0 when not acgtACGT */);

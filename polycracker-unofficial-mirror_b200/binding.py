@@ -77,6 +77,8 @@ _SIGS = {
     "pc_reset_counters": (C.c_int, [_vp]),
     "pc_host_pack_word": (C.c_int, [_vp, C.c_int, _P(_u64), _P(_u32)]),
     "pc_host_canonical": (C.c_int, [_u64, C.c_int, _P(_u64)]),
+    "pc_host_pack_chunks": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _P(_i64)]),
+    "pc_host_extract": (C.c_int, [_vp, _vp, _i64, C.c_int, _vp, _vp]),
     "pc_kmer_decode": (C.c_int, [_vp, _i64, C.c_int, _vp]),
     "pc_kmer_encode": (C.c_int, [_vp, _i64, C.c_int, _vp]),
     "pc_fasta_scan": (C.c_int, [C.c_char_p, _P(_i64), _P(_i64), _P(_i64)]),
@@ -187,6 +189,28 @@ def host_pack_word(bases):
     w, m = _u64(), _u32()
     check(lib.pc_host_pack_word(b.ctypes.data, len(b), C.byref(w), C.byref(m)), "pc_host_pack_word")
     return w.value, m.value
+
+
+def host_pack_chunks(seq, chunk_begin, chunk_end):
+    seq = np.ascontiguousarray(seq, dtype=np.uint8)
+    cb = np.ascontiguousarray(chunk_begin, dtype=np.int64); ce = np.ascontiguousarray(chunk_end, dtype=np.int64)
+    n = _i64()
+    check(lib.pc_host_pack_chunks(seq.ctypes.data, cb.ctypes.data, ce.ctypes.data, len(cb), None, None, None, 0,
+                                  C.byref(n)), "pc_host_pack_chunks")
+    words = np.zeros(n.value + 1, np.uint64); nmask = np.zeros(n.value + 1, np.uint32)
+    w0 = np.zeros(len(cb) + 1, np.int64)
+    check(lib.pc_host_pack_chunks(seq.ctypes.data, cb.ctypes.data, ce.ctypes.data, len(cb), words.ctypes.data,
+                                  nmask.ctypes.data, w0.ctypes.data, n.value + 1, C.byref(n)), "pc_host_pack_chunks")
+    return words, nmask, w0
+
+
+def host_extract(words, nmask, k):
+    """words/nmask include the trailing guard word.  -> (keys uint64[n*32], valid bool[n*32])"""
+    n = len(words) - 1
+    keys = np.zeros(n * 32, np.uint64); valid = np.zeros(n * 32, np.uint8)
+    check(lib.pc_host_extract(words.ctypes.data, nmask.ctypes.data, n, k, keys.ctypes.data, valid.ctypes.data),
+          "pc_host_extract")
+    return keys, valid.astype(bool)
 
 
 def host_canonical(kmer, k):

@@ -690,6 +690,46 @@ int pc_host_pack_word(const uint8_t* bases, int n, uint64_t* word, uint32_t* nma
     return PC_OK;
 }
 
+// host emulation of k_pack's layout rules with the same SWAR routines (unit tests of the bit tricks)
+int pc_host_pack_chunks(const uint8_t* ascii, const int64_t* chunk_begin, const int64_t* chunk_end, int64_t n_chunks,
+                        uint64_t* words, uint32_t* nmask, int64_t* chunk_word0, int64_t cap_words, int64_t* n_words) {
+    if (!chunk_begin || !chunk_end || !n_words) return fail(PC_EINVAL, "bad pack_chunks arguments");
+    int64_t wsum = 0;
+    for (int64_t c = 0; c < n_chunks; ++c) wsum += (chunk_end[c] - chunk_begin[c]) / 32 + 1;
+    *n_words = wsum;
+    if (!words) return PC_OK;
+    if (cap_words < wsum + 1) return fail(PC_EINVAL, "need %lld words", (long long)(wsum + 1));
+    int64_t w = 0;
+    for (int64_t c = 0; c < n_chunks; ++c) {
+        int64_t len = chunk_end[c] - chunk_begin[c];
+        if (chunk_word0) chunk_word0[c] = w;
+        for (int64_t off = 0; off < len / 32 * 32 + 32; off += 32, ++w) {
+            int64_t rem = len - off;
+            int n = (int)(rem < 0 ? 0 : (rem > 32 ? 32 : rem));
+            int rc = pc_host_pack_word(ascii + chunk_begin[c] + off, n, &words[w], &nmask[w]);
+            if (rc) return rc;
+        }
+    }
+    if (chunk_word0) chunk_word0[n_chunks] = w;
+    words[w] = 0; nmask[w] = 0xFFFFFFFFu;
+    return PC_OK;
+}
+
+// host run of the device Roller over packed words: 32 (canonical k-mer, valid) pairs per word
+int pc_host_extract(const uint64_t* words, const uint32_t* nmask, int64_t n_words, int k, uint64_t* keys, uint8_t* valid) {
+    if (!words || !nmask || !keys || !valid || k < 1 || k > 32) return fail(PC_EINVAL, "bad extract arguments");
+    for (int64_t w = 0; w < n_words; ++w) {
+        pc::Roller r;
+        r.init(words[w], words[w + 1], nmask[w], nmask[w + 1], k);     // word n_words is the guard word
+        for (int b = 0; b < 32; ++b) {
+            keys[w * 32 + b] = r.canonical();
+            valid[w * 32 + b] = r.valid(b) ? 1 : 0;
+            if (b < 31) r.step(b);
+        }
+    }
+    return PC_OK;
+}
+
 int pc_host_canonical(uint64_t kmer, int k, uint64_t* out) {
     if (k < 1 || k > 32 || !out) return fail(PC_EINVAL, "bad canonical arguments");
     uint64_t x = kmer & pc::kmer_mask(k), rc = pc::revcomp_bits(x, k);

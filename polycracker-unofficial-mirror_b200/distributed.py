@@ -1,0 +1,175 @@
+"""Multi-GPU hot path: one process per GPU, torch.distributed (NCCL over NVLink/NVSwitch) for the plumbing.
+
+Sharding: chunks are independent records, so the string-sorted chunk list is cut into `world`
+contiguous blocks balanced by bases; shard-local CSR blocks concatenate into the final row order.  The only global
+coupling is the k-mer count reduction and the broadcast of the selected repeat set:
+
+  1. local count (K1-K3)                    -> pc_export_by_owner: (k-mer, count) grouped by owner = hash % world
+  2. all-to-all of the pairs (sizes first)  -> owners merge-add (k_merge) and threshold (K4) their key range
+  3. all-gather of the selected keys        -> every rank installs the identical sorted repeat set
+  4. local probe + CSR (K5, K6); df all-reduce; TF-IDF (K7) with the global idf
+  5. optional gather of the row blocks to rank 0 (host side; outside the timed region of bench.py)
+
+The reference's only precedent is query-sharded bbmap with file concatenation (polycracker.nf:247-295).
+"""
+import numpy as np
+
+from .pipeline import ChunkLayout, HotPathResult, effective_low_count, fetch_result
+
+
+def shard_chunks(layout, world):
+    """Contiguous blocks of the string-sorted chunk list, balanced by bases.  Returns a list (per rank) of chunk
+    index arrays, each in sorted-name order."""
+    order = sorted(range(layout.n_chunks), key=lambda i: layout.chunk_names[i])
+    lens = (layout.chunk_end - layout.chunk_start)[order] if order else np.zeros(0, np.int64)
+    cum = np.cumsum(lens)
+    total = int(cum[-1]) if len(cum) else 0
+    cuts = [0]
+    for r in range(1, world):
+        cuts.append(int(np.searchsorted(cum, total * r / world, side="left")))
+    cuts.append(len(order))
+    for i in range(1, len(cuts)):
+        cuts[i] = max(cuts[i], cuts[i - 1])
+    order = np.asarray(order, dtype=np.int64)
+    return [order[cuts[r]:cuts[r + 1]] for r in range(world)]
+
+
+def local_buffer_plan(layout, my_chunks):
+    """Byte plan of this rank's private ASCII buffer: its chunks in (sequence, start) order, back to back.
+    Returns (chunk ids in buffer order, begin offsets, end offsets, total bytes)."""
+    ids = np.sort(np.asarray(my_chunks, dtype=np.int64))      # chunk table order == (sequence, start) order
+    lens = layout.chunk_end[ids] - layout.chunk_start[ids]
+    ends = np.cumsum(lens)
+    begins = ends - lens
+    return ids, begins, ends, int(ends[-1]) if len(ends) else 0
+
+
+def _all_to_all_v(dist, send, send_counts, torch):
+    """Variable-size all-to-all of a 1-D tensor: exchange sizes first, then the payload (one
+    ncclGroupStart{Send/Recv} under NCCL)."""
+    world = dist.get_world_size()
+    sc = torch.tensor(send_counts, dtype=torch.int64, device=send.device)
+    rc = torch.empty(world, dtype=torch.int64, device=send.device)
+    dist.all_to_all_single(rc, sc)
+    recv_counts = rc.tolist()
+    recv = torch.empty(int(sum(recv_counts)), dtype=send.dtype, device=send.device)
+    dist.all_to_all_single(recv, send, output_split_sizes=recv_counts, input_split_sizes=list(send_counts))
+    return recv, recv_counts
+
+
+def _all_gather_v(dist, local, torch):
+    """Variable-size all-gather of a 1-D tensor: counts first, then padded payloads."""
+    world = dist.get_world_size()
+    n = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
+    ns = [torch.empty(1, dtype=torch.int64, device=local.device) for _ in range(world)]
+    dist.all_gather(ns, n)
+    counts = [int(x.item()) for x in ns]
+    m = max(counts + [1])
+    pad = torch.zeros(m, dtype=local.dtype, device=local.device)
+    pad[:local.numel()] = local
+    outs = [torch.empty(m, dtype=local.dtype, device=local.device) for _ in range(world)]
+    dist.all_gather(outs, pad)
+    return torch.cat([o[:c] for o, c in zip(outs, counts)]), counts
+
+
+def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000, k=23, kmer_low_count=100,
+                             high_bool=0, kmer_high_count=2000000, sampling_sensitivity=1, remove_non_chunk=1,
+                             min_chunk_threshold=0, min_chunk_size=0, prefilter=0, tfidf=True, fetch=True,
+                             staged=None, arena=None):
+    """One rank's share of the hot path.  `layout` describes the WHOLE genome (every rank builds the same one from
+    names + lengths); `fetch_chunks(ids, begins, ends, total)` returns this rank's ASCII buffer (uint8, host numpy /
+    pinned torch / CUDA torch) laid out by local_buffer_plan; `staged` short-circuits it with a prebuilt
+    (buffer, ids, begins, ends).  Returns a HotPathResult for the local row block (stats carry the global sizes).
+    """
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    blocks = shard_chunks(layout, world)
+    if staged is None:
+        ids, begins, ends, total = local_buffer_plan(layout, blocks[rank])
+        buf = fetch_chunks(ids, begins, ends, total)
+    else:
+        buf, ids, begins, ends = staged
+    # global row universe (host integer logic, identical on every rank) and this rank's slice of it
+    scaffolds_all, chunk_row_all = layout.rows(remove_non_chunk, min_chunk_threshold, min_chunk_size, prefilter)
+    my_rows_global = chunk_row_all[ids]
+    kept = np.flatnonzero(my_rows_global >= 0)
+    row0 = int(my_rows_global[kept].min()) if len(kept) else 0
+    local_chunk_row = np.where(my_rows_global >= 0, my_rows_global - row0, -1).astype(np.int32)
+    n_local_rows = len(kept)
+    assert n_local_rows == 0 or int(my_rows_global[kept].max()) - row0 + 1 == n_local_rows, "row block not contiguous"
+
+    # 1. local count
+    ctx.load_sequences(buf, begins, ends)
+    ctx.count(k)
+    info = ctx.count_info()
+    d_local = info["distinct"]
+    keys_t = torch.empty(max(d_local, 1), dtype=torch.int64, device=device)
+    counts_t = torch.empty(max(d_local, 1), dtype=torch.int32, device=device)
+    offs = ctx.export_by_owner(world, keys_t, counts_t) if d_local else np.zeros(world + 1, np.int64)
+    send_counts = np.diff(offs).tolist()
+    # 2. all-to-all, owners merge + threshold
+    rkeys, _ = _all_to_all_v(dist, keys_t[:d_local], send_counts, torch)
+    rcounts, _ = _all_to_all_v(dist, counts_t[:d_local], send_counts, torch)
+    del keys_t, counts_t
+    ctx.merge_counts(rkeys, rcounts, rkeys.numel(), k, fresh=True)
+    owner_info = ctx.count_info()
+    del rkeys, rcounts
+    n_owner_sel = ctx.select(effective_low_count(k, kmer_low_count), kmer_high_count, bool(high_bool), 1)
+    sel_local = torch.empty(max(n_owner_sel, 1), dtype=torch.int64, device=device)
+    if n_owner_sel:
+        ctx.selected_into(sel_local)
+    # 3. all-gather the repeat set; every rank sorts it to the same column order
+    sel_all, _ = _all_gather_v(dist, sel_local[:n_owner_sel], torch)
+    if sampling_sensitivity > 1 and sel_all.numel():
+        # sampling is defined on the globally sorted survivor list (pc_select semantics)
+        sel_all = torch.sort(sel_all.view(torch.int64) ^ (-2**63))[0] ^ (-2**63)       # unsigned order
+        sel_all = sel_all[::int(sampling_sensitivity)].contiguous()
+    n_sel = ctx.set_selected(sel_all, k, n=sel_all.numel())
+    # 4. local matrix, global idf
+    nnz = ctx.build_matrix(local_chunk_row, n_local_rows)
+    df_t = torch.zeros(max(n_sel, 1), dtype=torch.int32, device=device)
+    if n_sel:
+        ctx.df_into(df_t)
+    dist.all_reduce(df_t, op=dist.ReduceOp.SUM)
+    if tfidf:
+        ctx.tfidf(len(scaffolds_all), df_t if n_sel else None)
+    t = torch.tensor([info["valid_windows"], owner_info["distinct"], nnz], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    stats = dict(info)
+    stats.update(n_selected=n_sel, nnz=nnz, n_rows=n_local_rows, n_rows_global=len(scaffolds_all), row0=row0,
+                 valid_windows_global=int(t[0]), distinct_global=int(t[1]), nnz_global=int(t[2]),
+                 owner_distinct=owner_info["distinct"], local_bases=int(ends[-1]) if len(ends) else 0)
+    scaffolds = scaffolds_all[row0:row0 + n_local_rows]
+    if not fetch:
+        return HotPathResult(layout, k, scaffolds, np.empty(0, np.uint64), None, None, None, None, None, stats,
+                             ctx.timings())
+    return fetch_result(ctx, layout, k, scaffolds, n_sel, nnz, tfidf, stats, arena, df=df_t[:n_sel].cpu().numpy())
+
+
+def gather_rows(result, dst=0):
+    """Concatenate the shard-local CSR blocks on rank `dst` (host side, gather_object).  Returns the global
+    HotPathResult on dst, None elsewhere."""
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    payload = (result.stats["row0"], result.scaffolds, result.indptr, result.indices, result.data, result.tfidf)
+    gathered = [None] * world if rank == dst else None
+    dist.gather_object(payload, gathered, dst=dst)
+    if rank != dst:
+        return None
+    gathered.sort(key=lambda p: (p[0], len(p[1]) == 0))
+    scaffolds, indptr, indices, data, tf = [], [np.zeros(1, np.int64)], [], [], []
+    base = 0
+    for _row0, sc, ip, ix, dt, tv in gathered:
+        scaffolds += sc
+        indptr.append(ip[1:] + base)
+        base += int(ip[-1])
+        indices.append(ix); data.append(dt)
+        if tv is not None:
+            tf.append(tv)
+    stats = dict(result.stats)
+    stats.update(n_rows=len(scaffolds), nnz=base)
+    return HotPathResult(result.layout, result.k, scaffolds, result.kmer_keys, np.concatenate(indptr),
+                         np.concatenate(indices) if indices else np.zeros(0, np.int32),
+                         np.concatenate(data) if data else np.zeros(0, np.float32),
+                         np.concatenate(tf) if tf else None, result.df, stats, result.timings)

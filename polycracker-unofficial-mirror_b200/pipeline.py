@@ -26,6 +26,7 @@ class ChunkLayout:
         self.chunk_names = ["%s_%d_%d" % (self.seq_names[s], a, b)
                             for s, a, b in zip(self.chunk_seq.tolist(), self.chunk_start.tolist(),
                                                self.chunk_end.tolist())]
+        self._rows_cache = {}
 
     @property
     def n_chunks(self):
@@ -44,6 +45,10 @@ class ChunkLayout:
     def rows(self, remove_non_chunk=1, min_chunk_threshold=0, min_chunk_size=0, prefilter=0, keep_names=None):
         """Row universe after the filter of polycracker.py:322-327 -> (scaffolds, chunk_row int32).
         keep_names (optional set) restricts rows further (a correspondence.bed that was pre-filtered)."""
+        key = (bool(remove_non_chunk), bool(min_chunk_threshold), int(min_chunk_size), int(prefilter),
+               None if keep_names is None else frozenset(keep_names))
+        if key in self._rows_cache:
+            return self._rows_cache[key]
         clen = np.abs(self.chunk_end - self.chunk_start)
         if remove_non_chunk and prefilter == 0:
             keep = clen == self.chunk_size
@@ -55,7 +60,8 @@ class ChunkLayout:
         idx.sort(key=lambda i: self.chunk_names[i])
         chunk_row = np.full(self.n_chunks, -1, np.int32)
         chunk_row[idx] = np.arange(len(idx), dtype=np.int32)
-        return [self.chunk_names[i] for i in idx], chunk_row
+        self._rows_cache[key] = ([self.chunk_names[i] for i in idx], chunk_row)
+        return self._rows_cache[key]
 
 
 @dataclass
@@ -93,6 +99,28 @@ class HotPathResult:
                                np.asarray(self.indptr).astype(idt, copy=False)), shape=self.shape)
 
 
+class HostArena:
+    """Reusable page-locked host buffers for the D2H of results (a pageable numpy target would make the copy
+    synchronous and several times slower).  Falls back to plain numpy when torch/CUDA is unavailable."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, name, n, dtype):
+        dtype = np.dtype(dtype)
+        need = max(int(n), 1) * dtype.itemsize
+        buf = self._bufs.get(name)
+        if buf is None or buf.nbytes < need:
+            try:
+                import torch
+                t = torch.empty(int(need * 1.25) + 64, dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+                buf = t.numpy()                            # the view keeps the pinned tensor alive
+            except Exception:
+                buf = np.empty(int(need * 1.25) + 64, np.uint8)
+            self._bufs[name] = buf
+        return buf[:int(n) * dtype.itemsize].view(dtype)
+
+
 def effective_low_count(k, kmer_low_count):
     """kmer2Fasta only ever sees what writeKmerCount dumped: `mincount=3` for k <= 31 (polycracker.py:199),
     everything for k > 31 (jellyfish dump without -L, polycracker.py:203)."""
@@ -101,7 +129,7 @@ def effective_low_count(k, kmer_low_count):
 
 def run_hot_path(ctx, seq, seq_offsets, names, chunk_size=75000, k=23, kmer_low_count=100, high_bool=0,
                  kmer_high_count=2000000, sampling_sensitivity=1, remove_non_chunk=1, min_chunk_threshold=0,
-                 min_chunk_size=0, prefilter=0, tfidf=True, table_capacity=0, fetch=True, layout=None):
+                 min_chunk_size=0, prefilter=0, tfidf=True, table_capacity=0, fetch=True, layout=None, arena=None):
     """One pass of the hot path on one GPU.
 
     seq: newline-free ASCII bases, numpy uint8 (pageable or pinned) or a torch uint8 tensor (CPU pinned or CUDA).
@@ -122,8 +150,33 @@ def run_hot_path(ctx, seq, seq_offsets, names, chunk_size=75000, k=23, kmer_low_
     if not fetch:
         return HotPathResult(layout, k, scaffolds, np.empty(0, np.uint64), None, None, None, None, None, stats,
                              ctx.timings())
-    keys = ctx.selected(n_sel)
-    indptr, indices, data = ctx.csr(len(scaffolds), nnz)
-    tf = ctx.tfidf_values(nnz) if tfidf else None
-    df = ctx.df(n_sel)
+    return fetch_result(ctx, layout, k, scaffolds, n_sel, nnz, tfidf, stats, arena)
+
+
+def fetch_result(ctx, layout, k, scaffolds, n_sel, nnz, tfidf, stats, arena=None, df=None):
+    """D2H of the repeat set, CSR and TF-IDF values (into page-locked buffers when an arena is given)."""
+    n_rows = len(scaffolds)
+    if arena is None:
+        keys = ctx.selected(n_sel)
+        indptr, indices, data = ctx.csr(n_rows, nnz)
+        tf = ctx.tfidf_values(nnz) if tfidf else None
+        if df is None:
+            df = ctx.df(n_sel)
+    else:
+        keys = arena.get("keys", n_sel, np.uint64)
+        indptr = arena.get("indptr", n_rows + 1, np.int64)
+        indices = arena.get("indices", nnz, np.int32)
+        data = arena.get("data", nnz, np.float32)
+        if n_sel:
+            ctx.selected_into(keys)
+        ctx.csr_into(indptr, indices if nnz else None, data if nnz else None)
+        tf = None
+        if tfidf:
+            tf = arena.get("tfidf", nnz, np.float32)
+            if nnz:
+                ctx.tfidf_into(tf)
+        if df is None:
+            df = arena.get("df", n_sel, np.int32)
+            if n_sel:
+                ctx.df_into(df)
     return HotPathResult(layout, k, scaffolds, keys, indptr, indices, data, tf, df, stats, ctx.timings())

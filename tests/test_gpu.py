@@ -1,0 +1,265 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Every check goes through the C ABI
+(polycracker_b200.binding -> libpolycracker_b200.so) and compares against the CPU checkers in oracle/.
+
+Bars (north_star): k-mer counts, repeat set, CSR matrix bit-exact; TF-IDF within 1e-6 relative (fp32).
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+from oracle import c_oracle, py_oracle
+from polycracker_b200 import binding, synth
+from polycracker_b200.pipeline import ChunkLayout, run_hot_path
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    if binding.device_count() == 0:
+        pytest.fail("no CUDA device: -m gpu tests need the B200 (there is no CPU fallback to test)")
+    c = binding.Context(0)
+    yield c
+    c.close()
+
+
+def _check_against_c_oracle(ctx, seq, off, names, chunk, k, low, **kw):
+    res = run_hot_path(ctx, seq, off, names, chunk_size=chunk, k=k, kmer_low_count=low, **kw)
+    want = util.c_oracle_path(seq, off, names, chunk, k, low,
+                              high_bool=kw.get("high_bool", 0), high=kw.get("kmer_high_count", 2000000),
+                              sampling=kw.get("sampling_sensitivity", 1),
+                              remove_non_chunk=kw.get("remove_non_chunk", 1),
+                              min_chunk_threshold=kw.get("min_chunk_threshold", 0),
+                              min_chunk_size=kw.get("min_chunk_size", 0))
+    assert res.stats["valid_windows"] == want["n_windows"]
+    assert res.stats["distinct"] == len(want["keys"])
+    assert res.kmer_keys.tolist() == want["sel"].tolist()
+    assert res.scaffolds == want["scaffolds"]
+    assert np.array_equal(res.indptr, want["indptr"])
+    assert np.array_equal(res.indices, want["indices"])
+    assert np.array_equal(res.data, want["data"])
+    util.assert_tfidf_close(res.tfidf, want["tfidf"])
+    return res, want
+
+
+def test_known_answer_survey_8c(ctx):
+    seq, off, names = util.from_sequences([("s1", "ACGTACGTAC")])
+    res = run_hot_path(ctx, seq, off, names, chunk_size=5, k=3, kmer_low_count=3)
+    assert res.kmers() == ["ACG", "GTA"] and res.kmers("max") == ["CGT", "TAC"]
+    assert res.scaffolds == ["s1_0_5", "s1_5_10"]
+    assert res.csr_matrix().toarray().tolist() == [[2, 1], [1, 2]]
+    csc = res.csr_matrix().tocsc()
+    assert csc.indptr.tolist() == [0, 2, 4] and csc.indices.tolist() == [0, 1, 0, 1] and csc.data.tolist() == [2, 1, 1, 2]
+    np.testing.assert_allclose(res.csr_matrix("tfidf").toarray(), np.array([[2, 1], [1, 2]]) / np.sqrt(5), rtol=1e-6)
+    res = run_hot_path(ctx, seq, off, names, chunk_size=5, k=3, kmer_low_count=4)
+    assert res.shape == (2, 0) and len(res.indices) == 0 and res.indptr.tolist() == [0, 0, 0]
+
+
+@pytest.mark.parametrize("chunk", [997, 1024, 75000])
+def test_pack_matches_host_layout(ctx, chunk):
+    p = synth.small_params(seed=21, genome_size=300_000, n_fraction=0.02)
+    seq, off, names = synth.generate(p)
+    lay = ChunkLayout(names, off, chunk)
+    ctx.load_sequences(seq, lay.chunk_begin_abs, lay.chunk_end_abs)
+    words, nmask, w0 = ctx.packed()
+    hw, hm, h0 = binding.host_pack_chunks(seq, lay.chunk_begin_abs, lay.chunk_end_abs)
+    assert np.array_equal(w0, h0)
+    assert np.array_equal(words, hw[:-1]) and np.array_equal(nmask, hm[:-1])
+
+
+def test_pack_every_byte_phase(ctx):
+    # chunk starts at every offset mod 16 (the 128-bit load realignment) and every length mod 32
+    rng = np.random.default_rng(5)
+    seq = np.frombuffer(b"ACGTNacgtn", dtype=np.uint8)[rng.integers(0, 10, 5000)].copy()
+    begins = np.arange(0, 4000, 101, dtype=np.int64)
+    ends = begins + (np.arange(len(begins)) % 67) + 30
+    ctx.load_sequences(seq, begins, ends)
+    words, nmask, w0 = ctx.packed()
+    hw, hm, h0 = binding.host_pack_chunks(seq, begins, ends)
+    assert np.array_equal(words, hw[:-1]) and np.array_equal(nmask, hm[:-1]) and np.array_equal(w0, h0)
+
+
+@pytest.mark.parametrize("k", [1, 2, 5, 11, 16, 23, 26, 31, 32])
+def test_counts_bit_exact(ctx, k):
+    p = synth.small_params(seed=100 + k, genome_size=400_000, n_fraction=0.01)
+    seq, off, names = synth.generate(p)
+    lay = ChunkLayout(names, off, 5000)
+    ctx.load_sequences(seq, lay.chunk_begin_abs, lay.chunk_end_abs)
+    ctx.count(k)
+    keys, counts = ctx.dump_counts(1)
+    order = np.argsort(keys)
+    want_keys, want_counts, n_windows = c_oracle.count(seq, lay.chunk_begin_abs, lay.chunk_end_abs, k)
+    assert np.array_equal(keys[order], want_keys)
+    assert np.array_equal(counts[order].astype(np.uint64), want_counts)
+    info = ctx.count_info()
+    assert info["valid_windows"] == n_windows and info["distinct"] == len(want_keys)
+    # the .kcount dump: mincount=3 (polycracker.py:199)
+    k3, c3 = ctx.dump_counts(3)
+    assert sorted(k3.tolist()) == want_keys[want_counts >= 3].tolist()
+
+
+def test_small_table_reports_overflow_not_garbage(ctx):
+    p = synth.small_params(seed=9, genome_size=100_000)
+    seq, off, names = synth.generate(p)
+    lay = ChunkLayout(names, off, 5000)
+    ctx.load_sequences(seq, lay.chunk_begin_abs, lay.chunk_end_abs)
+    with pytest.raises(binding.PolycrackerError, match="overflow"):
+        ctx.count(23, capacity=1000)
+    with pytest.raises(binding.PolycrackerError, match="unsupported"):
+        ctx.count(33)
+
+
+def test_full_path_vs_literal_oracle(ctx):
+    p = synth.small_params(seed=31, genome_size=30_000, n_chrom=2)
+    seq, off, names = synth.generate(p)
+    for k, low in ((5, 8), (23, 4), (32, 2)):
+        lit = py_oracle.run_path(util.to_sequences(seq, off, names), 2500, k, low)
+        res = run_hot_path(ctx, seq, off, names, chunk_size=2500, k=k, kmer_low_count=low)
+        assert res.kmers() == lit["kmers"] and res.scaffolds == lit["scaffolds"]
+        want = sps.csr_matrix(lit["matrix"]); want.sort_indices()
+        assert np.array_equal(res.indptr, want.indptr) and np.array_equal(res.indices, want.indices)
+        assert np.array_equal(res.data, want.data)
+        got_csc = res.csr_matrix().tocsc()                 # what clusteringMatrix.npz holds
+        assert np.array_equal(got_csc.indptr, lit["matrix"].indptr) and np.array_equal(got_csc.indices, lit["matrix"].indices)
+        assert np.array_equal(got_csc.data, lit["matrix"].data)
+        util.assert_tfidf_close(res.tfidf, lit["tfidf"].data)      # sklearn TfidfTransformer itself
+        assert want.nnz > 0
+
+
+@pytest.mark.parametrize("k,low,chunk", [(23, 10, 75000), (26, 30, 50000), (15, 50, 10000), (31, 5, 33333), (32, 4, 75000)])
+def test_full_path_vs_c_oracle(ctx, k, low, chunk):
+    p = synth.small_params(seed=40 + k, genome_size=3_000_000, n_shared_families=6, n_specific_families=8,
+                           max_family_len=1500)
+    seq, off, names = synth.generate(p)
+    res, want = _check_against_c_oracle(ctx, seq, off, names, chunk, k, low)
+    assert len(want["sel"]) > 100 and len(want["data"]) > 1000
+    # sklearn on the GPU-built matrix (the reference's own downstream call, polycracker.py:395-396)
+    from sklearn.feature_extraction.text import TfidfTransformer
+    sk = sps.csr_matrix(TfidfTransformer().fit_transform(res.csr_matrix().tocsc()))
+    sk.sort_indices()
+    util.assert_tfidf_close(res.tfidf, sk.data)
+
+
+def test_thresholds_sampling_and_row_filters(ctx):
+    p = synth.small_params(seed=77, genome_size=1_000_000)
+    seq, off, names = synth.generate(p)
+    _check_against_c_oracle(ctx, seq, off, names, 20000, 23, 10, high_bool=1, kmer_high_count=40)
+    _check_against_c_oracle(ctx, seq, off, names, 20000, 23, 10, sampling_sensitivity=7)
+    _check_against_c_oracle(ctx, seq, off, names, 20000, 23, 1)                          # mincount=3 floor
+    _check_against_c_oracle(ctx, seq, off, names, 20000, 23, 10, remove_non_chunk=0)     # tails are rows too
+    _check_against_c_oracle(ctx, seq, off, names, 20000, 23, 10, remove_non_chunk=0, min_chunk_threshold=1,
+                            min_chunk_size=15000)
+    res, _ = _check_against_c_oracle(ctx, seq, off, names, 20000, 23, 10**6)             # nothing selected
+    assert res.shape[1] == 0
+
+
+def test_degenerate_inputs(ctx):
+    # all N, chunk shorter than k, one-base tail, empty sequence in the middle, no rows at all
+    seqs = [("n", "N" * 100), ("short", "ACGTACG"), ("e", ""), ("r", "ACGTTGCA" * 20 + "A")]
+    seq, off, names = util.from_sequences(seqs)
+    for chunk, kw in ((40, {}), (40, dict(remove_non_chunk=0)), (1000, {}), (1000, dict(remove_non_chunk=0))):
+        lit = py_oracle.run_path(seqs, chunk, 8, 3, **kw)
+        res = run_hot_path(ctx, seq, off, names, chunk_size=chunk, k=8, kmer_low_count=3, **kw)
+        assert res.kmers() == lit["kmers"] and res.scaffolds == lit["scaffolds"]
+        want = sps.csr_matrix(lit["matrix"]); want.sort_indices()
+        assert np.array_equal(res.indptr, want.indptr) and np.array_equal(res.indices, want.indices)
+        assert np.array_equal(res.data, want.data)
+        util.assert_tfidf_close(res.tfidf, sps.csr_matrix(lit["tfidf"]).data)
+    seq, off, names = util.from_sequences([("e", "")])
+    res = run_hot_path(ctx, seq, off, names, chunk_size=10, k=5, kmer_low_count=3)
+    assert res.shape == (0, 0)
+
+
+def test_low_complexity_heavy_hitters(ctx):
+    # poly-A / tandem repeats: thousands of atomics on one slot, long runs in the row sort
+    seqs = [("a", "A" * 70000), ("t", "T" * 70000), ("at", "AT" * 35000), ("mix", ("ACGTTGCAAC" * 7000))]
+    seq, off, names = util.from_sequences(seqs)
+    _check_against_c_oracle(ctx, seq, off, names, 10000, 23, 3)
+    _check_against_c_oracle(ctx, seq, off, names, 70000, 32, 3)
+
+
+def test_external_repeat_set(ctx):
+    """blast_kmers as a separately invoked stage: the repeat set comes from a k-mer FASTA, in either orientation,
+    unsorted, with duplicates."""
+    p = synth.small_params(seed=55, genome_size=500_000)
+    seq, off, names = synth.generate(p)
+    k, chunk = 23, 20000
+    want = util.c_oracle_path(seq, off, names, chunk, k, 10)
+    lay = ChunkLayout(names, off, chunk)
+    scaffolds, chunk_row = lay.rows()
+    ctx.load_sequences(seq, lay.chunk_begin_abs, lay.chunk_end_abs)
+    kmers = binding.kmer_decode(want["sel"], k)
+    shuffled = [py_oracle.revcomp(km) if i % 2 else km for i, km in enumerate(kmers)][::-1] + kmers[:5]
+    n = ctx.set_selected(binding.kmer_encode(shuffled, k), k)
+    assert n == len(kmers) and ctx.selected(n).tolist() == want["sel"].tolist()
+    nnz = ctx.build_matrix(chunk_row, len(scaffolds))
+    indptr, indices, data = ctx.csr(len(scaffolds), nnz)
+    assert np.array_equal(indptr, want["indptr"]) and np.array_equal(indices, want["indices"]) and np.array_equal(data, want["data"])
+
+
+def test_owner_partitioned_counts_two_ranks_on_one_gpu(ctx):
+    """The multi-GPU count exchange with both ranks emulated on one device: shard by chromosome,
+    count locally, export by owner, merge at the owners, select, gather."""
+    import torch
+    p = synth.small_params(seed=66, genome_size=800_000, n_chrom=2)
+    seq, off, names = synth.generate(p)
+    k, chunk, low, world = 23, 20000, 10, 2
+    want = util.c_oracle_path(seq, off, names, chunk, k, low)
+    shards = [[0, 2], [1, 3]]
+    exported = []
+    for r in range(world):
+        s_seq = np.concatenate([seq[off[c]:off[c + 1]] for c in shards[r]])
+        s_off = np.concatenate([[0], np.cumsum([off[c + 1] - off[c] for c in shards[r]])])
+        lay = ChunkLayout([names[c] for c in shards[r]], s_off, chunk)
+        ctx.load_sequences(s_seq, lay.chunk_begin_abs, lay.chunk_end_abs)
+        ctx.count(k)
+        d = ctx.count_info()["distinct"]
+        keys_t = torch.empty(d, dtype=torch.int64, device="cuda"); counts_t = torch.empty(d, dtype=torch.int32, device="cuda")
+        offs = ctx.export_by_owner(world, keys_t, counts_t)
+        assert offs[-1] == d
+        exported.append((keys_t, counts_t, offs))
+    selected = []
+    total_distinct = 0
+    for owner in range(world):
+        ks = torch.cat([exported[r][0][exported[r][2][owner]:exported[r][2][owner + 1]] for r in range(world)])
+        cs = torch.cat([exported[r][1][exported[r][2][owner]:exported[r][2][owner + 1]] for r in range(world)])
+        ctx.merge_counts(ks, cs, ks.numel(), k, fresh=True)
+        total_distinct += ctx.count_info()["distinct"]
+        n = ctx.select(low)
+        selected.append(ctx.selected(n))
+    assert total_distinct == len(want["keys"])
+    union = np.sort(np.concatenate(selected))
+    assert union.tolist() == want["sel"].tolist()
+
+
+def test_properties_at_scale(ctx):
+    """Size-independent invariants on a 60 Mbp genome (the oracle would take minutes here): column sums over all
+    chunks equal the global counts, row sums bounded by windows, unit L2 rows, df bounds."""
+    p = synth.make_params(20260002, 60_000_000)
+    seq, off, names = synth.generate(p, threads=8)
+    k, chunk, low = 23, 75000, 30
+    res = run_hot_path(ctx, seq, off, names, chunk_size=chunk, k=k, kmer_low_count=low, remove_non_chunk=0)
+    m = res.csr_matrix()
+    assert res.shape[1] > 1000 and m.nnz > 10000
+    keys, counts = ctx.dump_counts(low)
+    order = np.argsort(keys)
+    assert np.array_equal(keys[order], res.kmer_keys)                      # repeat set == thresholded dump
+    assert np.array_equal(np.asarray(m.sum(axis=0)).ravel().astype(np.int64), counts[order].astype(np.int64))
+    lens = res.layout.chunk_end - res.layout.chunk_start
+    row_len = dict(zip(res.layout.chunk_names, lens.tolist()))
+    rs = np.asarray(m.sum(axis=1)).ravel()
+    assert all(rs[i] <= max(0, row_len[s] - k + 1) for i, s in enumerate(res.scaffolds))
+    assert np.all(np.diff(res.kmer_keys.astype(np.uint64)) > 0)            # sorted, unique
+    for r in range(0, m.shape[0], 97):                                     # sorted column ids inside rows
+        seg = res.indices[res.indptr[r]:res.indptr[r + 1]]
+        assert np.all(np.diff(seg) > 0)
+    assert np.array_equal(res.df, np.bincount(res.indices, minlength=res.shape[1]))
+    t = res.csr_matrix("tfidf")
+    norms = np.sqrt(np.asarray(t.multiply(t).sum(axis=1)).ravel())
+    nz = np.diff(res.indptr) > 0
+    np.testing.assert_allclose(norms[nz], 1.0, rtol=1e-6)
+    assert np.all(norms[~nz] == 0)
+    # and the C oracle on a slice of the same genome (first 2 chromosomes), bit-exact
+    cut = int(off[2])
+    _check_against_c_oracle(ctx, seq[:cut].copy(), off[:3], names[:2], chunk, k, 5)
