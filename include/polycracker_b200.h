@@ -123,6 +123,10 @@ int pc_tfidf_get(pc_ctx* ctx, float* data, int loc);                   /* nnz va
 int pc_timings(pc_ctx* ctx, float ms[PC_N_STAGES]);
 int pc_launch_count(pc_ctx* ctx, int64_t* launches);
 int pc_reset_counters(pc_ctx* ctx);
+/* kernel tunables (measurement / tuning only; defaults are the shipped configuration):
+ * count_batch {4,8,16}, count_minb {2,3,4}, count_mode {0 load-first, 1 prefetch-ahead, 2 CAS-first},
+ * table_load_pct (5..95), l2_fetch_granularity {32,64,128}. */
+int pc_tune(pc_ctx* ctx, const char* key, int64_t value);
 
 /* ---- host helpers (no GPU) -------------------------------------------------------------------------------- */
 /* pack one 32-base word on the host with the exact device routine (unit tests) */

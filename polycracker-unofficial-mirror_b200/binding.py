@@ -75,6 +75,7 @@ _SIGS = {
     "pc_timings": (C.c_int, [_vp, _vp]),
     "pc_launch_count": (C.c_int, [_vp, _P(_i64)]),
     "pc_reset_counters": (C.c_int, [_vp]),
+    "pc_tune": (C.c_int, [_vp, C.c_char_p, _i64]),
     "pc_host_pack_word": (C.c_int, [_vp, C.c_int, _P(_u64), _P(_u32)]),
     "pc_host_canonical": (C.c_int, [_u64, C.c_int, _P(_u64)]),
     "pc_host_pack_chunks": (C.c_int, [_vp, _vp, _vp, _i64, _vp, _vp, _vp, _i64, _P(_i64)]),
@@ -382,6 +383,10 @@ class Context:
         n = _i64()
         check(lib.pc_launch_count(self._h, C.byref(n)), "pc_launch_count")
         return n.value
+
+    def tune(self, **kw):
+        for key, value in kw.items():
+            check(lib.pc_tune(self._h, key.encode(), int(value)), "pc_tune(%s)" % key)
 
     def reset_counters(self):
         check(lib.pc_reset_counters(self._h), "pc_reset_counters")

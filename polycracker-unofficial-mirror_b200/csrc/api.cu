@@ -84,6 +84,10 @@ struct pc_ctx {
     DevBuf<int32_t> d_indices; DevBuf<float> d_data, d_idf, d_tfidf; DevBuf<int> d_df, d_df_global;
     int64_t n_rows = 0, nnz = 0;
     bool built = false, tfidf_done = false;
+
+    // tunables (pc_tune)
+    int count_batch = 8, count_minb = 2, count_mode = 0;
+    double table_load = 0.6;
 };
 
 namespace {
@@ -347,6 +351,32 @@ static int fetch_stats(pc_ctx* c) {
     return PC_OK;
 }
 
+#define COUNT_CASE(B, M, MODE)                                                                               \
+    if (c->count_batch == B && c->count_minb == M && c->count_mode == MODE) {                                \
+        LAUNCH(c, (pc::k_count<B, M, MODE>), blocks_for(c->n_words, 256), 256, c->words.p, c->nmask.p,       \
+               c->n_words, c->k, c->table.p, c->capacity, c->d_stats.p);                                      \
+        return PC_OK;                                                                                        \
+    }
+static int launch_count(pc_ctx* c) {
+    COUNT_CASE(8, 2, 0) COUNT_CASE(8, 3, 0) COUNT_CASE(8, 4, 0) COUNT_CASE(16, 2, 0) COUNT_CASE(4, 4, 0)
+    COUNT_CASE(8, 2, 1) COUNT_CASE(8, 3, 1) COUNT_CASE(8, 4, 1) COUNT_CASE(16, 2, 1) COUNT_CASE(4, 4, 1)
+    COUNT_CASE(8, 2, 2) COUNT_CASE(8, 3, 2) COUNT_CASE(8, 4, 2) COUNT_CASE(16, 2, 2) COUNT_CASE(4, 4, 2)
+    return fail(PC_EINVAL, "no k_count instantiation for batch=%d minb=%d mode=%d", c->count_batch, c->count_minb, c->count_mode);
+}
+
+int pc_tune(pc_ctx* c, const char* key, int64_t value) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!key) return fail(PC_EINVAL, "null key");
+    std::string k(key);
+    if (k == "count_batch") c->count_batch = (int)value;
+    else if (k == "count_minb") c->count_minb = (int)value;
+    else if (k == "count_mode") c->count_mode = (int)value;
+    else if (k == "table_load_pct") c->table_load = std::min(0.95, std::max(0.05, value / 100.0));
+    else if (k == "l2_fetch_granularity") CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
+    else return fail(PC_EINVAL, "unknown tunable %s", key);
+    return PC_OK;
+}
+
 int pc_count(pc_ctx* c, int k, int64_t capacity) {
     int rc = use_device(c); if (rc) return rc;
     if (!c->loaded) return fail(PC_ESTATE, "pc_count before pc_load_sequences");
@@ -358,14 +388,14 @@ int pc_count(pc_ctx* c, int k, int64_t capacity) {
         // distinct canonical k-mers <= windows and <= 4^k (palindrome-aware bound not needed: it is an upper bound)
         double space = k >= 31 ? 9.3e18 : (double)(1ull << (2 * k));
         double bound = std::min((double)windows, space);
-        capacity = (int64_t)(bound / 0.6) + 1024;
+        capacity = (int64_t)(bound / c->table_load) + 1024;
     }
     rc = table_prepare(c, k, capacity); if (rc) return rc;
     {
         StageTimer t(c, ST_COUNT);
-        if (c->n_words > 0)
-            LAUNCH(c, (pc::k_count<8>), blocks_for(c->n_words, 256), 256, c->words.p, c->nmask.p, c->n_words, k,
-                   c->table.p, c->capacity, c->d_stats.p);
+        if (c->n_words > 0) {
+            rc = launch_count(c); if (rc) return rc;
+        }
     }
     rc = fetch_stats(c); if (rc) return rc;
     c->counted = true;

@@ -187,8 +187,15 @@ __device__ __forceinline__ void count_insert(CountSlot* __restrict__ table, uint
     max_probe = max(max_probe, probes);
 }
 
-template <int BATCH>
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+}
+
+// MODE 0: load the slot key, then CAS/RED.   MODE 1: as 0, but a second roller runs one batch ahead and issues
+// prefetch.global.L2 for the slots of the next batch (memory-level parallelism without holding registers).
+// MODE 2: CAS first (no separate load): one ATOM + one RED per insert.
+template <int BATCH, int MINB, int MODE>
+__global__ void __launch_bounds__(256, MINB)
 k_count(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, int64_t n_words, int k,
         CountSlot* __restrict__ table, uint64_t capacity, CountStats* __restrict__ stats)
 {
@@ -197,8 +204,24 @@ k_count(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, 
     unsigned int nvalid = 0, new_keys = 0, max_probe = 0;
     if (p.m0 != 0xFFFFFFFFu) {
         Roller r; r.init(p.w0, p.w1, p.m0, p.m1, k);
+        Roller lead = r;
+        if (MODE == 1) {
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j) {
+                if (lead.valid(j)) prefetch_l2(&table[slot_of(mix64(lead.canonical()), capacity)]);
+                lead.step(j);
+            }
+        }
 #pragma unroll 1
         for (int b0 = 0; b0 < 32; b0 += BATCH) {
+            if (MODE == 1 && b0 + BATCH < 32) {
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) {
+                    int b = b0 + BATCH + j;
+                    if (lead.valid(b)) prefetch_l2(&table[slot_of(mix64(lead.canonical()), capacity)]);
+                    if (b < 31) lead.step(b);
+                }
+            }
             unsigned long long skey[BATCH]; uint64_t slot[BATCH]; unsigned long long cur[BATCH];
             unsigned int vmask = 0;
 #pragma unroll
@@ -212,12 +235,19 @@ k_count(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, 
                 if (b < 31) r.step(b);
             }
 #pragma unroll
-            for (int j = 0; j < BATCH; ++j)                    // all probes of the batch in flight together
-                cur[j] = ((vmask >> j) & 1u) ? ldcg_u64(&table[slot[j]].skey) : 0ull;
+            for (int j = 0; j < BATCH; ++j) {                  // all probes of the batch in flight together
+                if (MODE == 2) {
+                    cur[j] = ((vmask >> j) & 1u) ? atomicCAS(&table[slot[j]].skey, 0ull, skey[j]) : 0ull;
+                } else {
+                    cur[j] = ((vmask >> j) & 1u) ? ldcg_u64(&table[slot[j]].skey) : 0ull;
+                }
+            }
 #pragma unroll
             for (int j = 0; j < BATCH; ++j)
-                if ((vmask >> j) & 1u)
+                if ((vmask >> j) & 1u) {
+                    if (MODE == 2 && cur[j] == 0ull) { ++new_keys; cur[j] = skey[j]; }
                     count_insert(table, capacity, slot[j], skey[j], cur[j], new_keys, max_probe, stats);
+                }
             nvalid += __popc(vmask);
         }
     }
