@@ -13,7 +13,7 @@ from . import build as _build
 PC_HOST, PC_DEVICE = 0, 1
 PC_N_STAGES = 16
 STAGE_NAMES = ["h2d", "pack", "table_init", "count", "select", "sort", "rep_table", "probe", "row_sort", "emit",
-               "tfidf", "d2h", "export", "merge"]
+               "tfidf", "d2h", "export", "merge", "part_hist", "part_scatter"]
 
 
 class PolycrackerError(RuntimeError):

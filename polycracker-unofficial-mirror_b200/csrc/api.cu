@@ -30,7 +30,7 @@ int fail(int code, const char* fmt, ...) {
     } while (0)
 
 enum Stage { ST_H2D = 0, ST_PACK, ST_TABLE_INIT, ST_COUNT, ST_SELECT, ST_SORT, ST_REPTABLE, ST_PROBE,
-             ST_ROWSORT, ST_EMIT, ST_TFIDF, ST_D2H, ST_EXPORT, ST_MERGE, ST_N };
+             ST_ROWSORT, ST_EMIT, ST_TFIDF, ST_D2H, ST_EXPORT, ST_MERGE, ST_PART_HIST, ST_PART_SCATTER, ST_N };
 static_assert(ST_N <= PC_N_STAGES, "stage table too small");
 
 template <typename T>
@@ -88,6 +88,14 @@ struct pc_ctx {
     // tunables (pc_tune)
     int count_batch = 8, count_minb = 2, count_mode = 0;
     double table_load = 0.6;
+    int part_mode = -1;                         // -1 auto, 0 direct global table, 1 partitioned
+    int64_t part_bytes = 32ll << 20;            // target size of one L2-resident sub-table
+    int part_blocks = 512;                      // blocks per bucket in k_count_part
+
+    // partitioned count state
+    int pb = 0; uint64_t part_S = 0;
+    DevBuf<uint64_t> kbuf, kstream; DevBuf<unsigned long long> d_part_hist;
+    int count_items = 4;
 };
 
 namespace {
@@ -125,15 +133,15 @@ constexpr int RS_WARPS = 8;
 int radix_sort_u64(pc_ctx* c, uint64_t* a, uint64_t* b, int64_t n, int bits, uint64_t** out) {
     *out = a;
     if (n <= 1) return PC_OK;
-    int n_ctas = (int)std::min<int64_t>(296, std::max<int64_t>(1, n / (RS_WARPS * 32 * 16)));
+    int n_ctas = (int)std::min<int64_t>(296, std::max<int64_t>(1, n / (RS_WARPS * 32 * 64)));   // >= 2048 keys per warp
     int NW = n_ctas * RS_WARPS;
     int64_t ipw = (((n + NW - 1) / NW) + 31) & ~(int64_t)31;
-    int rc = c->rs_hist.alloc((size_t)256 * NW);
+    int rc = c->rs_hist.alloc((size_t)256 * NW + 1);
     if (rc) return rc;
     uint64_t* src = a; uint64_t* dst = b;
     for (int shift = 0; shift < bits; shift += 8) {
         LAUNCH(c, (pc::k_rs_hist<uint64_t, RS_WARPS>), n_ctas, RS_WARPS * 32, src, n, ipw, shift, c->rs_hist.p, NW);
-        LAUNCH(c, pc::k_rs_scan, 1, 1024, c->rs_hist.p, (int64_t)256 * NW);
+        LAUNCH(c, pc::k_rs_scan<unsigned int>, 1, 1024, c->rs_hist.p, (int64_t)256 * NW);
         LAUNCH(c, (pc::k_rs_scatter<uint64_t, RS_WARPS, false>), n_ctas, RS_WARPS * 32, src, dst,
                (const uint32_t*)nullptr, (uint32_t*)nullptr, n, ipw, shift, c->rs_hist.p, NW);
         std::swap(src, dst);
@@ -196,6 +204,7 @@ int pc_destroy(pc_ctx* c) {
     cudaStreamSynchronize(c->stream);
     c->ascii.release(); c->d_word0.release(); c->d_begin.release(); c->d_len.release();
     c->words.release(); c->nmask.release(); c->table.release(); c->d_stats.release();
+    c->kbuf.release(); c->kstream.release(); c->d_part_hist.release();
     c->sel_a.release(); c->sel_b.release(); c->rs_hist.release(); c->d_counter.release(); c->rtable.release();
     c->d_chunk_row.release(); c->d_row_base.release(); c->d_row_cursor.release(); c->hits_a.release();
     c->hits_b.release(); c->d_row_nnz.release(); c->d_indptr.release(); c->d_indices.release();
@@ -371,6 +380,10 @@ int pc_tune(pc_ctx* c, const char* key, int64_t value) {
     if (k == "count_batch") c->count_batch = (int)value;
     else if (k == "count_minb") c->count_minb = (int)value;
     else if (k == "count_mode") c->count_mode = (int)value;
+    else if (k == "part_mode") c->part_mode = (int)value;
+    else if (k == "count_items") c->count_items = (int)value;
+    else if (k == "part_mbytes") c->part_bytes = std::max<int64_t>(1, value) << 20;
+    else if (k == "part_blocks") c->part_blocks = (int)std::max<int64_t>(1, value);
     else if (k == "table_load_pct") c->table_load = std::min(0.95, std::max(0.05, value / 100.0));
     else if (k == "l2_fetch_granularity") CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
     else return fail(PC_EINVAL, "unknown tunable %s", key);
@@ -382,19 +395,66 @@ int pc_count(pc_ctx* c, int k, int64_t capacity) {
     if (!c->loaded) return fail(PC_ESTATE, "pc_count before pc_load_sequences");
     if (k < 1 || k > 32) return fail(PC_EINVAL, "k = %d unsupported: this path handles 1 <= k <= 32 (uint64 k-mers)", k);
     c->counted = c->selected = c->built = c->tfidf_done = false;
+    int64_t windows = 0;
+    for (int64_t i = 0; i < c->n_chunks; ++i) windows += std::max<int64_t>(0, c->h_len[i] - k + 1);
     if (capacity <= 0) {
-        int64_t windows = 0;
-        for (int64_t i = 0; i < c->n_chunks; ++i) windows += std::max<int64_t>(0, c->h_len[i] - k + 1);
         // distinct canonical k-mers <= windows and <= 4^k (palindrome-aware bound not needed: it is an upper bound)
         double space = k >= 31 ? 9.3e18 : (double)(1ull << (2 * k));
         double bound = std::min((double)windows, space);
         capacity = (int64_t)(bound / c->table_load) + 1024;
     }
+    // partition plan: P = 2^pb sub-tables of S slots, each about part_bytes so that it stays L2 resident
+    int pb = 0;
+    bool partitioned = c->part_mode == 1 || (c->part_mode < 0 && (size_t)capacity * sizeof(pc::CountSlot) > (size_t)(64ll << 20));
+    if (partitioned) {
+        while (pb < 12 && ((size_t)capacity * sizeof(pc::CountSlot)) >> pb > (size_t)c->part_bytes) ++pb;
+        if (pb == 0) pb = 1;
+    }
+    uint64_t P = 1ull << pb;
+    uint64_t S = ((uint64_t)capacity + P - 1) / P;
+    if (S < 64) S = 64;
+    capacity = (int64_t)(S * P);
     rc = table_prepare(c, k, capacity); if (rc) return rc;
-    {
+    c->pb = pb; c->part_S = S;
+    if (c->n_words > 0 && !partitioned) {
         StageTimer t(c, ST_COUNT);
-        if (c->n_words > 0) {
-            rc = launch_count(c); if (rc) return rc;
+        rc = launch_count(c); if (rc) return rc;
+    } else if (c->n_words > 0) {
+        int64_t n_stream = ((c->n_words + 255) / 256) * 256 * 32;          // one slot per window start
+        rc = c->kstream.alloc((size_t)n_stream); if (rc) return rc;
+        rc = c->kbuf.alloc((size_t)std::max<int64_t>(windows, 1)); if (rc) return rc;
+        rc = c->d_part_hist.alloc((size_t)3 * P + 2); if (rc) return rc;
+        unsigned long long* bucket_hist = c->d_part_hist.p;
+        unsigned long long* bucket_off = bucket_hist + P;              // [P + 1]
+        unsigned long long* bucket_cur = bucket_off + P + 1;           // [P]
+        {
+            StageTimer t(c, ST_PART_HIST);
+            CU(cudaMemsetAsync(bucket_hist, 0, P * sizeof(unsigned long long), c->stream));
+            c->launches++;
+            pc::k_extract<<<blocks_for(c->n_words, 256), 256, P * sizeof(unsigned int), c->stream>>>(
+                c->words.p, c->nmask.p, c->n_words, k, pb, c->kstream.p, bucket_hist, c->d_stats.p);
+            CU(cudaGetLastError());
+            LAUNCH(c, pc::k_bucket_scan, 1, 1024, bucket_hist, (unsigned int)P, bucket_off, bucket_cur);
+        }
+        {
+            StageTimer t(c, ST_PART_SCATTER);
+            constexpr int TILE = 8192;
+            size_t smem = (size_t)TILE * 8 + P * 8 + P * 4 + (P + 2) * 4 + (size_t)TILE * 2 + 16;
+            CU(cudaFuncSetAttribute(pc::k_tile_scatter<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            unsigned int grid = (unsigned int)std::min<int64_t>(148 * 2, (n_stream + TILE - 1) / TILE);
+            c->launches++;
+            pc::k_tile_scatter<TILE><<<grid, 256, smem, c->stream>>>(c->kstream.p, n_stream, pb, bucket_off, bucket_cur, c->kbuf.p);
+            CU(cudaGetLastError());
+        }
+        {
+            StageTimer t(c, ST_COUNT);
+            unsigned int B = (unsigned int)c->part_blocks;
+            if (c->count_items == 8)
+                LAUNCH(c, (pc::k_count_part<8>), (unsigned int)(P * B), 256, c->kbuf.p, bucket_off, pb, S, B, c->table.p, c->d_stats.p);
+            else if (c->count_items == 2)
+                LAUNCH(c, (pc::k_count_part<2>), (unsigned int)(P * B), 256, c->kbuf.p, bucket_off, pb, S, B, c->table.p, c->d_stats.p);
+            else
+                LAUNCH(c, (pc::k_count_part<4>), (unsigned int)(P * B), 256, c->kbuf.p, bucket_off, pb, S, B, c->table.p, c->d_stats.p);
         }
     }
     rc = fetch_stats(c); if (rc) return rc;
@@ -473,9 +533,12 @@ int pc_merge_counts(pc_ctx* c, const uint64_t* keys_dev, const uint32_t* counts_
     if (fresh) {
         if (capacity <= 0) capacity = (int64_t)(n / 0.6) + 1024;
         rc = table_prepare(c, k, capacity); if (rc) return rc;
+        c->pb = 0; c->part_S = (uint64_t)c->capacity;
         c->selected = c->built = c->tfidf_done = false;
     } else if (!c->counted || c->k != k) {
         return fail(PC_ESTATE, "pc_merge_counts(fresh=0) needs an existing table with the same k");
+    } else if (c->pb != 0) {
+        return fail(PC_ESTATE, "pc_merge_counts(fresh=0) cannot add to a partitioned count table");
     }
     {
         StageTimer t(c, ST_MERGE);

@@ -265,6 +265,201 @@ k_count(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ K3, partitioned
+// Random inserts into a table much larger than L2 are bound by DRAM row activations: every insert fetches a
+// whole 128-byte line and later writes a sector back (ncu: 150 B of DRAM traffic per insert, 26 % of peak
+// bandwidth, 30 us queueing latency).  The partitioned path restores locality: the table is P = 2^pb independent
+// sub-tables of S slots (partition = top pb bits of the hash), the k-mers are first radix-partitioned into P
+// buckets with streaming writes, then the buckets are counted one after the other, so the sub-table being
+// updated stays L2 resident and every table line moves between DRAM and L2 once.
+__device__ __forceinline__ unsigned int part_of(uint64_t h, int pb) { return pb ? (unsigned int)(h >> (64 - pb)) : 0u; }
+__device__ __forceinline__ uint64_t slot_in_part(uint64_t h, int pb, uint64_t S) { return __umul64hi(h << pb, S); }
+
+#define PC_KEY_SENTINEL (~0ull)      // never a canonical-min k-mer (its reverse complement, all A, is smaller)
+
+// pass A: packed genome -> stream of canonical k-mers, one slot per window start (invalid windows hold the
+// sentinel), plus the global bucket histogram.  Stream layout [warp tile][window b][lane]: every store
+// instruction writes 256 contiguous bytes.
+__global__ void __launch_bounds__(256)
+k_extract(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, int64_t n_words, int k, int pb,
+          uint64_t* __restrict__ stream, unsigned long long* __restrict__ bucket_hist, CountStats* __restrict__ stats)
+{
+    extern __shared__ unsigned int shh[];                     // [P] bucket counts of this CTA
+    const unsigned int P = 1u << pb;
+    for (unsigned int i = threadIdx.x; i < P; i += blockDim.x) shh[i] = 0;
+    __syncthreads();
+    int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int lane = threadIdx.x & 31;
+    WordPair p = load_word_pair(words, nmask, w, n_words);
+    uint64_t* out = stream + (w - lane) * 32 + lane;
+    unsigned int nvalid = 0;
+    if (p.m0 != 0xFFFFFFFFu) {
+        Roller r; r.init(p.w0, p.w1, p.m0, p.m1, k);
+#pragma unroll 8
+        for (int b = 0; b < 32; ++b) {
+            bool v = r.valid(b);
+            uint64_t key = r.canonical();
+            __stcs(out + b * 32, v ? key : PC_KEY_SENTINEL);
+            if (v) { atomicAdd(&shh[part_of(mix64(key), pb)], 1u); ++nvalid; }
+            if (b < 31) r.step(b);
+        }
+    } else {
+#pragma unroll 8
+        for (int b = 0; b < 32; ++b) __stcs(out + b * 32, PC_KEY_SENTINEL);
+    }
+    __syncthreads();
+    for (unsigned int i = threadIdx.x; i < P; i += blockDim.x)
+        if (shh[i]) atomicAdd(&bucket_hist[i], (unsigned long long)shh[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(0xFFFFFFFFu, nvalid, o);
+    if (lane == 0 && nvalid) atomicAdd(&stats->valid_windows, (unsigned long long)nvalid);
+}
+
+// exclusive scan of the P bucket sizes -> bucket_off[P+1]; cursors reset.  P <= 4096: one CTA.
+__global__ void __launch_bounds__(1024)
+k_bucket_scan(const unsigned long long* __restrict__ hist, unsigned int P, unsigned long long* __restrict__ bucket_off,
+              unsigned long long* __restrict__ cursor)
+{
+    __shared__ unsigned long long part[1024];
+    int t = threadIdx.x;
+    unsigned int per = (P + 1023) / 1024;
+    unsigned int beg = min(P, t * per), end = min(P, beg + per);
+    unsigned long long s = 0;
+    for (unsigned int i = beg; i < end; ++i) s += hist[i];
+    part[t] = s;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        unsigned long long v = (t >= o) ? part[t - o] : 0ull;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    unsigned long long run = part[t] - s;
+    for (unsigned int i = beg; i < end; ++i) { bucket_off[i] = run; cursor[i] = 0ull; run += hist[i]; }
+    if (t == 1023) bucket_off[P] = part[1023];
+}
+
+// pass B: tile-wise counting sort by bucket in shared memory, then coalesced copy-out.  A tile (TILE stream slots)
+// is histogrammed, one global atomic per non-empty (tile, bucket) reserves a contiguous run in the bucket, the
+// keys are ranked into a bucket-sorted smem array and written out run by run: consecutive threads write
+// consecutive addresses (scattered 8-byte stores into hundreds of open runs were the bottleneck of the first
+// version: 42 G stores/s regardless of how the ranks were computed).
+template <int TILE>
+__global__ void __launch_bounds__(256)
+k_tile_scatter(const uint64_t* __restrict__ stream, int64_t n_stream, int pb,
+               const unsigned long long* __restrict__ bucket_off, unsigned long long* __restrict__ cursor,
+               uint64_t* __restrict__ kbuf)
+{
+    extern __shared__ unsigned long long sm64[];
+    const unsigned int P = 1u << pb;
+    unsigned long long* sorted = sm64;                                   // [TILE]
+    unsigned long long* gbase = sm64 + TILE;                             // [P]
+    unsigned int* cnt = reinterpret_cast<unsigned int*>(gbase + P);      // [P]
+    unsigned int* lstart = cnt + P;                                      // [P + 1]
+    unsigned short* qs = reinterpret_cast<unsigned short*>(lstart + P + 1 + ((P + 1) & 1));   // [TILE]
+    __shared__ unsigned int wsum[8];
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    int64_t n_tiles = (n_stream + TILE - 1) / TILE;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t* src = stream + tile * TILE;
+        int64_t lim = min((int64_t)TILE, n_stream - tile * TILE);
+        for (unsigned int i = t; i < P; i += 256) cnt[i] = 0;
+        __syncthreads();
+#pragma unroll 8
+        for (int j = 0; j < TILE / 256; ++j) {
+            int i = j * 256 + t;
+            uint64_t key = (i < lim) ? __ldg(src + i) : PC_KEY_SENTINEL;
+            if (key != PC_KEY_SENTINEL) atomicAdd(&cnt[part_of(mix64(key), pb)], 1u);
+        }
+        __syncthreads();
+        // exclusive scan of cnt[P] -> lstart; reserve the global runs; cnt becomes the rank counter
+        {
+            unsigned int per = (P + 255) / 256;
+            unsigned int b0 = min(P, t * per), b1 = min(P, b0 + per);
+            unsigned int s = 0;
+            for (unsigned int q = b0; q < b1; ++q) s += cnt[q];
+            unsigned int incl = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned int u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            if (lane == 31) wsum[wid] = incl;
+            __syncthreads();
+            unsigned int before = 0;
+#pragma unroll
+            for (int x = 0; x < 8; ++x) if (x < wid) before += wsum[x];
+            unsigned int run = before + incl - s;
+            for (unsigned int q = b0; q < b1; ++q) {
+                unsigned int c = cnt[q];
+                lstart[q] = run;
+                if (c) gbase[q] = bucket_off[q] + atomicAdd(&cursor[q], (unsigned long long)c);
+                cnt[q] = 0;
+                run += c;
+            }
+            if (t == 255) lstart[P] = run;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int j = 0; j < TILE / 256; ++j) {
+            int i = j * 256 + t;
+            uint64_t key = (i < lim) ? __ldg(src + i) : PC_KEY_SENTINEL;
+            if (key != PC_KEY_SENTINEL) {
+                unsigned int q = part_of(mix64(key), pb);
+                unsigned int pos = lstart[q] + atomicAdd(&cnt[q], 1u);
+                sorted[pos] = key;
+                qs[pos] = (unsigned short)q;
+            }
+        }
+        __syncthreads();
+        unsigned int nv = lstart[P];
+        for (unsigned int i = t; i < nv; i += 256) {
+            unsigned int q = qs[i];
+            kbuf[gbase[q] + (i - lstart[q])] = sorted[i];
+        }
+        __syncthreads();
+    }
+}
+
+// pass C: count one bucket after the other.  blockIdx = bucket * B + b: blocks are dispatched in index order, so
+// at any time the resident blocks work on one or two adjacent buckets whose sub-tables (S slots) sit in L2.
+template <int ITEMS>
+__global__ void __launch_bounds__(256)
+k_count_part(const uint64_t* __restrict__ kbuf, const unsigned long long* __restrict__ bucket_off, int pb, uint64_t S,
+             unsigned int B, CountSlot* __restrict__ table, CountStats* __restrict__ stats)
+{
+    unsigned int q = blockIdx.x / B, b = blockIdx.x % B;
+    unsigned long long beg = bucket_off[q], end = bucket_off[q + 1];
+    CountSlot* sub = table + (uint64_t)q * S;
+    unsigned int new_keys = 0, max_probe = 0;
+    for (unsigned long long i0 = beg + ((unsigned long long)b * 256u + threadIdx.x) * ITEMS; i0 < end;
+         i0 += (unsigned long long)B * 256u * ITEMS) {
+        unsigned long long skey[ITEMS]; uint64_t slot[ITEMS]; unsigned long long cur[ITEMS];
+        bool on[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            on[j] = i0 + j < end;
+            uint64_t key = on[j] ? __ldcs(kbuf + i0 + j) : 0ull;          // streaming: evict-first in L2
+            skey[j] = ~key;
+            slot[j] = slot_in_part(mix64(key), pb, S);
+        }
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) cur[j] = on[j] ? ldcg_u64(&sub[slot[j]].skey) : 0ull;
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j)
+            if (on[j]) count_insert(sub, S, slot[j], skey[j], cur[j], new_keys, max_probe, stats);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        new_keys += __shfl_xor_sync(0xFFFFFFFFu, new_keys, o);
+        max_probe = max(max_probe, __shfl_xor_sync(0xFFFFFFFFu, max_probe, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (new_keys) atomicAdd(&stats->distinct, (unsigned long long)new_keys);
+        if (max_probe > 8) atomicMax(&stats->max_probe, (unsigned long long)max_probe);
+    }
+}
+
 // merge (kmer, count) pairs received from other ranks into the owner's table (multi-GPU)
 __global__ void __launch_bounds__(256)
 k_merge(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, int64_t n,
@@ -384,27 +579,59 @@ k_rs_hist(const K* __restrict__ src, int64_t n, int64_t ipw, int shift, unsigned
     for (int d = lane; d < 256; d += 32) hist[(int64_t)d * NW + gw] = h[wid][d];
 }
 
-// single-CTA exclusive scan of `m` counters (m = 256*NW, a few 1e5)
+// single-CTA exclusive scan of `m` counters (m = 256*NW).  Warp q owns a contiguous segment and walks it with
+// coalesced, 4x-unrolled loads; the 32 segment totals are scanned in shared memory.
+template <typename T>
 __global__ void __launch_bounds__(1024)
-k_rs_scan(unsigned int* __restrict__ hist, int64_t m)
+k_rs_scan(T* __restrict__ hist, int64_t m)                  // hist[m] receives the grand total
 {
-    __shared__ unsigned int part[1024];
-    int t = threadIdx.x;
-    int64_t per = (m + 1023) / 1024;
-    int64_t beg = (int64_t)t * per, end = min(m, beg + per);
-    unsigned int s = 0;
-    for (int64_t i = beg; i < end; ++i) s += hist[i];
-    part[t] = s;
-    __syncthreads();
-    // Hillis-Steele inclusive scan over 1024 partials
-    for (int o = 1; o < 1024; o <<= 1) {
-        unsigned int v = (t >= o) ? part[t - o] : 0u;
-        __syncthreads();
-        part[t] += v;
-        __syncthreads();
+    __shared__ T wtot[32];
+    int t = threadIdx.x, lane = t & 31, wq = t >> 5;
+    int64_t seg = (((m + 31) / 32) + 127) & ~(int64_t)127;    // multiple of 128 = 4 tiles of 32
+    int64_t beg = min(m, (int64_t)wq * seg), end = min(m, beg + seg);
+    T s = 0;
+    for (int64_t i = beg + lane; i < end; i += 128) {
+        T a0 = hist[i];
+        T a1 = (i + 32 < end) ? hist[i + 32] : (T)0;
+        T a2 = (i + 64 < end) ? hist[i + 64] : (T)0;
+        T a3 = (i + 96 < end) ? hist[i + 96] : (T)0;
+        s += a0 + a1 + a2 + a3;
     }
-    unsigned int run = part[t] - s;                          // exclusive
-    for (int64_t i = beg; i < end; ++i) { unsigned int v = hist[i]; hist[i] = run; run += v; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    if (lane == 0) wtot[wq] = s;
+    __syncthreads();
+    if (wq == 0) {
+        T v = wtot[lane], incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            T u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        wtot[lane] = incl - v;
+        if (lane == 31) hist[m] = incl;
+    }
+    __syncthreads();
+    T carry = wtot[wq];
+    for (int64_t i0 = beg; i0 < end; i0 += 128) {
+        T v[4], incl[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { int64_t i = i0 + 32 * u + lane; v[u] = (i < end) ? hist[i] : (T)0; incl[u] = v[u]; }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                T x = __shfl_up_sync(0xFFFFFFFFu, incl[u], o);
+                if (lane >= o) incl[u] += x;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            int64_t i = i0 + 32 * u + lane;
+            if (i < end) hist[i] = carry + incl[u] - v[u];
+            carry += __shfl_sync(0xFFFFFFFFu, incl[u], 31);
+        }
+    }
 }
 
 template <typename K, int WARPS, bool HAS_VAL>

@@ -99,6 +99,31 @@ def test_counts_bit_exact(ctx, k):
     assert sorted(k3.tolist()) == want_keys[want_counts >= 3].tolist()
 
 
+@pytest.mark.parametrize("k,mb", [(23, 1), (31, 4), (11, 1), (32, 2)])
+def test_partitioned_count_equals_direct_and_oracle(ctx, k, mb):
+    """The L2-partitioned count path (radix partition of the k-mers, one sub-table per bucket) forced on at a size
+    where the direct path would normally run; both must reproduce the oracle bit for bit."""
+    p = synth.small_params(seed=200 + k, genome_size=1_500_000, n_fraction=0.01)
+    seq, off, names = synth.generate(p)
+    lay = ChunkLayout(names, off, 20000)
+    ctx.load_sequences(seq, lay.chunk_begin_abs, lay.chunk_end_abs)
+    want_keys, want_counts, n_windows = c_oracle.count(seq, lay.chunk_begin_abs, lay.chunk_end_abs, k)
+    try:
+        for mode in (1, 0):
+            ctx.tune(part_mode=mode, part_mbytes=mb)
+            ctx.count(k)
+            keys, counts = ctx.dump_counts(1)
+            order = np.argsort(keys)
+            assert np.array_equal(keys[order], want_keys), "mode %d" % mode
+            assert np.array_equal(counts[order].astype(np.uint64), want_counts), "mode %d" % mode
+            info = ctx.count_info()
+            assert info["valid_windows"] == n_windows and info["distinct"] == len(want_keys)
+        ctx.tune(part_mode=1, part_mbytes=mb)
+        _check_against_c_oracle(ctx, seq, off, names, 20000, k, 5)
+    finally:
+        ctx.tune(part_mode=-1, part_mbytes=32)
+
+
 def test_small_table_reports_overflow_not_garbage(ctx):
     p = synth.small_params(seed=9, genome_size=100_000)
     seq, off, names = synth.generate(p)

@@ -50,13 +50,14 @@ def main():
             for _ in range(a.reps):
                 ctx.count(a.k)
                 t = ctx.timings()
-                ts.append((t["count"], t["table_init"]))
+                ts.append((t["count"] + t["part_hist"] + t["part_scatter"], t["table_init"], t["count"], t["part_hist"], t["part_scatter"]))
             info = ctx.count_info()
             sig = (info["distinct"], info["valid_windows"])
             if base is None:
                 base = sig
             best = min(ts)
-            print(json.dumps(dict(variant=v, count_ms=round(best[0], 3), init_ms=round(best[1], 3),
+            print(json.dumps(dict(variant=v, total_ms=round(best[0], 3), init_ms=round(best[1], 3), count_ms=round(best[2], 3),
+                                  hist_ms=round(best[3], 3), scatter_ms=round(best[4], 3),
                                   ginserts_per_s=round(info["valid_windows"] / best[0] / 1e6, 2),
                                   load=round(info["distinct"] / info["capacity"], 3), max_probe=info["max_probe"],
                                   ok=(sig == base))), flush=True)
