@@ -89,7 +89,11 @@ struct pc_ctx {
     int count_batch = 8, count_minb = 2, count_mode = 0;
     double table_load = 0.6;
     int part_mode = -1;                         // -1 auto, 0 direct global table, 1 partitioned
-    int64_t part_bytes = 32ll << 20;            // target size of one L2-resident sub-table
+    int64_t part_bytes = 64ll << 20;            // target size of one L2-resident sub-table
+    int probe_mode = -1;                        // -1 auto (stream when available), 0 roller, 1 stream
+    int probe_batch = 4;
+    int rep_load_inv = 4;                       // repeat table capacity = rep_load_inv * n_selected
+    bool stream_valid = false; int stream_k = 0;
     int part_blocks = 512;                      // blocks per bucket in k_count_part
 
     // partitioned count state
@@ -152,7 +156,7 @@ int radix_sort_u64(pc_ctx* c, uint64_t* a, uint64_t* b, int64_t n, int bits, uin
 
 int build_rep_table(pc_ctx* c) {
     StageTimer t(c, ST_REPTABLE);
-    c->rcap = std::max<uint64_t>(64, (uint64_t)c->n_sel * 2);
+    c->rcap = std::max<uint64_t>(64, (uint64_t)c->n_sel * (uint64_t)std::max(2, c->rep_load_inv));
     int rc = c->rtable.alloc(c->rcap);
     if (rc) return rc;
     CU(cudaMemsetAsync(c->rtable.p, 0, c->rcap * sizeof(pc::RepSlot), c->stream));
@@ -270,6 +274,7 @@ int pc_load_sequences(pc_ctx* c, const uint8_t* ascii, int64_t n_bytes, int loc,
     if (n_bytes < 0 || n_chunks < 0 || (n_bytes > 0 && !ascii) || (n_chunks > 0 && (!chunk_begin || !chunk_end)))
         return fail(PC_EINVAL, "bad load_sequences arguments");
     c->loaded = c->counted = c->selected = c->built = c->tfidf_done = false;
+    c->stream_valid = false;
     c->h_word0.assign(n_chunks + 1, 0); c->h_begin.assign(std::max<int64_t>(n_chunks, 1), 0); c->h_len.assign(std::max<int64_t>(n_chunks, 1), 0);
     int64_t prev_end = 0, wsum = 0;
     for (int64_t i = 0; i < n_chunks; ++i) {
@@ -382,6 +387,9 @@ int pc_tune(pc_ctx* c, const char* key, int64_t value) {
     else if (k == "count_mode") c->count_mode = (int)value;
     else if (k == "part_mode") c->part_mode = (int)value;
     else if (k == "count_items") c->count_items = (int)value;
+    else if (k == "probe_mode") c->probe_mode = (int)value;
+    else if (k == "probe_batch") c->probe_batch = (int)value;
+    else if (k == "rep_load_inv") c->rep_load_inv = (int)value;
     else if (k == "part_mbytes") c->part_bytes = std::max<int64_t>(1, value) << 20;
     else if (k == "part_blocks") c->part_blocks = (int)std::max<int64_t>(1, value);
     else if (k == "table_load_pct") c->table_load = std::min(0.95, std::max(0.05, value / 100.0));
@@ -395,6 +403,7 @@ int pc_count(pc_ctx* c, int k, int64_t capacity) {
     if (!c->loaded) return fail(PC_ESTATE, "pc_count before pc_load_sequences");
     if (k < 1 || k > 32) return fail(PC_EINVAL, "k = %d unsupported: this path handles 1 <= k <= 32 (uint64 k-mers)", k);
     c->counted = c->selected = c->built = c->tfidf_done = false;
+    c->stream_valid = false;
     int64_t windows = 0;
     for (int64_t i = 0; i < c->n_chunks; ++i) windows += std::max<int64_t>(0, c->h_len[i] - k + 1);
     if (capacity <= 0) {
@@ -436,6 +445,7 @@ int pc_count(pc_ctx* c, int k, int64_t capacity) {
             CU(cudaGetLastError());
             LAUNCH(c, pc::k_bucket_scan, 1, 1024, bucket_hist, (unsigned int)P, bucket_off, bucket_cur);
         }
+        c->stream_valid = true; c->stream_k = k;
         {
             StageTimer t(c, ST_PART_SCATTER);
             constexpr int TILE = 8192;
@@ -660,10 +670,22 @@ int pc_build_matrix(pc_ctx* c, const int32_t* chunk_row, int64_t n_rows, int64_t
     CU(cudaMemsetAsync(c->d_indptr.p, 0, (n_rows + 1) * sizeof(int64_t), c->stream));
     {
         StageTimer t(c, ST_PROBE);
-        if (c->n_words > 0 && n_rows > 0 && c->n_sel > 0)
-            LAUNCH(c, (pc::k_probe<8>), blocks_for(c->n_words, 256), 256, c->words.p, c->nmask.p, c->n_words, k,
-                   c->d_word0.p, c->n_chunks, c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, c->hits_a.p,
-                   c->d_row_cursor.p);
+        if (c->n_words > 0 && n_rows > 0 && c->n_sel > 0) {
+            bool use_stream = c->stream_valid && c->stream_k == k && c->probe_mode != 0;
+            if (c->probe_mode == 1 && !use_stream) return fail(PC_ESTATE, "probe_mode=1 needs the k-mer stream of a partitioned pc_count");
+            unsigned int grid = blocks_for(c->n_words, 256);
+            if (use_stream) {
+                if (c->probe_batch == 4)
+                    LAUNCH(c, (pc::k_probe_stream<4>), grid, 256, c->kstream.p, c->n_words, c->d_word0.p, c->n_chunks,
+                           c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, c->hits_a.p, c->d_row_cursor.p);
+                else
+                    LAUNCH(c, (pc::k_probe_stream<8>), grid, 256, c->kstream.p, c->n_words, c->d_word0.p, c->n_chunks,
+                           c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, c->hits_a.p, c->d_row_cursor.p);
+            } else {
+                LAUNCH(c, (pc::k_probe<8>), grid, 256, c->words.p, c->nmask.p, c->n_words, k, c->d_word0.p, c->n_chunks,
+                       c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, c->hits_a.p, c->d_row_cursor.p);
+            }
+        }
     }
     int bits = 1; while (((int64_t)1 << bits) < c->n_sel) ++bits;
     int n_passes = std::max(1, (bits + 7) / 8);

@@ -827,6 +827,90 @@ k_probe(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, 
     }
 }
 
+// Stream variant of the probe: when the partitioned count already materialised the canonical k-mer of every window
+// (k_extract), K5 re-reads that stream (8 coalesced bytes per window) instead of re-running the roller.
+template <int BATCH>
+__global__ void __launch_bounds__(256)
+k_probe_stream(const uint64_t* __restrict__ stream, int64_t n_words,
+               const int64_t* __restrict__ chunk_word0, int64_t n_chunks, const int32_t* __restrict__ chunk_row,
+               const int64_t* __restrict__ row_hit_base, const RepSlot* __restrict__ rtable, uint64_t rcap,
+               int32_t* __restrict__ hits, unsigned int* __restrict__ row_cursor)
+{
+    int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int lane = threadIdx.x & 31;
+    int64_t w_lane0 = w - lane;
+    if (w_lane0 >= n_words) return;                           // whole warp past the end
+    int row = -1;
+    if (w < n_words) {
+        int64_t c = chunk_of_word(chunk_word0, n_chunks, w, w_lane0);
+        row = __ldg(chunk_row + c);
+    }
+    bool lane_on = row >= 0;
+    unsigned int on_mask = __ballot_sync(0xFFFFFFFFu, lane_on);
+    if (on_mask == 0u) return;
+    int row0 = __shfl_sync(0xFFFFFFFFu, row, __ffs(on_mask) - 1);
+    bool uniform = __all_sync(0xFFFFFFFFu, !lane_on || row == row0);
+    const uint64_t* src = stream + w_lane0 * 32 + lane;
+#pragma unroll 1
+    for (int b0 = 0; b0 < 32; b0 += BATCH) {
+        int cols[BATCH];
+        unsigned int hmask = 0;
+        if (lane_on) {
+            unsigned long long skey[BATCH]; uint64_t slot[BATCH]; uint4 cur[BATCH];
+            unsigned int vmask = 0;
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j) {
+                uint64_t key = __ldcs(src + (b0 + j) * 32);
+                vmask |= (unsigned int)(key != PC_KEY_SENTINEL) << j;
+                skey[j] = ~key;
+                slot[j] = slot_of(mix64(key), rcap);
+            }
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j)
+                cur[j] = ((vmask >> j) & 1u) ? __ldg(reinterpret_cast<const uint4*>(rtable + slot[j])) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j) {
+                cols[j] = 0;
+                if (!((vmask >> j) & 1u)) continue;
+                unsigned long long ck = ((unsigned long long)cur[j].y << 32) | cur[j].x;
+                int col = (int)cur[j].z;
+                uint64_t s = slot[j];
+                while (ck != 0ull && ck != skey[j]) {
+                    if (++s == rcap) s = 0;
+                    uint4 c2 = __ldg(reinterpret_cast<const uint4*>(rtable + s));
+                    ck = ((unsigned long long)c2.y << 32) | c2.x; col = (int)c2.z;
+                }
+                if (ck != 0ull) { cols[j] = col; hmask |= 1u << j; }
+            }
+        }
+        int nh = __popc(hmask);
+        unsigned int any = __ballot_sync(0xFFFFFFFFu, nh > 0);
+        if (any == 0u) continue;
+        int32_t* dst = nullptr;
+        if (uniform) {
+            int incl = nh;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            unsigned int base = 0;
+            if (lane == 0) base = atomicAdd(&row_cursor[row0], (unsigned int)total);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (nh > 0) dst = hits + __ldg(row_hit_base + row0) + base + (incl - nh);
+        } else if (nh > 0) {
+            unsigned int base = atomicAdd(&row_cursor[row], (unsigned int)nh);
+            dst = hits + __ldg(row_hit_base + row) + base;
+        }
+        if (nh > 0) {
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j)
+                if ((hmask >> j) & 1u) dst[__popc(hmask & ((1u << j) - 1u))] = cols[j];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ K6 rows -> CSR
 // One CTA per matrix row.  The row's hits (column ids, unordered, with multiplicity) are sorted with the same
 // stable LSD scheme, CTA-local: warp wq owns a contiguous slice, hist[wq][256] lives in shared memory, data
