@@ -284,7 +284,8 @@ class Context:
         info = np.zeros(8, np.int64)
         check(lib.pc_count_info(self._h, info.ctypes.data), "pc_count_info")
         return dict(capacity=int(info[0]), distinct=int(info[1]), valid_windows=int(info[2]),
-                    table_bytes=int(info[3]), max_probe=int(info[4]), k=int(info[5]))
+                    table_bytes=int(info[3]), max_probe=int(info[4]), k=int(info[5]),
+                    distinct_estimate=int(info[6]), partition_bits=int(info[7]))
 
     def dump_counts(self, min_count=1, max_count=0xFFFFFFFF):
         n = _i64()

@@ -4,7 +4,9 @@
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
+#include <math.h>
 #include <algorithm>
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -98,7 +100,10 @@ struct pc_ctx {
 
     // partitioned count state
     int pb = 0; uint64_t part_S = 0;
-    DevBuf<uint64_t> kbuf, kstream; DevBuf<unsigned long long> d_part_hist;
+    DevBuf<uint64_t> kbuf, kstream; DevBuf<unsigned long long> d_part_hist; DevBuf<unsigned int> d_hll;
+    // measured on B200 (profiles/r01_kbench_count.md): the bucket count is bound by L2 sector operations, so the
+    // variants that trade probes for DRAM traffic (HLL-sized denser table, in-kernel zeroing, CAS-first) are slower
+    int hll_sizing = 0, fused_zero = 0, hll_bias_pct = 100, part_casfirst = 0; int64_t distinct_estimate = 0;
     int count_items = 4;
 };
 
@@ -208,7 +213,7 @@ int pc_destroy(pc_ctx* c) {
     cudaStreamSynchronize(c->stream);
     c->ascii.release(); c->d_word0.release(); c->d_begin.release(); c->d_len.release();
     c->words.release(); c->nmask.release(); c->table.release(); c->d_stats.release();
-    c->kbuf.release(); c->kstream.release(); c->d_part_hist.release();
+    c->kbuf.release(); c->kstream.release(); c->d_part_hist.release(); c->d_hll.release();
     c->sel_a.release(); c->sel_b.release(); c->rs_hist.release(); c->d_counter.release(); c->rtable.release();
     c->d_chunk_row.release(); c->d_row_base.release(); c->d_row_cursor.release(); c->hits_a.release();
     c->hits_b.release(); c->d_row_nnz.release(); c->d_indptr.release(); c->d_indices.release();
@@ -339,7 +344,7 @@ int pc_packed_get(pc_ctx* c, uint64_t* words, uint32_t* nmask, int64_t* chunk_wo
 }
 
 // ---------------------------------------------------------------------------------------------- K3
-static int table_prepare(pc_ctx* c, int k, int64_t capacity) {
+static int table_prepare(pc_ctx* c, int k, int64_t capacity, bool reset_stats = true) {
     if (k < 1 || k > 32) return fail(PC_EINVAL, "k = %d unsupported: this path handles 1 <= k <= 32 (uint64 k-mers)", k);
     if (capacity < 64) capacity = 64;
     size_t free_b = 0, total_b = 0;
@@ -352,7 +357,7 @@ static int table_prepare(pc_ctx* c, int k, int64_t capacity) {
     c->capacity = (uint64_t)capacity; c->k = k;
     StageTimer t(c, ST_TABLE_INIT);
     CU(cudaMemsetAsync(c->table.p, 0, (size_t)capacity * sizeof(pc::CountSlot), c->stream));
-    CU(cudaMemsetAsync(c->d_stats.p, 0, sizeof(pc::CountStats), c->stream));
+    if (reset_stats) CU(cudaMemsetAsync(c->d_stats.p, 0, sizeof(pc::CountStats), c->stream));
     return PC_OK;
 }
 
@@ -388,6 +393,10 @@ int pc_tune(pc_ctx* c, const char* key, int64_t value) {
     else if (k == "part_mode") c->part_mode = (int)value;
     else if (k == "count_items") c->count_items = (int)value;
     else if (k == "probe_mode") c->probe_mode = (int)value;
+    else if (k == "hll_sizing") c->hll_sizing = (int)value;
+    else if (k == "part_casfirst") c->part_casfirst = (int)value;
+    else if (k == "hll_bias_pct") c->hll_bias_pct = (int)value;
+    else if (k == "fused_zero") c->fused_zero = (int)value;
     else if (k == "probe_batch") c->probe_batch = (int)value;
     else if (k == "rep_load_inv") c->rep_load_inv = (int)value;
     else if (k == "part_mbytes") c->part_bytes = std::max<int64_t>(1, value) << 20;
@@ -398,7 +407,8 @@ int pc_tune(pc_ctx* c, const char* key, int64_t value) {
     return PC_OK;
 }
 
-int pc_count(pc_ctx* c, int k, int64_t capacity) {
+int pc_count(pc_ctx* c, int k, int64_t capacity_arg) {
+    int64_t capacity = capacity_arg;
     int rc = use_device(c); if (rc) return rc;
     if (!c->loaded) return fail(PC_ESTATE, "pc_count before pc_load_sequences");
     if (k < 1 || k > 32) return fail(PC_EINVAL, "k = %d unsupported: this path handles 1 <= k <= 32 (uint64 k-mers)", k);
@@ -413,6 +423,7 @@ int pc_count(pc_ctx* c, int k, int64_t capacity) {
         capacity = (int64_t)(bound / c->table_load) + 1024;
     }
     // partition plan: P = 2^pb sub-tables of S slots, each about part_bytes so that it stays L2 resident
+    const bool user_capacity = capacity_arg > 0;
     int pb = 0;
     bool partitioned = c->part_mode == 1 || (c->part_mode < 0 && (size_t)capacity * sizeof(pc::CountSlot) > (size_t)(64ll << 20));
     if (partitioned) {
@@ -420,52 +431,116 @@ int pc_count(pc_ctx* c, int k, int64_t capacity) {
         if (pb == 0) pb = 1;
     }
     uint64_t P = 1ull << pb;
-    uint64_t S = ((uint64_t)capacity + P - 1) / P;
-    if (S < 64) S = 64;
-    capacity = (int64_t)(S * P);
-    rc = table_prepare(c, k, capacity); if (rc) return rc;
-    c->pb = pb; c->part_S = S;
-    if (c->n_words > 0 && !partitioned) {
-        StageTimer t(c, ST_COUNT);
-        rc = launch_count(c); if (rc) return rc;
-    } else if (c->n_words > 0) {
-        int64_t n_stream = ((c->n_words + 255) / 256) * 256 * 32;          // one slot per window start
-        rc = c->kstream.alloc((size_t)n_stream); if (rc) return rc;
-        rc = c->kbuf.alloc((size_t)std::max<int64_t>(windows, 1)); if (rc) return rc;
-        rc = c->d_part_hist.alloc((size_t)3 * P + 2); if (rc) return rc;
-        unsigned long long* bucket_hist = c->d_part_hist.p;
-        unsigned long long* bucket_off = bucket_hist + P;              // [P + 1]
-        unsigned long long* bucket_cur = bucket_off + P + 1;           // [P]
-        {
-            StageTimer t(c, ST_PART_HIST);
-            CU(cudaMemsetAsync(bucket_hist, 0, P * sizeof(unsigned long long), c->stream));
-            c->launches++;
-            pc::k_extract<<<blocks_for(c->n_words, 256), 256, P * sizeof(unsigned int), c->stream>>>(
-                c->words.p, c->nmask.p, c->n_words, k, pb, c->kstream.p, bucket_hist, c->d_stats.p);
-            CU(cudaGetLastError());
-            LAUNCH(c, pc::k_bucket_scan, 1, 1024, bucket_hist, (unsigned int)P, bucket_off, bucket_cur);
-        }
-        c->stream_valid = true; c->stream_k = k;
-        {
-            StageTimer t(c, ST_PART_SCATTER);
-            constexpr int TILE = 8192;
-            size_t smem = (size_t)TILE * 8 + P * 8 + P * 4 + (P + 2) * 4 + (size_t)TILE * 2 + 16;
-            CU(cudaFuncSetAttribute(pc::k_tile_scatter<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            unsigned int grid = (unsigned int)std::min<int64_t>(148 * 2, (n_stream + TILE - 1) / TILE);
-            c->launches++;
-            pc::k_tile_scatter<TILE><<<grid, 256, smem, c->stream>>>(c->kstream.p, n_stream, pb, bucket_off, bucket_cur, c->kbuf.p);
-            CU(cudaGetLastError());
-        }
-        {
+    if (!partitioned || c->n_words == 0) {
+        uint64_t S = std::max<uint64_t>(64, (uint64_t)capacity);
+        rc = table_prepare(c, k, (int64_t)S); if (rc) return rc;
+        c->pb = 0; c->part_S = S;
+        if (c->n_words > 0) {
             StageTimer t(c, ST_COUNT);
-            unsigned int B = (unsigned int)c->part_blocks;
-            if (c->count_items == 8)
-                LAUNCH(c, (pc::k_count_part<8>), (unsigned int)(P * B), 256, c->kbuf.p, bucket_off, pb, S, B, c->table.p, c->d_stats.p);
-            else if (c->count_items == 2)
-                LAUNCH(c, (pc::k_count_part<2>), (unsigned int)(P * B), 256, c->kbuf.p, bucket_off, pb, S, B, c->table.p, c->d_stats.p);
-            else
-                LAUNCH(c, (pc::k_count_part<4>), (unsigned int)(P * B), 256, c->kbuf.p, bucket_off, pb, S, B, c->table.p, c->d_stats.p);
+            rc = launch_count(c); if (rc) return rc;
         }
+        rc = fetch_stats(c); if (rc) return rc;
+        c->counted = true;
+        return PC_OK;
+    }
+
+    // ---- partitioned path: extract -> (size the table) -> tile scatter -> bucket-by-bucket count -------------
+    int64_t n_stream = ((c->n_words + 255) / 256) * 256 * 32;              // one slot per window start
+    rc = c->kstream.alloc((size_t)n_stream); if (rc) return rc;
+    rc = c->kbuf.alloc((size_t)std::max<int64_t>(windows, 1)); if (rc) return rc;
+    rc = c->d_part_hist.alloc((size_t)3 * P + 2); if (rc) return rc;
+    rc = c->d_hll.alloc(PC_HLL_M + P + 2); if (rc) return rc;
+    unsigned long long* bucket_hist = c->d_part_hist.p;
+    unsigned long long* bucket_off = bucket_hist + P;                      // [P + 1]
+    unsigned long long* bucket_cur = bucket_off + P + 1;                   // [P]
+    unsigned int* hll = c->d_hll.p;                                        // [PC_HLL_M]
+    unsigned int* ready = hll + PC_HLL_M;                                  // [P]
+    unsigned int* ticket = ready + P;                                      // [1]
+    CU(cudaMemsetAsync(c->d_stats.p, 0, sizeof(pc::CountStats), c->stream));
+    {
+        StageTimer t(c, ST_PART_HIST);
+        CU(cudaMemsetAsync(bucket_hist, 0, P * sizeof(unsigned long long), c->stream));
+        CU(cudaMemsetAsync(hll, 0, (PC_HLL_M + P + 2) * sizeof(unsigned int), c->stream));
+        c->launches++;
+        pc::k_extract<<<blocks_for(c->n_words, 256), 256, (P + PC_HLL_M) * sizeof(unsigned int), c->stream>>>(
+            c->words.p, c->nmask.p, c->n_words, k, pb, c->kstream.p, bucket_hist, hll, c->d_stats.p);
+        CU(cudaGetLastError());
+        LAUNCH(c, pc::k_bucket_scan, 1, 1024, bucket_hist, (unsigned int)P, bucket_off, bucket_cur);
+    }
+    c->stream_valid = true; c->stream_k = k;
+    // scatter is independent of the table size: issue it before the host looks at the HLL registers
+    {
+        StageTimer t(c, ST_PART_SCATTER);
+        constexpr int TILE = 8192;
+        size_t smem = (size_t)TILE * 8 + P * 8 + P * 4 + (P + 2) * 4 + (size_t)TILE * 2 + 16;
+        CU(cudaFuncSetAttribute(pc::k_tile_scatter<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        unsigned int grid = (unsigned int)std::min<int64_t>(148 * 2, (n_stream + TILE - 1) / TILE);
+        c->launches++;
+        pc::k_tile_scatter<TILE><<<grid, 256, smem, c->stream>>>(c->kstream.p, n_stream, pb, bucket_off, bucket_cur, c->kbuf.p);
+        CU(cudaGetLastError());
+    }
+    // distinct-k-mer estimate (HyperLogLog over a 1/16 hash sample) -> table capacity
+    int64_t cap_upper = capacity;
+    bool estimated = false;
+    if (!user_capacity && c->hll_sizing) {
+        std::vector<unsigned int> reg(PC_HLL_M);
+        CU(cudaMemcpyAsync(reg.data(), hll, PC_HLL_M * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        double m = (double)PC_HLL_M, sum = 0.0; int zeros = 0;
+        for (unsigned int v : reg) { sum += std::ldexp(1.0, -(int)v); zeros += (v == 0); }
+        double est = (0.7213 / (1.0 + 1.079 / m)) * m * m / sum;
+        if (est <= 2.5 * m && zeros > 0) est = m * std::log(m / zeros);
+        double distinct_est = 16.0 * est * (c->hll_bias_pct / 100.0);   // bias: test hook for the retry path
+        int64_t cap_est = (int64_t)(distinct_est * 1.06 / c->table_load) + (int64_t)P * 4096;
+        c->distinct_estimate = (int64_t)distinct_est;
+        if (cap_est < cap_upper) { capacity = cap_est; estimated = true; }
+    }
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        uint64_t S = ((uint64_t)capacity + P - 1) / P;
+        if (S < 64) S = 64;
+        capacity = (int64_t)(S * P);
+        unsigned int B = (unsigned int)c->part_blocks;
+        if (c->fused_zero) {
+            size_t free_b = 0, total_b = 0;
+            CU(cudaMemGetInfo(&free_b, &total_b));
+            size_t need = (size_t)capacity * sizeof(pc::CountSlot);
+            if (need > free_b + c->table.n * sizeof(pc::CountSlot))
+                return fail(PC_ENOMEM, "count table of %lld slots (%.1f GB) does not fit in free HBM (%.1f GB): shard the genome over more GPUs",
+                            (long long)capacity, need / 1e9, free_b / 1e9);
+            rc = c->table.alloc((size_t)capacity); if (rc) return rc;
+            c->capacity = (uint64_t)capacity; c->k = k;
+            CU(cudaMemsetAsync(ready, 0, (P + 2) * sizeof(unsigned int), c->stream));
+            StageTimer t(c, ST_COUNT);
+            if (c->count_items == 2)
+                LAUNCH(c, (pc::k_count_part_fused<2, true>), (unsigned int)(P * B), 256, c->kbuf.p, bucket_off, pb, S, B, c->table.p, ready, ticket, c->d_stats.p);
+            else
+                LAUNCH(c, (pc::k_count_part_fused<4, true>), (unsigned int)(P * B), 256, c->kbuf.p, bucket_off, pb, S, B, c->table.p, ready, ticket, c->d_stats.p);
+        } else {
+            unsigned long long keep_valid = 0;
+            rc = table_prepare(c, k, capacity, /*reset_stats=*/false); if (rc) return rc;
+            (void)keep_valid;
+            StageTimer t(c, ST_COUNT);
+            if (c->count_items == 8)
+                LAUNCH(c, (pc::k_count_part<8, true>), (unsigned int)(P * B), 256, c->kbuf.p, bucket_off, pb, S, B, c->table.p, c->d_stats.p);
+            else if (c->count_items == 2)
+                LAUNCH(c, (pc::k_count_part<2, true>), (unsigned int)(P * B), 256, c->kbuf.p, bucket_off, pb, S, B, c->table.p, c->d_stats.p);
+            else if (!c->part_casfirst)
+                LAUNCH(c, (pc::k_count_part<4, false>), (unsigned int)(P * B), 256, c->kbuf.p, bucket_off, pb, S, B, c->table.p, c->d_stats.p);
+            else
+                LAUNCH(c, (pc::k_count_part<4, true>), (unsigned int)(P * B), 256, c->kbuf.p, bucket_off, pb, S, B, c->table.p, c->d_stats.p);
+        }
+        c->pb = pb; c->part_S = S;
+        rc = fetch_stats(c);
+        if (rc == PC_ENOMEM && estimated && attempt == 0) {
+            // the estimate was too small (an adversarial hash sample): redo the count with the safe upper bound
+            capacity = cap_upper; estimated = false;
+            pc::CountStats z = c->h_stats; z.distinct = 0; z.overflow = 0; z.max_probe = 0;
+            CU(cudaMemcpyAsync(c->d_stats.p, &z, sizeof z, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            continue;
+        }
+        if (rc) return rc;
+        break;
     }
     rc = fetch_stats(c); if (rc) return rc;
     c->counted = true;
@@ -477,6 +552,7 @@ int pc_count_info(pc_ctx* c, int64_t info[8]) {
     memset(info, 0, 8 * sizeof(int64_t));
     info[0] = (int64_t)c->capacity; info[1] = (int64_t)c->h_stats.distinct; info[2] = (int64_t)c->h_stats.valid_windows;
     info[3] = (int64_t)(c->capacity * sizeof(pc::CountSlot)); info[4] = (int64_t)c->h_stats.max_probe; info[5] = c->k;
+    info[6] = c->distinct_estimate; info[7] = c->pb;
     return PC_OK;
 }
 

@@ -11,6 +11,8 @@ namespace pc {
 // Count table slot (K3).  skey = ~kmer so that a zeroed table is empty (the all-ones pattern is never a
 // canonical-min k-mer: its reverse complement, all A, is smaller).  16-byte slots keep key and count in one
 // 32-byte DRAM sector: one sector read per probe instead of two with a split layout.
+// count holds (occurrences - 1): claiming a slot with the CAS already records the first occurrence, so a new k-mer
+// costs one L2 transaction and only repeats pay for a RED.
 struct __align__(16) CountSlot {
     unsigned long long skey;
     unsigned int count;
@@ -174,17 +176,69 @@ __device__ __forceinline__ void count_insert(CountSlot* __restrict__ table, uint
     for (;;) {
         if (cur == 0ull) {
             cur = atomicCAS(&table[slot].skey, 0ull, skey);
-            if (cur == 0ull) { ++new_keys; cur = skey; }
+            if (cur == 0ull) { ++new_keys; break; }            // claimed: count field 0 == one occurrence
         }
         if (cur == skey) {
             atomicAdd(&table[slot].count, 1u);                // result unused -> RED
             break;
         }
-        if (++probes > PC_PROBE_LIMIT) { atomicAdd(&stats->overflow, 1ull); break; }
+        if (++probes > PC_PROBE_LIMIT || probes >= capacity) { atomicAdd(&stats->overflow, 1ull); break; }
         if (++slot == capacity) slot = 0;
         cur = ldcg_u64(&table[slot].skey);
     }
     max_probe = max(max_probe, probes);
+}
+
+// CAS-first variant for L2-resident sub-tables: no separate load, one ATOM per new k-mer, ATOM + RED per repeat.
+// `cur` is the value the first CAS on table[slot] returned.
+__device__ __forceinline__ void count_insert_cas(CountSlot* __restrict__ table, uint64_t capacity, uint64_t slot,
+                                                 unsigned long long skey, unsigned long long cur,
+                                                 unsigned int& new_keys, unsigned int& max_probe, CountStats* stats)
+{
+    unsigned int probes = 0;
+    for (;;) {
+        if (cur == 0ull) { ++new_keys; break; }
+        if (cur == skey) { atomicAdd(&table[slot].count, 1u); break; }
+        if (++probes > PC_PROBE_LIMIT || probes >= capacity) { atomicAdd(&stats->overflow, 1ull); break; }
+        if (++slot == capacity) slot = 0;
+        cur = atomicCAS(&table[slot].skey, 0ull, skey);
+    }
+    max_probe = max(max_probe, probes);
+}
+
+// insert phases shared by the count kernels: the table loads of a batch are already in flight / landed in cur[];
+// (1) every CAS the batch needs is issued back to back, (2) results are folded, (3) REDs go out, and only keys that
+// collided with a different k-mer enter the (serial) linear-probing loop.
+template <int N>
+__device__ __forceinline__ void count_insert_batch(CountSlot* __restrict__ table, uint64_t capacity, const uint64_t (&slot)[N],
+                                                   const unsigned long long (&skey)[N], unsigned long long (&cur)[N],
+                                                   const bool (&on)[N], unsigned int& new_keys, unsigned int& max_probe,
+                                                   CountStats* stats)
+{
+    bool cas[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        cas[j] = on[j] && cur[j] == 0ull;
+        if (cas[j]) cur[j] = atomicCAS(&table[slot[j]].skey, 0ull, skey[j]);
+    }
+    bool claimed[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        claimed[j] = cas[j] && cur[j] == 0ull;
+        new_keys += claimed[j];
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+        if (on[j] && !claimed[j] && cur[j] == skey[j]) atomicAdd(&table[slot[j]].count, 1u);
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+        if (on[j] && !claimed[j] && cur[j] != skey[j]) {       // occupied by another k-mer: probe onwards
+            uint64_t s = slot[j] + 1; if (s == capacity) s = 0;
+            unsigned long long c2 = ldcg_u64(&table[s].skey);
+            unsigned int mp = 0;
+            count_insert(table, capacity, s, skey[j], c2, new_keys, mp, stats);
+            max_probe = max(max_probe, mp + 1u);
+        }
 }
 
 __device__ __forceinline__ void prefetch_l2(const void* p) {
@@ -242,12 +296,17 @@ k_count(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, 
                     cur[j] = ((vmask >> j) & 1u) ? ldcg_u64(&table[slot[j]].skey) : 0ull;
                 }
             }
+            if (MODE == 2) {
 #pragma unroll
-            for (int j = 0; j < BATCH; ++j)
-                if ((vmask >> j) & 1u) {
-                    if (MODE == 2 && cur[j] == 0ull) { ++new_keys; cur[j] = skey[j]; }
-                    count_insert(table, capacity, slot[j], skey[j], cur[j], new_keys, max_probe, stats);
-                }
+                for (int j = 0; j < BATCH; ++j)
+                    if ((vmask >> j) & 1u)
+                        count_insert_cas(table, capacity, slot[j], skey[j], cur[j], new_keys, max_probe, stats);
+            } else {
+                bool on[BATCH];
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) on[j] = (vmask >> j) & 1u;
+                count_insert_batch<BATCH>(table, capacity, slot, skey, cur, on, new_keys, max_probe, stats);
+            }
             nvalid += __popc(vmask);
         }
     }
@@ -275,6 +334,7 @@ k_count(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, 
 __device__ __forceinline__ unsigned int part_of(uint64_t h, int pb) { return pb ? (unsigned int)(h >> (64 - pb)) : 0u; }
 __device__ __forceinline__ uint64_t slot_in_part(uint64_t h, int pb, uint64_t S) { return __umul64hi(h << pb, S); }
 
+#define PC_HLL_M 4096u
 #define PC_KEY_SENTINEL (~0ull)      // never a canonical-min k-mer (its reverse complement, all A, is smaller)
 
 // pass A: packed genome -> stream of canonical k-mers, one slot per window start (invalid windows hold the
@@ -282,11 +342,15 @@ __device__ __forceinline__ uint64_t slot_in_part(uint64_t h, int pb, uint64_t S)
 // instruction writes 256 contiguous bytes.
 __global__ void __launch_bounds__(256)
 k_extract(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, int64_t n_words, int k, int pb,
-          uint64_t* __restrict__ stream, unsigned long long* __restrict__ bucket_hist, CountStats* __restrict__ stats)
+          uint64_t* __restrict__ stream, unsigned long long* __restrict__ bucket_hist, unsigned int* __restrict__ hll,
+          CountStats* __restrict__ stats)
 {
-    extern __shared__ unsigned int shh[];                     // [P] bucket counts of this CTA
+    // hll: HyperLogLog registers (PC_HLL_M of them) over the 1/16 hash-sample of the k-mers whose low hash nibble
+    // is 0; the host turns them into an estimate of the number of DISTINCT k-mers to size the count table.
+    extern __shared__ unsigned int shh[];                     // [P] bucket counts of this CTA, then [PC_HLL_M] registers
     const unsigned int P = 1u << pb;
-    for (unsigned int i = threadIdx.x; i < P; i += blockDim.x) shh[i] = 0;
+    unsigned int* shl = shh + P;
+    for (unsigned int i = threadIdx.x; i < P + PC_HLL_M; i += blockDim.x) shh[i] = 0;
     __syncthreads();
     int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int lane = threadIdx.x & 31;
@@ -300,7 +364,16 @@ k_extract(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask
             bool v = r.valid(b);
             uint64_t key = r.canonical();
             __stcs(out + b * 32, v ? key : PC_KEY_SENTINEL);
-            if (v) { atomicAdd(&shh[part_of(mix64(key), pb)], 1u); ++nvalid; }
+            if (v) {
+                uint64_t h = mix64(key);
+                atomicAdd(&shh[part_of(h, pb)], 1u);
+                ++nvalid;
+                if ((h & 15ull) == 0ull) {
+                    unsigned int idx = (unsigned int)(h >> 4) & (PC_HLL_M - 1);
+                    unsigned int rho = (unsigned int)__clzll((h >> 16) << 16 | 0x8000ull) + 1u;
+                    atomicMax(&shl[idx], rho);
+                }
+            }
             if (b < 31) r.step(b);
         }
     } else {
@@ -310,6 +383,8 @@ k_extract(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask
     __syncthreads();
     for (unsigned int i = threadIdx.x; i < P; i += blockDim.x)
         if (shh[i]) atomicAdd(&bucket_hist[i], (unsigned long long)shh[i]);
+    for (unsigned int i = threadIdx.x; i < PC_HLL_M; i += blockDim.x)
+        if (shl[i]) atomicMax(&hll[i], shl[i]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(0xFFFFFFFFu, nvalid, o);
     if (lane == 0 && nvalid) atomicAdd(&stats->valid_windows, (unsigned long long)nvalid);
@@ -423,7 +498,7 @@ k_tile_scatter(const uint64_t* __restrict__ stream, int64_t n_stream, int pb,
 
 // pass C: count one bucket after the other.  blockIdx = bucket * B + b: blocks are dispatched in index order, so
 // at any time the resident blocks work on one or two adjacent buckets whose sub-tables (S slots) sit in L2.
-template <int ITEMS>
+template <int ITEMS, bool CASFIRST>
 __global__ void __launch_bounds__(256)
 k_count_part(const uint64_t* __restrict__ kbuf, const unsigned long long* __restrict__ bucket_off, int pb, uint64_t S,
              unsigned int B, CountSlot* __restrict__ table, CountStats* __restrict__ stats)
@@ -432,22 +507,115 @@ k_count_part(const uint64_t* __restrict__ kbuf, const unsigned long long* __rest
     unsigned long long beg = bucket_off[q], end = bucket_off[q + 1];
     CountSlot* sub = table + (uint64_t)q * S;
     unsigned int new_keys = 0, max_probe = 0;
-    for (unsigned long long i0 = beg + ((unsigned long long)b * 256u + threadIdx.x) * ITEMS; i0 < end;
-         i0 += (unsigned long long)B * 256u * ITEMS) {
+    // software pipeline: the bucket keys of the next iteration (a DRAM stream) are requested before this
+    // iteration's table accesses (L2) are issued
+    const unsigned long long stride = (unsigned long long)B * 256u * ITEMS;
+    unsigned long long i0 = beg + ((unsigned long long)b * 256u + threadIdx.x) * ITEMS;
+    uint64_t nkey[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) nkey[j] = (i0 + j < end) ? __ldcs(kbuf + i0 + j) : PC_KEY_SENTINEL;
+    for (; i0 < end; i0 += stride) {
         unsigned long long skey[ITEMS]; uint64_t slot[ITEMS]; unsigned long long cur[ITEMS];
         bool on[ITEMS];
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
-            on[j] = i0 + j < end;
-            uint64_t key = on[j] ? __ldcs(kbuf + i0 + j) : 0ull;          // streaming: evict-first in L2
+            uint64_t key = nkey[j];
+            on[j] = key != PC_KEY_SENTINEL;
             skey[j] = ~key;
             slot[j] = slot_in_part(mix64(key), pb, S);
         }
 #pragma unroll
-        for (int j = 0; j < ITEMS; ++j) cur[j] = on[j] ? ldcg_u64(&sub[slot[j]].skey) : 0ull;
+        for (int j = 0; j < ITEMS; ++j) nkey[j] = (i0 + stride + j < end) ? __ldcs(kbuf + i0 + stride + j) : PC_KEY_SENTINEL;
+        if (CASFIRST) {
 #pragma unroll
-        for (int j = 0; j < ITEMS; ++j)
-            if (on[j]) count_insert(sub, S, slot[j], skey[j], cur[j], new_keys, max_probe, stats);
+            for (int j = 0; j < ITEMS; ++j) cur[j] = on[j] ? atomicCAS(&sub[slot[j]].skey, 0ull, skey[j]) : 0ull;
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j)
+                if (on[j]) count_insert_cas(sub, S, slot[j], skey[j], cur[j], new_keys, max_probe, stats);
+        } else {
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) cur[j] = on[j] ? ldcg_u64(&sub[slot[j]].skey) : 0ull;
+            count_insert_batch<ITEMS>(sub, S, slot, skey, cur, on, new_keys, max_probe, stats);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        new_keys += __shfl_xor_sync(0xFFFFFFFFu, new_keys, o);
+        max_probe = max(max_probe, __shfl_xor_sync(0xFFFFFFFFu, max_probe, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (new_keys) atomicAdd(&stats->distinct, (unsigned long long)new_keys);
+        if (max_probe > 8) atomicMax(&stats->max_probe, (unsigned long long)max_probe);
+    }
+}
+
+// pass C, fused with the table initialisation.  Virtual block ids come from a ticket counter, so a block with a
+// smaller ticket is always already running (the decoupled-look-back guarantee).  Block (q, b) first zeroes slice b
+// of sub-table q+1 (full-sector stores: the lines are created dirty in L2, nothing is read from or written to
+// DRAM), publishes that through ready[q+1], waits until all B slices of its own sub-table q are zeroed, then counts
+// slice b of bucket q.  The table is never memset from the host and every table line crosses the HBM bus exactly
+// once, on eviction.
+template <int ITEMS, bool CASFIRST>
+__global__ void __launch_bounds__(256)
+k_count_part_fused(const uint64_t* __restrict__ kbuf, const unsigned long long* __restrict__ bucket_off, int pb, uint64_t S,
+                   unsigned int B, CountSlot* __restrict__ table, unsigned int* __restrict__ ready /* [P] zeroed */,
+                   unsigned int* __restrict__ ticket, CountStats* __restrict__ stats)
+{
+    __shared__ unsigned int vb_s;
+    if (threadIdx.x == 0) vb_s = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const unsigned int P = 1u << pb;
+    unsigned int q = vb_s / B, b = vb_s % B;
+    // phase 0: zero slice b of sub-table q+1 (and of sub-table 0 for the very first bucket)
+    uint64_t per = (S + B - 1) / B;
+    uint64_t z0 = min(S, (uint64_t)b * per), z1 = min(S, z0 + per);
+    for (unsigned int tq = (q == 0 ? 0u : q + 1u); tq <= q + 1u && tq < P; ++tq) {
+        uint4* dst = reinterpret_cast<uint4*>(table + (uint64_t)tq * S);
+        for (uint64_t i = z0 + threadIdx.x; i < z1; i += 256) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(&ready[tq], 1u);
+    }
+    // phase 1: wait for sub-table q
+    if (threadIdx.x == 0) {
+        while (atomicAdd(&ready[q], 0u) < B) __nanosleep(100);
+        __threadfence();
+    }
+    __syncthreads();
+    // phase 2: count
+    unsigned long long beg = bucket_off[q], end = bucket_off[q + 1];
+    CountSlot* sub = table + (uint64_t)q * S;
+    unsigned int new_keys = 0, max_probe = 0;
+    // software pipeline: the bucket keys of the next iteration (a DRAM stream) are requested before this
+    // iteration's table accesses (L2) are issued
+    const unsigned long long stride = (unsigned long long)B * 256u * ITEMS;
+    unsigned long long i0 = beg + ((unsigned long long)b * 256u + threadIdx.x) * ITEMS;
+    uint64_t nkey[ITEMS];
+#pragma unroll
+    for (int j = 0; j < ITEMS; ++j) nkey[j] = (i0 + j < end) ? __ldcs(kbuf + i0 + j) : PC_KEY_SENTINEL;
+    for (; i0 < end; i0 += stride) {
+        unsigned long long skey[ITEMS]; uint64_t slot[ITEMS]; unsigned long long cur[ITEMS];
+        bool on[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            uint64_t key = nkey[j];
+            on[j] = key != PC_KEY_SENTINEL;
+            skey[j] = ~key;
+            slot[j] = slot_in_part(mix64(key), pb, S);
+        }
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) nkey[j] = (i0 + stride + j < end) ? __ldcs(kbuf + i0 + stride + j) : PC_KEY_SENTINEL;
+        if (CASFIRST) {
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) cur[j] = on[j] ? atomicCAS(&sub[slot[j]].skey, 0ull, skey[j]) : 0ull;
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j)
+                if (on[j]) count_insert_cas(sub, S, slot[j], skey[j], cur[j], new_keys, max_probe, stats);
+        } else {
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) cur[j] = on[j] ? ldcg_u64(&sub[slot[j]].skey) : 0ull;
+            count_insert_batch<ITEMS>(sub, S, slot, skey, cur, on, new_keys, max_probe, stats);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -476,10 +644,14 @@ k_merge(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, 
         unsigned long long cur = ldcg_u64(&table[slot].skey);
         if (cur == 0ull) {
             cur = atomicCAS(&table[slot].skey, 0ull, skey);
-            if (cur == 0ull) { atomicAdd(&stats->distinct, 1ull); cur = skey; }
+            if (cur == 0ull) {                                // claimed: the slot already stands for one occurrence
+                atomicAdd(&stats->distinct, 1ull);
+                if (add > 1u) atomicAdd(&table[slot].count, add - 1u);
+                break;
+            }
         }
         if (cur == skey) { atomicAdd(&table[slot].count, add); break; }
-        if (++probes > PC_PROBE_LIMIT) { atomicAdd(&stats->overflow, 1ull); break; }
+        if (++probes > PC_PROBE_LIMIT || probes >= capacity) { atomicAdd(&stats->overflow, 1ull); break; }
         if (++slot == capacity) slot = 0;
     }
 }
@@ -497,7 +669,7 @@ k_select(const CountSlot* __restrict__ table, uint64_t capacity, unsigned int lo
         bool keep = false; unsigned long long skey = 0; unsigned int cnt = 0;
         if (i < capacity) {
             uint4 s = ldnc_u4(table + i);
-            skey = ((unsigned long long)s.y << 32) | s.x; cnt = s.z;
+            skey = ((unsigned long long)s.y << 32) | s.x; cnt = s.z + 1u;          // stored = occurrences - 1
             keep = skey != 0ull && cnt >= low && cnt <= high;
         }
         unsigned int bal = __ballot_sync(0xFFFFFFFFu, keep);
@@ -552,7 +724,7 @@ k_owner_scatter(const CountSlot* __restrict__ table, uint64_t capacity, unsigned
             if (lane == leader) base = atomicAdd(&cursor[o], (unsigned long long)__popc(peers));
             base = __shfl_sync(peers, base, leader);
             unsigned long long pos = base + __popc(peers & ((1u << lane) - 1u));
-            out_keys[pos] = ~skey; out_counts[pos] = s.z;
+            out_keys[pos] = ~skey; out_counts[pos] = s.z + 1u;
         }
     }
 }

@@ -118,10 +118,23 @@ def test_partitioned_count_equals_direct_and_oracle(ctx, k, mb):
             assert np.array_equal(counts[order].astype(np.uint64), want_counts), "mode %d" % mode
             info = ctx.count_info()
             assert info["valid_windows"] == n_windows and info["distinct"] == len(want_keys)
-        ctx.tune(part_mode=1, part_mbytes=mb)
+        # every combination of table initialisation (host memset / fused in-kernel zeroing) and table sizing
+        # (window upper bound / HyperLogLog estimate, including an estimate that is far too small -> retry)
+        for fused, hll, bias in ((0, 0, 100), (1, 0, 100), (0, 1, 100), (1, 1, 100), (1, 1, 15), (0, 1, 15)):
+            ctx.tune(part_mode=1, part_mbytes=mb, fused_zero=fused, hll_sizing=hll, hll_bias_pct=bias)
+            ctx.count(k)
+            keys, counts = ctx.dump_counts(1)
+            order = np.argsort(keys)
+            assert np.array_equal(keys[order], want_keys), (fused, hll, bias)
+            assert np.array_equal(counts[order].astype(np.uint64), want_counts), (fused, hll, bias)
+            info = ctx.count_info()
+            assert info["valid_windows"] == n_windows and info["distinct"] == len(want_keys)
+            if hll and bias == 100:
+                assert abs(info["distinct_estimate"] - len(want_keys)) <= 0.1 * len(want_keys)
+        ctx.tune(part_mode=1, part_mbytes=mb, fused_zero=1, hll_sizing=1, hll_bias_pct=100)
         _check_against_c_oracle(ctx, seq, off, names, 20000, k, 5)
     finally:
-        ctx.tune(part_mode=-1, part_mbytes=32)
+        ctx.tune(part_mode=-1, part_mbytes=64, fused_zero=0, hll_sizing=0, hll_bias_pct=100)
 
 
 def test_small_table_reports_overflow_not_garbage(ctx):
