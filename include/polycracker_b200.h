@@ -106,6 +106,11 @@ int pc_set_selected(pc_ctx* ctx, const uint64_t* keys, int64_t n, int k, int loc
  * (polycracker.py:322-327).  Result: CSR (n_rows x n_selected), entry = number of windows of chunk i whose
  * canonical k-mer is repeat k-mer j.  Column indices ascending within a row. */
 int pc_build_matrix(pc_ctx* ctx, const int32_t* chunk_row, int64_t n_rows, int64_t* nnz);
+/* K6 alone, from hit lists that already exist (generate_Kmer_Matrix invoked on a blasted_merged.bed text artefact,
+ * polycracker.py:343-355): row r holds column ids cols[row_offsets[r] .. row_offsets[r+1]) with multiplicity (host
+ * arrays).  The Counter -> dok -> sparse work (sort + run-length encode per row, df) runs on the GPU. */
+int pc_matrix_from_hits(pc_ctx* ctx, const int64_t* row_offsets, const int32_t* cols, int64_t n_rows, int64_t n_cols,
+                        int64_t* nnz);
 int pc_csr_get(pc_ctx* ctx, int64_t* indptr, int32_t* indices, float* data, int loc);
 int pc_df_get(pc_ctx* ctx, int32_t* df, int loc);                      /* stored entries per column */
 
@@ -147,6 +152,13 @@ int pc_fasta_read(const char* path, uint8_t* seq, int64_t* offsets, char* names)
 /* text writers: "KMER\tCOUNT\n" (.kcount) and ">KMER\nKMER\n" (.kcount.fa) */
 int pc_write_kcount(const char* path, const uint64_t* keys, const uint32_t* counts, int64_t n, int k, int append);
 int pc_write_kmer_fasta(const char* path, const uint64_t* keys, int64_t n, int k, int rc_labels);
+
+/* text artefacts of the mapping stages from a CSR (row = chunk, column = repeat k-mer): mode 0 headerless SAM
+ * (polycracker.py:252; QNAME/RNAME as blast2bed reads them, POS 0), mode 1 blasted.bed, mode 2 blasted_merged.bed
+ * (polycracker.py:272, 280).  names_blob/name_off: row labels back to back; row_len: chunk lengths. */
+int pc_write_hit_lines(const char* path, int mode, const int64_t* indptr, const int32_t* indices, const float* data,
+                       int64_t n_rows, const uint64_t* keys, int k, const char* names_blob, const int64_t* name_off,
+                       const int64_t* row_len, int append);
 
 /* deterministic synthetic polyploid genome (bench + tests).  See csrc/synth.cpp. */
 typedef struct pc_synth_params {

@@ -68,6 +68,7 @@ _SIGS = {
     "pc_selected_get": (C.c_int, [_vp, _vp, C.c_int]),
     "pc_set_selected": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, _P(_i64)]),
     "pc_build_matrix": (C.c_int, [_vp, _vp, _i64, _P(_i64)]),
+    "pc_matrix_from_hits": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _P(_i64)]),
     "pc_csr_get": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int]),
     "pc_df_get": (C.c_int, [_vp, _vp, C.c_int]),
     "pc_tfidf": (C.c_int, [_vp, _i64, _vp, C.c_int]),
@@ -86,6 +87,7 @@ _SIGS = {
     "pc_fasta_read": (C.c_int, [C.c_char_p, _vp, _vp, _vp]),
     "pc_write_kcount": (C.c_int, [C.c_char_p, _vp, _vp, _i64, C.c_int, C.c_int]),
     "pc_write_kmer_fasta": (C.c_int, [C.c_char_p, _vp, _i64, C.c_int, C.c_int]),
+    "pc_write_hit_lines": (C.c_int, [C.c_char_p, C.c_int, _vp, _vp, _vp, _i64, _vp, C.c_int, _vp, _vp, _vp, C.c_int]),
     "pc_synth_n_chrom": (_i64, [_P(SynthParams)]),
     "pc_synth_chrom_len": (C.c_int, [_P(SynthParams), _i64, _P(_i64), C.c_char_p]),
     "pc_synth_chrom": (C.c_int, [_P(SynthParams), _i64, _vp]),
@@ -183,6 +185,23 @@ def write_kmer_fasta(path, keys, k, rc_labels=False):
     keys = np.ascontiguousarray(keys, dtype=np.uint64)
     check(lib.pc_write_kmer_fasta(path.encode(), keys.ctypes.data, len(keys), k, int(rc_labels)),
           "pc_write_kmer_fasta")
+
+
+def write_hit_lines(path, mode, indptr, indices, data, keys, k, row_names, row_len, append=False):
+    """mode: 'sam' | 'bed' | 'merged' (see pc_write_hit_lines)."""
+    indptr = np.ascontiguousarray(indptr, dtype=np.int64)
+    indices = np.ascontiguousarray(indices, dtype=np.int32)
+    data = np.ascontiguousarray(data, dtype=np.float32)
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    blob = "".join(row_names).encode()
+    name_off = np.zeros(len(row_names) + 1, np.int64)
+    name_off[1:] = np.cumsum([len(n.encode()) for n in row_names])
+    row_len = np.ascontiguousarray(row_len, dtype=np.int64)
+    blob_arr = np.frombuffer(blob + b"\0", dtype=np.uint8)
+    check(lib.pc_write_hit_lines(path.encode(), {"sam": 0, "bed": 1, "merged": 2}[mode], indptr.ctypes.data,
+                                 indices.ctypes.data, data.ctypes.data, len(indptr) - 1, keys.ctypes.data, int(k),
+                                 blob_arr.ctypes.data, name_off.ctypes.data, row_len.ctypes.data, int(append)),
+          "pc_write_hit_lines")
 
 
 def host_pack_word(bases):
@@ -335,6 +354,14 @@ class Context:
         cr = np.ascontiguousarray(chunk_row, dtype=np.int32)
         nnz = _i64()
         check(lib.pc_build_matrix(self._h, cr.ctypes.data, int(n_rows), C.byref(nnz)), "pc_build_matrix")
+        return nnz.value
+
+    def matrix_from_hits(self, row_offsets, cols, n_cols):
+        ro = np.ascontiguousarray(row_offsets, dtype=np.int64)
+        cl = np.ascontiguousarray(cols, dtype=np.int32)
+        nnz = _i64()
+        check(lib.pc_matrix_from_hits(self._h, ro.ctypes.data, cl.ctypes.data if len(cl) else None, len(ro) - 1,
+                                      int(n_cols), C.byref(nnz)), "pc_matrix_from_hits")
         return nnz.value
 
     def csr(self, n_rows, nnz):

@@ -1,0 +1,124 @@
+"""`polycracker` console script: the reference's click group (polycracker/polycracker.py:51-54) with the hot-path
+sub-commands re-implemented on the GPU.  Option names, short flags and defaults are the reference's
+(polycracker.py:113-122, 174-179, 212-218, 241-249, 255-262, 299-316) so polycracker.nf and the README recipes call
+them unchanged.  Sub-commands outside the hot path (transform_plot, cluster, subgenomeExtraction, plots, ...) stay with
+the reference package.
+"""
+import click
+
+from . import stages
+from .binding import PolycrackerError
+
+CONTEXT_SETTINGS = dict(help_option_names=["-h", "--help"], max_content_width=90)
+
+
+@click.group(context_settings=CONTEXT_SETTINGS)
+@click.version_option(version="1.1.3+b200")
+def polycracker():
+    pass
+
+
+def _run(fn, **kw):
+    try:
+        return fn(**kw)
+    except PolycrackerError as exc:          # the reference ignores tool failures; this path fails loudly
+        raise click.ClickException(str(exc))
+
+
+@polycracker.command(name="splitFasta")
+@click.option("-i", "--fasta_file", help="Input polyploid fasta filename.", type=click.Path(exists=False))
+@click.option("-d", "--fasta_path", default="./fasta_files/", help="Directory containing polyploids fasta file", show_default=True, type=click.Path(exists=False))
+@click.option("-c", "--chunk_size", default=75000, help="Length of chunk of split fasta file", show_default=True)
+@click.option("-p", "--prefilter", default=0, help="Remove chunks based on certain conditions as a preprocessing step to reduce memory", show_default=True)
+@click.option("-m", "--min_chunk_size", default=0, help="If min_chunk_threshold and prefilter flag is on, use chunks with lengths greater than a certain size", show_default=True)
+@click.option("-r", "--remove_non_chunk", default=0, help="If min_chunk_threshold and prefilter flag is on, remove chunks that are not the same size as chunk_size", show_default=True)
+@click.option("-t", "--min_chunk_threshold", default=0, help="If prefilter is on, remove chunks with lengths less than a certain threshold", show_default=True)
+@click.option("-l", "--low_memory", default=0, help="Must use with prefilter in order for prefilter to work.", show_default=True)
+def splitFasta(fasta_file, fasta_path, chunk_size, prefilter, min_chunk_size, remove_non_chunk, min_chunk_threshold, low_memory):
+    """Split fasta file into chunks of a specified length"""
+    _run(stages.splitFasta, fasta_file=fasta_file, fasta_path=fasta_path, chunk_size=chunk_size, prefilter=prefilter,
+         min_chunk_size=min_chunk_size, remove_non_chunk=remove_non_chunk, min_chunk_threshold=min_chunk_threshold,
+         low_memory=low_memory)
+
+
+@polycracker.command(name="writeKmerCount")
+@click.option("-d", "--fasta_path", default="./fasta_files/", help="Directory containing chunked polyploids fasta file", show_default=True, type=click.Path(exists=False))
+@click.option("-k", "--kmercount_path", default="./kmercount_files", help="Directory containing kmer count files", show_default=True, type=click.Path(exists=False))
+@click.option("-l", "--kmer_length", default="23,31", help="Length of kmers to find; can include multiple lengths if comma delimited (e.g. 23,25,27)", show_default=True)
+@click.option("-m", "--blast_mem", default="100", help="Accepted for compatibility (JVM heap of the BBTools run it replaces); ignored.", show_default=True)
+def writeKmerCount(fasta_path, kmercount_path, kmer_length, blast_mem):
+    """Counts the canonical k-mers of every chunked fasta file on the GPU (replaces kmercountexact.sh / jellyfish)"""
+    _run(stages.writeKmerCount, fasta_path=fasta_path, kmercount_path=kmercount_path, kmer_length=kmer_length, blast_mem=blast_mem)
+
+
+@polycracker.command(name="kmer2Fasta")
+@click.option("-k", "--kmercount_path", default="./kmercount_files/", help="Directory containing kmer count files", show_default=True, type=click.Path(exists=False))
+@click.option("-lc", "--kmer_low_count", default=100, help="Omit kmers from analysis that have less than x occurrences throughout genome.", show_default=True)
+@click.option("-hb", "--high_bool", default=0, help="Enter 1 if you would like to use the kmer_high_count option.", show_default=True)
+@click.option("-hc", "--kmer_high_count", default=2000000, help="If high_bool is set to one, omit kmers that have greater than x occurrences.", show_default=True)
+@click.option("-s", "--sampling_sensitivity", default=1, help="If this option, x, is set greater than one, kmers are sampled at lower frequency, and total number of kmers included in the analysis is reduced to (total #)/(sampling_sensitivity), after threshold filtering", show_default=True)
+def kmer2Fasta(kmercount_path, kmer_low_count, high_bool, kmer_high_count, sampling_sensitivity):
+    """Converts kmer count file into a fasta file for blasting, after some threshold filtering and sampling"""
+    _run(stages.kmer2Fasta, kmercount_path=kmercount_path, kmer_low_count=kmer_low_count, high_bool=high_bool,
+         kmer_high_count=kmer_high_count, sampling_sensitivity=sampling_sensitivity)
+
+
+@polycracker.command(name="blast_kmers")
+@click.option("-m", "--blast_mem", default="48", help="Accepted for compatibility; ignored.", show_default=True)
+@click.option("-r", "--reference_genome", help="Genome to blast against.", type=click.Path(exists=False))
+@click.option("-k", "--kmer_fasta", help="Kmer fasta converted from kmer count file", type=click.Path(exists=False))
+@click.option("-o", "--output_file", default="results.sam", show_default=True, help="Output sam file.", type=click.Path(exists=False))
+@click.option("-kl", "--kmer_length", default=13, help="Accepted for compatibility (bbmap seed length); ignored.", show_default=True)
+@click.option("-pm", "--perfect_mode", default=1, help="Perfect mode (must be 1: exact matching).", show_default=True)
+@click.option("-t", "--threads", default=5, help="Accepted for compatibility; ignored.", show_default=True)
+def blast_kmers(blast_mem, reference_genome, kmer_fasta, output_file, kmer_length, perfect_mode, threads):
+    """Maps kmers fasta file to a reference genome (exact matches, either strand) on the GPU."""
+    _run(stages.blast_kmers, blast_mem=blast_mem, reference_genome=reference_genome, kmer_fasta=kmer_fasta,
+         output_file=output_file, kmer_length=kmer_length, perfect_mode=perfect_mode, threads=threads)
+
+
+@polycracker.command(name="blast2bed")
+@click.option("-i", "--blast_file", default="./blast_files/results.sam", help="Output file after blasting kmers to genome. Must be input into this command.", show_default=True, type=click.Path(exists=False))
+@click.option("-b", "--bb", default=1, help="Whether bbtools were used in generating blasted sam file.", show_default=True)
+@click.option("-l", "--low_memory", default=0, help="Do not merge the bed file. Takes longer to process but uses lower memory.", show_default=True)
+@click.option("-o", "--output_bed_file", default="blasted.bed", show_default=True, help="Output bed file, not merged.", type=click.Path(exists=False))
+@click.option("-om", "--output_merged_bed_file", default="blasted_merged.bed", show_default=True, help="Output bed file, merged.", type=click.Path(exists=False))
+@click.option("-ex", "--external_call", is_flag=True, help="External call from non-polyCRACKER pipeline.")
+def blast2bed(blast_file, bb, low_memory, output_bed_file, output_merged_bed_file, external_call):
+    """Converts the blast results from blast or bbtools into a bed file"""
+    _run(stages.blast2bed, blast_file=blast_file, bb=bb, low_memory=low_memory, output_bed_file=output_bed_file,
+         output_merged_bed_file=output_merged_bed_file, external_call=external_call)
+
+
+@polycracker.command(name="generate_Kmer_Matrix")
+@click.option("-d", "--kmercount_path", default="./kmercount_files/", help="Directory containing kmer count files", type=click.Path(exists=False))
+@click.option("-g", "--genome", help="File name of chunked genome fasta", type=click.Path(exists=False))
+@click.option("-c", "--chunk_size", default=75000, help="Length of chunk of split/chunked fasta file", show_default=True)
+@click.option("-mc", "--min_chunk_size", default=0, help="If min_chunk_threshold and prefilter flag is on, use chunks with lengths greater than a certain size", show_default=True)
+@click.option("-r", "--remove_non_chunk", default=1, help="If min_chunk_threshold and prefilter flag is on, remove chunks that are not the same size as chunk_size", show_default=True)
+@click.option("-t", "--min_chunk_threshold", default=0, help="If prefilter is on, remove chunks with lengths less than a certain threshold", show_default=True)
+@click.option("-l", "--low_memory", default=0, help="Must use with prefilter in order for prefilter to work. Without prefilter, populates matrix using unmerged blasted bed (slow).", show_default=True)
+@click.option("-p", "--prefilter", default=0, help="If selected, will now add chunks that were removed during preprocessing.", show_default=True)
+@click.option("-f", "--fasta_path", default="./fasta_files/", help="Directory containing chunked polyploids fasta file", type=click.Path(exists=False))
+@click.option("-gs", "--genome_split_name", help="File name of chunked genome fasta", type=click.Path(exists=False))
+@click.option("-go", "--original_genome", help="File name of original, prechunked genome fasta", type=click.Path(exists=False))
+@click.option("-i", "--input_bed_file", default="blasted.bed", show_default=True, help="Input bed file, not merged.", type=click.Path(exists=False))
+@click.option("-im", "--input_merged_bed_file", default="blasted_merged.bed", show_default=True, help="Input bed file, merged.", type=click.Path(exists=False))
+@click.option("-npz", "--output_sparse_matrix", default="clusteringMatrix.npz", show_default=True, help="Output sparse matrix file, in npz format.", type=click.Path(exists=False))
+@click.option("-k", "--output_kmer_file", default="kmers.p", show_default=True, help="Output kmer pickle file.", type=click.Path(exists=False))
+@click.option("-tf", "--tfidf", default=0, help="If set to one, no sequence length normalization will be done.", show_default=True)
+def generate_Kmer_Matrix(kmercount_path, genome, chunk_size, min_chunk_size, remove_non_chunk, min_chunk_threshold, low_memory, prefilter, fasta_path, genome_split_name, original_genome, input_bed_file, input_merged_bed_file, output_sparse_matrix, output_kmer_file, tfidf):
+    """From blasted bed file, generate the sparse k-mer (columns) x subsequence (rows) occurrence matrix"""
+    _run(stages.generate_Kmer_Matrix, kmercount_path=kmercount_path, genome=genome, chunk_size=chunk_size,
+         min_chunk_size=min_chunk_size, remove_non_chunk=remove_non_chunk, min_chunk_threshold=min_chunk_threshold,
+         low_memory=low_memory, prefilter=prefilter, fasta_path=fasta_path, genome_split_name=genome_split_name,
+         original_genome=original_genome, input_bed_file=input_bed_file, input_merged_bed_file=input_merged_bed_file,
+         output_sparse_matrix=output_sparse_matrix, output_kmer_file=output_kmer_file, tfidf=tfidf)
+
+
+def main():
+    polycracker()
+
+
+if __name__ == "__main__":
+    main()

@@ -710,6 +710,37 @@ int pc_set_selected(pc_ctx* c, const uint64_t* keys, int64_t n, int k, int loc, 
 }
 
 // ---------------------------------------------------------------------------------------------- K5 + K6
+// K6: sort every row's hit list, run-length encode it into CSR and accumulate df.  Expects hits_a / d_row_base /
+// d_row_cursor / d_df / d_indptr prepared on the device and c->n_sel = number of columns.
+static int rows_to_csr(pc_ctx* c, int64_t n_rows) {
+    int rc;
+    int bits = 1; while (((int64_t)1 << bits) < c->n_sel) ++bits;
+    int n_passes = std::max(1, (bits + 7) / 8);
+    int32_t* sorted = (n_passes & 1) ? c->hits_b.p : c->hits_a.p;
+    c->nnz = 0;
+    if (n_rows > 0) {
+        {
+            StageTimer t(c, ST_ROWSORT);
+            LAUNCH(c, (pc::k_row_sort<16>), (unsigned int)n_rows, 512, c->hits_a.p, c->hits_b.p, c->d_row_base.p,
+                   c->d_row_cursor.p, n_passes, c->d_row_nnz.p);
+            LAUNCH(c, pc::k_indptr, 1, 1024, c->d_row_nnz.p, n_rows, c->d_indptr.p);
+        }
+        int64_t total = 0;
+        CU(cudaMemcpyAsync(&total, c->d_indptr.p + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->nnz = total;
+        rc = c->d_indices.alloc(std::max<int64_t>(total, 1)); if (rc) return rc;
+        rc = c->d_data.alloc(std::max<int64_t>(total, 1)); if (rc) return rc;
+        StageTimer t(c, ST_EMIT);
+        LAUNCH(c, (pc::k_row_emit<256>), (unsigned int)n_rows, 256, sorted, c->d_row_base.p, c->d_row_cursor.p,
+               c->d_indptr.p, c->d_indices.p, c->d_data.p, c->d_df.p);
+    }
+    CU(cudaStreamSynchronize(c->stream));                      // host staging vectors no longer needed
+    c->n_rows = n_rows;
+    c->built = true;
+    return PC_OK;
+}
+
 int pc_build_matrix(pc_ctx* c, const int32_t* chunk_row, int64_t n_rows, int64_t* nnz) {
     int rc = use_device(c); if (rc) return rc;
     if (!c->loaded || !c->selected) return fail(PC_ESTATE, "pc_build_matrix needs loaded sequences and a repeat set");
@@ -763,30 +794,41 @@ int pc_build_matrix(pc_ctx* c, const int32_t* chunk_row, int64_t n_rows, int64_t
             }
         }
     }
-    int bits = 1; while (((int64_t)1 << bits) < c->n_sel) ++bits;
-    int n_passes = std::max(1, (bits + 7) / 8);
-    int32_t* sorted = (n_passes & 1) ? c->hits_b.p : c->hits_a.p;
-    c->nnz = 0;
-    if (n_rows > 0) {
-        {
-            StageTimer t(c, ST_ROWSORT);
-            LAUNCH(c, (pc::k_row_sort<16>), (unsigned int)n_rows, 512, c->hits_a.p, c->hits_b.p, c->d_row_base.p,
-                   c->d_row_cursor.p, n_passes, c->d_row_nnz.p);
-            LAUNCH(c, pc::k_indptr, 1, 1024, c->d_row_nnz.p, n_rows, c->d_indptr.p);
-        }
-        int64_t total = 0;
-        CU(cudaMemcpyAsync(&total, c->d_indptr.p + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        c->nnz = total;
-        rc = c->d_indices.alloc(std::max<int64_t>(total, 1)); if (rc) return rc;
-        rc = c->d_data.alloc(std::max<int64_t>(total, 1)); if (rc) return rc;
-        StageTimer t(c, ST_EMIT);
-        LAUNCH(c, (pc::k_row_emit<256>), (unsigned int)n_rows, 256, sorted, c->d_row_base.p, c->d_row_cursor.p,
-               c->d_indptr.p, c->d_indices.p, c->d_data.p, c->d_df.p);
+    rc = rows_to_csr(c, n_rows); if (rc) return rc;
+    if (nnz) *nnz = c->nnz;
+    return PC_OK;
+}
+
+// K6 alone, for hit lists that already exist as text artefacts: the separately invoked generate_Kmer_Matrix stage
+// reads blasted_merged.bed (one line per chunk, comma-joined k-mer names with multiplicity, polycracker.py:343-353),
+// the host maps names to ids, and the Counter/dok/tocsc work (sort + run-length encode per row) runs on the GPU.
+int pc_matrix_from_hits(pc_ctx* c, const int64_t* row_offsets, const int32_t* cols, int64_t n_rows, int64_t n_cols,
+                        int64_t* nnz) {
+    int rc = use_device(c); if (rc) return rc;
+    if (n_rows < 0 || n_cols < 0 || !row_offsets || n_rows > 0x7FFFFFFF) return fail(PC_EINVAL, "bad matrix_from_hits arguments");
+    int64_t total = row_offsets[n_rows];
+    if (total < 0 || (total > 0 && !cols)) return fail(PC_EINVAL, "bad hit list");
+    std::vector<unsigned int> cursor(std::max<int64_t>(n_rows, 1), 0);
+    for (int64_t r = 0; r < n_rows; ++r) {
+        int64_t n = row_offsets[r + 1] - row_offsets[r];
+        if (n < 0 || n > 0xFFFFFFFFll) return fail(PC_EINVAL, "row %lld has a bad hit count", (long long)r);
+        cursor[r] = (unsigned int)n;
     }
-    CU(cudaStreamSynchronize(c->stream));                      // row_base (host vector) no longer needed
-    c->n_rows = n_rows;
-    c->built = true;
+    c->built = c->tfidf_done = false;
+    c->n_sel = n_cols;                                         // column universe of this matrix
+    rc = c->d_row_base.alloc(n_rows + 1); if (rc) return rc;
+    rc = c->d_row_cursor.alloc(n_rows); if (rc) return rc;
+    rc = c->d_row_nnz.alloc(n_rows); if (rc) return rc;
+    rc = c->d_indptr.alloc(n_rows + 1); if (rc) return rc;
+    rc = c->hits_a.alloc(total); if (rc) return rc;
+    rc = c->hits_b.alloc(total); if (rc) return rc;
+    rc = c->d_df.alloc(std::max<int64_t>(n_cols, 1)); if (rc) return rc;
+    CU(cudaMemcpyAsync(c->d_row_base.p, row_offsets, (n_rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    if (n_rows) CU(cudaMemcpyAsync(c->d_row_cursor.p, cursor.data(), n_rows * sizeof(unsigned int), cudaMemcpyHostToDevice, c->stream));
+    if (total) CU(cudaMemcpyAsync(c->hits_a.p, cols, total * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(c->d_df.p, 0, std::max<int64_t>(n_cols, 1) * sizeof(int), c->stream));
+    CU(cudaMemsetAsync(c->d_indptr.p, 0, (n_rows + 1) * sizeof(int64_t), c->stream));
+    rc = rows_to_csr(c, n_rows); if (rc) return rc;
     if (nnz) *nnz = c->nnz;
     return PC_OK;
 }

@@ -140,4 +140,58 @@ int pc_write_kmer_fasta(const char* path, const uint64_t* keys, int64_t n, int k
     return bad ? PC_EIO : PC_OK;
 }
 
+
+// Text artefacts of the mapping stages, written straight from the CSR the GPU produced (row = chunk/record,
+// column = repeat k-mer, value = number of exact occurrences):
+//   mode 0  headerless SAM, one record per occurrence (bbmap.sh outm=..., polycracker.py:252).  Only the fields the
+//           reference reads are meaningful: QNAME = k-mer, RNAME = chunk (polycracker.py:271-272); POS is 0.
+//   mode 1  blasted.bed: "chunk\t0\tlen\tkmer" per occurrence (polycracker.py:272)
+//   mode 2  blasted_merged.bed: one line per chunk with >= 1 hit, names comma-joined with multiplicity
+//           (`sort().merge(c=4,o='collapse')`, polycracker.py:280)
+int pc_write_hit_lines(const char* path, int mode, const int64_t* indptr, const int32_t* indices, const float* data,
+                       int64_t n_rows, const uint64_t* keys, int k, const char* names_blob, const int64_t* name_off,
+                       const int64_t* row_len, int append) {
+    if (!path || !indptr || !names_blob || !name_off || k < 1 || k > 32 || mode < 0 || mode > 2) return PC_EINVAL;
+    if (indptr[n_rows] > 0 && (!indices || !data || !keys)) return PC_EINVAL;
+    if (mode != 0 && !row_len) return PC_EINVAL;
+    FILE* f = fopen(path, append ? "ab" : "wb");
+    if (!f) return PC_EIO;
+    std::string buf; buf.reserve(1 << 22);
+    char km[33]; km[k] = 0;
+    char num[32];
+    for (int64_t r = 0; r < n_rows; ++r) {
+        int64_t b = indptr[r], e = indptr[r + 1];
+        if (b == e) continue;
+        const char* name = names_blob + name_off[r];
+        size_t nlen = (size_t)(name_off[r + 1] - name_off[r]);
+        int numlen = row_len ? snprintf(num, sizeof num, "%lld", (long long)row_len[r]) : 0;
+        if (mode == 2) { buf.append(name, nlen); buf.append("\t0\t"); buf.append(num, numlen); buf.push_back('\t'); }
+        bool first = true;
+        for (int64_t i = b; i < e; ++i) {
+            uint64_t x = keys[indices[i]];
+            for (int j = 0; j < k; ++j) km[j] = BASES[(x >> (2 * (k - 1 - j))) & 3u];
+            int64_t cnt = (int64_t)data[i];
+            for (int64_t c = 0; c < cnt; ++c) {
+                if (mode == 0) {
+                    buf.append(km, k); buf.append("\t0\t"); buf.append(name, nlen); buf.append("\t0\t255\t");
+                    int l = snprintf(num, sizeof num, "%dM", k); buf.append(num, l);
+                    buf.append("\t*\t0\t0\t"); buf.append(km, k); buf.append("\t*\n");
+                } else if (mode == 1) {
+                    buf.append(name, nlen); buf.append("\t0\t"); buf.append(num, numlen); buf.push_back('\t');
+                    buf.append(km, k); buf.push_back('\n');
+                } else {
+                    if (!first) buf.push_back(',');
+                    buf.append(km, k); first = false;
+                }
+                if (buf.size() > (1u << 22) - 4096) { fwrite(buf.data(), 1, buf.size(), f); buf.clear(); }
+            }
+        }
+        if (mode == 2) buf.push_back('\n');
+    }
+    if (!buf.empty()) fwrite(buf.data(), 1, buf.size(), f);
+    int bad = ferror(f);
+    fclose(f);
+    return bad ? PC_EIO : PC_OK;
+}
+
 }  // extern "C"
