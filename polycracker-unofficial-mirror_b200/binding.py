@@ -263,7 +263,15 @@ class Context:
         self.close()
 
     def set_stream(self, cuda_stream):
-        check(lib.pc_set_stream(self._h, _vp(cuda_stream or 0)), "pc_set_stream")
+        """Issue all work of this context on `cuda_stream` (a raw cudaStream_t, e.g.
+        torch.cuda.current_stream().cuda_stream).  torch reports the legacy default stream as handle 0, which the
+        C ABI reads as "the context's own stream"; it is mapped to cudaStreamLegacy (0x1) so that kernels launched
+        here are ordered with torch / NCCL work on that stream.  None restores the context's own stream."""
+        if cuda_stream is None:
+            handle = 0
+        else:
+            handle = int(cuda_stream) or 1                 # cudaStreamLegacy
+        check(lib.pc_set_stream(self._h, _vp(handle)), "pc_set_stream")
 
     def sync(self):
         check(lib.pc_sync(self._h), "pc_sync")

@@ -72,6 +72,14 @@ def _all_gather_v(dist, local, torch):
     return torch.cat([o[:c] for o, c in zip(outs, counts)]), counts
 
 
+def _stream_sync(torch, device):
+    """The C ABI is host-synchronous on the context's stream; collectives are asynchronous on torch's stream.  When
+    the two streams differ, wait for the collective before handing its output to the context (and vice versa the
+    context calls have already synchronised).  A no-op on CPU (gloo)."""
+    if getattr(device, "type", "cpu") == "cuda":
+        torch.cuda.current_stream(device).synchronize()
+
+
 def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000, k=23, kmer_low_count=100,
                              high_bool=0, kmer_high_count=2000000, sampling_sensitivity=1, remove_non_chunk=1,
                              min_chunk_threshold=0, min_chunk_size=0, prefilter=0, tfidf=True, fetch=True,
@@ -111,6 +119,7 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
     # 2. all-to-all, owners merge + threshold
     rkeys, _ = _all_to_all_v(dist, keys_t[:d_local], send_counts, torch)
     rcounts, _ = _all_to_all_v(dist, counts_t[:d_local], send_counts, torch)
+    _stream_sync(torch, device)
     del keys_t, counts_t
     ctx.merge_counts(rkeys, rcounts, rkeys.numel(), k, fresh=True)
     owner_info = ctx.count_info()
@@ -125,6 +134,7 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
         # sampling is defined on the globally sorted survivor list (pc_select semantics)
         sel_all = torch.sort(sel_all.view(torch.int64) ^ (-2**63))[0] ^ (-2**63)       # unsigned order
         sel_all = sel_all[::int(sampling_sensitivity)].contiguous()
+    _stream_sync(torch, device)
     n_sel = ctx.set_selected(sel_all, k, n=sel_all.numel())
     # 4. local matrix, global idf
     nnz = ctx.build_matrix(local_chunk_row, n_local_rows)
@@ -132,6 +142,7 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
     if n_sel:
         ctx.df_into(df_t)
     dist.all_reduce(df_t, op=dist.ReduceOp.SUM)
+    _stream_sync(torch, device)
     if tfidf:
         ctx.tfidf(len(scaffolds_all), df_t if n_sel else None)
     t = torch.tensor([info["valid_windows"], owner_info["distinct"], nnz], dtype=torch.int64, device=device)
