@@ -81,7 +81,17 @@ int pc_count_info(pc_ctx* ctx, int64_t info[8]);
  * polycracker.py:199).  keys == NULL -> only *n is written.  Unordered, like the tools' dumps. */
 int pc_dump_counts(pc_ctx* ctx, uint32_t min_count, uint32_t max_count,
                    uint64_t* keys, uint32_t* counts, int64_t cap, int loc, int64_t* n);
-/* multi-GPU exchange: all (kmer,count) pairs of the local table grouped by owner rank
+/* multi-GPU counting.  Bucket = top pb bits of the k-mer hash; rank r owns a contiguous bucket range.
+ * pc_partition: K1 must have run; extracts the canonical k-mers of the local chunks and radix-partitions them into
+ * 2^pb buckets.  bucket_off[2^pb + 1] (host) receives the bucket offsets into *keys_dev (device, bucket-sorted k-mers).
+ * The slices other ranks own travel as raw 8-byte k-mers in one all-to-all (torch.distributed / NCCL, caller side).
+ * pc_count_buckets: counts n_buckets buckets into a fresh table; bucket i consists of the n_seg segments
+ * keys_dev[seg_begin[i*n_seg+s] .. +seg_len[i*n_seg+s]) (one segment per sending rank).  Afterwards pc_select /
+ * pc_dump_counts see the owner's share of the global counts. */
+int pc_partition(pc_ctx* ctx, int k, int pb, int64_t* bucket_off, uint64_t** keys_dev);
+int pc_count_buckets(pc_ctx* ctx, int k, int pb, int n_buckets, const uint64_t* keys_dev, const int64_t* seg_begin,
+                     const int64_t* seg_len, int n_seg, int64_t capacity);
+/* alternative exchange of pre-aggregated pairs: all (kmer,count) pairs of the local table grouped by owner rank
  * (owner = hash(kmer) % world); offsets[world+1] is a host array.  keys/counts are device buffers of
  * capacity >= distinct k-mers.  pc_merge_counts adds received pairs into the ctx table (creating it with
  * `capacity` slots when *fresh* != 0). */
@@ -129,8 +139,9 @@ int pc_timings(pc_ctx* ctx, float ms[PC_N_STAGES]);
 int pc_launch_count(pc_ctx* ctx, int64_t* launches);
 int pc_reset_counters(pc_ctx* ctx);
 /* kernel tunables (measurement / tuning only; defaults are the shipped configuration):
- * count_batch {4,8,16}, count_minb {2,3,4}, count_mode {0 load-first, 1 prefetch-ahead, 2 CAS-first},
- * table_load_pct (5..95), l2_fetch_granularity {32,64,128}. */
+ * count_batch {4,8,16}, count_minb {2,3,4}, count_mode {0 load-first, 1 prefetch-ahead, 2 CAS-first} (direct table);
+ * part_mode {-1 auto, 0 direct, 1 partitioned}, part_mbytes, part_blocks, part_casfirst, count_items {2,4};
+ * probe_mode {-1 auto, 0 roller, 1 stream}, probe_batch {4,8}, rep_load_inv; table_load_pct (5..95). */
 int pc_tune(pc_ctx* ctx, const char* key, int64_t value);
 
 /* ---- host helpers (no GPU) -------------------------------------------------------------------------------- */

@@ -62,6 +62,8 @@ _SIGS = {
     "pc_count": (C.c_int, [_vp, C.c_int, _i64]),
     "pc_count_info": (C.c_int, [_vp, _vp]),
     "pc_dump_counts": (C.c_int, [_vp, _u32, _u32, _vp, _vp, _i64, C.c_int, _P(_i64)]),
+    "pc_partition": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _P(_vp)]),
+    "pc_count_buckets": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _i64]),
     "pc_export_by_owner": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _vp]),
     "pc_merge_counts": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, _i64, C.c_int]),
     "pc_select": (C.c_int, [_vp, _u32, _u32, C.c_int, _i64, _P(_i64)]),
@@ -311,8 +313,7 @@ class Context:
         info = np.zeros(8, np.int64)
         check(lib.pc_count_info(self._h, info.ctypes.data), "pc_count_info")
         return dict(capacity=int(info[0]), distinct=int(info[1]), valid_windows=int(info[2]),
-                    table_bytes=int(info[3]), max_probe=int(info[4]), k=int(info[5]),
-                    distinct_estimate=int(info[6]), partition_bits=int(info[7]))
+                    table_bytes=int(info[3]), max_probe=int(info[4]), k=int(info[5]), partition_bits=int(info[7]))
 
     def dump_counts(self, min_count=1, max_count=0xFFFFFFFF):
         n = _i64()
@@ -322,6 +323,22 @@ class Context:
             check(lib.pc_dump_counts(self._h, min_count, max_count, keys.ctypes.data, counts.ctypes.data, n.value,
                                      PC_HOST, C.byref(n)), "pc_dump_counts")
         return keys, counts
+
+    def partition(self, k, pb):
+        """-> (bucket_off int64[2^pb + 1], device pointer of the bucket-sorted k-mers)"""
+        off = np.zeros((1 << pb) + 1, np.int64)
+        keys = _vp()
+        check(lib.pc_partition(self._h, int(k), int(pb), off.ctypes.data, C.byref(keys)), "pc_partition")
+        return off, keys.value
+
+    def count_buckets(self, k, pb, keys, seg_begin, seg_len, capacity=0):
+        """keys: torch CUDA tensor (int64 view of the k-mers) or a raw device pointer; seg_begin/seg_len:
+        int64[n_buckets, n_seg]."""
+        sb = np.ascontiguousarray(seg_begin, dtype=np.int64); sl = np.ascontiguousarray(seg_len, dtype=np.int64)
+        assert sb.ndim == 2 and sb.shape == sl.shape
+        p = keys if isinstance(keys, int) else keys.data_ptr()
+        check(lib.pc_count_buckets(self._h, int(k), int(pb), sb.shape[0], p, sb.ctypes.data, sl.ctypes.data, sb.shape[1],
+                                   int(capacity)), "pc_count_buckets")
 
     def export_by_owner(self, world, keys_t, counts_t):
         """keys_t (int64/uint64 view) and counts_t (int32) are torch CUDA tensors with >= distinct elements."""

@@ -100,10 +100,12 @@ struct pc_ctx {
 
     // partitioned count state
     int pb = 0; uint64_t part_S = 0;
-    DevBuf<uint64_t> kbuf, kstream; DevBuf<unsigned long long> d_part_hist; DevBuf<unsigned int> d_hll;
-    // measured on B200 (profiles/r01_kbench_count.md): the bucket count is bound by L2 sector operations, so the
-    // variants that trade probes for DRAM traffic (HLL-sized denser table, in-kernel zeroing, CAS-first) are slower
-    int hll_sizing = 0, fused_zero = 0, hll_bias_pct = 100, part_casfirst = 0; int64_t distinct_estimate = 0;
+    DevBuf<uint64_t> kbuf, kstream; DevBuf<unsigned long long> d_part_hist; DevBuf<int64_t> d_seg;
+    std::vector<int64_t> h_bucket_off;
+    // measured on B200 (profiles/r01_kbench_count.md): the bucket count is bound by L2 sector operations; CAS-first
+    // inserts (one ATOM per new k-mer, no load) are slower than load-first; HyperLogLog-sized denser tables and
+    // in-kernel zeroing of the next sub-table were slower too and have been removed again
+    int part_casfirst = 0;
     int count_items = 4;
 };
 
@@ -213,7 +215,7 @@ int pc_destroy(pc_ctx* c) {
     cudaStreamSynchronize(c->stream);
     c->ascii.release(); c->d_word0.release(); c->d_begin.release(); c->d_len.release();
     c->words.release(); c->nmask.release(); c->table.release(); c->d_stats.release();
-    c->kbuf.release(); c->kstream.release(); c->d_part_hist.release(); c->d_hll.release();
+    c->kbuf.release(); c->kstream.release(); c->d_part_hist.release(); c->d_seg.release();
     c->sel_a.release(); c->sel_b.release(); c->rs_hist.release(); c->d_counter.release(); c->rtable.release();
     c->d_chunk_row.release(); c->d_row_base.release(); c->d_row_cursor.release(); c->hits_a.release();
     c->hits_b.release(); c->d_row_nnz.release(); c->d_indptr.release(); c->d_indices.release();
@@ -383,6 +385,95 @@ static int launch_count(pc_ctx* c) {
     return fail(PC_EINVAL, "no k_count instantiation for batch=%d minb=%d mode=%d", c->count_batch, c->count_minb, c->count_mode);
 }
 
+// extract (k-mer stream + bucket histogram) and tile scatter; leaves the bucket-sorted k-mers in c->kbuf and the
+// bucket offsets in c->h_bucket_off.  d_stats must have been reset by the caller.
+static int do_partition(pc_ctx* c, int k, int pb) {
+    int rc;
+    const uint64_t P = 1ull << pb;
+    int64_t windows = 0;
+    for (int64_t i = 0; i < c->n_chunks; ++i) windows += std::max<int64_t>(0, c->h_len[i] - k + 1);
+    int64_t n_stream = ((c->n_words + 255) / 256) * 256 * 32;              // one slot per window start
+    rc = c->kstream.alloc((size_t)std::max<int64_t>(n_stream, 1)); if (rc) return rc;
+    rc = c->kbuf.alloc((size_t)std::max<int64_t>(windows, 1)); if (rc) return rc;
+    rc = c->d_part_hist.alloc((size_t)3 * P + 2); if (rc) return rc;
+    unsigned long long* bucket_hist = c->d_part_hist.p;
+    unsigned long long* bucket_off = bucket_hist + P;                      // [P + 1]
+    unsigned long long* bucket_cur = bucket_off + P + 1;                   // [P]
+    {
+        StageTimer t(c, ST_PART_HIST);
+        CU(cudaMemsetAsync(bucket_hist, 0, P * sizeof(unsigned long long), c->stream));
+        if (c->n_words > 0) {
+            c->launches++;
+            pc::k_extract<<<blocks_for(c->n_words, 256), 256, P * sizeof(unsigned int), c->stream>>>(
+                c->words.p, c->nmask.p, c->n_words, k, pb, c->kstream.p, bucket_hist, c->d_stats.p);
+            CU(cudaGetLastError());
+        }
+        LAUNCH(c, pc::k_bucket_scan, 1, 1024, bucket_hist, (unsigned int)P, bucket_off, bucket_cur);
+    }
+    c->stream_valid = c->n_words > 0; c->stream_k = k;
+    if (c->n_words > 0) {
+        StageTimer t(c, ST_PART_SCATTER);
+        constexpr int TILE = 8192;
+        size_t smem = (size_t)TILE * 8 + P * 8 + P * 4 + (P + 2) * 4 + (size_t)TILE * 2 + 16;
+        CU(cudaFuncSetAttribute(pc::k_tile_scatter<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        unsigned int grid = (unsigned int)std::min<int64_t>(148 * 2, (n_stream + TILE - 1) / TILE);
+        c->launches++;
+        pc::k_tile_scatter<TILE><<<grid, 256, smem, c->stream>>>(c->kstream.p, n_stream, pb, bucket_off, bucket_cur, c->kbuf.p);
+        CU(cudaGetLastError());
+    }
+    c->h_bucket_off.assign(P + 1, 0);
+    static_assert(sizeof(unsigned long long) == sizeof(int64_t), "offset width");
+    CU(cudaMemcpyAsync(c->h_bucket_off.data(), bucket_off, (P + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(&c->h_stats, c->d_stats.p, sizeof(pc::CountStats), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return PC_OK;
+}
+
+// count n_buckets buckets (sub-table i <- segments [i*n_seg, (i+1)*n_seg) of keys_dev) into a fresh table
+static int do_count_buckets(pc_ctx* c, int k, int pb, int n_buckets, const uint64_t* keys_dev, const int64_t* seg_begin,
+                            const int64_t* seg_len, int n_seg, int64_t capacity) {
+    int rc;
+    int64_t total = 0, max_bucket = 0;
+    for (int q = 0; q < n_buckets; ++q) {
+        int64_t t = 0;
+        for (int s = 0; s < n_seg; ++s) {
+            if (seg_len[(int64_t)q * n_seg + s] < 0 || seg_begin[(int64_t)q * n_seg + s] < 0) return fail(PC_EINVAL, "bad segment");
+            t += seg_len[(int64_t)q * n_seg + s];
+        }
+        total += t; max_bucket = std::max(max_bucket, t);
+    }
+    if (capacity <= 0) {
+        double space = k >= 31 ? 9.3e18 : (double)(1ull << (2 * k));
+        capacity = (int64_t)(std::min((double)total, space) / c->table_load) + 1024;
+    }
+    uint64_t S = ((uint64_t)capacity + n_buckets - 1) / n_buckets;
+    // a bucket fed by heavy-hitter k-mers may hold more instances than the average, never more distinct keys than
+    // instances: keep every sub-table at least big enough for the mean and let the probe limit report the rest
+    if (S < 64) S = 64;
+    capacity = (int64_t)(S * (uint64_t)n_buckets);
+    rc = table_prepare(c, k, capacity, /*reset_stats=*/false); if (rc) return rc;
+    c->pb = pb; c->part_S = S;
+    rc = c->d_seg.alloc((size_t)2 * n_buckets * n_seg); if (rc) return rc;
+    CU(cudaMemcpyAsync(c->d_seg.p, seg_begin, (size_t)n_buckets * n_seg * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_seg.p + (size_t)n_buckets * n_seg, seg_len, (size_t)n_buckets * n_seg * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    const long long* d_beg = reinterpret_cast<const long long*>(c->d_seg.p);
+    const long long* d_len = d_beg + (size_t)n_buckets * n_seg;
+    if (total > 0) {
+        StageTimer t(c, ST_COUNT);
+        unsigned int B = (unsigned int)c->part_blocks;
+        unsigned int grid = (unsigned int)n_buckets * B;
+        if (c->part_casfirst)
+            LAUNCH(c, (pc::k_count_part<4, true>), grid, 256, keys_dev, d_beg, d_len, n_seg, pb, S, B, c->table.p, c->d_stats.p);
+        else if (c->count_items == 2)
+            LAUNCH(c, (pc::k_count_part<2, false>), grid, 256, keys_dev, d_beg, d_len, n_seg, pb, S, B, c->table.p, c->d_stats.p);
+        else
+            LAUNCH(c, (pc::k_count_part<4, false>), grid, 256, keys_dev, d_beg, d_len, n_seg, pb, S, B, c->table.p, c->d_stats.p);
+    }
+    rc = fetch_stats(c); if (rc) return rc;                   // synchronises: the host segment arrays may go away
+    c->counted = true;
+    return PC_OK;
+}
+
 int pc_tune(pc_ctx* c, const char* key, int64_t value) {
     int rc = use_device(c); if (rc) return rc;
     if (!key) return fail(PC_EINVAL, "null key");
@@ -393,10 +484,7 @@ int pc_tune(pc_ctx* c, const char* key, int64_t value) {
     else if (k == "part_mode") c->part_mode = (int)value;
     else if (k == "count_items") c->count_items = (int)value;
     else if (k == "probe_mode") c->probe_mode = (int)value;
-    else if (k == "hll_sizing") c->hll_sizing = (int)value;
     else if (k == "part_casfirst") c->part_casfirst = (int)value;
-    else if (k == "hll_bias_pct") c->hll_bias_pct = (int)value;
-    else if (k == "fused_zero") c->fused_zero = (int)value;
     else if (k == "probe_batch") c->probe_batch = (int)value;
     else if (k == "rep_load_inv") c->rep_load_inv = (int)value;
     else if (k == "part_mbytes") c->part_bytes = std::max<int64_t>(1, value) << 20;
@@ -407,8 +495,7 @@ int pc_tune(pc_ctx* c, const char* key, int64_t value) {
     return PC_OK;
 }
 
-int pc_count(pc_ctx* c, int k, int64_t capacity_arg) {
-    int64_t capacity = capacity_arg;
+int pc_count(pc_ctx* c, int k, int64_t capacity) {
     int rc = use_device(c); if (rc) return rc;
     if (!c->loaded) return fail(PC_ESTATE, "pc_count before pc_load_sequences");
     if (k < 1 || k > 32) return fail(PC_EINVAL, "k = %d unsupported: this path handles 1 <= k <= 32 (uint64 k-mers)", k);
@@ -423,7 +510,6 @@ int pc_count(pc_ctx* c, int k, int64_t capacity_arg) {
         capacity = (int64_t)(bound / c->table_load) + 1024;
     }
     // partition plan: P = 2^pb sub-tables of S slots, each about part_bytes so that it stays L2 resident
-    const bool user_capacity = capacity_arg > 0;
     int pb = 0;
     bool partitioned = c->part_mode == 1 || (c->part_mode < 0 && (size_t)capacity * sizeof(pc::CountSlot) > (size_t)(64ll << 20));
     if (partitioned) {
@@ -444,107 +530,45 @@ int pc_count(pc_ctx* c, int k, int64_t capacity_arg) {
         return PC_OK;
     }
 
-    // ---- partitioned path: extract -> (size the table) -> tile scatter -> bucket-by-bucket count -------------
-    int64_t n_stream = ((c->n_words + 255) / 256) * 256 * 32;              // one slot per window start
-    rc = c->kstream.alloc((size_t)n_stream); if (rc) return rc;
-    rc = c->kbuf.alloc((size_t)std::max<int64_t>(windows, 1)); if (rc) return rc;
-    rc = c->d_part_hist.alloc((size_t)3 * P + 2); if (rc) return rc;
-    rc = c->d_hll.alloc(PC_HLL_M + P + 2); if (rc) return rc;
-    unsigned long long* bucket_hist = c->d_part_hist.p;
-    unsigned long long* bucket_off = bucket_hist + P;                      // [P + 1]
-    unsigned long long* bucket_cur = bucket_off + P + 1;                   // [P]
-    unsigned int* hll = c->d_hll.p;                                        // [PC_HLL_M]
-    unsigned int* ready = hll + PC_HLL_M;                                  // [P]
-    unsigned int* ticket = ready + P;                                      // [1]
+    // ---- partitioned path: extract -> tile scatter -> bucket-by-bucket count ----------------------------------
     CU(cudaMemsetAsync(c->d_stats.p, 0, sizeof(pc::CountStats), c->stream));
-    {
-        StageTimer t(c, ST_PART_HIST);
-        CU(cudaMemsetAsync(bucket_hist, 0, P * sizeof(unsigned long long), c->stream));
-        CU(cudaMemsetAsync(hll, 0, (PC_HLL_M + P + 2) * sizeof(unsigned int), c->stream));
-        c->launches++;
-        pc::k_extract<<<blocks_for(c->n_words, 256), 256, (P + PC_HLL_M) * sizeof(unsigned int), c->stream>>>(
-            c->words.p, c->nmask.p, c->n_words, k, pb, c->kstream.p, bucket_hist, hll, c->d_stats.p);
-        CU(cudaGetLastError());
-        LAUNCH(c, pc::k_bucket_scan, 1, 1024, bucket_hist, (unsigned int)P, bucket_off, bucket_cur);
-    }
-    c->stream_valid = true; c->stream_k = k;
-    // scatter is independent of the table size: issue it before the host looks at the HLL registers
-    {
-        StageTimer t(c, ST_PART_SCATTER);
-        constexpr int TILE = 8192;
-        size_t smem = (size_t)TILE * 8 + P * 8 + P * 4 + (P + 2) * 4 + (size_t)TILE * 2 + 16;
-        CU(cudaFuncSetAttribute(pc::k_tile_scatter<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        unsigned int grid = (unsigned int)std::min<int64_t>(148 * 2, (n_stream + TILE - 1) / TILE);
-        c->launches++;
-        pc::k_tile_scatter<TILE><<<grid, 256, smem, c->stream>>>(c->kstream.p, n_stream, pb, bucket_off, bucket_cur, c->kbuf.p);
-        CU(cudaGetLastError());
-    }
-    // distinct-k-mer estimate (HyperLogLog over a 1/16 hash sample) -> table capacity
-    int64_t cap_upper = capacity;
-    bool estimated = false;
-    if (!user_capacity && c->hll_sizing) {
-        std::vector<unsigned int> reg(PC_HLL_M);
-        CU(cudaMemcpyAsync(reg.data(), hll, PC_HLL_M * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
-        double m = (double)PC_HLL_M, sum = 0.0; int zeros = 0;
-        for (unsigned int v : reg) { sum += std::ldexp(1.0, -(int)v); zeros += (v == 0); }
-        double est = (0.7213 / (1.0 + 1.079 / m)) * m * m / sum;
-        if (est <= 2.5 * m && zeros > 0) est = m * std::log(m / zeros);
-        double distinct_est = 16.0 * est * (c->hll_bias_pct / 100.0);   // bias: test hook for the retry path
-        int64_t cap_est = (int64_t)(distinct_est * 1.06 / c->table_load) + (int64_t)P * 4096;
-        c->distinct_estimate = (int64_t)distinct_est;
-        if (cap_est < cap_upper) { capacity = cap_est; estimated = true; }
-    }
-    for (int attempt = 0; attempt < 2; ++attempt) {
-        uint64_t S = ((uint64_t)capacity + P - 1) / P;
-        if (S < 64) S = 64;
-        capacity = (int64_t)(S * P);
-        unsigned int B = (unsigned int)c->part_blocks;
-        if (c->fused_zero) {
-            size_t free_b = 0, total_b = 0;
-            CU(cudaMemGetInfo(&free_b, &total_b));
-            size_t need = (size_t)capacity * sizeof(pc::CountSlot);
-            if (need > free_b + c->table.n * sizeof(pc::CountSlot))
-                return fail(PC_ENOMEM, "count table of %lld slots (%.1f GB) does not fit in free HBM (%.1f GB): shard the genome over more GPUs",
-                            (long long)capacity, need / 1e9, free_b / 1e9);
-            rc = c->table.alloc((size_t)capacity); if (rc) return rc;
-            c->capacity = (uint64_t)capacity; c->k = k;
-            CU(cudaMemsetAsync(ready, 0, (P + 2) * sizeof(unsigned int), c->stream));
-            StageTimer t(c, ST_COUNT);
-            if (c->count_items == 2)
-                LAUNCH(c, (pc::k_count_part_fused<2, true>), (unsigned int)(P * B), 256, c->kbuf.p, bucket_off, pb, S, B, c->table.p, ready, ticket, c->d_stats.p);
-            else
-                LAUNCH(c, (pc::k_count_part_fused<4, true>), (unsigned int)(P * B), 256, c->kbuf.p, bucket_off, pb, S, B, c->table.p, ready, ticket, c->d_stats.p);
-        } else {
-            unsigned long long keep_valid = 0;
-            rc = table_prepare(c, k, capacity, /*reset_stats=*/false); if (rc) return rc;
-            (void)keep_valid;
-            StageTimer t(c, ST_COUNT);
-            if (c->count_items == 8)
-                LAUNCH(c, (pc::k_count_part<8, true>), (unsigned int)(P * B), 256, c->kbuf.p, bucket_off, pb, S, B, c->table.p, c->d_stats.p);
-            else if (c->count_items == 2)
-                LAUNCH(c, (pc::k_count_part<2, true>), (unsigned int)(P * B), 256, c->kbuf.p, bucket_off, pb, S, B, c->table.p, c->d_stats.p);
-            else if (!c->part_casfirst)
-                LAUNCH(c, (pc::k_count_part<4, false>), (unsigned int)(P * B), 256, c->kbuf.p, bucket_off, pb, S, B, c->table.p, c->d_stats.p);
-            else
-                LAUNCH(c, (pc::k_count_part<4, true>), (unsigned int)(P * B), 256, c->kbuf.p, bucket_off, pb, S, B, c->table.p, c->d_stats.p);
-        }
-        c->pb = pb; c->part_S = S;
-        rc = fetch_stats(c);
-        if (rc == PC_ENOMEM && estimated && attempt == 0) {
-            // the estimate was too small (an adversarial hash sample): redo the count with the safe upper bound
-            capacity = cap_upper; estimated = false;
-            pc::CountStats z = c->h_stats; z.distinct = 0; z.overflow = 0; z.max_probe = 0;
-            CU(cudaMemcpyAsync(c->d_stats.p, &z, sizeof z, cudaMemcpyHostToDevice, c->stream));
-            CU(cudaStreamSynchronize(c->stream));
-            continue;
-        }
-        if (rc) return rc;
-        break;
-    }
-    rc = fetch_stats(c); if (rc) return rc;
-    c->counted = true;
+    rc = do_partition(c, k, pb); if (rc) return rc;
+    std::vector<int64_t> seg_begin(P), seg_len(P);
+    for (uint64_t q = 0; q < P; ++q) { seg_begin[q] = c->h_bucket_off[q]; seg_len[q] = c->h_bucket_off[q + 1] - c->h_bucket_off[q]; }
+    rc = do_count_buckets(c, k, pb, (int)P, c->kbuf.p, seg_begin.data(), seg_len.data(), 1, capacity); if (rc) return rc;
     return PC_OK;
+}
+
+// Multi-GPU building blocks: the bucket id is the top pb bits of the k-mer hash and rank r owns a
+// contiguous range of buckets, so after pc_partition the k-mers every peer must receive are one contiguous slice of the
+// bucket-sorted buffer: they travel as raw 8-byte k-mers in one all-to-all over NVLink and are counted once, by their
+// owner, with the same L2-resident bucket kernel the single-GPU path uses.
+int pc_partition(pc_ctx* c, int k, int pb, int64_t* bucket_off, uint64_t** keys_dev) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!c->loaded) return fail(PC_ESTATE, "pc_partition before pc_load_sequences");
+    if (k < 1 || k > 32) return fail(PC_EINVAL, "k = %d unsupported: this path handles 1 <= k <= 32 (uint64 k-mers)", k);
+    if (pb < 0 || pb > 12 || !bucket_off || !keys_dev) return fail(PC_EINVAL, "bad pc_partition arguments");
+    c->counted = c->selected = c->built = c->tfidf_done = false;
+    c->stream_valid = false;
+    CU(cudaMemsetAsync(c->d_stats.p, 0, sizeof(pc::CountStats), c->stream));
+    rc = do_partition(c, k, pb); if (rc) return rc;
+    memcpy(bucket_off, c->h_bucket_off.data(), ((size_t)(1u << pb) + 1) * sizeof(int64_t));
+    *keys_dev = c->kbuf.p;
+    return PC_OK;
+}
+
+int pc_count_buckets(pc_ctx* c, int k, int pb, int n_buckets, const uint64_t* keys_dev, const int64_t* seg_begin,
+                     const int64_t* seg_len, int n_seg, int64_t capacity) {
+    int rc = use_device(c); if (rc) return rc;
+    if (k < 1 || k > 32) return fail(PC_EINVAL, "k = %d unsupported: this path handles 1 <= k <= 32 (uint64 k-mers)", k);
+    if (pb < 0 || pb > 12 || n_buckets < 1 || n_buckets > (1 << pb) || n_seg < 1 || !seg_begin || !seg_len)
+        return fail(PC_EINVAL, "bad pc_count_buckets arguments");
+    c->counted = c->selected = c->built = c->tfidf_done = false;
+    unsigned long long keep = c->h_stats.valid_windows;        // pc_partition already counted the local windows
+    pc::CountStats z{}; z.valid_windows = keep;
+    CU(cudaMemcpyAsync(c->d_stats.p, &z, sizeof z, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return do_count_buckets(c, k, pb, n_buckets, keys_dev, seg_begin, seg_len, n_seg, capacity);
 }
 
 int pc_count_info(pc_ctx* c, int64_t info[8]) {
@@ -552,7 +576,7 @@ int pc_count_info(pc_ctx* c, int64_t info[8]) {
     memset(info, 0, 8 * sizeof(int64_t));
     info[0] = (int64_t)c->capacity; info[1] = (int64_t)c->h_stats.distinct; info[2] = (int64_t)c->h_stats.valid_windows;
     info[3] = (int64_t)(c->capacity * sizeof(pc::CountSlot)); info[4] = (int64_t)c->h_stats.max_probe; info[5] = c->k;
-    info[6] = c->distinct_estimate; info[7] = c->pb;
+    info[6] = 0; info[7] = c->pb;
     return PC_OK;
 }
 

@@ -334,7 +334,6 @@ k_count(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, 
 __device__ __forceinline__ unsigned int part_of(uint64_t h, int pb) { return pb ? (unsigned int)(h >> (64 - pb)) : 0u; }
 __device__ __forceinline__ uint64_t slot_in_part(uint64_t h, int pb, uint64_t S) { return __umul64hi(h << pb, S); }
 
-#define PC_HLL_M 4096u
 #define PC_KEY_SENTINEL (~0ull)      // never a canonical-min k-mer (its reverse complement, all A, is smaller)
 
 // pass A: packed genome -> stream of canonical k-mers, one slot per window start (invalid windows hold the
@@ -342,15 +341,11 @@ __device__ __forceinline__ uint64_t slot_in_part(uint64_t h, int pb, uint64_t S)
 // instruction writes 256 contiguous bytes.
 __global__ void __launch_bounds__(256)
 k_extract(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, int64_t n_words, int k, int pb,
-          uint64_t* __restrict__ stream, unsigned long long* __restrict__ bucket_hist, unsigned int* __restrict__ hll,
-          CountStats* __restrict__ stats)
+          uint64_t* __restrict__ stream, unsigned long long* __restrict__ bucket_hist, CountStats* __restrict__ stats)
 {
-    // hll: HyperLogLog registers (PC_HLL_M of them) over the 1/16 hash-sample of the k-mers whose low hash nibble
-    // is 0; the host turns them into an estimate of the number of DISTINCT k-mers to size the count table.
-    extern __shared__ unsigned int shh[];                     // [P] bucket counts of this CTA, then [PC_HLL_M] registers
+    extern __shared__ unsigned int shh[];                     // [P] bucket counts of this CTA
     const unsigned int P = 1u << pb;
-    unsigned int* shl = shh + P;
-    for (unsigned int i = threadIdx.x; i < P + PC_HLL_M; i += blockDim.x) shh[i] = 0;
+    for (unsigned int i = threadIdx.x; i < P; i += blockDim.x) shh[i] = 0;
     __syncthreads();
     int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int lane = threadIdx.x & 31;
@@ -364,16 +359,7 @@ k_extract(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask
             bool v = r.valid(b);
             uint64_t key = r.canonical();
             __stcs(out + b * 32, v ? key : PC_KEY_SENTINEL);
-            if (v) {
-                uint64_t h = mix64(key);
-                atomicAdd(&shh[part_of(h, pb)], 1u);
-                ++nvalid;
-                if ((h & 15ull) == 0ull) {
-                    unsigned int idx = (unsigned int)(h >> 4) & (PC_HLL_M - 1);
-                    unsigned int rho = (unsigned int)__clzll((h >> 16) << 16 | 0x8000ull) + 1u;
-                    atomicMax(&shl[idx], rho);
-                }
-            }
+            if (v) { atomicAdd(&shh[part_of(mix64(key), pb)], 1u); ++nvalid; }
             if (b < 31) r.step(b);
         }
     } else {
@@ -383,8 +369,6 @@ k_extract(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask
     __syncthreads();
     for (unsigned int i = threadIdx.x; i < P; i += blockDim.x)
         if (shh[i]) atomicAdd(&bucket_hist[i], (unsigned long long)shh[i]);
-    for (unsigned int i = threadIdx.x; i < PC_HLL_M; i += blockDim.x)
-        if (shl[i]) atomicMax(&hll[i], shl[i]);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) nvalid += __shfl_xor_sync(0xFFFFFFFFu, nvalid, o);
     if (lane == 0 && nvalid) atomicAdd(&stats->valid_windows, (unsigned long long)nvalid);
@@ -496,125 +480,50 @@ k_tile_scatter(const uint64_t* __restrict__ stream, int64_t n_stream, int pb,
     }
 }
 
-// pass C: count one bucket after the other.  blockIdx = bucket * B + b: blocks are dispatched in index order, so
-// at any time the resident blocks work on one or two adjacent buckets whose sub-tables (S slots) sit in L2.
+// pass C: count one bucket after the other.  blockIdx = local_bucket * B + b: blocks are dispatched in index order,
+// so at any time the resident blocks work on one or two adjacent buckets whose sub-tables (S slots) sit in L2.
+// A bucket's k-mers arrive as n_seg segments of `keys` (one per sending rank; a single segment on one GPU).
 template <int ITEMS, bool CASFIRST>
 __global__ void __launch_bounds__(256)
-k_count_part(const uint64_t* __restrict__ kbuf, const unsigned long long* __restrict__ bucket_off, int pb, uint64_t S,
-             unsigned int B, CountSlot* __restrict__ table, CountStats* __restrict__ stats)
+k_count_part(const uint64_t* __restrict__ keys, const long long* __restrict__ seg_begin, const long long* __restrict__ seg_len,
+             int n_seg, int pb, uint64_t S, unsigned int B, CountSlot* __restrict__ table, CountStats* __restrict__ stats)
 {
     unsigned int q = blockIdx.x / B, b = blockIdx.x % B;
-    unsigned long long beg = bucket_off[q], end = bucket_off[q + 1];
     CountSlot* sub = table + (uint64_t)q * S;
     unsigned int new_keys = 0, max_probe = 0;
-    // software pipeline: the bucket keys of the next iteration (a DRAM stream) are requested before this
-    // iteration's table accesses (L2) are issued
     const unsigned long long stride = (unsigned long long)B * 256u * ITEMS;
-    unsigned long long i0 = beg + ((unsigned long long)b * 256u + threadIdx.x) * ITEMS;
-    uint64_t nkey[ITEMS];
+    for (int sg = 0; sg < n_seg; ++sg) {
+        const uint64_t* kbuf = keys + seg_begin[(int64_t)q * n_seg + sg];
+        const unsigned long long end = (unsigned long long)seg_len[(int64_t)q * n_seg + sg];
+        // software pipeline: the keys of the next iteration (a DRAM stream) are requested before this iteration's
+        // table accesses (L2) are issued
+        unsigned long long i0 = ((unsigned long long)b * 256u + threadIdx.x) * ITEMS;
+        uint64_t nkey[ITEMS];
 #pragma unroll
-    for (int j = 0; j < ITEMS; ++j) nkey[j] = (i0 + j < end) ? __ldcs(kbuf + i0 + j) : PC_KEY_SENTINEL;
-    for (; i0 < end; i0 += stride) {
-        unsigned long long skey[ITEMS]; uint64_t slot[ITEMS]; unsigned long long cur[ITEMS];
-        bool on[ITEMS];
+        for (int j = 0; j < ITEMS; ++j) nkey[j] = (i0 + j < end) ? __ldcs(kbuf + i0 + j) : PC_KEY_SENTINEL;
+        for (; i0 < end; i0 += stride) {
+            unsigned long long skey[ITEMS]; uint64_t slot[ITEMS]; unsigned long long cur[ITEMS];
+            bool on[ITEMS];
 #pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            uint64_t key = nkey[j];
-            on[j] = key != PC_KEY_SENTINEL;
-            skey[j] = ~key;
-            slot[j] = slot_in_part(mix64(key), pb, S);
-        }
+            for (int j = 0; j < ITEMS; ++j) {
+                uint64_t key = nkey[j];
+                on[j] = key != PC_KEY_SENTINEL;
+                skey[j] = ~key;
+                slot[j] = slot_in_part(mix64(key), pb, S);
+            }
 #pragma unroll
-        for (int j = 0; j < ITEMS; ++j) nkey[j] = (i0 + stride + j < end) ? __ldcs(kbuf + i0 + stride + j) : PC_KEY_SENTINEL;
-        if (CASFIRST) {
+            for (int j = 0; j < ITEMS; ++j) nkey[j] = (i0 + stride + j < end) ? __ldcs(kbuf + i0 + stride + j) : PC_KEY_SENTINEL;
+            if (CASFIRST) {
 #pragma unroll
-            for (int j = 0; j < ITEMS; ++j) cur[j] = on[j] ? atomicCAS(&sub[slot[j]].skey, 0ull, skey[j]) : 0ull;
+                for (int j = 0; j < ITEMS; ++j) cur[j] = on[j] ? atomicCAS(&sub[slot[j]].skey, 0ull, skey[j]) : 0ull;
 #pragma unroll
-            for (int j = 0; j < ITEMS; ++j)
-                if (on[j]) count_insert_cas(sub, S, slot[j], skey[j], cur[j], new_keys, max_probe, stats);
-        } else {
+                for (int j = 0; j < ITEMS; ++j)
+                    if (on[j]) count_insert_cas(sub, S, slot[j], skey[j], cur[j], new_keys, max_probe, stats);
+            } else {
 #pragma unroll
-            for (int j = 0; j < ITEMS; ++j) cur[j] = on[j] ? ldcg_u64(&sub[slot[j]].skey) : 0ull;
-            count_insert_batch<ITEMS>(sub, S, slot, skey, cur, on, new_keys, max_probe, stats);
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        new_keys += __shfl_xor_sync(0xFFFFFFFFu, new_keys, o);
-        max_probe = max(max_probe, __shfl_xor_sync(0xFFFFFFFFu, max_probe, o));
-    }
-    if ((threadIdx.x & 31) == 0) {
-        if (new_keys) atomicAdd(&stats->distinct, (unsigned long long)new_keys);
-        if (max_probe > 8) atomicMax(&stats->max_probe, (unsigned long long)max_probe);
-    }
-}
-
-// pass C, fused with the table initialisation.  Virtual block ids come from a ticket counter, so a block with a
-// smaller ticket is always already running (the decoupled-look-back guarantee).  Block (q, b) first zeroes slice b
-// of sub-table q+1 (full-sector stores: the lines are created dirty in L2, nothing is read from or written to
-// DRAM), publishes that through ready[q+1], waits until all B slices of its own sub-table q are zeroed, then counts
-// slice b of bucket q.  The table is never memset from the host and every table line crosses the HBM bus exactly
-// once, on eviction.
-template <int ITEMS, bool CASFIRST>
-__global__ void __launch_bounds__(256)
-k_count_part_fused(const uint64_t* __restrict__ kbuf, const unsigned long long* __restrict__ bucket_off, int pb, uint64_t S,
-                   unsigned int B, CountSlot* __restrict__ table, unsigned int* __restrict__ ready /* [P] zeroed */,
-                   unsigned int* __restrict__ ticket, CountStats* __restrict__ stats)
-{
-    __shared__ unsigned int vb_s;
-    if (threadIdx.x == 0) vb_s = atomicAdd(ticket, 1u);
-    __syncthreads();
-    const unsigned int P = 1u << pb;
-    unsigned int q = vb_s / B, b = vb_s % B;
-    // phase 0: zero slice b of sub-table q+1 (and of sub-table 0 for the very first bucket)
-    uint64_t per = (S + B - 1) / B;
-    uint64_t z0 = min(S, (uint64_t)b * per), z1 = min(S, z0 + per);
-    for (unsigned int tq = (q == 0 ? 0u : q + 1u); tq <= q + 1u && tq < P; ++tq) {
-        uint4* dst = reinterpret_cast<uint4*>(table + (uint64_t)tq * S);
-        for (uint64_t i = z0 + threadIdx.x; i < z1; i += 256) dst[i] = make_uint4(0u, 0u, 0u, 0u);
-        __threadfence();
-        __syncthreads();
-        if (threadIdx.x == 0) atomicAdd(&ready[tq], 1u);
-    }
-    // phase 1: wait for sub-table q
-    if (threadIdx.x == 0) {
-        while (atomicAdd(&ready[q], 0u) < B) __nanosleep(100);
-        __threadfence();
-    }
-    __syncthreads();
-    // phase 2: count
-    unsigned long long beg = bucket_off[q], end = bucket_off[q + 1];
-    CountSlot* sub = table + (uint64_t)q * S;
-    unsigned int new_keys = 0, max_probe = 0;
-    // software pipeline: the bucket keys of the next iteration (a DRAM stream) are requested before this
-    // iteration's table accesses (L2) are issued
-    const unsigned long long stride = (unsigned long long)B * 256u * ITEMS;
-    unsigned long long i0 = beg + ((unsigned long long)b * 256u + threadIdx.x) * ITEMS;
-    uint64_t nkey[ITEMS];
-#pragma unroll
-    for (int j = 0; j < ITEMS; ++j) nkey[j] = (i0 + j < end) ? __ldcs(kbuf + i0 + j) : PC_KEY_SENTINEL;
-    for (; i0 < end; i0 += stride) {
-        unsigned long long skey[ITEMS]; uint64_t slot[ITEMS]; unsigned long long cur[ITEMS];
-        bool on[ITEMS];
-#pragma unroll
-        for (int j = 0; j < ITEMS; ++j) {
-            uint64_t key = nkey[j];
-            on[j] = key != PC_KEY_SENTINEL;
-            skey[j] = ~key;
-            slot[j] = slot_in_part(mix64(key), pb, S);
-        }
-#pragma unroll
-        for (int j = 0; j < ITEMS; ++j) nkey[j] = (i0 + stride + j < end) ? __ldcs(kbuf + i0 + stride + j) : PC_KEY_SENTINEL;
-        if (CASFIRST) {
-#pragma unroll
-            for (int j = 0; j < ITEMS; ++j) cur[j] = on[j] ? atomicCAS(&sub[slot[j]].skey, 0ull, skey[j]) : 0ull;
-#pragma unroll
-            for (int j = 0; j < ITEMS; ++j)
-                if (on[j]) count_insert_cas(sub, S, slot[j], skey[j], cur[j], new_keys, max_probe, stats);
-        } else {
-#pragma unroll
-            for (int j = 0; j < ITEMS; ++j) cur[j] = on[j] ? ldcg_u64(&sub[slot[j]].skey) : 0ull;
-            count_insert_batch<ITEMS>(sub, S, slot, skey, cur, on, new_keys, max_probe, stats);
+                for (int j = 0; j < ITEMS; ++j) cur[j] = on[j] ? ldcg_u64(&sub[slot[j]].skey) : 0ull;
+                count_insert_batch<ITEMS>(sub, S, slot, skey, cur, on, new_keys, max_probe, stats);
+            }
         }
     }
 #pragma unroll

@@ -4,8 +4,10 @@ Sharding: chunks are independent records, so the string-sorted ch
 contiguous blocks balanced by bases; shard-local CSR blocks concatenate into the final row order.  The only global
 coupling is the k-mer count reduction and the broadcast of the selected repeat set:
 
-  1. local count (K1-K3)                    -> pc_export_by_owner: (k-mer, count) grouped by owner = hash % world
-  2. all-to-all of the pairs (sizes first)  -> owners merge-add (k_merge) and threshold (K4) their key range
+  1. local K1 + pc_partition: canonical k-mers of the local chunks, radix-partitioned by the top bits of their hash;
+     rank r owns a contiguous range of buckets, so what each peer must receive is one contiguous slice
+  2. all-to-all of the raw 8-byte k-mers (bucket sizes first) -> every k-mer instance is counted exactly once, by its
+     owner, with the L2-resident bucket kernel (pc_count_buckets); owners threshold (K4) their share
   3. all-gather of the selected keys        -> every rank installs the identical sorted repeat set
   4. local probe + CSR (K5, K6); df all-reduce; TF-IDF (K7) with the global idf
   5. optional gather of the row blocks to rank 0 (host side; outside the timed region of bench.py)
@@ -72,6 +74,30 @@ def _all_gather_v(dist, local, torch):
     return torch.cat([o[:c] for o, c in zip(outs, counts)]), counts
 
 
+def plan_partition_bits(windows_global, world, part_bytes=64 << 20, table_load=0.6, slot_bytes=16):
+    """Bucket bits shared by all ranks: enough buckets that one sub-table (the unit that must stay L2 resident while it
+    is being counted) is about part_bytes, and at least one bucket per rank."""
+    cap_bytes = windows_global / table_load * slot_bytes
+    pb = 1
+    while pb < 12 and cap_bytes / (1 << pb) > part_bytes:
+        pb += 1
+    while (1 << pb) < world:
+        pb += 1
+    return pb
+
+
+class _DevView:
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
+
+
+def device_view(torch, ptr, n, device):
+    """Zero-copy int64 torch view of n k-mers at a raw device pointer owned by the context."""
+    if n == 0 or not ptr:
+        return torch.empty(0, dtype=torch.int64, device=device)
+    return torch.as_tensor(_DevView(ptr, n), device=device)
+
+
 def _stream_sync(torch, device):
     """The C ABI is host-synchronous on the context's stream; collectives are asynchronous on torch's stream.  When
     the two streams differ, wait for the collective before handing its output to the context (and vice versa the
@@ -107,23 +133,34 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
     n_local_rows = len(kept)
     assert n_local_rows == 0 or int(my_rows_global[kept].max()) - row0 + 1 == n_local_rows, "row block not contiguous"
 
-    # 1. local count
+    # 1. local partition: bucket = top pb bits of the k-mer hash, the same pb on every rank
+    windows_global = int(np.maximum(0, (layout.chunk_end - layout.chunk_start) - k + 1).sum())
+    pb = plan_partition_bits(windows_global, world)
+    P = 1 << pb
     ctx.load_sequences(buf, begins, ends)
-    ctx.count(k)
-    info = ctx.count_info()
-    d_local = info["distinct"]
-    keys_t = torch.empty(max(d_local, 1), dtype=torch.int64, device=device)
-    counts_t = torch.empty(max(d_local, 1), dtype=torch.int32, device=device)
-    offs = ctx.export_by_owner(world, keys_t, counts_t) if d_local else np.zeros(world + 1, np.int64)
-    send_counts = np.diff(offs).tolist()
-    # 2. all-to-all, owners merge + threshold
-    rkeys, _ = _all_to_all_v(dist, keys_t[:d_local], send_counts, torch)
-    rcounts, _ = _all_to_all_v(dist, counts_t[:d_local], send_counts, torch)
+    off, keys = ctx.partition(k, pb)
+    n_local = int(off[-1])
+    sizes = torch.from_numpy(np.diff(off).astype(np.int64)).to(device)
+    gathered = [torch.empty(P, dtype=torch.int64, device=device) for _ in range(world)]
+    dist.all_gather(gathered, sizes)
+    sizes_all = torch.stack(gathered).cpu().numpy()                       # [sender, bucket]
+    q_lo = [(r * P + world - 1) // world for r in range(world + 1)]      # rank r owns buckets [q_lo[r], q_lo[r+1])
+    send_counts = [int(sizes_all[rank, q_lo[r]:q_lo[r + 1]].sum()) for r in range(world)]
+    recv_counts = [int(sizes_all[s, q_lo[rank]:q_lo[rank + 1]].sum()) for s in range(world)]
+    send = keys if torch.is_tensor(keys) else device_view(torch, keys, n_local, device)
+    # 2. all-to-all of the raw k-mers over NVLink; count at the owner
+    recv = torch.empty(int(sum(recv_counts)), dtype=torch.int64, device=device)
+    dist.all_to_all_single(recv, send[:n_local], output_split_sizes=recv_counts, input_split_sizes=send_counts)
     _stream_sync(torch, device)
-    del keys_t, counts_t
-    ctx.merge_counts(rkeys, rcounts, rkeys.numel(), k, fresh=True)
+    mine = sizes_all[:, q_lo[rank]:q_lo[rank + 1]]                        # [sender, my bucket]
+    recv_off = np.concatenate([[0], np.cumsum(recv_counts)])[:-1]
+    within = np.cumsum(mine, axis=1) - mine                               # offset of bucket q inside sender s's slice
+    seg_begin = (recv_off[:, None] + within).T.copy()                     # [my bucket, sender]
+    seg_len = mine.T.copy()
+    ctx.count_buckets(k, pb, recv, seg_begin, seg_len)
     owner_info = ctx.count_info()
-    del rkeys, rcounts
+    info = dict(owner_info, valid_windows=n_local)
+    del recv
     n_owner_sel = ctx.select(effective_low_count(k, kmer_low_count), kmer_high_count, bool(high_bool), 1)
     sel_local = torch.empty(max(n_owner_sel, 1), dtype=torch.int64, device=device)
     if n_owner_sel:
@@ -145,7 +182,7 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
     _stream_sync(torch, device)
     if tfidf:
         ctx.tfidf(len(scaffolds_all), df_t if n_sel else None)
-    t = torch.tensor([info["valid_windows"], owner_info["distinct"], nnz], dtype=torch.int64, device=device)
+    t = torch.tensor([n_local, owner_info["distinct"], nnz], dtype=torch.int64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     stats = dict(info)
     stats.update(n_selected=n_sel, nnz=nnz, n_rows=n_local_rows, n_rows_global=len(scaffolds_all), row0=row0,

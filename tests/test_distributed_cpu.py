@@ -31,6 +31,30 @@ class OracleContext:
         return dict(capacity=0, distinct=len(self.keys), valid_windows=int(getattr(self, "n_windows", 0)),
                     table_bytes=0, max_probe=0, k=self.k)
 
+    def partition(self, k, pb):
+        """Stand-in for pc_partition: every canonical k-mer INSTANCE of the local chunks, grouped by a hash bucket."""
+        import torch
+        from polycracker_b200 import binding
+        words, nmask, _ = binding.host_pack_chunks(self.seq, self.begins, self.ends)
+        keys, valid = binding.host_extract(words, nmask, k)
+        inst = keys[valid]
+        with np.errstate(over="ignore"):
+            h = inst * np.uint64(0x9E3779B97F4A7C15)
+        bucket = (h >> np.uint64(64 - pb)).astype(np.int64)
+        order = np.argsort(bucket, kind="stable")
+        self.k = k
+        off = np.concatenate([[0], np.cumsum(np.bincount(bucket, minlength=1 << pb))]).astype(np.int64)
+        return off, torch.from_numpy(inst[order].view(np.int64).copy())
+
+    def count_buckets(self, k, pb, keys, seg_begin, seg_len, capacity=0):
+        arr = keys.numpy().view(np.uint64)
+        parts = [arr[b:b + n] for b, n in zip(np.asarray(seg_begin).ravel().tolist(), np.asarray(seg_len).ravel().tolist())]
+        allk = np.concatenate(parts) if parts else np.empty(0, np.uint64)
+        self.k = k
+        self.keys, cnt = np.unique(allk, return_counts=True)
+        self.counts = cnt.astype(np.uint64)
+        self.n_windows = 0
+
     def export_by_owner(self, world, keys_t, counts_t):
         owner = (self.keys % np.uint64(world)).astype(np.int64)
         order = np.argsort(owner, kind="stable")

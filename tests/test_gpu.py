@@ -118,23 +118,33 @@ def test_partitioned_count_equals_direct_and_oracle(ctx, k, mb):
             assert np.array_equal(counts[order].astype(np.uint64), want_counts), "mode %d" % mode
             info = ctx.count_info()
             assert info["valid_windows"] == n_windows and info["distinct"] == len(want_keys)
-        # every combination of table initialisation (host memset / fused in-kernel zeroing) and table sizing
-        # (window upper bound / HyperLogLog estimate, including an estimate that is far too small -> retry)
-        for fused, hll, bias in ((0, 0, 100), (1, 0, 100), (0, 1, 100), (1, 1, 100), (1, 1, 15), (0, 1, 15)):
-            ctx.tune(part_mode=1, part_mbytes=mb, fused_zero=fused, hll_sizing=hll, hll_bias_pct=bias)
+        # insert variants of the bucket kernel (load-first / CAS-first, 2 or 4 k-mers in flight per thread)
+        for casfirst, items in ((1, 4), (0, 2), (0, 4)):
+            ctx.tune(part_mode=1, part_mbytes=mb, part_casfirst=casfirst, count_items=items)
             ctx.count(k)
             keys, counts = ctx.dump_counts(1)
             order = np.argsort(keys)
-            assert np.array_equal(keys[order], want_keys), (fused, hll, bias)
-            assert np.array_equal(counts[order].astype(np.uint64), want_counts), (fused, hll, bias)
-            info = ctx.count_info()
-            assert info["valid_windows"] == n_windows and info["distinct"] == len(want_keys)
-            if hll and bias == 100:
-                assert abs(info["distinct_estimate"] - len(want_keys)) <= 0.1 * len(want_keys)
-        ctx.tune(part_mode=1, part_mbytes=mb, fused_zero=1, hll_sizing=1, hll_bias_pct=100)
+            assert np.array_equal(keys[order], want_keys), (casfirst, items)
+            assert np.array_equal(counts[order].astype(np.uint64), want_counts), (casfirst, items)
+        # the multi-GPU building blocks on one device: partition, then count the buckets as two "ranks" would
+        # (bucket ranges [0, P/2) and [P/2, P), each fed by two segments per bucket)
+        pb = 3
+        off_b, keys_ptr = ctx.partition(k, pb)
+        assert off_b[-1] == n_windows and np.all(np.diff(off_b) >= 0)
+        got = {}
+        for lo, hi in ((0, 4), (4, 8)):
+            seg_begin = np.array([[off_b[q], off_b[q] + (off_b[q + 1] - off_b[q]) // 3] for q in range(lo, hi)])
+            seg_len = np.array([[(off_b[q + 1] - off_b[q]) // 3, (off_b[q + 1] - off_b[q]) - (off_b[q + 1] - off_b[q]) // 3]
+                                for q in range(lo, hi)])
+            ctx.count_buckets(k, pb, keys_ptr, seg_begin, seg_len)
+            kk, cc = ctx.dump_counts(1)
+            assert not (set(kk.tolist()) & set(got))                         # owners hold disjoint k-mers
+            got.update(zip(kk.tolist(), cc.tolist()))
+        assert got == dict(zip(want_keys.tolist(), want_counts.tolist()))
+        ctx.tune(part_mode=1, part_mbytes=mb)
         _check_against_c_oracle(ctx, seq, off, names, 20000, k, 5)
     finally:
-        ctx.tune(part_mode=-1, part_mbytes=64, fused_zero=0, hll_sizing=0, hll_bias_pct=100)
+        ctx.tune(part_mode=-1, part_mbytes=64, part_casfirst=0, count_items=4)
 
 
 def test_small_table_reports_overflow_not_garbage(ctx):
