@@ -31,6 +31,9 @@ METRIC = "matrix_build_gbp_per_s_k23"
 UNIT = "Gbp/s"
 WORKLOAD = "cfg2_500Mbp_allotetraploid"
 FALLBACK_HBM_GBS = 6650.0
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
+# capture of this workload (profiles/); None until a capture of the current kernel exists
+NCU_TRAFFIC = {}
 
 
 def parse_args():
@@ -263,7 +266,7 @@ def run_b200_arm(args):
     if rank == 0:
         sampler.start()
     per_step_timings = []
-    ms_total, _ = timed(args.steps, True, False, per_step_timings)
+    ms_total, last_resident = timed(args.steps, True, False, per_step_timings)
     clocks = sampler.stop() if rank == 0 else None
     launches = ctx.launch_count()
     ms_per_step = ms_total / args.steps
@@ -290,18 +293,40 @@ def run_b200_arm(args):
         return 0
 
     # ---- roofline of the dominant kernel, from the CUDA-event time of its launches ------------------------------
+    # ALGORITHMIC bytes (DESIGN.md "Roofline model"), per rank: G packed bases, T valid windows,
+    # cap table slots, Ds selected k-mers, nnz matrix entries, R rows.  The K3 model (0.375 G + 24 T) is split over
+    # the three kernels that implement K3 here: the bucket count kernel owns the 24 T (one 12-byte slot
+    # read-modify-write per k-mer instance), extract + scatter own the packed-genome read.
     peak, peak_src = hbm_peak()
     stage_ms = {name: float(np.mean([t[name] for t in per_step_timings])) for name in per_step_timings[0]}
-    dom = max((n for n in stage_ms if n not in ("h2d", "d2h")), key=lambda n: stage_ms[n])
-    n_words = sum(int((e - b) // 32 + 1) for b, e in zip(begins.tolist(), ends.tolist()))
-    count_bytes = algorithmic_bytes_count(n_words * 32, info["valid_windows"])
-    count_ms = stage_ms["count"]
-    achieved = count_bytes / (count_ms * 1e-3) / 1e9 if count_ms > 0 else 0.0
-    roofline = {"bound": "hbm", "kernel": "k_count", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": count_bytes, "launch_ms": count_ms,
-                "dominant_stage_by_time": dom, "stage_ms": stage_ms,
-                "model": "0.375 B/packed base + 24 B/k-mer instance (SURVEY.md 8d K3), per rank"}
+    st = last_resident.stats
+    G = sum(int((e - b) // 32 + 1) for b, e in zip(begins.tolist(), ends.tolist())) * 32
+    T, cap, Ds, nnz, R = st["valid_windows"], info["capacity"], st["n_selected"], st["nnz"], st["n_rows"]
+    model = {
+        "K1_pack": (1.375 * G, stage_ms["pack"]),
+        "K3_extract+scatter": (0.375 * G, stage_ms["part_hist"] + stage_ms["part_scatter"]),
+        "K3_count": (24.0 * T, stage_ms["count"]),
+        "K4_select+sort": (12.0 * cap + 12.0 * Ds, stage_ms["table_init"] + stage_ms["select"] + stage_ms["sort"] + stage_ms["rep_table"]),
+        "K5_probe": (0.375 * G + 12.0 * T + 8.0 * nnz, stage_ms["probe"]),
+        "K6_rows_to_csr": (16.0 * nnz + 8.0 * R, stage_ms["row_sort"] + stage_ms["emit"]),
+        "K7_tfidf": (12.0 * nnz + 4.0 * Ds, stage_ms["tfidf"]),
+    }
+    kernels = {}
+    for name, (nbytes, ms) in model.items():
+        gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        kernels[name] = {"algorithmic_bytes": nbytes, "ms": ms, "achieved_gbs": gbs, "frac": gbs / peak}
+    dom = max(kernels, key=lambda n: kernels[n]["ms"])
+    d = kernels[dom]
+    path_bytes = sum(v[0] for v in model.values())
+    roofline = {"bound": "hbm", "kernel": {"K3_count": "k_count_part (bucket count)"}.get(dom, dom), "achieved": d["achieved_gbs"],
+                "peak": peak, "unit": "GB/s", "frac": d["frac"], "traffic": NCU_TRAFFIC.get(dom), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": d["algorithmic_bytes"], "launch_ms": d["ms"],
+                "whole_path": {"algorithmic_bytes": path_bytes, "ms": ms_per_step,
+                               "achieved_gbs": path_bytes / (ms_per_step * 1e-3) / 1e9,
+                               "frac": path_bytes / (ms_per_step * 1e-3) / 1e9 / peak},
+                "per_kernel": kernels, "stage_ms": stage_ms,
+                "model": "SURVEY.md 8d per-unit bytes x units of this launch, per rank; the timed kernel is "
+                         "L2-sector/atomic bound, not HBM-stream bound (profiles/)"}
 
     cpu_baseline = None
     if not args.no_cpu_baseline:

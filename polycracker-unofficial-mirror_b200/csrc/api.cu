@@ -721,12 +721,22 @@ int pc_set_selected(pc_ctx* c, const uint64_t* keys, int64_t n, int k, int loc, 
     rc = radix_sort_u64(c, c->sel_a.p, c->sel_b.p, n, 2 * k, &sorted); if (rc) return rc;
     uint64_t* other = (sorted == c->sel_a.p) ? c->sel_b.p : c->sel_a.p;
     unsigned long long nu = 0;
+    uint64_t* result = sorted;
     if (n > 0) {
-        LAUNCH(c, pc::k_unique_sorted_single, 1, 1024, sorted, n, other, c->d_counter.p);
-        CU(cudaMemcpyAsync(&nu, c->d_counter.p, sizeof nu, cudaMemcpyDeviceToHost, c->stream));
+        unsigned long long dups = 0;
+        CU(cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned long long), c->stream));
+        LAUNCH(c, pc::k_count_dups, blocks_for(n, 256), 256, sorted, n, c->d_counter.p);
+        CU(cudaMemcpyAsync(&dups, c->d_counter.p, sizeof dups, cudaMemcpyDeviceToHost, c->stream));
         CU(cudaStreamSynchronize(c->stream));
+        nu = (unsigned long long)n;
+        if (dups) {                                            // rare: a k-mer FASTA listing a k-mer (or both strands) twice
+            LAUNCH(c, pc::k_unique_sorted_single, 1, 1024, sorted, n, other, c->d_counter.p);
+            CU(cudaMemcpyAsync(&nu, c->d_counter.p, sizeof nu, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            result = other;
+        }
     }
-    c->sel = other; c->n_sel = (int64_t)nu;
+    c->sel = result; c->n_sel = (int64_t)nu;
     rc = build_rep_table(c); if (rc) return rc;
     c->selected = true;
     if (n_unique) *n_unique = c->n_sel;

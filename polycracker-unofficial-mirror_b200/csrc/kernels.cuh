@@ -776,6 +776,16 @@ k_unique_sorted_single(const uint64_t* __restrict__ src, int64_t n, uint64_t* __
     if (t == 0) *n_out = carry;
 }
 
+// number of adjacent duplicates in a sorted array (0 in the normal case: owners select disjoint key sets)
+__global__ void __launch_bounds__(256)
+k_count_dups(const uint64_t* __restrict__ sorted, int64_t n, unsigned long long* __restrict__ n_dups)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool dup = i > 0 && i < n && sorted[i] == sorted[i - 1];
+    unsigned int bal = __ballot_sync(0xFFFFFFFFu, dup);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(n_dups, (unsigned long long)__popc(bal));
+}
+
 __global__ void __launch_bounds__(256)
 k_canonicalize(uint64_t* __restrict__ keys, int64_t n, int k)
 {
