@@ -104,6 +104,10 @@ int pc_merge_counts(pc_ctx* ctx, const uint64_t* keys_dev, const uint32_t* count
  * keep count >= low (and <= high when use_high); sort ascending; keep every `sampling`-th survivor
  * (sorted-order sampling: declared deviation, the reference samples in the counter's dump order). */
 int pc_select(pc_ctx* ctx, uint32_t low, uint32_t high, int use_high, int64_t sampling, int64_t* n_selected);
+/* optional, before pc_count / pc_count_buckets: fuse K4 into K3.  The insert that lifts a k-mer to exactly `low`
+ * occurrences records it, so a following pc_select(low, use_high = 0) does not re-scan the table (12 B x capacity of
+ * HBM traffic).  low = 0 switches the watch off.  Any other pc_select argument falls back to the scan. */
+int pc_watch_threshold(pc_ctx* ctx, uint32_t low);
 int pc_selected_get(pc_ctx* ctx, uint64_t* keys, int loc);             /* n_selected keys, ascending */
 /* install an externally chosen repeat set (the separately invoked blast_kmers stage reads it from the k-mer
  * FASTA, polycracker.py:244; the multi-GPU path installs the all-gathered set).  Keys need not be sorted or

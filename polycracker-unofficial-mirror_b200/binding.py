@@ -67,6 +67,7 @@ _SIGS = {
     "pc_export_by_owner": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _vp]),
     "pc_merge_counts": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, _i64, C.c_int]),
     "pc_select": (C.c_int, [_vp, _u32, _u32, C.c_int, _i64, _P(_i64)]),
+    "pc_watch_threshold": (C.c_int, [_vp, _u32]),
     "pc_selected_get": (C.c_int, [_vp, _vp, C.c_int]),
     "pc_set_selected": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, _P(_i64)]),
     "pc_build_matrix": (C.c_int, [_vp, _vp, _i64, _P(_i64)]),
@@ -352,6 +353,9 @@ class Context:
                                   int(n), int(k), int(capacity), int(bool(fresh))), "pc_merge_counts")
 
     # K4
+    def watch_threshold(self, low):
+        check(lib.pc_watch_threshold(self._h, int(low)), "pc_watch_threshold")
+
     def select(self, low, high=2000000, use_high=False, sampling=1):
         n = _i64()
         check(lib.pc_select(self._h, int(low), int(high), int(bool(use_high)), int(sampling), C.byref(n)), "pc_select")

@@ -54,7 +54,9 @@ struct DevBuf {
 
 struct pc_ctx {
     int device = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t own_stream = nullptr, stream = nullptr, aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    uint64_t zeroed_slots = 0;                  // slots of `table` zeroed by the pending side-stream memset
     cudaEvent_t ev[ST_N][2];
     bool ev_used[ST_N];
     int64_t launches = 0;
@@ -77,7 +79,7 @@ struct pc_ctx {
     DevBuf<uint64_t> sel_a, sel_b; uint64_t* sel = nullptr; int64_t n_sel = 0;
     DevBuf<unsigned int> rs_hist;
     DevBuf<unsigned long long> d_counter;
-    DevBuf<pc::RepSlot> rtable; uint64_t rcap = 0;
+    DevBuf<pc::RepSlot> rtable; DevBuf<unsigned int> rocc; uint64_t rcap = 0;
     bool selected = false;
 
     // matrix
@@ -106,6 +108,9 @@ struct pc_ctx {
     // inserts (one ATOM per new k-mer, no load) are slower than load-first; HyperLogLog-sized denser tables and
     // in-kernel zeroing of the next sub-table were slower too and have been removed again
     int part_casfirst = 0;
+    // threshold watch (pc_watch_threshold): k-mers that reach watch_low during a partitioned count
+    uint32_t watch_low = 0; bool cross_valid = false; uint32_t cross_low = 0;
+    DevBuf<uint64_t> cross_keys; DevBuf<unsigned long long> d_cross_n;
     int count_items = 4;
 };
 
@@ -166,9 +171,12 @@ int build_rep_table(pc_ctx* c) {
     c->rcap = std::max<uint64_t>(64, (uint64_t)c->n_sel * (uint64_t)std::max(2, c->rep_load_inv));
     int rc = c->rtable.alloc(c->rcap);
     if (rc) return rc;
+    rc = c->rocc.alloc((c->rcap + 31) / 32 + 1);
+    if (rc) return rc;
     CU(cudaMemsetAsync(c->rtable.p, 0, c->rcap * sizeof(pc::RepSlot), c->stream));
+    CU(cudaMemsetAsync(c->rocc.p, 0, ((c->rcap + 31) / 32 + 1) * sizeof(unsigned int), c->stream));
     if (c->n_sel > 0)
-        LAUNCH(c, pc::k_rep_build, blocks_for(c->n_sel, 256), 256, c->sel, c->n_sel, c->rtable.p, c->rcap);
+        LAUNCH(c, pc::k_rep_build, blocks_for(c->n_sel, 256), 256, c->sel, c->n_sel, c->rtable.p, c->rcap, c->rocc.p);
     return PC_OK;
 }
 
@@ -199,6 +207,9 @@ int pc_create(int device, pc_ctx** out) {
     pc_ctx* c = new pc_ctx();
     c->device = device;
     CU(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     c->stream = c->own_stream;
     for (int i = 0; i < ST_N; ++i) {
         CU(cudaEventCreate(&c->ev[i][0])); CU(cudaEventCreate(&c->ev[i][1])); c->ev_used[i] = false;
@@ -215,13 +226,15 @@ int pc_destroy(pc_ctx* c) {
     cudaStreamSynchronize(c->stream);
     c->ascii.release(); c->d_word0.release(); c->d_begin.release(); c->d_len.release();
     c->words.release(); c->nmask.release(); c->table.release(); c->d_stats.release();
-    c->kbuf.release(); c->kstream.release(); c->d_part_hist.release(); c->d_seg.release();
-    c->sel_a.release(); c->sel_b.release(); c->rs_hist.release(); c->d_counter.release(); c->rtable.release();
+    c->kbuf.release(); c->kstream.release(); c->d_part_hist.release(); c->d_seg.release(); c->cross_keys.release(); c->d_cross_n.release();
+    c->sel_a.release(); c->sel_b.release(); c->rs_hist.release(); c->d_counter.release(); c->rtable.release(); c->rocc.release();
     c->d_chunk_row.release(); c->d_row_base.release(); c->d_row_cursor.release(); c->hits_a.release();
     c->hits_b.release(); c->d_row_nnz.release(); c->d_indptr.release(); c->d_indices.release();
     c->d_data.release(); c->d_idf.release(); c->d_tfidf.release(); c->d_df.release(); c->d_df_global.release();
     for (int i = 0; i < ST_N; ++i) { cudaEventDestroy(c->ev[i][0]); cudaEventDestroy(c->ev[i][1]); }
     cudaStreamDestroy(c->own_stream);
+    cudaStreamDestroy(c->aux_stream);
+    cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
     delete c;
     return PC_OK;
 }
@@ -346,19 +359,49 @@ int pc_packed_get(pc_ctx* c, uint64_t* words, uint32_t* nmask, int64_t* chunk_wo
 }
 
 // ---------------------------------------------------------------------------------------------- K3
-static int table_prepare(pc_ctx* c, int k, int64_t capacity, bool reset_stats = true) {
+static int table_alloc(pc_ctx* c, int k, int64_t capacity) {
     if (k < 1 || k > 32) return fail(PC_EINVAL, "k = %d unsupported: this path handles 1 <= k <= 32 (uint64 k-mers)", k);
-    if (capacity < 64) capacity = 64;
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
     size_t need = (size_t)capacity * sizeof(pc::CountSlot);
     if (need > free_b + c->table.n * sizeof(pc::CountSlot))
         return fail(PC_ENOMEM, "count table of %lld slots (%.1f GB) does not fit in free HBM (%.1f GB): shard the genome over more GPUs",
                     (long long)capacity, need / 1e9, free_b / 1e9);
-    int rc = c->table.alloc((size_t)capacity); if (rc) return rc;
+    return c->table.alloc((size_t)capacity);
+}
+
+// Start zeroing `capacity` slots on the side stream (ordered after everything already queued on the main stream), so
+// the 16 B/slot memset overlaps the extract + scatter kernels, which leave most of the HBM bandwidth unused.
+static int table_prezero(pc_ctx* c, int k, int64_t capacity) {
+    if (capacity < 64) capacity = 64;
+    int rc = table_alloc(c, k, capacity); if (rc) return rc;
+    CU(cudaEventRecord(c->ev_fork, c->stream));
+    CU(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+    CU(cudaEventRecord(c->ev[ST_TABLE_INIT][0], c->aux_stream));
+    CU(cudaMemsetAsync(c->table.p, 0, (size_t)capacity * sizeof(pc::CountSlot), c->aux_stream));
+    CU(cudaEventRecord(c->ev[ST_TABLE_INIT][1], c->aux_stream));
+    c->ev_used[ST_TABLE_INIT] = true;
+    CU(cudaEventRecord(c->ev_join, c->aux_stream));
+    c->zeroed_slots = (uint64_t)capacity;
+    return PC_OK;
+}
+
+static int table_prepare(pc_ctx* c, int k, int64_t capacity, bool reset_stats = true) {
+    if (capacity < 64) capacity = 64;
+    if (c->zeroed_slots > 0 && c->table.p && c->table.n >= (size_t)capacity) {
+        // a side-stream memset is pending: join it, zero whatever it did not cover
+        CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        if ((uint64_t)capacity > c->zeroed_slots)
+            CU(cudaMemsetAsync(c->table.p + c->zeroed_slots, 0, ((size_t)capacity - c->zeroed_slots) * sizeof(pc::CountSlot), c->stream));
+        c->zeroed_slots = 0;
+    } else {
+        if (c->zeroed_slots > 0) { CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0)); c->zeroed_slots = 0; }
+        int rc = table_alloc(c, k, capacity); if (rc) return rc;
+        StageTimer t(c, ST_TABLE_INIT);
+        CU(cudaMemsetAsync(c->table.p, 0, (size_t)capacity * sizeof(pc::CountSlot), c->stream));
+    }
     c->capacity = (uint64_t)capacity; c->k = k;
-    StageTimer t(c, ST_TABLE_INIT);
-    CU(cudaMemsetAsync(c->table.p, 0, (size_t)capacity * sizeof(pc::CountSlot), c->stream));
+    c->cross_valid = false;
     if (reset_stats) CU(cudaMemsetAsync(c->d_stats.p, 0, sizeof(pc::CountStats), c->stream));
     return PC_OK;
 }
@@ -458,19 +501,35 @@ static int do_count_buckets(pc_ctx* c, int k, int pb, int n_buckets, const uint6
     CU(cudaMemcpyAsync(c->d_seg.p + (size_t)n_buckets * n_seg, seg_len, (size_t)n_buckets * n_seg * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
     const long long* d_beg = reinterpret_cast<const long long*>(c->d_seg.p);
     const long long* d_len = d_beg + (size_t)n_buckets * n_seg;
+    pc::Watch w{0u, nullptr, nullptr, 0ull};
+    c->cross_valid = false;
+    if (c->watch_low > 0) {
+        unsigned long long cap = (unsigned long long)(total / c->watch_low) + 1024ull;
+        rc = c->cross_keys.alloc((size_t)cap); if (rc) return rc;
+        rc = c->d_cross_n.alloc(1); if (rc) return rc;
+        CU(cudaMemsetAsync(c->d_cross_n.p, 0, sizeof(unsigned long long), c->stream));
+        w = pc::Watch{c->watch_low, c->d_cross_n.p, c->cross_keys.p, cap};
+        c->cross_valid = true; c->cross_low = c->watch_low;
+    }
     if (total > 0) {
         StageTimer t(c, ST_COUNT);
         unsigned int B = (unsigned int)c->part_blocks;
         unsigned int grid = (unsigned int)n_buckets * B;
         if (c->part_casfirst)
-            LAUNCH(c, (pc::k_count_part<4, true>), grid, 256, keys_dev, d_beg, d_len, n_seg, pb, S, B, c->table.p, c->d_stats.p);
+            LAUNCH(c, (pc::k_count_part<4, true>), grid, 256, keys_dev, d_beg, d_len, n_seg, pb, S, B, c->table.p, c->d_stats.p, w);
         else if (c->count_items == 2)
-            LAUNCH(c, (pc::k_count_part<2, false>), grid, 256, keys_dev, d_beg, d_len, n_seg, pb, S, B, c->table.p, c->d_stats.p);
+            LAUNCH(c, (pc::k_count_part<2, false>), grid, 256, keys_dev, d_beg, d_len, n_seg, pb, S, B, c->table.p, c->d_stats.p, w);
         else
-            LAUNCH(c, (pc::k_count_part<4, false>), grid, 256, keys_dev, d_beg, d_len, n_seg, pb, S, B, c->table.p, c->d_stats.p);
+            LAUNCH(c, (pc::k_count_part<4, false>), grid, 256, keys_dev, d_beg, d_len, n_seg, pb, S, B, c->table.p, c->d_stats.p, w);
     }
     rc = fetch_stats(c); if (rc) return rc;                   // synchronises: the host segment arrays may go away
     c->counted = true;
+    return PC_OK;
+}
+
+int pc_watch_threshold(pc_ctx* c, uint32_t low) {
+    if (!c) return fail(PC_EINVAL, "null context");
+    c->watch_low = low;
     return PC_OK;
 }
 
@@ -532,6 +591,7 @@ int pc_count(pc_ctx* c, int k, int64_t capacity) {
 
     // ---- partitioned path: extract -> tile scatter -> bucket-by-bucket count ----------------------------------
     CU(cudaMemsetAsync(c->d_stats.p, 0, sizeof(pc::CountStats), c->stream));
+    rc = table_prezero(c, k, (int64_t)(((uint64_t)capacity + P - 1) / P * P)); if (rc) return rc;
     rc = do_partition(c, k, pb); if (rc) return rc;
     std::vector<int64_t> seg_begin(P), seg_len(P);
     for (uint64_t q = 0; q < P; ++q) { seg_begin[q] = c->h_bucket_off[q]; seg_len[q] = c->h_bucket_off[q + 1] - c->h_bucket_off[q]; }
@@ -551,6 +611,11 @@ int pc_partition(pc_ctx* c, int k, int pb, int64_t* bucket_off, uint64_t** keys_
     c->counted = c->selected = c->built = c->tfidf_done = false;
     c->stream_valid = false;
     CU(cudaMemsetAsync(c->d_stats.p, 0, sizeof(pc::CountStats), c->stream));
+    {   // the owner will count about as many k-mers as this rank extracts: start zeroing a table of that size now
+        int64_t windows = 0;
+        for (int64_t i = 0; i < c->n_chunks; ++i) windows += std::max<int64_t>(0, c->h_len[i] - k + 1);
+        rc = table_prezero(c, k, (int64_t)(windows / c->table_load) + 1024); if (rc) return rc;
+    }
     rc = do_partition(c, k, pb); if (rc) return rc;
     memcpy(bucket_off, c->h_bucket_off.data(), ((size_t)(1u << pb) + 1) * sizeof(int64_t));
     *keys_dev = c->kbuf.p;
@@ -670,7 +735,16 @@ int pc_select(pc_ctx* c, uint32_t low, uint32_t high, int use_high, int64_t samp
     int64_t cap = std::min<int64_t>((int64_t)c->h_stats.distinct, (int64_t)1 << 26);
     cap = std::max<int64_t>(cap, 1024);
     int64_t n = 0;
-    {
+    if (c->cross_valid && !use_high && c->cross_low == low) {
+        // K4 was fused into the count: the k-mers that reached `low` are already listed
+        StageTimer t(c, ST_SELECT);
+        unsigned long long nc = 0;
+        CU(cudaMemcpyAsync(&nc, c->d_cross_n.p, sizeof nc, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        n = (int64_t)nc;
+        rc = c->sel_a.alloc(std::max<int64_t>(n, 1024)); if (rc) return rc;
+        if (n) CU(cudaMemcpyAsync(c->sel_a.p, c->cross_keys.p, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
+    } else {
         StageTimer t(c, ST_SELECT);
         rc = c->sel_a.alloc(cap); if (rc) return rc;
         rc = select_into(c, low, high, c->sel_a.p, nullptr, cap, &n); if (rc) return rc;
@@ -818,13 +892,13 @@ int pc_build_matrix(pc_ctx* c, const int32_t* chunk_row, int64_t n_rows, int64_t
             if (use_stream) {
                 if (c->probe_batch == 4)
                     LAUNCH(c, (pc::k_probe_stream<4>), grid, 256, c->kstream.p, c->n_words, c->d_word0.p, c->n_chunks,
-                           c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, c->hits_a.p, c->d_row_cursor.p);
+                           c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, c->rocc.p, c->hits_a.p, c->d_row_cursor.p);
                 else
                     LAUNCH(c, (pc::k_probe_stream<8>), grid, 256, c->kstream.p, c->n_words, c->d_word0.p, c->n_chunks,
-                           c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, c->hits_a.p, c->d_row_cursor.p);
+                           c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, c->rocc.p, c->hits_a.p, c->d_row_cursor.p);
             } else {
                 LAUNCH(c, (pc::k_probe<8>), grid, 256, c->words.p, c->nmask.p, c->n_words, k, c->d_word0.p, c->n_chunks,
-                       c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, c->hits_a.p, c->d_row_cursor.p);
+                       c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, c->rocc.p, c->hits_a.p, c->d_row_cursor.p);
             }
         }
     }

@@ -32,6 +32,28 @@ struct CountStats {
     unsigned long long max_probe;
 };
 
+// Threshold watch (K4 fused into K3): when low != 0 the increment of a repeat is a returning atomic and the insert
+// that lifts a k-mer to exactly `low` occurrences appends it to `keys` -- each k-mer with count >= low exactly once --
+// so pc_select(low) does not have to scan the whole table again.
+struct Watch {
+    unsigned int low;
+    unsigned long long* n;
+    uint64_t* keys;
+    unsigned long long cap;
+};
+__device__ __forceinline__ void watch_append(const Watch& w, unsigned long long skey) {
+    unsigned long long pos = atomicAdd(w.n, 1ull);
+    if (pos < w.cap) w.keys[pos] = ~skey;
+}
+__device__ __forceinline__ void count_repeat(CountSlot* slot, unsigned long long skey, const Watch& w) {
+    if (w.low) {
+        unsigned int old = atomicAdd(&slot->count, 1u);      // stored = occurrences - 1
+        if (old + 2u == w.low) watch_append(w, skey);
+    } else {
+        atomicAdd(&slot->count, 1u);                          // result unused -> RED
+    }
+}
+
 __device__ __forceinline__ unsigned long long ldcg_u64(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p));
@@ -169,19 +191,20 @@ __device__ __forceinline__ WordPair load_word_pair(const uint64_t* __restrict__ 
 __device__ __forceinline__ void count_insert(CountSlot* __restrict__ table, uint64_t capacity, uint64_t slot,
                                              unsigned long long skey, unsigned long long cur,
                                              unsigned int& new_keys, unsigned int& max_probe,
-                                             CountStats* stats)
+                                             CountStats* stats, const Watch w = Watch{0u, nullptr, nullptr, 0ull})
 {
     // `cur` is the (possibly stale-empty) key already loaded from table[slot]
     unsigned int probes = 0;
     for (;;) {
         if (cur == 0ull) {
             cur = atomicCAS(&table[slot].skey, 0ull, skey);
-            if (cur == 0ull) { ++new_keys; break; }            // claimed: count field 0 == one occurrence
+            if (cur == 0ull) {                                 // claimed: count field 0 == one occurrence
+                ++new_keys;
+                if (w.low == 1u) watch_append(w, skey);
+                break;
+            }
         }
-        if (cur == skey) {
-            atomicAdd(&table[slot].count, 1u);                // result unused -> RED
-            break;
-        }
+        if (cur == skey) { count_repeat(&table[slot], skey, w); break; }
         if (++probes > PC_PROBE_LIMIT || probes >= capacity) { atomicAdd(&stats->overflow, 1ull); break; }
         if (++slot == capacity) slot = 0;
         cur = ldcg_u64(&table[slot].skey);
@@ -193,12 +216,13 @@ __device__ __forceinline__ void count_insert(CountSlot* __restrict__ table, uint
 // `cur` is the value the first CAS on table[slot] returned.
 __device__ __forceinline__ void count_insert_cas(CountSlot* __restrict__ table, uint64_t capacity, uint64_t slot,
                                                  unsigned long long skey, unsigned long long cur,
-                                                 unsigned int& new_keys, unsigned int& max_probe, CountStats* stats)
+                                                 unsigned int& new_keys, unsigned int& max_probe, CountStats* stats,
+                                                 const Watch w = Watch{0u, nullptr, nullptr, 0ull})
 {
     unsigned int probes = 0;
     for (;;) {
-        if (cur == 0ull) { ++new_keys; break; }
-        if (cur == skey) { atomicAdd(&table[slot].count, 1u); break; }
+        if (cur == 0ull) { ++new_keys; if (w.low == 1u) watch_append(w, skey); break; }
+        if (cur == skey) { count_repeat(&table[slot], skey, w); break; }
         if (++probes > PC_PROBE_LIMIT || probes >= capacity) { atomicAdd(&stats->overflow, 1ull); break; }
         if (++slot == capacity) slot = 0;
         cur = atomicCAS(&table[slot].skey, 0ull, skey);
@@ -213,7 +237,7 @@ template <int N>
 __device__ __forceinline__ void count_insert_batch(CountSlot* __restrict__ table, uint64_t capacity, const uint64_t (&slot)[N],
                                                    const unsigned long long (&skey)[N], unsigned long long (&cur)[N],
                                                    const bool (&on)[N], unsigned int& new_keys, unsigned int& max_probe,
-                                                   CountStats* stats)
+                                                   CountStats* stats, const Watch w = Watch{0u, nullptr, nullptr, 0ull})
 {
     bool cas[N];
 #pragma unroll
@@ -226,17 +250,28 @@ __device__ __forceinline__ void count_insert_batch(CountSlot* __restrict__ table
     for (int j = 0; j < N; ++j) {
         claimed[j] = cas[j] && cur[j] == 0ull;
         new_keys += claimed[j];
+        if (claimed[j] && w.low == 1u) watch_append(w, skey[j]);
     }
+    if (w.low) {                                               // returning atomics, all issued before any is consumed
+        unsigned int old[N];
 #pragma unroll
-    for (int j = 0; j < N; ++j)
-        if (on[j] && !claimed[j] && cur[j] == skey[j]) atomicAdd(&table[slot[j]].count, 1u);
+        for (int j = 0; j < N; ++j)
+            old[j] = (on[j] && !claimed[j] && cur[j] == skey[j]) ? atomicAdd(&table[slot[j]].count, 1u) : 0xFFFFFFF0u;
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+            if (old[j] + 2u == w.low) watch_append(w, skey[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+            if (on[j] && !claimed[j] && cur[j] == skey[j]) atomicAdd(&table[slot[j]].count, 1u);
+    }
 #pragma unroll
     for (int j = 0; j < N; ++j)
         if (on[j] && !claimed[j] && cur[j] != skey[j]) {       // occupied by another k-mer: probe onwards
             uint64_t s = slot[j] + 1; if (s == capacity) s = 0;
             unsigned long long c2 = ldcg_u64(&table[s].skey);
             unsigned int mp = 0;
-            count_insert(table, capacity, s, skey[j], c2, new_keys, mp, stats);
+            count_insert(table, capacity, s, skey[j], c2, new_keys, mp, stats, w);
             max_probe = max(max_probe, mp + 1u);
         }
 }
@@ -486,7 +521,8 @@ k_tile_scatter(const uint64_t* __restrict__ stream, int64_t n_stream, int pb,
 template <int ITEMS, bool CASFIRST>
 __global__ void __launch_bounds__(256)
 k_count_part(const uint64_t* __restrict__ keys, const long long* __restrict__ seg_begin, const long long* __restrict__ seg_len,
-             int n_seg, int pb, uint64_t S, unsigned int B, CountSlot* __restrict__ table, CountStats* __restrict__ stats)
+             int n_seg, int pb, uint64_t S, unsigned int B, CountSlot* __restrict__ table, CountStats* __restrict__ stats,
+             const Watch w)
 {
     unsigned int q = blockIdx.x / B, b = blockIdx.x % B;
     CountSlot* sub = table + (uint64_t)q * S;
@@ -518,11 +554,11 @@ k_count_part(const uint64_t* __restrict__ keys, const long long* __restrict__ se
                 for (int j = 0; j < ITEMS; ++j) cur[j] = on[j] ? atomicCAS(&sub[slot[j]].skey, 0ull, skey[j]) : 0ull;
 #pragma unroll
                 for (int j = 0; j < ITEMS; ++j)
-                    if (on[j]) count_insert_cas(sub, S, slot[j], skey[j], cur[j], new_keys, max_probe, stats);
+                    if (on[j]) count_insert_cas(sub, S, slot[j], skey[j], cur[j], new_keys, max_probe, stats, w);
             } else {
 #pragma unroll
                 for (int j = 0; j < ITEMS; ++j) cur[j] = on[j] ? ldcg_u64(&sub[slot[j]].skey) : 0ull;
-                count_insert_batch<ITEMS>(sub, S, slot, skey, cur, on, new_keys, max_probe, stats);
+                count_insert_batch<ITEMS>(sub, S, slot, skey, cur, on, new_keys, max_probe, stats, w);
             }
         }
     }
@@ -805,7 +841,8 @@ k_stride_gather(const uint64_t* __restrict__ src, int64_t n_out, int64_t stride,
 
 // ------------------------------------------------------------------------------------------------ K5 repeat table + probe
 __global__ void __launch_bounds__(256)
-k_rep_build(const uint64_t* __restrict__ sorted_keys, int64_t n, RepSlot* __restrict__ table, uint64_t capacity)
+k_rep_build(const uint64_t* __restrict__ sorted_keys, int64_t n, RepSlot* __restrict__ table, uint64_t capacity,
+            unsigned int* __restrict__ occ /* one bit per slot, zeroed */)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -814,7 +851,7 @@ k_rep_build(const uint64_t* __restrict__ sorted_keys, int64_t n, RepSlot* __rest
     uint64_t slot = slot_of(mix64(key), capacity);
     for (;;) {                                               // keys are unique and capacity >= 2n: terminates
         unsigned long long cur = atomicCAS(&table[slot].skey, 0ull, skey);
-        if (cur == 0ull) { table[slot].col = (int)i; break; }
+        if (cur == 0ull) { table[slot].col = (int)i; atomicOr(&occ[slot >> 5], 1u << (slot & 31)); break; }
         if (++slot == capacity) slot = 0;
     }
 }
@@ -835,7 +872,7 @@ __global__ void __launch_bounds__(256)
 k_probe(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, int64_t n_words, int k,
         const int64_t* __restrict__ chunk_word0, int64_t n_chunks, const int32_t* __restrict__ chunk_row,
         const int64_t* __restrict__ row_hit_base, const RepSlot* __restrict__ rtable, uint64_t rcap,
-        int32_t* __restrict__ hits, unsigned int* __restrict__ row_cursor)
+        const unsigned int* __restrict__ occ, int32_t* __restrict__ hits, unsigned int* __restrict__ row_cursor)
 {
     int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int lane = threadIdx.x & 31;
@@ -870,6 +907,14 @@ k_probe(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, 
                 skey[j] = ~key;
                 slot[j] = slot_of(mix64(key), rcap);
                 if (b < 31) r.step(b);
+            }
+            // occupancy bitmap (1 bit per slot, L1/L2 resident): ~3 of 4 windows end here without touching the table
+            {
+                unsigned int ob[BATCH];
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) ob[j] = ((vmask >> j) & 1u) ? __ldg(occ + (slot[j] >> 5)) : 0u;
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) if (!((ob[j] >> (slot[j] & 31)) & 1u)) vmask &= ~(1u << j);
             }
 #pragma unroll
             for (int j = 0; j < BATCH; ++j)
@@ -925,7 +970,7 @@ __global__ void __launch_bounds__(256)
 k_probe_stream(const uint64_t* __restrict__ stream, int64_t n_words,
                const int64_t* __restrict__ chunk_word0, int64_t n_chunks, const int32_t* __restrict__ chunk_row,
                const int64_t* __restrict__ row_hit_base, const RepSlot* __restrict__ rtable, uint64_t rcap,
-               int32_t* __restrict__ hits, unsigned int* __restrict__ row_cursor)
+               const unsigned int* __restrict__ occ, int32_t* __restrict__ hits, unsigned int* __restrict__ row_cursor)
 {
     int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int lane = threadIdx.x & 31;
@@ -955,6 +1000,14 @@ k_probe_stream(const uint64_t* __restrict__ stream, int64_t n_words,
                 vmask |= (unsigned int)(key != PC_KEY_SENTINEL) << j;
                 skey[j] = ~key;
                 slot[j] = slot_of(mix64(key), rcap);
+            }
+            // occupancy bitmap (1 bit per slot, L1/L2 resident): ~3 of 4 windows end here without touching the table
+            {
+                unsigned int ob[BATCH];
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) ob[j] = ((vmask >> j) & 1u) ? __ldg(occ + (slot[j] >> 5)) : 0u;
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) if (!((ob[j] >> (slot[j] & 31)) & 1u)) vmask &= ~(1u << j);
             }
 #pragma unroll
             for (int j = 0; j < BATCH; ++j)

@@ -157,6 +157,8 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
     within = np.cumsum(mine, axis=1) - mine                               # offset of bucket q inside sender s's slice
     seg_begin = (recv_off[:, None] + within).T.copy()                     # [my bucket, sender]
     seg_len = mine.T.copy()
+    if hasattr(ctx, "watch_threshold"):
+        ctx.watch_threshold(0 if high_bool else effective_low_count(k, kmer_low_count))  # K4 fused into K3
     ctx.count_buckets(k, pb, recv, seg_begin, seg_len)
     owner_info = ctx.count_info()
     info = dict(owner_info, valid_windows=n_local)

@@ -139,6 +139,7 @@ def run_hot_path(ctx, seq, seq_offsets, names, chunk_size=75000, k=23, kmer_low_
         layout = ChunkLayout(names, seq_offsets, chunk_size)
     scaffolds, chunk_row = layout.rows(remove_non_chunk, min_chunk_threshold, min_chunk_size, prefilter)
     ctx.load_sequences(seq, layout.chunk_begin_abs, layout.chunk_end_abs)
+    ctx.watch_threshold(0 if high_bool else effective_low_count(k, kmer_low_count))      # K4 fused into K3
     ctx.count(k, table_capacity)
     n_sel = ctx.select(effective_low_count(k, kmer_low_count), kmer_high_count, bool(high_bool),
                        sampling_sensitivity)
