@@ -57,6 +57,8 @@ struct pc_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr, aux_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint64_t zeroed_slots = 0;                  // slots of `table` zeroed by the pending side-stream memset
+    int prezero = 0;                            // overlap the table memset with extract+scatter (measured: no gain)
+    int probe_bitmap = 0;                       // occupancy bitmap in front of the repeat table (measured: slower)
     cudaEvent_t ev[ST_N][2];
     bool ev_used[ST_N];
     int64_t launches = 0;
@@ -71,7 +73,8 @@ struct pc_ctx {
 
     // count table
     int k = 0;
-    DevBuf<pc::CountSlot> table; uint64_t capacity = 0;
+    DevBuf<unsigned long long> table_keys; DevBuf<unsigned int> table_counts; uint64_t capacity = 0;
+    pc::CountTable table() const { return pc::CountTable{table_keys.p, table_counts.p}; }
     DevBuf<pc::CountStats> d_stats; pc::CountStats h_stats{};
     bool counted = false;
 
@@ -98,7 +101,7 @@ struct pc_ctx {
     int probe_batch = 4;
     int rep_load_inv = 4;                       // repeat table capacity = rep_load_inv * n_selected
     bool stream_valid = false; int stream_k = 0;
-    int part_blocks = 512;                      // blocks per bucket in k_count_part
+    int part_blocks = 0;                        // blocks per bucket in k_count_part (0 = from the bucket size)
 
     // partitioned count state
     int pb = 0; uint64_t part_S = 0;
@@ -225,7 +228,7 @@ int pc_destroy(pc_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->ascii.release(); c->d_word0.release(); c->d_begin.release(); c->d_len.release();
-    c->words.release(); c->nmask.release(); c->table.release(); c->d_stats.release();
+    c->words.release(); c->nmask.release(); c->table_keys.release(); c->table_counts.release(); c->d_stats.release();
     c->kbuf.release(); c->kstream.release(); c->d_part_hist.release(); c->d_seg.release(); c->cross_keys.release(); c->d_cross_n.release();
     c->sel_a.release(); c->sel_b.release(); c->rs_hist.release(); c->d_counter.release(); c->rtable.release(); c->rocc.release();
     c->d_chunk_row.release(); c->d_row_base.release(); c->d_row_cursor.release(); c->hits_a.release();
@@ -363,22 +366,25 @@ static int table_alloc(pc_ctx* c, int k, int64_t capacity) {
     if (k < 1 || k > 32) return fail(PC_EINVAL, "k = %d unsupported: this path handles 1 <= k <= 32 (uint64 k-mers)", k);
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    size_t need = (size_t)capacity * sizeof(pc::CountSlot);
-    if (need > free_b + c->table.n * sizeof(pc::CountSlot))
+    size_t need = (size_t)capacity * (size_t)PC_SLOT_BYTES;
+    if (need > free_b + c->table_keys.n * (size_t)PC_SLOT_BYTES)
         return fail(PC_ENOMEM, "count table of %lld slots (%.1f GB) does not fit in free HBM (%.1f GB): shard the genome over more GPUs",
                     (long long)capacity, need / 1e9, free_b / 1e9);
-    return c->table.alloc((size_t)capacity);
+    int rc = c->table_keys.alloc((size_t)capacity); if (rc) return rc;
+    return c->table_counts.alloc((size_t)capacity);
 }
 
 // Start zeroing `capacity` slots on the side stream (ordered after everything already queued on the main stream), so
 // the 16 B/slot memset overlaps the extract + scatter kernels, which leave most of the HBM bandwidth unused.
 static int table_prezero(pc_ctx* c, int k, int64_t capacity) {
+    if (!c->prezero) return PC_OK;
     if (capacity < 64) capacity = 64;
     int rc = table_alloc(c, k, capacity); if (rc) return rc;
     CU(cudaEventRecord(c->ev_fork, c->stream));
     CU(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
     CU(cudaEventRecord(c->ev[ST_TABLE_INIT][0], c->aux_stream));
-    CU(cudaMemsetAsync(c->table.p, 0, (size_t)capacity * sizeof(pc::CountSlot), c->aux_stream));
+    CU(cudaMemsetAsync(c->table_keys.p, 0, (size_t)capacity * 8, c->aux_stream));
+    CU(cudaMemsetAsync(c->table_counts.p, 0, (size_t)capacity * 4, c->aux_stream));
     CU(cudaEventRecord(c->ev[ST_TABLE_INIT][1], c->aux_stream));
     c->ev_used[ST_TABLE_INIT] = true;
     CU(cudaEventRecord(c->ev_join, c->aux_stream));
@@ -388,17 +394,21 @@ static int table_prezero(pc_ctx* c, int k, int64_t capacity) {
 
 static int table_prepare(pc_ctx* c, int k, int64_t capacity, bool reset_stats = true) {
     if (capacity < 64) capacity = 64;
-    if (c->zeroed_slots > 0 && c->table.p && c->table.n >= (size_t)capacity) {
+    if (c->zeroed_slots > 0 && c->table_keys.p && c->table_keys.n >= (size_t)capacity && c->table_counts.n >= (size_t)capacity) {
         // a side-stream memset is pending: join it, zero whatever it did not cover
         CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0));
         if ((uint64_t)capacity > c->zeroed_slots)
-            CU(cudaMemsetAsync(c->table.p + c->zeroed_slots, 0, ((size_t)capacity - c->zeroed_slots) * sizeof(pc::CountSlot), c->stream));
+        {
+            CU(cudaMemsetAsync(c->table_keys.p + c->zeroed_slots, 0, ((size_t)capacity - c->zeroed_slots) * 8, c->stream));
+            CU(cudaMemsetAsync(c->table_counts.p + c->zeroed_slots, 0, ((size_t)capacity - c->zeroed_slots) * 4, c->stream));
+        }
         c->zeroed_slots = 0;
     } else {
         if (c->zeroed_slots > 0) { CU(cudaStreamWaitEvent(c->stream, c->ev_join, 0)); c->zeroed_slots = 0; }
         int rc = table_alloc(c, k, capacity); if (rc) return rc;
         StageTimer t(c, ST_TABLE_INIT);
-        CU(cudaMemsetAsync(c->table.p, 0, (size_t)capacity * sizeof(pc::CountSlot), c->stream));
+        CU(cudaMemsetAsync(c->table_keys.p, 0, (size_t)capacity * 8, c->stream));
+        CU(cudaMemsetAsync(c->table_counts.p, 0, (size_t)capacity * 4, c->stream));
     }
     c->capacity = (uint64_t)capacity; c->k = k;
     c->cross_valid = false;
@@ -418,7 +428,7 @@ static int fetch_stats(pc_ctx* c) {
 #define COUNT_CASE(B, M, MODE)                                                                               \
     if (c->count_batch == B && c->count_minb == M && c->count_mode == MODE) {                                \
         LAUNCH(c, (pc::k_count<B, M, MODE>), blocks_for(c->n_words, 256), 256, c->words.p, c->nmask.p,       \
-               c->n_words, c->k, c->table.p, c->capacity, c->d_stats.p);                                      \
+               c->n_words, c->k, c->table(), c->capacity, c->d_stats.p);                                      \
         return PC_OK;                                                                                        \
     }
 static int launch_count(pc_ctx* c) {
@@ -513,14 +523,21 @@ static int do_count_buckets(pc_ctx* c, int k, int pb, int n_buckets, const uint6
     }
     if (total > 0) {
         StageTimer t(c, ST_COUNT);
+        // blocks per bucket: ~14 k-mers per thread keeps the resident blocks on one or two buckets (L2) and still
+        // amortises the block prologue (measured: B=512 best at 1.5 M keys/bucket, B=1024 at 3.9 M)
         unsigned int B = (unsigned int)c->part_blocks;
+        if (c->part_blocks <= 0) {
+            double want = (double)(total / n_buckets) / 3600.0;
+            B = 64; while (B < 4096 && (double)B * 1.41 < want) B <<= 1;
+        }
         unsigned int grid = (unsigned int)n_buckets * B;
-        if (c->part_casfirst)
-            LAUNCH(c, (pc::k_count_part<4, true>), grid, 256, keys_dev, d_beg, d_len, n_seg, pb, S, B, c->table.p, c->d_stats.p, w);
-        else if (c->count_items == 2)
-            LAUNCH(c, (pc::k_count_part<2, false>), grid, 256, keys_dev, d_beg, d_len, n_seg, pb, S, B, c->table.p, c->d_stats.p, w);
-        else
-            LAUNCH(c, (pc::k_count_part<4, false>), grid, 256, keys_dev, d_beg, d_len, n_seg, pb, S, B, c->table.p, c->d_stats.p, w);
+#define COUNT_PART(I, CF, W) LAUNCH(c, (pc::k_count_part<I, CF, W>), grid, 256, keys_dev, d_beg, d_len, n_seg, pb, S, B, c->table(), c->d_stats.p, w)
+        if (w.low) {
+            if (c->part_casfirst) COUNT_PART(4, true, true); else COUNT_PART(4, false, true);
+        } else if (c->part_casfirst) COUNT_PART(4, true, false);
+        else if (c->count_items == 2) COUNT_PART(2, false, false);
+        else COUNT_PART(4, false, false);
+#undef COUNT_PART
     }
     rc = fetch_stats(c); if (rc) return rc;                   // synchronises: the host segment arrays may go away
     c->counted = true;
@@ -543,11 +560,13 @@ int pc_tune(pc_ctx* c, const char* key, int64_t value) {
     else if (k == "part_mode") c->part_mode = (int)value;
     else if (k == "count_items") c->count_items = (int)value;
     else if (k == "probe_mode") c->probe_mode = (int)value;
+    else if (k == "prezero") c->prezero = (int)value;
+    else if (k == "probe_bitmap") c->probe_bitmap = (int)value;
     else if (k == "part_casfirst") c->part_casfirst = (int)value;
     else if (k == "probe_batch") c->probe_batch = (int)value;
     else if (k == "rep_load_inv") c->rep_load_inv = (int)value;
     else if (k == "part_mbytes") c->part_bytes = std::max<int64_t>(1, value) << 20;
-    else if (k == "part_blocks") c->part_blocks = (int)std::max<int64_t>(1, value);
+    else if (k == "part_blocks") c->part_blocks = (int)std::max<int64_t>(0, value);
     else if (k == "table_load_pct") c->table_load = std::min(0.95, std::max(0.05, value / 100.0));
     else if (k == "l2_fetch_granularity") CU(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)value));
     else return fail(PC_EINVAL, "unknown tunable %s", key);
@@ -570,9 +589,9 @@ int pc_count(pc_ctx* c, int k, int64_t capacity) {
     }
     // partition plan: P = 2^pb sub-tables of S slots, each about part_bytes so that it stays L2 resident
     int pb = 0;
-    bool partitioned = c->part_mode == 1 || (c->part_mode < 0 && (size_t)capacity * sizeof(pc::CountSlot) > (size_t)(64ll << 20));
+    bool partitioned = c->part_mode == 1 || (c->part_mode < 0 && (size_t)capacity * (size_t)PC_SLOT_BYTES > (size_t)(64ll << 20));
     if (partitioned) {
-        while (pb < 12 && ((size_t)capacity * sizeof(pc::CountSlot)) >> pb > (size_t)c->part_bytes) ++pb;
+        while (pb < 12 && ((size_t)capacity * (size_t)PC_SLOT_BYTES) >> pb > (size_t)c->part_bytes) ++pb;
         if (pb == 0) pb = 1;
     }
     uint64_t P = 1ull << pb;
@@ -640,7 +659,7 @@ int pc_count_info(pc_ctx* c, int64_t info[8]) {
     if (!c || !c->counted) return fail(PC_ESTATE, "no count table");
     memset(info, 0, 8 * sizeof(int64_t));
     info[0] = (int64_t)c->capacity; info[1] = (int64_t)c->h_stats.distinct; info[2] = (int64_t)c->h_stats.valid_windows;
-    info[3] = (int64_t)(c->capacity * sizeof(pc::CountSlot)); info[4] = (int64_t)c->h_stats.max_probe; info[5] = c->k;
+    info[3] = (int64_t)(c->capacity * (size_t)PC_SLOT_BYTES); info[4] = (int64_t)c->h_stats.max_probe; info[5] = c->k;
     info[6] = 0; info[7] = c->pb;
     return PC_OK;
 }
@@ -650,7 +669,7 @@ static int select_into(pc_ctx* c, uint32_t low, uint32_t high, uint64_t* keys_de
                        int64_t* n_out) {
     CU(cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned long long), c->stream));
     unsigned int grid = (unsigned int)std::min<uint64_t>((c->capacity + 255) / 256, 148ull * 16);
-    LAUNCH(c, pc::k_select, grid, 256, c->table.p, c->capacity, low, high, keys_dev, counts_dev,
+    LAUNCH(c, pc::k_select, grid, 256, c->table(), c->capacity, low, high, keys_dev, counts_dev,
            (unsigned long long)cap, c->d_counter.p);
     unsigned long long n = 0;
     CU(cudaMemcpyAsync(&n, c->d_counter.p, sizeof n, cudaMemcpyDeviceToHost, c->stream));
@@ -689,14 +708,14 @@ int pc_export_by_owner(pc_ctx* c, int world, uint64_t* keys_dev, uint32_t* count
     StageTimer t(c, ST_EXPORT);
     CU(cudaMemsetAsync(c->d_counter.p, 0, 64 * sizeof(unsigned long long), c->stream));
     unsigned int grid = (unsigned int)std::min<uint64_t>((c->capacity + 255) / 256, 148ull * 16);
-    LAUNCH(c, pc::k_owner_hist, grid, 256, c->table.p, c->capacity, (unsigned int)world, c->d_counter.p);
+    LAUNCH(c, pc::k_owner_hist, grid, 256, c->table(), c->capacity, (unsigned int)world, c->d_counter.p);
     unsigned long long hist[64];
     CU(cudaMemcpyAsync(hist, c->d_counter.p, world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     unsigned long long start[64]; offsets[0] = 0;
     for (int r = 0; r < world; ++r) { start[r] = (unsigned long long)offsets[r]; offsets[r + 1] = offsets[r] + (int64_t)hist[r]; }
     CU(cudaMemcpyAsync(c->d_counter.p, start, world * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
-    LAUNCH(c, pc::k_owner_scatter, grid, 256, c->table.p, c->capacity, (unsigned int)world, c->d_counter.p, keys_dev, counts_dev);
+    LAUNCH(c, pc::k_owner_scatter, grid, 256, c->table(), c->capacity, (unsigned int)world, c->d_counter.p, keys_dev, counts_dev);
     CU(cudaStreamSynchronize(c->stream));
     return PC_OK;
 }
@@ -717,7 +736,7 @@ int pc_merge_counts(pc_ctx* c, const uint64_t* keys_dev, const uint32_t* counts_
     }
     {
         StageTimer t(c, ST_MERGE);
-        if (n > 0) LAUNCH(c, pc::k_merge, blocks_for(n, 256), 256, keys_dev, counts_dev, n, c->table.p, c->capacity, c->d_stats.p);
+        if (n > 0) LAUNCH(c, pc::k_merge, blocks_for(n, 256), 256, keys_dev, counts_dev, n, c->table(), c->capacity, c->d_stats.p);
     }
     rc = fetch_stats(c); if (rc) return rc;
     c->counted = true;
@@ -892,13 +911,13 @@ int pc_build_matrix(pc_ctx* c, const int32_t* chunk_row, int64_t n_rows, int64_t
             if (use_stream) {
                 if (c->probe_batch == 4)
                     LAUNCH(c, (pc::k_probe_stream<4>), grid, 256, c->kstream.p, c->n_words, c->d_word0.p, c->n_chunks,
-                           c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, c->rocc.p, c->hits_a.p, c->d_row_cursor.p);
+                           c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, c->probe_bitmap ? c->rocc.p : nullptr, c->hits_a.p, c->d_row_cursor.p);
                 else
                     LAUNCH(c, (pc::k_probe_stream<8>), grid, 256, c->kstream.p, c->n_words, c->d_word0.p, c->n_chunks,
-                           c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, c->rocc.p, c->hits_a.p, c->d_row_cursor.p);
+                           c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, c->probe_bitmap ? c->rocc.p : nullptr, c->hits_a.p, c->d_row_cursor.p);
             } else {
                 LAUNCH(c, (pc::k_probe<8>), grid, 256, c->words.p, c->nmask.p, c->n_words, k, c->d_word0.p, c->n_chunks,
-                       c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, c->rocc.p, c->hits_a.p, c->d_row_cursor.p);
+                       c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, c->probe_bitmap ? c->rocc.p : nullptr, c->hits_a.p, c->d_row_cursor.p);
             }
         }
     }

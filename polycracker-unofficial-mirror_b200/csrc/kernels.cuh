@@ -8,15 +8,18 @@
 namespace pc {
 
 // ------------------------------------------------------------------------------------------------ tables
-// Count table slot (K3).  skey = ~kmer so that a zeroed table is empty (the all-ones pattern is never a
-// canonical-min k-mer: its reverse complement, all A, is smaller).  16-byte slots keep key and count in one
-// 32-byte DRAM sector: one sector read per probe instead of two with a split layout.
-// count holds (occurrences - 1): claiming a slot with the CAS already records the first occurrence, so a new k-mer
-// costs one L2 transaction and only repeats pay for a RED.
-struct __align__(16) CountSlot {
-    unsigned long long skey;
-    unsigned int count;
-    unsigned int pad;
+// Count table (K3): open addressing, linear probing, structure of arrays.  keys[s] = ~kmer so that a zeroed table is
+// empty (the all-ones pattern is never a canonical-min k-mer: its reverse complement, all A, is smaller);
+// counts[s] = occurrences - 1: the CAS that claims a slot already records the first occurrence, so a new k-mer costs
+// one L2 operation and only repeats pay for a RED.  12 bytes per slot; four keys share a 32-byte sector, the threshold
+// scan (K4) reads only the 4-byte counts.
+#define PC_SLOT_BYTES 12
+struct CountTable {
+    unsigned long long* keys;
+    unsigned int* counts;
+    __device__ __forceinline__ unsigned long long* key(uint64_t s) const { return keys + s; }
+    __device__ __forceinline__ unsigned int* cnt(uint64_t s) const { return counts + s; }
+    __device__ __forceinline__ CountTable sub(uint64_t off) const { return CountTable{keys + off, counts + off}; }
 };
 // Repeat table slot (K5): selected k-mer -> column id.
 struct __align__(16) RepSlot {
@@ -45,12 +48,12 @@ __device__ __forceinline__ void watch_append(const Watch& w, unsigned long long 
     unsigned long long pos = atomicAdd(w.n, 1ull);
     if (pos < w.cap) w.keys[pos] = ~skey;
 }
-__device__ __forceinline__ void count_repeat(CountSlot* slot, unsigned long long skey, const Watch& w) {
+__device__ __forceinline__ void count_repeat(unsigned int* cnt, unsigned long long skey, const Watch& w) {
     if (w.low) {
-        unsigned int old = atomicAdd(&slot->count, 1u);      // stored = occurrences - 1
+        unsigned int old = atomicAdd(cnt, 1u);               // stored = occurrences - 1
         if (old + 2u == w.low) watch_append(w, skey);
     } else {
-        atomicAdd(&slot->count, 1u);                          // result unused -> RED
+        atomicAdd(cnt, 1u);                                   // result unused -> RED
     }
 }
 
@@ -188,7 +191,7 @@ __device__ __forceinline__ WordPair load_word_pair(const uint64_t* __restrict__ 
 // ------------------------------------------------------------------------------------------------ K3 count
 #define PC_PROBE_LIMIT (1u << 22)
 
-__device__ __forceinline__ void count_insert(CountSlot* __restrict__ table, uint64_t capacity, uint64_t slot,
+__device__ __forceinline__ void count_insert(CountTable table, uint64_t capacity, uint64_t slot,
                                              unsigned long long skey, unsigned long long cur,
                                              unsigned int& new_keys, unsigned int& max_probe,
                                              CountStats* stats, const Watch w = Watch{0u, nullptr, nullptr, 0ull})
@@ -197,24 +200,24 @@ __device__ __forceinline__ void count_insert(CountSlot* __restrict__ table, uint
     unsigned int probes = 0;
     for (;;) {
         if (cur == 0ull) {
-            cur = atomicCAS(&table[slot].skey, 0ull, skey);
+            cur = atomicCAS(table.key(slot), 0ull, skey);
             if (cur == 0ull) {                                 // claimed: count field 0 == one occurrence
                 ++new_keys;
                 if (w.low == 1u) watch_append(w, skey);
                 break;
             }
         }
-        if (cur == skey) { count_repeat(&table[slot], skey, w); break; }
+        if (cur == skey) { count_repeat(table.cnt(slot), skey, w); break; }
         if (++probes > PC_PROBE_LIMIT || probes >= capacity) { atomicAdd(&stats->overflow, 1ull); break; }
         if (++slot == capacity) slot = 0;
-        cur = ldcg_u64(&table[slot].skey);
+        cur = ldcg_u64(table.key(slot));
     }
     max_probe = max(max_probe, probes);
 }
 
 // CAS-first variant for L2-resident sub-tables: no separate load, one ATOM per new k-mer, ATOM + RED per repeat.
 // `cur` is the value the first CAS on table[slot] returned.
-__device__ __forceinline__ void count_insert_cas(CountSlot* __restrict__ table, uint64_t capacity, uint64_t slot,
+__device__ __forceinline__ void count_insert_cas(CountTable table, uint64_t capacity, uint64_t slot,
                                                  unsigned long long skey, unsigned long long cur,
                                                  unsigned int& new_keys, unsigned int& max_probe, CountStats* stats,
                                                  const Watch w = Watch{0u, nullptr, nullptr, 0ull})
@@ -222,10 +225,10 @@ __device__ __forceinline__ void count_insert_cas(CountSlot* __restrict__ table, 
     unsigned int probes = 0;
     for (;;) {
         if (cur == 0ull) { ++new_keys; if (w.low == 1u) watch_append(w, skey); break; }
-        if (cur == skey) { count_repeat(&table[slot], skey, w); break; }
+        if (cur == skey) { count_repeat(table.cnt(slot), skey, w); break; }
         if (++probes > PC_PROBE_LIMIT || probes >= capacity) { atomicAdd(&stats->overflow, 1ull); break; }
         if (++slot == capacity) slot = 0;
-        cur = atomicCAS(&table[slot].skey, 0ull, skey);
+        cur = atomicCAS(table.key(slot), 0ull, skey);
     }
     max_probe = max(max_probe, probes);
 }
@@ -234,7 +237,7 @@ __device__ __forceinline__ void count_insert_cas(CountSlot* __restrict__ table, 
 // (1) every CAS the batch needs is issued back to back, (2) results are folded, (3) REDs go out, and only keys that
 // collided with a different k-mer enter the (serial) linear-probing loop.
 template <int N>
-__device__ __forceinline__ void count_insert_batch(CountSlot* __restrict__ table, uint64_t capacity, const uint64_t (&slot)[N],
+__device__ __forceinline__ void count_insert_batch(CountTable table, uint64_t capacity, const uint64_t (&slot)[N],
                                                    const unsigned long long (&skey)[N], unsigned long long (&cur)[N],
                                                    const bool (&on)[N], unsigned int& new_keys, unsigned int& max_probe,
                                                    CountStats* stats, const Watch w = Watch{0u, nullptr, nullptr, 0ull})
@@ -243,7 +246,7 @@ __device__ __forceinline__ void count_insert_batch(CountSlot* __restrict__ table
 #pragma unroll
     for (int j = 0; j < N; ++j) {
         cas[j] = on[j] && cur[j] == 0ull;
-        if (cas[j]) cur[j] = atomicCAS(&table[slot[j]].skey, 0ull, skey[j]);
+        if (cas[j]) cur[j] = atomicCAS(table.key(slot[j]), 0ull, skey[j]);
     }
     bool claimed[N];
 #pragma unroll
@@ -256,20 +259,20 @@ __device__ __forceinline__ void count_insert_batch(CountSlot* __restrict__ table
         unsigned int old[N];
 #pragma unroll
         for (int j = 0; j < N; ++j)
-            old[j] = (on[j] && !claimed[j] && cur[j] == skey[j]) ? atomicAdd(&table[slot[j]].count, 1u) : 0xFFFFFFF0u;
+            old[j] = (on[j] && !claimed[j] && cur[j] == skey[j]) ? atomicAdd(table.cnt(slot[j]), 1u) : 0xFFFFFFF0u;
 #pragma unroll
         for (int j = 0; j < N; ++j)
             if (old[j] + 2u == w.low) watch_append(w, skey[j]);
     } else {
 #pragma unroll
         for (int j = 0; j < N; ++j)
-            if (on[j] && !claimed[j] && cur[j] == skey[j]) atomicAdd(&table[slot[j]].count, 1u);
+            if (on[j] && !claimed[j] && cur[j] == skey[j]) atomicAdd(table.cnt(slot[j]), 1u);
     }
 #pragma unroll
     for (int j = 0; j < N; ++j)
         if (on[j] && !claimed[j] && cur[j] != skey[j]) {       // occupied by another k-mer: probe onwards
             uint64_t s = slot[j] + 1; if (s == capacity) s = 0;
-            unsigned long long c2 = ldcg_u64(&table[s].skey);
+            unsigned long long c2 = ldcg_u64(table.key(s));
             unsigned int mp = 0;
             count_insert(table, capacity, s, skey[j], c2, new_keys, mp, stats, w);
             max_probe = max(max_probe, mp + 1u);
@@ -286,7 +289,7 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 template <int BATCH, int MINB, int MODE>
 __global__ void __launch_bounds__(256, MINB)
 k_count(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, int64_t n_words, int k,
-        CountSlot* __restrict__ table, uint64_t capacity, CountStats* __restrict__ stats)
+        CountTable table, uint64_t capacity, CountStats* __restrict__ stats)
 {
     int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     WordPair p = load_word_pair(words, nmask, w, n_words);
@@ -297,7 +300,7 @@ k_count(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, 
         if (MODE == 1) {
 #pragma unroll
             for (int j = 0; j < BATCH; ++j) {
-                if (lead.valid(j)) prefetch_l2(&table[slot_of(mix64(lead.canonical()), capacity)]);
+                if (lead.valid(j)) prefetch_l2(table.key(slot_of(mix64(lead.canonical()), capacity)));
                 lead.step(j);
             }
         }
@@ -307,7 +310,7 @@ k_count(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, 
 #pragma unroll
                 for (int j = 0; j < BATCH; ++j) {
                     int b = b0 + BATCH + j;
-                    if (lead.valid(b)) prefetch_l2(&table[slot_of(mix64(lead.canonical()), capacity)]);
+                    if (lead.valid(b)) prefetch_l2(table.key(slot_of(mix64(lead.canonical()), capacity)));
                     if (b < 31) lead.step(b);
                 }
             }
@@ -326,9 +329,9 @@ k_count(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, 
 #pragma unroll
             for (int j = 0; j < BATCH; ++j) {                  // all probes of the batch in flight together
                 if (MODE == 2) {
-                    cur[j] = ((vmask >> j) & 1u) ? atomicCAS(&table[slot[j]].skey, 0ull, skey[j]) : 0ull;
+                    cur[j] = ((vmask >> j) & 1u) ? atomicCAS(table.key(slot[j]), 0ull, skey[j]) : 0ull;
                 } else {
-                    cur[j] = ((vmask >> j) & 1u) ? ldcg_u64(&table[slot[j]].skey) : 0ull;
+                    cur[j] = ((vmask >> j) & 1u) ? ldcg_u64(table.key(slot[j])) : 0ull;
                 }
             }
             if (MODE == 2) {
@@ -439,11 +442,12 @@ k_bucket_scan(const unsigned long long* __restrict__ hist, unsigned int P, unsig
 // consecutive addresses (scattered 8-byte stores into hundreds of open runs were the bottleneck of the first
 // version: 42 G stores/s regardless of how the ranks were computed).
 template <int TILE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 k_tile_scatter(const uint64_t* __restrict__ stream, int64_t n_stream, int pb,
                const unsigned long long* __restrict__ bucket_off, unsigned long long* __restrict__ cursor,
                uint64_t* __restrict__ kbuf)
 {
+    constexpr int PER = TILE / 256;                                      // keys per thread, held in registers
     extern __shared__ unsigned long long sm64[];
     const unsigned int P = 1u << pb;
     unsigned long long* sorted = sm64;                                   // [TILE]
@@ -457,13 +461,22 @@ k_tile_scatter(const uint64_t* __restrict__ stream, int64_t n_stream, int pb,
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint64_t* src = stream + tile * TILE;
         int64_t lim = min((int64_t)TILE, n_stream - tile * TILE);
+        // all PER loads of a thread are issued before any is consumed (the first version interleaved each load with
+        // its smem atomic and sat on long-scoreboard stalls at 25 % occupancy); the keys stay in registers for the
+        // ranking pass, so the stream is read once
+        uint64_t key[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            int i = j * 256 + t;
+            key[j] = (i < lim) ? __ldcs(src + i) : PC_KEY_SENTINEL;
+        }
         for (unsigned int i = t; i < P; i += 256) cnt[i] = 0;
         __syncthreads();
-#pragma unroll 8
-        for (int j = 0; j < TILE / 256; ++j) {
-            int i = j * 256 + t;
-            uint64_t key = (i < lim) ? __ldg(src + i) : PC_KEY_SENTINEL;
-            if (key != PC_KEY_SENTINEL) atomicAdd(&cnt[part_of(mix64(key), pb)], 1u);
+        unsigned short q[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            q[j] = (unsigned short)part_of(mix64(key[j]), pb);
+            if (key[j] != PC_KEY_SENTINEL) atomicAdd(&cnt[q[j]], 1u);
         }
         __syncthreads();
         // exclusive scan of cnt[P] -> lstart; reserve the global runs; cnt becomes the rank counter
@@ -471,7 +484,7 @@ k_tile_scatter(const uint64_t* __restrict__ stream, int64_t n_stream, int pb,
             unsigned int per = (P + 255) / 256;
             unsigned int b0 = min(P, t * per), b1 = min(P, b0 + per);
             unsigned int s = 0;
-            for (unsigned int q = b0; q < b1; ++q) s += cnt[q];
+            for (unsigned int x = b0; x < b1; ++x) s += cnt[x];
             unsigned int incl = s;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -484,32 +497,29 @@ k_tile_scatter(const uint64_t* __restrict__ stream, int64_t n_stream, int pb,
 #pragma unroll
             for (int x = 0; x < 8; ++x) if (x < wid) before += wsum[x];
             unsigned int run = before + incl - s;
-            for (unsigned int q = b0; q < b1; ++q) {
-                unsigned int c = cnt[q];
-                lstart[q] = run;
-                if (c) gbase[q] = bucket_off[q] + atomicAdd(&cursor[q], (unsigned long long)c);
-                cnt[q] = 0;
+            for (unsigned int x = b0; x < b1; ++x) {
+                unsigned int c = cnt[x];
+                lstart[x] = run;
+                if (c) gbase[x] = bucket_off[x] + atomicAdd(&cursor[x], (unsigned long long)c);
+                cnt[x] = 0;
                 run += c;
             }
             if (t == 255) lstart[P] = run;
         }
         __syncthreads();
-#pragma unroll 8
-        for (int j = 0; j < TILE / 256; ++j) {
-            int i = j * 256 + t;
-            uint64_t key = (i < lim) ? __ldg(src + i) : PC_KEY_SENTINEL;
-            if (key != PC_KEY_SENTINEL) {
-                unsigned int q = part_of(mix64(key), pb);
-                unsigned int pos = lstart[q] + atomicAdd(&cnt[q], 1u);
-                sorted[pos] = key;
-                qs[pos] = (unsigned short)q;
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            if (key[j] != PC_KEY_SENTINEL) {
+                unsigned int pos = lstart[q[j]] + atomicAdd(&cnt[q[j]], 1u);
+                sorted[pos] = key[j];
+                qs[pos] = q[j];
             }
         }
         __syncthreads();
         unsigned int nv = lstart[P];
         for (unsigned int i = t; i < nv; i += 256) {
-            unsigned int q = qs[i];
-            kbuf[gbase[q] + (i - lstart[q])] = sorted[i];
+            unsigned int x = qs[i];
+            kbuf[gbase[x] + (i - lstart[x])] = sorted[i];
         }
         __syncthreads();
     }
@@ -518,14 +528,15 @@ k_tile_scatter(const uint64_t* __restrict__ stream, int64_t n_stream, int pb,
 // pass C: count one bucket after the other.  blockIdx = local_bucket * B + b: blocks are dispatched in index order,
 // so at any time the resident blocks work on one or two adjacent buckets whose sub-tables (S slots) sit in L2.
 // A bucket's k-mers arrive as n_seg segments of `keys` (one per sending rank; a single segment on one GPU).
-template <int ITEMS, bool CASFIRST>
+template <int ITEMS, bool CASFIRST, bool WATCH>
 __global__ void __launch_bounds__(256)
 k_count_part(const uint64_t* __restrict__ keys, const long long* __restrict__ seg_begin, const long long* __restrict__ seg_len,
-             int n_seg, int pb, uint64_t S, unsigned int B, CountSlot* __restrict__ table, CountStats* __restrict__ stats,
-             const Watch w)
+             int n_seg, int pb, uint64_t S, unsigned int B, CountTable table, CountStats* __restrict__ stats,
+             const Watch w_in)
 {
+    const Watch w = WATCH ? w_in : Watch{0u, nullptr, nullptr, 0ull};    // compile-time off: plain REDs, no extra registers
     unsigned int q = blockIdx.x / B, b = blockIdx.x % B;
-    CountSlot* sub = table + (uint64_t)q * S;
+    CountTable sub = table.sub((uint64_t)q * S);
     unsigned int new_keys = 0, max_probe = 0;
     const unsigned long long stride = (unsigned long long)B * 256u * ITEMS;
     for (int sg = 0; sg < n_seg; ++sg) {
@@ -551,13 +562,13 @@ k_count_part(const uint64_t* __restrict__ keys, const long long* __restrict__ se
             for (int j = 0; j < ITEMS; ++j) nkey[j] = (i0 + stride + j < end) ? __ldcs(kbuf + i0 + stride + j) : PC_KEY_SENTINEL;
             if (CASFIRST) {
 #pragma unroll
-                for (int j = 0; j < ITEMS; ++j) cur[j] = on[j] ? atomicCAS(&sub[slot[j]].skey, 0ull, skey[j]) : 0ull;
+                for (int j = 0; j < ITEMS; ++j) cur[j] = on[j] ? atomicCAS(sub.key(slot[j]), 0ull, skey[j]) : 0ull;
 #pragma unroll
                 for (int j = 0; j < ITEMS; ++j)
                     if (on[j]) count_insert_cas(sub, S, slot[j], skey[j], cur[j], new_keys, max_probe, stats, w);
             } else {
 #pragma unroll
-                for (int j = 0; j < ITEMS; ++j) cur[j] = on[j] ? ldcg_u64(&sub[slot[j]].skey) : 0ull;
+                for (int j = 0; j < ITEMS; ++j) cur[j] = on[j] ? ldcg_u64(sub.key(slot[j])) : 0ull;
                 count_insert_batch<ITEMS>(sub, S, slot, skey, cur, on, new_keys, max_probe, stats, w);
             }
         }
@@ -576,7 +587,7 @@ k_count_part(const uint64_t* __restrict__ keys, const long long* __restrict__ se
 // merge (kmer, count) pairs received from other ranks into the owner's table (multi-GPU)
 __global__ void __launch_bounds__(256)
 k_merge(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, int64_t n,
-        CountSlot* __restrict__ table, uint64_t capacity, CountStats* __restrict__ stats)
+        CountTable table, uint64_t capacity, CountStats* __restrict__ stats)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -586,16 +597,16 @@ k_merge(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, 
     uint64_t slot = slot_of(mix64(key), capacity);
     unsigned int probes = 0;
     for (;;) {
-        unsigned long long cur = ldcg_u64(&table[slot].skey);
+        unsigned long long cur = ldcg_u64(table.key(slot));
         if (cur == 0ull) {
-            cur = atomicCAS(&table[slot].skey, 0ull, skey);
+            cur = atomicCAS(table.key(slot), 0ull, skey);
             if (cur == 0ull) {                                // claimed: the slot already stands for one occurrence
                 atomicAdd(&stats->distinct, 1ull);
-                if (add > 1u) atomicAdd(&table[slot].count, add - 1u);
+                if (add > 1u) atomicAdd(table.cnt(slot), add - 1u);
                 break;
             }
         }
-        if (cur == skey) { atomicAdd(&table[slot].count, add); break; }
+        if (cur == skey) { atomicAdd(table.cnt(slot), add); break; }
         if (++probes > PC_PROBE_LIMIT || probes >= capacity) { atomicAdd(&stats->overflow, 1ull); break; }
         if (++slot == capacity) slot = 0;
     }
@@ -603,63 +614,74 @@ k_merge(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, 
 
 // ------------------------------------------------------------------------------------------------ K4 select
 // Streaming scan of the table; survivors appended with one atomic per warp.  out_keys may be null (count only).
+// Only the 4-byte counts are streamed; the key of a slot is read when its count passes the thresholds (an empty slot
+// has count field 0 = "one occurrence", so for low >= 2 no key of an empty slot is ever touched).
 __global__ void __launch_bounds__(256)
-k_select(const CountSlot* __restrict__ table, uint64_t capacity, unsigned int low, unsigned int high,
+k_select(CountTable table, uint64_t capacity, unsigned int low, unsigned int high,
          uint64_t* __restrict__ out_keys, uint32_t* __restrict__ out_counts, unsigned long long out_cap,
          unsigned long long* __restrict__ n_out)
 {
-    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    uint64_t cap_round = (capacity + 31) & ~31ull;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap_round; i += stride) {
-        bool keep = false; unsigned long long skey = 0; unsigned int cnt = 0;
-        if (i < capacity) {
-            uint4 s = ldnc_u4(table + i);
-            skey = ((unsigned long long)s.y << 32) | s.x; cnt = s.z + 1u;          // stored = occurrences - 1
-            keep = skey != 0ull && cnt >= low && cnt <= high;
+    // 4 slots per thread per iteration: one 128-bit streaming load of counts (the table arrays are 256-byte aligned)
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x * 4;
+    uint64_t cap_round = (capacity + 127) & ~127ull;
+    for (uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < cap_round; i += stride) {
+        unsigned int cnt[4] = {0u, 0u, 0u, 0u};
+        if (i + 3 < capacity) {
+            uint4 v = __ldcs(reinterpret_cast<const uint4*>(table.counts + i));
+            cnt[0] = v.x; cnt[1] = v.y; cnt[2] = v.z; cnt[3] = v.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) if (i + j < capacity) cnt[j] = __ldcs(table.counts + i + j);
         }
-        unsigned int bal = __ballot_sync(0xFFFFFFFFu, keep);
-        if (bal) {
-            int lane = threadIdx.x & 31;
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(n_out, (unsigned long long)__popc(bal));
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
-            if (keep && out_keys) {
-                unsigned long long pos = base + __popc(bal & ((1u << lane) - 1u));
-                if (pos < out_cap) {
-                    out_keys[pos] = ~skey;
-                    if (out_counts) out_counts[pos] = cnt;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            bool keep = false; unsigned long long skey = 0;
+            unsigned int c = cnt[j] + 1u;                                     // stored = occurrences - 1
+            if (i + j < capacity && c >= low && c <= high) {
+                skey = __ldcs(table.keys + i + j);
+                keep = skey != 0ull;
+            }
+            unsigned int bal = __ballot_sync(0xFFFFFFFFu, keep);
+            if (bal) {
+                int lane = threadIdx.x & 31;
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(n_out, (unsigned long long)__popc(bal));
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (keep && out_keys) {
+                    unsigned long long pos = base + __popc(bal & ((1u << lane) - 1u));
+                    if (pos < out_cap) {
+                        out_keys[pos] = ~skey;
+                        if (out_counts) out_counts[pos] = c;
+                    }
                 }
             }
         }
     }
 }
 
-// owner histogram + scatter for the multi-GPU exchange
+// owner histogram + scatter for the pre-aggregated multi-GPU exchange
 __global__ void __launch_bounds__(256)
-k_owner_hist(const CountSlot* __restrict__ table, uint64_t capacity, unsigned int world,
-             unsigned long long* __restrict__ hist /* world */)
+k_owner_hist(CountTable table, uint64_t capacity, unsigned int world, unsigned long long* __restrict__ hist /* world */)
 {
     __shared__ unsigned int sh[64];
     if (threadIdx.x < 64) sh[threadIdx.x] = 0;
     __syncthreads();
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < capacity; i += stride) {
-        uint4 s = ldnc_u4(table + i);
-        unsigned long long skey = ((unsigned long long)s.y << 32) | s.x;
+        unsigned long long skey = __ldcs(table.keys + i);
         if (skey != 0ull) atomicAdd(&sh[owner_of(~skey, world)], 1u);
     }
     __syncthreads();
     if (threadIdx.x < world && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)sh[threadIdx.x]);
 }
 __global__ void __launch_bounds__(256)
-k_owner_scatter(const CountSlot* __restrict__ table, uint64_t capacity, unsigned int world,
+k_owner_scatter(CountTable table, uint64_t capacity, unsigned int world,
                 unsigned long long* __restrict__ cursor /* world, pre-set to bucket starts */,
                 uint64_t* __restrict__ out_keys, uint32_t* __restrict__ out_counts)
 {
     uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < capacity; i += stride) {
-        uint4 s = ldnc_u4(table + i);
-        unsigned long long skey = ((unsigned long long)s.y << 32) | s.x;
+        unsigned long long skey = __ldcs(table.keys + i);
         if (skey != 0ull) {
             unsigned int o = owner_of(~skey, world);
             unsigned int peers = __match_any_sync(__activemask(), o);
@@ -669,7 +691,7 @@ k_owner_scatter(const CountSlot* __restrict__ table, uint64_t capacity, unsigned
             if (lane == leader) base = atomicAdd(&cursor[o], (unsigned long long)__popc(peers));
             base = __shfl_sync(peers, base, leader);
             unsigned long long pos = base + __popc(peers & ((1u << lane) - 1u));
-            out_keys[pos] = ~skey; out_counts[pos] = s.z + 1u;
+            out_keys[pos] = ~skey; out_counts[pos] = __ldcs(table.counts + i) + 1u;
         }
     }
 }
@@ -908,8 +930,8 @@ k_probe(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, 
                 slot[j] = slot_of(mix64(key), rcap);
                 if (b < 31) r.step(b);
             }
-            // occupancy bitmap (1 bit per slot, L1/L2 resident): ~3 of 4 windows end here without touching the table
-            {
+            // optional occupancy bitmap (1 bit per slot): ~3 of 4 windows end here without touching the table
+            if (occ != nullptr) {
                 unsigned int ob[BATCH];
 #pragma unroll
                 for (int j = 0; j < BATCH; ++j) ob[j] = ((vmask >> j) & 1u) ? __ldg(occ + (slot[j] >> 5)) : 0u;
@@ -1001,8 +1023,8 @@ k_probe_stream(const uint64_t* __restrict__ stream, int64_t n_words,
                 skey[j] = ~key;
                 slot[j] = slot_of(mix64(key), rcap);
             }
-            // occupancy bitmap (1 bit per slot, L1/L2 resident): ~3 of 4 windows end here without touching the table
-            {
+            // optional occupancy bitmap (1 bit per slot): ~3 of 4 windows end here without touching the table
+            if (occ != nullptr) {
                 unsigned int ob[BATCH];
 #pragma unroll
                 for (int j = 0; j < BATCH; ++j) ob[j] = ((vmask >> j) & 1u) ? __ldg(occ + (slot[j] >> 5)) : 0u;

@@ -74,7 +74,7 @@ def _all_gather_v(dist, local, torch):
     return torch.cat([o[:c] for o, c in zip(outs, counts)]), counts
 
 
-def plan_partition_bits(windows_global, world, part_bytes=64 << 20, table_load=0.6, slot_bytes=16):
+def plan_partition_bits(windows_global, world, part_bytes=64 << 20, table_load=0.6, slot_bytes=12):
     """Bucket bits shared by all ranks: enough buckets that one sub-table (the unit that must stay L2 resident while it
     is being counted) is about part_bytes, and at least one bucket per rank."""
     cap_bytes = windows_global / table_load * slot_bytes
@@ -158,7 +158,7 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
     seg_begin = (recv_off[:, None] + within).T.copy()                     # [my bucket, sender]
     seg_len = mine.T.copy()
     if hasattr(ctx, "watch_threshold"):
-        ctx.watch_threshold(0 if high_bool else effective_low_count(k, kmer_low_count))  # K4 fused into K3
+        ctx.watch_threshold(0)
     ctx.count_buckets(k, pb, recv, seg_begin, seg_len)
     owner_info = ctx.count_info()
     info = dict(owner_info, valid_windows=n_local)

@@ -129,8 +129,10 @@ def effective_low_count(k, kmer_low_count):
 
 def run_hot_path(ctx, seq, seq_offsets, names, chunk_size=75000, k=23, kmer_low_count=100, high_bool=0,
                  kmer_high_count=2000000, sampling_sensitivity=1, remove_non_chunk=1, min_chunk_threshold=0,
-                 min_chunk_size=0, prefilter=0, tfidf=True, table_capacity=0, fetch=True, layout=None, arena=None):
-    """One pass of the hot path on one GPU.
+                 min_chunk_size=0, prefilter=0, tfidf=True, table_capacity=0, fetch=True, layout=None, arena=None,
+                 fuse_select=False):
+    """One pass of the hot path on one GPU.  fuse_select: record threshold crossings during the count instead of
+    re-scanning the table (pc_watch_threshold); measured slower on B200 (returning atomics cost more than the scan).
 
     seq: newline-free ASCII bases, numpy uint8 (pageable or pinned) or a torch uint8 tensor (CPU pinned or CUDA).
     Returns a HotPathResult; with fetch=False the CSR stays on the device and only sizes are returned.
@@ -139,7 +141,7 @@ def run_hot_path(ctx, seq, seq_offsets, names, chunk_size=75000, k=23, kmer_low_
         layout = ChunkLayout(names, seq_offsets, chunk_size)
     scaffolds, chunk_row = layout.rows(remove_non_chunk, min_chunk_threshold, min_chunk_size, prefilter)
     ctx.load_sequences(seq, layout.chunk_begin_abs, layout.chunk_end_abs)
-    ctx.watch_threshold(0 if high_bool else effective_low_count(k, kmer_low_count))      # K4 fused into K3
+    ctx.watch_threshold(effective_low_count(k, kmer_low_count) if (fuse_select and not high_bool) else 0)
     ctx.count(k, table_capacity)
     n_sel = ctx.select(effective_low_count(k, kmer_low_count), kmer_high_count, bool(high_bool),
                        sampling_sensitivity)
