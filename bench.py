@@ -39,7 +39,7 @@ NCU_TRAFFIC = {}
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--genome-size", type=int, default=0, help="override bases per GPU (testing only)")
@@ -58,18 +58,22 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  The process is started
+    long before the timed region (its start-up -- NVML initialisation on a fresh box -- contends with CUDA calls of this
+    process and would otherwise land inside the first timed steps); lines are time-stamped on arrival and only those
+    inside [mark_begin, mark_end] are reported."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
         self.proc, self.lines, self.gpu = None, [], gpu_index
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -77,15 +81,27 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def wait_ready(self, timeout=20.0):
+        t = time.perf_counter()
+        while self.proc and not self.lines and time.perf_counter() - t < timeout:
+            time.sleep(0.05)
+
+    def mark_begin(self):
+        self.t0 = time.perf_counter()
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        inside = [ln for ts, ln in self.lines if self.t0 is None or (self.t0 - 0.06 <= ts <= (self.t1 or ts) + 0.12)]
+        for ln in inside or [ln for _, ln in self.lines[-3:]]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -96,9 +112,8 @@ class ClockSampler:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        busy = [s for s in sm if s > 0.5 * max(mx + [1])] or sm
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "samples_in_timed_region": len(inside), "reasons": sorted(reasons)}
 
 
 def workload_params(n_gpus, genome_size_override):
@@ -199,6 +214,9 @@ def run_b200_arm(args):
     genome_bases = int(offs_all[-1])
     layout = ChunkLayout(names_all, offs_all, chunk)
 
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                                    # long before the timed region, see ClockSampler
     ctx = binding.Context(local_rank)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
 
@@ -262,12 +280,13 @@ def run_b200_arm(args):
     # ---- device-resident throughput (`value`) ------------------------------------------------------------------
     timed(args.warmup, True, False)
     ctx.reset_counters()
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.wait_ready()
+        sampler.mark_begin()
     per_step_timings = []
     ms_total, last_resident = timed(args.steps, True, False, per_step_timings)
-    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        sampler.mark_end()
     launches = ctx.launch_count()
     ms_per_step = ms_total / args.steps
     value = genome_bases / (ms_per_step * 1e-3) / 1e9
@@ -291,6 +310,7 @@ def run_b200_arm(args):
         if dist is not None:
             dist.barrier(); dist.destroy_process_group()
         return 0
+    clocks = sampler.stop()
 
     # ---- roofline of the dominant kernel, from the CUDA-event time of its launches ------------------------------
     # ALGORITHMIC bytes (DESIGN.md "Roofline model"), per rank: G packed bases, T valid windows,

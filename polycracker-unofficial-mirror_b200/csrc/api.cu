@@ -172,6 +172,7 @@ int radix_sort_u64(pc_ctx* c, uint64_t* a, uint64_t* b, int64_t n, int bits, uin
 int build_rep_table(pc_ctx* c) {
     StageTimer t(c, ST_REPTABLE);
     c->rcap = std::max<uint64_t>(64, (uint64_t)c->n_sel * (uint64_t)std::max(2, c->rep_load_inv));
+    if (c->rcap >= (1ull << 32)) return fail(PC_EINVAL, "repeat set of %lld k-mers is too large for the repeat table", (long long)c->n_sel);
     int rc = c->rtable.alloc(c->rcap);
     if (rc) return rc;
     rc = c->rocc.alloc((c->rcap + 31) / 32 + 1);
@@ -560,6 +561,13 @@ int pc_tune(pc_ctx* c, const char* key, int64_t value) {
     else if (k == "part_mode") c->part_mode = (int)value;
     else if (k == "count_items") c->count_items = (int)value;
     else if (k == "probe_mode") c->probe_mode = (int)value;
+    else if (k == "hash_mode") {
+        int m = (int)value;
+        if (m < 0 || m > 1) return fail(PC_EINVAL, "hash_mode must be 0 or 1");
+        CU(cudaMemcpyToSymbol(pc::g_hash_mode, &m, sizeof m));
+        c->counted = c->selected = c->built = false;          // tables built with the other hash are unusable
+        c->stream_valid = false;
+    }
     else if (k == "prezero") c->prezero = (int)value;
     else if (k == "probe_bitmap") c->probe_bitmap = (int)value;
     else if (k == "part_casfirst") c->part_casfirst = (int)value;
@@ -668,7 +676,7 @@ int pc_count_info(pc_ctx* c, int64_t info[8]) {
 static int select_into(pc_ctx* c, uint32_t low, uint32_t high, uint64_t* keys_dev, uint32_t* counts_dev, int64_t cap,
                        int64_t* n_out) {
     CU(cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned long long), c->stream));
-    unsigned int grid = (unsigned int)std::min<uint64_t>((c->capacity + 255) / 256, 148ull * 16);
+    unsigned int grid = (unsigned int)std::min<uint64_t>((c->capacity + 1023) / 1024, 148ull * 64);
     LAUNCH(c, pc::k_select, grid, 256, c->table(), c->capacity, low, high, keys_dev, counts_dev,
            (unsigned long long)cap, c->d_counter.p);
     unsigned long long n = 0;
@@ -842,14 +850,31 @@ int pc_set_selected(pc_ctx* c, const uint64_t* keys, int64_t n, int k, int loc, 
 static int rows_to_csr(pc_ctx* c, int64_t n_rows) {
     int rc;
     int bits = 1; while (((int64_t)1 << bits) < c->n_sel) ++bits;
-    int n_passes = std::max(1, (bits + 7) / 8);
+    // digit width: fewest passes, then the narrowest digit (smem = 17 * 2^DB * 4 bytes)
+    int db = 8;
+    {
+        int best = (bits + 7) / 8;
+        if ((bits + 9) / 10 < best) { db = 10; best = (bits + 9) / 10; }
+        if ((bits + 10) / 11 < best) { db = 11; best = (bits + 10) / 11; }
+    }
+    int n_passes = std::max(1, (bits + db - 1) / db);
     int32_t* sorted = (n_passes & 1) ? c->hits_b.p : c->hits_a.p;
     c->nnz = 0;
     if (n_rows > 0) {
         {
             StageTimer t(c, ST_ROWSORT);
-            LAUNCH(c, (pc::k_row_sort<16>), (unsigned int)n_rows, 512, c->hits_a.p, c->hits_b.p, c->d_row_base.p,
-                   c->d_row_cursor.p, n_passes, c->d_row_nnz.p);
+            size_t smem = (size_t)17 * ((size_t)1 << db) * sizeof(unsigned int);
+            c->launches++;
+            if (db == 8) {
+                pc::k_row_sort<16, 8><<<(unsigned int)n_rows, 512, smem, c->stream>>>(c->hits_a.p, c->hits_b.p, c->d_row_base.p, c->d_row_cursor.p, n_passes, c->d_row_nnz.p);
+            } else if (db == 10) {
+                CU(cudaFuncSetAttribute(pc::k_row_sort<16, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                pc::k_row_sort<16, 10><<<(unsigned int)n_rows, 512, smem, c->stream>>>(c->hits_a.p, c->hits_b.p, c->d_row_base.p, c->d_row_cursor.p, n_passes, c->d_row_nnz.p);
+            } else {
+                CU(cudaFuncSetAttribute(pc::k_row_sort<16, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                pc::k_row_sort<16, 11><<<(unsigned int)n_rows, 512, smem, c->stream>>>(c->hits_a.p, c->hits_b.p, c->d_row_base.p, c->d_row_cursor.p, n_passes, c->d_row_nnz.p);
+            }
+            CU(cudaGetLastError());
             LAUNCH(c, pc::k_indptr, 1, 1024, c->d_row_nnz.p, n_rows, c->d_indptr.p);
         }
         int64_t total = 0;

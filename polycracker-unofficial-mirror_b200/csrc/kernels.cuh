@@ -7,6 +7,27 @@
 
 namespace pc {
 
+// Hash of a k-mer for bucket / slot selection.  g_hash_mode (set by the host, tunable "hash_mode"):
+//   0  murmur3 finaliser (two 64-bit multiplies, three xor-shifts: ~30 integer instructions)
+//   1  one 64-bit Fibonacci multiply + xor-fold (~8 instructions); the top bits choose the bucket, the following
+//      bits the slot.  Any mode gives the same counts; only probe lengths and bucket balance can differ.
+__constant__ int g_hash_mode = 0;
+__device__ __forceinline__ uint64_t hash64(uint64_t key) {
+    if (g_hash_mode == 1) {
+        uint64_t h = key * 0x9E3779B97F4A7C15ull;
+        return h ^ (h >> 29);
+    }
+    return mix64(key);
+}
+// repeat-table slot (K5): rcap < 2^32, so one 32x32->64 multiply maps the high hash word onto [0, rcap)
+__device__ __forceinline__ uint64_t rep_slot(uint64_t key, uint64_t rcap) {
+    if (g_hash_mode == 1) {
+        uint64_t h = key * 0x9E3779B97F4A7C15ull;
+        return ((h >> 32) * rcap) >> 32;
+    }
+    return __umul64hi(mix64(key), rcap);
+}
+
 // ------------------------------------------------------------------------------------------------ tables
 // Count table (K3): open addressing, linear probing, structure of arrays.  keys[s] = ~kmer so that a zeroed table is
 // empty (the all-ones pattern is never a canonical-min k-mer: its reverse complement, all A, is smaller);
@@ -95,30 +116,106 @@ __device__ __forceinline__ void realign8(const uint32_t (&r)[12], int bs, uint32
     for (int i = 0; i < 8; ++i) o[i] = __funnelshift_r(r[WS + i], r[WS + i + 1], bs);
 }
 
+// TMA (1-D bulk copy) helpers: one elected thread arms an mbarrier with the byte count and issues
+// cp.async.bulk global -> shared; everybody waits on the barrier phase.  SASS: UBLKCP / SYNCS.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, unsigned int bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t}"
+        :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// One CTA = 256 words = 8 KiB of ASCII.  When the CTA's words lie in one chunk (the normal case: chunks are tens of
+// kilobases) its ASCII range is staged in shared memory with ONE bulk copy (TMA engine, fully coalesced 16-byte
+// aligned HBM reads, no LSU instructions) and every thread converts its 32 bases out of shared memory; CTAs that
+// straddle a chunk boundary or touch the end of a caller-owned buffer use per-thread 128-bit global loads.
+#define PC_PACK_TILE_BYTES 8192
 __global__ void __launch_bounds__(256)
 k_pack(const uint8_t* __restrict__ ascii, int64_t ascii_bytes_padded,
        const int64_t* __restrict__ chunk_word0, const int64_t* __restrict__ chunk_begin,
        const int64_t* __restrict__ chunk_len, int64_t n_chunks, int64_t n_words_total,
        uint64_t* __restrict__ words, uint32_t* __restrict__ nmask)
 {
-    int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ __align__(128) uint8_t stage[PC_PACK_TILE_BYTES + 64];
+    __shared__ __align__(8) unsigned long long bar;
+    __shared__ long long s_c0, s_a0;
+    __shared__ int s_bulk;
+    const int64_t data_words = __ldg(chunk_word0 + n_chunks);
+    const int64_t w_first = (int64_t)blockIdx.x * blockDim.x;
+    if (threadIdx.x == 0) {
+        int bulk = 0; long long c0 = 0, a0 = 0;
+        if (n_chunks > 0 && w_first < data_words) {
+            c0 = find_le(chunk_word0, n_chunks, w_first);
+            int64_t w_last = min(w_first + (int64_t)blockDim.x, data_words) - 1;
+            int64_t off = (w_first - __ldg(chunk_word0 + c0)) * 32;
+            int64_t avail = __ldg(chunk_len + c0) - off;                     // bases of the chunk from this CTA on
+            if (w_last < __ldg(chunk_word0 + c0 + 1) && avail > 0) {
+                int64_t src = __ldg(chunk_begin + c0) + off;
+                int sh = (int)((reinterpret_cast<uintptr_t>(ascii) + (uintptr_t)src) & 15);
+                a0 = src - sh;
+                int64_t need = min((int64_t)PC_PACK_TILE_BYTES, avail);
+                int64_t size = (sh + need + 15) & ~(int64_t)15;               // <= 8192 + 16
+                // the per-thread realignment reads up to 48 bytes from its 16-byte aligned start: keep that inside
+                // the staged range by copying 48 more bytes when the buffer allows it
+                size = min(size + 48, (int64_t)(PC_PACK_TILE_BYTES + 64));
+                if (a0 >= 0 && a0 + size <= ascii_bytes_padded) {
+                    bulk = 1;
+                    mbar_init(&bar, 1);
+                    mbar_expect_tx(&bar, (unsigned int)size);
+                    bulk_g2s(stage, ascii + a0, (unsigned int)size, &bar);
+                }
+            }
+        }
+        s_bulk = bulk; s_c0 = c0; s_a0 = a0;
+    }
+    __syncthreads();
+    const bool bulk = s_bulk != 0;
+    if (bulk) mbar_wait(&bar, 0);
+    int64_t w = w_first + threadIdx.x;
     if (w >= n_words_total) return;
-    int64_t data_words = __ldg(chunk_word0 + n_chunks);
     if (w >= data_words) {             // trailing guard word(s): all padding
         words[w] = 0ull; nmask[w] = 0xFFFFFFFFu; return;
     }
-    int64_t c = find_le(chunk_word0, n_chunks, w);
+    int64_t c = s_c0;                  // chunk of the CTA's first word; walk forward (rarely more than one step)
+    while (c + 1 < n_chunks && __ldg(chunk_word0 + c + 1) <= w) ++c;
     int64_t off = (w - __ldg(chunk_word0 + c)) * 32;
     int64_t remaining = __ldg(chunk_len + c) - off;         // may be <= 0: pure padding word
     uint64_t word = 0ull; uint32_t nm = 0xFFFFFFFFu;
     if (remaining > 0) {
         int64_t src = __ldg(chunk_begin + c) + off;          // byte offset into ascii
         int sh = (int)((reinterpret_cast<uintptr_t>(ascii) + (uintptr_t)src) & 15);
-        int64_t a0 = src - sh;                                // 16-byte aligned (ascii itself is 256-aligned)
+        int64_t a0 = src - sh;                                // 16-byte aligned
         uint32_t o[8];
-        if (a0 >= 0 && a0 + 48 <= ascii_bytes_padded) {
+        bool have = false;
+        uint4 q0, q1, q2;
+        if (bulk) {
+            const uint8_t* p = stage + (a0 - s_a0);           // 16-byte aligned inside the staged range
+            q0 = *reinterpret_cast<const uint4*>(p);
+            q1 = *reinterpret_cast<const uint4*>(p + 16);
+            q2 = *reinterpret_cast<const uint4*>(p + 32);
+            have = true;
+        } else if (a0 >= 0 && a0 + 48 <= ascii_bytes_padded) {
             const uint8_t* p = ascii + a0;
-            uint4 q0 = ldnc_u4(p), q1 = ldnc_u4(p + 16), q2 = ldnc_u4(p + 32);
+            q0 = ldnc_u4(p); q1 = ldnc_u4(p + 16); q2 = ldnc_u4(p + 32);
+            have = true;
+        }
+        if (have) {
             uint32_t r[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
             int bs = (sh & 3) * 8;
             switch (sh >> 2) {
@@ -300,7 +397,7 @@ k_count(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, 
         if (MODE == 1) {
 #pragma unroll
             for (int j = 0; j < BATCH; ++j) {
-                if (lead.valid(j)) prefetch_l2(table.key(slot_of(mix64(lead.canonical()), capacity)));
+                if (lead.valid(j)) prefetch_l2(table.key(slot_of(hash64(lead.canonical()), capacity)));
                 lead.step(j);
             }
         }
@@ -310,7 +407,7 @@ k_count(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, 
 #pragma unroll
                 for (int j = 0; j < BATCH; ++j) {
                     int b = b0 + BATCH + j;
-                    if (lead.valid(b)) prefetch_l2(table.key(slot_of(mix64(lead.canonical()), capacity)));
+                    if (lead.valid(b)) prefetch_l2(table.key(slot_of(hash64(lead.canonical()), capacity)));
                     if (b < 31) lead.step(b);
                 }
             }
@@ -323,7 +420,7 @@ k_count(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, 
                 bool v = r.valid(b);
                 vmask |= (unsigned int)v << j;
                 skey[j] = ~key;
-                slot[j] = slot_of(mix64(key), capacity);
+                slot[j] = slot_of(hash64(key), capacity);
                 if (b < 31) r.step(b);
             }
 #pragma unroll
@@ -397,7 +494,7 @@ k_extract(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask
             bool v = r.valid(b);
             uint64_t key = r.canonical();
             __stcs(out + b * 32, v ? key : PC_KEY_SENTINEL);
-            if (v) { atomicAdd(&shh[part_of(mix64(key), pb)], 1u); ++nvalid; }
+            if (v) { atomicAdd(&shh[part_of(hash64(key), pb)], 1u); ++nvalid; }
             if (b < 31) r.step(b);
         }
     } else {
@@ -475,7 +572,7 @@ k_tile_scatter(const uint64_t* __restrict__ stream, int64_t n_stream, int pb,
         unsigned short q[PER];
 #pragma unroll
         for (int j = 0; j < PER; ++j) {
-            q[j] = (unsigned short)part_of(mix64(key[j]), pb);
+            q[j] = (unsigned short)part_of(hash64(key[j]), pb);
             if (key[j] != PC_KEY_SENTINEL) atomicAdd(&cnt[q[j]], 1u);
         }
         __syncthreads();
@@ -556,7 +653,7 @@ k_count_part(const uint64_t* __restrict__ keys, const long long* __restrict__ se
                 uint64_t key = nkey[j];
                 on[j] = key != PC_KEY_SENTINEL;
                 skey[j] = ~key;
-                slot[j] = slot_in_part(mix64(key), pb, S);
+                slot[j] = slot_in_part(hash64(key), pb, S);
             }
 #pragma unroll
             for (int j = 0; j < ITEMS; ++j) nkey[j] = (i0 + stride + j < end) ? __ldcs(kbuf + i0 + stride + j) : PC_KEY_SENTINEL;
@@ -594,7 +691,7 @@ k_merge(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, 
     uint64_t key = keys[i];
     unsigned int add = counts[i];
     unsigned long long skey = ~key;
-    uint64_t slot = slot_of(mix64(key), capacity);
+    uint64_t slot = slot_of(hash64(key), capacity);
     unsigned int probes = 0;
     for (;;) {
         unsigned long long cur = ldcg_u64(table.key(slot));
@@ -870,7 +967,7 @@ k_rep_build(const uint64_t* __restrict__ sorted_keys, int64_t n, RepSlot* __rest
     if (i >= n) return;
     uint64_t key = sorted_keys[i];
     unsigned long long skey = ~key;
-    uint64_t slot = slot_of(mix64(key), capacity);
+    uint64_t slot = rep_slot(key, capacity);
     for (;;) {                                               // keys are unique and capacity >= 2n: terminates
         unsigned long long cur = atomicCAS(&table[slot].skey, 0ull, skey);
         if (cur == 0ull) { table[slot].col = (int)i; atomicOr(&occ[slot >> 5], 1u << (slot & 31)); break; }
@@ -927,7 +1024,7 @@ k_probe(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, 
                 uint64_t key = r.canonical();
                 vmask |= (unsigned int)r.valid(b) << j;
                 skey[j] = ~key;
-                slot[j] = slot_of(mix64(key), rcap);
+                slot[j] = rep_slot(key, rcap);
                 if (b < 31) r.step(b);
             }
             // optional occupancy bitmap (1 bit per slot): ~3 of 4 windows end here without touching the table
@@ -1021,7 +1118,7 @@ k_probe_stream(const uint64_t* __restrict__ stream, int64_t n_words,
                 uint64_t key = __ldcs(src + (b0 + j) * 32);
                 vmask |= (unsigned int)(key != PC_KEY_SENTINEL) << j;
                 skey[j] = ~key;
-                slot[j] = slot_of(mix64(key), rcap);
+                slot[j] = rep_slot(key, rcap);
             }
             // optional occupancy bitmap (1 bit per slot): ~3 of 4 windows end here without touching the table
             if (occ != nullptr) {
@@ -1081,14 +1178,18 @@ k_probe_stream(const uint64_t* __restrict__ stream, int64_t n_words,
 // One CTA per matrix row.  The row's hits (column ids, unordered, with multiplicity) are sorted with the same
 // stable LSD scheme, CTA-local: warp wq owns a contiguous slice, hist[wq][256] lives in shared memory, data
 // ping-pongs between the row's slices of two global buffers (L2 resident: a 75 kb chunk is <= 300 KB).
-template <int WARPS>
+template <int WARPS, int DB>
 __global__ void __launch_bounds__(WARPS * 32)
 k_row_sort(int32_t* buf_a, int32_t* buf_b, const int64_t* __restrict__ row_hit_base,
            const unsigned int* __restrict__ row_cursor, int n_passes, int64_t* __restrict__ row_nnz)
 {
-    __shared__ unsigned int h[WARPS][256];
-    __shared__ unsigned int tot[256];
+    // DB digit bits per pass (8, 10 or 11): 20-bit column ids sort in two passes of 10 bits instead of three of 8
+    constexpr int BINS = 1 << DB;
+    extern __shared__ unsigned int rs_smem[];
+    unsigned int (*h)[BINS] = reinterpret_cast<unsigned int (*)[BINS]>(rs_smem);   // [WARPS][BINS]
+    unsigned int* tot = rs_smem + WARPS * BINS;                                    // [BINS]
     __shared__ unsigned int red[WARPS];
+    __shared__ unsigned int carry_s[BINS / 32 + 1];
     int row = blockIdx.x;
     int t = threadIdx.x, wid = t >> 5, lane = t & 31;
     unsigned int n = row_cursor[row];
@@ -1098,34 +1199,47 @@ k_row_sort(int32_t* buf_a, int32_t* buf_b, const int64_t* __restrict__ row_hit_b
     unsigned int ipw = ((n + WARPS - 1) / WARPS + 31u) & ~31u;
     unsigned int beg = min(n, wid * ipw), end = min(n, beg + ipw);
     for (int pass = 0; pass < n_passes; ++pass) {
-        int shift = 8 * pass;
-        for (int i = t; i < WARPS * 256; i += WARPS * 32) (&h[0][0])[i] = 0;
+        int shift = DB * pass;
+        for (int i = t; i < WARPS * BINS; i += WARPS * 32) rs_smem[i] = 0;
         __syncthreads();
         for (unsigned int i = beg + lane; i < end; i += 32)
-            atomicAdd(&h[wid][((unsigned int)src[i] >> shift) & 0xFFu], 1u);
+            atomicAdd(&h[wid][((unsigned int)src[i] >> shift) & (BINS - 1)], 1u);
         __syncthreads();
-        if (t < 256) {                                        // per digit: exclusive scan over warps
+        for (int d = t; d < BINS; d += WARPS * 32) {          // per digit: exclusive scan over warps
             unsigned int s = 0;
 #pragma unroll
-            for (int q = 0; q < WARPS; ++q) { unsigned int v = h[q][t]; h[q][t] = s; s += v; }
-            tot[t] = s;
+            for (int q = 0; q < WARPS; ++q) { unsigned int v = h[q][d]; h[q][d] = s; s += v; }
+            tot[d] = s;
         }
         __syncthreads();
-        if (wid == 0) {                                       // exclusive scan of the 256 digit totals
-            unsigned int carry = 0;
-            for (int d0 = 0; d0 < 256; d0 += 32) {
-                unsigned int v = tot[d0 + lane], incl = v;
+        // exclusive scan of the BINS digit totals: each warp scans 32-wide groups, then the group sums are chained
+        for (int g = wid; g < BINS / 32; g += WARPS) {
+            unsigned int v = tot[g * 32 + lane], incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned int u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            tot[g * 32 + lane] = incl - v;
+            if (lane == 31) carry_s[g] = incl;
+        }
+        __syncthreads();
+        if (wid == 0) {
+            unsigned int run = 0;
+            for (int g0 = 0; g0 < BINS / 32; g0 += 32) {
+                int g = g0 + lane;
+                unsigned int v = (g < BINS / 32) ? carry_s[g] : 0u, incl = v;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
                     unsigned int u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
                     if (lane >= o) incl += u;
                 }
-                tot[d0 + lane] = carry + incl - v;
-                carry += __shfl_sync(0xFFFFFFFFu, incl, 31);
+                if (g < BINS / 32) carry_s[g] = run + incl - v;
+                run += __shfl_sync(0xFFFFFFFFu, incl, 31);
             }
         }
         __syncthreads();
-        for (int d = lane; d < 256; d += 32) h[wid][d] += tot[d];
+        for (int d = lane; d < BINS; d += 32) h[wid][d] += tot[d] + carry_s[d >> 5];
         __syncwarp();
         for (unsigned int i0 = beg; i0 < end; i0 += 32) {
             unsigned int i = i0 + lane;
@@ -1133,7 +1247,7 @@ k_row_sort(int32_t* buf_a, int32_t* buf_b, const int64_t* __restrict__ row_hit_b
             unsigned int amask = __ballot_sync(0xFFFFFFFFu, act);
             if (act) {
                 int32_t key = src[i];
-                unsigned int d = ((unsigned int)key >> shift) & 0xFFu;
+                unsigned int d = ((unsigned int)key >> shift) & (BINS - 1);
                 unsigned int peers = __match_any_sync(amask, d);
                 unsigned int rank = __popc(peers & ((1u << lane) - 1u));
                 unsigned int ob = h[wid][d];

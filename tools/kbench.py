@@ -69,6 +69,8 @@ def main():
         for v in variants:
             if v:
                 ctx.tune(**{k_: int(x) for k_, x in v.items()})
+                if "hash_mode" in v:
+                    ctx.count(a.k)
             best = None
             for _ in range(a.reps):
                 n_sel = ctx.select(30)
