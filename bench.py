@@ -33,7 +33,7 @@ WORKLOAD = "cfg2_500Mbp_allotetraploid"
 FALLBACK_HBM_GBS = 6650.0
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
 # capture of this workload (profiles/); None until a capture of the current kernel exists
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {"K3_count": 18.126e9}   # profiles/r01_ncu_full_all_kernels_final_details.csv: 11.932 GB read + 6.194 GB written
 
 
 def parse_args():

@@ -110,11 +110,11 @@ struct pc_ctx {
     // measured on B200 (profiles/r01_kbench_count.md): the bucket count is bound by L2 sector operations; CAS-first
     // inserts (one ATOM per new k-mer, no load) are slower than load-first; HyperLogLog-sized denser tables and
     // in-kernel zeroing of the next sub-table were slower too and have been removed again
-    int part_casfirst = 0;
+    int part_casfirst = 0, part_minb = 1;
     // threshold watch (pc_watch_threshold): k-mers that reach watch_low during a partitioned count
     uint32_t watch_low = 0; bool cross_valid = false; uint32_t cross_low = 0;
     DevBuf<uint64_t> cross_keys; DevBuf<unsigned long long> d_cross_n;
-    int count_items = 4;
+    int count_items = 2;                        // k-mers in flight per thread in the bucket kernel (2: 48 regs, best measured)
 };
 
 namespace {
@@ -532,12 +532,17 @@ static int do_count_buckets(pc_ctx* c, int k, int pb, int n_buckets, const uint6
             B = 64; while (B < 4096 && (double)B * 1.41 < want) B <<= 1;
         }
         unsigned int grid = (unsigned int)n_buckets * B;
-#define COUNT_PART(I, CF, W) LAUNCH(c, (pc::k_count_part<I, CF, W>), grid, 256, keys_dev, d_beg, d_len, n_seg, pb, S, B, c->table(), c->d_stats.p, w)
+#define COUNT_PART(I, CF, W, MB) LAUNCH(c, (pc::k_count_part<I, CF, W, MB>), grid, 256, keys_dev, d_beg, d_len, n_seg, pb, S, B, c->table(), c->d_stats.p, w)
         if (w.low) {
-            if (c->part_casfirst) COUNT_PART(4, true, true); else COUNT_PART(4, false, true);
-        } else if (c->part_casfirst) COUNT_PART(4, true, false);
-        else if (c->count_items == 2) COUNT_PART(2, false, false);
-        else COUNT_PART(4, false, false);
+            if (c->part_casfirst) COUNT_PART(4, true, true, 1); else COUNT_PART(4, false, true, 1);
+        } else if (c->part_casfirst) COUNT_PART(4, true, false, 1);
+        else if (c->count_items == 2) {
+            if (c->part_minb == 6) COUNT_PART(2, false, false, 6); else if (c->part_minb == 8) COUNT_PART(2, false, false, 8); else COUNT_PART(2, false, false, 1);
+        } else if (c->count_items == 1) {
+            if (c->part_minb == 8) COUNT_PART(1, false, false, 8); else COUNT_PART(1, false, false, 1);
+        } else {
+            if (c->part_minb == 5) COUNT_PART(4, false, false, 5); else if (c->part_minb == 6) COUNT_PART(4, false, false, 6); else COUNT_PART(4, false, false, 1);
+        }
 #undef COUNT_PART
     }
     rc = fetch_stats(c); if (rc) return rc;                   // synchronises: the host segment arrays may go away
@@ -571,6 +576,7 @@ int pc_tune(pc_ctx* c, const char* key, int64_t value) {
     else if (k == "prezero") c->prezero = (int)value;
     else if (k == "probe_bitmap") c->probe_bitmap = (int)value;
     else if (k == "part_casfirst") c->part_casfirst = (int)value;
+    else if (k == "part_minb") c->part_minb = (int)value;
     else if (k == "probe_batch") c->probe_batch = (int)value;
     else if (k == "rep_load_inv") c->rep_load_inv = (int)value;
     else if (k == "part_mbytes") c->part_bytes = std::max<int64_t>(1, value) << 20;

@@ -625,8 +625,8 @@ k_tile_scatter(const uint64_t* __restrict__ stream, int64_t n_stream, int pb,
 // pass C: count one bucket after the other.  blockIdx = local_bucket * B + b: blocks are dispatched in index order,
 // so at any time the resident blocks work on one or two adjacent buckets whose sub-tables (S slots) sit in L2.
 // A bucket's k-mers arrive as n_seg segments of `keys` (one per sending rank; a single segment on one GPU).
-template <int ITEMS, bool CASFIRST, bool WATCH>
-__global__ void __launch_bounds__(256)
+template <int ITEMS, bool CASFIRST, bool WATCH, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 k_count_part(const uint64_t* __restrict__ keys, const long long* __restrict__ seg_begin, const long long* __restrict__ seg_len,
              int n_seg, int pb, uint64_t S, unsigned int B, CountTable table, CountStats* __restrict__ stats,
              const Watch w_in)

@@ -144,7 +144,7 @@ def test_partitioned_count_equals_direct_and_oracle(ctx, k, mb):
         ctx.tune(part_mode=1, part_mbytes=mb)
         _check_against_c_oracle(ctx, seq, off, names, 20000, k, 5)
     finally:
-        ctx.tune(part_mode=-1, part_mbytes=64, part_casfirst=0, count_items=4)
+        ctx.tune(part_mode=-1, part_mbytes=64, part_casfirst=0, count_items=2)
 
 
 def test_small_table_reports_overflow_not_garbage(ctx):
