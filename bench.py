@@ -58,34 +58,75 @@ def hbm_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe).  The process is started
-    long before the timed region (its start-up -- NVML initialisation on a fresh box -- contends with CUDA calls of this
-    process and would otherwise land inside the first timed steps); lines are time-stamped on arrival and only those
-    inside [mark_begin, mark_end] are reported."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md recipe), sampled in-process through
+    NVML (nvidia_ml_py) every 100 ms.  An `nvidia-smi -lms` child was measured to stall this process's CUDA calls for
+    ~35 ms per query on these boxes (every other step of the timed loop took 70 ms instead of 36), so nvidia-smi is
+    only the fallback, at a 1 s period.  Samples are time-stamped; only those inside [mark_begin, mark_end] count."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
-        self.proc, self.lines, self.gpu = None, [], gpu_index
+        self.gpu = gpu_index
+        self.samples = []                 # (t, sm_mhz, max_mhz, set(reasons))
         self.t0 = self.t1 = None
+        self._stop = False
+        self.proc = None
+        self.how = None
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            names = {"hw_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(pynvml, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(pynvml, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self._stop:
+                    try:
+                        sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                        bits = get_reasons(h)
+                        self.samples.append((time.perf_counter(), float(sm), float(mx),
+                                             {n for n, b in names.items() if bits & b}))
+                    except Exception:
+                        pass
+                    time.sleep(0.1)
+            threading.Thread(target=loop, daemon=True).start()
+            self.how = "nvml"
+            return
+        except Exception:
+            pass
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "1000"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
+            self.how = "nvidia-smi"
         except Exception:
             self.proc = None
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append((time.perf_counter(), line.strip()))
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm, mx = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            rs = {n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9])
+                  if v.lower().startswith("active")}
+            self.samples.append((time.perf_counter(), sm, mx, rs))
 
     def wait_ready(self, timeout=20.0):
         t = time.perf_counter()
-        while self.proc and not self.lines and time.perf_counter() - t < timeout:
+        while self.how and not self.samples and time.perf_counter() - t < timeout:
             time.sleep(0.05)
 
     def mark_begin(self):
@@ -95,25 +136,40 @@ class ClockSampler:
         self.t1 = time.perf_counter()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.12)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        inside = [ln for ts, ln in self.lines if self.t0 is None or (self.t0 - 0.06 <= ts <= (self.t1 or ts) + 0.12)]
-        for ln in inside or [ln for _, ln in self.lines[-3:]]:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "samples_in_timed_region": len(inside), "reasons": sorted(reasons)}
+        self._stop = True
+        if self.proc:
+            self.proc.terminate()
+        if not self.how:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"]}
+        inside = [x for x in self.samples if self.t0 is None or (self.t0 - 0.11 <= x[0] <= (self.t1 or x[0]) + 0.11)]
+        use = inside or self.samples[-3:]
+        reasons = set()
+        for x in use:
+            reasons |= x[3]
+        return {"sm_mhz": float(np.median([x[1] for x in use])) if use else None,
+                "sm_max_mhz": max([x[2] for x in use]) if use else None, "samples": len(use),
+                "samples_in_timed_region": len(inside), "source": self.how, "reasons": sorted(reasons)}
+
+
+def wait_for_quiet_gpu(gpu_index, timeout=20.0):
+    """Timing hygiene: a process that has just exited (the test-suite, a previous bench) is still tearing its CUDA
+    context down for a second or two and its driver locks stall this process's launches and synchronisations.  Wait
+    until no other compute process is listed on the GPU (bounded)."""
+    me = str(os.getpid())
+    t0 = time.perf_counter()
+    waited = 0.0
+    while time.perf_counter() - t0 < timeout:
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(gpu_index), "--query-compute-apps=pid", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=10).stdout
+        except Exception:
+            break
+        others = [p.strip() for p in out.split("\n") if p.strip() and p.strip() != me]
+        if not others:
+            break
+        time.sleep(0.5)
+        waited = time.perf_counter() - t0
+    return waited
 
 
 def workload_params(n_gpus, genome_size_override):
@@ -214,6 +270,7 @@ def run_b200_arm(args):
     genome_bases = int(offs_all[-1])
     layout = ChunkLayout(names_all, offs_all, chunk)
 
+    quiet_wait = wait_for_quiet_gpu(local_rank)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()                                    # long before the timed region, see ClockSampler
@@ -259,15 +316,32 @@ def run_b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    step_wall = []
+    # Host hygiene: a generation-2 garbage collection walks every object torch and numpy created at import
+    # (30-100 ms on this image) and would land inside random steps of the timed loop.  Freeze what exists and keep the
+    # collector off while timing; the steps themselves allocate no cycles.
+    import gc
+    gc.collect()
+    gc.freeze()
+
     def timed(n_steps, resident, fetch, collect=None):
+        gc.disable()
+        try:
+            return _timed(n_steps, resident, fetch, collect)
+        finally:
+            gc.enable()
+
+    def _timed(n_steps, resident, fetch, collect=None):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         last = None
         for _ in range(n_steps):
+            t_s = time.perf_counter()
             last = step(resident, fetch)
             if collect is not None:
                 collect.append(ctx.timings())
+                step_wall.append((time.perf_counter() - t_s) * 1e3)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -368,7 +442,7 @@ def run_b200_arm(args):
                        "parallelism": "chunks sharded over %d rank(s); all-to-all of (kmer,count) by owner, "
                                       "all-gather of the repeat set, all-reduce of df" % world},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks,
+            "clocks": clocks, "step_wall_ms": [round(x, 2) for x in step_wall], "quiet_gpu_wait_s": round(quiet_wait, 2),
             "result": {"distinct_kmers_rank0": info["distinct"], "valid_windows_rank0": info["valid_windows"],
                        "table_capacity": info["capacity"], "load_factor": info["distinct"] / max(1, info["capacity"]),
                        "n_selected": (res.stats["n_selected"] if res is not None else None),
