@@ -447,7 +447,9 @@ def run_b200_arm(args):
                        "table_capacity": info["capacity"], "load_factor": info["distinct"] / max(1, info["capacity"]),
                        "n_selected": (res.stats["n_selected"] if res is not None else None),
                        "nnz_rank0": (res.stats["nnz"] if res is not None else None),
-                       "rows_rank0": (res.stats["n_rows"] if res is not None else None)}}
+                       "rows_rank0": (res.stats["n_rows"] if res is not None else None),
+                       "phase_ms_rank0": last_resident.stats.get("phase_ms"),
+                       "exchange_bytes_sent_rank0": last_resident.stats.get("exchange_bytes_sent")}}
     print(json.dumps(line))
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <time.h>
 #include <string.h>
 #include <math.h>
 #include <algorithm>
@@ -14,6 +16,11 @@
 #include "kernels.cuh"
 
 namespace {
+
+// PC_TRACE=1: host wall-clock trace points on stderr (development aid)
+static bool trace_on() { static int v = -1; if (v < 0) { const char* e = getenv("PC_TRACE"); v = (e && *e == '1') ? 1 : 0; } return v == 1; }
+static double now_ms() { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; }
+#define TRACE(label) do { if (trace_on()) fprintf(stderr, "[pc_trace] %-28s %.3f ms\n", label, now_ms()); } while (0)
 
 thread_local std::string g_err;
 
@@ -778,9 +785,12 @@ int pc_select(pc_ctx* c, uint32_t low, uint32_t high, int use_high, int64_t samp
         rc = c->sel_a.alloc(std::max<int64_t>(n, 1024)); if (rc) return rc;
         if (n) CU(cudaMemcpyAsync(c->sel_a.p, c->cross_keys.p, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
     } else {
+        TRACE("select: begin");
         StageTimer t(c, ST_SELECT);
         rc = c->sel_a.alloc(cap); if (rc) return rc;
+        TRACE("select: alloc done");
         rc = select_into(c, low, high, c->sel_a.p, nullptr, cap, &n); if (rc) return rc;
+        TRACE("select: scan done");
         if (n > cap) {                                         // rare: more survivors than the first guess
             cap = n;
             rc = c->sel_a.alloc(cap); if (rc) return rc;
@@ -800,7 +810,9 @@ int pc_select(pc_ctx* c, uint32_t low, uint32_t high, int use_high, int64_t samp
         }
         c->sel = sorted; c->n_sel = n;
     }
+    TRACE("select: sort queued");
     rc = build_rep_table(c); if (rc) return rc;
+    TRACE("select: rep table queued");
     c->selected = true;
     if (n_selected) *n_selected = n;
     return PC_OK;

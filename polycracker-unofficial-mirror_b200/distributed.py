@@ -115,11 +115,22 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
     pinned torch / CUDA torch) laid out by local_buffer_plan; `staged` short-circuits it with a prebuilt
     (buffer, ids, begins, ends).  Returns a HotPathResult for the local row block (stats carry the global sizes).
     """
+    import time
     import torch
     import torch.distributed as dist
     world, rank = dist.get_world_size(), dist.get_rank()
-    blocks = shard_chunks(layout, world)
+    phase, t_last = {}, [time.perf_counter()]
+
+    def mark(name):
+        """host wall time of a phase, device work included (every context call is host-synchronous; collectives are
+        followed by a stream sync)"""
+        _stream_sync(torch, device)
+        now = time.perf_counter()
+        phase[name] = phase.get(name, 0.0) + (now - t_last[0]) * 1e3
+        t_last[0] = now
+
     if staged is None:
+        blocks = shard_chunks(layout, world)
         ids, begins, ends, total = local_buffer_plan(layout, blocks[rank])
         buf = fetch_chunks(ids, begins, ends, total)
     else:
@@ -137,8 +148,10 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
     windows_global = int(np.maximum(0, (layout.chunk_end - layout.chunk_start) - k + 1).sum())
     pb = plan_partition_bits(windows_global, world)
     P = 1 << pb
+    mark("host_plan")
     ctx.load_sequences(buf, begins, ends)
     off, keys = ctx.partition(k, pb)
+    mark("pack+partition")
     n_local = int(off[-1])
     sizes = torch.from_numpy(np.diff(off).astype(np.int64)).to(device)
     gathered = [torch.empty(P, dtype=torch.int64, device=device) for _ in range(world)]
@@ -150,8 +163,9 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
     send = keys if torch.is_tensor(keys) else device_view(torch, keys, n_local, device)
     # 2. all-to-all of the raw k-mers over NVLink; count at the owner
     recv = torch.empty(int(sum(recv_counts)), dtype=torch.int64, device=device)
+    mark("bucket_sizes_allgather")
     dist.all_to_all_single(recv, send[:n_local], output_split_sizes=recv_counts, input_split_sizes=send_counts)
-    _stream_sync(torch, device)
+    mark("kmer_all_to_all")
     mine = sizes_all[:, q_lo[rank]:q_lo[rank + 1]]                        # [sender, my bucket]
     recv_off = np.concatenate([[0], np.cumsum(recv_counts)])[:-1]
     within = np.cumsum(mine, axis=1) - mine                               # offset of bucket q inside sender s's slice
@@ -162,34 +176,45 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
     ctx.count_buckets(k, pb, recv, seg_begin, seg_len)
     owner_info = ctx.count_info()
     info = dict(owner_info, valid_windows=n_local)
+    mark("count_buckets")
     del recv
+    mark("free_recv")
     n_owner_sel = ctx.select(effective_low_count(k, kmer_low_count), kmer_high_count, bool(high_bool), 1)
+    mark("select")
+    if hasattr(ctx, "timings"):
+        tm = ctx.timings()
+        phase.update({"select.k_select": tm.get("select", 0.0), "select.sort": tm.get("sort", 0.0),
+                      "select.rep_table": tm.get("rep_table", 0.0)})
     sel_local = torch.empty(max(n_owner_sel, 1), dtype=torch.int64, device=device)
     if n_owner_sel:
         ctx.selected_into(sel_local)
+    mark("selected_copy")
     # 3. all-gather the repeat set; every rank sorts it to the same column order
     sel_all, _ = _all_gather_v(dist, sel_local[:n_owner_sel], torch)
     if sampling_sensitivity > 1 and sel_all.numel():
         # sampling is defined on the globally sorted survivor list (pc_select semantics)
         sel_all = torch.sort(sel_all.view(torch.int64) ^ (-2**63))[0] ^ (-2**63)       # unsigned order
         sel_all = sel_all[::int(sampling_sensitivity)].contiguous()
-    _stream_sync(torch, device)
+    mark("selected_allgather")
     n_sel = ctx.set_selected(sel_all, k, n=sel_all.numel())
     # 4. local matrix, global idf
     nnz = ctx.build_matrix(local_chunk_row, n_local_rows)
     df_t = torch.zeros(max(n_sel, 1), dtype=torch.int32, device=device)
     if n_sel:
         ctx.df_into(df_t)
+    mark("matrix")
     dist.all_reduce(df_t, op=dist.ReduceOp.SUM)
-    _stream_sync(torch, device)
+    mark("df_allreduce")
     if tfidf:
         ctx.tfidf(len(scaffolds_all), df_t if n_sel else None)
+    mark("tfidf")
     t = torch.tensor([n_local, owner_info["distinct"], nnz], dtype=torch.int64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     stats = dict(info)
     stats.update(n_selected=n_sel, nnz=nnz, n_rows=n_local_rows, n_rows_global=len(scaffolds_all), row0=row0,
                  valid_windows_global=int(t[0]), distinct_global=int(t[1]), nnz_global=int(t[2]),
-                 owner_distinct=owner_info["distinct"], local_bases=int(ends[-1]) if len(ends) else 0)
+                 owner_distinct=owner_info["distinct"], local_bases=int(ends[-1]) if len(ends) else 0,
+                 phase_ms={k_: round(v, 2) for k_, v in phase.items()}, exchange_bytes_sent=8 * (n_local - send_counts[rank]))
     scaffolds = scaffolds_all[row0:row0 + n_local_rows]
     if not fetch:
         return HotPathResult(layout, k, scaffolds, np.empty(0, np.uint64), None, None, None, None, None, stats,
