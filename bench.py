@@ -307,7 +307,8 @@ def run_b200_arm(args):
             return run_hot_path(ctx, src, offs_all, names_all, chunk_size=chunk, k=k, kmer_low_count=low,
                                 fetch=fetch, layout=layout, arena=arena)
         return pcd.run_hot_path_distributed(ctx, layout, None, device, chunk_size=chunk, k=k, kmer_low_count=low,
-                                            fetch=fetch, staged=(src, ids, begins, ends), arena=arena)
+                                            fetch=fetch, staged=(src, ids, begins, ends), arena=arena,
+                                            exchange=os.environ.get("PC_EXCHANGE", "auto"))
 
     layout.rows()                                          # host-side row order: cached, reused by every step
 
@@ -449,7 +450,8 @@ def run_b200_arm(args):
                        "nnz_rank0": (res.stats["nnz"] if res is not None else None),
                        "rows_rank0": (res.stats["n_rows"] if res is not None else None),
                        "phase_ms_rank0": last_resident.stats.get("phase_ms"),
-                       "exchange_bytes_sent_rank0": last_resident.stats.get("exchange_bytes_sent")}}
+                       "exchange_bytes_rank0": last_resident.stats.get("exchange_bytes_sent"),
+                       "exchange": last_resident.stats.get("exchange")}}
     print(json.dumps(line))
     if dist is not None:
         dist.barrier(); dist.destroy_process_group()

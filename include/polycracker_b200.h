@@ -91,6 +91,17 @@ int pc_dump_counts(pc_ctx* ctx, uint32_t min_count, uint32_t max_count,
 int pc_partition(pc_ctx* ctx, int k, int pb, int64_t* bucket_off, uint64_t** keys_dev);
 int pc_count_buckets(pc_ctx* ctx, int k, int pb, int n_buckets, const uint64_t* keys_dev, const int64_t* seg_begin,
                      const int64_t* seg_len, int n_seg, int64_t capacity);
+/* Peer-memory variant (one node, NVLink): instead of an all-to-all into a receive buffer the owner's count kernel
+ * streams each sender's slice straight out of that sender's bucket buffer.  pc_kbuf_export pins the bucket buffer at
+ * >= n_keys k-mers and returns its 64-byte CUDA IPC handle; pc_peer_open maps a peer's handle into this process;
+ * pc_count_buckets_from is pc_count_buckets with one base pointer per segment (host array of device pointers,
+ * seg_begin = offset inside that sender's buffer).  The caller orders partition -> count -> next partition across
+ * ranks (the bucket-size all-gather before and the repeat-set all-gather after the count already do). */
+int pc_kbuf_export(pc_ctx* ctx, int64_t n_keys, void* ipc_handle_64);
+int pc_peer_open(pc_ctx* ctx, const void* ipc_handle_64, uint64_t** dev_ptr);
+int pc_peer_close(pc_ctx* ctx, uint64_t* dev_ptr);
+int pc_count_buckets_from(pc_ctx* ctx, int k, int pb, int n_buckets, const uint64_t* const* seg_base,
+                          const int64_t* seg_begin, const int64_t* seg_len, int n_seg, int64_t capacity);
 /* alternative exchange of pre-aggregated pairs: all (kmer,count) pairs of the local table grouped by owner rank
  * (owner = hash(kmer) % world); offsets[world+1] is a host array.  keys/counts are device buffers of
  * capacity >= distinct k-mers.  pc_merge_counts adds received pairs into the ctx table (creating it with

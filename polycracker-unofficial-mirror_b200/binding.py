@@ -64,6 +64,10 @@ _SIGS = {
     "pc_dump_counts": (C.c_int, [_vp, _u32, _u32, _vp, _vp, _i64, C.c_int, _P(_i64)]),
     "pc_partition": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _P(_vp)]),
     "pc_count_buckets": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _i64]),
+    "pc_kbuf_export": (C.c_int, [_vp, _i64, _vp]),
+    "pc_peer_open": (C.c_int, [_vp, _vp, _P(_vp)]),
+    "pc_peer_close": (C.c_int, [_vp, _vp]),
+    "pc_count_buckets_from": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _i64]),
     "pc_export_by_owner": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _vp]),
     "pc_merge_counts": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, _i64, C.c_int]),
     "pc_select": (C.c_int, [_vp, _u32, _u32, C.c_int, _i64, _P(_i64)]),
@@ -340,6 +344,26 @@ class Context:
         p = keys if isinstance(keys, int) else keys.data_ptr()
         check(lib.pc_count_buckets(self._h, int(k), int(pb), sb.shape[0], p, sb.ctypes.data, sl.ctypes.data, sb.shape[1],
                                    int(capacity)), "pc_count_buckets")
+
+    def kbuf_export(self, n_keys):
+        """-> 64-byte CUDA IPC handle (numpy uint8[64]) of the bucket buffer, pinned at >= n_keys k-mers"""
+        h = np.zeros(64, np.uint8)
+        check(lib.pc_kbuf_export(self._h, int(n_keys), h.ctypes.data), "pc_kbuf_export")
+        return h
+
+    def peer_open(self, handle):
+        h = np.ascontiguousarray(handle, dtype=np.uint8)
+        out = _vp()
+        check(lib.pc_peer_open(self._h, h.ctypes.data, C.byref(out)), "pc_peer_open")
+        return out.value
+
+    def count_buckets_from(self, k, pb, seg_base, seg_begin, seg_len, capacity=0):
+        """seg_base: uint64[n_buckets, n_seg] device base pointers (own or peer-mapped bucket buffers)."""
+        sp = np.ascontiguousarray(seg_base, dtype=np.uint64)
+        sb = np.ascontiguousarray(seg_begin, dtype=np.int64); sl = np.ascontiguousarray(seg_len, dtype=np.int64)
+        assert sp.shape == sb.shape == sl.shape and sb.ndim == 2
+        check(lib.pc_count_buckets_from(self._h, int(k), int(pb), sb.shape[0], sp.ctypes.data, sb.ctypes.data,
+                                        sl.ctypes.data, sb.shape[1], int(capacity)), "pc_count_buckets_from")
 
     def export_by_owner(self, world, keys_t, counts_t):
         """keys_t (int64/uint64 view) and counts_t (int32) are torch CUDA tensors with >= distinct elements."""

@@ -492,7 +492,7 @@ static int do_partition(pc_ctx* c, int k, int pb) {
 
 // count n_buckets buckets (sub-table i <- segments [i*n_seg, (i+1)*n_seg) of keys_dev) into a fresh table
 static int do_count_buckets(pc_ctx* c, int k, int pb, int n_buckets, const uint64_t* keys_dev, const int64_t* seg_begin,
-                            const int64_t* seg_len, int n_seg, int64_t capacity) {
+                            const int64_t* seg_len, int n_seg, int64_t capacity, const uint64_t* const* seg_base_host = nullptr) {
     int rc;
     int64_t total = 0, max_bucket = 0;
     for (int q = 0; q < n_buckets; ++q) {
@@ -514,11 +514,17 @@ static int do_count_buckets(pc_ctx* c, int k, int pb, int n_buckets, const uint6
     capacity = (int64_t)(S * (uint64_t)n_buckets);
     rc = table_prepare(c, k, capacity, /*reset_stats=*/false); if (rc) return rc;
     c->pb = pb; c->part_S = S;
-    rc = c->d_seg.alloc((size_t)2 * n_buckets * n_seg); if (rc) return rc;
+    rc = c->d_seg.alloc((size_t)3 * n_buckets * n_seg); if (rc) return rc;
     CU(cudaMemcpyAsync(c->d_seg.p, seg_begin, (size_t)n_buckets * n_seg * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_seg.p + (size_t)n_buckets * n_seg, seg_len, (size_t)n_buckets * n_seg * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
     const long long* d_beg = reinterpret_cast<const long long*>(c->d_seg.p);
     const long long* d_len = d_beg + (size_t)n_buckets * n_seg;
+    const uint64_t* const* d_base = nullptr;
+    if (seg_base_host) {
+        static_assert(sizeof(uint64_t*) == sizeof(int64_t), "pointer width");
+        CU(cudaMemcpyAsync(c->d_seg.p + (size_t)2 * n_buckets * n_seg, seg_base_host, (size_t)n_buckets * n_seg * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        d_base = reinterpret_cast<const uint64_t* const*>(c->d_seg.p + (size_t)2 * n_buckets * n_seg);
+    }
     pc::Watch w{0u, nullptr, nullptr, 0ull};
     c->cross_valid = false;
     if (c->watch_low > 0) {
@@ -539,7 +545,7 @@ static int do_count_buckets(pc_ctx* c, int k, int pb, int n_buckets, const uint6
             B = 64; while (B < 4096 && (double)B * 1.41 < want) B <<= 1;
         }
         unsigned int grid = (unsigned int)n_buckets * B;
-#define COUNT_PART(I, CF, W, MB) LAUNCH(c, (pc::k_count_part<I, CF, W, MB>), grid, 256, keys_dev, d_beg, d_len, n_seg, pb, S, B, c->table(), c->d_stats.p, w)
+#define COUNT_PART(I, CF, W, MB) LAUNCH(c, (pc::k_count_part<I, CF, W, MB>), grid, 256, keys_dev, d_base, d_beg, d_len, n_seg, pb, S, B, c->table(), c->d_stats.p, w)
         if (w.low) {
             if (c->part_casfirst) COUNT_PART(4, true, true, 1); else COUNT_PART(4, false, true, 1);
         } else if (c->part_casfirst) COUNT_PART(4, true, false, 1);
@@ -660,6 +666,49 @@ int pc_partition(pc_ctx* c, int k, int pb, int64_t* bucket_off, uint64_t** keys_
     memcpy(bucket_off, c->h_bucket_off.data(), ((size_t)(1u << pb) + 1) * sizeof(int64_t));
     *keys_dev = c->kbuf.p;
     return PC_OK;
+}
+
+// ---- peer-memory variant of the exchange: owners read the senders' bucket buffers directly over NVLink ------------
+int pc_kbuf_export(pc_ctx* c, int64_t n_keys, void* ipc_handle) {
+    int rc = use_device(c); if (rc) return rc;
+    if (n_keys < 1 || !ipc_handle) return fail(PC_EINVAL, "bad pc_kbuf_export arguments");
+    rc = c->kbuf.alloc((size_t)n_keys); if (rc) return rc;           // kept (and re-used by pc_partition) while it is big enough
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, c->kbuf.p));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    memcpy(ipc_handle, &h, sizeof h);
+    return PC_OK;
+}
+
+int pc_peer_open(pc_ctx* c, const void* ipc_handle, uint64_t** dev_ptr) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!ipc_handle || !dev_ptr) return fail(PC_EINVAL, "bad pc_peer_open arguments");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof h);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *dev_ptr = static_cast<uint64_t*>(p);
+    return PC_OK;
+}
+
+int pc_peer_close(pc_ctx* c, uint64_t* dev_ptr) {
+    int rc = use_device(c); if (rc) return rc;
+    if (dev_ptr) CU(cudaIpcCloseMemHandle(dev_ptr));
+    return PC_OK;
+}
+
+int pc_count_buckets_from(pc_ctx* c, int k, int pb, int n_buckets, const uint64_t* const* seg_base, const int64_t* seg_begin,
+                          const int64_t* seg_len, int n_seg, int64_t capacity) {
+    int rc = use_device(c); if (rc) return rc;
+    if (k < 1 || k > 32) return fail(PC_EINVAL, "k = %d unsupported: this path handles 1 <= k <= 32 (uint64 k-mers)", k);
+    if (pb < 0 || pb > 12 || n_buckets < 1 || n_buckets > (1 << pb) || n_seg < 1 || !seg_base || !seg_begin || !seg_len)
+        return fail(PC_EINVAL, "bad pc_count_buckets_from arguments");
+    c->counted = c->selected = c->built = c->tfidf_done = false;
+    unsigned long long keep = c->h_stats.valid_windows;
+    pc::CountStats z{}; z.valid_windows = keep;
+    CU(cudaMemcpyAsync(c->d_stats.p, &z, sizeof z, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return do_count_buckets(c, k, pb, n_buckets, nullptr, seg_begin, seg_len, n_seg, capacity, seg_base);
 }
 
 int pc_count_buckets(pc_ctx* c, int k, int pb, int n_buckets, const uint64_t* keys_dev, const int64_t* seg_begin,

@@ -627,10 +627,11 @@ k_tile_scatter(const uint64_t* __restrict__ stream, int64_t n_stream, int pb,
 
 // pass C: count one bucket after the other.  blockIdx = local_bucket * B + b: blocks are dispatched in index order,
 // so at any time the resident blocks work on one or two adjacent buckets whose sub-tables (S slots) sit in L2.
-// A bucket's k-mers arrive as n_seg segments of `keys` (one per sending rank; a single segment on one GPU).
+// A bucket's k-mers arrive as n_seg segments (one per sending rank; a single segment on one GPU).
 template <int ITEMS, bool CASFIRST, bool WATCH, int MINB>
 __global__ void __launch_bounds__(256, MINB)
-k_count_part(const uint64_t* __restrict__ keys, const long long* __restrict__ seg_begin, const long long* __restrict__ seg_len,
+k_count_part(const uint64_t* __restrict__ keys, const uint64_t* const* __restrict__ seg_base,
+             const long long* __restrict__ seg_begin, const long long* __restrict__ seg_len,
              int n_seg, int pb, uint64_t S, unsigned int B, CountTable table, CountStats* __restrict__ stats,
              const Watch w_in)
 {
@@ -640,7 +641,10 @@ k_count_part(const uint64_t* __restrict__ keys, const long long* __restrict__ se
     unsigned int new_keys = 0, max_probe = 0;
     const unsigned long long stride = (unsigned long long)B * 256u * ITEMS;
     for (int sg = 0; sg < n_seg; ++sg) {
-        const uint64_t* kbuf = keys + seg_begin[(int64_t)q * n_seg + sg];
+        // seg_base != null: every segment lives in its sender's bucket buffer, mapped into this process over
+        // NVLink (CUDA IPC).  The owner streams its peers' k-mers straight out of their HBM while it updates its
+        // L2-resident sub-table: the exchange is fused into the count, no all-to-all, no receive buffer.
+        const uint64_t* kbuf = (seg_base ? seg_base[(int64_t)q * n_seg + sg] : keys) + seg_begin[(int64_t)q * n_seg + sg];
         const unsigned long long end = (unsigned long long)seg_len[(int64_t)q * n_seg + sg];
         // software pipeline: the keys of the next iteration (a DRAM stream) are requested before this iteration's
         // table accesses (L2) are issued

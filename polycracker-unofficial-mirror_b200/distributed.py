@@ -98,6 +98,30 @@ def device_view(torch, ptr, n, device):
     return torch.as_tensor(_DevView(ptr, n), device=device)
 
 
+def peer_pointers(ctx, torch, dist, device, kbuf_keys, own_ptr):
+    """Device pointers of every rank's bucket buffer in THIS process (own buffer: own pointer).  The 64-byte CUDA IPC
+    handles are all-gathered every step (a 64-byte collective) and a peer buffer is (re)opened only when its handle
+    changed, i.e. when that rank had to grow its buffer."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    mine = torch.from_numpy(ctx._pc_handle.copy()).to(device)
+    allh = [torch.empty(64, dtype=torch.uint8, device=device) for _ in range(world)]
+    dist.all_gather(allh, mine)
+    handles = [h.cpu().numpy().tobytes() for h in allh]
+    cache = getattr(ctx, "_pc_peers", None)
+    if cache is None:
+        cache = ctx._pc_peers = {}
+    ptrs = []
+    for r in range(world):
+        if r == rank:
+            ptrs.append(int(own_ptr))
+            continue
+        ent = cache.get(r)
+        if ent is None or ent[0] != handles[r]:
+            ent = cache[r] = (handles[r], ctx.peer_open(np.frombuffer(handles[r], dtype=np.uint8)))
+        ptrs.append(ent[1])
+    return ptrs
+
+
 def _stream_sync(torch, device):
     """The C ABI is host-synchronous on the context's stream; collectives are asynchronous on torch's stream.  When
     the two streams differ, wait for the collective before handing its output to the context (and vice versa the
@@ -109,7 +133,7 @@ def _stream_sync(torch, device):
 def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000, k=23, kmer_low_count=100,
                              high_bool=0, kmer_high_count=2000000, sampling_sensitivity=1, remove_non_chunk=1,
                              min_chunk_threshold=0, min_chunk_size=0, prefilter=0, tfidf=True, fetch=True,
-                             staged=None, arena=None):
+                             staged=None, arena=None, exchange="auto"):
     """One rank's share of the hot path.  `layout` describes the WHOLE genome (every rank builds the same one from
     names + lengths); `fetch_chunks(ids, begins, ends, total)` returns this rank's ASCII buffer (uint8, host numpy /
     pinned torch / CUDA torch) laid out by local_buffer_plan; `staged` short-circuits it with a prebuilt
@@ -150,6 +174,10 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
     P = 1 << pb
     mark("host_plan")
     ctx.load_sequences(buf, begins, ends)
+    kbuf_keys = int((ends - begins).sum()) if len(ends) else 1            # >= local windows: pins the bucket buffer
+    if hasattr(ctx, "kbuf_export") and getattr(device, "type", "cpu") == "cuda" and exchange != "nccl":
+        ctx._pc_handle = ctx.kbuf_export(max(kbuf_keys, getattr(ctx, "_pc_kbuf_keys", 1)))
+        ctx._pc_kbuf_keys = max(kbuf_keys, getattr(ctx, "_pc_kbuf_keys", 1))
     off, keys = ctx.partition(k, pb)
     mark("pack+partition")
     n_local = int(off[-1])
@@ -160,25 +188,41 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
     q_lo = [(r * P + world - 1) // world for r in range(world + 1)]      # rank r owns buckets [q_lo[r], q_lo[r+1])
     send_counts = [int(sizes_all[rank, q_lo[r]:q_lo[r + 1]].sum()) for r in range(world)]
     recv_counts = [int(sizes_all[s, q_lo[rank]:q_lo[rank + 1]].sum()) for s in range(world)]
-    send = keys if torch.is_tensor(keys) else device_view(torch, keys, n_local, device)
-    # 2. all-to-all of the raw k-mers over NVLink; count at the owner
-    recv = torch.empty(int(sum(recv_counts)), dtype=torch.int64, device=device)
-    mark("bucket_sizes_allgather")
-    dist.all_to_all_single(recv, send[:n_local], output_split_sizes=recv_counts, input_split_sizes=send_counts)
-    mark("kmer_all_to_all")
     mine = sizes_all[:, q_lo[rank]:q_lo[rank + 1]]                        # [sender, my bucket]
-    recv_off = np.concatenate([[0], np.cumsum(recv_counts)])[:-1]
-    within = np.cumsum(mine, axis=1) - mine                               # offset of bucket q inside sender s's slice
-    seg_begin = (recv_off[:, None] + within).T.copy()                     # [my bucket, sender]
-    seg_len = mine.T.copy()
     if hasattr(ctx, "watch_threshold"):
         ctx.watch_threshold(0)
-    ctx.count_buckets(k, pb, recv, seg_begin, seg_len)
+    use_peer = exchange == "peer" or (exchange == "auto" and getattr(device, "type", "cpu") == "cuda"
+                                      and hasattr(ctx, "kbuf_export") and not torch.is_tensor(keys))
+    mark("bucket_sizes_allgather")
+    if use_peer:
+        # 2a. fused exchange: the owner's count kernel reads every sender's slice straight out of that sender's bucket
+        # buffer over NVLink (CUDA IPC mapping).  The all-gather of the bucket sizes above is the barrier that says
+        # "every rank has finished its partition"; the repeat-set all-gather below says "every rank has finished
+        # reading", so the next step may overwrite the buffers.
+        peers = peer_pointers(ctx, torch, dist, device, kbuf_keys, keys)
+        mark("peer_handles")
+        sender_off = np.cumsum(sizes_all, axis=1) - sizes_all             # bucket offsets inside each sender's buffer
+        seg_begin = sender_off[:, q_lo[rank]:q_lo[rank + 1]].T.copy()     # [my bucket, sender]
+        seg_len = mine.T.copy()
+        seg_base = np.repeat(np.asarray(peers, dtype=np.uint64)[None, :], seg_len.shape[0], axis=0)
+        ctx.count_buckets_from(k, pb, seg_base, seg_begin, seg_len)
+        exchanged = 8 * (int(sum(recv_counts)) - recv_counts[rank])    # bytes read from peers' HBM over NVLink
+    else:
+        # 2b. all-to-all of the raw k-mers over NVLink (NCCL); count at the owner
+        send = keys if torch.is_tensor(keys) else device_view(torch, keys, n_local, device)
+        recv = torch.empty(int(sum(recv_counts)), dtype=torch.int64, device=device)
+        dist.all_to_all_single(recv, send[:n_local], output_split_sizes=recv_counts, input_split_sizes=send_counts)
+        mark("kmer_all_to_all")
+        recv_off = np.concatenate([[0], np.cumsum(recv_counts)])[:-1]
+        within = np.cumsum(mine, axis=1) - mine                           # offset of bucket q inside sender s's slice
+        seg_begin = (recv_off[:, None] + within).T.copy()                 # [my bucket, sender]
+        seg_len = mine.T.copy()
+        ctx.count_buckets(k, pb, recv, seg_begin, seg_len)
+        del recv
+        exchanged = 8 * (n_local - send_counts[rank])
     owner_info = ctx.count_info()
     info = dict(owner_info, valid_windows=n_local)
     mark("count_buckets")
-    del recv
-    mark("free_recv")
     n_owner_sel = ctx.select(effective_low_count(k, kmer_low_count), kmer_high_count, bool(high_bool), 1)
     mark("select")
     if hasattr(ctx, "timings"):
@@ -214,7 +258,7 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
     stats.update(n_selected=n_sel, nnz=nnz, n_rows=n_local_rows, n_rows_global=len(scaffolds_all), row0=row0,
                  valid_windows_global=int(t[0]), distinct_global=int(t[1]), nnz_global=int(t[2]),
                  owner_distinct=owner_info["distinct"], local_bases=int(ends[-1]) if len(ends) else 0,
-                 phase_ms={k_: round(v, 2) for k_, v in phase.items()}, exchange_bytes_sent=8 * (n_local - send_counts[rank]))
+                 phase_ms={k_: round(v, 2) for k_, v in phase.items()}, exchange_bytes_sent=exchanged, exchange="peer" if use_peer else "nccl_all_to_all")
     scaffolds = scaffolds_all[row0:row0 + n_local_rows]
     if not fetch:
         return HotPathResult(layout, k, scaffolds, np.empty(0, np.uint64), None, None, None, None, None, stats,

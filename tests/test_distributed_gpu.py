@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def _worker(rank, world, port, tmpdir, part_mode):
+def _worker(rank, world, port, tmpdir, part_mode, exchange):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -40,7 +40,10 @@ def _worker(rank, world, port, tmpdir, part_mode):
         ctx = binding.Context(rank)
         ctx.set_stream(torch.cuda.current_stream().cuda_stream)
         ctx.tune(part_mode=part_mode, part_mbytes=1)
-        res = pcd.run_hot_path_distributed(ctx, layout, fetch, dev, chunk_size=20000, k=23, kmer_low_count=10)
+        for _ in range(2):                                    # twice: the peer mappings and buffers are re-used
+            res = pcd.run_hot_path_distributed(ctx, layout, fetch, dev, chunk_size=20000, k=23, kmer_low_count=10,
+                                               exchange=exchange)
+        assert res.stats["exchange"] == ("peer" if exchange == "peer" else "nccl_all_to_all")
         full = pcd.gather_rows(res)
         if rank == 0:
             np.savez(os.path.join(tmpdir, "out.npz"), keys=full.kmer_keys, indptr=full.indptr, indices=full.indices,
@@ -52,15 +55,15 @@ def _worker(rank, world, port, tmpdir, part_mode):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("part_mode", [0, 1])
-def test_two_gpus_nccl_match_oracle(tmp_path, part_mode):
+@pytest.mark.parametrize("part_mode,exchange", [(0, "nccl"), (1, "nccl"), (1, "peer")])
+def test_two_gpus_nccl_match_oracle(tmp_path, part_mode, exchange):
     from polycracker_b200 import binding, synth
     from tests import util
     if binding.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_worker, args=(2, port, str(tmp_path), part_mode), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), part_mode, exchange), nprocs=2, join=True)
     got = np.load(tmp_path / "out.npz")
     p = synth.small_params(seed=191, genome_size=3_000_000, n_chrom=3, n_shared_families=6, n_specific_families=8)
     seq, off, names = synth.generate(p)
