@@ -145,6 +145,17 @@ int pc_df_get(pc_ctx* ctx, int32_t* df, int loc);                      /* stored
 int pc_tfidf(pc_ctx* ctx, int64_t n_rows_global, const int32_t* df_global, int df_loc);
 int pc_tfidf_get(pc_ctx* ctx, float* data, int loc);                   /* nnz values, CSR order */
 
+/* ---- memory ---------------------------------------------------------------------------------------------
+ * Release device buffers later stages do not need (bit mask).  At Gbp scale the count table, the bucket buffer, the
+ * k-mer stream and the hit buffers are tens of GB each: releasing the bucket buffer after pc_count and the table after
+ * pc_select lets a 4.5 Gbp genome run on one 180 GB B200.  Releasing the stream makes K5 fall back to the roller. */
+#define PC_REL_ASCII   1
+#define PC_REL_BUCKETS 2
+#define PC_REL_TABLE   4
+#define PC_REL_STREAM  8
+#define PC_REL_HITS    16
+int pc_release(pc_ctx* ctx, int what);
+
 /* ---- measurement ------------------------------------------------------------------------------------------
  * CUDA-event time (ms) of the last run of each stage on the ctx stream.  Index: 0 h2d, 1 pack, 2 table-init,
  * 3 count, 4 select(scan), 5 sort, 6 repeat-table, 7 probe, 8 row-sort, 9 emit, 10 tfidf, 11 d2h.

@@ -70,6 +70,7 @@ _SIGS = {
     "pc_count_buckets_from": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _i64]),
     "pc_export_by_owner": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _vp]),
     "pc_merge_counts": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, _i64, C.c_int]),
+    "pc_release": (C.c_int, [_vp, C.c_int]),
     "pc_select": (C.c_int, [_vp, _u32, _u32, C.c_int, _i64, _P(_i64)]),
     "pc_watch_threshold": (C.c_int, [_vp, _u32]),
     "pc_selected_get": (C.c_int, [_vp, _vp, C.c_int]),
@@ -377,6 +378,11 @@ class Context:
                                   int(n), int(k), int(capacity), int(bool(fresh))), "pc_merge_counts")
 
     # K4
+    REL_ASCII, REL_BUCKETS, REL_TABLE, REL_STREAM, REL_HITS = 1, 2, 4, 8, 16
+
+    def release(self, what):
+        check(lib.pc_release(self._h, int(what)), "pc_release")
+
     def watch_threshold(self, low):
         check(lib.pc_watch_threshold(self._h, int(low)), "pc_watch_threshold")
 

@@ -563,6 +563,20 @@ static int do_count_buckets(pc_ctx* c, int k, int pb, int n_buckets, const uint6
     return PC_OK;
 }
 
+// Free device buffers that later stages no longer need (large genomes on one GPU: the count table, the bucket buffer
+// and the hit buffers are each tens of GB at Gbp scale and are never needed at the same time).
+int pc_release(pc_ctx* c, int what) {
+    int rc = use_device(c); if (rc) return rc;
+    CU(cudaStreamSynchronize(c->stream));
+    if (c->zeroed_slots > 0) { CU(cudaStreamSynchronize(c->aux_stream)); c->zeroed_slots = 0; }
+    if (what & PC_REL_ASCII) { c->ascii.release(); c->ascii_padded = 0; }
+    if (what & PC_REL_BUCKETS) c->kbuf.release();
+    if (what & PC_REL_TABLE) { c->table_keys.release(); c->table_counts.release(); c->counted = false; c->cross_valid = false; c->cross_keys.release(); }
+    if (what & PC_REL_STREAM) { c->kstream.release(); c->stream_valid = false; }
+    if (what & PC_REL_HITS) { c->hits_a.release(); c->hits_b.release(); }
+    return PC_OK;
+}
+
 int pc_watch_threshold(pc_ctx* c, uint32_t low) {
     if (!c) return fail(PC_EINVAL, "null context");
     c->watch_low = low;

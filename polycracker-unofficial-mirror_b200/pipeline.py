@@ -130,7 +130,7 @@ def effective_low_count(k, kmer_low_count):
 def run_hot_path(ctx, seq, seq_offsets, names, chunk_size=75000, k=23, kmer_low_count=100, high_bool=0,
                  kmer_high_count=2000000, sampling_sensitivity=1, remove_non_chunk=1, min_chunk_threshold=0,
                  min_chunk_size=0, prefilter=0, tfidf=True, table_capacity=0, fetch=True, layout=None, arena=None,
-                 fuse_select=False):
+                 fuse_select=False, low_memory=False):
     """One pass of the hot path on one GPU.  fuse_select: record threshold crossings during the count instead of
     re-scanning the table (pc_watch_threshold); measured slower on B200 (returning atomics cost more than the scan).
 
@@ -143,12 +143,16 @@ def run_hot_path(ctx, seq, seq_offsets, names, chunk_size=75000, k=23, kmer_low_
     ctx.load_sequences(seq, layout.chunk_begin_abs, layout.chunk_end_abs)
     ctx.watch_threshold(effective_low_count(k, kmer_low_count) if (fuse_select and not high_bool) else 0)
     ctx.count(k, table_capacity)
+    stats = ctx.count_info()
+    if low_memory:                                        # Gbp-scale genomes on one GPU: see pc_release
+        ctx.release(ctx.REL_BUCKETS | ctx.REL_ASCII)
     n_sel = ctx.select(effective_low_count(k, kmer_low_count), kmer_high_count, bool(high_bool),
                        sampling_sensitivity)
+    if low_memory:
+        ctx.release(ctx.REL_TABLE)
     nnz = ctx.build_matrix(chunk_row, len(scaffolds))
     if tfidf:
         ctx.tfidf(len(scaffolds))
-    stats = ctx.count_info()
     stats.update(n_selected=n_sel, nnz=nnz, n_rows=len(scaffolds), n_chunks=layout.n_chunks)
     if not fetch:
         return HotPathResult(layout, k, scaffolds, np.empty(0, np.uint64), None, None, None, None, None, stats,

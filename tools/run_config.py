@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Run one BASELINE.json config through the in-memory hot path on ONE GPU and print sizes, stage times and a few
+size-independent invariants.  For the multi-GPU runs use bench.py under torchrun.
+
+    python tools/run_config.py --config cfg3_4.5Gbp_tobacco --low-memory
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from polycracker_b200 import binding, synth  # noqa: E402
+from polycracker_b200.pipeline import ChunkLayout, HostArena, run_hot_path  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="cfg3_4.5Gbp_tobacco", choices=sorted(synth.CONFIGS))
+    ap.add_argument("--genome-size", type=int, default=0)
+    ap.add_argument("--low-memory", action="store_true")
+    ap.add_argument("--fetch", action="store_true", help="also copy the CSR + TF-IDF to the host")
+    ap.add_argument("--part-mbytes", type=int, default=0)
+    a = ap.parse_args()
+    import torch
+    cfg = dict(synth.CONFIGS[a.config])
+    gsize = a.genome_size or cfg["genome_size"]
+    params = synth.make_params(cfg["seed"], gsize, n_subgenomes=cfg["n_subgenomes"])
+    t0 = time.time()
+    pinned = torch.empty(gsize, dtype=torch.uint8, pin_memory=True)
+    seq, off, names = synth.generate(params, out=pinned.numpy(), threads=min(16, os.cpu_count() or 8))
+    t_gen = time.time() - t0
+    layout = ChunkLayout(names, off, cfg["chunk_size"])
+    layout.rows()
+    ctx = binding.Context(0)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    if a.part_mbytes:
+        ctx.tune(part_mbytes=a.part_mbytes)
+    dev = pinned[:len(seq)].to("cuda")
+    arena = HostArena()
+    out = {}
+    for it in range(2):                                    # first pass allocates, second is the steady state
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        res = run_hot_path(ctx, dev, off, names, chunk_size=cfg["chunk_size"], k=cfg["k"],
+                           kmer_low_count=cfg["kmer_low_count"], fetch=a.fetch, layout=layout, arena=arena,
+                           low_memory=a.low_memory)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        out["pass%d_s" % it] = round(dt, 4)
+    st = res.stats
+    free_b, total_b = torch.cuda.mem_get_info()
+    out.update(config=a.config, genome_bases=int(len(seq)), gen_s=round(t_gen, 1), gbp_per_s=round(len(seq) / dt / 1e9, 2),
+               stats={k_: int(v) for k_, v in st.items() if isinstance(v, (int, np.integer))},
+               stage_ms={k_: round(v, 2) for k_, v in res.timings.items() if v > 0},
+               hbm_used_gb=round((total_b - free_b) / 1e9, 1), hbm_total_gb=round(total_b / 1e9, 1),
+               torch_peak_gb=round(torch.cuda.max_memory_allocated() / 1e9, 1))
+    if a.fetch:
+        m = res.csr_matrix()
+        lens = dict(zip(layout.chunk_names, (layout.chunk_end - layout.chunk_start).tolist()))
+        rs = np.asarray(m.sum(axis=1)).ravel()
+        out["row_sums_bounded"] = bool(all(rs[i] <= lens[s] - cfg["k"] + 1 for i, s in enumerate(res.scaffolds)))
+        out["indices_sorted"] = bool(all(np.all(np.diff(res.indices[res.indptr[r]:res.indptr[r + 1]]) > 0)
+                                         for r in range(0, m.shape[0], max(1, m.shape[0] // 200))))
+        out["keys_sorted_unique"] = bool(np.all(np.diff(res.kmer_keys.astype(np.uint64)) > 0))
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
