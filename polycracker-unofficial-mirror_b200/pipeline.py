@@ -151,6 +151,8 @@ def run_hot_path(ctx, seq, seq_offsets, names, chunk_size=75000, k=23, kmer_low_
     if low_memory:
         ctx.release(ctx.REL_TABLE)
     nnz = ctx.build_matrix(chunk_row, len(scaffolds))
+    if low_memory:
+        ctx.release(ctx.REL_HITS | ctx.REL_STREAM)          # scratch of K5/K6; the CSR is separate
     if tfidf:
         ctx.tfidf(len(scaffolds))
     stats.update(n_selected=n_sel, nnz=nnz, n_rows=len(scaffolds), n_chunks=layout.n_chunks)
