@@ -266,6 +266,48 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
     return fetch_result(ctx, layout, k, scaffolds, n_sel, nnz, tfidf, stats, arena, df=df_t[:n_sel].cpu().numpy())
 
 
+def rerun_threshold(ctx, layout, ids, device, k=23, kmer_low_count=100, high_bool=0, kmer_high_count=2000000,
+                    sampling_sensitivity=1, remove_non_chunk=1, min_chunk_threshold=0, min_chunk_size=0, prefilter=0,
+                    tfidf=True, fetch=True, arena=None):
+    """Threshold sweep (BASELINE config 4): the owners' count tables of a previous run_hot_path_distributed call on
+    this context are kept; only K4 -> all-gather of the repeat set -> K5..K7 are repeated for the new threshold."""
+    import torch
+    import torch.distributed as dist
+    scaffolds_all, chunk_row_all = layout.rows(remove_non_chunk, min_chunk_threshold, min_chunk_size, prefilter)
+    my_rows_global = chunk_row_all[ids]
+    kept = np.flatnonzero(my_rows_global >= 0)
+    row0 = int(my_rows_global[kept].min()) if len(kept) else 0
+    local_chunk_row = np.where(my_rows_global >= 0, my_rows_global - row0, -1).astype(np.int32)
+    n_local_rows = len(kept)
+    n_owner_sel = ctx.select(effective_low_count(k, kmer_low_count), kmer_high_count, bool(high_bool), 1)
+    sel_local = torch.empty(max(n_owner_sel, 1), dtype=torch.int64, device=device)
+    if n_owner_sel:
+        ctx.selected_into(sel_local)
+    sel_all, _ = _all_gather_v(dist, sel_local[:n_owner_sel], torch)
+    if sampling_sensitivity > 1 and sel_all.numel():
+        sel_all = torch.sort(sel_all.view(torch.int64) ^ (-2**63))[0] ^ (-2**63)
+        sel_all = sel_all[::int(sampling_sensitivity)].contiguous()
+    _stream_sync(torch, device)
+    n_sel = ctx.set_selected(sel_all, k, n=sel_all.numel())
+    nnz = ctx.build_matrix(local_chunk_row, n_local_rows)
+    df_t = torch.zeros(max(n_sel, 1), dtype=torch.int32, device=device)
+    if n_sel:
+        ctx.df_into(df_t)
+    dist.all_reduce(df_t, op=dist.ReduceOp.SUM)
+    _stream_sync(torch, device)
+    if tfidf:
+        ctx.tfidf(len(scaffolds_all), df_t if n_sel else None)
+    t = torch.tensor([nnz], dtype=torch.int64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    stats = dict(n_selected=n_sel, nnz=nnz, n_rows=n_local_rows, n_rows_global=len(scaffolds_all), row0=row0,
+                 nnz_global=int(t[0]))
+    scaffolds = scaffolds_all[row0:row0 + n_local_rows]
+    if not fetch:
+        return HotPathResult(layout, k, scaffolds, np.empty(0, np.uint64), None, None, None, None, None, stats,
+                             ctx.timings())
+    return fetch_result(ctx, layout, k, scaffolds, n_sel, nnz, tfidf, stats, arena, df=df_t[:n_sel].cpu().numpy())
+
+
 def gather_rows(result, dst=0):
     """Concatenate the shard-local CSR blocks on rank `dst` (host side, gather_object).  Returns the global
     HotPathResult on dst, None elsewhere."""
