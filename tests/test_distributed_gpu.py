@@ -44,6 +44,14 @@ def _worker(rank, world, port, tmpdir, part_mode, exchange):
             res = pcd.run_hot_path_distributed(ctx, layout, fetch, dev, chunk_size=20000, k=23, kmer_low_count=10,
                                                exchange=exchange)
         assert res.stats["exchange"] == ("peer" if exchange == "peer" else "nccl_all_to_all")
+        if exchange == "peer":                                # threshold sweep on the kept count tables (config 4)
+            blocks = pcd.shard_chunks(layout, world)
+            ids = pcd.local_buffer_plan(layout, blocks[rank])[0]
+            res2 = pcd.rerun_threshold(ctx, layout, ids, dev, k=23, kmer_low_count=25)
+            full2 = pcd.gather_rows(res2)
+            if rank == 0:
+                np.savez(os.path.join(tmpdir, "out25.npz"), keys=full2.kmer_keys, indptr=full2.indptr,
+                         indices=full2.indices, data=full2.data, tfidf=full2.tfidf)
         full = pcd.gather_rows(res)
         if rank == 0:
             np.savez(os.path.join(tmpdir, "out.npz"), keys=full.kmer_keys, indptr=full.indptr, indices=full.indices,
@@ -75,3 +83,10 @@ def test_two_gpus_nccl_match_oracle(tmp_path, part_mode, exchange):
     util.assert_tfidf_close(got["tfidf"], want["tfidf"])
     assert got["stats"].tolist() == [want["n_windows"], len(want["keys"]), len(want["data"])]
     assert len(want["sel"]) > 100
+    if exchange == "peer":
+        got25 = np.load(tmp_path / "out25.npz")
+        want25 = util.c_oracle_path(seq, off, names, 20000, 23, 25)
+        assert got25["keys"].tolist() == want25["sel"].tolist() and len(want25["sel"]) < len(want["sel"])
+        assert np.array_equal(got25["indptr"], want25["indptr"]) and np.array_equal(got25["indices"], want25["indices"])
+        assert np.array_equal(got25["data"], want25["data"])
+        util.assert_tfidf_close(got25["tfidf"], want25["tfidf"])

@@ -66,13 +66,15 @@ def main():
             torch.cuda.synchronize(); dt = time.perf_counter() - t0
             t = torch.tensor([dt], dtype=torch.float64, device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            if ti == 0:
+                first = res
             results.append(dict(threshold=low, seconds=round(float(t.item()), 4), n_selected=res.stats["n_selected"],
                                 nnz_global=res.stats["nnz_global"], rows=res.stats["n_rows_global"],
                                 full_path=(ti == 0), phase_ms=res.stats.get("phase_ms")))
     if rank == 0:
         free_b, total_b = torch.cuda.mem_get_info()
         print(json.dumps(dict(config=a.config, n_gpus=world, genome_bases=int(offs[-1]), gen_s=round(t_gen, 1),
-                              valid_windows=res.stats["valid_windows_global"], distinct=res.stats["distinct_global"],
+                              valid_windows=first.stats["valid_windows_global"], distinct=first.stats["distinct_global"],
                               gbp_per_s_full_path=round(int(offs[-1]) / results[0]["seconds"] / 1e9, 2),
                               hbm_used_gb_rank0=round((total_b - free_b) / 1e9, 1), sweep=results)))
     dist.barrier(); dist.destroy_process_group()
