@@ -227,6 +227,24 @@ def test_low_complexity_heavy_hitters(ctx):
     _check_against_c_oracle(ctx, seq, off, names, 70000, 32, 3)
 
 
+def test_partitioned_path_skewed_buckets_and_odd_shapes(ctx):
+    """Forced partitioned count + stream probe on inputs that unbalance the buckets (poly-A / tandem repeats put
+    hundreds of thousands of instances of ONE k-mer into one bucket), on thousands of tiny scaffolds (every warp tile
+    spans many chunks) and on one chunk longer than any tile."""
+    rng = np.random.default_rng(3)
+    tiny = [("t%d" % i, "".join(rng.choice(list("ACGT"), int(rng.integers(1, 90))))) for i in range(3000)]
+    seqs = [("polyA", "A" * 300000), ("at", "AT" * 100000), ("unit", "ACGTTGCAAC" * 30000)] + tiny + \
+           [("big", "".join(rng.choice(list("ACGTN"), 400000, p=[.245, .245, .245, .245, .02])))]
+    seq, off, names = util.from_sequences(seqs)
+    try:
+        for mb in (1, 4):
+            ctx.tune(part_mode=1, part_mbytes=mb)
+            _check_against_c_oracle(ctx, seq, off, names, 50000, 23, 3, remove_non_chunk=0)
+            _check_against_c_oracle(ctx, seq, off, names, 1000000, 16, 3, remove_non_chunk=0)
+    finally:
+        ctx.tune(part_mode=-1, part_mbytes=64)
+
+
 def test_external_repeat_set(ctx):
     """blast_kmers as a separately invoked stage: the repeat set comes from a k-mer FASTA, in either orientation,
     unsorted, with duplicates."""
