@@ -145,6 +145,29 @@ int pc_df_get(pc_ctx* ctx, int32_t* df, int loc);                      /* stored
 int pc_tfidf(pc_ctx* ctx, int64_t n_rows_global, const int32_t* df_global, int df_loc);
 int pc_tfidf_get(pc_ctx* ctx, float* data, int loc);                   /* nnz values, CSR order */
 
+/* ---- N1  subgenome extraction inner loop (scope row N1; replaces the external-tool chain of
+ * subgenomeExtraction, polycracker.py:991-1020: kmercountexact per subgenome 692-719, compareKmers 735-783,
+ * bbmap map-back 786-799, blast2bed3 + bedtools coverage 802-865) ------------------------------------------
+ * A session holds up to PC_MAX_GROUPS subgenomes and PC_MAX_SUB_K k-mer lengths.  Per length k:
+ *   for each subgenome g: pc_load_sequences(its chunks); pc_count(k); pc_sub_add_counts(g, min_count)
+ *   pc_sub_compare(...)   -> the differential k-mers of every subgenome for this k
+ * then pc_load_sequences(all chunks); pc_sub_mapback(coverage).
+ * min_count is the counter's dump floor (kmercountexact mincount=3 for k <= 31, jellyfish 1; pc.py:711-714).
+ * compare: k-mer of g is differential if for ANY other subgenome o  count_g / count_o > ratio_threshold, where the
+ * division floors when o holds the k-mer (Python 2 int / int, pc.py:765,778) and is count_g / default_value
+ * otherwise.  sampling > 1 keeps every sampling-th differential k-mer in ascending k-mer order (the reference samples
+ * in Python-2 dict order, which is not reproducible).  n_diff[n_groups] receives the set sizes.
+ * diff_get: the set of (k, group), ascending, with counts[i * n_groups + o] = count in subgenome o (0 = absent).
+ * mapback: coverage[chunk * n_groups + g] = number of distinct window starts in the chunk (loaded order) where a
+ * differential k-mer of g, of any compared length, matches on either strand = column 6 of `bedtools coverage`. */
+#define PC_MAX_GROUPS 8
+#define PC_MAX_SUB_K  8
+int pc_sub_begin(pc_ctx* ctx, int n_groups);
+int pc_sub_add_counts(pc_ctx* ctx, int group, uint32_t min_count, int64_t* n_kmers);
+int pc_sub_compare(pc_ctx* ctx, double ratio_threshold, double default_value, int64_t sampling, int64_t* n_diff);
+int pc_sub_diff_get(pc_ctx* ctx, int k, int group, uint64_t* keys, uint32_t* counts, int loc, int64_t* n);
+int pc_sub_mapback(pc_ctx* ctx, int32_t* coverage, int loc);
+
 /* ---- memory ---------------------------------------------------------------------------------------------
  * Release device buffers later stages do not need (bit mask).  At Gbp scale the count table, the bucket buffer, the
  * k-mer stream and the hit buffers are tens of GB each: releasing the bucket buffer after pc_count and the table after
@@ -158,9 +181,10 @@ int pc_release(pc_ctx* ctx, int what);
 
 /* ---- measurement ------------------------------------------------------------------------------------------
  * CUDA-event time (ms) of the last run of each stage on the ctx stream.  Index: 0 h2d, 1 pack, 2 table-init,
- * 3 count, 4 select(scan), 5 sort, 6 repeat-table, 7 probe, 8 row-sort, 9 emit, 10 tfidf, 11 d2h.
+ * 3 count, 4 select(scan), 5 sort, 6 repeat-table, 7 probe, 8 row-sort, 9 emit, 10 tfidf, 11 d2h, 12 export, 13 merge,
+ * 14 bucket histogram, 15 bucket scatter, 16 subgenome dictionary, 17 subgenome compare, 18 subgenome map-back.
  * launches: kernels launched by this ctx since the last pc_reset_counters. */
-#define PC_N_STAGES 16
+#define PC_N_STAGES 20
 int pc_timings(pc_ctx* ctx, float ms[PC_N_STAGES]);
 int pc_launch_count(pc_ctx* ctx, int64_t* launches);
 int pc_reset_counters(pc_ctx* ctx);

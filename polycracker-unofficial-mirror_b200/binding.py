@@ -11,9 +11,11 @@ import numpy as np
 from . import build as _build
 
 PC_HOST, PC_DEVICE = 0, 1
-PC_N_STAGES = 16
+PC_N_STAGES = 20
 STAGE_NAMES = ["h2d", "pack", "table_init", "count", "select", "sort", "rep_table", "probe", "row_sort", "emit",
-               "tfidf", "d2h", "export", "merge", "part_hist", "part_scatter"]
+               "tfidf", "d2h", "export", "merge", "part_hist", "part_scatter", "sub_dict", "sub_compare", "sub_mapback",
+               "reserved"]
+PC_MAX_GROUPS, PC_MAX_SUB_K = 8, 8
 
 
 class PolycrackerError(RuntimeError):
@@ -71,6 +73,11 @@ _SIGS = {
     "pc_export_by_owner": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _vp]),
     "pc_merge_counts": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, _i64, C.c_int]),
     "pc_release": (C.c_int, [_vp, C.c_int]),
+    "pc_sub_begin": (C.c_int, [_vp, C.c_int]),
+    "pc_sub_add_counts": (C.c_int, [_vp, C.c_int, _u32, _P(_i64)]),
+    "pc_sub_compare": (C.c_int, [_vp, C.c_double, C.c_double, _i64, _vp]),
+    "pc_sub_diff_get": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_int, _P(_i64)]),
+    "pc_sub_mapback": (C.c_int, [_vp, _vp, C.c_int]),
     "pc_select": (C.c_int, [_vp, _u32, _u32, C.c_int, _i64, _P(_i64)]),
     "pc_watch_threshold": (C.c_int, [_vp, _u32]),
     "pc_selected_get": (C.c_int, [_vp, _vp, C.c_int]),
@@ -329,6 +336,41 @@ class Context:
             check(lib.pc_dump_counts(self._h, min_count, max_count, keys.ctypes.data, counts.ctypes.data, n.value,
                                      PC_HOST, C.byref(n)), "pc_dump_counts")
         return keys, counts
+
+    # N1: subgenome extraction inner loop (polycracker.py:692-865)
+    def sub_begin(self, n_groups):
+        check(lib.pc_sub_begin(self._h, int(n_groups)), "pc_sub_begin")
+        self._sub_groups = int(n_groups)
+
+    def sub_add_counts(self, group, min_count):
+        """the current count table becomes subgenome `group`'s k-mer:count dictionary -> number of entries"""
+        n = _i64()
+        check(lib.pc_sub_add_counts(self._h, int(group), int(min_count), C.byref(n)), "pc_sub_add_counts")
+        return n.value
+
+    def sub_compare(self, ratio_threshold, default_value, sampling=1):
+        """compareKmers for the pending k -> number of differential k-mers per subgenome"""
+        n = np.zeros(PC_MAX_GROUPS, np.int64)
+        check(lib.pc_sub_compare(self._h, float(ratio_threshold), float(default_value), int(sampling), n.ctypes.data),
+              "pc_sub_compare")
+        return n[:self._sub_groups].copy()
+
+    def sub_diff(self, k, group):
+        """-> (keys uint64[n] ascending, counts uint32[n, n_groups]; 0 = absent from that subgenome's dictionary)"""
+        n = _i64()
+        check(lib.pc_sub_diff_get(self._h, int(k), int(group), None, None, PC_HOST, C.byref(n)), "pc_sub_diff_get")
+        keys = np.empty(n.value, np.uint64); counts = np.empty((n.value, self._sub_groups), np.uint32)
+        if n.value:
+            check(lib.pc_sub_diff_get(self._h, int(k), int(group), keys.ctypes.data, counts.ctypes.data, PC_HOST,
+                                      C.byref(n)), "pc_sub_diff_get")
+        return keys, counts
+
+    def sub_mapback(self, n_chunks):
+        """-> int32[n_chunks, n_groups]: distinct window starts per loaded chunk matched by each subgenome's
+        differential k-mers"""
+        out = np.zeros((int(n_chunks), self._sub_groups), np.int32)
+        check(lib.pc_sub_mapback(self._h, out.ctypes.data, PC_HOST), "pc_sub_mapback")
+        return out
 
     def partition(self, k, pb):
         """-> (bucket_off int64[2^pb + 1], device pointer of the bucket-sorted k-mers)"""

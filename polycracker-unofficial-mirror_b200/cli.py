@@ -1,12 +1,13 @@
 """`polycracker` console script: the reference's click group (polycracker/polycracker.py:51-54) with the hot-path
 sub-commands re-implemented on the GPU.  Option names, short flags and defaults are the reference's
 (polycracker.py:113-122, 174-179, 212-218, 241-249, 255-262, 299-316) so polycracker.nf and the README recipes call
-them unchanged.  Sub-commands outside the hot path (transform_plot, cluster, subgenomeExtraction, plots, ...) stay with
-the reference package.
+them unchanged.  `subgenomeExtraction` (scope row N1; options of polycracker.py:970-990) runs its count / compare /
+map-back loop on the GPU too.  Sub-commands outside these rows (transform_plot, cluster, plots, ...) stay with the
+reference package.
 """
 import click
 
-from . import stages
+from . import stages, subgenome
 from .binding import PolycrackerError
 
 CONTEXT_SETTINGS = dict(help_option_names=["-h", "--help"], max_content_width=90)
@@ -114,6 +115,36 @@ def generate_Kmer_Matrix(kmercount_path, genome, chunk_size, min_chunk_size, rem
          low_memory=low_memory, prefilter=prefilter, fasta_path=fasta_path, genome_split_name=genome_split_name,
          original_genome=original_genome, input_bed_file=input_bed_file, input_merged_bed_file=input_merged_bed_file,
          output_sparse_matrix=output_sparse_matrix, output_kmer_file=output_kmer_file, tfidf=tfidf)
+
+
+@polycracker.command(name="subgenomeExtraction")
+@click.option("-s", "--subgenome_folder", help="Subgenome folder where subgenome extraction is taking place. This should be the bootstrap_0 folder.", type=click.Path(exists=False))
+@click.option("-os", "--original_subgenome_path", help="One level up from subgenomeFolder. Final outputs are stored here.", type=click.Path(exists=False))
+@click.option("-p", "--fasta_path", default="./fasta_files/", help="Directory containing chunked polyploids fasta file", show_default=True, type=click.Path(exists=False))
+@click.option("-g", "--genome_name", help="Filename of chunked polyploid fasta.", type=click.Path(exists=False))
+@click.option("-go", "--original_genome", help="Filename of polyploid fasta; can be either original or chunked, just make sure original is set to 1 if using original genome.", type=click.Path(exists=False))
+@click.option("-bb", "--bb", default=1, help="Whether bbtools were used in generating blasted sam file (must be 1).", show_default=True)
+@click.option("-b", "--bootstrap", default=0, help="Number of times to bootstrap the subgenome extraction process.", show_default=True)
+@click.option("-i", "--iteration", default=0, help="Current iteration of bootstrapping process. Please set to 0, when initially beginning.", show_default=True)
+@click.option("-l", "--kmer_length", default="23,31", help="Length of kmers to find; can include multiple lengths if comma delimited (e.g. 23,25,27)", show_default=True)
+@click.option("-r", "--run_final", default=0, help="Turn this to 0 when starting the command.", show_default=True)
+@click.option("-o", "--original", default=0, help="Select 1 if trying to extract subgenomes based on original nonchunked genome.", show_default=True)
+@click.option("-m", "--blast_mem", default="100", help="Accepted for compatibility; ignored.", show_default=True)
+@click.option("-kl", "--kmer_low_count", default=100, help="Accepted for compatibility (unused by the reference here too).", show_default=True)
+@click.option("-dk", "--diff_kmer_threshold", default=20, help="A kmer is differential if its count in a subgenome divided by its count in any other subgenome exceeds this value.", show_default=True)
+@click.option("-u", "--unionbed_threshold", default="10,2", help="Two comma delimited values (absolute, ratio) used for binning regions into subgenomes.", show_default=True)
+@click.option("-ds", "--diff_sample_rate", default=1, help="If greater than one, keep every x-th differential kmer after threshold filtering.", show_default=True)
+@click.option("-kv", "--default_kmercount_value", default=3., help="Count used for a kmer that is not found in another subgenome's kmercount dictionary.", show_default=True)
+@click.option("-sl", "--search_length", default=13, help="Accepted for compatibility (bbmap seed length); ignored.", show_default=True)
+@click.option("-pm", "--perfect_mode", default=1, help="Perfect mode (must be 1: exact matching).", show_default=True)
+def subgenomeExtraction(subgenome_folder, original_subgenome_path, fasta_path, genome_name, original_genome, bb, bootstrap, iteration, kmer_length, run_final, original, blast_mem, kmer_low_count, diff_kmer_threshold, unionbed_threshold, diff_sample_rate, default_kmercount_value, search_length, perfect_mode):
+    """Extract subgenomes from genome, either chunked genome or original genome can be fed in as argument"""
+    _run(subgenome.subgenomeExtraction, subgenome_folder=subgenome_folder, original_subgenome_path=original_subgenome_path,
+         fasta_path=fasta_path, genome_name=genome_name, original_genome=original_genome, bb=bb, bootstrap=bootstrap,
+         iteration=iteration, kmer_length=kmer_length, run_final=run_final, original=original, blast_mem=blast_mem,
+         kmer_low_count=kmer_low_count, diff_kmer_threshold=diff_kmer_threshold, unionbed_threshold=unionbed_threshold,
+         diff_sample_rate=diff_sample_rate, default_kmercount_value=default_kmercount_value,
+         search_length=search_length, perfect_mode=perfect_mode)
 
 
 def main():

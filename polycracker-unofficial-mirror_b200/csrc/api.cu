@@ -39,8 +39,10 @@ int fail(int code, const char* fmt, ...) {
     } while (0)
 
 enum Stage { ST_H2D = 0, ST_PACK, ST_TABLE_INIT, ST_COUNT, ST_SELECT, ST_SORT, ST_REPTABLE, ST_PROBE,
-             ST_ROWSORT, ST_EMIT, ST_TFIDF, ST_D2H, ST_EXPORT, ST_MERGE, ST_PART_HIST, ST_PART_SCATTER, ST_N };
+             ST_ROWSORT, ST_EMIT, ST_TFIDF, ST_D2H, ST_EXPORT, ST_MERGE, ST_PART_HIST, ST_PART_SCATTER,
+             ST_SUB_DICT, ST_SUB_COMPARE, ST_SUB_MAPBACK, ST_N };
 static_assert(ST_N <= PC_N_STAGES, "stage table too small");
+static_assert(pc::kMaxGroups == PC_MAX_GROUPS && pc::kMaxSubK == PC_MAX_SUB_K, "header and kernels disagree");
 
 template <typename T>
 struct DevBuf {
@@ -65,7 +67,7 @@ struct pc_ctx {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint64_t zeroed_slots = 0;                  // slots of `table` zeroed by the pending side-stream memset
     int prezero = 0;                            // overlap the table memset with extract+scatter (measured: no gain)
-    int probe_bitmap = 0;                       // occupancy bitmap in front of the repeat table (measured: slower)
+    int probe_fp = -1;                          // fingerprint-first probing: -1 auto (table > 256 MB), 0 off, 1 on
     cudaEvent_t ev[ST_N][2];
     bool ev_used[ST_N];
     int64_t launches = 0;
@@ -89,7 +91,7 @@ struct pc_ctx {
     DevBuf<uint64_t> sel_a, sel_b; uint64_t* sel = nullptr; int64_t n_sel = 0;
     DevBuf<unsigned int> rs_hist;
     DevBuf<unsigned long long> d_counter;
-    DevBuf<pc::RepSlot> rtable; DevBuf<unsigned int> rocc; uint64_t rcap = 0;
+    DevBuf<pc::RepSlot> rtable; DevBuf<unsigned short> rfp; uint64_t rcap = 0;
     bool selected = false;
 
     // matrix
@@ -122,6 +124,25 @@ struct pc_ctx {
     uint32_t watch_low = 0; bool cross_valid = false; uint32_t cross_low = 0;
     DevBuf<uint64_t> cross_keys; DevBuf<unsigned long long> d_cross_n;
     int count_items = 2;                        // k-mers in flight per thread in the bucket kernel (2: 48 regs, best measured)
+
+    // N1 subgenome-extraction session (pc_sub_*): per-subgenome dictionaries of the k being compared, then per k the
+    // differential sets and their union mask table
+    struct SubDict { DevBuf<pc::RepSlot> table; uint64_t cap = 0; DevBuf<uint64_t> keys; DevBuf<uint32_t> counts; int64_t n = 0; bool set = false; };
+    struct SubLen { int k = 0; DevBuf<pc::RepSlot> mask; uint64_t cap = 0; DevBuf<uint64_t> diff_keys[pc::kMaxGroups];
+                    DevBuf<uint32_t> diff_counts[pc::kMaxGroups]; int64_t n_diff[pc::kMaxGroups] = {}; };
+    int sub_groups = 0, sub_k = 0, sub_n_len = 0;
+    SubDict sub_dict[pc::kMaxGroups];
+    SubLen sub_len[pc::kMaxSubK];
+    DevBuf<uint64_t> sub_tmp_a, sub_tmp_b; DevBuf<int> d_cov;
+    void sub_clear() {
+        for (auto& d : sub_dict) { d.table.release(); d.keys.release(); d.counts.release(); d.cap = 0; d.n = 0; d.set = false; }
+        for (auto& l : sub_len) {
+            l.mask.release(); l.cap = 0; l.k = 0;
+            for (int g = 0; g < pc::kMaxGroups; ++g) { l.diff_keys[g].release(); l.diff_counts[g].release(); l.n_diff[g] = 0; }
+        }
+        sub_tmp_a.release(); sub_tmp_b.release(); d_cov.release();
+        sub_groups = sub_k = sub_n_len = 0;
+    }
 };
 
 namespace {
@@ -182,12 +203,12 @@ int build_rep_table(pc_ctx* c) {
     if (c->rcap >= (1ull << 32)) return fail(PC_EINVAL, "repeat set of %lld k-mers is too large for the repeat table", (long long)c->n_sel);
     int rc = c->rtable.alloc(c->rcap);
     if (rc) return rc;
-    rc = c->rocc.alloc((c->rcap + 31) / 32 + 1);
+    rc = c->rfp.alloc(c->rcap + 8);
     if (rc) return rc;
     CU(cudaMemsetAsync(c->rtable.p, 0, c->rcap * sizeof(pc::RepSlot), c->stream));
-    CU(cudaMemsetAsync(c->rocc.p, 0, ((c->rcap + 31) / 32 + 1) * sizeof(unsigned int), c->stream));
+    CU(cudaMemsetAsync(c->rfp.p, 0, (c->rcap + 8) * sizeof(unsigned short), c->stream));
     if (c->n_sel > 0)
-        LAUNCH(c, pc::k_rep_build, blocks_for(c->n_sel, 256), 256, c->sel, c->n_sel, c->rtable.p, c->rcap, c->rocc.p);
+        LAUNCH(c, pc::k_rep_build, blocks_for(c->n_sel, 256), 256, c->sel, c->n_sel, c->rtable.p, c->rcap, c->rfp.p);
     return PC_OK;
 }
 
@@ -238,10 +259,11 @@ int pc_destroy(pc_ctx* c) {
     c->ascii.release(); c->d_word0.release(); c->d_begin.release(); c->d_len.release();
     c->words.release(); c->nmask.release(); c->table_keys.release(); c->table_counts.release(); c->d_stats.release();
     c->kbuf.release(); c->kstream.release(); c->d_part_hist.release(); c->d_seg.release(); c->cross_keys.release(); c->d_cross_n.release();
-    c->sel_a.release(); c->sel_b.release(); c->rs_hist.release(); c->d_counter.release(); c->rtable.release(); c->rocc.release();
+    c->sel_a.release(); c->sel_b.release(); c->rs_hist.release(); c->d_counter.release(); c->rtable.release(); c->rfp.release();
     c->d_chunk_row.release(); c->d_row_base.release(); c->d_row_cursor.release(); c->hits_a.release();
     c->hits_b.release(); c->d_row_nnz.release(); c->d_indptr.release(); c->d_indices.release();
     c->d_data.release(); c->d_idf.release(); c->d_tfidf.release(); c->d_df.release(); c->d_df_global.release();
+    c->sub_clear();
     for (int i = 0; i < ST_N; ++i) { cudaEventDestroy(c->ev[i][0]); cudaEventDestroy(c->ev[i][1]); }
     cudaStreamDestroy(c->own_stream);
     cudaStreamDestroy(c->aux_stream);
@@ -601,7 +623,7 @@ int pc_tune(pc_ctx* c, const char* key, int64_t value) {
         c->stream_valid = false;
     }
     else if (k == "prezero") c->prezero = (int)value;
-    else if (k == "probe_bitmap") c->probe_bitmap = (int)value;
+    else if (k == "probe_fp") c->probe_fp = (int)value;
     else if (k == "part_casfirst") c->part_casfirst = (int)value;
     else if (k == "part_minb") c->part_minb = (int)value;
     else if (k == "probe_batch") c->probe_batch = (int)value;
@@ -827,6 +849,140 @@ int pc_merge_counts(pc_ctx* c, const uint64_t* keys_dev, const uint32_t* counts_
     return PC_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- N1 subgenome extraction
+int pc_sub_begin(pc_ctx* c, int n_groups) {
+    int rc = use_device(c); if (rc) return rc;
+    if (n_groups < 1 || n_groups > pc::kMaxGroups)
+        return fail(PC_EINVAL, "n_groups = %d unsupported: 1..%d subgenomes per session", n_groups, pc::kMaxGroups);
+    CU(cudaStreamSynchronize(c->stream));
+    c->sub_clear();
+    c->sub_groups = n_groups;
+    return PC_OK;
+}
+
+int pc_sub_add_counts(pc_ctx* c, int group, uint32_t min_count, int64_t* n_kmers) {
+    int rc = use_device(c); if (rc) return rc;
+    if (c->sub_groups == 0) return fail(PC_ESTATE, "pc_sub_add_counts before pc_sub_begin");
+    if (!c->counted) return fail(PC_ESTATE, "pc_sub_add_counts before pc_count");
+    if (group < 0 || group >= c->sub_groups) return fail(PC_EINVAL, "group %d out of range (have %d)", group, c->sub_groups);
+    bool any = false;
+    for (int g = 0; g < c->sub_groups; ++g) any |= c->sub_dict[g].set;
+    if (any && c->sub_k != c->k)
+        return fail(PC_ESTATE, "dictionaries of k = %d are pending: call pc_sub_compare before counting k = %d", c->sub_k, c->k);
+    c->sub_k = c->k;
+    if (min_count == 0) min_count = 1;
+    pc_ctx::SubDict& d = c->sub_dict[group];
+    StageTimer t(c, ST_SUB_DICT);
+    int64_t n = 0;
+    rc = select_into(c, min_count, 0xFFFFFFFFu, nullptr, nullptr, 0, &n); if (rc) return rc;
+    rc = d.keys.alloc(std::max<int64_t>(n, 1)); if (rc) return rc;
+    rc = d.counts.alloc(std::max<int64_t>(n, 1)); if (rc) return rc;
+    int64_t n2 = 0;
+    rc = select_into(c, min_count, 0xFFFFFFFFu, d.keys.p, d.counts.p, n, &n2); if (rc) return rc;
+    if (n2 != n) return fail(PC_ESTATE, "count table changed while it was being read");
+    d.cap = std::max<uint64_t>(64, (uint64_t)n * 4);
+    if (d.cap >= (1ull << 32)) return fail(PC_EINVAL, "dictionary of %lld k-mers is too large", (long long)n);
+    rc = d.table.alloc(d.cap); if (rc) return rc;
+    CU(cudaMemsetAsync(d.table.p, 0, d.cap * sizeof(pc::RepSlot), c->stream));
+    if (n > 0) LAUNCH(c, pc::k_kv_build, blocks_for(n, 256), 256, d.keys.p, d.counts.p, n, d.table.p, d.cap);
+    d.n = n; d.set = true;
+    if (n_kmers) *n_kmers = n;
+    return PC_OK;
+}
+
+int pc_sub_compare(pc_ctx* c, double ratio_threshold, double default_value, int64_t sampling, int64_t* n_diff) {
+    int rc = use_device(c); if (rc) return rc;
+    const int G = c->sub_groups;
+    if (G == 0) return fail(PC_ESTATE, "pc_sub_compare before pc_sub_begin");
+    for (int g = 0; g < G; ++g)
+        if (!c->sub_dict[g].set) return fail(PC_ESTATE, "subgenome %d has no dictionary for k = %d", g, c->sub_k);
+    if (default_value == 0.0) return fail(PC_EINVAL, "default_kmercount_value = 0 divides by zero (the reference raises too)");
+    if (c->sub_n_len >= pc::kMaxSubK) return fail(PC_EINVAL, "more than %d k-mer lengths in one session", pc::kMaxSubK);
+    for (int q = 0; q < c->sub_n_len; ++q)
+        if (c->sub_len[q].k == c->sub_k) return fail(PC_EINVAL, "k = %d was already compared in this session", c->sub_k);
+    if (sampling < 1) sampling = 1;                            // polycracker.py:738-739
+    pc_ctx::SubLen& L = c->sub_len[c->sub_n_len];
+    L.k = c->sub_k;
+    StageTimer t(c, ST_SUB_COMPARE);
+    pc::GroupTables all{}; all.n = G;
+    for (int g = 0; g < G; ++g) { all.t[g] = c->sub_dict[g].table.p; all.cap[g] = c->sub_dict[g].cap; }
+    int64_t total = 0;
+    for (int g = 0; g < G; ++g) {
+        pc_ctx::SubDict& d = c->sub_dict[g];
+        pc::GroupTables others{}; others.n = 0;
+        for (int o = 0; o < G; ++o) if (o != g) { others.t[others.n] = all.t[o]; others.cap[others.n] = all.cap[o]; ++others.n; }
+        rc = c->sub_tmp_a.alloc(std::max<int64_t>(d.n, 1)); if (rc) return rc;
+        rc = c->sub_tmp_b.alloc(std::max<int64_t>(d.n, 1)); if (rc) return rc;
+        unsigned long long nd = 0;
+        if (d.n > 0) {
+            CU(cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned long long), c->stream));
+            LAUNCH(c, pc::k_diff_test, blocks_for(d.n, 256), 256, d.keys.p, d.counts.p, d.n, others, ratio_threshold,
+                   default_value, c->sub_tmp_a.p, c->d_counter.p);
+            CU(cudaMemcpyAsync(&nd, c->d_counter.p, sizeof nd, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+        }
+        int64_t n = (int64_t)nd;
+        uint64_t* sorted = nullptr;
+        rc = radix_sort_u64(c, c->sub_tmp_a.p, c->sub_tmp_b.p, n, 2 * L.k, &sorted); if (rc) return rc;
+        int64_t n_out = (n + sampling - 1) / sampling;         // every sampling-th survivor, in k-mer order
+        rc = L.diff_keys[g].alloc(std::max<int64_t>(n_out, 1)); if (rc) return rc;
+        rc = L.diff_counts[g].alloc(std::max<int64_t>(n_out * G, 1)); if (rc) return rc;
+        if (n_out > 0) {
+            LAUNCH(c, pc::k_stride_gather, blocks_for(n_out, 256), 256, sorted, n_out, sampling, L.diff_keys[g].p);
+            LAUNCH(c, pc::k_diff_counts, blocks_for(n_out, 256), 256, L.diff_keys[g].p, n_out, all, L.diff_counts[g].p);
+        }
+        L.n_diff[g] = n_out; total += n_out;
+        if (n_diff) n_diff[g] = n_out;
+    }
+    L.cap = std::max<uint64_t>(64, (uint64_t)total * 4);
+    if (L.cap >= (1ull << 32)) return fail(PC_EINVAL, "%lld differential k-mers are too many for the mask table", (long long)total);
+    rc = L.mask.alloc(L.cap); if (rc) return rc;
+    CU(cudaMemsetAsync(L.mask.p, 0, L.cap * sizeof(pc::RepSlot), c->stream));
+    for (int g = 0; g < G; ++g)
+        if (L.n_diff[g] > 0)
+            LAUNCH(c, pc::k_mask_build, blocks_for(L.n_diff[g], 256), 256, L.diff_keys[g].p, L.n_diff[g], 1 << g, L.mask.p, L.cap);
+    CU(cudaStreamSynchronize(c->stream));
+    for (int g = 0; g < G; ++g) {                              // the dictionaries of this k are done
+        pc_ctx::SubDict& d = c->sub_dict[g];
+        d.table.release(); d.keys.release(); d.counts.release(); d.cap = 0; d.n = 0; d.set = false;
+    }
+    ++c->sub_n_len;
+    return PC_OK;
+}
+
+int pc_sub_diff_get(pc_ctx* c, int k, int group, uint64_t* keys, uint32_t* counts, int loc, int64_t* n) {
+    int rc = use_device(c); if (rc) return rc;
+    if (group < 0 || group >= c->sub_groups) return fail(PC_EINVAL, "group %d out of range (have %d)", group, c->sub_groups);
+    for (int q = 0; q < c->sub_n_len; ++q) {
+        pc_ctx::SubLen& L = c->sub_len[q];
+        if (L.k != k) continue;
+        if (n) *n = L.n_diff[group];
+        if (keys) { rc = copy_out(c, keys, L.diff_keys[group].p, L.n_diff[group] * sizeof(uint64_t), loc); if (rc) return rc; }
+        if (counts) { rc = copy_out(c, counts, L.diff_counts[group].p, L.n_diff[group] * c->sub_groups * sizeof(uint32_t), loc); if (rc) return rc; }
+        return PC_OK;
+    }
+    return fail(PC_ESTATE, "k = %d has not been compared in this session", k);
+}
+
+int pc_sub_mapback(pc_ctx* c, int32_t* coverage, int loc) {
+    int rc = use_device(c); if (rc) return rc;
+    if (c->sub_groups == 0 || c->sub_n_len == 0) return fail(PC_ESTATE, "pc_sub_mapback before pc_sub_compare");
+    if (!c->loaded) return fail(PC_ESTATE, "pc_sub_mapback before pc_load_sequences");
+    if (!coverage) return fail(PC_EINVAL, "coverage is null");
+    const int G = c->sub_groups;
+    rc = c->d_cov.alloc(std::max<int64_t>(c->n_chunks * G, 1)); if (rc) return rc;
+    {
+        StageTimer t(c, ST_SUB_MAPBACK);
+        CU(cudaMemsetAsync(c->d_cov.p, 0, std::max<int64_t>(c->n_chunks * G, 1) * sizeof(int), c->stream));
+        pc::SubKSet ks{}; ks.n = c->sub_n_len;
+        for (int q = 0; q < ks.n; ++q) { ks.t[q] = c->sub_len[q].mask.p; ks.cap[q] = c->sub_len[q].cap; ks.k[q] = c->sub_len[q].k; }
+        if (c->n_words > 0)
+            LAUNCH(c, pc::k_probe_groups<4>, blocks_for(c->n_words, 256), 256, c->words.p, c->nmask.p, c->n_words, ks,
+                   c->d_word0.p, c->n_chunks, G, c->d_cov.p);
+    }
+    return copy_out(c, coverage, c->d_cov.p, (size_t)c->n_chunks * G * sizeof(int32_t), loc);
+}
+
 // ---------------------------------------------------------------------------------------------- K4
 int pc_select(pc_ctx* c, uint32_t low, uint32_t high, int use_high, int64_t sampling, int64_t* n_selected) {
     int rc = use_device(c); if (rc) return rc;
@@ -1014,16 +1170,18 @@ int pc_build_matrix(pc_ctx* c, const int32_t* chunk_row, int64_t n_rows, int64_t
             bool use_stream = c->stream_valid && c->stream_k == k && c->probe_mode != 0;
             if (c->probe_mode == 1 && !use_stream) return fail(PC_ESTATE, "probe_mode=1 needs the k-mer stream of a partitioned pc_count");
             unsigned int grid = blocks_for(c->n_words, 256);
+            // fingerprint-first walk when the 16 B/slot table is far beyond L2 (measured: +17 % at 43 MB, -9 % at 650 MB)
+            const bool use_fp = c->probe_fp == 1 || (c->probe_fp < 0 && c->rcap * sizeof(pc::RepSlot) > (size_t)(256ull << 20));
             if (use_stream) {
                 if (c->probe_batch == 4)
                     LAUNCH(c, (pc::k_probe_stream<4>), grid, 256, c->kstream.p, c->n_words, c->d_word0.p, c->n_chunks,
-                           c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, c->probe_bitmap ? c->rocc.p : nullptr, c->hits_a.p, c->d_row_cursor.p);
+                           c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, use_fp ? c->rfp.p : nullptr, c->hits_a.p, c->d_row_cursor.p);
                 else
                     LAUNCH(c, (pc::k_probe_stream<8>), grid, 256, c->kstream.p, c->n_words, c->d_word0.p, c->n_chunks,
-                           c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, c->probe_bitmap ? c->rocc.p : nullptr, c->hits_a.p, c->d_row_cursor.p);
+                           c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, use_fp ? c->rfp.p : nullptr, c->hits_a.p, c->d_row_cursor.p);
             } else {
                 LAUNCH(c, (pc::k_probe<8>), grid, 256, c->words.p, c->nmask.p, c->n_words, k, c->d_word0.p, c->n_chunks,
-                       c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, c->probe_bitmap ? c->rocc.p : nullptr, c->hits_a.p, c->d_row_cursor.p);
+                       c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, use_fp ? c->rfp.p : nullptr, c->hits_a.p, c->d_row_cursor.p);
             }
         }
     }

@@ -31,6 +31,11 @@ __device__ __forceinline__ uint64_t rep_slot(uint64_t key, uint64_t rcap) {
     return __umul64hi(mix64(key ^ 0x9E3779B97F4A7C15ull), rcap);
 }
 
+// 16-bit fingerprint of a k-mer (never 0), from a third independent multiplicative hash
+__device__ __forceinline__ unsigned short fp_of(uint64_t key) {
+    return (unsigned short)(((key * 0xC2B2AE3D27D4EB4Full) >> 48) | 1ull);
+}
+
 // ------------------------------------------------------------------------------------------------ tables
 // Count table (K3): open addressing, linear probing, structure of arrays.  keys[s] = ~kmer so that a zeroed table is
 // empty (the all-ones pattern is never a canonical-min k-mer: its reverse complement, all A, is smaller);
@@ -968,7 +973,7 @@ k_stride_gather(const uint64_t* __restrict__ src, int64_t n_out, int64_t stride,
 // ------------------------------------------------------------------------------------------------ K5 repeat table + probe
 __global__ void __launch_bounds__(256)
 k_rep_build(const uint64_t* __restrict__ sorted_keys, int64_t n, RepSlot* __restrict__ table, uint64_t capacity,
-            unsigned int* __restrict__ occ /* one bit per slot, zeroed */)
+            unsigned short* __restrict__ fp /* one fingerprint per slot, zeroed = empty */)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -977,7 +982,7 @@ k_rep_build(const uint64_t* __restrict__ sorted_keys, int64_t n, RepSlot* __rest
     uint64_t slot = rep_slot(key, capacity);
     for (;;) {                                               // keys are unique and capacity >= 2n: terminates
         unsigned long long cur = atomicCAS(&table[slot].skey, 0ull, skey);
-        if (cur == 0ull) { table[slot].col = (int)i; atomicOr(&occ[slot >> 5], 1u << (slot & 31)); break; }
+        if (cur == 0ull) { table[slot].col = (int)i; fp[slot] = fp_of(key); break; }
         if (++slot == capacity) slot = 0;
     }
 }
@@ -998,7 +1003,7 @@ __global__ void __launch_bounds__(256)
 k_probe(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, int64_t n_words, int k,
         const int64_t* __restrict__ chunk_word0, int64_t n_chunks, const int32_t* __restrict__ chunk_row,
         const int64_t* __restrict__ row_hit_base, const RepSlot* __restrict__ rtable, uint64_t rcap,
-        const unsigned int* __restrict__ occ, int32_t* __restrict__ hits, unsigned int* __restrict__ row_cursor)
+        const unsigned short* __restrict__ fp, int32_t* __restrict__ hits, unsigned int* __restrict__ row_cursor)
 {
     int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int lane = threadIdx.x & 31;
@@ -1034,20 +1039,38 @@ k_probe(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, 
                 slot[j] = rep_slot(key, rcap);
                 if (b < 31) r.step(b);
             }
-            // optional occupancy bitmap (1 bit per slot): ~3 of 4 windows end here without touching the table
-            if (occ != nullptr) {
-                unsigned int ob[BATCH];
+            if (fp != nullptr) {
+                // fingerprint-first probing (large repeat sets): the walk reads 2-byte fingerprints (16 slots per
+                // sector, an array 8x smaller than the table, so it stays in L2 when the table does not) and touches a
+                // 16-byte slot only when the fingerprint matches
+                unsigned short f[BATCH];
 #pragma unroll
-                for (int j = 0; j < BATCH; ++j) ob[j] = ((vmask >> j) & 1u) ? __ldg(occ + (slot[j] >> 5)) : 0u;
+                for (int j = 0; j < BATCH; ++j) f[j] = ((vmask >> j) & 1u) ? __ldg(fp + slot[j]) : (unsigned short)0;
 #pragma unroll
-                for (int j = 0; j < BATCH; ++j) if (!((ob[j] >> (slot[j] & 31)) & 1u)) vmask &= ~(1u << j);
+                for (int j = 0; j < BATCH; ++j) {
+                    cols[j] = 0;
+                    if (!((vmask >> j) & 1u)) continue;
+                    const unsigned short mine = fp_of(~skey[j]);
+                    unsigned short ff = f[j];
+                    uint64_t s = slot[j];
+                    while (ff != 0) {
+                        if (ff == mine) {
+                            uint4 c2 = __ldg(reinterpret_cast<const uint4*>(rtable + s));
+                            unsigned long long ck = ((unsigned long long)c2.y << 32) | c2.x;
+                            if (ck == skey[j]) { cols[j] = (int)c2.z; hmask |= 1u << j; break; }
+                        }
+                        if (++s == rcap) s = 0;
+                        ff = __ldg(fp + s);
+                    }
+                }
+                vmask = 0;                                    // done: skip the direct walk below
             }
 #pragma unroll
             for (int j = 0; j < BATCH; ++j)
                 cur[j] = ((vmask >> j) & 1u) ? __ldg(reinterpret_cast<const uint4*>(rtable + slot[j])) : make_uint4(0, 0, 0, 0);
 #pragma unroll
             for (int j = 0; j < BATCH; ++j) {
-                cols[j] = 0;
+                if (fp == nullptr) cols[j] = 0;
                 if (!((vmask >> j) & 1u)) continue;
                 unsigned long long ck = ((unsigned long long)cur[j].y << 32) | cur[j].x;
                 int col = (int)cur[j].z;
@@ -1096,7 +1119,7 @@ __global__ void __launch_bounds__(256)
 k_probe_stream(const uint64_t* __restrict__ stream, int64_t n_words,
                const int64_t* __restrict__ chunk_word0, int64_t n_chunks, const int32_t* __restrict__ chunk_row,
                const int64_t* __restrict__ row_hit_base, const RepSlot* __restrict__ rtable, uint64_t rcap,
-               const unsigned int* __restrict__ occ, int32_t* __restrict__ hits, unsigned int* __restrict__ row_cursor)
+               const unsigned short* __restrict__ fp, int32_t* __restrict__ hits, unsigned int* __restrict__ row_cursor)
 {
     int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int lane = threadIdx.x & 31;
@@ -1127,20 +1150,38 @@ k_probe_stream(const uint64_t* __restrict__ stream, int64_t n_words,
                 skey[j] = ~key;
                 slot[j] = rep_slot(key, rcap);
             }
-            // optional occupancy bitmap (1 bit per slot): ~3 of 4 windows end here without touching the table
-            if (occ != nullptr) {
-                unsigned int ob[BATCH];
+            if (fp != nullptr) {
+                // fingerprint-first probing (large repeat sets): the walk reads 2-byte fingerprints (16 slots per
+                // sector, an array 8x smaller than the table, so it stays in L2 when the table does not) and touches a
+                // 16-byte slot only when the fingerprint matches
+                unsigned short f[BATCH];
 #pragma unroll
-                for (int j = 0; j < BATCH; ++j) ob[j] = ((vmask >> j) & 1u) ? __ldg(occ + (slot[j] >> 5)) : 0u;
+                for (int j = 0; j < BATCH; ++j) f[j] = ((vmask >> j) & 1u) ? __ldg(fp + slot[j]) : (unsigned short)0;
 #pragma unroll
-                for (int j = 0; j < BATCH; ++j) if (!((ob[j] >> (slot[j] & 31)) & 1u)) vmask &= ~(1u << j);
+                for (int j = 0; j < BATCH; ++j) {
+                    cols[j] = 0;
+                    if (!((vmask >> j) & 1u)) continue;
+                    const unsigned short mine = fp_of(~skey[j]);
+                    unsigned short ff = f[j];
+                    uint64_t s = slot[j];
+                    while (ff != 0) {
+                        if (ff == mine) {
+                            uint4 c2 = __ldg(reinterpret_cast<const uint4*>(rtable + s));
+                            unsigned long long ck = ((unsigned long long)c2.y << 32) | c2.x;
+                            if (ck == skey[j]) { cols[j] = (int)c2.z; hmask |= 1u << j; break; }
+                        }
+                        if (++s == rcap) s = 0;
+                        ff = __ldg(fp + s);
+                    }
+                }
+                vmask = 0;                                    // done: skip the direct walk below
             }
 #pragma unroll
             for (int j = 0; j < BATCH; ++j)
                 cur[j] = ((vmask >> j) & 1u) ? __ldg(reinterpret_cast<const uint4*>(rtable + slot[j])) : make_uint4(0, 0, 0, 0);
 #pragma unroll
             for (int j = 0; j < BATCH; ++j) {
-                cols[j] = 0;
+                if (fp == nullptr) cols[j] = 0;
                 if (!((vmask >> j) & 1u)) continue;
                 unsigned long long ck = ((unsigned long long)cur[j].y << 32) | cur[j].x;
                 int col = (int)cur[j].z;
@@ -1396,6 +1437,177 @@ k_tfidf(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
     double nrm = norm_s;
     if (nrm == 0.0) return;
     for (int64_t i = beg + t; i < end; i += THREADS) out[i] = (float)((double)out[i] / nrm);
+}
+
+// ------------------------------------------------------------------------------------------------ N1 subgenome extraction
+// Row N1 of the scope table (polycracker.py:692-865): per-subgenome k-mer dictionaries, the differential-k-mer ratio
+// test, and the map-back of the differential k-mers onto every chunk.  All dictionaries are RepSlot tables (key -> int).
+constexpr int kMaxGroups = 8;                                  // subgenomes per session (one mask byte per k-mer)
+constexpr int kMaxSubK = 8;                                    // k-mer lengths per session (reference default: 23,31)
+
+struct GroupTables { const RepSlot* t[kMaxGroups]; uint64_t cap[kMaxGroups]; int n; };
+
+// value stored for `key`, 0 when absent (dictionary values are counts >= 1 or non-empty masks)
+__device__ __forceinline__ int kv_find(const RepSlot* __restrict__ table, uint64_t cap, uint64_t key)
+{
+    if (cap == 0) return 0;
+    const unsigned long long skey = ~key;
+    uint64_t s = rep_slot(key, cap);
+    for (;;) {
+        uint4 c = __ldg(reinterpret_cast<const uint4*>(table + s));
+        unsigned long long ck = ((unsigned long long)c.y << 32) | c.x;
+        if (ck == 0ull) return 0;
+        if (ck == skey) return (int)c.z;
+        if (++s == cap) s = 0;
+    }
+}
+
+// kmercounttodict (polycracker.py:722-733): unique keys, value = count
+__global__ void __launch_bounds__(256)
+k_kv_build(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ vals, int64_t n,
+           RepSlot* __restrict__ table, uint64_t cap)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t key = keys[i];
+    unsigned long long skey = ~key;
+    uint64_t s = rep_slot(key, cap);
+    for (;;) {
+        unsigned long long cur = atomicCAS(&table[s].skey, 0ull, skey);
+        if (cur == 0ull) { table[s].col = (int)vals[i]; break; }
+        if (++s == cap) s = 0;
+    }
+}
+
+// compareKmers (polycracker.py:735-783): a k-mer of this subgenome is differential when its count divided by the count
+// in ANY other subgenome exceeds the threshold.  The reference is Python 2: int / int floors when the other dictionary
+// holds the k-mer (pc.py:765, 778), and is a float division by default_kmercount_value (a float) when it does not.
+__global__ void __launch_bounds__(256)
+k_diff_test(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, int64_t n, GroupTables others,
+            double ratio_threshold, double default_value, uint64_t* __restrict__ out, unsigned long long* counter)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t key = keys[i];
+    uint32_t v1 = counts[i];
+    bool pass = false;
+    for (int o = 0; o < others.n; ++o) {
+        int v2 = kv_find(others.t[o], others.cap[o], key);
+        if (v2 > 0) pass |= (double)(v1 / (uint32_t)v2) > ratio_threshold;
+        else pass |= ((double)v1 / default_value) > ratio_threshold;
+    }
+    if (pass) out[atomicAdd(counter, 1ull)] = key;
+}
+
+// header values of `>kmer.val1.others` (pc.py:767, 781): the count of each differential k-mer in every subgenome
+__global__ void __launch_bounds__(256)
+k_diff_counts(const uint64_t* __restrict__ keys, int64_t n, GroupTables all, uint32_t* __restrict__ out)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t key = keys[i];
+    for (int g = 0; g < all.n; ++g) out[i * all.n + g] = (uint32_t)kv_find(all.t[g], all.cap[g], key);
+}
+
+// union of the differential sets: key -> bit mask of the subgenomes it is differential for
+__global__ void __launch_bounds__(256)
+k_mask_build(const uint64_t* __restrict__ keys, int64_t n, int bit, RepSlot* __restrict__ table, uint64_t cap)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint64_t key = keys[i];
+    unsigned long long skey = ~key;
+    uint64_t s = rep_slot(key, cap);
+    for (;;) {
+        unsigned long long cur = atomicCAS(&table[s].skey, 0ull, skey);
+        if (cur == 0ull || cur == skey) { atomicOr(&table[s].col, bit); break; }
+        if (++s == cap) s = 0;
+    }
+}
+
+struct SubKSet { const RepSlot* t[kMaxSubK]; uint64_t cap[kMaxSubK]; int k[kMaxSubK]; int n; };
+
+// writeBlast + blast2bed3 (polycracker.py:786-865): bbmap perfectmode reports every exact occurrence (either strand) of
+// every differential k-mer; blast2bed3 turns each into the 1-base interval at its leftmost position and `bedtools
+// coverage` reports, per chunk, the number of bases covered at least once (column 6 of the 4-column windows) -- i.e.
+// the number of DISTINCT window starts where a differential k-mer of that subgenome (of any of the lengths) matches.
+// One thread owns the 32 window starts of one packed word for every k, so the union over lengths is a register OR.
+template <int BATCH>
+__global__ void __launch_bounds__(256)
+k_probe_groups(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, int64_t n_words, SubKSet ks,
+               const int64_t* __restrict__ chunk_word0, int64_t n_chunks, int n_groups, int* __restrict__ coverage)
+{
+    int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int lane = threadIdx.x & 31;
+    WordPair p = load_word_pair(words, nmask, w, n_words);
+    int64_t w_lane0 = w - lane;
+    if (w_lane0 >= n_words) return;
+    bool lane_on = w < n_words && p.m0 != 0xFFFFFFFFu;
+    int64_t chunk = -1;
+    if (lane_on) chunk = chunk_of_word(chunk_word0, n_chunks, w, w_lane0);
+    unsigned int on_mask = __ballot_sync(0xFFFFFFFFu, lane_on);
+    if (on_mask == 0u) return;
+    int64_t chunk0 = __shfl_sync(0xFFFFFFFFu, chunk, __ffs(on_mask) - 1);
+    bool uniform = __all_sync(0xFFFFFFFFu, !lane_on || chunk == chunk0);
+
+    unsigned int hit[kMaxGroups];                             // bit b of hit[g]: window start b matched subgenome g
+#pragma unroll
+    for (int g = 0; g < kMaxGroups; ++g) hit[g] = 0u;
+    if (lane_on) {
+#pragma unroll 1
+        for (int q = 0; q < ks.n; ++q) {
+            const RepSlot* __restrict__ table = ks.t[q];
+            const uint64_t cap = ks.cap[q];
+            if (cap == 0) continue;
+            Roller r;
+            r.init(p.w0, p.w1, p.m0, p.m1, ks.k[q]);
+#pragma unroll 1
+            for (int b0 = 0; b0 < 32; b0 += BATCH) {
+                unsigned long long skey[BATCH]; uint64_t slot[BATCH]; uint4 cur[BATCH];
+                unsigned int vmask = 0;
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) {
+                    int b = b0 + j;
+                    uint64_t key = r.canonical();
+                    vmask |= (unsigned int)r.valid(b) << j;
+                    skey[j] = ~key;
+                    slot[j] = rep_slot(key, cap);
+                    if (b < 31) r.step(b);
+                }
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j)
+                    cur[j] = ((vmask >> j) & 1u) ? __ldg(reinterpret_cast<const uint4*>(table + slot[j])) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) {
+                    if (!((vmask >> j) & 1u)) continue;
+                    unsigned long long ck = ((unsigned long long)cur[j].y << 32) | cur[j].x;
+                    unsigned int m = cur[j].z;
+                    uint64_t s = slot[j];
+                    while (ck != 0ull && ck != skey[j]) {
+                        if (++s == cap) s = 0;
+                        uint4 c2 = __ldg(reinterpret_cast<const uint4*>(table + s));
+                        ck = ((unsigned long long)c2.y << 32) | c2.x; m = c2.z;
+                    }
+                    if (ck != 0ull) {
+#pragma unroll
+                        for (int g = 0; g < kMaxGroups; ++g) hit[g] |= ((m >> g) & 1u) << (b0 + j);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int g = 0; g < kMaxGroups; ++g) {
+        if (g >= n_groups) break;
+        int cnt = __popc(hit[g]);
+        if (uniform) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+            if (lane == 0 && cnt) atomicAdd(&coverage[chunk0 * n_groups + g], cnt);
+        } else if (cnt) {
+            atomicAdd(&coverage[chunk * n_groups + g], cnt);
+        }
+    }
 }
 
 }  // namespace pc

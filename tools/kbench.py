@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--what", default="count")
     ap.add_argument("--variants", default="")
     ap.add_argument("--reps", type=int, default=2)
+    ap.add_argument("--low", type=int, default=30, help="repeat threshold for --what matrix")
     a = ap.parse_args()
     import torch
     p = synth.make_params(20260002, a.genome_size)
@@ -73,7 +74,7 @@ def main():
                     ctx.count(a.k)
             best = None
             for _ in range(a.reps):
-                n_sel = ctx.select(30)
+                n_sel = ctx.select(a.low)
                 nnz = ctx.build_matrix(chunk_row, len(scaffolds))
                 ctx.tfidf(len(scaffolds))
                 t = ctx.timings()
