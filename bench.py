@@ -33,7 +33,7 @@ WORKLOAD = "cfg2_500Mbp_allotetraploid"
 FALLBACK_HBM_GBS = 6650.0
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
 # capture of this workload (profiles/); None until a capture of the current kernel exists
-NCU_TRAFFIC = {"K3_count": 18.126e9}   # profiles/r01_ncu_full_all_kernels_final_details.csv: 11.932 GB read + 6.194 GB written
+NCU_TRAFFIC = {}                      # filled from the committed ncu capture of the current kernels (profiles/), per launch
 
 
 def parse_args():
@@ -397,11 +397,16 @@ def run_b200_arm(args):
     st = last_resident.stats
     G = sum(int((e - b) // 32 + 1) for b, e in zip(begins.tolist(), ends.tolist())) * 32
     T, cap, Ds, nnz, R = st["valid_windows"], info["capacity"], st["n_selected"], st["nnz"], st["n_rows"]
+    detail = ctx.count_detail()
+    # K4 scans the count result: 12 B x table slots, or 12 B x list entries when the shared-memory count left a
+    # compact (k-mer, count) list instead of a table
+    scan_units = detail["kept"] if detail["kind"] == "list" else cap
+    k3_ms = stage_ms["part_hist"] + stage_ms["part_scatter"] + stage_ms["part2"] + stage_ms["table_init"] + stage_ms["count"]
     model = {
         "K1_pack": (1.375 * G, stage_ms["pack"]),
-        "K3_extract+scatter": (0.375 * G, stage_ms["part_hist"] + stage_ms["part_scatter"]),
+        "K3_partition(extract,scatter,level2)": (0.375 * G, stage_ms["part_hist"] + stage_ms["part_scatter"] + stage_ms["part2"]),
         "K3_count": (24.0 * T, stage_ms["count"]),
-        "K4_select+sort": (12.0 * cap + 12.0 * Ds, stage_ms["table_init"] + stage_ms["select"] + stage_ms["sort"] + stage_ms["rep_table"]),
+        "K4_select+sort": (12.0 * scan_units + 12.0 * Ds, stage_ms["select"] + stage_ms["sort"] + stage_ms["rep_table"]),
         "K5_probe": (0.375 * G + 12.0 * T + 8.0 * nnz, stage_ms["probe"]),
         "K6_rows_to_csr": (16.0 * nnz + 8.0 * R, stage_ms["row_sort"] + stage_ms["emit"]),
         "K7_tfidf": (12.0 * nnz + 4.0 * Ds, stage_ms["tfidf"]),
@@ -410,18 +415,27 @@ def run_b200_arm(args):
     for name, (nbytes, ms) in model.items():
         gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         kernels[name] = {"algorithmic_bytes": nbytes, "ms": ms, "achieved_gbs": gbs, "frac": gbs / peak}
-    dom = max(kernels, key=lambda n: kernels[n]["ms"])
+    dom = max((n for n in kernels if not n.startswith("K3_partition")), key=lambda n: kernels[n]["ms"])
     d = kernels[dom]
     path_bytes = sum(v[0] for v in model.values())
-    roofline = {"bound": "hbm", "kernel": {"K3_count": "k_count_part (bucket count)"}.get(dom, dom), "achieved": d["achieved_gbs"],
+    k3_bytes = 0.375 * G + 24.0 * T
+    kernels["K3_whole(partition+count)"] = {"algorithmic_bytes": k3_bytes, "ms": k3_ms,
+                                            "achieved_gbs": k3_bytes / (k3_ms * 1e-3) / 1e9 if k3_ms > 0 else 0.0,
+                                            "frac": (k3_bytes / (k3_ms * 1e-3) / 1e9 / peak) if k3_ms > 0 else 0.0}
+    count_kernel = "k_count_smem (shared-memory sub-bucket count)" if detail["kind"] == "list" else "k_count_part (bucket count)"
+    roofline = {"bound": "hbm", "kernel": {"K3_count": count_kernel, "K5_probe": "k_probe_stream (repeat-table probe)"}.get(dom, dom),
+                "achieved": d["achieved_gbs"],
                 "peak": peak, "unit": "GB/s", "frac": d["frac"], "traffic": NCU_TRAFFIC.get(dom), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": d["algorithmic_bytes"], "launch_ms": d["ms"],
                 "whole_path": {"algorithmic_bytes": path_bytes, "ms": ms_per_step,
                                "achieved_gbs": path_bytes / (ms_per_step * 1e-3) / 1e9,
                                "frac": path_bytes / (ms_per_step * 1e-3) / 1e9 / peak},
                 "per_kernel": kernels, "stage_ms": stage_ms,
-                "model": "SURVEY.md 8d per-unit bytes x units of this launch, per rank; the timed kernel is "
-                         "L2-sector/atomic bound, not HBM-stream bound (profiles/)"}
+                "count": detail,
+                "model": "SURVEY.md 8d per-unit bytes x units of this launch, per rank (K3 = 0.375 G + 24 T is split: the "
+                         "count kernel owns the 24 T, the partition passes the packed-genome read; K3_whole puts the whole "
+                         "K3 model over all of its passes).  The probe and the count are L2 / shared-memory-atomic bound, "
+                         "not HBM-stream bound (profiles/)"}
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
@@ -438,8 +452,9 @@ def run_b200_arm(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "genome_bases": genome_bases, "bases_per_gpu": per_gpu, "k": k,
                        "chunk_size": chunk, "kmer_low_count": low, "n_subgenomes": cfg["n_subgenomes"],
-                       "l2_policy": "inputs larger than L2 (ASCII %.0f MB, count table %.1f GB per rank)" % (
-                           local_bases / 1e6, info["table_bytes"] / 1e9),
+                       "l2_policy": "inputs larger than L2 (ASCII %.0f MB, k-mer stream %.1f GB, count %s %.1f GB per rank)" % (
+                           local_bases / 1e6, 8.0 * T / 1e9, "buffers" if detail["kind"] == "list" else "table",
+                           info["table_bytes"] / 1e9),
                        "parallelism": "chunks sharded over %d rank(s); all-to-all of (kmer,count) by owner, "
                                       "all-gather of the repeat set, all-reduce of df" % world},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),

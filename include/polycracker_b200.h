@@ -77,6 +77,13 @@ int pc_packed_get(pc_ctx* ctx, uint64_t* words, uint32_t* nmask, int64_t* chunk_
 int pc_count(pc_ctx* ctx, int k, int64_t capacity);
 /* info[0]=capacity info[1]=distinct k-mers info[2]=valid windows info[3]=table bytes info[4]=max probe length */
 int pc_count_info(pc_ctx* ctx, int64_t info[8]);
+/* how the last count is held.  detail[0] = 0: global open-addressing table; 1: compact (k-mer, count) list produced by
+ * the shared-memory count (two-level radix partition, one shared-memory table per sub-bucket; pc_tune part_mode 2 or
+ * auto).  For the list: detail[1] = entries, detail[2] = lowest count kept (pc_tune keep_min: kmercountexact only ever
+ * dumps mincount=3, polycracker.py:199, so k-mers below it never have to leave the SM), detail[3] = sub-buckets,
+ * detail[4] = sub-buckets per level-1 bucket, detail[5] = sub-buckets re-counted through a global table because their
+ * distinct k-mers did not fit the shared-memory table. */
+int pc_count_detail(pc_ctx* ctx, int64_t detail[8]);
 /* dump (kmer, count) with min_count <= count <= max_count (the .kcount file: `mincount=3` for k<=31,
  * polycracker.py:199).  keys == NULL -> only *n is written.  Unordered, like the tools' dumps. */
 int pc_dump_counts(pc_ctx* ctx, uint32_t min_count, uint32_t max_count,
@@ -182,7 +189,8 @@ int pc_release(pc_ctx* ctx, int what);
 /* ---- measurement ------------------------------------------------------------------------------------------
  * CUDA-event time (ms) of the last run of each stage on the ctx stream.  Index: 0 h2d, 1 pack, 2 table-init,
  * 3 count, 4 select(scan), 5 sort, 6 repeat-table, 7 probe, 8 row-sort, 9 emit, 10 tfidf, 11 d2h, 12 export, 13 merge,
- * 14 bucket histogram, 15 bucket scatter, 16 subgenome dictionary, 17 subgenome compare, 18 subgenome map-back.
+ * 14 bucket histogram, 15 bucket scatter, 16 subgenome dictionary, 17 subgenome compare, 18 subgenome map-back,
+ * 19 level-2 histogram + scatter of the shared-memory count.
  * launches: kernels launched by this ctx since the last pc_reset_counters. */
 #define PC_N_STAGES 20
 int pc_timings(pc_ctx* ctx, float ms[PC_N_STAGES]);
@@ -190,7 +198,9 @@ int pc_launch_count(pc_ctx* ctx, int64_t* launches);
 int pc_reset_counters(pc_ctx* ctx);
 /* kernel tunables (measurement / tuning only; defaults are the shipped configuration):
  * count_batch {4,8,16}, count_minb {2,3,4}, count_mode {0 load-first, 1 prefetch-ahead, 2 CAS-first} (direct table);
- * part_mode {-1 auto, 0 direct, 1 partitioned}, part_mbytes, part_blocks, part_casfirst, count_items {2,4};
+ * part_mode {-1 auto, 0 direct global table, 1 L2-partitioned global table, 2 shared-memory count}, part_mbytes,
+ * part_blocks, part_casfirst, count_items {2,4}; keep_min (shared-memory count: lowest count kept, default 1),
+ * smem_target (mean k-mers per sub-bucket), smem_variant {0..4: slots x threads x k-mers in flight};
  * probe_mode {-1 auto, 0 roller, 1 stream}, probe_batch {4,8}, rep_load_inv; table_load_pct (5..95). */
 int pc_tune(pc_ctx* ctx, const char* key, int64_t value);
 

@@ -14,7 +14,7 @@ PC_HOST, PC_DEVICE = 0, 1
 PC_N_STAGES = 20
 STAGE_NAMES = ["h2d", "pack", "table_init", "count", "select", "sort", "rep_table", "probe", "row_sort", "emit",
                "tfidf", "d2h", "export", "merge", "part_hist", "part_scatter", "sub_dict", "sub_compare", "sub_mapback",
-               "reserved"]
+               "part2"]
 PC_MAX_GROUPS, PC_MAX_SUB_K = 8, 8
 
 
@@ -63,6 +63,7 @@ _SIGS = {
     "pc_packed_get": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int]),
     "pc_count": (C.c_int, [_vp, C.c_int, _i64]),
     "pc_count_info": (C.c_int, [_vp, _vp]),
+    "pc_count_detail": (C.c_int, [_vp, _vp]),
     "pc_dump_counts": (C.c_int, [_vp, _u32, _u32, _vp, _vp, _i64, C.c_int, _P(_i64)]),
     "pc_partition": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _P(_vp)]),
     "pc_count_buckets": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _i64]),
@@ -327,6 +328,12 @@ class Context:
         check(lib.pc_count_info(self._h, info.ctypes.data), "pc_count_info")
         return dict(capacity=int(info[0]), distinct=int(info[1]), valid_windows=int(info[2]),
                     table_bytes=int(info[3]), max_probe=int(info[4]), k=int(info[5]), partition_bits=int(info[7]))
+
+    def count_detail(self):
+        d = np.zeros(8, np.int64)
+        check(lib.pc_count_detail(self._h, d.ctypes.data), "pc_count_detail")
+        return dict(kind="list" if d[0] == 1 else "table", kept=int(d[1]), keep_min=int(d[2]), sub_buckets=int(d[3]),
+                    sub_per_bucket=int(d[4]), overflowed=int(d[5]))
 
     def dump_counts(self, min_count=1, max_count=0xFFFFFFFF):
         n = _i64()

@@ -14,6 +14,7 @@
 
 #include "../../include/polycracker_b200.h"
 #include "kernels.cuh"
+#include "kernels_smem.cuh"
 
 namespace {
 
@@ -40,7 +41,7 @@ int fail(int code, const char* fmt, ...) {
 
 enum Stage { ST_H2D = 0, ST_PACK, ST_TABLE_INIT, ST_COUNT, ST_SELECT, ST_SORT, ST_REPTABLE, ST_PROBE,
              ST_ROWSORT, ST_EMIT, ST_TFIDF, ST_D2H, ST_EXPORT, ST_MERGE, ST_PART_HIST, ST_PART_SCATTER,
-             ST_SUB_DICT, ST_SUB_COMPARE, ST_SUB_MAPBACK, ST_N };
+             ST_SUB_DICT, ST_SUB_COMPARE, ST_SUB_MAPBACK, ST_PART2, ST_N };
 static_assert(ST_N <= PC_N_STAGES, "stage table too small");
 static_assert(pc::kMaxGroups == PC_MAX_GROUPS && pc::kMaxSubK == PC_MAX_SUB_K, "header and kernels disagree");
 
@@ -124,6 +125,18 @@ struct pc_ctx {
     uint32_t watch_low = 0; bool cross_valid = false; uint32_t cross_low = 0;
     DevBuf<uint64_t> cross_keys; DevBuf<unsigned long long> d_cross_n;
     int count_items = 2;                        // k-mers in flight per thread in the bucket kernel (2: 48 regs, best measured)
+
+    // shared-memory count (part_mode 2, kernels_smem.cuh): level-2 buckets, then a compact (k-mer, count) list of the
+    // k-mers with count >= list_min instead of a global table.  count_kind says what pc_select / pc_dump_counts read.
+    int count_kind = 0;                         // 0 global table, 1 compact list
+    uint32_t keep_min = 1;                      // tunable: lowest count worth keeping (the reference dumps mincount=3)
+    int64_t smem_target = 0;                    // tunable: mean k-mer instances per sub-bucket (0 = 7/16 of the table slots)
+    int smem_slots() const { return smem_variant == 1 ? 4096 : smem_variant == 2 ? 16384 : 8192; }
+    int64_t smem_mean() const { return smem_target > 0 ? smem_target : (int64_t)smem_slots() * 7 / 16; }
+    int smem_variant = 0;                       // tunable: 0 = 8192 slots x 512 threads x 4 k-mers in flight, 1 = 4096 x 256 x 8, 2 = 16384 x 1024 x 8, 3 = 8192 x 256 x 8, 4 = 8192 x 512 x 8
+    DevBuf<uint64_t> kbuf2, list_keys; DevBuf<uint32_t> list_counts; DevBuf<unsigned long long> d_sub; DevBuf<int64_t> d_tile;
+    DevBuf<unsigned int> d_ovf;
+    int64_t n_list = 0, n_sub = 0, n_ovf = 0; uint32_t list_min = 1; unsigned int sub_nb2 = 0;
 
     // N1 subgenome-extraction session (pc_sub_*): per-subgenome dictionaries of the k being compared, then per k the
     // differential sets and their union mask table
@@ -259,6 +272,7 @@ int pc_destroy(pc_ctx* c) {
     c->ascii.release(); c->d_word0.release(); c->d_begin.release(); c->d_len.release();
     c->words.release(); c->nmask.release(); c->table_keys.release(); c->table_counts.release(); c->d_stats.release();
     c->kbuf.release(); c->kstream.release(); c->d_part_hist.release(); c->d_seg.release(); c->cross_keys.release(); c->d_cross_n.release();
+    c->kbuf2.release(); c->list_keys.release(); c->list_counts.release(); c->d_sub.release(); c->d_tile.release(); c->d_ovf.release();
     c->sel_a.release(); c->sel_b.release(); c->rs_hist.release(); c->d_counter.release(); c->rtable.release(); c->rfp.release();
     c->d_chunk_row.release(); c->d_row_base.release(); c->d_row_cursor.release(); c->hits_a.release();
     c->hits_b.release(); c->d_row_nnz.release(); c->d_indptr.release(); c->d_indices.release();
@@ -513,8 +527,8 @@ static int do_partition(pc_ctx* c, int k, int pb) {
 }
 
 // count n_buckets buckets (sub-table i <- segments [i*n_seg, (i+1)*n_seg) of keys_dev) into a fresh table
-static int do_count_buckets(pc_ctx* c, int k, int pb, int n_buckets, const uint64_t* keys_dev, const int64_t* seg_begin,
-                            const int64_t* seg_len, int n_seg, int64_t capacity, const uint64_t* const* seg_base_host = nullptr) {
+static int count_buckets_table(pc_ctx* c, int k, int pb, int n_buckets, const uint64_t* keys_dev, const int64_t* seg_begin,
+                               const int64_t* seg_len, int n_seg, int64_t capacity, const uint64_t* const* seg_base_host = nullptr) {
     int rc;
     int64_t total = 0, max_bucket = 0;
     for (int q = 0; q < n_buckets; ++q) {
@@ -581,8 +595,143 @@ static int do_count_buckets(pc_ctx* c, int k, int pb, int n_buckets, const uint6
 #undef COUNT_PART
     }
     rc = fetch_stats(c); if (rc) return rc;                   // synchronises: the host segment arrays may go away
-    c->counted = true;
+    c->counted = true; c->count_kind = 0;
     return PC_OK;
+}
+
+// Shared-memory count (kernels_smem.cuh): level-2 histogram + scatter of the n_buckets level-1 buckets into sub-buckets
+// of about smem_target k-mers, one CTA-private shared-memory table per sub-bucket, survivors (count >= keep_min) to a
+// compact list.  Sub-buckets that do not fit their table are re-counted through a global table (count_buckets_table).
+extern "C++" {
+template <int SLOTS, int THREADS, int PER>
+static int launch_count_smem(pc_ctx* c, unsigned int n_sub, unsigned long long list_cap, unsigned long long* d_nlist, unsigned int* d_novf) {
+    size_t smem = (size_t)SLOTS * 12;
+    CU(cudaFuncSetAttribute(pc::k_count_smem<SLOTS, THREADS, PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = std::max(1, (int)((size_t)(220 << 10) / (smem + 1024)));
+    per_sm = std::min(per_sm, 2048 / THREADS);
+    unsigned int grid = std::min<unsigned int>(n_sub, 148u * (unsigned int)per_sm);
+    c->launches++;
+    pc::k_count_smem<SLOTS, THREADS, PER><<<grid, THREADS, smem, c->stream>>>(
+        c->kbuf2.p, c->d_sub.p, n_sub, c->keep_min, c->list_keys.p, c->list_counts.p, list_cap, d_nlist, c->d_ovf.p, d_novf, c->d_stats.p);
+    CU(cudaGetLastError());
+    return PC_OK;
+}
+}  // extern "C++"
+
+static int count_buckets_smem(pc_ctx* c, int k, int pb, int n_buckets, const uint64_t* keys_dev, const int64_t* seg_begin,
+                              const int64_t* seg_len, int n_seg, const uint64_t* const* seg_base_host) {
+    int rc;
+    constexpr int TILE = 8192;
+    const int64_t n_pairs = (int64_t)n_buckets * n_seg;
+    std::vector<int64_t> tile_start(n_pairs + 1, 0);
+    int64_t total = 0;
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        if (seg_len[p] < 0 || seg_begin[p] < 0) return fail(PC_EINVAL, "bad segment");
+        total += seg_len[p];
+        tile_start[p + 1] = tile_start[p] + (seg_len[p] + TILE - 1) / TILE;
+    }
+    if (c->keep_min < 1) c->keep_min = 1;
+    const int64_t n_tiles = tile_start[n_pairs];
+    int64_t nb2 = (total + (int64_t)n_buckets * c->smem_mean() - 1) / ((int64_t)n_buckets * c->smem_mean());
+    const unsigned int NB2 = (unsigned int)std::min<int64_t>(PC_SUB_MAX, std::max<int64_t>(1, nb2));
+    const int64_t n_sub = (int64_t)n_buckets * NB2;
+    if (n_sub >= (1ll << 31)) return fail(PC_EINVAL, "too many sub-buckets");
+    c->k = k; c->pb = pb; c->sub_nb2 = NB2; c->n_sub = n_sub; c->cross_valid = false;
+    c->part_S = 0; c->capacity = (uint64_t)n_sub * (uint64_t)c->smem_slots();
+
+    rc = c->d_seg.alloc((size_t)3 * n_pairs); if (rc) return rc;
+    rc = c->d_tile.alloc((size_t)n_pairs + 1); if (rc) return rc;
+    rc = c->d_sub.alloc((size_t)2 * n_sub + 8); if (rc) return rc;
+    rc = c->d_ovf.alloc((size_t)n_sub + 2); if (rc) return rc;
+    rc = c->kbuf2.alloc((size_t)std::max<int64_t>(total, 1)); if (rc) return rc;
+    const unsigned long long list_cap = (unsigned long long)(total / c->keep_min) + 1024ull;
+    rc = c->list_keys.alloc((size_t)list_cap); if (rc) return rc;
+    rc = c->list_counts.alloc((size_t)list_cap); if (rc) return rc;
+    CU(cudaMemcpyAsync(c->d_seg.p, seg_begin, (size_t)n_pairs * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_seg.p + n_pairs, seg_len, (size_t)n_pairs * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    const int64_t* d_beg = c->d_seg.p;
+    const int64_t* d_len = c->d_seg.p + n_pairs;
+    const uint64_t* const* d_base = nullptr;
+    if (seg_base_host) {
+        CU(cudaMemcpyAsync(c->d_seg.p + 2 * n_pairs, seg_base_host, (size_t)n_pairs * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        d_base = reinterpret_cast<const uint64_t* const*>(c->d_seg.p + 2 * n_pairs);
+    }
+    CU(cudaMemcpyAsync(c->d_tile.p, tile_start.data(), (size_t)(n_pairs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    unsigned long long* sub_off = c->d_sub.p;                              // [n_sub + 1] sizes, then offsets
+    unsigned long long* sub_cur = c->d_sub.p + n_sub + 1;                  // [n_sub] scatter cursors
+    unsigned long long* d_nlist = c->d_sub.p + 2 * n_sub + 2;              // [1]
+    unsigned int* d_novf = reinterpret_cast<unsigned int*>(c->d_sub.p + 2 * n_sub + 3);
+    CU(cudaMemsetAsync(c->d_sub.p, 0, ((size_t)2 * n_sub + 8) * sizeof(unsigned long long), c->stream));
+    if (total > 0) {
+        {
+            StageTimer t(c, ST_PART2);
+            unsigned int grid = (unsigned int)std::min<int64_t>(148 * 8, n_tiles);
+            c->launches++;
+            pc::k_sub_hist<TILE><<<grid, 256, NB2 * sizeof(unsigned int), c->stream>>>(
+                keys_dev, d_base, d_beg, d_len, c->d_tile.p, (int)n_pairs, n_seg, pb, NB2, sub_off);
+            CU(cudaGetLastError());
+            LAUNCH(c, pc::k_rs_scan<unsigned long long>, 1, 1024, sub_off, n_sub);
+            size_t smem = (size_t)TILE * 8 + (size_t)NB2 * 8 + (size_t)NB2 * 4 + ((size_t)NB2 + 2) * 4 + (size_t)TILE * 2 + 16;
+            CU(cudaFuncSetAttribute(pc::k_sub_scatter<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            grid = (unsigned int)std::min<int64_t>(148 * 2, n_tiles);
+            c->launches++;
+            pc::k_sub_scatter<TILE><<<grid, 256, smem, c->stream>>>(
+                keys_dev, d_base, d_beg, d_len, c->d_tile.p, (int)n_pairs, n_seg, pb, NB2, sub_off, sub_cur, c->kbuf2.p);
+            CU(cudaGetLastError());
+        }
+        {
+            StageTimer t(c, ST_COUNT);
+            if (c->smem_variant == 1) rc = launch_count_smem<4096, 256, 8>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
+            else if (c->smem_variant == 2) rc = launch_count_smem<16384, 1024, 8>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
+            else if (c->smem_variant == 3) rc = launch_count_smem<8192, 256, 8>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
+            else if (c->smem_variant == 4) rc = launch_count_smem<8192, 512, 8>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
+            else rc = launch_count_smem<8192, 512, 4>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
+            if (rc) return rc;
+        }
+    }
+    unsigned long long h_nlist = 0; unsigned int h_novf = 0;
+    CU(cudaMemcpyAsync(&h_nlist, d_nlist, sizeof h_nlist, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(&h_novf, d_novf, sizeof h_novf, cudaMemcpyDeviceToHost, c->stream));
+    rc = fetch_stats(c); if (rc) return rc;                   // synchronises
+    c->n_ovf = h_novf;
+    if (h_novf > 0) {
+        // sub-buckets whose distinct k-mers did not fit a shared-memory table: count them in one global table and
+        // append its survivors to the list
+        std::vector<unsigned int> ids(h_novf);
+        std::vector<unsigned long long> off(n_sub + 1);
+        CU(cudaMemcpyAsync(ids.data(), c->d_ovf.p, (size_t)h_novf * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(off.data(), sub_off, (size_t)(n_sub + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        std::sort(ids.begin(), ids.end());
+        std::vector<int64_t> fb_begin(h_novf), fb_len(h_novf);
+        int64_t fb_total = 0;
+        for (unsigned int i = 0; i < h_novf; ++i) {
+            fb_begin[i] = (int64_t)off[ids[i]]; fb_len[i] = (int64_t)(off[ids[i] + 1] - off[ids[i]]); fb_total += fb_len[i];
+        }
+        const uint32_t keep_watch = c->watch_low; c->watch_low = 0;
+        rc = count_buckets_table(c, k, 0, 1, c->kbuf2.p, fb_begin.data(), fb_len.data(), (int)h_novf,
+                                 (int64_t)(fb_total / c->table_load) + 1024);
+        c->watch_low = keep_watch;
+        if (rc) return rc;
+        unsigned int grid = (unsigned int)std::min<uint64_t>((c->capacity + 1023) / 1024, 148ull * 64);
+        LAUNCH(c, pc::k_select, grid, 256, c->table(), c->capacity, c->keep_min, 0xFFFFFFFFu, c->list_keys.p, c->list_counts.p,
+               list_cap, d_nlist);
+        CU(cudaMemcpyAsync(&h_nlist, d_nlist, sizeof h_nlist, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        c->pb = pb; c->part_S = 0; c->capacity = (uint64_t)n_sub * (uint64_t)c->smem_slots();
+    }
+    if (h_nlist > list_cap) return fail(PC_ESTATE, "k-mer list overflow: %llu entries for %llu slots", h_nlist, list_cap);
+    c->n_list = (int64_t)h_nlist; c->list_min = c->keep_min;
+    c->counted = true; c->count_kind = 1;
+    return PC_OK;
+}
+
+static bool smem_mode(const pc_ctx* c) { return c->part_mode == 2 || c->part_mode < 0; }
+
+static int do_count_buckets(pc_ctx* c, int k, int pb, int n_buckets, const uint64_t* keys_dev, const int64_t* seg_begin,
+                            const int64_t* seg_len, int n_seg, int64_t capacity, const uint64_t* const* seg_base_host = nullptr) {
+    if (smem_mode(c)) return count_buckets_smem(c, k, pb, n_buckets, keys_dev, seg_begin, seg_len, n_seg, seg_base_host);
+    return count_buckets_table(c, k, pb, n_buckets, keys_dev, seg_begin, seg_len, n_seg, capacity, seg_base_host);
 }
 
 // Free device buffers that later stages no longer need (large genomes on one GPU: the count table, the bucket buffer
@@ -592,8 +741,11 @@ int pc_release(pc_ctx* c, int what) {
     CU(cudaStreamSynchronize(c->stream));
     if (c->zeroed_slots > 0) { CU(cudaStreamSynchronize(c->aux_stream)); c->zeroed_slots = 0; }
     if (what & PC_REL_ASCII) { c->ascii.release(); c->ascii_padded = 0; }
-    if (what & PC_REL_BUCKETS) c->kbuf.release();
-    if (what & PC_REL_TABLE) { c->table_keys.release(); c->table_counts.release(); c->counted = false; c->cross_valid = false; c->cross_keys.release(); }
+    if (what & PC_REL_BUCKETS) { c->kbuf.release(); c->kbuf2.release(); }
+    if (what & PC_REL_TABLE) {
+        c->table_keys.release(); c->table_counts.release(); c->counted = false; c->cross_valid = false; c->cross_keys.release();
+        c->list_keys.release(); c->list_counts.release(); c->n_list = 0;
+    }
     if (what & PC_REL_STREAM) { c->kstream.release(); c->stream_valid = false; }
     if (what & PC_REL_HITS) { c->hits_a.release(); c->hits_b.release(); }
     return PC_OK;
@@ -622,6 +774,9 @@ int pc_tune(pc_ctx* c, const char* key, int64_t value) {
         c->counted = c->selected = c->built = false;          // tables built with the other hash are unusable
         c->stream_valid = false;
     }
+    else if (k == "keep_min") c->keep_min = (uint32_t)std::max<int64_t>(1, value);
+    else if (k == "smem_target") c->smem_target = value <= 0 ? 0 : std::max<int64_t>(64, value);
+    else if (k == "smem_variant") c->smem_variant = (int)value;
     else if (k == "prezero") c->prezero = (int)value;
     else if (k == "probe_fp") c->probe_fp = (int)value;
     else if (k == "part_casfirst") c->part_casfirst = (int)value;
@@ -652,8 +807,14 @@ int pc_count(pc_ctx* c, int k, int64_t capacity) {
     }
     // partition plan: P = 2^pb sub-tables of S slots, each about part_bytes so that it stays L2 resident
     int pb = 0;
-    bool partitioned = c->part_mode == 1 || (c->part_mode < 0 && (size_t)capacity * (size_t)PC_SLOT_BYTES > (size_t)(64ll << 20));
-    if (partitioned) {
+    bool partitioned = c->part_mode == 1 || c->part_mode == 2 || (c->part_mode < 0 && (size_t)capacity * (size_t)PC_SLOT_BYTES > (size_t)(64ll << 20));
+    if (partitioned && smem_mode(c)) {
+        // two-level split into about windows / smem_target sub-buckets: level 1 takes the square root, rounded to a
+        // power of two, the level-2 fan-out is fixed once the exact number of valid windows is known
+        int64_t nb_total = std::max<int64_t>(1, windows / c->smem_mean());
+        pb = 1;
+        while (pb < 12 && ((int64_t)1 << (2 * pb)) < nb_total) ++pb;
+    } else if (partitioned) {
         while (pb < 12 && ((size_t)capacity * (size_t)PC_SLOT_BYTES) >> pb > (size_t)c->part_bytes) ++pb;
         if (pb == 0) pb = 1;
     }
@@ -667,13 +828,13 @@ int pc_count(pc_ctx* c, int k, int64_t capacity) {
             rc = launch_count(c); if (rc) return rc;
         }
         rc = fetch_stats(c); if (rc) return rc;
-        c->counted = true;
+        c->counted = true; c->count_kind = 0;
         return PC_OK;
     }
 
     // ---- partitioned path: extract -> tile scatter -> bucket-by-bucket count ----------------------------------
     CU(cudaMemsetAsync(c->d_stats.p, 0, sizeof(pc::CountStats), c->stream));
-    rc = table_prezero(c, k, (int64_t)(((uint64_t)capacity + P - 1) / P * P)); if (rc) return rc;
+    if (!smem_mode(c)) { rc = table_prezero(c, k, (int64_t)(((uint64_t)capacity + P - 1) / P * P)); if (rc) return rc; }
     rc = do_partition(c, k, pb); if (rc) return rc;
     std::vector<int64_t> seg_begin(P), seg_len(P);
     for (uint64_t q = 0; q < P; ++q) { seg_begin[q] = c->h_bucket_off[q]; seg_len[q] = c->h_bucket_off[q + 1] - c->h_bucket_off[q]; }
@@ -696,7 +857,7 @@ int pc_partition(pc_ctx* c, int k, int pb, int64_t* bucket_off, uint64_t** keys_
     {   // the owner will count about as many k-mers as this rank extracts: start zeroing a table of that size now
         int64_t windows = 0;
         for (int64_t i = 0; i < c->n_chunks; ++i) windows += std::max<int64_t>(0, c->h_len[i] - k + 1);
-        rc = table_prezero(c, k, (int64_t)(windows / c->table_load) + 1024); if (rc) return rc;
+        if (!smem_mode(c)) { rc = table_prezero(c, k, (int64_t)(windows / c->table_load) + 1024); if (rc) return rc; }
     }
     rc = do_partition(c, k, pb); if (rc) return rc;
     memcpy(bucket_off, c->h_bucket_off.data(), ((size_t)(1u << pb) + 1) * sizeof(int64_t));
@@ -766,7 +927,18 @@ int pc_count_info(pc_ctx* c, int64_t info[8]) {
     memset(info, 0, 8 * sizeof(int64_t));
     info[0] = (int64_t)c->capacity; info[1] = (int64_t)c->h_stats.distinct; info[2] = (int64_t)c->h_stats.valid_windows;
     info[3] = (int64_t)(c->capacity * (size_t)PC_SLOT_BYTES); info[4] = (int64_t)c->h_stats.max_probe; info[5] = c->k;
-    info[6] = 0; info[7] = c->pb;
+    info[6] = c->count_kind == 1 ? c->n_list : 0; info[7] = c->pb;
+    if (c->count_kind == 1) info[3] = (int64_t)((size_t)c->list_keys.n * 12 + (size_t)c->kbuf2.n * 8);
+    return PC_OK;
+}
+
+int pc_count_detail(pc_ctx* c, int64_t detail[8]) {
+    if (!c || !c->counted) return fail(PC_ESTATE, "no count result");
+    memset(detail, 0, 8 * sizeof(int64_t));
+    detail[0] = c->count_kind;
+    if (c->count_kind == 1) {
+        detail[1] = c->n_list; detail[2] = c->list_min; detail[3] = c->n_sub; detail[4] = c->sub_nb2; detail[5] = c->n_ovf;
+    }
     return PC_OK;
 }
 
@@ -774,9 +946,20 @@ int pc_count_info(pc_ctx* c, int64_t info[8]) {
 static int select_into(pc_ctx* c, uint32_t low, uint32_t high, uint64_t* keys_dev, uint32_t* counts_dev, int64_t cap,
                        int64_t* n_out) {
     CU(cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned long long), c->stream));
+    if (c->count_kind == 1) {
+        if (low < c->list_min)
+            return fail(PC_ESTATE, "k-mers with fewer than %u occurrences were not kept by this count (pc_tune keep_min); asked for >= %u",
+                        c->list_min, low);
+        if (c->n_list > 0) {
+            unsigned int grid = (unsigned int)std::min<int64_t>((c->n_list + 1023) / 1024, 148ll * 16);
+            LAUNCH(c, pc::k_select_list, grid, 256, c->list_keys.p, c->list_counts.p, c->n_list, low, high, keys_dev, counts_dev,
+                   (unsigned long long)cap, c->d_counter.p);
+        }
+    } else {
     unsigned int grid = (unsigned int)std::min<uint64_t>((c->capacity + 1023) / 1024, 148ull * 64);
     LAUNCH(c, pc::k_select, grid, 256, c->table(), c->capacity, low, high, keys_dev, counts_dev,
            (unsigned long long)cap, c->d_counter.p);
+    }
     unsigned long long n = 0;
     CU(cudaMemcpyAsync(&n, c->d_counter.p, sizeof n, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -809,6 +992,7 @@ int pc_dump_counts(pc_ctx* c, uint32_t min_count, uint32_t max_count, uint64_t* 
 int pc_export_by_owner(pc_ctx* c, int world, uint64_t* keys_dev, uint32_t* counts_dev, int64_t cap, int64_t* offsets) {
     int rc = use_device(c); if (rc) return rc;
     if (!c->counted) return fail(PC_ESTATE, "pc_export_by_owner before pc_count");
+    if (c->count_kind != 0) return fail(PC_ESTATE, "pc_export_by_owner needs a global count table (pc_tune part_mode 0 or 1)");
     if (world < 1 || world > 64 || !keys_dev || !counts_dev || !offsets) return fail(PC_EINVAL, "bad export arguments");
     if (cap < (int64_t)c->h_stats.distinct) return fail(PC_EINVAL, "export buffer too small: need %llu", c->h_stats.distinct);
     StageTimer t(c, ST_EXPORT);
@@ -837,7 +1021,7 @@ int pc_merge_counts(pc_ctx* c, const uint64_t* keys_dev, const uint32_t* counts_
         c->selected = c->built = c->tfidf_done = false;
     } else if (!c->counted || c->k != k) {
         return fail(PC_ESTATE, "pc_merge_counts(fresh=0) needs an existing table with the same k");
-    } else if (c->pb != 0) {
+    } else if (c->pb != 0 || c->count_kind != 0) {
         return fail(PC_ESTATE, "pc_merge_counts(fresh=0) cannot add to a partitioned count table");
     }
     {
@@ -845,7 +1029,7 @@ int pc_merge_counts(pc_ctx* c, const uint64_t* keys_dev, const uint32_t* counts_
         if (n > 0) LAUNCH(c, pc::k_merge, blocks_for(n, 256), 256, keys_dev, counts_dev, n, c->table(), c->capacity, c->d_stats.p);
     }
     rc = fetch_stats(c); if (rc) return rc;
-    c->counted = true;
+    c->counted = true; c->count_kind = 0;
     return PC_OK;
 }
 

@@ -1,0 +1,335 @@
+// K3, shared-memory path: two-level radix partition, then every sub-bucket is counted in a shared-memory hash table.
+//
+// The L2-resident bucket count (k_count_part) is bound by random L2 sector operations (~4 per insert, half of them
+// across the die-to-die fabric; profiles/r01_kbench_count.md).  This path trades them for one more streaming pass:
+// each level-1 bucket (top pb bits of the hash) is split again into NB2 sub-buckets of a few thousand k-mers, small
+// enough that ALL distinct k-mers of a sub-bucket fit a shared-memory table.  One CTA then streams a sub-bucket
+// (contiguous, coalesced), inserts with shared-memory atomics, and writes out only the k-mers whose count reaches
+// keep_min as a compact (k-mer, count) list -- no global table, no table memset, and the threshold scan (K4) reads the
+// list instead of 12 B x capacity.  A sub-bucket whose distinct k-mers do not fit (adversarial input, capped NB2) is
+// reported in an overflow list and counted by the global-table kernel instead, so the result never depends on sizing.
+#pragma once
+#include "kernels.cuh"
+
+namespace pc {
+
+#define PC_SUB_MAX 2048                                   // sub-buckets per level-1 bucket (smem arrays of the scatter)
+
+// sub-bucket of a k-mer inside its level-1 bucket: the 32 hash bits below the bucket bits, scaled to [0, NB2)
+__device__ __forceinline__ unsigned int sub_of(uint64_t h, int pb, unsigned int NB2) {
+    return (unsigned int)((((h << pb) >> 32) * (uint64_t)NB2) >> 32);
+}
+
+// A level-1 bucket q arrives as n_seg segments (one per sending rank; one on a single GPU), pair p = q * n_seg + sg.
+// Tiles never span two pairs, so every key of a tile belongs to level-1 bucket q: tile_start[p] = first tile of pair p.
+struct SegTile { const uint64_t* src; int64_t lim; int64_t q; };
+template <int TILE>
+__device__ __forceinline__ SegTile seg_tile(const uint64_t* __restrict__ keys, const uint64_t* const* __restrict__ seg_base,
+                                            const int64_t* __restrict__ seg_begin, const int64_t* __restrict__ seg_len,
+                                            const int64_t* __restrict__ tile_start, int n_pairs, int n_seg, int64_t g)
+{
+    int64_t p = find_le(tile_start, n_pairs, g);
+    int64_t t_in = g - __ldg(tile_start + p);
+    const uint64_t* base = (seg_base ? seg_base[p] : keys) + __ldg(seg_begin + p);
+    SegTile s;
+    s.src = base + t_in * TILE;
+    s.lim = min((int64_t)TILE, __ldg(seg_len + p) - t_in * TILE);
+    s.q = p / n_seg;
+    return s;
+}
+
+// level-2 pass A: sizes of the sub-buckets.  Per tile a shared-memory histogram of NB2 bins, flushed with one global
+// atomic per non-empty bin.
+template <int TILE>
+__global__ void __launch_bounds__(256)
+k_sub_hist(const uint64_t* __restrict__ keys, const uint64_t* const* __restrict__ seg_base,
+           const int64_t* __restrict__ seg_begin, const int64_t* __restrict__ seg_len,
+           const int64_t* __restrict__ tile_start, int n_pairs, int n_seg, int pb, unsigned int NB2,
+           unsigned long long* __restrict__ sub_hist)
+{
+    constexpr int PER = TILE / 256;
+    extern __shared__ unsigned int sh_hist[];
+    const int t = threadIdx.x;
+    for (unsigned int i = t; i < NB2; i += 256) sh_hist[i] = 0;
+    __syncthreads();
+    const int64_t n_tiles = __ldg(tile_start + n_pairs);
+    for (int64_t g = blockIdx.x; g < n_tiles; g += gridDim.x) {
+        SegTile s = seg_tile<TILE>(keys, seg_base, seg_begin, seg_len, tile_start, n_pairs, n_seg, g);
+#pragma unroll 8
+        for (int j = 0; j < PER; ++j) {
+            int i = j * 256 + t;
+            if (i < s.lim) atomicAdd(&sh_hist[sub_of(hash64(__ldcs(s.src + i)), pb, NB2)], 1u);
+        }
+        __syncthreads();
+        for (unsigned int x = t; x < NB2; x += 256) {
+            unsigned int c = sh_hist[x];
+            if (c) { atomicAdd(&sub_hist[s.q * NB2 + x], (unsigned long long)c); sh_hist[x] = 0; }
+        }
+        __syncthreads();
+    }
+}
+
+// level-2 pass B: the tile-wise counting sort of k_tile_scatter, by sub-bucket.  The source may be a peer's bucket
+// buffer (NVLink): the multi-GPU exchange is fused into this read.
+template <int TILE>
+__global__ void __launch_bounds__(256, 2)
+k_sub_scatter(const uint64_t* __restrict__ keys, const uint64_t* const* __restrict__ seg_base,
+              const int64_t* __restrict__ seg_begin, const int64_t* __restrict__ seg_len,
+              const int64_t* __restrict__ tile_start, int n_pairs, int n_seg, int pb, unsigned int NB2,
+              const unsigned long long* __restrict__ sub_off, unsigned long long* __restrict__ cursor,
+              uint64_t* __restrict__ out)
+{
+    constexpr int PER = TILE / 256;
+    extern __shared__ unsigned long long sm64[];
+    unsigned long long* sorted = sm64;                                   // [TILE]
+    unsigned long long* gbase = sm64 + TILE;                             // [NB2]
+    unsigned int* cnt = reinterpret_cast<unsigned int*>(gbase + NB2);    // [NB2]
+    unsigned int* lstart = cnt + NB2;                                    // [NB2 + 1]
+    unsigned short* qs = reinterpret_cast<unsigned short*>(lstart + NB2 + 1 + ((NB2 + 1) & 1));   // [TILE]
+    __shared__ unsigned int wsum[8];
+    __shared__ SegTile s_tile;                                           // tile descriptor (keeps it out of the registers)
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int64_t n_tiles = __ldg(tile_start + n_pairs);
+    for (int64_t g = blockIdx.x; g < n_tiles; g += gridDim.x) {
+        if (t == 0) s_tile = seg_tile<TILE>(keys, seg_base, seg_begin, seg_len, tile_start, n_pairs, n_seg, g);
+        __syncthreads();
+        uint64_t key[PER];
+        {
+            const uint64_t* src = s_tile.src + t;
+            const int lim = (int)s_tile.lim - t;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) key[j] = (j * 256 < lim) ? __ldcs(src + j * 256) : PC_KEY_SENTINEL;
+        }
+        for (unsigned int i = t; i < NB2; i += 256) cnt[i] = 0;
+        __syncthreads();
+        unsigned int q2[PER / 2];                                        // two 16-bit sub-bucket ids per register
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            unsigned int q = sub_of(hash64(key[j]), pb, NB2);
+            if (key[j] != PC_KEY_SENTINEL) atomicAdd(&cnt[q], 1u);
+            if (j & 1) q2[j >> 1] |= q << 16; else q2[j >> 1] = q;
+        }
+        __syncthreads();
+        {
+            unsigned int per = (NB2 + 255) / 256;
+            unsigned int b0 = min(NB2, t * per), b1 = min(NB2, b0 + per);
+            unsigned int sum = 0;
+            for (unsigned int x = b0; x < b1; ++x) sum += cnt[x];
+            unsigned int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned int u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            if (lane == 31) wsum[wid] = incl;
+            __syncthreads();
+            unsigned int before = 0;
+#pragma unroll
+            for (int x = 0; x < 8; ++x) if (x < wid) before += wsum[x];
+            unsigned int run = before + incl - sum;
+            const unsigned long long sub0 = (unsigned long long)s_tile.q * NB2;
+            for (unsigned int x = b0; x < b1; ++x) {
+                unsigned int c = cnt[x];
+                lstart[x] = run;
+                if (c) gbase[x] = sub_off[sub0 + x] + atomicAdd(&cursor[sub0 + x], (unsigned long long)c);
+                cnt[x] = 0;
+                run += c;
+            }
+            if (t == 255) lstart[NB2] = run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            if (key[j] != PC_KEY_SENTINEL) {
+                unsigned int q = (j & 1) ? (q2[j >> 1] >> 16) : (q2[j >> 1] & 0xFFFFu);
+                unsigned int pos = lstart[q] + atomicAdd(&cnt[q], 1u);
+                sorted[pos] = key[j];
+                qs[pos] = (unsigned short)q;
+            }
+        }
+        __syncthreads();
+        unsigned int nv = lstart[NB2];
+        for (unsigned int i = t; i < nv; i += 256) {
+            unsigned int x = qs[i];
+            out[gbase[x] + (i - lstart[x])] = sorted[i];
+        }
+        __syncthreads();
+    }
+}
+
+// level-2 pass C: one CTA per sub-bucket at a time (persistent, strided: neighbouring CTAs stream neighbouring
+// sub-buckets).  Shared-memory table: keys[SLOTS] (stored complemented, 0 = empty) + counts[SLOTS] (occurrences - 1: the
+// CAS that claims a slot records the first occurrence, so a new k-mer costs one shared atomic, a repeat two).
+// The k-mers of the next batch / next sub-bucket are requested from HBM before the current batch is inserted.
+// Output: (k-mer, count) of every k-mer with count >= keep_min, appended to a list with one global atomic per
+// sub-bucket; ids of sub-buckets that did not fit go to ovf_ids.
+#define PC_SMEM_PROBE_LIMIT 1024u
+template <int SLOTS, int THREADS, int PER>
+__global__ void __launch_bounds__(THREADS, (2048 / THREADS) < (int)((220u << 10) / (SLOTS * 12u + 1024u)) ? (2048 / THREADS) : (int)((220u << 10) / (SLOTS * 12u + 1024u)))
+k_count_smem(const uint64_t* __restrict__ kbuf2, const unsigned long long* __restrict__ sub_off, unsigned int n_sub,
+             unsigned int keep_min, uint64_t* __restrict__ list_keys, uint32_t* __restrict__ list_counts,
+             unsigned long long list_cap, unsigned long long* __restrict__ n_list,
+             unsigned int* __restrict__ ovf_ids, unsigned int* __restrict__ n_ovf, CountStats* __restrict__ stats)
+{
+    constexpr int WARPS = THREADS / 32;
+    constexpr int SPW = SLOTS / WARPS;                           // slots scanned by one warp
+    constexpr int IT = SPW / 32;
+    constexpr unsigned int BATCH = THREADS * PER;
+    static_assert(SLOTS % (WARPS * 32) == 0 && (SLOTS & (SLOTS - 1)) == 0, "slot layout");
+    extern __shared__ unsigned long long skeys[];                // [SLOTS]
+    unsigned int* scnt = reinterpret_cast<unsigned int*>(skeys + SLOTS);   // [SLOTS]
+    __shared__ unsigned int s_total, s_ovf;
+    __shared__ unsigned long long s_gbase;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const unsigned int G = gridDim.x;
+
+    for (int i = t; i < SLOTS; i += THREADS) { skeys[i] = 0ull; scnt[i] = 0u; }
+    if (t == 0) { s_total = 0; s_ovf = 0; }
+    __syncthreads();
+
+    unsigned long long distinct = 0;
+    unsigned int max_probe = 0;
+    // pipeline state: (cur_sb, cur_i0, cur_end) describe the batch whose k-mers are in nkey[]
+    unsigned int cur_sb = blockIdx.x;
+    if (cur_sb >= n_sub) return;
+    unsigned long long cur_i0 = __ldg(sub_off + cur_sb), cur_end = __ldg(sub_off + cur_sb + 1);
+    unsigned long long nbeg = 0, nend = 0;                       // bounds of sub-bucket cur_sb + G
+    if (cur_sb + G < n_sub) { nbeg = __ldg(sub_off + cur_sb + G); nend = __ldg(sub_off + cur_sb + G + 1); }
+    uint64_t nkey[PER];
+#pragma unroll
+    for (int j = 0; j < PER; ++j) {
+        unsigned long long i = cur_i0 + (unsigned long long)j * THREADS + t;
+        nkey[j] = (i < cur_end) ? __ldcs(kbuf2 + i) : PC_KEY_SENTINEL;
+    }
+    unsigned int nk = 0;                                         // slots this thread claimed in the current sub-bucket
+    for (;;) {
+        uint64_t key[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) key[j] = nkey[j];
+        const unsigned int this_sb = cur_sb;
+        const bool last_batch = cur_i0 + BATCH >= cur_end;
+        if (!last_batch) cur_i0 += BATCH;
+        else {
+            cur_sb += G; cur_i0 = nbeg; cur_end = nend;
+            if (cur_sb + G < n_sub) { nbeg = __ldg(sub_off + cur_sb + G); nend = __ldg(sub_off + cur_sb + G + 1); }
+        }
+        const bool more = cur_sb < n_sub;
+        if (more) {
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                unsigned long long i = cur_i0 + (unsigned long long)j * THREADS + t;
+                nkey[j] = (i < cur_end) ? __ldcs(kbuf2 + i) : PC_KEY_SENTINEL;
+            }
+        }
+        // ---- insert this batch
+        if (*(volatile unsigned int*)&s_ovf == 0u) {
+            unsigned long long old[PER]; unsigned int slot[PER];
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                slot[j] = (unsigned int)hash64(key[j]) & (SLOTS - 1);
+                old[j] = (key[j] != PC_KEY_SENTINEL) ? atomicCAS(&skeys[slot[j]], 0ull, ~key[j]) : 0ull;
+            }
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                if (key[j] == PC_KEY_SENTINEL) continue;
+                const unsigned long long skey = ~key[j];
+                unsigned long long o = old[j];
+                unsigned int s = slot[j], probes = 0;
+                for (;;) {
+                    if (o == 0ull) { ++nk; break; }
+                    if (o == skey) { atomicAdd(&scnt[s], 1u); break; }
+                    if (++probes > PC_SMEM_PROBE_LIMIT) { s_ovf = 1u; break; }
+                    s = (s + 1) & (SLOTS - 1);
+                    o = atomicCAS(&skeys[s], 0ull, skey);
+                }
+                max_probe = max(max_probe, probes);
+            }
+        }
+        if (!last_batch) continue;
+
+        // ---- sub-bucket complete: emit the k-mers that reach keep_min, re-zero the table
+        __syncthreads();                                         // A: all inserts of this_sb done
+        const bool ovf = s_ovf != 0u;
+        if (!ovf) distinct += nk;
+        nk = 0;
+        unsigned int c[IT];
+        unsigned int emask = 0, n_emit = 0;
+#pragma unroll
+        for (int i = 0; i < IT; ++i) {
+            int s = wid * SPW + i * 32 + lane;
+            c[i] = scnt[s];
+            bool e = !ovf && c[i] + 1u >= keep_min;
+            if (e && keep_min <= 1u) e = skeys[s] != 0ull;       // count field 0 is also what an empty slot holds
+            emask |= (unsigned int)e << i;
+            n_emit += e;
+        }
+        unsigned int wtot = n_emit;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wtot += __shfl_xor_sync(0xFFFFFFFFu, wtot, o);
+        unsigned int wbase = 0;
+        if (lane == 0 && wtot) wbase = atomicAdd(&s_total, wtot);
+        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
+        __syncthreads();                                         // B: s_total complete, everybody has read s_ovf
+        if (t == 0) {
+            unsigned int tot = s_total;
+            s_gbase = tot ? atomicAdd(n_list, (unsigned long long)tot) : 0ull;
+            s_total = 0; s_ovf = 0;
+            if (ovf) ovf_ids[atomicAdd(n_ovf, 1u)] = this_sb;
+        }
+        __syncthreads();                                         // C: s_gbase valid
+        unsigned long long pos0 = s_gbase + wbase;
+#pragma unroll
+        for (int i = 0; i < IT; ++i) {
+            int s = wid * SPW + i * 32 + lane;
+            bool e = (emask >> i) & 1u;
+            unsigned int bal = __ballot_sync(0xFFFFFFFFu, e);
+            if (e) {
+                unsigned long long pos = pos0 + __popc(bal & ((1u << lane) - 1u));
+                if (pos < list_cap) { list_keys[pos] = ~skeys[s]; list_counts[pos] = c[i] + 1u; }
+            }
+            pos0 += __popc(bal);
+            skeys[s] = 0ull; scnt[s] = 0u;
+        }
+        __syncthreads();                                         // D: table is empty again
+        if (!more) break;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        distinct += __shfl_xor_sync(0xFFFFFFFFu, distinct, o);
+        max_probe = max(max_probe, __shfl_xor_sync(0xFFFFFFFFu, max_probe, o));
+    }
+    if (lane == 0) {
+        if (distinct) atomicAdd(&stats->distinct, distinct);
+        if (max_probe > 8) atomicMax(&stats->max_probe, (unsigned long long)max_probe);
+    }
+}
+
+// K4 over the compact list: survivors appended with one atomic per warp (same contract as k_select)
+__global__ void __launch_bounds__(256)
+k_select_list(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, int64_t n, unsigned int low,
+              unsigned int high, uint64_t* __restrict__ out_keys, uint32_t* __restrict__ out_counts,
+              unsigned long long out_cap, unsigned long long* __restrict__ n_out)
+{
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t n_round = (n + 31) & ~(int64_t)31;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        unsigned int c = (i < n) ? __ldcs(counts + i) : 0u;
+        bool keep = i < n && c >= low && c <= high;
+        unsigned int bal = __ballot_sync(0xFFFFFFFFu, keep);
+        if (bal) {
+            int lane = threadIdx.x & 31;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(n_out, (unsigned long long)__popc(bal));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (keep && out_keys) {
+                unsigned long long pos = base + __popc(bal & ((1u << lane) - 1u));
+                if (pos < out_cap) {
+                    out_keys[pos] = __ldcs(keys + i);
+                    if (out_counts) out_counts[pos] = c;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace pc

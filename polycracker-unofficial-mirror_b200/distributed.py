@@ -16,7 +16,7 @@ The reference's only precedent is query-sharded bbmap with file concatenation (p
 """
 import numpy as np
 
-from .pipeline import ChunkLayout, HotPathResult, effective_low_count, fetch_result
+from .pipeline import ChunkLayout, HotPathResult, dump_floor, effective_low_count, fetch_result
 
 
 def shard_chunks(layout, world):
@@ -194,6 +194,8 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
     use_peer = exchange == "peer" or (exchange == "auto" and getattr(device, "type", "cpu") == "cuda"
                                       and hasattr(ctx, "kbuf_export") and not torch.is_tensor(keys))
     mark("bucket_sizes_allgather")
+    if hasattr(ctx, "tune"):
+        ctx.tune(keep_min=dump_floor(k))                                  # the owners keep what the reference's counter dumps
     if use_peer:
         # 2a. fused exchange: the owner's count kernel reads every sender's slice straight out of that sender's bucket
         # buffer over NVLink (CUDA IPC mapping).  The all-gather of the bucket sizes above is the barrier that says
@@ -220,6 +222,8 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
         ctx.count_buckets(k, pb, recv, seg_begin, seg_len)
         del recv
         exchanged = 8 * (n_local - send_counts[rank])
+    if hasattr(ctx, "tune"):
+        ctx.tune(keep_min=1)
     owner_info = ctx.count_info()
     info = dict(owner_info, valid_windows=n_local)
     mark("count_buckets")

@@ -127,6 +127,13 @@ def effective_low_count(k, kmer_low_count):
     return max(int(kmer_low_count), 3 if k <= 31 else 1)
 
 
+def dump_floor(k):
+    """Lowest count the reference's counter ever writes: kmercountexact `mincount=3` for k <= 31 (polycracker.py:199),
+    jellyfish dump without -L for k > 31 (polycracker.py:203).  The shared-memory count keeps only k-mers that reach
+    it (pc_tune keep_min), so the 2/3 of a genome's k-mers that occur once or twice never leave the SM."""
+    return 3 if k <= 31 else 1
+
+
 def run_hot_path(ctx, seq, seq_offsets, names, chunk_size=75000, k=23, kmer_low_count=100, high_bool=0,
                  kmer_high_count=2000000, sampling_sensitivity=1, remove_non_chunk=1, min_chunk_threshold=0,
                  min_chunk_size=0, prefilter=0, tfidf=True, table_capacity=0, fetch=True, layout=None, arena=None,
@@ -142,7 +149,11 @@ def run_hot_path(ctx, seq, seq_offsets, names, chunk_size=75000, k=23, kmer_low_
     scaffolds, chunk_row = layout.rows(remove_non_chunk, min_chunk_threshold, min_chunk_size, prefilter)
     ctx.load_sequences(seq, layout.chunk_begin_abs, layout.chunk_end_abs)
     ctx.watch_threshold(effective_low_count(k, kmer_low_count) if (fuse_select and not high_bool) else 0)
-    ctx.count(k, table_capacity)
+    ctx.tune(keep_min=dump_floor(k))
+    try:
+        ctx.count(k, table_capacity)
+    finally:
+        ctx.tune(keep_min=1)
     stats = ctx.count_info()
     if low_memory:                                        # Gbp-scale genomes on one GPU: see pc_release
         ctx.release(ctx.REL_BUCKETS | ctx.REL_ASCII)

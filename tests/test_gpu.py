@@ -109,9 +109,10 @@ def test_partitioned_count_equals_direct_and_oracle(ctx, k, mb):
     ctx.load_sequences(seq, lay.chunk_begin_abs, lay.chunk_end_abs)
     want_keys, want_counts, n_windows = c_oracle.count(seq, lay.chunk_begin_abs, lay.chunk_end_abs, k)
     try:
-        for mode in (1, 0):
+        for mode in (2, 1, 0):
             ctx.tune(part_mode=mode, part_mbytes=mb)
             ctx.count(k)
+            assert ctx.count_detail()["kind"] == ("list" if mode == 2 else "table")
             keys, counts = ctx.dump_counts(1)
             order = np.argsort(keys)
             assert np.array_equal(keys[order], want_keys), "mode %d" % mode
@@ -129,22 +130,76 @@ def test_partitioned_count_equals_direct_and_oracle(ctx, k, mb):
         # the multi-GPU building blocks on one device: partition, then count the buckets as two "ranks" would
         # (bucket ranges [0, P/2) and [P/2, P), each fed by two segments per bucket)
         pb = 3
-        off_b, keys_ptr = ctx.partition(k, pb)
-        assert off_b[-1] == n_windows and np.all(np.diff(off_b) >= 0)
-        got = {}
-        for lo, hi in ((0, 4), (4, 8)):
-            seg_begin = np.array([[off_b[q], off_b[q] + (off_b[q + 1] - off_b[q]) // 3] for q in range(lo, hi)])
-            seg_len = np.array([[(off_b[q + 1] - off_b[q]) // 3, (off_b[q + 1] - off_b[q]) - (off_b[q + 1] - off_b[q]) // 3]
-                                for q in range(lo, hi)])
-            ctx.count_buckets(k, pb, keys_ptr, seg_begin, seg_len)
-            kk, cc = ctx.dump_counts(1)
-            assert not (set(kk.tolist()) & set(got))                         # owners hold disjoint k-mers
-            got.update(zip(kk.tolist(), cc.tolist()))
-        assert got == dict(zip(want_keys.tolist(), want_counts.tolist()))
+        for mode in (1, 2):
+            ctx.tune(part_mode=mode, part_mbytes=mb, part_casfirst=0, count_items=2)
+            off_b, keys_ptr = ctx.partition(k, pb)
+            assert off_b[-1] == n_windows and np.all(np.diff(off_b) >= 0)
+            got = {}
+            for lo, hi in ((0, 4), (4, 8)):
+                seg_begin = np.array([[off_b[q], off_b[q] + (off_b[q + 1] - off_b[q]) // 3] for q in range(lo, hi)])
+                seg_len = np.array([[(off_b[q + 1] - off_b[q]) // 3, (off_b[q + 1] - off_b[q]) - (off_b[q + 1] - off_b[q]) // 3]
+                                    for q in range(lo, hi)])
+                ctx.count_buckets(k, pb, keys_ptr, seg_begin, seg_len)
+                kk, cc = ctx.dump_counts(1)
+                assert not (set(kk.tolist()) & set(got))                         # owners hold disjoint k-mers
+                got.update(zip(kk.tolist(), cc.tolist()))
+            assert got == dict(zip(want_keys.tolist(), want_counts.tolist())), "mode %d" % mode
         ctx.tune(part_mode=1, part_mbytes=mb)
         _check_against_c_oracle(ctx, seq, off, names, 20000, k, 5)
     finally:
         ctx.tune(part_mode=-1, part_mbytes=64, part_casfirst=0, count_items=2)
+
+
+@pytest.mark.parametrize("k", [9, 23, 32])
+def test_shared_memory_count(ctx, k):
+    """The shared-memory count (two-level partition, one smem table per sub-bucket, compact list of survivors): every
+    kernel variant, tiny and huge sub-buckets (the latter overflow their table and take the global-table fall-back),
+    keep_min floors, all against the oracle."""
+    p = synth.small_params(seed=300 + k, genome_size=2_000_000, n_fraction=0.01)
+    seq, off, names = synth.generate(p)
+    lay = ChunkLayout(names, off, 20000)
+    ctx.load_sequences(seq, lay.chunk_begin_abs, lay.chunk_end_abs)
+    want_keys, want_counts, n_windows = c_oracle.count(seq, lay.chunk_begin_abs, lay.chunk_end_abs, k)
+    distinct = len(want_keys)
+
+    def check(keep_min, expect_overflow=None):
+        ctx.count(k)
+        d = ctx.count_detail()
+        assert d["kind"] == "list" and d["keep_min"] == keep_min
+        if expect_overflow is not None:
+            assert (d["overflowed"] > 0) == expect_overflow, d
+        keys, counts = ctx.dump_counts(keep_min)
+        order = np.argsort(keys)
+        m = want_counts >= keep_min
+        assert d["kept"] == int(m.sum())
+        assert np.array_equal(keys[order], want_keys[m]) and np.array_equal(counts[order].astype(np.uint64), want_counts[m])
+        info = ctx.count_info()
+        assert info["valid_windows"] == n_windows and info["distinct"] == distinct
+        return d
+
+    try:
+        for variant in range(5):
+            ctx.tune(part_mode=2, smem_variant=variant, smem_target=0, keep_min=1)
+            check(1, expect_overflow=False)
+        ctx.tune(smem_variant=0, keep_min=3)
+        check(3)
+        with pytest.raises(binding.PolycrackerError, match="not kept"):
+            ctx.dump_counts(2)
+        k5, c5 = ctx.dump_counts(5, 9)
+        m = (want_counts >= 5) & (want_counts <= 9)
+        assert sorted(k5.tolist()) == want_keys[m].tolist()
+        ctx.tune(smem_target=100, keep_min=2)                    # hundreds of tiny sub-buckets per bucket
+        d = check(2, expect_overflow=False)
+        assert d["sub_per_bucket"] > 50
+        # sub-buckets far larger than a table: with enough distinct k-mers they overflow and are re-counted globally
+        ctx.tune(smem_target=200_000, keep_min=1)
+        check(1, expect_overflow=distinct > 100_000)
+        ctx.tune(keep_min=4)
+        check(4)
+        ctx.tune(smem_target=0, keep_min=3)
+        _check_against_c_oracle(ctx, seq, off, names, 20000, k, 5)
+    finally:
+        ctx.tune(part_mode=-1, smem_variant=0, smem_target=0, keep_min=1)
 
 
 def test_small_table_reports_overflow_not_garbage(ctx):
@@ -241,6 +296,11 @@ def test_partitioned_path_skewed_buckets_and_odd_shapes(ctx):
             ctx.tune(part_mode=1, part_mbytes=mb)
             _check_against_c_oracle(ctx, seq, off, names, 50000, 23, 3, remove_non_chunk=0)
             _check_against_c_oracle(ctx, seq, off, names, 1000000, 16, 3, remove_non_chunk=0)
+        for target in (0, 300):                              # the shared-memory count on the same inputs
+            ctx.tune(part_mode=2, smem_target=target)
+            _check_against_c_oracle(ctx, seq, off, names, 50000, 23, 3, remove_non_chunk=0)
+            _check_against_c_oracle(ctx, seq, off, names, 1000000, 16, 3, remove_non_chunk=0)
+        ctx.tune(smem_target=0)
     finally:
         ctx.tune(part_mode=-1, part_mbytes=64)
 
