@@ -109,6 +109,11 @@ struct pc_ctx {
     int64_t part_bytes = 64ll << 20;            // target size of one L2-resident sub-table
     int probe_mode = -1;                        // -1 auto (stream when available), 0 roller, 1 stream
     int probe_batch = 4;
+    int probe_threads = 0;                      // filtered probe: 0 auto, 512 (two CTAs per SM) or 1024
+    int probe_filter = -1;                      // shared-memory bitmap filter in front of the repeat table: -1 auto, 0 off, 1 on
+    int64_t filter_bits = 1310720;              // 160 KB of shared memory (measured best: 1.0 M bits 3.58 ms, 1.31 M 3.49, 1.74 M 3.89 -- the
+                                                // largest bitmap leaves the SM no L1 for the chunk / row look-ups)
+    DevBuf<unsigned int> rfilter; unsigned int rfilter_bits = 0;
     int rep_load_inv = 4;                       // repeat table capacity = rep_load_inv * n_selected
     bool stream_valid = false; int stream_k = 0;
     int part_blocks = 0;                        // blocks per bucket in k_count_part (0 = from the bucket size)
@@ -133,7 +138,7 @@ struct pc_ctx {
     int64_t smem_target = 0;                    // tunable: mean k-mer instances per sub-bucket (0 = 7/16 of the table slots)
     int smem_slots() const { return smem_variant == 1 ? 4096 : smem_variant == 2 ? 16384 : 8192; }
     int64_t smem_mean() const { return smem_target > 0 ? smem_target : (int64_t)smem_slots() * 7 / 16; }
-    int smem_variant = 0;                       // tunable: 0 = 8192 slots x 512 threads x 4 k-mers in flight, 1 = 4096 x 256 x 8, 2 = 16384 x 1024 x 8, 3 = 8192 x 256 x 8, 4 = 8192 x 512 x 8
+    int smem_variant = 0;                       // tunable: 0 = 8192 slots x 512 threads x 4 k-mers in flight, 1 = 4096 x 256 x 4, 2 = 16384 x 1024 x 4, 3 = 8192 x 256 x 8, 4 = 8192 x 256 x 4
     DevBuf<uint64_t> kbuf2, list_keys; DevBuf<uint32_t> list_counts; DevBuf<unsigned long long> d_sub; DevBuf<int64_t> d_tile;
     DevBuf<unsigned int> d_ovf;
     int64_t n_list = 0, n_sub = 0, n_ovf = 0; uint32_t list_min = 1; unsigned int sub_nb2 = 0;
@@ -222,6 +227,15 @@ int build_rep_table(pc_ctx* c) {
     CU(cudaMemsetAsync(c->rfp.p, 0, (c->rcap + 8) * sizeof(unsigned short), c->stream));
     if (c->n_sel > 0)
         LAUNCH(c, pc::k_rep_build, blocks_for(c->n_sel, 256), 256, c->sel, c->n_sel, c->rtable.p, c->rcap, c->rfp.p);
+    // shared-memory filter of the probe: worth it while the bitmap stays sparse (>= 1.2 bits per repeat k-mer: fill < 57 %)
+    c->rfilter_bits = 0;
+    if (c->n_sel > 0 && c->probe_filter != 0 && (c->probe_filter == 1 || c->filter_bits * 5 >= c->n_sel * 6)) {
+        unsigned int nbits = (unsigned int)std::min<int64_t>(std::max<int64_t>(c->filter_bits, 1024), 1744896) & ~127u;
+        rc = c->rfilter.alloc(nbits / 32 + 4); if (rc) return rc;
+        CU(cudaMemsetAsync(c->rfilter.p, 0, (nbits / 32 + 4) * sizeof(unsigned int), c->stream));
+        LAUNCH(c, pc::k_filter_build, blocks_for(c->n_sel, 256), 256, c->sel, c->n_sel, nbits, c->rfilter.p);
+        c->rfilter_bits = nbits;
+    }
     return PC_OK;
 }
 
@@ -273,7 +287,7 @@ int pc_destroy(pc_ctx* c) {
     c->words.release(); c->nmask.release(); c->table_keys.release(); c->table_counts.release(); c->d_stats.release();
     c->kbuf.release(); c->kstream.release(); c->d_part_hist.release(); c->d_seg.release(); c->cross_keys.release(); c->d_cross_n.release();
     c->kbuf2.release(); c->list_keys.release(); c->list_counts.release(); c->d_sub.release(); c->d_tile.release(); c->d_ovf.release();
-    c->sel_a.release(); c->sel_b.release(); c->rs_hist.release(); c->d_counter.release(); c->rtable.release(); c->rfp.release();
+    c->sel_a.release(); c->sel_b.release(); c->rs_hist.release(); c->d_counter.release(); c->rtable.release(); c->rfp.release(); c->rfilter.release();
     c->d_chunk_row.release(); c->d_row_base.release(); c->d_row_cursor.release(); c->hits_a.release();
     c->hits_b.release(); c->d_row_nnz.release(); c->d_indptr.release(); c->d_indices.release();
     c->d_data.release(); c->d_idf.release(); c->d_tfidf.release(); c->d_df.release(); c->d_df_global.release();
@@ -681,10 +695,10 @@ static int count_buckets_smem(pc_ctx* c, int k, int pb, int n_buckets, const uin
         }
         {
             StageTimer t(c, ST_COUNT);
-            if (c->smem_variant == 1) rc = launch_count_smem<4096, 256, 8>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
-            else if (c->smem_variant == 2) rc = launch_count_smem<16384, 1024, 8>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
+            if (c->smem_variant == 1) rc = launch_count_smem<4096, 256, 4>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
+            else if (c->smem_variant == 2) rc = launch_count_smem<16384, 1024, 4>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
             else if (c->smem_variant == 3) rc = launch_count_smem<8192, 256, 8>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
-            else if (c->smem_variant == 4) rc = launch_count_smem<8192, 512, 8>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
+            else if (c->smem_variant == 4) rc = launch_count_smem<8192, 256, 4>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
             else rc = launch_count_smem<8192, 512, 4>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
             if (rc) return rc;
         }
@@ -779,6 +793,9 @@ int pc_tune(pc_ctx* c, const char* key, int64_t value) {
     else if (k == "smem_variant") c->smem_variant = (int)value;
     else if (k == "prezero") c->prezero = (int)value;
     else if (k == "probe_fp") c->probe_fp = (int)value;
+    else if (k == "probe_filter") c->probe_filter = (int)value;
+    else if (k == "probe_threads") c->probe_threads = (int)value;
+    else if (k == "filter_bits") c->filter_bits = std::max<int64_t>(1024, value);
     else if (k == "part_casfirst") c->part_casfirst = (int)value;
     else if (k == "part_minb") c->part_minb = (int)value;
     else if (k == "probe_batch") c->probe_batch = (int)value;
@@ -1356,7 +1373,24 @@ int pc_build_matrix(pc_ctx* c, const int32_t* chunk_row, int64_t n_rows, int64_t
             unsigned int grid = blocks_for(c->n_words, 256);
             // fingerprint-first walk when the 16 B/slot table is far beyond L2 (measured: +17 % at 43 MB, -9 % at 650 MB)
             const bool use_fp = c->probe_fp == 1 || (c->probe_fp < 0 && c->rcap * sizeof(pc::RepSlot) > (size_t)(256ull << 20));
-            if (use_stream) {
+            if (use_stream && c->rfilter_bits > 0 && !use_fp) {
+                // one persistent CTA of 1024 threads per SM, or two of 512 when two copies of the bitmap fit
+                size_t smem = (size_t)(c->rfilter_bits / 32 + 4) * sizeof(unsigned int);
+                const bool two = c->probe_threads == 512 && smem <= (size_t)(110 << 10);   // measured slower than one CTA of 1024
+                const int threads = two ? 512 : 1024;
+                unsigned int pgrid = (unsigned int)std::min<int64_t>(two ? 296 : 148, (c->n_words + threads - 1) / threads);
+                c->launches++;
+                if (two) {
+                    CU(cudaFuncSetAttribute(pc::k_probe_stream_filt<4, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    pc::k_probe_stream_filt<4, 512><<<pgrid, 512, smem, c->stream>>>(c->kstream.p, c->n_words, c->d_word0.p, c->n_chunks,
+                        c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, c->rfilter.p, c->rfilter_bits, c->hits_a.p, c->d_row_cursor.p);
+                } else {
+                    CU(cudaFuncSetAttribute(pc::k_probe_stream_filt<4, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    pc::k_probe_stream_filt<4, 1024><<<pgrid, 1024, smem, c->stream>>>(c->kstream.p, c->n_words, c->d_word0.p, c->n_chunks,
+                        c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, c->rfilter.p, c->rfilter_bits, c->hits_a.p, c->d_row_cursor.p);
+                }
+                CU(cudaGetLastError());
+            } else if (use_stream) {
                 if (c->probe_batch == 4)
                     LAUNCH(c, (pc::k_probe_stream<4>), grid, 256, c->kstream.p, c->n_words, c->d_word0.p, c->n_chunks,
                            c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, use_fp ? c->rfp.p : nullptr, c->hits_a.p, c->d_row_cursor.p);

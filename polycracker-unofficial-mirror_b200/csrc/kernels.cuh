@@ -1136,16 +1136,28 @@ k_probe_stream(const uint64_t* __restrict__ stream, int64_t n_words,
     int row0 = __shfl_sync(0xFFFFFFFFu, row, __ffs(on_mask) - 1);
     bool uniform = __all_sync(0xFFFFFFFFu, !lane_on || row == row0);
     const uint64_t* src = stream + w_lane0 * 32 + lane;
+    // software pipeline: the stream k-mers of the next batch are requested (DRAM) before this batch's table probes (L2)
+    // are issued -- ncu showed a third of the stall samples on the first use of the stream loads
+    uint64_t nkey[BATCH];
+#pragma unroll
+    for (int j = 0; j < BATCH; ++j) nkey[j] = lane_on ? __ldcs(src + j * 32) : PC_KEY_SENTINEL;
 #pragma unroll 1
     for (int b0 = 0; b0 < 32; b0 += BATCH) {
         int cols[BATCH];
         unsigned int hmask = 0;
+        uint64_t kcur[BATCH];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) kcur[j] = nkey[j];
+        if (lane_on && b0 + BATCH < 32) {
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j) nkey[j] = __ldcs(src + (b0 + BATCH + j) * 32);
+        }
         if (lane_on) {
             unsigned long long skey[BATCH]; uint64_t slot[BATCH]; uint4 cur[BATCH];
             unsigned int vmask = 0;
 #pragma unroll
             for (int j = 0; j < BATCH; ++j) {
-                uint64_t key = __ldcs(src + (b0 + j) * 32);
+                uint64_t key = kcur[j];
                 vmask |= (unsigned int)(key != PC_KEY_SENTINEL) << j;
                 skey[j] = ~key;
                 slot[j] = rep_slot(key, rcap);

@@ -55,10 +55,16 @@ k_sub_hist(const uint64_t* __restrict__ keys, const uint64_t* const* __restrict_
     const int64_t n_tiles = __ldg(tile_start + n_pairs);
     for (int64_t g = blockIdx.x; g < n_tiles; g += gridDim.x) {
         SegTile s = seg_tile<TILE>(keys, seg_base, seg_begin, seg_len, tile_start, n_pairs, n_seg, g);
-#pragma unroll 8
-        for (int j = 0; j < PER; ++j) {
-            int i = j * 256 + t;
-            if (i < s.lim) atomicAdd(&sh_hist[sub_of(hash64(__ldcs(s.src + i)), pb, NB2)], 1u);
+        const uint64_t* src = s.src + t;
+        const int lim = (int)s.lim - t;
+#pragma unroll
+        for (int j0 = 0; j0 < PER; j0 += 8) {                    // 8 loads in flight per thread, then their atomics
+            uint64_t kk[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) kk[j] = ((j0 + j) * 256 < lim) ? __ldcs(src + (j0 + j) * 256) : PC_KEY_SENTINEL;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (kk[j] != PC_KEY_SENTINEL) atomicAdd(&sh_hist[sub_of(hash64(kk[j]), pb, NB2)], 1u);
         }
         __syncthreads();
         for (unsigned int x = t; x < NB2; x += 256) {
@@ -163,7 +169,18 @@ k_sub_scatter(const uint64_t* __restrict__ keys, const uint64_t* const* __restri
 // The k-mers of the next batch / next sub-bucket are requested from HBM before the current batch is inserted.
 // Output: (k-mer, count) of every k-mer with count >= keep_min, appended to a list with one global atomic per
 // sub-bucket; ids of sub-buckets that did not fit go to ovf_ids.
+// The kernel is instruction-issue bound (ncu: 63 % issue active, DRAM 11 %), so the per-sub-bucket epilogue is written
+// for few instructions: every lane owns 4 consecutive slots per step (one 128-bit load of the counts, three 128-bit
+// stores to re-zero them), and the slot hash is one 32-bit multiply -- the sub-bucket was chosen by the strong 64-bit
+// mix, so inside it any cheap independent hash spreads the k-mers.
 #define PC_SMEM_PROBE_LIMIT 1024u
+template <int SLOTS>
+__device__ __forceinline__ unsigned int smem_slot(uint64_t key) {
+    constexpr int LOG = SLOTS == 4096 ? 12 : SLOTS == 8192 ? 13 : SLOTS == 16384 ? 14 : -1;
+    static_assert(LOG > 0, "table size");
+    return (((unsigned int)key ^ (unsigned int)(key >> 32)) * 0x9E3779B1u) >> (32 - LOG);
+}
+
 template <int SLOTS, int THREADS, int PER>
 __global__ void __launch_bounds__(THREADS, (2048 / THREADS) < (int)((220u << 10) / (SLOTS * 12u + 1024u)) ? (2048 / THREADS) : (int)((220u << 10) / (SLOTS * 12u + 1024u)))
 k_count_smem(const uint64_t* __restrict__ kbuf2, const unsigned long long* __restrict__ sub_off, unsigned int n_sub,
@@ -173,10 +190,10 @@ k_count_smem(const uint64_t* __restrict__ kbuf2, const unsigned long long* __res
 {
     constexpr int WARPS = THREADS / 32;
     constexpr int SPW = SLOTS / WARPS;                           // slots scanned by one warp
-    constexpr int IT = SPW / 32;
+    constexpr int IT4 = SPW / 128;                               // steps of 32 lanes x 4 slots
     constexpr unsigned int BATCH = THREADS * PER;
-    static_assert(SLOTS % (WARPS * 32) == 0 && (SLOTS & (SLOTS - 1)) == 0, "slot layout");
-    extern __shared__ unsigned long long skeys[];                // [SLOTS]
+    static_assert(SLOTS % (WARPS * 128) == 0 && IT4 * 4 <= 32, "slot layout");
+    extern __shared__ __align__(16) unsigned long long skeys[];  // [SLOTS]
     unsigned int* scnt = reinterpret_cast<unsigned int*>(skeys + SLOTS);   // [SLOTS]
     __shared__ unsigned int s_total, s_ovf;
     __shared__ unsigned long long s_gbase;
@@ -226,7 +243,7 @@ k_count_smem(const uint64_t* __restrict__ kbuf2, const unsigned long long* __res
             unsigned long long old[PER]; unsigned int slot[PER];
 #pragma unroll
             for (int j = 0; j < PER; ++j) {
-                slot[j] = (unsigned int)hash64(key[j]) & (SLOTS - 1);
+                slot[j] = smem_slot<SLOTS>(key[j]);
                 old[j] = (key[j] != PC_KEY_SENTINEL) ? atomicCAS(&skeys[slot[j]], 0ull, ~key[j]) : 0ull;
             }
 #pragma unroll
@@ -252,20 +269,29 @@ k_count_smem(const uint64_t* __restrict__ kbuf2, const unsigned long long* __res
         const bool ovf = s_ovf != 0u;
         if (!ovf) distinct += nk;
         nk = 0;
-        unsigned int c[IT];
-        unsigned int emask = 0, n_emit = 0;
+        uint4 c4[IT4];
+        unsigned int emask = 0, n_emit = 0;                      // bit (4 i + j): slot j of step i is emitted
+        const int s0 = wid * SPW + lane * 4;
 #pragma unroll
-        for (int i = 0; i < IT; ++i) {
-            int s = wid * SPW + i * 32 + lane;
-            c[i] = scnt[s];
-            bool e = !ovf && c[i] + 1u >= keep_min;
-            if (e && keep_min <= 1u) e = skeys[s] != 0ull;       // count field 0 is also what an empty slot holds
-            emask |= (unsigned int)e << i;
-            n_emit += e;
+        for (int i = 0; i < IT4; ++i) {
+            const int s = s0 + i * 128;
+            c4[i] = *reinterpret_cast<const uint4*>(scnt + s);
+            const unsigned int cc[4] = {c4[i].x, c4[i].y, c4[i].z, c4[i].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                bool e = !ovf && cc[j] + 1u >= keep_min;
+                if (e && keep_min <= 1u) e = skeys[s + j] != 0ull;   // count field 0 is also what an empty slot holds
+                emask |= (unsigned int)e << (4 * i + j);
+                n_emit += e;
+            }
         }
-        unsigned int wtot = n_emit;
+        unsigned int incl = n_emit;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) wtot += __shfl_xor_sync(0xFFFFFFFFu, wtot, o);
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned int u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if (lane >= o) incl += u;
+        }
+        const unsigned int wtot = __shfl_sync(0xFFFFFFFFu, incl, 31);
         unsigned int wbase = 0;
         if (lane == 0 && wtot) wbase = atomicAdd(&s_total, wtot);
         wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
@@ -277,18 +303,24 @@ k_count_smem(const uint64_t* __restrict__ kbuf2, const unsigned long long* __res
             if (ovf) ovf_ids[atomicAdd(n_ovf, 1u)] = this_sb;
         }
         __syncthreads();                                         // C: s_gbase valid
-        unsigned long long pos0 = s_gbase + wbase;
+        unsigned long long pos = s_gbase + wbase + (incl - n_emit);
 #pragma unroll
-        for (int i = 0; i < IT; ++i) {
-            int s = wid * SPW + i * 32 + lane;
-            bool e = (emask >> i) & 1u;
-            unsigned int bal = __ballot_sync(0xFFFFFFFFu, e);
-            if (e) {
-                unsigned long long pos = pos0 + __popc(bal & ((1u << lane) - 1u));
-                if (pos < list_cap) { list_keys[pos] = ~skeys[s]; list_counts[pos] = c[i] + 1u; }
+        for (int i = 0; i < IT4; ++i) {
+            const int s = s0 + i * 128;
+            if ((emask >> (4 * i)) & 0xFu) {
+                const unsigned int cc[4] = {c4[i].x, c4[i].y, c4[i].z, c4[i].w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if ((emask >> (4 * i + j)) & 1u) {
+                        if (pos < list_cap) { list_keys[pos] = ~skeys[s + j]; list_counts[pos] = cc[j] + 1u; }
+                        ++pos;
+                    }
             }
-            pos0 += __popc(bal);
-            skeys[s] = 0ull; scnt[s] = 0u;
+            __syncwarp();                                        // the key stores below cover other lanes' slots
+            *reinterpret_cast<uint4*>(scnt + s) = make_uint4(0u, 0u, 0u, 0u);
+            uint4* kz = reinterpret_cast<uint4*>(skeys + wid * SPW + i * 128);   // 128 slots = 64 x 16 bytes
+            kz[lane] = make_uint4(0u, 0u, 0u, 0u);
+            kz[lane + 32] = make_uint4(0u, 0u, 0u, 0u);
         }
         __syncthreads();                                         // D: table is empty again
         if (!more) break;
@@ -327,6 +359,134 @@ k_select_list(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ co
                     out_keys[pos] = __ldcs(keys + i);
                     if (out_counts) out_counts[pos] = c;
                 }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ K5, filtered probe
+// The stream probe is bound by random L2 accesses to the repeat table (ncu: DRAM 10 %, every warp on long-scoreboard;
+// half of the accesses cross the die-to-die fabric).  Most windows are NOT repeat k-mers, so a 1-bit-per-k-mer filter
+// held in SHARED memory (up to ~1.7 Mbit: one hash, load ~0.4) answers "certainly not a repeat" for about two thirds of
+// them without leaving the SM; only the rest goes to L2.  Persistent CTAs (one per SM, the filter fills its shared
+// memory) load the bitmap once and then walk word tiles.  Used when the repeat set is small enough for the filter to
+// discriminate (host side: bits >= 2 x n_selected).
+__device__ __forceinline__ unsigned int filt_bit(uint64_t key, unsigned int nbits) {
+    return (unsigned int)((((key * 0xA24BAED4963EE407ull) >> 32) * (uint64_t)nbits) >> 32);
+}
+
+__global__ void __launch_bounds__(256)
+k_filter_build(const uint64_t* __restrict__ sorted_keys, int64_t n, unsigned int nbits, unsigned int* __restrict__ bitmap)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned int b = filt_bit(sorted_keys[i], nbits);
+    atomicOr(&bitmap[b >> 5], 1u << (b & 31));
+}
+
+template <int BATCH, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
+k_probe_stream_filt(const uint64_t* __restrict__ stream, int64_t n_words,
+                    const int64_t* __restrict__ chunk_word0, int64_t n_chunks, const int32_t* __restrict__ chunk_row,
+                    const int64_t* __restrict__ row_hit_base, const RepSlot* __restrict__ rtable, uint64_t rcap,
+                    const unsigned int* __restrict__ bitmap, unsigned int nbits,
+                    int32_t* __restrict__ hits, unsigned int* __restrict__ row_cursor)
+{
+    extern __shared__ __align__(16) unsigned int sbits[];        // [(nbits + 31) / 32 rounded up to 4]
+    {
+        const unsigned int n4 = ((nbits + 31) / 32 + 3) / 4;
+        const uint4* src = reinterpret_cast<const uint4*>(bitmap);
+        uint4* dst = reinterpret_cast<uint4*>(sbits);
+        for (unsigned int i = threadIdx.x; i < n4; i += THREADS) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int64_t n_tiles = (n_words + THREADS - 1) / THREADS;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        int64_t w = tile * THREADS + threadIdx.x;
+        int64_t w_lane0 = w - lane;
+        if (w_lane0 >= n_words) continue;                        // whole warp past the end
+        int row = -1;
+        if (w < n_words) {
+            int64_t c = chunk_of_word(chunk_word0, n_chunks, w, w_lane0);
+            row = __ldg(chunk_row + c);
+        }
+        bool lane_on = row >= 0;
+        unsigned int on_mask = __ballot_sync(0xFFFFFFFFu, lane_on);
+        if (on_mask == 0u) continue;
+        int row0 = __shfl_sync(0xFFFFFFFFu, row, __ffs(on_mask) - 1);
+        bool uniform = __all_sync(0xFFFFFFFFu, !lane_on || row == row0);
+        const uint64_t* src = stream + w_lane0 * 32 + lane;
+        // software pipeline: the stream k-mers of the next batch are requested (DRAM) before this batch's table probes
+        // (L2) are issued -- ncu showed a third of the stall samples on the first use of the stream loads
+        uint64_t nkey[BATCH];
+#pragma unroll
+        for (int j = 0; j < BATCH; ++j) nkey[j] = lane_on ? __ldcs(src + j * 32) : PC_KEY_SENTINEL;
+#pragma unroll 1
+        for (int b0 = 0; b0 < 32; b0 += BATCH) {
+            int cols[BATCH];
+            unsigned int hmask = 0;
+            uint64_t kcur[BATCH];
+#pragma unroll
+            for (int j = 0; j < BATCH; ++j) kcur[j] = nkey[j];
+            if (lane_on && b0 + BATCH < 32) {
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) nkey[j] = __ldcs(src + (b0 + BATCH + j) * 32);
+            }
+            if (lane_on) {
+                unsigned long long skey[BATCH]; uint64_t slot[BATCH]; uint4 cur[BATCH];
+                unsigned int vmask = 0;
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) {
+                    uint64_t key = kcur[j];
+                    unsigned int fb = filt_bit(key, nbits);
+                    bool maybe = key != PC_KEY_SENTINEL && ((sbits[fb >> 5] >> (fb & 31)) & 1u);
+                    vmask |= (unsigned int)maybe << j;
+                    skey[j] = ~key;
+                    slot[j] = rep_slot(key, rcap);
+                }
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j)
+                    cur[j] = ((vmask >> j) & 1u) ? __ldg(reinterpret_cast<const uint4*>(rtable + slot[j])) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) {
+                    cols[j] = 0;
+                    if (!((vmask >> j) & 1u)) continue;
+                    unsigned long long ck = ((unsigned long long)cur[j].y << 32) | cur[j].x;
+                    int col = (int)cur[j].z;
+                    uint64_t s = slot[j];
+                    while (ck != 0ull && ck != skey[j]) {
+                        if (++s == rcap) s = 0;
+                        uint4 c2 = __ldg(reinterpret_cast<const uint4*>(rtable + s));
+                        ck = ((unsigned long long)c2.y << 32) | c2.x; col = (int)c2.z;
+                    }
+                    if (ck != 0ull) { cols[j] = col; hmask |= 1u << j; }
+                }
+            }
+            int nh = __popc(hmask);
+            unsigned int any = __ballot_sync(0xFFFFFFFFu, nh > 0);
+            if (any == 0u) continue;
+            int32_t* dst = nullptr;
+            if (uniform) {
+                int incl = nh;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    int v = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                unsigned int base = 0;
+                if (lane == 0) base = atomicAdd(&row_cursor[row0], (unsigned int)total);
+                base = __shfl_sync(0xFFFFFFFFu, base, 0);
+                if (nh > 0) dst = hits + __ldg(row_hit_base + row0) + base + (incl - nh);
+            } else if (nh > 0) {
+                unsigned int base = atomicAdd(&row_cursor[row], (unsigned int)nh);
+                dst = hits + __ldg(row_hit_base + row) + base;
+            }
+            if (nh > 0) {
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j)
+                    if ((hmask >> j) & 1u) dst[__popc(hmask & ((1u << j) - 1u))] = cols[j];
             }
         }
     }
