@@ -109,6 +109,17 @@ int pc_peer_open(pc_ctx* ctx, const void* ipc_handle_64, uint64_t** dev_ptr);
 int pc_peer_close(pc_ctx* ctx, uint64_t* dev_ptr);
 int pc_count_buckets_from(pc_ctx* ctx, int k, int pb, int n_buckets, const uint64_t* const* seg_base,
                           const int64_t* seg_begin, const int64_t* seg_len, int n_seg, int64_t capacity);
+/* Shared-memory count on several GPUs: the owner splits each of its buckets into nb2 sub-buckets and needs their sizes
+ * before it scatters.  Computing them itself would stream every peer segment over NVLink twice; instead every sender
+ * histograms its own bucket buffer (local HBM) and the small histograms are exchanged.
+ * pc_sub_plan: sub-buckets per bucket the count would choose for `total` k-mers in n_buckets buckets (0 when the
+ * shared-memory count is not in use: skip the rest).  pc_sub_hist: after pc_partition, hist_dev[q * nb2 + x] (device,
+ * uint64, 2^pb * nb2 entries) = local k-mers of bucket q in sub-bucket x.  pc_sub_hist_set: stage the owner's summed
+ * histogram (device, uint64[n = n_buckets * nb2], must stay valid until the count returns) for the NEXT
+ * pc_count_buckets / pc_count_buckets_from call, which then skips its own histogram pass. */
+int pc_sub_plan(pc_ctx* ctx, int64_t total, int n_buckets);
+int pc_sub_hist(pc_ctx* ctx, int pb, int nb2, uint64_t* hist_dev);
+int pc_sub_hist_set(pc_ctx* ctx, int nb2, const uint64_t* hist_dev, int64_t n);
 /* alternative exchange of pre-aggregated pairs: all (kmer,count) pairs of the local table grouped by owner rank
  * (owner = hash(kmer) % world); offsets[world+1] is a host array.  keys/counts are device buffers of
  * capacity >= distinct k-mers.  pc_merge_counts adds received pairs into the ctx table (creating it with

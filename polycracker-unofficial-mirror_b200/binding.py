@@ -64,6 +64,9 @@ _SIGS = {
     "pc_count": (C.c_int, [_vp, C.c_int, _i64]),
     "pc_count_info": (C.c_int, [_vp, _vp]),
     "pc_count_detail": (C.c_int, [_vp, _vp]),
+    "pc_sub_plan": (C.c_int, [_vp, _i64, C.c_int]),
+    "pc_sub_hist": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "pc_sub_hist_set": (C.c_int, [_vp, C.c_int, _vp, _i64]),
     "pc_dump_counts": (C.c_int, [_vp, _u32, _u32, _vp, _vp, _i64, C.c_int, _P(_i64)]),
     "pc_partition": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _P(_vp)]),
     "pc_count_buckets": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _i64]),
@@ -328,6 +331,20 @@ class Context:
         check(lib.pc_count_info(self._h, info.ctypes.data), "pc_count_info")
         return dict(capacity=int(info[0]), distinct=int(info[1]), valid_windows=int(info[2]),
                     table_bytes=int(info[3]), max_probe=int(info[4]), k=int(info[5]), partition_bits=int(info[7]))
+
+    def sub_plan(self, total, n_buckets):
+        return int(lib.pc_sub_plan(self._h, int(total), int(n_buckets)))
+
+    def sub_hist(self, pb, nb2, hist_t):
+        """hist_t: torch CUDA int64 tensor with 2^pb * nb2 elements (filled with this rank's sub-bucket sizes)."""
+        assert hist_t.is_cuda and hist_t.is_contiguous() and hist_t.numel() == (1 << pb) * nb2
+        check(lib.pc_sub_hist(self._h, int(pb), int(nb2), hist_t.data_ptr()), "pc_sub_hist")
+
+    def sub_hist_set(self, nb2, hist_t):
+        """Stage the owner's summed histogram (torch CUDA int64, n_buckets * nb2) for the next count_buckets[_from];
+        the tensor must stay alive until that call returns."""
+        assert hist_t.is_cuda and hist_t.is_contiguous()
+        check(lib.pc_sub_hist_set(self._h, int(nb2), hist_t.data_ptr(), hist_t.numel()), "pc_sub_hist_set")
 
     def count_detail(self):
         d = np.zeros(8, np.int64)

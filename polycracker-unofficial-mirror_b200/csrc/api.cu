@@ -142,6 +142,8 @@ struct pc_ctx {
     DevBuf<uint64_t> kbuf2, list_keys; DevBuf<uint32_t> list_counts; DevBuf<unsigned long long> d_sub; DevBuf<int64_t> d_tile;
     DevBuf<unsigned int> d_ovf;
     int64_t n_list = 0, n_sub = 0, n_ovf = 0; uint32_t list_min = 1; unsigned int sub_nb2 = 0;
+    // multi-GPU: level-2 histogram computed by the senders (pc_sub_hist), summed by the owner and staged for the next count
+    const unsigned long long* staged_hist = nullptr; int64_t staged_n = 0; unsigned int staged_nb2 = 0;
 
     // N1 subgenome-extraction session (pc_sub_*): per-subgenome dictionaries of the k being compared, then per k the
     // differential sets and their union mask table
@@ -632,6 +634,11 @@ static int launch_count_smem(pc_ctx* c, unsigned int n_sub, unsigned long long l
 }
 }  // extern "C++"
 
+static unsigned int sub_plan(const pc_ctx* c, int64_t total, int n_buckets) {
+    int64_t nb2 = (total + (int64_t)n_buckets * c->smem_mean() - 1) / ((int64_t)n_buckets * c->smem_mean());
+    return (unsigned int)std::min<int64_t>(PC_SUB_MAX, std::max<int64_t>(1, nb2));
+}
+
 static int count_buckets_smem(pc_ctx* c, int k, int pb, int n_buckets, const uint64_t* keys_dev, const int64_t* seg_begin,
                               const int64_t* seg_len, int n_seg, const uint64_t* const* seg_base_host) {
     int rc;
@@ -646,8 +653,12 @@ static int count_buckets_smem(pc_ctx* c, int k, int pb, int n_buckets, const uin
     }
     if (c->keep_min < 1) c->keep_min = 1;
     const int64_t n_tiles = tile_start[n_pairs];
-    int64_t nb2 = (total + (int64_t)n_buckets * c->smem_mean() - 1) / ((int64_t)n_buckets * c->smem_mean());
-    const unsigned int NB2 = (unsigned int)std::min<int64_t>(PC_SUB_MAX, std::max<int64_t>(1, nb2));
+    unsigned int NB2 = sub_plan(c, total, n_buckets);
+    const unsigned long long* staged = nullptr;
+    if (c->staged_hist && c->staged_nb2 >= 1 && c->staged_nb2 <= PC_SUB_MAX && c->staged_n == (int64_t)n_buckets * c->staged_nb2) {
+        staged = c->staged_hist; NB2 = c->staged_nb2;
+    }
+    c->staged_hist = nullptr; c->staged_n = 0; c->staged_nb2 = 0;  // one-shot
     const int64_t n_sub = (int64_t)n_buckets * NB2;
     if (n_sub >= (1ll << 31)) return fail(PC_EINVAL, "too many sub-buckets");
     c->k = k; c->pb = pb; c->sub_nb2 = NB2; c->n_sub = n_sub; c->cross_valid = false;
@@ -680,10 +691,14 @@ static int count_buckets_smem(pc_ctx* c, int k, int pb, int n_buckets, const uin
         {
             StageTimer t(c, ST_PART2);
             unsigned int grid = (unsigned int)std::min<int64_t>(148 * 8, n_tiles);
-            c->launches++;
-            pc::k_sub_hist<TILE><<<grid, 256, NB2 * sizeof(unsigned int), c->stream>>>(
-                keys_dev, d_base, d_beg, d_len, c->d_tile.p, (int)n_pairs, n_seg, pb, NB2, sub_off);
-            CU(cudaGetLastError());
+            if (staged) {
+                CU(cudaMemcpyAsync(sub_off, staged, (size_t)n_sub * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
+            } else {
+                c->launches++;
+                pc::k_sub_hist<TILE><<<grid, 256, NB2 * sizeof(unsigned int), c->stream>>>(
+                    keys_dev, d_base, d_beg, d_len, c->d_tile.p, (int)n_pairs, n_seg, pb, NB2, sub_off);
+                CU(cudaGetLastError());
+            }
             LAUNCH(c, pc::k_rs_scan<unsigned long long>, 1, 1024, sub_off, n_sub);
             size_t smem = (size_t)TILE * 8 + (size_t)NB2 * 8 + (size_t)NB2 * 4 + ((size_t)NB2 + 2) * 4 + (size_t)TILE * 2 + 16;
             CU(cudaFuncSetAttribute(pc::k_sub_scatter<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -937,6 +952,48 @@ int pc_count_buckets(pc_ctx* c, int k, int pb, int n_buckets, const uint64_t* ke
     CU(cudaMemcpyAsync(c->d_stats.p, &z, sizeof z, cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return do_count_buckets(c, k, pb, n_buckets, keys_dev, seg_begin, seg_len, n_seg, capacity);
+}
+
+// ---- sender-side level-2 histogram (multi-GPU): the owner would otherwise read every peer segment twice over NVLink
+int pc_sub_plan(pc_ctx* c, int64_t total, int n_buckets) {
+    if (!c || total < 0 || n_buckets < 1) return 0;
+    if (!smem_mode(c)) return 0;
+    return (int)sub_plan(c, total, n_buckets);
+}
+
+int pc_sub_hist(pc_ctx* c, int pb, int nb2, uint64_t* hist_dev) {
+    int rc = use_device(c); if (rc) return rc;
+    if (pb < 0 || pb > 12 || nb2 < 1 || nb2 > PC_SUB_MAX || !hist_dev) return fail(PC_EINVAL, "bad pc_sub_hist arguments");
+    const int64_t P = (int64_t)1 << pb;
+    if ((int64_t)c->h_bucket_off.size() != P + 1) return fail(PC_ESTATE, "pc_sub_hist needs the buckets of pc_partition(pb = %d)", pb);
+    constexpr int TILE = 8192;
+    std::vector<int64_t> desc(3 * P + 1, 0);                   // seg_begin[P], seg_len[P], tile_start[P + 1]
+    for (int64_t q = 0; q < P; ++q) {
+        desc[q] = c->h_bucket_off[q]; desc[P + q] = c->h_bucket_off[q + 1] - c->h_bucket_off[q];
+        desc[2 * P + q + 1] = desc[2 * P + q] + (desc[P + q] + TILE - 1) / TILE;
+    }
+    const int64_t n_tiles = desc[3 * P];
+    rc = c->d_tile.alloc((size_t)3 * P + 1); if (rc) return rc;
+    CU(cudaMemcpyAsync(c->d_tile.p, desc.data(), desc.size() * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(hist_dev, 0, (size_t)P * nb2 * sizeof(uint64_t), c->stream));
+    if (n_tiles > 0) {
+        StageTimer t(c, ST_PART2);
+        unsigned int grid = (unsigned int)std::min<int64_t>(148 * 8, n_tiles);
+        c->launches++;
+        pc::k_sub_hist<TILE><<<grid, 256, (size_t)nb2 * sizeof(unsigned int), c->stream>>>(
+            c->kbuf.p, nullptr, c->d_tile.p, c->d_tile.p + P, c->d_tile.p + 2 * P, (int)P, 1, pb, (unsigned int)nb2,
+            reinterpret_cast<unsigned long long*>(hist_dev));
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(c->stream));                      // the host descriptor goes away
+    return PC_OK;
+}
+
+int pc_sub_hist_set(pc_ctx* c, int nb2, const uint64_t* hist_dev, int64_t n) {
+    if (!c) return fail(PC_EINVAL, "null context");
+    if (!hist_dev || nb2 < 1 || nb2 > PC_SUB_MAX || n < nb2 || n % nb2) return fail(PC_EINVAL, "bad pc_sub_hist_set arguments");
+    c->staged_hist = reinterpret_cast<const unsigned long long*>(hist_dev); c->staged_n = n; c->staged_nb2 = (unsigned int)nb2;
+    return PC_OK;
 }
 
 int pc_count_info(pc_ctx* c, int64_t info[8]) {

@@ -196,6 +196,24 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
     mark("bucket_sizes_allgather")
     if hasattr(ctx, "tune"):
         ctx.tune(keep_min=dump_floor(k))                                  # the owners keep what the reference's counter dumps
+    staged_hist = None
+    if use_peer and hasattr(ctx, "sub_plan"):
+        # shared-memory count: the owner needs the sizes of its sub-buckets before it scatters.  Every sender histograms
+        # its own bucket buffer (local HBM) and the small histograms travel, instead of the owner streaming every peer
+        # segment over NVLink a second time.  One fan-out for all ranks, from the all-gathered bucket sizes.
+        nb2 = max(ctx.sub_plan(int(sizes_all[:, q_lo[r]:q_lo[r + 1]].sum()), max(1, q_lo[r + 1] - q_lo[r]))
+                  for r in range(world))
+        if nb2 > 0 and all(q_lo[r + 1] > q_lo[r] for r in range(world)):
+            h_local = torch.empty(P * nb2, dtype=torch.int64, device=device)
+            ctx.sub_hist(pb, nb2, h_local)
+            n_mine = (q_lo[rank + 1] - q_lo[rank]) * nb2
+            h_recv = torch.empty(world * n_mine, dtype=torch.int64, device=device)
+            dist.all_to_all_single(h_recv, h_local, output_split_sizes=[n_mine] * world,
+                                   input_split_sizes=[(q_lo[r + 1] - q_lo[r]) * nb2 for r in range(world)])
+            staged_hist = h_recv.view(world, n_mine).sum(dim=0).contiguous()
+            _stream_sync(torch, device)
+            ctx.sub_hist_set(nb2, staged_hist)
+            mark("sub_hist_exchange")
     if use_peer:
         # 2a. fused exchange: the owner's count kernel reads every sender's slice straight out of that sender's bucket
         # buffer over NVLink (CUDA IPC mapping).  The all-gather of the bucket sizes above is the barrier that says

@@ -63,7 +63,7 @@ def _worker(rank, world, port, tmpdir, part_mode, exchange):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("part_mode,exchange", [(0, "nccl"), (1, "nccl"), (1, "peer")])
+@pytest.mark.parametrize("part_mode,exchange", [(0, "nccl"), (1, "nccl"), (1, "peer"), (2, "nccl"), (2, "peer"), (-1, "peer")])
 def test_two_gpus_nccl_match_oracle(tmp_path, part_mode, exchange):
     from polycracker_b200 import binding, synth
     from tests import util
