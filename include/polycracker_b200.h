@@ -197,6 +197,19 @@ int pc_sub_mapback(pc_ctx* ctx, int32_t* coverage, int loc);
 #define PC_REL_HITS    16
 int pc_release(pc_ctx* ctx, int what);
 
+/* Small device -> host read-back (bytes a multiple of 4, up to ~256 KB; larger or odd sizes fall back to a plain copy),
+ * synchronous on the ctx stream.  Unlike cudaMemcpy it does not queue on a copy engine, so it is not delayed by a bulk
+ * transfer of a neighbouring pipeline step (the context's own counters travel the same way). */
+int pc_read_back(pc_ctx* ctx, void* dst_host, const void* src_dev, int64_t bytes);
+
+/* ---- copies made by SMs -----------------------------------------------------------------------------------
+ * dst/src: device memory or PAGE-LOCKED host memory (mapped into the device under unified addressing), 16-byte aligned
+ * (otherwise the call falls back to cudaMemcpyAsync).  Enqueues a small grid (n_ctas CTAs, 0 = 32) on `stream` (NULL =
+ * the ctx stream) that moves the bytes with 128-bit loads/stores.  For overlapping the bulk H2D / D2H of neighbouring
+ * steps with this context's kernels without putting 400 MB transfers in front of its own tiny copies on the copy
+ * engines (polycracker_b200/overlap.py). */
+int pc_copy_async(pc_ctx* ctx, void* dst, const void* src, int64_t bytes, void* stream, int n_ctas);
+
 /* ---- measurement ------------------------------------------------------------------------------------------
  * CUDA-event time (ms) of the last run of each stage on the ctx stream.  Index: 0 h2d, 1 pack, 2 table-init,
  * 3 count, 4 select(scan), 5 sort, 6 repeat-table, 7 probe, 8 row-sort, 9 emit, 10 tfidf, 11 d2h, 12 export, 13 merge,

@@ -64,6 +64,8 @@ _SIGS = {
     "pc_count": (C.c_int, [_vp, C.c_int, _i64]),
     "pc_count_info": (C.c_int, [_vp, _vp]),
     "pc_count_detail": (C.c_int, [_vp, _vp]),
+    "pc_copy_async": (C.c_int, [_vp, _vp, _vp, _i64, _vp, C.c_int]),
+    "pc_read_back": (C.c_int, [_vp, _vp, _vp, _i64]),
     "pc_sub_plan": (C.c_int, [_vp, _i64, C.c_int]),
     "pc_sub_hist": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "pc_sub_hist_set": (C.c_int, [_vp, C.c_int, _vp, _i64]),
@@ -345,6 +347,27 @@ class Context:
         the tensor must stay alive until that call returns."""
         assert hist_t.is_cuda and hist_t.is_contiguous()
         check(lib.pc_sub_hist_set(self._h, int(nb2), hist_t.data_ptr(), hist_t.numel()), "pc_sub_hist_set")
+
+    def to_host(self, tensor):
+        """numpy copy of a small CUDA tensor, read back through the context's mailbox (pc_read_back): ordered on the
+        context stream, never queued behind a bulk copy on a copy engine."""
+        import torch
+        t = tensor.contiguous()
+        np_dtype = {torch.int64: np.int64, torch.int32: np.int32, torch.uint8: np.uint8, torch.float32: np.float32,
+                    torch.float64: np.float64}[t.dtype]
+        out = np.empty(tuple(t.shape), np_dtype)
+        if t.numel():
+            check(lib.pc_read_back(self._h, out.ctypes.data, _vp(t.data_ptr()), t.numel() * t.element_size()),
+                  "pc_read_back")
+        return out
+
+    def copy_async(self, dst, src, stream=None, n_ctas=0):
+        """dst / src: torch tensors (CUDA, or page-locked CPU) of equal byte size; the copy is made by SMs on `stream`
+        (raw handle; None = the context stream).  See pc_copy_async."""
+        nb = src.numel() * src.element_size()
+        assert nb == dst.numel() * dst.element_size() and src.is_contiguous() and dst.is_contiguous()
+        check(lib.pc_copy_async(self._h, _vp(dst.data_ptr()), _vp(src.data_ptr()), nb, _vp(int(stream or 0)), int(n_ctas)),
+              "pc_copy_async")
 
     def count_detail(self):
         d = np.zeros(8, np.int64)

@@ -72,6 +72,10 @@ struct pc_ctx {
     cudaEvent_t ev[ST_N][2];
     bool ev_used[ST_N];
     int64_t launches = 0;
+    // read-back mailbox: page-locked host memory the device writes small results into (see read_small)
+    uint8_t* mailbox = nullptr; size_t mailbox_cap = 0, mailbox_used = 0;
+    struct PendingRead { void* dst; size_t off, bytes; };
+    std::vector<PendingRead> pending_reads;
 
     // sequences
     DevBuf<uint8_t> ascii; int64_t ascii_padded = 0;
@@ -138,6 +142,7 @@ struct pc_ctx {
     int64_t smem_target = 0;                    // tunable: mean k-mer instances per sub-bucket (0 = 7/16 of the table slots)
     int smem_slots() const { return smem_variant == 1 ? 4096 : smem_variant == 2 ? 16384 : 8192; }
     int64_t smem_mean() const { return smem_target > 0 ? smem_target : (int64_t)smem_slots() * 7 / 16; }
+    int scatter_variant = 0;                    // tunable: 0 = two shared atomics per k-mer (256 x 32), 1 = one returning atomic (512 x 16)
     int smem_variant = 0;                       // tunable: 0 = 8192 slots x 512 threads x 4 k-mers in flight, 1 = 4096 x 256 x 4, 2 = 16384 x 1024 x 4, 3 = 8192 x 256 x 8, 4 = 8192 x 256 x 4
     DevBuf<uint64_t> kbuf2, list_keys; DevBuf<uint32_t> list_counts; DevBuf<unsigned long long> d_sub; DevBuf<int64_t> d_tile;
     DevBuf<unsigned int> d_ovf;
@@ -180,18 +185,53 @@ struct StageTimer {
         CU(cudaGetLastError());                                                                    \
     } while (0)
 
+// Small device -> host read-backs (counters, bucket offsets) do not use cudaMemcpy: a copy engine serves its queue in
+// order, so behind the bulk D2H of a neighbouring pipeline step (overlap.py) every 8-byte read waited for hundreds of
+// megabytes and the steps serialised (measured: 35 ms instead of 20 ms per step with kernel times unchanged).  A tiny
+// kernel writes the value into a page-locked, device-mapped mailbox instead; sync_stream() hands it to the caller.
+__global__ void k_mail(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, size_t n_words) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
+int read_small(pc_ctx* c, void* dst, const void* src_dev, size_t bytes) {
+    if (bytes == 0) return PC_OK;
+    if (!c->mailbox || (bytes & 3) || ((uintptr_t)src_dev & 3) || bytes > c->mailbox_cap - c->mailbox_used) {
+        CU(cudaMemcpyAsync(dst, src_dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+        return PC_OK;
+    }
+    size_t off = c->mailbox_used;
+    size_t words = bytes / 4;
+    k_mail<<<(unsigned int)std::min<size_t>(64, (words + 255) / 256), 256, 0, c->stream>>>(
+        static_cast<const uint32_t*>(src_dev), reinterpret_cast<uint32_t*>(c->mailbox + off), words);
+    CU(cudaGetLastError());
+    c->pending_reads.push_back({dst, off, bytes});
+    c->mailbox_used = (off + bytes + 15) & ~(size_t)15;
+    return PC_OK;
+}
+
+int sync_stream(pc_ctx* c) {
+    CU(cudaStreamSynchronize(c->stream));
+    for (const auto& r : c->pending_reads) memcpy(r.dst, c->mailbox + r.off, r.bytes);
+    c->pending_reads.clear();
+    c->mailbox_used = 0;
+    return PC_OK;
+}
+#define SYNC(ctx) do { int rc_sync_ = sync_stream(ctx); if (rc_sync_) return rc_sync_; } while (0)
+#define READ_SMALL(ctx, dst, src, bytes) do { int rc_rd_ = read_small(ctx, dst, src, bytes); if (rc_rd_) return rc_rd_; } while (0)
+
 inline unsigned int blocks_for(int64_t n, int per) { return (unsigned int)std::max<int64_t>(1, (n + per - 1) / per); }
 
 int use_device(pc_ctx* c) {
     if (!c) return fail(PC_EINVAL, "null context");
     CU(cudaSetDevice(c->device));
+    c->pending_reads.clear(); c->mailbox_used = 0;            // a call that failed half-way leaves no stale read-backs
     return PC_OK;
 }
 
 int copy_out(pc_ctx* c, void* dst, const void* src_dev, size_t bytes, int loc) {
     if (bytes == 0) return PC_OK;
     CU(cudaMemcpyAsync(dst, src_dev, bytes, loc == PC_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
-    if (loc == PC_HOST) CU(cudaStreamSynchronize(c->stream));
+    if (loc == PC_HOST) SYNC(c);
     return PC_OK;
 }
 
@@ -275,6 +315,10 @@ int pc_create(int device, pc_ctx** out) {
     for (int i = 0; i < ST_N; ++i) {
         CU(cudaEventCreate(&c->ev[i][0])); CU(cudaEventCreate(&c->ev[i][1])); c->ev_used[i] = false;
     }
+    c->mailbox_cap = 256 << 10;
+    if (cudaHostAlloc(reinterpret_cast<void**>(&c->mailbox), c->mailbox_cap, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError(); c->mailbox = nullptr; c->mailbox_cap = 0;          // read_small falls back to cudaMemcpyAsync
+    }
     int rc = c->d_stats.alloc(1); if (rc) { delete c; return rc; }
     rc = c->d_counter.alloc(64); if (rc) { delete c; return rc; }
     *out = c;
@@ -295,6 +339,7 @@ int pc_destroy(pc_ctx* c) {
     c->d_data.release(); c->d_idf.release(); c->d_tfidf.release(); c->d_df.release(); c->d_df_global.release();
     c->sub_clear();
     for (int i = 0; i < ST_N; ++i) { cudaEventDestroy(c->ev[i][0]); cudaEventDestroy(c->ev[i][1]); }
+    if (c->mailbox) cudaFreeHost(c->mailbox);
     cudaStreamDestroy(c->own_stream);
     cudaStreamDestroy(c->aux_stream);
     cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
@@ -310,7 +355,7 @@ int pc_set_stream(pc_ctx* c, void* s) {
 
 int pc_sync(pc_ctx* c) {
     int rc = use_device(c); if (rc) return rc;
-    CU(cudaStreamSynchronize(c->stream));
+    SYNC(c);
     return PC_OK;
 }
 
@@ -400,7 +445,7 @@ int pc_load_sequences(pc_ctx* c, const uint8_t* ascii, int64_t n_bytes, int loc,
                c->d_len.p, n_chunks, wsum + 1, c->words.p, c->nmask.p);
     }
     // the h_* vectors are re-used by later host code; the async copies above read them now
-    CU(cudaStreamSynchronize(c->stream));
+    SYNC(c);
     c->loaded = true;
     return PC_OK;
 }
@@ -477,8 +522,8 @@ static int table_prepare(pc_ctx* c, int k, int64_t capacity, bool reset_stats = 
 }
 
 static int fetch_stats(pc_ctx* c) {
-    CU(cudaMemcpyAsync(&c->h_stats, c->d_stats.p, sizeof(pc::CountStats), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    READ_SMALL(c, &c->h_stats, c->d_stats.p, sizeof(pc::CountStats));
+    SYNC(c);
     if (c->h_stats.overflow)
         return fail(PC_ENOMEM, "count table overflow: %llu insertions hit the probe limit (capacity %llu)",
                     c->h_stats.overflow, (unsigned long long)c->capacity);
@@ -536,9 +581,9 @@ static int do_partition(pc_ctx* c, int k, int pb) {
     }
     c->h_bucket_off.assign(P + 1, 0);
     static_assert(sizeof(unsigned long long) == sizeof(int64_t), "offset width");
-    CU(cudaMemcpyAsync(c->h_bucket_off.data(), bucket_off, (P + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(&c->h_stats, c->d_stats.p, sizeof(pc::CountStats), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    READ_SMALL(c, c->h_bucket_off.data(), bucket_off, (P + 1) * sizeof(int64_t));
+    READ_SMALL(c, &c->h_stats, c->d_stats.p, sizeof(pc::CountStats));
+    SYNC(c);
     return PC_OK;
 }
 
@@ -704,8 +749,14 @@ static int count_buckets_smem(pc_ctx* c, int k, int pb, int n_buckets, const uin
             CU(cudaFuncSetAttribute(pc::k_sub_scatter<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             grid = (unsigned int)std::min<int64_t>(148 * 2, n_tiles);
             c->launches++;
-            pc::k_sub_scatter<TILE><<<grid, 256, smem, c->stream>>>(
-                keys_dev, d_base, d_beg, d_len, c->d_tile.p, (int)n_pairs, n_seg, pb, NB2, sub_off, sub_cur, c->kbuf2.p);
+            if (c->scatter_variant == 1) {
+                CU(cudaFuncSetAttribute((pc::k_sub_scatter_r<TILE, 512>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                pc::k_sub_scatter_r<TILE, 512><<<grid, 512, smem, c->stream>>>(
+                    keys_dev, d_base, d_beg, d_len, c->d_tile.p, (int)n_pairs, n_seg, pb, NB2, sub_off, sub_cur, c->kbuf2.p);
+            } else {
+                pc::k_sub_scatter<TILE><<<grid, 256, smem, c->stream>>>(
+                    keys_dev, d_base, d_beg, d_len, c->d_tile.p, (int)n_pairs, n_seg, pb, NB2, sub_off, sub_cur, c->kbuf2.p);
+            }
             CU(cudaGetLastError());
         }
         {
@@ -719,8 +770,8 @@ static int count_buckets_smem(pc_ctx* c, int k, int pb, int n_buckets, const uin
         }
     }
     unsigned long long h_nlist = 0; unsigned int h_novf = 0;
-    CU(cudaMemcpyAsync(&h_nlist, d_nlist, sizeof h_nlist, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(&h_novf, d_novf, sizeof h_novf, cudaMemcpyDeviceToHost, c->stream));
+    READ_SMALL(c, &h_nlist, d_nlist, sizeof h_nlist);
+    READ_SMALL(c, &h_novf, d_novf, sizeof h_novf);
     rc = fetch_stats(c); if (rc) return rc;                   // synchronises
     c->n_ovf = h_novf;
     if (h_novf > 0) {
@@ -728,9 +779,9 @@ static int count_buckets_smem(pc_ctx* c, int k, int pb, int n_buckets, const uin
         // append its survivors to the list
         std::vector<unsigned int> ids(h_novf);
         std::vector<unsigned long long> off(n_sub + 1);
-        CU(cudaMemcpyAsync(ids.data(), c->d_ovf.p, (size_t)h_novf * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaMemcpyAsync(off.data(), sub_off, (size_t)(n_sub + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
+        READ_SMALL(c, ids.data(), c->d_ovf.p, (size_t)h_novf * sizeof(unsigned int));
+        READ_SMALL(c, off.data(), sub_off, (size_t)(n_sub + 1) * sizeof(unsigned long long));
+        SYNC(c);
         std::sort(ids.begin(), ids.end());
         std::vector<int64_t> fb_begin(h_novf), fb_len(h_novf);
         int64_t fb_total = 0;
@@ -745,8 +796,8 @@ static int count_buckets_smem(pc_ctx* c, int k, int pb, int n_buckets, const uin
         unsigned int grid = (unsigned int)std::min<uint64_t>((c->capacity + 1023) / 1024, 148ull * 64);
         LAUNCH(c, pc::k_select, grid, 256, c->table(), c->capacity, c->keep_min, 0xFFFFFFFFu, c->list_keys.p, c->list_counts.p,
                list_cap, d_nlist);
-        CU(cudaMemcpyAsync(&h_nlist, d_nlist, sizeof h_nlist, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
+        READ_SMALL(c, &h_nlist, d_nlist, sizeof h_nlist);
+        SYNC(c);
         c->pb = pb; c->part_S = 0; c->capacity = (uint64_t)n_sub * (uint64_t)c->smem_slots();
     }
     if (h_nlist > list_cap) return fail(PC_ESTATE, "k-mer list overflow: %llu entries for %llu slots", h_nlist, list_cap);
@@ -767,7 +818,7 @@ static int do_count_buckets(pc_ctx* c, int k, int pb, int n_buckets, const uint6
 // and the hit buffers are each tens of GB at Gbp scale and are never needed at the same time).
 int pc_release(pc_ctx* c, int what) {
     int rc = use_device(c); if (rc) return rc;
-    CU(cudaStreamSynchronize(c->stream));
+    SYNC(c);
     if (c->zeroed_slots > 0) { CU(cudaStreamSynchronize(c->aux_stream)); c->zeroed_slots = 0; }
     if (what & PC_REL_ASCII) { c->ascii.release(); c->ascii_padded = 0; }
     if (what & PC_REL_BUCKETS) { c->kbuf.release(); c->kbuf2.release(); }
@@ -806,6 +857,7 @@ int pc_tune(pc_ctx* c, const char* key, int64_t value) {
     else if (k == "keep_min") c->keep_min = (uint32_t)std::max<int64_t>(1, value);
     else if (k == "smem_target") c->smem_target = value <= 0 ? 0 : std::max<int64_t>(64, value);
     else if (k == "smem_variant") c->smem_variant = (int)value;
+    else if (k == "scatter_variant") c->scatter_variant = (int)value;
     else if (k == "prezero") c->prezero = (int)value;
     else if (k == "probe_fp") c->probe_fp = (int)value;
     else if (k == "probe_filter") c->probe_filter = (int)value;
@@ -936,7 +988,7 @@ int pc_count_buckets_from(pc_ctx* c, int k, int pb, int n_buckets, const uint64_
     unsigned long long keep = c->h_stats.valid_windows;
     pc::CountStats z{}; z.valid_windows = keep;
     CU(cudaMemcpyAsync(c->d_stats.p, &z, sizeof z, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    SYNC(c);
     return do_count_buckets(c, k, pb, n_buckets, nullptr, seg_begin, seg_len, n_seg, capacity, seg_base);
 }
 
@@ -950,7 +1002,7 @@ int pc_count_buckets(pc_ctx* c, int k, int pb, int n_buckets, const uint64_t* ke
     unsigned long long keep = c->h_stats.valid_windows;        // pc_partition already counted the local windows
     pc::CountStats z{}; z.valid_windows = keep;
     CU(cudaMemcpyAsync(c->d_stats.p, &z, sizeof z, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    SYNC(c);
     return do_count_buckets(c, k, pb, n_buckets, keys_dev, seg_begin, seg_len, n_seg, capacity);
 }
 
@@ -985,7 +1037,7 @@ int pc_sub_hist(pc_ctx* c, int pb, int nb2, uint64_t* hist_dev) {
             reinterpret_cast<unsigned long long*>(hist_dev));
         CU(cudaGetLastError());
     }
-    CU(cudaStreamSynchronize(c->stream));                      // the host descriptor goes away
+    SYNC(c);                      // the host descriptor goes away
     return PC_OK;
 }
 
@@ -1035,8 +1087,8 @@ static int select_into(pc_ctx* c, uint32_t low, uint32_t high, uint64_t* keys_de
            (unsigned long long)cap, c->d_counter.p);
     }
     unsigned long long n = 0;
-    CU(cudaMemcpyAsync(&n, c->d_counter.p, sizeof n, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    READ_SMALL(c, &n, c->d_counter.p, sizeof n);
+    SYNC(c);
     *n_out = (int64_t)n;
     return PC_OK;
 }
@@ -1074,13 +1126,13 @@ int pc_export_by_owner(pc_ctx* c, int world, uint64_t* keys_dev, uint32_t* count
     unsigned int grid = (unsigned int)std::min<uint64_t>((c->capacity + 255) / 256, 148ull * 16);
     LAUNCH(c, pc::k_owner_hist, grid, 256, c->table(), c->capacity, (unsigned int)world, c->d_counter.p);
     unsigned long long hist[64];
-    CU(cudaMemcpyAsync(hist, c->d_counter.p, world * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
+    READ_SMALL(c, hist, c->d_counter.p, world * sizeof(unsigned long long));
+    SYNC(c);
     unsigned long long start[64]; offsets[0] = 0;
     for (int r = 0; r < world; ++r) { start[r] = (unsigned long long)offsets[r]; offsets[r + 1] = offsets[r] + (int64_t)hist[r]; }
     CU(cudaMemcpyAsync(c->d_counter.p, start, world * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
     LAUNCH(c, pc::k_owner_scatter, grid, 256, c->table(), c->capacity, (unsigned int)world, c->d_counter.p, keys_dev, counts_dev);
-    CU(cudaStreamSynchronize(c->stream));
+    SYNC(c);
     return PC_OK;
 }
 
@@ -1112,7 +1164,7 @@ int pc_sub_begin(pc_ctx* c, int n_groups) {
     int rc = use_device(c); if (rc) return rc;
     if (n_groups < 1 || n_groups > pc::kMaxGroups)
         return fail(PC_EINVAL, "n_groups = %d unsupported: 1..%d subgenomes per session", n_groups, pc::kMaxGroups);
-    CU(cudaStreamSynchronize(c->stream));
+    SYNC(c);
     c->sub_clear();
     c->sub_groups = n_groups;
     return PC_OK;
@@ -1176,8 +1228,8 @@ int pc_sub_compare(pc_ctx* c, double ratio_threshold, double default_value, int6
             CU(cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned long long), c->stream));
             LAUNCH(c, pc::k_diff_test, blocks_for(d.n, 256), 256, d.keys.p, d.counts.p, d.n, others, ratio_threshold,
                    default_value, c->sub_tmp_a.p, c->d_counter.p);
-            CU(cudaMemcpyAsync(&nd, c->d_counter.p, sizeof nd, cudaMemcpyDeviceToHost, c->stream));
-            CU(cudaStreamSynchronize(c->stream));
+            READ_SMALL(c, &nd, c->d_counter.p, sizeof nd);
+            SYNC(c);
         }
         int64_t n = (int64_t)nd;
         uint64_t* sorted = nullptr;
@@ -1199,7 +1251,7 @@ int pc_sub_compare(pc_ctx* c, double ratio_threshold, double default_value, int6
     for (int g = 0; g < G; ++g)
         if (L.n_diff[g] > 0)
             LAUNCH(c, pc::k_mask_build, blocks_for(L.n_diff[g], 256), 256, L.diff_keys[g].p, L.n_diff[g], 1 << g, L.mask.p, L.cap);
-    CU(cudaStreamSynchronize(c->stream));
+    SYNC(c);
     for (int g = 0; g < G; ++g) {                              // the dictionaries of this k are done
         pc_ctx::SubDict& d = c->sub_dict[g];
         d.table.release(); d.keys.release(); d.counts.release(); d.cap = 0; d.n = 0; d.set = false;
@@ -1256,8 +1308,8 @@ int pc_select(pc_ctx* c, uint32_t low, uint32_t high, int use_high, int64_t samp
         // K4 was fused into the count: the k-mers that reached `low` are already listed
         StageTimer t(c, ST_SELECT);
         unsigned long long nc = 0;
-        CU(cudaMemcpyAsync(&nc, c->d_cross_n.p, sizeof nc, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
+        READ_SMALL(c, &nc, c->d_cross_n.p, sizeof nc);
+        SYNC(c);
         n = (int64_t)nc;
         rc = c->sel_a.alloc(std::max<int64_t>(n, 1024)); if (rc) return rc;
         if (n) CU(cudaMemcpyAsync(c->sel_a.p, c->cross_keys.p, n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
@@ -1322,13 +1374,13 @@ int pc_set_selected(pc_ctx* c, const uint64_t* keys, int64_t n, int k, int loc, 
         unsigned long long dups = 0;
         CU(cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned long long), c->stream));
         LAUNCH(c, pc::k_count_dups, blocks_for(n, 256), 256, sorted, n, c->d_counter.p);
-        CU(cudaMemcpyAsync(&dups, c->d_counter.p, sizeof dups, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
+        READ_SMALL(c, &dups, c->d_counter.p, sizeof dups);
+        SYNC(c);
         nu = (unsigned long long)n;
         if (dups) {                                            // rare: a k-mer FASTA listing a k-mer (or both strands) twice
             LAUNCH(c, pc::k_unique_sorted_single, 1, 1024, sorted, n, other, c->d_counter.p);
-            CU(cudaMemcpyAsync(&nu, c->d_counter.p, sizeof nu, cudaMemcpyDeviceToHost, c->stream));
-            CU(cudaStreamSynchronize(c->stream));
+            READ_SMALL(c, &nu, c->d_counter.p, sizeof nu);
+            SYNC(c);
             result = other;
         }
     }
@@ -1373,8 +1425,8 @@ static int rows_to_csr(pc_ctx* c, int64_t n_rows) {
             LAUNCH(c, pc::k_indptr, 1, 1024, c->d_row_nnz.p, n_rows, c->d_indptr.p);
         }
         int64_t total = 0;
-        CU(cudaMemcpyAsync(&total, c->d_indptr.p + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
+        READ_SMALL(c, &total, c->d_indptr.p + n_rows, sizeof(int64_t));
+        SYNC(c);
         c->nnz = total;
         rc = c->d_indices.alloc(std::max<int64_t>(total, 1)); if (rc) return rc;
         rc = c->d_data.alloc(std::max<int64_t>(total, 1)); if (rc) return rc;
@@ -1382,7 +1434,7 @@ static int rows_to_csr(pc_ctx* c, int64_t n_rows) {
         LAUNCH(c, (pc::k_row_emit<256>), (unsigned int)n_rows, 256, sorted, c->d_row_base.p, c->d_row_cursor.p,
                c->d_indptr.p, c->d_indices.p, c->d_data.p, c->d_df.p);
     }
-    CU(cudaStreamSynchronize(c->stream));                      // host staging vectors no longer needed
+    SYNC(c);                      // host staging vectors no longer needed
     c->n_rows = n_rows;
     c->built = true;
     return PC_OK;
@@ -1538,7 +1590,7 @@ int pc_tfidf(pc_ctx* c, int64_t n_rows_global, const int32_t* df_global, int df_
         if (c->n_rows > 0 && c->nnz > 0)
             LAUNCH(c, (pc::k_tfidf<256>), (unsigned int)c->n_rows, 256, c->d_indptr.p, c->d_indices.p, c->d_data.p, c->d_idf.p, c->d_tfidf.p);
     }
-    CU(cudaStreamSynchronize(c->stream));
+    SYNC(c);
     c->tfidf_done = true;
     return PC_OK;
 }
@@ -1550,10 +1602,43 @@ int pc_tfidf_get(pc_ctx* c, float* data, int loc) {
     return copy_out(c, data, c->d_tfidf.p, c->nnz * sizeof(float), loc);
 }
 
+// small device -> host read-back through the mailbox (callers: the multi-GPU driver's bucket sizes, counts, handles)
+int pc_read_back(pc_ctx* c, void* dst_host, const void* src_dev, int64_t bytes) {
+    int rc = use_device(c); if (rc) return rc;
+    if (bytes < 0 || (bytes > 0 && (!dst_host || !src_dev))) return fail(PC_EINVAL, "bad pc_read_back arguments");
+    READ_SMALL(c, dst_host, src_dev, (size_t)bytes);
+    SYNC(c);
+    return PC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- SM-driven copies
+int pc_copy_async(pc_ctx* c, void* dst, const void* src, int64_t bytes, void* stream, int n_ctas) {
+    int rc = use_device(c); if (rc) return rc;
+    if (bytes < 0 || (bytes > 0 && (!dst || !src))) return fail(PC_EINVAL, "bad pc_copy_async arguments");
+    if (bytes == 0) return PC_OK;
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    if (((uintptr_t)dst | (uintptr_t)src) & 15) {              // unaligned: leave it to the copy engine
+        CU(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDefault, st));
+        return PC_OK;
+    }
+    if (n_ctas <= 0) n_ctas = 32;
+    const int64_t n16 = bytes / 16;
+    if (n16 > 0) {
+        unsigned int grid = (unsigned int)std::min<int64_t>(n_ctas, (n16 + 255) / 256);
+        pc::k_copy16<<<grid, 256, 0, st>>>(static_cast<const uint4*>(src), static_cast<uint4*>(dst), n16);
+        CU(cudaGetLastError());
+    }
+    if (bytes & 15) {
+        pc::k_copy_tail<<<1, 32, 0, st>>>(static_cast<const uint8_t*>(src) + n16 * 16, static_cast<uint8_t*>(dst) + n16 * 16, (int)(bytes & 15));
+        CU(cudaGetLastError());
+    }
+    return PC_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- measurement
 int pc_timings(pc_ctx* c, float ms[PC_N_STAGES]) {
     int rc = use_device(c); if (rc) return rc;
-    CU(cudaStreamSynchronize(c->stream));
+    SYNC(c);
     for (int i = 0; i < PC_N_STAGES; ++i) ms[i] = 0.f;
     for (int i = 0; i < ST_N; ++i)
         if (c->ev_used[i]) { float v = 0.f; if (cudaEventElapsedTime(&v, c->ev[i][0], c->ev[i][1]) == cudaSuccess) ms[i] = v; else cudaGetLastError(); }

@@ -163,6 +163,96 @@ k_sub_scatter(const uint64_t* __restrict__ keys, const uint64_t* const* __restri
     }
 }
 
+// Variant of pass B with ONE shared atomic per k-mer: the returning atomicAdd of the histogram pass already is the rank
+// of the k-mer inside its sub-bucket run, so the ranking pass needs no second atomic (and the counters no re-zeroing).
+// (sub-bucket id, rank) are kept packed in one register per k-mer (11 + 13 bits); with 512 threads x 16 k-mers the
+// register budget is the same as 256 x 32 and twice as many warps hide the latency of the returning atomics.
+template <int TILE, int THREADS>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
+k_sub_scatter_r(const uint64_t* __restrict__ keys, const uint64_t* const* __restrict__ seg_base,
+                const int64_t* __restrict__ seg_begin, const int64_t* __restrict__ seg_len,
+                const int64_t* __restrict__ tile_start, int n_pairs, int n_seg, int pb, unsigned int NB2,
+                const unsigned long long* __restrict__ sub_off, unsigned long long* __restrict__ cursor,
+                uint64_t* __restrict__ out)
+{
+    constexpr int PER = TILE / THREADS;
+    constexpr int WARPS = THREADS / 32;
+    static_assert(TILE <= 8192 && PC_SUB_MAX <= 2048, "packing of (sub-bucket, rank) into 24 bits");
+    extern __shared__ unsigned long long sm64[];
+    unsigned long long* sorted = sm64;                                   // [TILE]
+    unsigned long long* gbase = sm64 + TILE;                             // [NB2]
+    unsigned int* cnt = reinterpret_cast<unsigned int*>(gbase + NB2);    // [NB2]
+    unsigned int* lstart = cnt + NB2;                                    // [NB2 + 1]
+    unsigned short* qs = reinterpret_cast<unsigned short*>(lstart + NB2 + 1 + ((NB2 + 1) & 1));   // [TILE]
+    __shared__ unsigned int wsum[WARPS];
+    __shared__ SegTile s_tile;
+    const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int64_t n_tiles = __ldg(tile_start + n_pairs);
+    for (int64_t g = blockIdx.x; g < n_tiles; g += gridDim.x) {
+        if (t == 0) s_tile = seg_tile<TILE>(keys, seg_base, seg_begin, seg_len, tile_start, n_pairs, n_seg, g);
+        for (unsigned int i = t; i < NB2; i += THREADS) cnt[i] = 0;
+        __syncthreads();
+        uint64_t key[PER];
+        {
+            const uint64_t* src = s_tile.src + t;
+            const int lim = (int)s_tile.lim - t;
+#pragma unroll
+            for (int j = 0; j < PER; ++j) key[j] = (j * THREADS < lim) ? __ldcs(src + j * THREADS) : PC_KEY_SENTINEL;
+        }
+        unsigned int qr[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            unsigned int q = sub_of(hash64(key[j]), pb, NB2);
+            unsigned int r = (key[j] != PC_KEY_SENTINEL) ? atomicAdd(&cnt[q], 1u) : 0u;
+            qr[j] = q | (r << 11);
+        }
+        __syncthreads();
+        {
+            unsigned int per = (NB2 + THREADS - 1) / THREADS;
+            unsigned int b0 = min(NB2, t * per), b1 = min(NB2, b0 + per);
+            unsigned int sum = 0;
+            for (unsigned int x = b0; x < b1; ++x) sum += cnt[x];
+            unsigned int incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned int u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            if (lane == 31) wsum[wid] = incl;
+            __syncthreads();
+            unsigned int before = 0;
+#pragma unroll
+            for (int x = 0; x < WARPS; ++x) if (x < wid) before += wsum[x];
+            unsigned int run = before + incl - sum;
+            const unsigned long long sub0 = (unsigned long long)s_tile.q * NB2;
+            for (unsigned int x = b0; x < b1; ++x) {
+                unsigned int c = cnt[x];
+                lstart[x] = run;
+                if (c) gbase[x] = sub_off[sub0 + x] + atomicAdd(&cursor[sub0 + x], (unsigned long long)c);
+                run += c;
+            }
+            if (t == THREADS - 1) lstart[NB2] = run;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            if (key[j] != PC_KEY_SENTINEL) {
+                unsigned int q = qr[j] & 0x7FFu;
+                unsigned int pos = lstart[q] + (qr[j] >> 11);
+                sorted[pos] = key[j];
+                qs[pos] = (unsigned short)q;
+            }
+        }
+        __syncthreads();
+        unsigned int nv = lstart[NB2];
+        for (unsigned int i = t; i < nv; i += THREADS) {
+            unsigned int x = qs[i];
+            out[gbase[x] + (i - lstart[x])] = sorted[i];
+        }
+        __syncthreads();
+    }
+}
+
 // level-2 pass C: one CTA per sub-bucket at a time (persistent, strided: neighbouring CTAs stream neighbouring
 // sub-buckets).  Shared-memory table: keys[SLOTS] (stored complemented, 0 = empty) + counts[SLOTS] (occurrences - 1: the
 // CAS that claims a slot records the first occurrence, so a new k-mer costs one shared atomic, a repeat two).
@@ -490,6 +580,30 @@ k_probe_stream_filt(const uint64_t* __restrict__ stream, int64_t n_words,
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------ SM-driven copies
+// Host <-> device copies issued by a few CTAs instead of a copy engine (the host side is page-locked memory, which
+// under unified addressing is mapped into the device's address space).  Every stage of the hot path reads a few
+// counters back and uploads small tables with tiny copies on the copy engines; queued behind a 400 MB transfer of a
+// neighbouring pipeline step on the same engine each of them waits milliseconds (measured: the overlapped end-to-end
+// loop ran at 40 ms per step instead of ~21 ms, the engines serve their queue in order).  Copies made by SMs leave the
+// engines to the small ones.  16 bytes per thread, 4 independent transfers in flight per thread.
+__global__ void __launch_bounds__(256)
+k_copy16(const uint4* __restrict__ src, uint4* __restrict__ dst, int64_t n16)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n16; i += 4 * stride) {
+        uint4 a = src[i], b = src[i + stride], c = src[i + 2 * stride], d = src[i + 3 * stride];
+        dst[i] = a; dst[i + stride] = b; dst[i + 2 * stride] = c; dst[i + 3 * stride] = d;
+    }
+    for (; i < n16; i += stride) dst[i] = src[i];
+}
+__global__ void __launch_bounds__(32)
+k_copy_tail(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int n)
+{
+    if ((int)threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
 }
 
 }  // namespace pc

@@ -19,6 +19,15 @@ import numpy as np
 from .pipeline import ChunkLayout, HotPathResult, dump_floor, effective_low_count, fetch_result
 
 
+def _to_host(ctx, t, torch, device):
+    """Small tensor -> numpy.  On CUDA through the context's mailbox (Context.to_host): a plain .cpu() is a copy-engine
+    transfer and would wait behind the bulk D2H of a neighbouring pipeline step (overlap.py).  The context stream is
+    torch's current stream here, so the read is ordered after the collective that produced `t`."""
+    if ctx is not None and hasattr(ctx, "to_host") and getattr(device, "type", "cpu") == "cuda" and t.is_cuda:
+        return ctx.to_host(t)
+    return t.cpu().numpy()
+
+
 def shard_chunks(layout, world):
     """Contiguous blocks of the string-sorted chunk list, balanced by bases.  Returns a list (per rank) of chunk
     index arrays, each in sorted-name order."""
@@ -59,13 +68,13 @@ def _all_to_all_v(dist, send, send_counts, torch):
     return recv, recv_counts
 
 
-def _all_gather_v(dist, local, torch):
+def _all_gather_v(dist, local, torch, ctx=None):
     """Variable-size all-gather of a 1-D tensor: counts first, then padded payloads."""
     world = dist.get_world_size()
     n = torch.tensor([local.numel()], dtype=torch.int64, device=local.device)
     ns = [torch.empty(1, dtype=torch.int64, device=local.device) for _ in range(world)]
     dist.all_gather(ns, n)
-    counts = [int(x.item()) for x in ns]
+    counts = [int(x) for x in _to_host(ctx, torch.cat(ns), torch, local.device).tolist()]
     m = max(counts + [1])
     pad = torch.zeros(m, dtype=local.dtype, device=local.device)
     pad[:local.numel()] = local
@@ -106,7 +115,7 @@ def peer_pointers(ctx, torch, dist, device, kbuf_keys, own_ptr):
     mine = torch.from_numpy(ctx._pc_handle.copy()).to(device)
     allh = [torch.empty(64, dtype=torch.uint8, device=device) for _ in range(world)]
     dist.all_gather(allh, mine)
-    handles = [h.cpu().numpy().tobytes() for h in allh]
+    handles = [h.tobytes() for h in _to_host(ctx, torch.stack(allh), torch, device)]
     cache = getattr(ctx, "_pc_peers", None)
     if cache is None:
         cache = ctx._pc_peers = {}
@@ -184,7 +193,7 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
     sizes = torch.from_numpy(np.diff(off).astype(np.int64)).to(device)
     gathered = [torch.empty(P, dtype=torch.int64, device=device) for _ in range(world)]
     dist.all_gather(gathered, sizes)
-    sizes_all = torch.stack(gathered).cpu().numpy()                       # [sender, bucket]
+    sizes_all = _to_host(ctx, torch.stack(gathered), torch, device)       # [sender, bucket]
     q_lo = [(r * P + world - 1) // world for r in range(world + 1)]      # rank r owns buckets [q_lo[r], q_lo[r+1])
     send_counts = [int(sizes_all[rank, q_lo[r]:q_lo[r + 1]].sum()) for r in range(world)]
     recv_counts = [int(sizes_all[s, q_lo[rank]:q_lo[rank + 1]].sum()) for s in range(world)]
@@ -256,7 +265,7 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
         ctx.selected_into(sel_local)
     mark("selected_copy")
     # 3. all-gather the repeat set; every rank sorts it to the same column order
-    sel_all, _ = _all_gather_v(dist, sel_local[:n_owner_sel], torch)
+    sel_all, _ = _all_gather_v(dist, sel_local[:n_owner_sel], torch, ctx)
     if sampling_sensitivity > 1 and sel_all.numel():
         # sampling is defined on the globally sorted survivor list (pc_select semantics)
         sel_all = torch.sort(sel_all.view(torch.int64) ^ (-2**63))[0] ^ (-2**63)       # unsigned order
@@ -277,6 +286,7 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
     t = torch.tensor([n_local, owner_info["distinct"], nnz], dtype=torch.int64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM)
     stats = dict(info)
+    t = _to_host(ctx, t, torch, device)
     stats.update(n_selected=n_sel, nnz=nnz, n_rows=n_local_rows, n_rows_global=len(scaffolds_all), row0=row0,
                  valid_windows_global=int(t[0]), distinct_global=int(t[1]), nnz_global=int(t[2]),
                  owner_distinct=owner_info["distinct"], local_bases=int(ends[-1]) if len(ends) else 0,
@@ -305,7 +315,7 @@ def rerun_threshold(ctx, layout, ids, device, k=23, kmer_low_count=100, high_boo
     sel_local = torch.empty(max(n_owner_sel, 1), dtype=torch.int64, device=device)
     if n_owner_sel:
         ctx.selected_into(sel_local)
-    sel_all, _ = _all_gather_v(dist, sel_local[:n_owner_sel], torch)
+    sel_all, _ = _all_gather_v(dist, sel_local[:n_owner_sel], torch, ctx)
     if sampling_sensitivity > 1 and sel_all.numel():
         sel_all = torch.sort(sel_all.view(torch.int64) ^ (-2**63))[0] ^ (-2**63)
         sel_all = sel_all[::int(sampling_sensitivity)].contiguous()

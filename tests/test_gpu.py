@@ -179,7 +179,7 @@ def test_shared_memory_count(ctx, k):
 
     try:
         for variant in range(5):
-            ctx.tune(part_mode=2, smem_variant=variant, smem_target=0, keep_min=1)
+            ctx.tune(part_mode=2, smem_variant=variant, scatter_variant=variant & 1, smem_target=0, keep_min=1)
             check(1, expect_overflow=False)
         ctx.tune(smem_variant=0, keep_min=3)
         check(3)
@@ -199,7 +199,7 @@ def test_shared_memory_count(ctx, k):
         ctx.tune(smem_target=0, keep_min=3)
         _check_against_c_oracle(ctx, seq, off, names, 20000, k, 5)
     finally:
-        ctx.tune(part_mode=-1, smem_variant=0, smem_target=0, keep_min=1)
+        ctx.tune(part_mode=-1, smem_variant=0, scatter_variant=0, smem_target=0, keep_min=1)
 
 
 def test_small_table_reports_overflow_not_garbage(ctx):
