@@ -114,10 +114,11 @@ struct pc_ctx {
     int probe_mode = -1;                        // -1 auto (stream when available), 0 roller, 1 stream
     int probe_batch = 4;
     int probe_threads = 0;                      // filtered probe: 0 auto, 512 (two CTAs per SM) or 1024
+    // probe_filter: -1 auto, 0 off, 1 shared-memory bitmap, 2 L2-resident bitmap
     int probe_filter = -1;                      // shared-memory bitmap filter in front of the repeat table: -1 auto, 0 off, 1 on
     int64_t filter_bits = 1310720;              // 160 KB of shared memory (measured best: 1.0 M bits 3.58 ms, 1.31 M 3.49, 1.74 M 3.89 -- the
                                                 // largest bitmap leaves the SM no L1 for the chunk / row look-ups)
-    DevBuf<unsigned int> rfilter; unsigned int rfilter_bits = 0;
+    DevBuf<unsigned int> rfilter; unsigned int rfilter_bits = 0, gfilter_bits = 0;   // shared-memory / L2-resident bitmap
     int rep_load_inv = 4;                       // repeat table capacity = rep_load_inv * n_selected
     bool stream_valid = false; int stream_k = 0;
     int part_blocks = 0;                        // blocks per bucket in k_count_part (0 = from the bucket size)
@@ -270,8 +271,21 @@ int build_rep_table(pc_ctx* c) {
     if (c->n_sel > 0)
         LAUNCH(c, pc::k_rep_build, blocks_for(c->n_sel, 256), 256, c->sel, c->n_sel, c->rtable.p, c->rcap, c->rfp.p);
     // shared-memory filter of the probe: worth it while the bitmap stays sparse (>= 1.2 bits per repeat k-mer: fill < 57 %)
-    c->rfilter_bits = 0;
-    if (c->n_sel > 0 && c->probe_filter != 0 && (c->probe_filter == 1 || c->filter_bits * 5 >= c->n_sel * 6)) {
+    c->rfilter_bits = 0; c->gfilter_bits = 0;
+    const bool smem_filter = c->n_sel > 0 && c->probe_filter != 0 && c->probe_filter != 2 &&
+                             (c->probe_filter == 1 || c->filter_bits * 5 >= c->n_sel * 6);
+    if (c->n_sel > 0 && !smem_filter && (c->probe_filter == 2 || c->probe_filter < 0)) {
+        // L2-resident bitmap, 16 bits per repeat k-mer (false positives ~6 %): for repeat sets too large for the
+        // shared-memory filter (measured at 673 k repeat k-mers: no filter 5.16 ms, this 4.04 ms, shared-memory filter
+        // 3.48 ms; at 2.2 M repeat k-mers / 4.5 Gbp, where the table is beyond L2: 52.9 -> 41.7 ms)
+        uint64_t nb = std::min<uint64_t>((uint64_t)c->n_sel * 16, 1ull << 31);
+        unsigned int nbits = (unsigned int)std::max<uint64_t>(1024, nb) & ~127u;
+        rc = c->rfilter.alloc(nbits / 32 + 4); if (rc) return rc;
+        CU(cudaMemsetAsync(c->rfilter.p, 0, ((size_t)nbits / 32 + 4) * sizeof(unsigned int), c->stream));
+        LAUNCH(c, pc::k_filter_build, blocks_for(c->n_sel, 256), 256, c->sel, c->n_sel, nbits, c->rfilter.p);
+        c->gfilter_bits = nbits;
+    }
+    if (smem_filter) {
         unsigned int nbits = (unsigned int)std::min<int64_t>(std::max<int64_t>(c->filter_bits, 1024), 1744896) & ~127u;
         rc = c->rfilter.alloc(nbits / 32 + 4); if (rc) return rc;
         CU(cudaMemsetAsync(c->rfilter.p, 0, (nbits / 32 + 4) * sizeof(unsigned int), c->stream));
@@ -1502,10 +1516,12 @@ int pc_build_matrix(pc_ctx* c, const int32_t* chunk_row, int64_t n_rows, int64_t
             } else if (use_stream) {
                 if (c->probe_batch == 4)
                     LAUNCH(c, (pc::k_probe_stream<4>), grid, 256, c->kstream.p, c->n_words, c->d_word0.p, c->n_chunks,
-                           c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, use_fp ? c->rfp.p : nullptr, c->hits_a.p, c->d_row_cursor.p);
+                           c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, use_fp ? c->rfp.p : nullptr,
+                           c->gfilter_bits ? c->rfilter.p : nullptr, c->gfilter_bits, c->hits_a.p, c->d_row_cursor.p);
                 else
                     LAUNCH(c, (pc::k_probe_stream<8>), grid, 256, c->kstream.p, c->n_words, c->d_word0.p, c->n_chunks,
-                           c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, use_fp ? c->rfp.p : nullptr, c->hits_a.p, c->d_row_cursor.p);
+                           c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, use_fp ? c->rfp.p : nullptr,
+                           c->gfilter_bits ? c->rfilter.p : nullptr, c->gfilter_bits, c->hits_a.p, c->d_row_cursor.p);
             } else {
                 LAUNCH(c, (pc::k_probe<8>), grid, 256, c->words.p, c->nmask.p, c->n_words, k, c->d_word0.p, c->n_chunks,
                        c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, use_fp ? c->rfp.p : nullptr, c->hits_a.p, c->d_row_cursor.p);

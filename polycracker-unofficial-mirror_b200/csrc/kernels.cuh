@@ -31,6 +31,11 @@ __device__ __forceinline__ uint64_t rep_slot(uint64_t key, uint64_t rcap) {
     return __umul64hi(mix64(key ^ 0x9E3779B97F4A7C15ull), rcap);
 }
 
+// bit of a k-mer in the probe's bitmap filters (shared-memory or L2 resident): an independent multiplicative hash
+__device__ __forceinline__ unsigned int gbit_of(uint64_t key, unsigned int nbits) {
+    return (unsigned int)((((key * 0xA24BAED4963EE407ull) >> 32) * (uint64_t)nbits) >> 32);
+}
+
 // 16-bit fingerprint of a k-mer (never 0), from a third independent multiplicative hash
 __device__ __forceinline__ unsigned short fp_of(uint64_t key) {
     return (unsigned short)(((key * 0xC2B2AE3D27D4EB4Full) >> 48) | 1ull);
@@ -1119,7 +1124,8 @@ __global__ void __launch_bounds__(256)
 k_probe_stream(const uint64_t* __restrict__ stream, int64_t n_words,
                const int64_t* __restrict__ chunk_word0, int64_t n_chunks, const int32_t* __restrict__ chunk_row,
                const int64_t* __restrict__ row_hit_base, const RepSlot* __restrict__ rtable, uint64_t rcap,
-               const unsigned short* __restrict__ fp, int32_t* __restrict__ hits, unsigned int* __restrict__ row_cursor)
+               const unsigned short* __restrict__ fp, const unsigned int* __restrict__ gbits, unsigned int gnbits,
+               int32_t* __restrict__ hits, unsigned int* __restrict__ row_cursor)
 {
     int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     int lane = threadIdx.x & 31;
@@ -1161,6 +1167,20 @@ k_probe_stream(const uint64_t* __restrict__ stream, int64_t n_words,
                 vmask |= (unsigned int)(key != PC_KEY_SENTINEL) << j;
                 skey[j] = ~key;
                 slot[j] = rep_slot(key, rcap);
+            }
+            if (gbits != nullptr) {
+                // repeat sets too large for the shared-memory filter have a repeat table beyond L2: one bit per hash
+                // bucket in a bitmap that DOES stay in L2 (16 bits per repeat k-mer) keeps ~2/3 of the windows from
+                // touching DRAM at all
+                unsigned int wbits[BATCH], fb[BATCH];
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j) {
+                    fb[j] = gbit_of(~skey[j], gnbits);
+                    wbits[j] = ((vmask >> j) & 1u) ? __ldg(gbits + (fb[j] >> 5)) : 0u;
+                }
+#pragma unroll
+                for (int j = 0; j < BATCH; ++j)
+                    if (!((wbits[j] >> (fb[j] & 31)) & 1u)) vmask &= ~(1u << j);
             }
             if (fp != nullptr) {
                 // fingerprint-first probing (large repeat sets): the walk reads 2-byte fingerprints (16 slots per

@@ -461,9 +461,7 @@ k_select_list(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ co
 // them without leaving the SM; only the rest goes to L2.  Persistent CTAs (one per SM, the filter fills its shared
 // memory) load the bitmap once and then walk word tiles.  Used when the repeat set is small enough for the filter to
 // discriminate (host side: bits >= 2 x n_selected).
-__device__ __forceinline__ unsigned int filt_bit(uint64_t key, unsigned int nbits) {
-    return (unsigned int)((((key * 0xA24BAED4963EE407ull) >> 32) * (uint64_t)nbits) >> 32);
-}
+__device__ __forceinline__ unsigned int filt_bit(uint64_t key, unsigned int nbits) { return gbit_of(key, nbits); }
 
 __global__ void __launch_bounds__(256)
 k_filter_build(const uint64_t* __restrict__ sorted_keys, int64_t n, unsigned int nbits, unsigned int* __restrict__ bitmap)

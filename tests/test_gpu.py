@@ -305,6 +305,23 @@ def test_partitioned_path_skewed_buckets_and_odd_shapes(ctx):
         ctx.tune(part_mode=-1, part_mbytes=64)
 
 
+def test_probe_filters(ctx):
+    """K5 with no filter, the shared-memory bitmap, the L2-resident bitmap (large repeat sets) and the fingerprint walk,
+    roller and stream variants: identical matrices."""
+    p = synth.small_params(seed=88, genome_size=4_000_000, n_shared_families=6, n_specific_families=8, max_family_len=1500)
+    seq, off, names = synth.generate(p)
+    try:
+        for kw in (dict(probe_filter=0), dict(probe_filter=1), dict(probe_filter=1, filter_bits=4096),
+                   dict(probe_filter=2), dict(probe_filter=2, probe_fp=1), dict(probe_filter=0, probe_fp=1),
+                   dict(probe_filter=2, probe_mode=0)):
+            ctx.tune(part_mode=2, probe_mode=-1, probe_fp=-1, filter_bits=1310720)
+            ctx.tune(**kw)
+            res, want = _check_against_c_oracle(ctx, seq, off, names, 20000, 23, 5)
+            assert len(want["sel"]) > 1000
+    finally:
+        ctx.tune(part_mode=-1, probe_filter=-1, probe_fp=-1, probe_mode=-1, filter_bits=1310720)
+
+
 def test_external_repeat_set(ctx):
     """blast_kmers as a separately invoked stage: the repeat set comes from a k-mer FASTA, in either orientation,
     unsorted, with duplicates."""

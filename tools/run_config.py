@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--low-memory", action="store_true")
     ap.add_argument("--fetch", action="store_true", help="also copy the CSR + TF-IDF to the host")
     ap.add_argument("--part-mbytes", type=int, default=0)
+    ap.add_argument("--k-list", default="", help="comma separated k values (BASELINE config 5: 15,23,31); default = the config's k")
+    ap.add_argument("--tune", default="", help="pc_tune settings, e.g. part_mode=1")
     a = ap.parse_args()
     import torch
     cfg = dict(synth.CONFIGS[a.config])
@@ -39,9 +41,17 @@ def main():
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     if a.part_mbytes:
         ctx.tune(part_mbytes=a.part_mbytes)
+    if a.tune:
+        ctx.tune(**{kv.split("=")[0]: int(kv.split("=")[1]) for kv in a.tune.split(",")})
     dev = pinned[:len(seq)].to("cuda")
     arena = HostArena()
-    out = {}
+    for k in ([int(x) for x in a.k_list.split(",")] if a.k_list else [cfg["k"]]):
+        run_k(a, cfg, k, ctx, dev, off, names, layout, arena, seq, t_gen, torch)
+
+
+def run_k(a, cfg, k, ctx, dev, off, names, layout, arena, seq, t_gen, torch):
+    cfg = dict(cfg, k=k)
+    out = {"k": k}
     for it in range(2):                                    # first pass allocates, second is the steady state
         torch.cuda.synchronize(); t0 = time.perf_counter()
         res = run_hot_path(ctx, dev, off, names, chunk_size=cfg["chunk_size"], k=cfg["k"],
@@ -50,6 +60,10 @@ def main():
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
         out["pass%d_s" % it] = round(dt, 4)
     st = res.stats
+    try:
+        out["count"] = ctx.count_detail()
+    except Exception as exc:                               # low-memory mode has released the count result
+        out["count"] = str(exc)[:60]
     free_b, total_b = torch.cuda.mem_get_info()
     out.update(config=a.config, genome_bases=int(len(seq)), gen_s=round(t_gen, 1), gbp_per_s=round(len(seq) / dt / 1e9, 2),
                stats={k_: int(v) for k_, v in st.items() if isinstance(v, (int, np.integer))},
@@ -64,7 +78,7 @@ def main():
         out["indices_sorted"] = bool(all(np.all(np.diff(res.indices[res.indptr[r]:res.indptr[r + 1]]) > 0)
                                          for r in range(0, m.shape[0], max(1, m.shape[0] // 200))))
         out["keys_sorted_unique"] = bool(np.all(np.diff(res.kmer_keys.astype(np.uint64)) > 0))
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
 
 
 if __name__ == "__main__":
