@@ -143,6 +143,7 @@ struct pc_ctx {
     int64_t smem_target = 0;                    // tunable: mean k-mer instances per sub-bucket (0 = 7/16 of the table slots)
     int smem_slots() const { return smem_variant == 1 ? 4096 : smem_variant == 2 ? 16384 : 8192; }
     int64_t smem_mean() const { return smem_target > 0 ? smem_target : (int64_t)smem_slots() * 7 / 16; }
+    int smem_pb = 0;                            // tunable: level-1 bucket bits of the shared-memory count (0 = auto)
     int scatter_variant = 0;                    // tunable: 0 = two shared atomics per k-mer (256 x 32), 1 = one returning atomic (512 x 16)
     int smem_variant = 0;                       // tunable: 0 = 8192 slots x 512 threads x 4 k-mers in flight, 1 = 4096 x 256 x 4, 2 = 16384 x 1024 x 4, 3 = 8192 x 256 x 8, 4 = 8192 x 256 x 4
     DevBuf<uint64_t> kbuf2, list_keys; DevBuf<uint32_t> list_counts; DevBuf<unsigned long long> d_sub; DevBuf<int64_t> d_tile;
@@ -872,6 +873,7 @@ int pc_tune(pc_ctx* c, const char* key, int64_t value) {
     else if (k == "smem_target") c->smem_target = value <= 0 ? 0 : std::max<int64_t>(64, value);
     else if (k == "smem_variant") c->smem_variant = (int)value;
     else if (k == "scatter_variant") c->scatter_variant = (int)value;
+    else if (k == "smem_pb") c->smem_pb = (int)value;
     else if (k == "prezero") c->prezero = (int)value;
     else if (k == "probe_fp") c->probe_fp = (int)value;
     else if (k == "probe_filter") c->probe_filter = (int)value;
@@ -910,8 +912,11 @@ int pc_count(pc_ctx* c, int k, int64_t capacity) {
         // two-level split into about windows / smem_target sub-buckets: level 1 takes the square root, rounded to a
         // power of two, the level-2 fan-out is fixed once the exact number of valid windows is known
         int64_t nb_total = std::max<int64_t>(1, windows / c->smem_mean());
+        // (measured at 4.46e9 k-mers: level 1 / level 2 cost 23 + 55 ms at pb 9, 28 + 44 at 10, 44 + 37 at 11, 86 + 36 at
+        // 12 -- the level-1 scatter suffers more from short runs than level 2, so level 1 takes the smaller half)
         pb = 1;
-        while (pb < 12 && ((int64_t)1 << (2 * pb)) < nb_total) ++pb;
+        while (pb < 12 && ((int64_t)2 << (2 * pb)) < nb_total) ++pb;
+        if (c->smem_pb > 0) pb = std::min(12, c->smem_pb);       // tunable override
     } else if (partitioned) {
         while (pb < 12 && ((size_t)capacity * (size_t)PC_SLOT_BYTES) >> pb > (size_t)c->part_bytes) ++pb;
         if (pb == 0) pb = 1;

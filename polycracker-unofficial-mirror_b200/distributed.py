@@ -83,13 +83,20 @@ def _all_gather_v(dist, local, torch, ctx=None):
     return torch.cat([o[:c] for o, c in zip(outs, counts)]), counts
 
 
-def plan_partition_bits(windows_global, world, part_bytes=64 << 20, table_load=0.6, slot_bytes=12):
-    """Bucket bits shared by all ranks: enough buckets that one sub-table (the unit that must stay L2 resident while it
-    is being counted) is about part_bytes, and at least one bucket per rank."""
-    cap_bytes = windows_global / table_load * slot_bytes
+def plan_partition_bits(windows_global, world, part_bytes=64 << 20, table_load=0.6, slot_bytes=12, smem_mean=0):
+    """Bucket bits shared by all ranks, at least one bucket per rank.  Table count: enough buckets that one sub-table
+    (the unit that must stay L2 resident while it is being counted) is about part_bytes.  Shared-memory count
+    (smem_mean = mean k-mers per sub-bucket > 0): the two-level split needs windows / smem_mean sub-buckets in total and
+    level 1 takes the smaller half of the bits, as pc_count does on one GPU."""
     pb = 1
-    while pb < 12 and cap_bytes / (1 << pb) > part_bytes:
-        pb += 1
+    if smem_mean > 0:
+        nb_total = max(1, windows_global // smem_mean)
+        while pb < 12 and (2 << (2 * pb)) < nb_total:
+            pb += 1
+    else:
+        cap_bytes = windows_global / table_load * slot_bytes
+        while pb < 12 and cap_bytes / (1 << pb) > part_bytes:
+            pb += 1
     while (1 << pb) < world:
         pb += 1
     return pb
@@ -179,7 +186,11 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
 
     # 1. local partition: bucket = top pb bits of the k-mer hash, the same pb on every rank
     windows_global = int(np.maximum(0, (layout.chunk_end - layout.chunk_start) - k + 1).sum())
-    pb = plan_partition_bits(windows_global, world)
+    smem_mean = 0
+    if hasattr(ctx, "sub_plan"):
+        per = ctx.sub_plan(1 << 40, 1 << 20)                 # sub-buckets per bucket for 2^20 k-mers per bucket ...
+        smem_mean = (1 << 20) // per if per > 0 else 0        # ... = the mean sub-bucket size (0: table count in use)
+    pb = plan_partition_bits(windows_global, world, smem_mean=smem_mean)
     P = 1 << pb
     mark("host_plan")
     ctx.load_sequences(buf, begins, ends)
