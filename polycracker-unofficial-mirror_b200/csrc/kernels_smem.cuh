@@ -134,13 +134,22 @@ k_sub_scatter(const uint64_t* __restrict__ keys, const uint64_t* const* __restri
             for (int x = 0; x < 8; ++x) if (x < wid) before += wsum[x];
             unsigned int run = before + incl - sum;
             const unsigned long long sub0 = (unsigned long long)s_tile.q * NB2;
-            for (unsigned int x = b0; x < b1; ++x) {
-                unsigned int c = cnt[x];
-                lstart[x] = run;
-                if (c) gbase[x] = sub_off[sub0 + x] + atomicAdd(&cursor[sub0 + x], (unsigned long long)c);
-                cnt[x] = 0;
-                run += c;
+            // the run reservations are independent returning L2 atomics: all of a thread's (up to 8) are issued back to
+            // back instead of one per loop iteration (a chain of ~1 us round trips per tile once NB2 exceeds 256)
+            unsigned int cc[PC_SUB_MAX / 256];
+#pragma unroll
+            for (int u = 0; u < PC_SUB_MAX / 256; ++u) {
+                unsigned int x = b0 + u;
+                cc[u] = (x < b1) ? cnt[x] : 0u;
+                if (x < b1) { lstart[x] = run; cnt[x] = 0; run += cc[u]; }
             }
+            unsigned long long res[PC_SUB_MAX / 256];
+#pragma unroll
+            for (int u = 0; u < PC_SUB_MAX / 256; ++u)
+                res[u] = cc[u] ? __ldg(sub_off + sub0 + b0 + u) + atomicAdd(&cursor[sub0 + b0 + u], (unsigned long long)cc[u]) : 0ull;
+#pragma unroll
+            for (int u = 0; u < PC_SUB_MAX / 256; ++u)
+                if (cc[u]) gbase[b0 + u] = res[u];
             if (t == 255) lstart[NB2] = run;
         }
         __syncthreads();
