@@ -10,9 +10,11 @@ every rank gets one 500 Mbp share of an N x 500 Mbp genome of the same shape (we
 (all-to-all), repeat-set all-gather and df all-reduce run inside the step.
 
 One JSON line on stdout (rank 0).  `value` = genome bases / step time with the ASCII genome already resident in HBM;
-`e2e` = the same through the public API with pinned HOST buffers, H2D of the genome and D2H of the CSR + TF-IDF inside
-the timed region; `roofline` is for the dominant kernel (k_count) from its CUDA-event time; `cpu_baseline` is the C
-oracle (oracle/oracle.c, a port: the reference's own tool chain cannot run) on a bounded sample.
+`e2e` = K back-to-back steps through the public API with pinned HOST buffers, every step's H2D of the genome and D2H of
+the repeat set + CSR + TF-IDF inside the timed region, copies of neighbouring steps overlapping this step's kernels
+(`e2e.sequential_*`: nothing overlapped); `roofline` is for the longest-running kernel from its CUDA-event time, with the
+per-kernel table beside it; `cpu_baseline` is the C oracle (oracle/oracle.c, a port: the reference's own tool chain
+cannot run) on a bounded sample.
 """
 import argparse
 import json
@@ -509,8 +511,10 @@ def run_b200_arm(args):
                        "l2_policy": "inputs larger than L2 (ASCII %.0f MB, k-mer stream %.1f GB, count %s %.1f GB per rank)" % (
                            local_bases / 1e6, 8.0 * T / 1e9, "buffers" if detail["kind"] == "list" else "table",
                            info["table_bytes"] / 1e9),
-                       "parallelism": "chunks sharded over %d rank(s); all-to-all of (kmer,count) by owner, "
-                                      "all-gather of the repeat set, all-reduce of df" % world},
+                       "parallelism": ("one GPU" if world == 1 else
+                                       "chunks sharded over %d ranks; k-mers hash-partitioned by owner, owners read the "
+                                       "senders' bucket buffers over NVLink peer memory (level-2 histograms exchanged), "
+                                       "all-gather of the repeat set, all-reduce of df" % world)},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "step_wall_ms": [round(x, 2) for x in step_wall], "quiet_gpu_wait_s": round(quiet_wait, 2),
             "result": {"distinct_kmers_rank0": info["distinct"], "valid_windows_rank0": info["valid_windows"],

@@ -140,9 +140,9 @@ struct pc_ctx {
     // k-mers with count >= list_min instead of a global table.  count_kind says what pc_select / pc_dump_counts read.
     int count_kind = 0;                         // 0 global table, 1 compact list
     uint32_t keep_min = 1;                      // tunable: lowest count worth keeping (the reference dumps mincount=3)
-    int64_t smem_target = 0;                    // tunable: mean k-mer instances per sub-bucket (0 = 7/16 of the table slots)
+    int64_t smem_target = 0;                    // tunable: mean k-mer instances per sub-bucket (0 = half the table slots: an all-distinct sub-bucket loads its table to 0.5)
     int smem_slots() const { return smem_variant == 1 ? 4096 : smem_variant == 2 ? 16384 : 8192; }
-    int64_t smem_mean() const { return smem_target > 0 ? smem_target : (int64_t)smem_slots() * 7 / 16; }
+    int64_t smem_mean() const { return smem_target > 0 ? smem_target : (int64_t)smem_slots() / 2; }
     int smem_pb = 0;                            // tunable: level-1 bucket bits of the shared-memory count (0 = auto)
     int scatter_variant = 0;                    // tunable: 0 = two shared atomics per k-mer (256 x 32), 1 = one returning atomic (512 x 16)
     int smem_variant = 0;                       // tunable: 0 = 8192 slots x 512 threads x 4 k-mers in flight, 1 = 4096 x 256 x 4, 2 = 16384 x 1024 x 4, 3 = 8192 x 256 x 8, 4 = 8192 x 256 x 4

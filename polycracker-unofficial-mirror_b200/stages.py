@@ -116,8 +116,13 @@ def writeKmerCount(fasta_path="./fasta_files/", kmercount_path="./kmercount_file
             ctx = context()
             ctx.load_sequences(seq, offsets[:-1], offsets[1:])
             for k in kmer_lengths:
-                ctx.count(k)
-                keys, counts = ctx.dump_counts(3 if k <= 31 else 1)          # mincount=3 (pc.py:199) / dump all (pc.py:203)
+                floor = 3 if k <= 31 else 1                                  # mincount=3 (pc.py:199) / dump all (pc.py:203)
+                ctx.tune(keep_min=floor)                                     # rarer k-mers never leave the SM
+                try:
+                    ctx.count(k)
+                finally:
+                    ctx.tune(keep_min=1)
+                keys, counts = ctx.dump_counts(floor)
                 order = np.argsort(keys)
                 binding.write_kcount(out, keys[order], counts[order], k, append=True)
             written.append(out)

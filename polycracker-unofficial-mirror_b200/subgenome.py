@@ -52,7 +52,11 @@ def extract_pass(ctx, seq, rec_begin, rec_end, groups, kmer_lengths, diff_kmer_t
         for g, idx in enumerate(groups):
             idx = np.sort(np.asarray(idx, np.int64))           # counting is order-free; the loader wants ascending offsets
             ctx.load_sequences(seq, rec_begin[idx], rec_end[idx])
-            ctx.count(k)
+            ctx.tune(keep_min=dump_floor(k))                    # the dictionary only ever holds what the counter dumps
+            try:
+                ctx.count(k)
+            finally:
+                ctx.tune(keep_min=1)
             ctx.sub_add_counts(g, dump_floor(k))
         n_diff[k] = ctx.sub_compare(diff_kmer_threshold, default_kmercount_value, diff_sample_rate)
     if map_seq is None:
