@@ -186,6 +186,16 @@ int pc_sub_compare(pc_ctx* ctx, double ratio_threshold, double default_value, in
 int pc_sub_diff_get(pc_ctx* ctx, int k, int group, uint64_t* keys, uint32_t* counts, int loc, int64_t* n);
 int pc_sub_mapback(pc_ctx* ctx, int32_t* coverage, int loc);
 
+/* ---- N2  diagnostics (scope row N2) ------------------------------------------------------------------------
+ * pc_count_histogram: the data of `kcount_hist` (polycracker.py:1419-1496: Counter over the second column of a
+ * .kcount): hist[c - min_count] = number of distinct k-mers that occur exactly c times, min_count <= c <= max_count;
+ * hist[max_count - min_count + 1] = k-mers above max_count.  max_count - min_count + 2 entries (uint64, host or device).
+ * pc_row_hits: the data of `number_repeatmers_per_subsequence` (polycracker.py:1366-1382: k-mer names per
+ * blasted_merged.bed line): occurrences of repeat k-mers in every matrix row (rows with 0 have no line in the
+ * reference's file), after pc_build_matrix / pc_matrix_from_hits. */
+int pc_count_histogram(pc_ctx* ctx, uint32_t min_count, uint32_t max_count, uint64_t* hist, int loc);
+int pc_row_hits(pc_ctx* ctx, int64_t* hits_per_row, int loc);
+
 /* ---- memory ---------------------------------------------------------------------------------------------
  * Release device buffers later stages do not need (bit mask).  At Gbp scale the count table, the bucket buffer, the
  * k-mer stream and the hit buffers are tens of GB each: releasing the bucket buffer after pc_count and the table after

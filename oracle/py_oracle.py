@@ -211,5 +211,18 @@ def run_path(sequences, chunk_size, k, kmer_low_count, high_bool=0, kmer_high_co
     mat, scaffolds, kmers = generate_kmer_matrix(merged, original_scaffolds, kmers, chunk_size,
                                                  remove_non_chunk, min_chunk_threshold,
                                                  min_chunk_size)
-    return dict(bed=bed, counts=counts, kcount=kcount, kmers=kmers, scaffolds=scaffolds,
+    return dict(bed=bed, counts=counts, kcount=kcount, kmers=kmers, scaffolds=scaffolds, merged=merged,
                 original_scaffolds=original_scaffolds, matrix=mat, tfidf=tfidf(mat))
+
+
+# ---- N2 diagnostics (polycracker.py:1366-1382, 1419-1496) ----------------------------------------------------------
+def repeatmers_per_subsequence(merged_bed_lines):
+    """awk '{print gsub(/,/,"")+1}' over blasted_merged.bed (polycracker.py:1374): k-mer names per line."""
+    return [line.count(",") + 1 for line in merged_bed_lines]
+
+
+def kcount_histogram(kcount_lines):
+    """OrderedDict(sorted(Counter(second column).items())) (polycracker.py:1466-1469) -> [(count, n_kmers)]."""
+    from collections import Counter
+    c = Counter(int(line.split()[1]) for line in kcount_lines if line.strip())
+    return sorted(c.items())

@@ -66,6 +66,8 @@ _SIGS = {
     "pc_count_detail": (C.c_int, [_vp, _vp]),
     "pc_copy_async": (C.c_int, [_vp, _vp, _vp, _i64, _vp, C.c_int]),
     "pc_read_back": (C.c_int, [_vp, _vp, _vp, _i64]),
+    "pc_count_histogram": (C.c_int, [_vp, _u32, _u32, _vp, C.c_int]),
+    "pc_row_hits": (C.c_int, [_vp, _vp, C.c_int]),
     "pc_sub_plan": (C.c_int, [_vp, _i64, C.c_int]),
     "pc_sub_hist": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "pc_sub_hist_set": (C.c_int, [_vp, C.c_int, _vp, _i64]),
@@ -347,6 +349,22 @@ class Context:
         the tensor must stay alive until that call returns."""
         assert hist_t.is_cuda and hist_t.is_contiguous()
         check(lib.pc_sub_hist_set(self._h, int(nb2), hist_t.data_ptr(), hist_t.numel()), "pc_sub_hist_set")
+
+    # N2 diagnostics
+    def count_histogram(self, min_count=3, max_count=10000):
+        """(counts, n_kmers) like sorted(Counter(kcount column).items()) restricted to [min_count, max_count], plus the
+        number of k-mers above max_count (kcount_hist, polycracker.py:1468-1469)."""
+        h = np.zeros(max_count - min_count + 2, np.uint64)
+        check(lib.pc_count_histogram(self._h, int(min_count), int(max_count), h.ctypes.data, PC_HOST), "pc_count_histogram")
+        nz = np.flatnonzero(h[:-1])
+        return (nz + min_count).astype(np.int64), h[:-1][nz].astype(np.int64), int(h[-1])
+
+    def row_hits(self, n_rows):
+        """Repeat-k-mer occurrences per matrix row (number_repeatmers_per_subsequence, polycracker.py:1374)."""
+        out = np.zeros(n_rows, np.int64)
+        if n_rows:
+            check(lib.pc_row_hits(self._h, out.ctypes.data, PC_HOST), "pc_row_hits")
+        return out
 
     def to_host(self, tensor):
         """numpy copy of a small CUDA tensor, read back through the context's mailbox (pc_read_back): ordered on the

@@ -147,6 +147,29 @@ def subgenomeExtraction(subgenome_folder, original_subgenome_path, fasta_path, g
          search_length=search_length, perfect_mode=perfect_mode)
 
 
+@polycracker.command(name="number_repeatmers_per_subsequence")
+@click.option("-m", "--merged_bed", default="blasted_merged.bed", help="Merged bed file containing bed subsequences and kmers, comma delimited.", show_default=True, type=click.Path(exists=False))
+@click.option("-o", "--out_file", default="kmers_per_subsequence.png", help="Output histogram in png or pdf.", show_default=True, type=click.Path(exists=False))
+@click.option("--kde", is_flag=True, help="Add kernel density estimation.")
+def number_repeatmers_per_subsequence(merged_bed, out_file, kde):
+    """Find histogram depicting number of repeat kmers per subsequence."""
+    _run(stages.number_repeatmers_per_subsequence, merged_bed=merged_bed, out_file=out_file, kde=kde)
+
+
+@polycracker.command(name="kcount_hist")
+@click.option("-k", "--kcount_directory", help="Directory containing input kmer count files, named [kmer-length].kcount.", type=click.Path(exists=False))
+@click.option("-o", "--out_file", default="kmer_histogram.png", help="Output histogram in png.", show_default=True, type=click.Path(exists=False))
+@click.option("--log", is_flag=True, help="Scale x-axis to log base 10.")
+@click.option("-r", "--kcount_range", default="3,10000", help="Comma delimited list of two items, specifying range of kmer counts.", show_default=True)
+@click.option("-l", "--low_count", default=0., help="Input the kmer low count threshold and it will be plotted.", show_default=True)
+@click.option("-kl", "--kmer_lengths", default="", help="Optional: comma delimited list of kmer lengths to include in analysis.")
+@click.option("-s", "--sample_speed", default=1, help="Optional: increase sample speed to attempt to smooth kmer count histogram.", show_default=True)
+def kcount_hist(kcount_directory, out_file, log, kcount_range, low_count, kmer_lengths, sample_speed):
+    """Outputs a histogram plot of a given kmer count files."""
+    _run(stages.kcount_hist, kcount_directory=kcount_directory, out_file=out_file, log=log, kcount_range=kcount_range,
+         low_count=low_count, kmer_lengths=kmer_lengths, sample_speed=sample_speed)
+
+
 def main():
     polycracker()
 

@@ -1623,6 +1623,47 @@ int pc_tfidf_get(pc_ctx* c, float* data, int loc) {
     return copy_out(c, data, c->d_tfidf.p, c->nnz * sizeof(float), loc);
 }
 
+// ---------------------------------------------------------------------------------------------- N2 diagnostics
+int pc_count_histogram(pc_ctx* c, uint32_t min_count, uint32_t max_count, uint64_t* hist, int loc) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!c->counted) return fail(PC_ESTATE, "pc_count_histogram before pc_count");
+    if (!hist || min_count < 1 || max_count < min_count || (uint64_t)max_count - min_count > (1u << 26))
+        return fail(PC_EINVAL, "bad pc_count_histogram arguments");
+    if (c->count_kind == 1 && min_count < c->list_min)
+        return fail(PC_ESTATE, "k-mers with fewer than %u occurrences were not kept by this count (pc_tune keep_min); asked for >= %u",
+                    c->list_min, min_count);
+    const size_t bins = (size_t)(max_count - min_count) + 2;
+    DevBuf<unsigned long long> d;
+    rc = d.alloc(bins); if (rc) return rc;
+    CU(cudaMemsetAsync(d.p, 0, bins * sizeof(unsigned long long), c->stream));
+    if (c->count_kind == 1) {
+        if (c->n_list > 0)
+            LAUNCH(c, pc::k_count_hist_list, (unsigned int)std::min<int64_t>((c->n_list + 255) / 256, 148 * 8), 256,
+                   c->list_counts.p, c->n_list, min_count, max_count, d.p);
+    } else {
+        LAUNCH(c, pc::k_count_hist_table, (unsigned int)std::min<uint64_t>((c->capacity + 255) / 256, 148ull * 16), 256,
+               c->table(), c->capacity, min_count, max_count, d.p);
+    }
+    rc = copy_out(c, hist, d.p, bins * sizeof(uint64_t), loc);
+    if (!rc && loc == PC_DEVICE) rc = sync_stream(c);           // d is released below
+    d.release();
+    return rc;
+}
+
+int pc_row_hits(pc_ctx* c, int64_t* hits_per_row, int loc) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!c->built) return fail(PC_ESTATE, "pc_row_hits before pc_build_matrix");
+    if (!hits_per_row) return fail(PC_EINVAL, "hits_per_row is null");
+    if (c->n_rows == 0) return PC_OK;
+    DevBuf<int64_t> d;
+    rc = d.alloc((size_t)c->n_rows); if (rc) return rc;
+    LAUNCH(c, pc::k_row_hits, blocks_for(c->n_rows, 256), 256, c->d_row_cursor.p, c->n_rows, d.p);
+    rc = copy_out(c, hits_per_row, d.p, (size_t)c->n_rows * sizeof(int64_t), loc);
+    if (!rc && loc == PC_DEVICE) rc = sync_stream(c);
+    d.release();
+    return rc;
+}
+
 // small device -> host read-back through the mailbox (callers: the multi-GPU driver's bucket sizes, counts, handles)
 int pc_read_back(pc_ctx* c, void* dst_host, const void* src_dev, int64_t bytes) {
     int rc = use_device(c); if (rc) return rc;

@@ -613,4 +613,36 @@ k_copy_tail(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, int n)
     if ((int)threadIdx.x < n) dst[threadIdx.x] = src[threadIdx.x];
 }
 
+// ------------------------------------------------------------------------------------------------ N2 diagnostics
+// kcount_hist (polycracker.py:1419-1496): Counter over the counts of the dumped k-mers -> how many distinct k-mers occur
+// exactly c times.  hist[c - lo] for lo <= c <= hi, hist[hi - lo + 1] collects everything above hi.
+__global__ void __launch_bounds__(256)
+k_count_hist_list(const uint32_t* __restrict__ counts, int64_t n, unsigned int lo, unsigned int hi,
+                  unsigned long long* __restrict__ hist)
+{
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        unsigned int c = __ldcs(counts + i);
+        if (c >= lo) atomicAdd(&hist[min(c, hi + 1u) - lo], 1ull);
+    }
+}
+__global__ void __launch_bounds__(256)
+k_count_hist_table(CountTable table, uint64_t capacity, unsigned int lo, unsigned int hi, unsigned long long* __restrict__ hist)
+{
+    uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < capacity; i += stride) {
+        if (__ldcs(table.keys + i) == 0ull) continue;
+        unsigned int c = __ldcs(table.counts + i) + 1u;           // stored = occurrences - 1
+        if (c >= lo) atomicAdd(&hist[min(c, hi + 1u) - lo], 1ull);
+    }
+}
+// number_repeatmers_per_subsequence (polycracker.py:1366-1382): k-mer names on a chunk's blasted_merged.bed line = exact
+// occurrences of repeat k-mers in the chunk = what the probe appended to the row
+__global__ void __launch_bounds__(256)
+k_row_hits(const unsigned int* __restrict__ row_cursor, int64_t n_rows, int64_t* __restrict__ out)
+{
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_rows) out[r] = (int64_t)row_cursor[r];
+}
+
 }  // namespace pc

@@ -355,3 +355,91 @@ def generate_Kmer_Matrix(kmercount_path="./kmercount_files/", genome=None, chunk
     pickle.dump(original_scaffolds, open("originalScaffolds.p", "wb"), protocol=2)
     pickle.dump(kmers, open(output_kmer_file, "wb"), protocol=2)
     return mat
+
+
+# --------------------------------------------------------------------------------------------------- N2 diagnostics
+def repeatmers_per_subsequence(merged_bed="blasted_merged.bed"):
+    """The data behind `number_repeatmers_per_subsequence` (polycracker.py:1374: awk '{print gsub(/,/,"")+1}'): for every
+    line of the merged bed the number of comma separated k-mer names in it (awk counts commas on the whole line)."""
+    out = []
+    with open(merged_bed) as f:
+        for line in f:
+            out.append(line.count(",") + 1)
+    return np.asarray(out, np.int64)
+
+
+def number_repeatmers_per_subsequence(merged_bed="blasted_merged.bed", out_file="kmers_per_subsequence.png", kde=False):
+    """polycracker.py:1366-1382.  The per-chunk numbers are what `Context.row_hits` returns for the in-memory path; here
+    they come from the text artefact like in the reference.  Writes `<out_file>.tsv` (value, frequency) always and the
+    PNG when matplotlib is importable (the histogram is a plot of exactly that table)."""
+    kcount = repeatmers_per_subsequence(merged_bed)
+    if not out_file.endswith(".png"):
+        out_file += ".png"                                   # pc.py:1380-1381
+    values, freq = np.unique(kcount, return_counts=True)
+    with open(out_file + ".tsv", "w") as f:
+        f.write("\n".join("%d\t%d" % (v, n) for v, n in zip(values.tolist(), freq.tolist())))
+    try:
+        import matplotlib
+        matplotlib.use("Agg")
+        import matplotlib.pyplot as plt
+        plt.figure()
+        plt.hist(kcount, bins=min(100, max(1, len(values))), density=bool(kde))
+        plt.title("Histogram of Repeat-mers in Chunked Genome Fragment")
+        plt.xlabel("Number of Repeat-mers in Chunked Genome Fragment")
+        plt.ylabel("Frequency/Density")
+        plt.savefig(out_file, dpi=300)
+    except ImportError:
+        pass
+    return kcount
+
+
+def kcount_histogram(kcount_file):
+    """The data behind `kcount_hist` (polycracker.py:1466-1469): OrderedDict(sorted(Counter(second column).items()))
+    as two arrays (count value, number of k-mers).  `Context.count_histogram` is the same table straight from the GPU
+    count, without the text file."""
+    vals = []
+    with open(kcount_file) as f:
+        for line in f:
+            parts = line.split()
+            if len(parts) >= 2 and parts[1]:
+                vals.append(int(parts[1]))
+    values, freq = np.unique(np.asarray(vals, np.int64), return_counts=True)
+    return values, freq.astype(np.int64)
+
+
+def kcount_hist(kcount_directory, out_file="kmer_histogram.png", log=False, kcount_range="3,10000", low_count=0.,
+                kmer_lengths="", sample_speed=1):
+    """polycracker.py:1419-1496: one count histogram per `<k>.kcount` in the directory.  Writes `<out_file>.tsv` (file,
+    count, n_kmers) and, when matplotlib and scipy's smoothing are available, the PNG."""
+    wanted = None
+    if kmer_lengths:
+        wanted = set(int(x) for x in kmer_lengths.split(":")[0].split(","))
+    rows, tables = [], {}
+    for name in sorted(os.listdir(kcount_directory), reverse=True):            # pc.py:1450
+        if name.endswith(".kcount") and (wanted is None or int(name.split(".")[0]) in wanted):
+            values, freq = kcount_histogram(os.path.join(kcount_directory, name))
+            tables[name] = (values, freq)
+            rows += ["%s\t%d\t%d" % (name, v, n) for v, n in zip(values.tolist(), freq.tolist())]
+    with open(out_file + ".tsv", "w") as f:
+        f.write("\n".join(rows))
+    try:
+        import matplotlib
+        matplotlib.use("Agg")
+        import matplotlib.pyplot as plt
+        lo, hi = (int(x) for x in kcount_range.split(","))
+        plt.figure(figsize=(7, 7))
+        for name, (values, freq) in tables.items():
+            x = np.log(values) if log else values
+            m = (values >= lo) & (values <= hi)
+            plt.plot(x[m][::abs(int(sample_speed)) or 1], freq[m][::abs(int(sample_speed)) or 1],
+                     label="kmer length = %s" % name.split(".")[0])
+        if low_count:
+            plt.axvline(x=low_count, label="Kmer-Count Cutoff Value = %d" % low_count)
+        plt.title("KmerCount Histogram")
+        plt.xlabel("Total Kmer Counts in Genome in log(b10)x" if log else "Total Kmer Counts in Genome")
+        plt.ylabel("Frequency")
+        plt.legend()
+        plt.savefig(out_file, dpi=300)
+    except ImportError:
+        pass
+    return tables

@@ -125,7 +125,7 @@ def test_cli_surface_matches_reference_click_options():
     from polycracker_b200 import cli
     text = open(REF).read()
     for cmd_name, cmd in cli.polycracker.commands.items():
-        m = re.search(r"@polycracker\.command\(name='%s'\)\n((?:@click\.option\(.*\)\n)+)(?:@click\.pass_context\n)?def %s\(" % (cmd_name, cmd_name), text)
+        m = re.search(r"@polycracker\.command\(name=['\"]%s['\"]\)\n((?:@click\.option\(.*\)\n)+)(?:@click\.pass_context\n)?def %s\(" % (cmd_name, cmd_name), text)
         assert m, cmd_name
         ref_opts = {}
         for line in m.group(1).strip().split("\n"):
@@ -143,7 +143,8 @@ def test_cli_surface_matches_reference_click_options():
             if d is not None:
                 assert str(got) == d or (isinstance(got, float) and float(d) == got), (cmd_name, flags, got, d)
     assert set(cli.polycracker.commands) == {"splitFasta", "writeKmerCount", "kmer2Fasta", "blast_kmers", "blast2bed",
-                                             "generate_Kmer_Matrix", "subgenomeExtraction"}
+                                             "generate_Kmer_Matrix", "subgenomeExtraction",
+                                             "number_repeatmers_per_subsequence", "kcount_hist"}
 
 
 @pytest.mark.gpu
@@ -183,3 +184,33 @@ def test_file_based_pipeline_on_gpu_matches_reference_artefacts(case, sidecar, t
     from sklearn.feature_extraction.text import TfidfTransformer
     tf = sps.csr_matrix(TfidfTransformer().fit_transform(sps.load_npz("clusteringMatrix.npz"))); tf.sort_indices()
     util.assert_tfidf_close(sps.load_npz("clusteringMatrix.tfidf.npz").data, tf.data)
+
+
+@pytest.mark.parametrize("case", ["case_k23", "case_k11_high"])
+def test_n2_diagnostics_on_reference_artefacts(case):
+    """Scope row N2 on the artefacts the reference's own stage code produced: k-mer names per merged-bed line
+    (number_repeatmers_per_subsequence, polycracker.py:1374) and the count histogram of the .kcount file (kcount_hist,
+    polycracker.py:1466-1469): host stage mirror == literal oracle == row sums of the reference's matrix."""
+    import scipy.sparse as sps
+    from oracle import py_oracle
+    from polycracker_b200 import stages
+    d = os.path.join(GOLD, case)
+    merged = os.path.join(d, "blasted_merged.bed")
+    got = stages.repeatmers_per_subsequence(merged)
+    lines = open(merged).read().splitlines()
+    assert got.tolist() == py_oracle.repeatmers_per_subsequence(lines)
+    m = sps.load_npz(os.path.join(d, "clusteringMatrix.npz")).tocsr()
+    rows = open(os.path.join(d, "rowNames.txt")).read().split("\n")
+    row_of = {r.split("\t")[1]: int(r.split("\t")[0]) for r in rows if r}
+    sums = np.asarray(m.sum(axis=1)).ravel()
+    for line, n in zip(lines, got.tolist()):
+        chunk = line.split("\t")[0]
+        if chunk in row_of:                                  # chunks filtered out of the matrix still have a bed line
+            assert sums[row_of[chunk]] == n
+    kdir = os.path.join(d, "kmercount_files")
+    kfiles = [f for f in os.listdir(kdir) if f.endswith(".kcount")]
+    assert kfiles
+    for f in kfiles:
+        values, freq = stages.kcount_histogram(os.path.join(kdir, f))
+        assert list(zip(values.tolist(), freq.tolist())) == py_oracle.kcount_histogram(open(os.path.join(kdir, f)).read().splitlines())
+        assert values.min() >= 1 and freq.sum() == sum(1 for l in open(os.path.join(kdir, f)) if l.strip())

@@ -322,6 +322,50 @@ def test_probe_filters(ctx):
         ctx.tune(part_mode=-1, probe_filter=-1, probe_fp=-1, probe_mode=-1, filter_bits=1310720)
 
 
+def test_n2_diagnostics(ctx):
+    """Scope row N2: the data of kcount_hist (Counter over the dumped counts) and of number_repeatmers_per_subsequence
+    (k-mer names per merged-bed line), from the table count, the list count and against the literal oracle."""
+    from collections import Counter
+    p = synth.small_params(seed=91, genome_size=60_000, n_chrom=2)
+    seq, off, names = synth.generate(p)
+    k, chunk, low = 11, 2500, 4
+    lit = py_oracle.run_path(util.to_sequences(seq, off, names), chunk, k, low, remove_non_chunk=0)
+    want_hist = py_oracle.kcount_histogram(["%s\t%d" % kc for kc in lit["kcount"]])
+    per_line = dict(zip([m[0] for m in lit["merged"]],
+                        py_oracle.repeatmers_per_subsequence(["\t".join(map(str, m)) for m in lit["merged"]])))
+    try:
+        for mode in (0, 2):
+            ctx.tune(part_mode=mode, keep_min=3)
+            res = run_hot_path(ctx, seq, off, names, chunk_size=chunk, k=k, kmer_low_count=low, remove_non_chunk=0)
+            ctx.tune(keep_min=3)
+            ctx.count(k)
+            vals, freq, above = ctx.count_histogram(3, 50)
+            want = [(c, n) for c, n in want_hist if c <= 50]
+            assert list(zip(vals.tolist(), freq.tolist())) == want and above == sum(n for c, n in want_hist if c > 50)
+            ctx.select(low)
+            lay = res.layout
+            scaffolds, chunk_row = lay.rows(remove_non_chunk=0)
+            ctx.build_matrix(chunk_row, len(scaffolds))
+            hits = ctx.row_hits(len(scaffolds))
+            assert hits.tolist() == [per_line.get(s_, 0) for s_ in scaffolds]
+            assert hits.tolist() == np.asarray(res.csr_matrix().sum(axis=1)).ravel().astype(np.int64).tolist()
+        with pytest.raises(binding.PolycrackerError, match="not kept"):
+            ctx.count_histogram(1, 10)
+    finally:
+        ctx.tune(part_mode=-1, keep_min=1)
+    # larger: against the C oracle's counts
+    p = synth.small_params(seed=92, genome_size=3_000_000)
+    seq, off, names = synth.generate(p)
+    lay = ChunkLayout(names, off, 20000)
+    ctx.load_sequences(seq, lay.chunk_begin_abs, lay.chunk_end_abs)
+    ctx.count(23)
+    vals, freq, above = ctx.count_histogram(1, 200)
+    _, want_counts, _ = c_oracle.count(seq, lay.chunk_begin_abs, lay.chunk_end_abs, 23)
+    cnt = Counter(want_counts.tolist())
+    assert dict(zip(vals.tolist(), freq.tolist())) == {c: n for c, n in cnt.items() if c <= 200}
+    assert above == sum(n for c, n in cnt.items() if c > 200)
+
+
 def test_external_repeat_set(ctx):
     """blast_kmers as a separately invoked stage: the repeat set comes from a k-mer FASTA, in either orientation,
     unsorted, with duplicates."""
