@@ -186,6 +186,16 @@ int pc_sub_compare(pc_ctx* ctx, double ratio_threshold, double default_value, in
 int pc_sub_diff_get(pc_ctx* ctx, int k, int group, uint64_t* keys, uint32_t* counts, int loc, int64_t* n);
 int pc_sub_mapback(pc_ctx* ctx, int32_t* coverage, int loc);
 
+/* ---- N3  standard scaling (scope row N3, first half) --------------------------------------------------------
+ * The normalisation the reference applies when tfidf = 0: generate_Kmer_Matrix's length normalisation
+ * (polycracker.py:357-359: row i times row_scale[i] = 1 / (len_i / 5000.), value = float32(float64(v) * row_scale[i]);
+ * row_scale NULL = raw counts) followed by sklearn StandardScaler(with_mean=False).fit_transform
+ * (polycracker.py:392-393): every column divided by its standard deviation over all rows, near-constant columns
+ * untouched.  Values in CSR order (same indptr / indices as pc_csr_get), float32, within 1e-6 relative of sklearn.
+ * Single context only (the column statistics are not reduced across ranks). */
+int pc_standard_scale(pc_ctx* ctx, const double* row_scale, int loc);
+int pc_scaled_get(pc_ctx* ctx, float* data, int loc);
+
 /* ---- N2  diagnostics (scope row N2) ------------------------------------------------------------------------
  * pc_count_histogram: the data of `kcount_hist` (polycracker.py:1419-1496: Counter over the second column of a
  * .kcount): hist[c - min_count] = number of distinct k-mers that occur exactly c times, min_count <= c <= max_count;

@@ -67,6 +67,8 @@ _SIGS = {
     "pc_copy_async": (C.c_int, [_vp, _vp, _vp, _i64, _vp, C.c_int]),
     "pc_read_back": (C.c_int, [_vp, _vp, _vp, _i64]),
     "pc_count_histogram": (C.c_int, [_vp, _u32, _u32, _vp, C.c_int]),
+    "pc_standard_scale": (C.c_int, [_vp, _vp, C.c_int]),
+    "pc_scaled_get": (C.c_int, [_vp, _vp, C.c_int]),
     "pc_row_hits": (C.c_int, [_vp, _vp, C.c_int]),
     "pc_sub_plan": (C.c_int, [_vp, _i64, C.c_int]),
     "pc_sub_hist": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
@@ -349,6 +351,17 @@ class Context:
         the tensor must stay alive until that call returns."""
         assert hist_t.is_cuda and hist_t.is_contiguous()
         check(lib.pc_sub_hist_set(self._h, int(nb2), hist_t.data_ptr(), hist_t.numel()), "pc_sub_hist_set")
+
+    # N3 standard scaling
+    def standard_scale(self, nnz, row_scale=None):
+        """StandardScaler(with_mean=False) of the built matrix (after the optional length normalisation row_scale[r] =
+        1 / (len_r / 5000.), float64): float32 values in CSR order.  See pc_standard_scale."""
+        rs = None if row_scale is None else np.ascontiguousarray(row_scale, dtype=np.float64)
+        check(lib.pc_standard_scale(self._h, None if rs is None else rs.ctypes.data, PC_HOST), "pc_standard_scale")
+        out = np.empty(nnz, np.float32)
+        if nnz:
+            check(lib.pc_scaled_get(self._h, out.ctypes.data, PC_HOST), "pc_scaled_get")
+        return out
 
     # N2 diagnostics
     def count_histogram(self, min_count=3, max_count=10000):

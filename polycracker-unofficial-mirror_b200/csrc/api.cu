@@ -104,7 +104,8 @@ struct pc_ctx {
     DevBuf<int32_t> hits_a, hits_b; DevBuf<int64_t> d_row_nnz, d_indptr;
     DevBuf<int32_t> d_indices; DevBuf<float> d_data, d_idf, d_tfidf; DevBuf<int> d_df, d_df_global;
     int64_t n_rows = 0, nnz = 0;
-    bool built = false, tfidf_done = false;
+    bool built = false, tfidf_done = false, scaled_done = false;
+    DevBuf<float> d_scaled; DevBuf<double> d_colstat, d_rowscale;   // N3: StandardScaler(with_mean=False) values
 
     // tunables (pc_tune)
     int count_batch = 8, count_minb = 2, count_mode = 0;
@@ -347,6 +348,7 @@ int pc_destroy(pc_ctx* c) {
     c->ascii.release(); c->d_word0.release(); c->d_begin.release(); c->d_len.release();
     c->words.release(); c->nmask.release(); c->table_keys.release(); c->table_counts.release(); c->d_stats.release();
     c->kbuf.release(); c->kstream.release(); c->d_part_hist.release(); c->d_seg.release(); c->cross_keys.release(); c->d_cross_n.release();
+    c->d_scaled.release(); c->d_colstat.release(); c->d_rowscale.release();
     c->kbuf2.release(); c->list_keys.release(); c->list_counts.release(); c->d_sub.release(); c->d_tile.release(); c->d_ovf.release();
     c->sel_a.release(); c->sel_b.release(); c->rs_hist.release(); c->d_counter.release(); c->rtable.release(); c->rfp.release(); c->rfilter.release();
     c->d_chunk_row.release(); c->d_row_base.release(); c->d_row_cursor.release(); c->hits_a.release();
@@ -1621,6 +1623,43 @@ int pc_tfidf_get(pc_ctx* c, float* data, int loc) {
     if (!c->tfidf_done) return fail(PC_ESTATE, "no tf-idf computed");
     StageTimer t(c, ST_D2H);
     return copy_out(c, data, c->d_tfidf.p, c->nnz * sizeof(float), loc);
+}
+
+// ---------------------------------------------------------------------------------------------- N3 standard scaling
+int pc_standard_scale(pc_ctx* c, const double* row_scale, int loc) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!c->built) return fail(PC_ESTATE, "pc_standard_scale before pc_build_matrix");
+    c->scaled_done = false;
+    const int64_t R = c->n_rows, D = std::max<int64_t>(c->n_sel, 1);
+    rc = c->d_scaled.alloc(std::max<int64_t>(c->nnz, 1)); if (rc) return rc;
+    rc = c->d_colstat.alloc((size_t)3 * D); if (rc) return rc;
+    const double* rs = nullptr;
+    if (row_scale) {
+        if (loc == PC_DEVICE) rs = row_scale;
+        else {
+            rc = c->d_rowscale.alloc(std::max<int64_t>(R, 1)); if (rc) return rc;
+            if (R) CU(cudaMemcpyAsync(c->d_rowscale.p, row_scale, (size_t)R * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            rs = c->d_rowscale.p;
+        }
+    }
+    double* col_sum = c->d_colstat.p; double* col_ss = col_sum + D; double* factor = col_ss + D;
+    CU(cudaMemsetAsync(c->d_colstat.p, 0, (size_t)3 * D * sizeof(double), c->stream));
+    if (R > 0 && c->nnz > 0) {
+        StageTimer t(c, ST_TFIDF);
+        LAUNCH(c, (pc::k_col_sum<256>), (unsigned int)R, 256, c->d_indptr.p, c->d_indices.p, c->d_data.p, rs, col_sum);
+        LAUNCH(c, (pc::k_col_sqdev<256>), (unsigned int)R, 256, c->d_indptr.p, c->d_indices.p, c->d_data.p, rs, col_sum, (double)R, col_ss);
+        LAUNCH(c, pc::k_col_factor, blocks_for(c->n_sel, 256), 256, col_sum, col_ss, c->d_df.p, c->n_sel, (double)R, factor);
+        LAUNCH(c, (pc::k_col_apply<256>), (unsigned int)R, 256, c->d_indptr.p, c->d_indices.p, c->d_data.p, rs, factor, c->d_scaled.p);
+    }
+    SYNC(c);
+    c->scaled_done = true;
+    return PC_OK;
+}
+
+int pc_scaled_get(pc_ctx* c, float* data, int loc) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!c->scaled_done) return fail(PC_ESTATE, "no standard-scaled values computed");
+    return copy_out(c, data, c->d_scaled.p, c->nnz * sizeof(float), loc);
 }
 
 // ---------------------------------------------------------------------------------------------- N2 diagnostics

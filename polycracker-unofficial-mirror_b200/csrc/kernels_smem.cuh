@@ -645,4 +645,61 @@ k_row_hits(const unsigned int* __restrict__ row_cursor, int64_t n_rows, int64_t*
     if (r < n_rows) out[r] = (int64_t)row_cursor[r];
 }
 
+// ------------------------------------------------------------------------------------------------ N3 standard scaling
+// The other normalisation at the boundary (transform_plot with tfidf = 0): generate_Kmer_Matrix's length normalisation
+// (polycracker.py:357-359: row i times 1 / (len_i / 5000.), stored as float32(float64(v) * (1/x))) followed by sklearn's
+// StandardScaler(with_mean=False) (polycracker.py:392-393): column j divided by its standard deviation over ALL rows
+// (zeros included).  sklearn (1.9, sparsefuncs_fast.pyx, float32 input): means and variances accumulated in double,
+// variance = (sum over stored entries of (x - mean)^2 + (n - nnz_j) mean^2) / n, both rounded to float32 and widened
+// again, near-constant columns (var <= n eps var + (n mean eps)^2) get scale 1, values multiplied by 1/sqrt(var) in
+// double and rounded to float32 once.
+__device__ __forceinline__ float scaled_value(float v, const double* __restrict__ row_scale, int64_t row) {
+    return row_scale ? (float)((double)v * row_scale[row]) : v;
+}
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_col_sum(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ data,
+          const double* __restrict__ row_scale, double* __restrict__ col_sum)
+{
+    int64_t row = blockIdx.x;
+    for (int64_t i = indptr[row] + threadIdx.x; i < indptr[row + 1]; i += THREADS)
+        atomicAdd(&col_sum[indices[i]], (double)scaled_value(data[i], row_scale, row));
+}
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_col_sqdev(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ data,
+            const double* __restrict__ row_scale, const double* __restrict__ col_sum, double n_rows,
+            double* __restrict__ col_ss)
+{
+    int64_t row = blockIdx.x;
+    for (int64_t i = indptr[row] + threadIdx.x; i < indptr[row + 1]; i += THREADS) {
+        int c = indices[i];
+        double d = (double)scaled_value(data[i], row_scale, row) - col_sum[c] / n_rows;
+        atomicAdd(&col_ss[c], d * d);
+    }
+}
+__global__ void __launch_bounds__(256)
+k_col_factor(const double* __restrict__ col_sum, const double* __restrict__ col_ss, const int* __restrict__ df,
+             int64_t n_cols, double n_rows, double* __restrict__ factor)
+{
+    int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_cols) return;
+    double mean = col_sum[j] / n_rows;
+    double var = (col_ss[j] + (n_rows - (double)df[j]) * mean * mean) / n_rows;
+    double mean32 = (double)(float)mean, var32 = (double)(float)var;       // mean_variance_axis returns float32 for float32 input
+    const double eps = 2.220446049250313e-16;
+    double bound = n_rows * eps * var32 + (n_rows * mean32 * eps) * (n_rows * mean32 * eps);
+    double scale = (var32 <= bound) ? 1.0 : sqrt(var32);
+    factor[j] = 1.0 / scale;
+}
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_col_apply(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ data,
+            const double* __restrict__ row_scale, const double* __restrict__ factor, float* __restrict__ out)
+{
+    int64_t row = blockIdx.x;
+    for (int64_t i = indptr[row] + threadIdx.x; i < indptr[row + 1]; i += THREADS)
+        out[i] = (float)((double)scaled_value(data[i], row_scale, row) * factor[indices[i]]);
+}
+
 }  // namespace pc

@@ -366,6 +366,40 @@ def test_n2_diagnostics(ctx):
     assert above == sum(n for c, n in cnt.items() if c > 200)
 
 
+def test_n3_standard_scaler(ctx):
+    """Scope row N3: length normalisation (polycracker.py:357-359) + sklearn StandardScaler(with_mean=False)
+    (polycracker.py:392-393) on the GPU-built matrix, against sklearn itself; tolerance 1e-6 relative (float32)."""
+    from sklearn.preprocessing import StandardScaler
+    p = synth.small_params(seed=93, genome_size=3_000_000, n_shared_families=6, n_specific_families=8, max_family_len=1500)
+    seq, off, names = synth.generate(p)
+    res = run_hot_path(ctx, seq, off, names, chunk_size=20000, k=23, kmer_low_count=5, remove_non_chunk=0)
+    m = res.csr_matrix()
+    assert m.nnz > 10000
+    # raw counts
+    got = ctx.standard_scale(m.nnz)
+    want = sps.csr_matrix(StandardScaler(with_mean=False).fit_transform(m.tocsc())); want.sort_indices()
+    assert np.array_equal(want.indices, res.indices)
+    util.assert_tfidf_close(got, want.data)
+    # after the tfidf = 0 length normalisation of generate_Kmer_Matrix
+    lens = dict(zip(res.layout.chunk_names, np.abs(res.layout.chunk_end - res.layout.chunk_start).tolist()))
+    x = np.array([lens[s_] / 5000. for s_ in res.scaffolds], np.float64)
+    rs = 1.0 / x
+    rows = np.repeat(np.arange(m.shape[0]), np.diff(m.indptr))
+    ln = sps.csr_matrix(((m.data.astype(np.float64) * rs[rows]).astype(np.float32), m.indices, m.indptr), shape=m.shape)
+    got = ctx.standard_scale(m.nnz, rs)
+    want = sps.csr_matrix(StandardScaler(with_mean=False).fit_transform(ln.tocsc())); want.sort_indices()
+    util.assert_tfidf_close(got, want.data)
+    # a constant column (every row holds the same value) keeps its values: scale 1
+    seqs = [("c%d" % i, "ACGTTGCAACGGTTAA" * 4) for i in range(6)]
+    s2, o2, n2 = util.from_sequences(seqs)
+    r2 = run_hot_path(ctx, s2, o2, n2, chunk_size=64, k=8, kmer_low_count=3)
+    m2 = r2.csr_matrix()
+    got2 = ctx.standard_scale(m2.nnz)
+    want2 = sps.csr_matrix(StandardScaler(with_mean=False).fit_transform(m2.tocsc())); want2.sort_indices()
+    util.assert_tfidf_close(got2, want2.data)
+    assert m2.nnz > 0 and np.array_equal(got2, m2.data)
+
+
 def test_external_repeat_set(ctx):
     """blast_kmers as a separately invoked stage: the repeat set comes from a k-mer FASTA, in either orientation,
     unsorted, with duplicates."""
