@@ -260,8 +260,12 @@ def run_b200_arm(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     dist = None
+    numa = None
     if world > 1:
         import torch.distributed as dist
+        from polycracker_b200.distributed import bind_to_gpu_numa
+        if os.environ.get("PC_NUMA_BIND", "1") != "0":
+            numa = bind_to_gpu_numa(local_rank)             # before any pinned buffer is allocated (first touch)
         dist.init_process_group("nccl", device_id=device)
 
     cfg, params, per_gpu = workload_params(world, args.genome_size)
@@ -516,7 +520,7 @@ def run_b200_arm(args):
                                        "senders' bucket buffers over NVLink peer memory (level-2 histograms exchanged), "
                                        "all-gather of the repeat set, all-reduce of df" % world)},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "step_wall_ms": [round(x, 2) for x in step_wall], "quiet_gpu_wait_s": round(quiet_wait, 2),
+            "numa_binding_rank0": numa, "clocks": clocks, "step_wall_ms": [round(x, 2) for x in step_wall], "quiet_gpu_wait_s": round(quiet_wait, 2),
             "result": {"distinct_kmers_rank0": info["distinct"], "valid_windows_rank0": info["valid_windows"],
                        "table_capacity": info["capacity"], "load_factor": info["distinct"] / max(1, info["capacity"]),
                        "n_selected": (res.stats["n_selected"] if res is not None else None),

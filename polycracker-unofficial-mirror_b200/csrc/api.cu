@@ -276,7 +276,10 @@ int build_rep_table(pc_ctx* c) {
     c->rfilter_bits = 0; c->gfilter_bits = 0;
     const bool smem_filter = c->n_sel > 0 && c->probe_filter != 0 && c->probe_filter != 2 &&
                              (c->probe_filter == 1 || c->filter_bits * 5 >= c->n_sel * 6);
-    if (c->n_sel > 0 && !smem_filter && (c->probe_filter == 2 || c->probe_filter < 0)) {
+    // (not in front of the fingerprint walk, which already keeps misses away from the table: measured on 8 GPUs with
+    // 5.6 M repeat k-mers, probe 7.4 ms with fingerprints alone, 8.8 ms with the bitmap in front of them)
+    const bool fp_walk = c->probe_fp == 1 || (c->probe_fp < 0 && c->rcap * sizeof(pc::RepSlot) > (size_t)(256ull << 20));
+    if (c->n_sel > 0 && !smem_filter && (c->probe_filter == 2 || (c->probe_filter < 0 && !fp_walk))) {
         // L2-resident bitmap, 16 bits per repeat k-mer (false positives ~6 %): for repeat sets too large for the
         // shared-memory filter (measured at 673 k repeat k-mers: no filter 5.16 ms, this 4.04 ms, shared-memory filter
         // 3.48 ms; at 2.2 M repeat k-mers / 4.5 Gbp, where the table is beyond L2: 52.9 -> 41.7 ms)

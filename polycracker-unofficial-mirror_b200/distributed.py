@@ -19,6 +19,29 @@ import numpy as np
 from .pipeline import ChunkLayout, HotPathResult, dump_floor, effective_low_count, fetch_result
 
 
+def bind_to_gpu_numa(gpu_index):
+    """Pin this process (and therefore the pages of the pinned host buffers it allocates afterwards: first touch) to the
+    CPUs that are local to its GPU.  With one rank per GPU on a two-socket host, unbound ranks put most staging buffers on
+    one socket and every copy of the other socket's GPUs crosses the inter-socket link.  Returns a description or None
+    when NVML / sched_setaffinity are unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(gpu_index))
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = (cpus & allowed) or None
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return "%d cpus local to gpu %d (%d-%d)" % (len(cpus), gpu_index, min(cpus), max(cpus))
+    except Exception:
+        return None
+
+
 def _to_host(ctx, t, torch, device):
     """Small tensor -> numpy.  On CUDA through the context's mailbox (Context.to_host): a plain .cpu() is a copy-engine
     transfer and would wait behind the bulk D2H of a neighbouring pipeline step (overlap.py).  The context stream is
