@@ -146,7 +146,7 @@ struct pc_ctx {
     int64_t smem_mean() const { return smem_target > 0 ? smem_target : (int64_t)smem_slots() / 2; }
     int smem_pb = 0;                            // tunable: level-1 bucket bits of the shared-memory count (0 = auto)
     int scatter_variant = 0;                    // tunable: 0 = two shared atomics per k-mer (256 x 32), 1 = one returning atomic (512 x 16)
-    int smem_variant = 0;                       // tunable: 0 = 8192 slots x 512 threads x 4 k-mers in flight, 1 = 4096 x 256 x 4, 2 = 16384 x 1024 x 4, 3 = 8192 x 256 x 8, 4 = 8192 x 256 x 4
+    int smem_variant = 0;                       // tunable: 0 = 8192 slots x 512 threads x 4 k-mers in flight; 1 = 4096 x 256 x 4; 2 = 16384 x 1024 x 4; 3 = 8192 x 256 x 8; 4 = as 0 with read-first pair probing (measured slower: 6.1 vs 4.0 ms)
     DevBuf<uint64_t> kbuf2, list_keys; DevBuf<uint32_t> list_counts; DevBuf<unsigned long long> d_sub; DevBuf<int64_t> d_tile;
     DevBuf<unsigned int> d_ovf;
     int64_t n_list = 0, n_sub = 0, n_ovf = 0; uint32_t list_min = 1; unsigned int sub_nb2 = 0;
@@ -684,15 +684,15 @@ static int count_buckets_table(pc_ctx* c, int k, int pb, int n_buckets, const ui
 // of about smem_target k-mers, one CTA-private shared-memory table per sub-bucket, survivors (count >= keep_min) to a
 // compact list.  Sub-buckets that do not fit their table are re-counted through a global table (count_buckets_table).
 extern "C++" {
-template <int SLOTS, int THREADS, int PER>
+template <int SLOTS, int THREADS, int PER, bool PAIR>
 static int launch_count_smem(pc_ctx* c, unsigned int n_sub, unsigned long long list_cap, unsigned long long* d_nlist, unsigned int* d_novf) {
     size_t smem = (size_t)SLOTS * 12;
-    CU(cudaFuncSetAttribute(pc::k_count_smem<SLOTS, THREADS, PER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(pc::k_count_smem<SLOTS, THREADS, PER, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = std::max(1, (int)((size_t)(220 << 10) / (smem + 1024)));
     per_sm = std::min(per_sm, 2048 / THREADS);
     unsigned int grid = std::min<unsigned int>(n_sub, 148u * (unsigned int)per_sm);
     c->launches++;
-    pc::k_count_smem<SLOTS, THREADS, PER><<<grid, THREADS, smem, c->stream>>>(
+    pc::k_count_smem<SLOTS, THREADS, PER, PAIR><<<grid, THREADS, smem, c->stream>>>(
         c->kbuf2.p, c->d_sub.p, n_sub, c->keep_min, c->list_keys.p, c->list_counts.p, list_cap, d_nlist, c->d_ovf.p, d_novf, c->d_stats.p);
     CU(cudaGetLastError());
     return PC_OK;
@@ -781,11 +781,11 @@ static int count_buckets_smem(pc_ctx* c, int k, int pb, int n_buckets, const uin
         }
         {
             StageTimer t(c, ST_COUNT);
-            if (c->smem_variant == 1) rc = launch_count_smem<4096, 256, 4>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
-            else if (c->smem_variant == 2) rc = launch_count_smem<16384, 1024, 4>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
-            else if (c->smem_variant == 3) rc = launch_count_smem<8192, 256, 8>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
-            else if (c->smem_variant == 4) rc = launch_count_smem<8192, 256, 4>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
-            else rc = launch_count_smem<8192, 512, 4>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
+            if (c->smem_variant == 1) rc = launch_count_smem<4096, 256, 4, false>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
+            else if (c->smem_variant == 2) rc = launch_count_smem<16384, 1024, 4, false>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
+            else if (c->smem_variant == 3) rc = launch_count_smem<8192, 256, 8, false>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
+            else if (c->smem_variant == 4) rc = launch_count_smem<8192, 512, 4, true>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
+            else rc = launch_count_smem<8192, 512, 4, false>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
             if (rc) return rc;
         }
     }

@@ -22,13 +22,11 @@ __device__ __forceinline__ uint64_t hash64(uint64_t key) {
 // repeat-table slot (K5).  Deliberately NOT the bucket hash: an owner rank selects k-mers whose bucket hash lies in its
 // own 1/world slice of the hash space; reusing those bits would pile all of them into 1/world of the repeat table
 // (measured on 4 GPUs: 194 ms for a 750 k-key build instead of 0.03 ms).  rcap < 2^32.
+// One 64-bit multiply: the probe kernels are instruction-issue bound once the filters keep most windows away from L2
+// (ncu: 63 % of the issue slots busy, 135 warp instructions per 32 windows), and the murmur finaliser used here first
+// was a quarter of them.  The top 32 bits of the product depend on every bit of the k-mer.
 __device__ __forceinline__ uint64_t rep_slot(uint64_t key, uint64_t rcap) {
-    if (g_hash_mode == 1) {
-        uint64_t h = key * 0xD6E8FEB86659FD93ull;
-        h ^= h >> 32;
-        return ((h >> 32) * rcap) >> 32;
-    }
-    return __umul64hi(mix64(key ^ 0x9E3779B97F4A7C15ull), rcap);
+    return (((key * 0xD6E8FEB86659FD93ull) >> 32) * rcap) >> 32;
 }
 
 // bit of a k-mer in the probe's bitmap filters (shared-memory or L2 resident): an independent multiplicative hash

@@ -280,7 +280,7 @@ __device__ __forceinline__ unsigned int smem_slot(uint64_t key) {
     return (((unsigned int)key ^ (unsigned int)(key >> 32)) * 0x9E3779B1u) >> (32 - LOG);
 }
 
-template <int SLOTS, int THREADS, int PER>
+template <int SLOTS, int THREADS, int PER, bool PAIR>
 __global__ void __launch_bounds__(THREADS, (2048 / THREADS) < (int)((220u << 10) / (SLOTS * 12u + 1024u)) ? (2048 / THREADS) : (int)((220u << 10) / (SLOTS * 12u + 1024u)))
 k_count_smem(const uint64_t* __restrict__ kbuf2, const unsigned long long* __restrict__ sub_off, unsigned int n_sub,
              unsigned int keep_min, uint64_t* __restrict__ list_keys, uint32_t* __restrict__ list_counts,
@@ -338,7 +338,48 @@ k_count_smem(const uint64_t* __restrict__ kbuf2, const unsigned long long* __res
             }
         }
         // ---- insert this batch
-        if (*(volatile unsigned int*)&s_ovf == 0u) {
+        if (PAIR && *(volatile unsigned int*)&s_ovf == 0u) {
+            // Experiment kept as smem_variant 4: read-first insertion, two slots per probe step (one 128-bit shared load
+            // shows an aligned slot pair; a repeat costs that load + one atomicAdd, a new k-mer the load + one CAS, only
+            // a pair taken by two OTHER k-mers sends the lane round the loop).  Meant to cut the divergent probe loops
+            // of CAS-first linear probing (68 % of this kernel's instructions); MEASURED SLOWER, 6.1 vs 4.0 ms at
+            // 4.96e8 k-mers: the random 16-byte shared loads and the longer decision chain cost more than the loops.
+            // Slots only ever change from empty to a k-mer, so a non-empty read is final and a stale empty read is
+            // settled by the CAS.
+            ulonglong2 kk[PER]; unsigned int slot[PER];
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                slot[j] = smem_slot<SLOTS>(key[j]) & ~1u;
+                kk[j] = *reinterpret_cast<const ulonglong2*>(skeys + slot[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < PER; ++j) {
+                if (key[j] == PC_KEY_SENTINEL) continue;
+                const unsigned long long skey = ~key[j];
+                ulonglong2 cur = kk[j];
+                unsigned int b = slot[j], probes = 0;
+                for (;;) {
+                    int target = -1; bool fresh = false;
+                    if (cur.x == skey) target = (int)b;
+                    else if (cur.x == 0ull) { target = (int)b; fresh = true; }
+                    else if (cur.y == skey) target = (int)b + 1;
+                    else if (cur.y == 0ull) { target = (int)b + 1; fresh = true; }
+                    if (target >= 0) {
+                        if (!fresh) { atomicAdd(&scnt[target], 1u); break; }
+                        unsigned long long o = atomicCAS(&skeys[target], 0ull, skey);
+                        if (o == 0ull) { ++nk; break; }
+                        if (o == skey) { atomicAdd(&scnt[target], 1u); break; }
+                        if (target == (int)b) cur.x = o; else cur.y = o;   // lost the slot to another k-mer: look again
+                        continue;
+                    }
+                    if (++probes > PC_SMEM_PROBE_LIMIT) { s_ovf = 1u; break; }
+                    b = (b + 2) & (SLOTS - 1);
+                    cur = *reinterpret_cast<const ulonglong2*>(skeys + b);
+                }
+                max_probe = max(max_probe, probes);
+            }
+        }
+        if (!PAIR && *(volatile unsigned int*)&s_ovf == 0u) {
             unsigned long long old[PER]; unsigned int slot[PER];
 #pragma unroll
             for (int j = 0; j < PER; ++j) {
