@@ -35,7 +35,9 @@ WORKLOAD = "cfg2_500Mbp_allotetraploid"
 FALLBACK_HBM_GBS = 6650.0
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
 # capture of this workload (profiles/); None until a capture of the current kernel exists
-NCU_TRAFFIC = {}                      # filled from the committed ncu capture of the current kernels (profiles/), per launch
+NCU_TRAFFIC = {"K3_count": 4.048e9,   # k_count_smem: 3.978 GB read + 0.070 GB written (= one read of the 8-byte k-mers)
+               "K5_probe": 4.409e9}   # k_probe_stream_filt: 4.028 GB read + 0.382 GB written
+# (profiles/r01_ncu_full_bench_500Mbp_top_kernels_raw.csv: `ncu --set full` of this file's default workload)
 
 
 def parse_args():
