@@ -144,6 +144,8 @@ struct pc_ctx {
     int64_t smem_target = 0;                    // tunable: mean k-mer instances per sub-bucket (0 = half the table slots: an all-distinct sub-bucket loads its table to 0.5)
     int smem_slots() const { return smem_variant == 1 ? 4096 : smem_variant == 2 ? 16384 : 8192; }
     int64_t smem_mean() const { return smem_target > 0 ? smem_target : (int64_t)smem_slots() / 2; }
+    int scatter_pack = 1;                       // tunable: carry the bucket id in the spare top bits of the k-mer word (k <= 26)
+    int scatter_tile = 0;                       // tunable: k-mers per tile of the level-1 scatter (0 auto, 8192: 2 CTAs/SM, 4096: 4 CTAs/SM)
     int smem_pb = 0;                            // tunable: level-1 bucket bits of the shared-memory count (0 = auto)
     int scatter_variant = 0;                    // tunable: 0 = two shared atomics per k-mer (256 x 32), 1 = one returning atomic (512 x 16)
     int smem_variant = 0;                       // tunable: 0 = 8192 slots x 512 threads x 4 k-mers in flight; 1 = 4096 x 256 x 4; 2 = 16384 x 1024 x 4; 3 = 8192 x 256 x 8; 4 = as 0 with read-first pair probing (measured slower: 6.1 vs 4.0 ms)
@@ -591,12 +593,21 @@ static int do_partition(pc_ctx* c, int k, int pb) {
     c->stream_valid = c->n_words > 0; c->stream_k = k;
     if (c->n_words > 0) {
         StageTimer t(c, ST_PART_SCATTER);
-        constexpr int TILE = 8192;
-        size_t smem = (size_t)TILE * 8 + P * 8 + P * 4 + (P + 2) * 4 + (size_t)TILE * 2 + 16;
-        CU(cudaFuncSetAttribute(pc::k_tile_scatter<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        unsigned int grid = (unsigned int)std::min<int64_t>(148 * 2, (n_stream + TILE - 1) / TILE);
         c->launches++;
-        pc::k_tile_scatter<TILE><<<grid, 256, smem, c->stream>>>(c->kstream.p, n_stream, pb, bucket_off, bucket_cur, c->kbuf.p);
+        const bool pack = 2 * k <= PC_PACK_SHIFT && c->scatter_pack != 0;   // bucket id in the spare top bits of the k-mer word
+#define TILE_SCATTER(TILE_, PACK_, PER_SM)                                                                                  \
+        do {                                                                                                               \
+            size_t smem = (size_t)(TILE_) * 8 + P * 8 + P * 4 + (P + 2) * 4 + (size_t)(TILE_) * 2 + 16;                    \
+            CU(cudaFuncSetAttribute((pc::k_tile_scatter<TILE_, PACK_>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            unsigned int grid = (unsigned int)std::min<int64_t>(148 * (PER_SM), (n_stream + (TILE_) - 1) / (TILE_));       \
+            pc::k_tile_scatter<TILE_, PACK_><<<grid, 256, smem, c->stream>>>(c->kstream.p, n_stream, pb, bucket_off, bucket_cur, c->kbuf.p); \
+        } while (0)
+        // 4096-k-mer tiles (4 CTAs per SM) while the runs stay >= 8 k-mers long; measured at P = 512: 2.38 ms (8192, two
+        // arrays) -> 2.22 (bucket id packed) -> 2.10 (4096 + packed)
+        const bool small_tile = c->scatter_tile == 4096 || (c->scatter_tile == 0 && P <= 512);
+        if (small_tile) { if (pack) TILE_SCATTER(4096, true, 4); else TILE_SCATTER(4096, false, 4); }
+        else { if (pack) TILE_SCATTER(8192, true, 2); else TILE_SCATTER(8192, false, 2); }
+#undef TILE_SCATTER
         CU(cudaGetLastError());
     }
     c->h_bucket_off.assign(P + 1, 0);
@@ -766,7 +777,8 @@ static int count_buckets_smem(pc_ctx* c, int k, int pb, int n_buckets, const uin
             }
             LAUNCH(c, pc::k_rs_scan<unsigned long long>, 1, 1024, sub_off, n_sub);
             size_t smem = (size_t)TILE * 8 + (size_t)NB2 * 8 + (size_t)NB2 * 4 + ((size_t)NB2 + 2) * 4 + (size_t)TILE * 2 + 16;
-            CU(cudaFuncSetAttribute(pc::k_sub_scatter<TILE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaFuncSetAttribute((pc::k_sub_scatter<TILE, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU(cudaFuncSetAttribute((pc::k_sub_scatter<TILE, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             grid = (unsigned int)std::min<int64_t>(148 * 2, n_tiles);
             c->launches++;
             if (c->scatter_variant == 1) {
@@ -774,8 +786,12 @@ static int count_buckets_smem(pc_ctx* c, int k, int pb, int n_buckets, const uin
                 pc::k_sub_scatter_r<TILE, 512><<<grid, 512, smem, c->stream>>>(
                     keys_dev, d_base, d_beg, d_len, c->d_tile.p, (int)n_pairs, n_seg, pb, NB2, sub_off, sub_cur, c->kbuf2.p);
             } else {
-                pc::k_sub_scatter<TILE><<<grid, 256, smem, c->stream>>>(
-                    keys_dev, d_base, d_beg, d_len, c->d_tile.p, (int)n_pairs, n_seg, pb, NB2, sub_off, sub_cur, c->kbuf2.p);
+                if (2 * k <= PC_PACK_SHIFT && c->scatter_pack == 2)      // level 2: measured no gain (3.83 vs 3.89 ms), off by default
+                    pc::k_sub_scatter<TILE, true><<<grid, 256, smem, c->stream>>>(
+                        keys_dev, d_base, d_beg, d_len, c->d_tile.p, (int)n_pairs, n_seg, pb, NB2, sub_off, sub_cur, c->kbuf2.p);
+                else
+                    pc::k_sub_scatter<TILE, false><<<grid, 256, smem, c->stream>>>(
+                        keys_dev, d_base, d_beg, d_len, c->d_tile.p, (int)n_pairs, n_seg, pb, NB2, sub_off, sub_cur, c->kbuf2.p);
             }
             CU(cudaGetLastError());
         }
@@ -879,6 +895,8 @@ int pc_tune(pc_ctx* c, const char* key, int64_t value) {
     else if (k == "smem_variant") c->smem_variant = (int)value;
     else if (k == "scatter_variant") c->scatter_variant = (int)value;
     else if (k == "smem_pb") c->smem_pb = (int)value;
+    else if (k == "scatter_tile") c->scatter_tile = (int)value;
+    else if (k == "scatter_pack") c->scatter_pack = (int)value;
     else if (k == "prezero") c->prezero = (int)value;
     else if (k == "probe_fp") c->probe_fp = (int)value;
     else if (k == "probe_filter") c->probe_filter = (int)value;

@@ -549,8 +549,13 @@ k_bucket_scan(const unsigned long long* __restrict__ hist, unsigned int P, unsig
 // keys are ranked into a bucket-sorted smem array and written out run by run: consecutive threads write
 // consecutive addresses (scattered 8-byte stores into hundreds of open runs were the bottleneck of the first
 // version: 42 G stores/s regardless of how the ranks were computed).
-template <int TILE>
-__global__ void __launch_bounds__(256, 2)
+// PACK (k <= 26: the k-mer leaves the top 12 bits of its word free): the bucket id travels in those bits of the sorted
+// shared array instead of a second array, and gbase holds (global run base - local run start), so the copy-out costs two
+// shared loads per k-mer instead of four and the ranking pass one shared store instead of two.  These kernels are bound
+// by the shared-memory pipe (ncu: L1/shared 65-71 % busy at 25 % occupancy; more resident CTAs changed nothing).
+#define PC_PACK_SHIFT 52
+template <int TILE, bool PACK>
+__global__ void __launch_bounds__(256, TILE <= 4096 ? 4 : 2)
 k_tile_scatter(const uint64_t* __restrict__ stream, int64_t n_stream, int pb,
                const unsigned long long* __restrict__ bucket_off, unsigned long long* __restrict__ cursor,
                uint64_t* __restrict__ kbuf)
@@ -608,7 +613,7 @@ k_tile_scatter(const uint64_t* __restrict__ stream, int64_t n_stream, int pb,
             for (unsigned int x = b0; x < b1; ++x) {
                 unsigned int c = cnt[x];
                 lstart[x] = run;
-                if (c) gbase[x] = bucket_off[x] + atomicAdd(&cursor[x], (unsigned long long)c);
+                if (c) gbase[x] = bucket_off[x] + atomicAdd(&cursor[x], (unsigned long long)c) - run;   // minus the local run start
                 cnt[x] = 0;
                 run += c;
             }
@@ -619,15 +624,16 @@ k_tile_scatter(const uint64_t* __restrict__ stream, int64_t n_stream, int pb,
         for (int j = 0; j < PER; ++j) {
             if (key[j] != PC_KEY_SENTINEL) {
                 unsigned int pos = lstart[q[j]] + atomicAdd(&cnt[q[j]], 1u);
-                sorted[pos] = key[j];
-                qs[pos] = q[j];
+                if (PACK) sorted[pos] = key[j] | ((unsigned long long)q[j] << PC_PACK_SHIFT);
+                else { sorted[pos] = key[j]; qs[pos] = q[j]; }
             }
         }
         __syncthreads();
         unsigned int nv = lstart[P];
         for (unsigned int i = t; i < nv; i += 256) {
-            unsigned int x = qs[i];
-            kbuf[gbase[x] + (i - lstart[x])] = sorted[i];
+            unsigned long long v = sorted[i];
+            unsigned int x = PACK ? (unsigned int)(v >> PC_PACK_SHIFT) : qs[i];
+            kbuf[gbase[x] + i] = PACK ? (v & ((1ull << PC_PACK_SHIFT) - 1ull)) : v;
         }
         __syncthreads();
     }

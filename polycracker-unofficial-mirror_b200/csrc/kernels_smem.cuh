@@ -77,7 +77,7 @@ k_sub_hist(const uint64_t* __restrict__ keys, const uint64_t* const* __restrict_
 
 // level-2 pass B: the tile-wise counting sort of k_tile_scatter, by sub-bucket.  The source may be a peer's bucket
 // buffer (NVLink): the multi-GPU exchange is fused into this read.
-template <int TILE>
+template <int TILE, bool PACK>
 __global__ void __launch_bounds__(256, 2)
 k_sub_scatter(const uint64_t* __restrict__ keys, const uint64_t* const* __restrict__ seg_base,
               const int64_t* __restrict__ seg_begin, const int64_t* __restrict__ seg_len,
@@ -149,7 +149,7 @@ k_sub_scatter(const uint64_t* __restrict__ keys, const uint64_t* const* __restri
                 res[u] = cc[u] ? __ldg(sub_off + sub0 + b0 + u) + atomicAdd(&cursor[sub0 + b0 + u], (unsigned long long)cc[u]) : 0ull;
 #pragma unroll
             for (int u = 0; u < PC_SUB_MAX / 256; ++u)
-                if (cc[u]) gbase[b0 + u] = res[u];
+                if (cc[u]) gbase[b0 + u] = res[u] - lstart[b0 + u];     // minus the local run start
             if (t == 255) lstart[NB2] = run;
         }
         __syncthreads();
@@ -158,15 +158,16 @@ k_sub_scatter(const uint64_t* __restrict__ keys, const uint64_t* const* __restri
             if (key[j] != PC_KEY_SENTINEL) {
                 unsigned int q = (j & 1) ? (q2[j >> 1] >> 16) : (q2[j >> 1] & 0xFFFFu);
                 unsigned int pos = lstart[q] + atomicAdd(&cnt[q], 1u);
-                sorted[pos] = key[j];
-                qs[pos] = (unsigned short)q;
+                if (PACK) sorted[pos] = key[j] | ((unsigned long long)q << PC_PACK_SHIFT);
+                else { sorted[pos] = key[j]; qs[pos] = (unsigned short)q; }
             }
         }
         __syncthreads();
         unsigned int nv = lstart[NB2];
         for (unsigned int i = t; i < nv; i += 256) {
-            unsigned int x = qs[i];
-            out[gbase[x] + (i - lstart[x])] = sorted[i];
+            unsigned long long v = sorted[i];
+            unsigned int x = PACK ? (unsigned int)(v >> PC_PACK_SHIFT) : qs[i];
+            out[gbase[x] + i] = PACK ? (v & ((1ull << PC_PACK_SHIFT) - 1ull)) : v;
         }
         __syncthreads();
     }
