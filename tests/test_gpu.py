@@ -454,6 +454,36 @@ def test_owner_partitioned_counts_two_ranks_on_one_gpu(ctx):
     assert union.tolist() == want["sel"].tolist()
 
 
+def test_cfg1_full_size_parity(ctx):
+    """BASELINE.json configs[0] at full size (the reference's own CPU-runnable case: test_pipeline on the two-algae test
+    genome with the shipped config -- k = 26, 50 kb chunks, kmer_low_count 30, removeNonChunk = 1, tfidf = 1,
+    config_polyCRACKER.txt:27-53; the FASTA itself is not in the reference tree, so a synthetic stand-in of the same
+    size and shape): the whole path on the GPU against the C oracle, bit-exact counts / repeat set / CSR, TF-IDF within
+    1e-6.  k = 26 is even, so reverse-complement palindromes occur."""
+    cfg = synth.CONFIGS["cfg1_algae_standin"]
+    p = synth.make_params(cfg["seed"], cfg["genome_size"], n_subgenomes=cfg["n_subgenomes"])
+    seq, off, names = synth.generate(p, threads=8)
+    res, want = _check_against_c_oracle(ctx, seq, off, names, cfg["chunk_size"], cfg["k"], cfg["kmer_low_count"])
+    assert len(seq) > 150_000_000 and res.shape[0] > 3000 and res.shape[1] > 10_000 and len(want["data"]) > 1_000_000
+    assert ctx.count_detail()["kind"] == "list"                    # the shared-memory count ran
+    got_csc = res.csr_matrix().tocsc()                              # what clusteringMatrix.npz holds
+    assert got_csc.dtype == np.float32 and got_csc.shape == (len(want["scaffolds"]), len(want["sel"]))
+
+
+def test_cfg2_full_size_parity(ctx):
+    """BASELINE.json configs[1] -- the bench workload -- at full size: 497 Mbp synthetic allotetraploid, k = 23, 75 kb
+    chunks, threshold 30.  The whole GPU path (shared-memory count, filtered probe) against the C oracle: 4.96e8 k-mer
+    instances, 3.3e8 distinct, bit-exact repeat set and CSR (9.6e7 entries), TF-IDF within 1e-6."""
+    cfg = synth.CONFIGS["cfg2_500Mbp_allotetraploid"]
+    p = synth.make_params(cfg["seed"], cfg["genome_size"], n_subgenomes=cfg["n_subgenomes"])
+    seq, off, names = synth.generate(p, threads=8)
+    res, want = _check_against_c_oracle(ctx, seq, off, names, cfg["chunk_size"], cfg["k"], cfg["kmer_low_count"])
+    assert res.stats["valid_windows"] > 490_000_000 and res.shape[1] > 500_000 and len(want["data"]) > 90_000_000
+    d = ctx.count_detail()
+    assert d["kind"] == "list" and d["overflowed"] == 0
+    ctx.release(ctx.REL_BUCKETS | ctx.REL_TABLE | ctx.REL_STREAM | ctx.REL_HITS | ctx.REL_ASCII)   # 20 GB back for the next tests
+
+
 def test_properties_at_scale(ctx):
     """Size-independent invariants on a 60 Mbp genome (the oracle would take minutes here): column sums over all
     chunks equal the global counts, row sums bounded by windows, unit L2 rows, df bounds."""
