@@ -184,6 +184,15 @@ int pc_sub_begin(pc_ctx* ctx, int n_groups);
 int pc_sub_add_counts(pc_ctx* ctx, int group, uint32_t min_count, int64_t* n_kmers);
 int pc_sub_compare(pc_ctx* ctx, double ratio_threshold, double default_value, int64_t sampling, int64_t* n_diff);
 int pc_sub_diff_get(pc_ctx* ctx, int k, int group, uint64_t* keys, uint32_t* counts, int loc, int64_t* n);
+/* ---- N4  k-mer x genome count matrix (scope row N4; replaces the kmercountexact / dict / LabelEncoder / dok_matrix chain
+ * of `bio_hyp_class`, utilities.py:177-284) -- in the same session as N1: after pc_sub_add_counts for every genome (one k),
+ * pc_sub_union tests every k-mer of the UNION of the dictionaries: kept when max / clip(min, default_value) >=
+ * ratio_threshold (integer division, Python 2 int arrays; min is 0 when a genome lacks the k-mer) and max >= max_val
+ * (utilities.py:255-258).  *n_union = size of the union (rows of the reference's matrix before the filter), *n_kept = rows
+ * kept.  pc_sub_union_get: the kept k-mers ascending (= LabelEncoder order for one k) and counts[i * n_groups + g]
+ * (0 = absent) = union_kmer_matrix.npz / kmers_union.p.  The dictionaries stay pending (pc_sub_compare may follow). */
+int pc_sub_union(pc_ctx* ctx, int64_t ratio_threshold, int64_t default_value, int64_t max_val, int64_t* n_union, int64_t* n_kept);
+int pc_sub_union_get(pc_ctx* ctx, uint64_t* keys, uint32_t* counts, int loc, int64_t* n);
 int pc_sub_mapback(pc_ctx* ctx, int32_t* coverage, int loc);
 
 /* ---- N3  standard scaling (scope row N3, first half) --------------------------------------------------------

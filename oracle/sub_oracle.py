@@ -180,3 +180,27 @@ def map_back(seq, chunk_begin, chunk_end, diff_by_k):
                     hit[g, :len(keys)] |= valid & np.isin(keys, dk)
         cov[i] = hit.sum(axis=1)
     return cov
+
+
+# ------------------------------------------------------------------------------------------------ N4 (bio_hyp_class)
+def kmer_genome_matrix_literal(group_records, k, min_count=3, ratio_threshold=20, default_kcount_value=1, max_val=100):
+    """`bio_hyp_class` (utilities.py:177-284), the data path only, restated literally: per genome the counter's dump with
+    ``mincount=min_count`` (utilities.py:219-222) read back as a dict (215, 223); union of the keys (228), LabelEncoder =
+    sorted unique strings (230-231); genomes x k-mers int matrix with implicit zeros (233-236), transposed (252); kept rows:
+    ``max / clip(min, default_kcount_value) >= ratio_threshold`` and ``max >= max_val`` (255-258), where ``/`` on two
+    Python-2 numpy int arrays FLOORS and ``min`` over a sparse row sees the implicit zeros.
+    PARITY UNPINNED: the function needs Python 2, pandas.SparseDataFrame and the external counters; nothing of it can be
+    executed here, and the reference ships no test for it.  Returns (union size, kept k-mers sorted, counts[n][G])."""
+    dicts = []
+    for records in group_records:
+        counts = py_oracle.count_kmers(records, k)
+        dicts.append({km: c for km, c in counts.items() if c >= min_count})
+    kmers = sorted(set().union(*[d.keys() for d in dicts]))
+    kept, rows = [], []
+    for km in kmers:
+        row = [d.get(km, 0) for d in dicts]
+        mx, mn = max(row), min(row)
+        clipped = max(mn, default_kcount_value)
+        if clipped > 0 and (mx // clipped) >= ratio_threshold and mx >= max_val:
+            kept.append(km); rows.append(row)
+    return len(kmers), kept, rows

@@ -85,6 +85,8 @@ _SIGS = {
     "pc_release": (C.c_int, [_vp, C.c_int]),
     "pc_sub_begin": (C.c_int, [_vp, C.c_int]),
     "pc_sub_add_counts": (C.c_int, [_vp, C.c_int, _u32, _P(_i64)]),
+    "pc_sub_union": (C.c_int, [_vp, _i64, _i64, _i64, _P(_i64), _P(_i64)]),
+    "pc_sub_union_get": (C.c_int, [_vp, _vp, _vp, C.c_int, _P(_i64)]),
     "pc_sub_compare": (C.c_int, [_vp, C.c_double, C.c_double, _i64, _vp]),
     "pc_sub_diff_get": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_int, _P(_i64)]),
     "pc_sub_mapback": (C.c_int, [_vp, _vp, C.c_int]),
@@ -432,6 +434,18 @@ class Context:
         check(lib.pc_sub_compare(self._h, float(ratio_threshold), float(default_value), int(sampling), n.ctypes.data),
               "pc_sub_compare")
         return n[:self._sub_groups].copy()
+
+    def sub_union(self, ratio_threshold=20, default_value=1, max_val=100):
+        """bio_hyp_class's filter over the union of the pending dictionaries -> (union size, keys uint64[n] ascending,
+        counts uint32[n, n_groups])"""
+        nu, nk = _i64(), _i64()
+        check(lib.pc_sub_union(self._h, int(ratio_threshold), int(default_value), int(max_val), C.byref(nu), C.byref(nk)),
+              "pc_sub_union")
+        keys = np.empty(nk.value, np.uint64); counts = np.empty((nk.value, self._sub_groups), np.uint32)
+        if nk.value:
+            n = _i64()
+            check(lib.pc_sub_union_get(self._h, keys.ctypes.data, counts.ctypes.data, PC_HOST, C.byref(n)), "pc_sub_union_get")
+        return nu.value, keys, counts
 
     def sub_diff(self, k, group):
         """-> (keys uint64[n] ascending, counts uint32[n, n_groups]; 0 = absent from that subgenome's dictionary)"""

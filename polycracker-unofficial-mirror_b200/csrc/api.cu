@@ -164,6 +164,7 @@ struct pc_ctx {
     SubDict sub_dict[pc::kMaxGroups];
     SubLen sub_len[pc::kMaxSubK];
     DevBuf<uint64_t> sub_tmp_a, sub_tmp_b; DevBuf<int> d_cov;
+    DevBuf<uint64_t> union_keys; DevBuf<uint32_t> union_counts; int64_t n_union_kept = -1;   // N4 (pc_sub_union)
     void sub_clear() {
         for (auto& d : sub_dict) { d.table.release(); d.keys.release(); d.counts.release(); d.cap = 0; d.n = 0; d.set = false; }
         for (auto& l : sub_len) {
@@ -171,6 +172,7 @@ struct pc_ctx {
             for (int g = 0; g < pc::kMaxGroups; ++g) { l.diff_keys[g].release(); l.diff_counts[g].release(); l.n_diff[g] = 0; }
         }
         sub_tmp_a.release(); sub_tmp_b.release(); d_cov.release();
+        union_keys.release(); union_counts.release(); n_union_kept = -1;
         sub_groups = sub_k = sub_n_len = 0;
     }
 };
@@ -1299,6 +1301,54 @@ int pc_sub_compare(pc_ctx* c, double ratio_threshold, double default_value, int6
         d.table.release(); d.keys.release(); d.counts.release(); d.cap = 0; d.n = 0; d.set = false;
     }
     ++c->sub_n_len;
+    return PC_OK;
+}
+
+// N4: union of the pending dictionaries, filtered like bio_hyp_class (utilities.py:255-258)
+int pc_sub_union(pc_ctx* c, int64_t ratio_threshold, int64_t default_value, int64_t max_val, int64_t* n_union, int64_t* n_kept) {
+    int rc = use_device(c); if (rc) return rc;
+    const int G = c->sub_groups;
+    if (G == 0) return fail(PC_ESTATE, "pc_sub_union before pc_sub_begin");
+    for (int g = 0; g < G; ++g)
+        if (!c->sub_dict[g].set) return fail(PC_ESTATE, "genome %d has no dictionary for k = %d", g, c->sub_k);
+    StageTimer t(c, ST_SUB_COMPARE);
+    pc::GroupTables all{}; all.n = G;
+    int64_t total = 0;
+    for (int g = 0; g < G; ++g) { all.t[g] = c->sub_dict[g].table.p; all.cap[g] = c->sub_dict[g].cap; total += c->sub_dict[g].n; }
+    rc = c->sub_tmp_a.alloc(std::max<int64_t>(total, 1)); if (rc) return rc;
+    rc = c->sub_tmp_b.alloc(std::max<int64_t>(total, 1)); if (rc) return rc;
+    CU(cudaMemsetAsync(c->d_counter.p, 0, 2 * sizeof(unsigned long long), c->stream));
+    for (int g = 0; g < G; ++g) {
+        pc_ctx::SubDict& d = c->sub_dict[g];
+        if (d.n > 0)
+            LAUNCH(c, pc::k_union_test, blocks_for(d.n, 256), 256, d.keys.p, d.counts.p, d.n, g, all, (long long)ratio_threshold,
+                   (long long)default_value, (long long)max_val, c->sub_tmp_a.p, c->d_counter.p, c->d_counter.p + 1);
+    }
+    unsigned long long h[2] = {0, 0};
+    READ_SMALL(c, h, c->d_counter.p, sizeof h);
+    SYNC(c);
+    const int64_t n = (int64_t)h[0];
+    uint64_t* sorted = nullptr;
+    rc = radix_sort_u64(c, c->sub_tmp_a.p, c->sub_tmp_b.p, n, 2 * c->sub_k, &sorted); if (rc) return rc;
+    rc = c->union_keys.alloc(std::max<int64_t>(n, 1)); if (rc) return rc;
+    rc = c->union_counts.alloc(std::max<int64_t>(n * G, 1)); if (rc) return rc;
+    if (n > 0) {
+        CU(cudaMemcpyAsync(c->union_keys.p, sorted, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
+        LAUNCH(c, pc::k_diff_counts, blocks_for(n, 256), 256, c->union_keys.p, n, all, c->union_counts.p);
+    }
+    SYNC(c);
+    c->n_union_kept = n;
+    if (n_union) *n_union = (int64_t)h[1];
+    if (n_kept) *n_kept = n;
+    return PC_OK;
+}
+
+int pc_sub_union_get(pc_ctx* c, uint64_t* keys, uint32_t* counts, int loc, int64_t* n) {
+    int rc = use_device(c); if (rc) return rc;
+    if (c->sub_groups == 0 || c->n_union_kept < 0) return fail(PC_ESTATE, "pc_sub_union_get before pc_sub_union");
+    if (n) *n = c->n_union_kept;
+    if (keys) { rc = copy_out(c, keys, c->union_keys.p, (size_t)c->n_union_kept * sizeof(uint64_t), loc); if (rc) return rc; }
+    if (counts) { rc = copy_out(c, counts, c->union_counts.p, (size_t)c->n_union_kept * c->sub_groups * sizeof(uint32_t), loc); if (rc) return rc; }
     return PC_OK;
 }
 

@@ -1561,6 +1561,46 @@ k_mask_build(const uint64_t* __restrict__ keys, int64_t n, int bit, RepSlot* __r
     }
 }
 
+// N4, k-mer x genome count matrix (`bio_hyp_class`, utilities.py:177-284): over the UNION of the genomes' dumped k-mers,
+// keep a k-mer when max / clip(min, default) >= ratio (Python-2 integer arrays: the division floors; min is 0 when any
+// genome lacks the k-mer, because the matrix is sparse with implicit zeros) and max >= max_val (utilities.py:255-258).
+// Run once per genome g over its dictionary; a k-mer is handled by the FIRST genome that holds it, so every union member
+// is tested exactly once.
+__global__ void __launch_bounds__(256)
+k_union_test(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, int64_t n, int g, GroupTables all,
+             long long ratio_threshold, long long default_value, long long max_val,
+             uint64_t* __restrict__ out, unsigned long long* __restrict__ n_out, unsigned long long* __restrict__ n_union)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool first = false, keep = false;
+    uint64_t key = 0;
+    if (i < n) {
+        key = keys[i];
+        first = true;
+        long long mx = counts[i], mn = counts[i];
+        for (int o = 0; o < all.n; ++o) {
+            if (o == g) continue;
+            long long v = kv_find(all.t[o], all.cap[o], key);
+            if (o < g && v > 0) { first = false; break; }           // an earlier genome owns this k-mer
+            mx = max(mx, v); mn = min(mn, v);
+        }
+        if (first) {
+            long long clipped = max(mn, default_value);
+            keep = clipped > 0 && (mx / clipped) >= ratio_threshold && mx >= max_val;
+        }
+    }
+    unsigned int bal_u = __ballot_sync(0xFFFFFFFFu, first);
+    unsigned int bal_k = __ballot_sync(0xFFFFFFFFu, keep);
+    int lane = threadIdx.x & 31;
+    unsigned long long base = 0;
+    if (lane == 0) {
+        if (bal_u) atomicAdd(n_union, (unsigned long long)__popc(bal_u));
+        if (bal_k) base = atomicAdd(n_out, (unsigned long long)__popc(bal_k));
+    }
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (keep) out[base + __popc(bal_k & ((1u << lane) - 1u))] = key;
+}
+
 struct SubKSet { const RepSlot* t[kMaxSubK]; uint64_t cap[kMaxSubK]; int k[kMaxSubK]; int n; };
 
 // writeBlast + blast2bed3 (polycracker.py:786-865): bbmap perfectmode reports every exact occurrence (either strand) of

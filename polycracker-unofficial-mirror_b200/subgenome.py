@@ -70,6 +70,30 @@ def extract_pass(ctx, seq, rec_begin, rec_end, groups, kmer_lengths, diff_kmer_t
     return coverage, diff, n_diff
 
 
+def kmer_genome_matrix(ctx, seq, rec_begin, rec_end, groups, k=23, min_count=3, ratio_threshold=20,
+                       default_kcount_value=1, max_val=100):
+    """Scope row N4, the data path of `bio_hyp_class` (utilities.py:177-284): count every genome (group of records) with the
+    counter's ``mincount=min_count`` floor, form the k-mer x genome count matrix over the union of the dumped k-mers and keep
+    the k-mers with max / clip(min, default) >= ratio_threshold (floored, Python 2) and max >= max_val.
+    Returns (union size, keys uint64[n] ascending = kmers_union.p order, counts uint32[n, n_genomes] =
+    union_kmer_matrix.npz)."""
+    if len(groups) > binding.PC_MAX_GROUPS:
+        raise binding.PolycrackerError("%d genomes: one session holds at most %d" % (len(groups), binding.PC_MAX_GROUPS))
+    rec_begin = np.ascontiguousarray(rec_begin, np.int64)
+    rec_end = np.ascontiguousarray(rec_end, np.int64)
+    ctx.sub_begin(len(groups))
+    for g, idx in enumerate(groups):
+        idx = np.sort(np.asarray(idx, np.int64))
+        ctx.load_sequences(seq, rec_begin[idx], rec_end[idx])
+        ctx.tune(keep_min=max(1, int(min_count)))
+        try:
+            ctx.count(k)
+        finally:
+            ctx.tune(keep_min=1)
+        ctx.sub_add_counts(g, max(1, int(min_count)))
+    return ctx.sub_union(ratio_threshold, default_kcount_value, max_val)
+
+
 def bin_records(coverage, absolute_threshold=10, ratio_threshold=2):
     """kmerratio2scaffasta's rule (polycracker.py:908-922), vectorised: record i goes to subgenome g when for EVERY
     other subgenome o either (x_o == 0 and x_g > absolute_threshold) or (x_o > 0 and x_g / x_o > ratio_threshold).

@@ -246,3 +246,60 @@ def test_gpu_sub_session_errors():
         assert n.tolist() == [0, 0]                                        # identical subgenomes: nothing differential
         cov = ctx.sub_mapback(1)
         assert cov.tolist() == [[0, 0]]
+
+
+def test_n4_literal_oracle_known_answer():
+    """Scope row N4 (bio_hyp_class, utilities.py:255-258) on a hand-checkable case: floor division, implicit zeros."""
+    recs_a = [("a", "ACGTTGCA" * 30)]
+    recs_b = [("b", "ACGTTGCA" * 2 + "TTTTCCCC" * 30)]
+    n_union, kept, rows = sub_oracle.kmer_genome_matrix_literal([recs_a, recs_b], 5, min_count=3, ratio_threshold=5,
+                                                                 default_kcount_value=1, max_val=20)
+    assert n_union >= len(kept) > 0
+    for km, row in zip(kept, rows):
+        mx, mn = max(row), min(row)
+        assert mx >= 20 and mx // max(mn, 1) >= 5
+    # a k-mer present 29 times in one genome and 6 times in the other: 29 // 6 = 4 < 5 -> dropped although 29 / 6 = 4.83
+    _, kept2, rows2 = sub_oracle.kmer_genome_matrix_literal([[("x", "ACGTA" * 29)], [("y", "ACGTA" * 6)]], 5, 3, 5, 1, 20)
+    assert all(r[0] // max(r[1], 1) >= 5 for r in rows2)
+    assert "ACGTA" not in kept2
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n_gen,k,min_count,ratio,dflt,max_val", [(2, 23, 3, 20, 1, 100), (3, 15, 3, 4, 1, 30), (4, 11, 5, 3, 2, 50),
+                                                                   (2, 32, 1, 2, 1, 3)])
+def test_gpu_n4_kmer_genome_matrix(n_gen, k, min_count, ratio, dflt, max_val):
+    """Scope row N4: the k-mer x genome count matrix of bio_hyp_class on the GPU against the restated oracle (literal on a
+    small case, numpy on a Mbp-sized one)."""
+    # small: literal oracle (string k-mers)
+    p = synth.small_params(seed=7000 + n_gen, genome_size=40_000 * n_gen, n_subgenomes=n_gen, n_chrom=1, n_shared_families=3,
+                           n_specific_families=3 * n_gen, max_family_len=600)
+    seq, off, names = synth.generate(p)
+    from tests import util
+    seqs = util.to_sequences(seq, off, names)
+    groups = [np.array([i]) for i in range(len(names))][:n_gen]
+    begins, ends = off[:-1].copy(), off[1:].copy()
+    small = (max(2, ratio // 4), max(3, max_val // 10))
+    with binding.Context(0) as ctx:
+        nu, keys, counts = subgenome.kmer_genome_matrix(ctx, seq, begins, ends, groups, k, min_count, small[0], dflt, small[1])
+    want_nu, want_kept, want_rows = sub_oracle.kmer_genome_matrix_literal([[seqs[i]] for i in range(n_gen)], k, min_count,
+                                                                           small[0], dflt, small[1])
+    assert nu == want_nu and binding.kmer_decode(keys, k) == want_kept
+    assert counts.astype(np.int64).tolist() == want_rows
+    # Mbp-sized: numpy oracle from the C counter
+    p = synth.small_params(seed=7100 + n_gen, genome_size=600_000 * n_gen, n_subgenomes=n_gen, n_chrom=1, n_shared_families=5,
+                           n_specific_families=4 * n_gen)
+    seq, off, names = synth.generate(p)
+    begins, ends = off[:-1].copy(), off[1:].copy()
+    groups = [np.array([i]) for i in range(n_gen)]
+    with binding.Context(0) as ctx:
+        nu, keys, counts = subgenome.kmer_genome_matrix(ctx, seq, begins, ends, groups, k, min_count, ratio, dflt, max_val)
+    arrs = [sub_oracle.count_group(seq, begins[g], ends[g], k, min_count) for g in groups]
+    union = np.unique(np.concatenate([a[0] for a in arrs]))
+    mat = np.zeros((len(union), n_gen), np.int64)
+    for g, (kk, cc) in enumerate(arrs):
+        mat[np.searchsorted(union, kk), g] = cc
+    mx, mn = mat.max(axis=1), mat.min(axis=1)
+    keep = ((mx // np.maximum(mn, dflt)) >= ratio) & (mx >= max_val)
+    assert nu == len(union)
+    assert np.array_equal(keys, union[keep]) and np.array_equal(counts.astype(np.int64), mat[keep])
+    assert keep.sum() > 0
