@@ -144,6 +144,7 @@ struct pc_ctx {
     int64_t smem_target = 0;                    // tunable: mean k-mer instances per sub-bucket (0 = half the table slots: an all-distinct sub-bucket loads its table to 0.5)
     int smem_slots() const { return smem_variant == 1 ? 4096 : smem_variant == 2 ? 16384 : 8192; }
     int64_t smem_mean() const { return smem_target > 0 ? smem_target : (int64_t)smem_slots() / 2; }
+    bool kbuf_shared = false;                   // the bucket buffer has been exported to peer processes (pc_kbuf_export)
     int scatter_pack = 1;                       // tunable: carry the bucket id in the spare top bits of the k-mer word (k <= 26)
     int scatter_tile = 0;                       // tunable: k-mers per tile of the level-1 scatter (0 auto, 8192: 2 CTAs/SM, 4096: 4 CTAs/SM)
     int smem_pb = 0;                            // tunable: level-1 bucket bits of the shared-memory count (0 = auto)
@@ -606,7 +607,9 @@ static int do_partition(pc_ctx* c, int k, int pb) {
         } while (0)
         // 4096-k-mer tiles (4 CTAs per SM) while the runs stay >= 8 k-mers long; measured at P = 512: 2.38 ms (8192, two
         // arrays) -> 2.22 (bucket id packed) -> 2.10 (4096 + packed)
-        const bool small_tile = c->scatter_tile == 4096 || (c->scatter_tile == 0 && P <= 512);
+        // (not when the bucket buffer is exported to peers over CUDA IPC: measured on 2 GPUs 3.63 ms with the small tiles
+        // against 2.58 ms with the large ones)
+        const bool small_tile = c->scatter_tile == 4096 || (c->scatter_tile == 0 && P <= 512 && !c->kbuf_shared);
         if (small_tile) { if (pack) TILE_SCATTER(4096, true, 4); else TILE_SCATTER(4096, false, 4); }
         else { if (pack) TILE_SCATTER(8192, true, 2); else TILE_SCATTER(8192, false, 2); }
 #undef TILE_SCATTER
@@ -859,7 +862,7 @@ int pc_release(pc_ctx* c, int what) {
     SYNC(c);
     if (c->zeroed_slots > 0) { CU(cudaStreamSynchronize(c->aux_stream)); c->zeroed_slots = 0; }
     if (what & PC_REL_ASCII) { c->ascii.release(); c->ascii_padded = 0; }
-    if (what & PC_REL_BUCKETS) { c->kbuf.release(); c->kbuf2.release(); }
+    if (what & PC_REL_BUCKETS) { c->kbuf.release(); c->kbuf2.release(); c->kbuf_shared = false; }
     if (what & PC_REL_TABLE) {
         c->table_keys.release(); c->table_counts.release(); c->counted = false; c->cross_valid = false; c->cross_keys.release();
         c->list_keys.release(); c->list_counts.release(); c->n_list = 0;
@@ -998,6 +1001,7 @@ int pc_kbuf_export(pc_ctx* c, int64_t n_keys, void* ipc_handle) {
     int rc = use_device(c); if (rc) return rc;
     if (n_keys < 1 || !ipc_handle) return fail(PC_EINVAL, "bad pc_kbuf_export arguments");
     rc = c->kbuf.alloc((size_t)n_keys); if (rc) return rc;           // kept (and re-used by pc_partition) while it is big enough
+    c->kbuf_shared = true;
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, c->kbuf.p));
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
