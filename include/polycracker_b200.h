@@ -253,7 +253,10 @@ int pc_reset_counters(pc_ctx* ctx);
  * count_batch {4,8,16}, count_minb {2,3,4}, count_mode {0 load-first, 1 prefetch-ahead, 2 CAS-first} (direct table);
  * part_mode {-1 auto, 0 direct global table, 1 L2-partitioned global table, 2 shared-memory count}, part_mbytes,
  * part_blocks, part_casfirst, count_items {2,4}; keep_min (shared-memory count: lowest count kept, default 1),
- * smem_target (mean k-mers per sub-bucket), smem_variant {0..4: slots x threads x k-mers in flight};
+ * smem_target (mean k-mers per sub-bucket, 0 = half a table), smem_variant {0..4: slots x threads x k-mers in flight},
+ * smem_pb (level-1 bucket bits, 0 auto), scatter_tile {0 auto, 4096, 8192}, scatter_pack {0, 1 level 1, 2 both levels},
+ * scatter_variant {0, 1 single returning atomic}; probe_filter {-1 auto, 0 off, 1 shared-memory bitmap, 2 L2 bitmap},
+ * filter_bits, probe_threads, probe_fp, rowsort_warps {8, 16};
  * probe_mode {-1 auto, 0 roller, 1 stream}, probe_batch {4,8}, rep_load_inv; table_load_pct (5..95). */
 int pc_tune(pc_ctx* ctx, const char* key, int64_t value);
 

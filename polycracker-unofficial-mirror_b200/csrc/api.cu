@@ -145,6 +145,7 @@ struct pc_ctx {
     int smem_slots() const { return smem_variant == 1 ? 4096 : smem_variant == 2 ? 16384 : 8192; }
     int64_t smem_mean() const { return smem_target > 0 ? smem_target : (int64_t)smem_slots() / 2; }
     bool kbuf_shared = false;                   // the bucket buffer has been exported to peer processes (pc_kbuf_export)
+    int rowsort_warps = 16;                     // tunable: warps per CTA in the per-row sort (8 or 16)
     int scatter_pack = 1;                       // tunable: carry the bucket id in the spare top bits of the k-mer word (k <= 26)
     int scatter_tile = 0;                       // tunable: k-mers per tile of the level-1 scatter (0 auto, 8192: 2 CTAs/SM, 4096: 4 CTAs/SM)
     int smem_pb = 0;                            // tunable: level-1 bucket bits of the shared-memory count (0 = auto)
@@ -902,6 +903,7 @@ int pc_tune(pc_ctx* c, const char* key, int64_t value) {
     else if (k == "smem_pb") c->smem_pb = (int)value;
     else if (k == "scatter_tile") c->scatter_tile = (int)value;
     else if (k == "scatter_pack") c->scatter_pack = (int)value;
+    else if (k == "rowsort_warps") c->rowsort_warps = (int)value;
     else if (k == "prezero") c->prezero = (int)value;
     else if (k == "probe_fp") c->probe_fp = (int)value;
     else if (k == "probe_filter") c->probe_filter = (int)value;
@@ -1506,17 +1508,22 @@ static int rows_to_csr(pc_ctx* c, int64_t n_rows) {
     if (n_rows > 0) {
         {
             StageTimer t(c, ST_ROWSORT);
-            size_t smem = (size_t)17 * ((size_t)1 << db) * sizeof(unsigned int);
             c->launches++;
-            if (db == 8) {
-                pc::k_row_sort<16, 8><<<(unsigned int)n_rows, 512, smem, c->stream>>>(c->hits_a.p, c->hits_b.p, c->d_row_base.p, c->d_row_cursor.p, n_passes, c->d_row_nnz.p);
-            } else if (db == 10) {
-                CU(cudaFuncSetAttribute(pc::k_row_sort<16, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                pc::k_row_sort<16, 10><<<(unsigned int)n_rows, 512, smem, c->stream>>>(c->hits_a.p, c->hits_b.p, c->d_row_base.p, c->d_row_cursor.p, n_passes, c->d_row_nnz.p);
+#define ROW_SORT(W_, DB_)                                                                                                  \
+            do {                                                                                                           \
+                size_t smem = (size_t)((W_) + 1) * ((size_t)1 << (DB_)) * sizeof(unsigned int);                            \
+                CU(cudaFuncSetAttribute((pc::k_row_sort<W_, DB_>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+                pc::k_row_sort<W_, DB_><<<(unsigned int)n_rows, (W_) * 32, smem, c->stream>>>(                            \
+                    c->hits_a.p, c->hits_b.p, c->d_row_base.p, c->d_row_cursor.p, n_passes, c->d_row_nnz.p);               \
+            } while (0)
+            // per-warp histograms: 16 warps x 2^DB counters are zeroed, scanned and offset every pass, which is as much
+            // shared-memory work as ranking a 25 k-hit row; rowsort_warps (8 or 16) trades that against parallelism
+            if (c->rowsort_warps == 8) {
+                if (db == 8) ROW_SORT(8, 8); else if (db == 10) ROW_SORT(8, 10); else ROW_SORT(8, 11);
             } else {
-                CU(cudaFuncSetAttribute(pc::k_row_sort<16, 11>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                pc::k_row_sort<16, 11><<<(unsigned int)n_rows, 512, smem, c->stream>>>(c->hits_a.p, c->hits_b.p, c->d_row_base.p, c->d_row_cursor.p, n_passes, c->d_row_nnz.p);
+                if (db == 8) ROW_SORT(16, 8); else if (db == 10) ROW_SORT(16, 10); else ROW_SORT(16, 11);
             }
+#undef ROW_SORT
             CU(cudaGetLastError());
             LAUNCH(c, pc::k_indptr, 1, 1024, c->d_row_nnz.p, n_rows, c->d_indptr.p);
         }
