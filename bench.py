@@ -24,6 +24,11 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv[1:]:
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm (rank 0 only) is meant to use every host core
+    # it can.  libgomp reads the variable when it is first loaded, so set it before anything links it in.
+    os.environ["OMP_NUM_THREADS"] = str(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -500,7 +505,7 @@ def run_b200_arm(args):
                          "not HBM-stream bound (profiles/)"}
 
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:            # the CPU baseline is reported at N = 1 only
         from oracle import c_oracle
         sample_bases = args.cpu_sample or min(per_gpu, 72_000_000)
         s_seq, s_off, s_names = cpu_sample(workload_params(1, args.genome_size)[1], sample_bases)
