@@ -12,14 +12,18 @@ host = torch.empty(n, dtype=torch.uint8, pin_memory=True)
 host.random_(0, 255)
 dev = torch.empty(n, dtype=torch.uint8, device="cuda")
 back = torch.empty(n, dtype=torch.uint8, pin_memory=True)
-st = torch.cuda.current_stream().cuda_stream
+side = torch.cuda.Stream()                      # pc_copy_async(stream = 0) means "the context stream": use a real handle
+st = side.cuda_stream
 
 
 def timeit(fn, reps=3):
     best = 1e9
     for _ in range(reps):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize(); e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(side):
+            e0.record(); fn(); e1.record()
+        torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     return n / best / 1e6
 
@@ -30,3 +34,4 @@ for ctas in (4, 8, 16, 24, 32, 64, 148):
     h2d = timeit(lambda: ctx.copy_async(dev, host, stream=st, n_ctas=ctas))
     d2h = timeit(lambda: ctx.copy_async(back, dev, stream=st, n_ctas=ctas))
     print("SM copy %3d CTAs  H2D %.1f GB/s  D2H %.1f GB/s  ok=%s" % (ctas, h2d, d2h, bool(torch.equal(back, host))))
+ctx.close()
