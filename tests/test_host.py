@@ -140,3 +140,45 @@ def test_synth_is_deterministic_and_shaped():
     assert one.tobytes() == a[off[2]:off[3]].tobytes()
     text = a.tobytes()
     assert set(text) <= set(b"ACGTacgtNn") and b"N" in text and b"a" in text
+
+
+def test_partition_planning_and_count_floors():
+    """Host integer logic around the count: bucket bits shared by all ranks (table count: ~64 MB sub-tables; shared-memory
+    count: level 1 takes the smaller half of the bits), the counter's dump floor (kmercountexact mincount=3 for k <= 31,
+    polycracker.py:199; everything for k > 31, polycracker.py:203) and the threshold the selection really applies."""
+    from polycracker_b200 import distributed as pcd
+    from polycracker_b200.pipeline import dump_floor, effective_low_count
+    # table count: 5e8 windows / 0.6 * 12 B = 10 GB -> 2^8 sub-tables of 39 MB
+    assert pcd.plan_partition_bits(500_000_000, 1) == 8
+    assert pcd.plan_partition_bits(1000, 8) == 3                       # at least one bucket per rank
+    # shared-memory count: windows / 4096 sub-buckets in total, 2 * 4^pb >= that
+    for windows, want in ((500_000_000, 8), (1_000_000_000, 9), (4_000_000_000, 10), (4_460_000_000, 10)):
+        pb = pcd.plan_partition_bits(windows, 1, smem_mean=4096)
+        assert pb == want and (2 << (2 * pb)) >= windows // 4096 and (pb == 1 or (2 << (2 * (pb - 1))) < windows // 4096)
+    assert pcd.plan_partition_bits(10_000, 4, smem_mean=4096) == 2
+    assert [dump_floor(k) for k in (15, 23, 31, 32)] == [3, 3, 3, 1]
+    assert effective_low_count(23, 1) == 3 and effective_low_count(23, 30) == 30 and effective_low_count(32, 1) == 1
+    assert pcd.bind_to_gpu_numa(0) is None or isinstance(pcd.bind_to_gpu_numa(0), str)   # no NVML / GPU here: None
+
+
+def test_n2_file_stage_writers(tmp_path):
+    """kcount_hist / number_repeatmers_per_subsequence mirrors: the tables they write (plots only when matplotlib is there)."""
+    from polycracker_b200 import stages
+    kdir = tmp_path / "k"
+    kdir.mkdir()
+    (kdir / "23.kcount").write_text("ACG\t3\nCCC\t5\nGGA\t3\nTTT\t12\n")
+    (kdir / "31.kcount").write_text("AAA 7\nAAC 7\n")
+    (kdir / "notes.txt").write_text("x")
+    out = str(tmp_path / "hist.png")
+    tables = stages.kcount_hist(str(kdir), out_file=out, kcount_range="3,100", kmer_lengths="23")
+    assert list(tables) == ["23.kcount"]
+    v, f = tables["23.kcount"]
+    assert v.tolist() == [3, 5, 12] and f.tolist() == [2, 1, 1]
+    assert open(out + ".tsv").read().split("\n") == ["23.kcount\t3\t2", "23.kcount\t5\t1", "23.kcount\t12\t1"]
+    tables = stages.kcount_hist(str(kdir), out_file=out)
+    assert sorted(tables) == ["23.kcount", "31.kcount"] and tables["31.kcount"][1].tolist() == [2]
+    bed = tmp_path / "blasted_merged.bed"
+    bed.write_text("c_0_10\t0\t10\tAAA,CCC,AAA\nc_10_20\t0\t10\tGGG\n")
+    got = stages.number_repeatmers_per_subsequence(str(bed), out_file=str(tmp_path / "per"))
+    assert got.tolist() == [3, 1]
+    assert open(str(tmp_path / "per.png.tsv")).read() == "1\t1\n3\t1"
