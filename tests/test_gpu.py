@@ -400,6 +400,21 @@ def test_n3_standard_scaler(ctx):
     assert m2.nnz > 0 and np.array_equal(got2, m2.data)
 
 
+def test_threshold_watch_fused_select(ctx):
+    """pc_watch_threshold (K4 fused into the table count through returning atomics on threshold crossings): same repeat
+    set and matrix as the scan; a no-op for the shared-memory count, whose list already is the thresholded dump."""
+    p = synth.small_params(seed=95, genome_size=2_000_000, n_shared_families=6, n_specific_families=8, max_family_len=1500)
+    seq, off, names = synth.generate(p)
+    try:
+        for mode in (1, 2, 0):
+            ctx.tune(part_mode=mode, part_mbytes=1)
+            _check_against_c_oracle(ctx, seq, off, names, 20000, 23, 7, fuse_select=True)
+        ctx.watch_threshold(0)
+    finally:
+        ctx.tune(part_mode=-1, part_mbytes=64)
+        ctx.watch_threshold(0)
+
+
 def test_external_repeat_set(ctx):
     """blast_kmers as a separately invoked stage: the repeat set comes from a k-mer FASTA, in either orientation,
     unsorted, with duplicates."""
