@@ -415,6 +415,54 @@ def test_threshold_watch_fused_select(ctx):
         ctx.watch_threshold(0)
 
 
+def test_overlap_pipeline_and_sm_copy():
+    """StepPipeline (H2D of the next genome / D2H of the previous result overlapped with this step's kernels) returns, one
+    call late, exactly what a plain call returns -- for a series of DIFFERENT genomes, with copy-engine and with SM-driven
+    bulk copies; pc_copy_async moves bytes faithfully in both directions, odd sizes included."""
+    import torch
+    from polycracker_b200.overlap import StepPipeline
+    dev = torch.device("cuda", 0)
+    genomes = []
+    for i in range(4):
+        p = synth.small_params(seed=400 + i, genome_size=600_000 + 100_003 * i)
+        seq, off, names = synth.generate(p)
+        genomes.append((torch.from_numpy(seq).pin_memory(), seq, off, names))
+    with binding.Context(0) as plain:
+        want = [run_hot_path(plain, seq, off, names, chunk_size=20000, k=23, kmer_low_count=5) for _, seq, off, names in genomes]
+    for ctas in (0, 8):
+        with binding.Context(0) as c2:
+            pipe = StepPipeline(c2, dev, sm_copy_ctas=ctas)
+            got = []
+            pipe.prefetch(genomes[0][0])
+            for i, (_, seq, off, names) in enumerate(genomes):
+                if i + 1 < len(genomes):
+                    pipe.prefetch(genomes[i + 1][0])
+                prev = pipe.step(lambda d, off=off, names=names: run_hot_path(c2, d, off, names, chunk_size=20000, k=23,
+                                                                              kmer_low_count=5, fetch=False))
+                if prev is not None:
+                    got.append((prev.kmer_keys.copy(), prev.indptr.copy(), prev.indices.copy(), prev.data.copy(),
+                                prev.tfidf.copy(), prev.df.copy(), prev.scaffolds))
+            last = pipe.flush()
+            got.append((last.kmer_keys.copy(), last.indptr.copy(), last.indices.copy(), last.data.copy(), last.tfidf.copy(),
+                        last.df.copy(), last.scaffolds))
+            pipe.close()
+            assert len(got) == len(want)
+            for g, w in zip(got, want):
+                assert np.array_equal(g[0], w.kmer_keys) and np.array_equal(g[1], w.indptr) and np.array_equal(g[2], w.indices)
+                assert np.array_equal(g[3], w.data) and np.array_equal(g[4], w.tfidf) and np.array_equal(g[5], w.df)
+                assert g[6] == w.scaffolds and len(w.data) > 1000
+            # pc_copy_async on its own
+            for n in (1 << 20, 1_000_003):
+                src = torch.randint(0, 255, (n,), dtype=torch.uint8).pin_memory()
+                d = torch.empty(n, dtype=torch.uint8, device=dev)
+                back = torch.empty(n, dtype=torch.uint8).pin_memory()
+                st = torch.cuda.Stream()
+                c2.copy_async(d, src, stream=st.cuda_stream, n_ctas=4)
+                c2.copy_async(back, d, stream=st.cuda_stream, n_ctas=4)
+                st.synchronize()
+                assert torch.equal(back, src)
+
+
 def test_external_repeat_set(ctx):
     """blast_kmers as a separately invoked stage: the repeat set comes from a k-mer FASTA, in either orientation,
     unsorted, with duplicates."""
