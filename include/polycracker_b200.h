@@ -82,7 +82,8 @@ int pc_count_info(pc_ctx* ctx, int64_t info[8]);
  * auto).  For the list: detail[1] = entries, detail[2] = lowest count kept (pc_tune keep_min: kmercountexact only ever
  * dumps mincount=3, polycracker.py:199, so k-mers below it never have to leave the SM), detail[3] = sub-buckets,
  * detail[4] = sub-buckets per level-1 bucket, detail[5] = sub-buckets re-counted through a global table because their
- * distinct k-mers did not fit the shared-memory table. */
+ * distinct k-mers did not fit the shared-memory table; super-k-mer count: detail[6] = records, detail[7] = minimizer
+ * length m (both 0 when the k-mers themselves were partitioned). */
 int pc_count_detail(pc_ctx* ctx, int64_t detail[8]);
 /* dump (kmer, count) with min_count <= count <= max_count (the .kcount file: `mincount=3` for k<=31,
  * polycracker.py:199).  keys == NULL -> only *n is written.  Unordered, like the tools' dumps. */
@@ -120,6 +121,25 @@ int pc_count_buckets_from(pc_ctx* ctx, int k, int pb, int n_buckets, const uint6
 int pc_sub_plan(pc_ctx* ctx, int64_t total, int n_buckets);
 int pc_sub_hist(pc_ctx* ctx, int pb, int nb2, uint64_t* hist_dev);
 int pc_sub_hist_set(pc_ctx* ctx, int nb2, const uint64_t* hist_dev, int64_t n);
+/* Super-k-mer variant of the multi-GPU count (pc_tune part_mode 3 / auto for k >= 17; kernels_skm.cuh).  What travels is
+ * not one 8-byte k-mer per window but 16-byte records: a run of consecutive windows that share their minimizer, as
+ * 2-bit packed bases + destination + length.  All instances of a canonical k-mer share the minimizer, so the owner of a
+ * bucket still sees every instance of its k-mers and the counts stay exact (same role as kmercountexact / jellyfish,
+ * polycracker.py:199, 203).
+ * pc_skm_plan: plan shared by all ranks from the GLOBAL number of windows: plan[0] = pb, [1] = sub-buckets per level-1
+ *   bucket, [2] = minimizer length m, [3] = W = k - m + 1, [4] = k-mers per record at most, [5] = 1 when usable for this k.
+ * pc_skm_partition: K1 must have run.  bucket_off[2^pb + 1] (host) = level-1 bucket offsets in RECORDS into *recs_dev
+ *   (device, 16 bytes per record); *hist_dev (device, uint64[2^pb * nb2]) = (k-mers << 32) | records of every sub-bucket.
+ * pc_skm_export: pins the record buffer at >= n_records and returns its CUDA IPC handle (peers open it with
+ *   pc_peer_open).  pc_skm_count_from: counts n_buckets buckets given as record segments (seg_base[i * n_seg + s] device
+ *   pointers, or all relative to recs_dev when seg_base is NULL; begin / length in records) with hist_dev = the packed
+ *   histogram of exactly these buckets summed over the senders (device, uint64[n_buckets * nb2]). */
+int pc_skm_plan(pc_ctx* ctx, int k, int64_t windows_global, int world, int32_t plan[8]);
+int pc_skm_partition(pc_ctx* ctx, int k, const int32_t plan[8], int64_t* bucket_off, uint64_t** recs_dev, uint64_t** hist_dev);
+int pc_skm_export(pc_ctx* ctx, int64_t n_records, void* ipc_handle_64);
+int pc_skm_count_from(pc_ctx* ctx, int k, const int32_t plan[8], int n_buckets, const uint64_t* recs_dev,
+                      const uint64_t* const* seg_base, const int64_t* seg_begin, const int64_t* seg_len, int n_seg,
+                      const uint64_t* hist_dev);
 /* alternative exchange of pre-aggregated pairs: all (kmer,count) pairs of the local table grouped by owner rank
  * (owner = hash(kmer) % world); offsets[world+1] is a host array.  keys/counts are device buffers of
  * capacity >= distinct k-mers.  pc_merge_counts adds received pairs into the ctx table (creating it with
@@ -243,9 +263,10 @@ int pc_copy_async(pc_ctx* ctx, void* dst, const void* src, int64_t bytes, void* 
  * CUDA-event time (ms) of the last run of each stage on the ctx stream.  Index: 0 h2d, 1 pack, 2 table-init,
  * 3 count, 4 select(scan), 5 sort, 6 repeat-table, 7 probe, 8 row-sort, 9 emit, 10 tfidf, 11 d2h, 12 export, 13 merge,
  * 14 bucket histogram, 15 bucket scatter, 16 subgenome dictionary, 17 subgenome compare, 18 subgenome map-back,
- * 19 level-2 histogram + scatter of the shared-memory count.
+ * 19 level-2 histogram + scatter of the shared-memory count, 20 global-table re-count of the sub-buckets that overflowed their
+ * shared-memory table, 21 Gram matrix, 22 expansion of super-k-mer records into k-mers.
  * launches: kernels launched by this ctx since the last pc_reset_counters. */
-#define PC_N_STAGES 20
+#define PC_N_STAGES 24
 int pc_timings(pc_ctx* ctx, float ms[PC_N_STAGES]);
 int pc_launch_count(pc_ctx* ctx, int64_t* launches);
 int pc_reset_counters(pc_ctx* ctx);
@@ -269,6 +290,13 @@ int pc_host_pack_chunks(const uint8_t* ascii, const int64_t* chunk_begin, const 
                         uint64_t* words, uint32_t* nmask, int64_t* chunk_word0, int64_t cap_words, int64_t* n_words);
 int pc_host_extract(const uint64_t* words, const uint32_t* nmask, int64_t n_words, int k, uint64_t* keys,
                     uint8_t* valid);
+/* host run of the super-k-mer extraction and expansion with the device's own inline routines (unit tests):
+ * records (two uint64 each: hi, lo) of the packed words; canonical k-mers (+ destination) of records, in record order */
+int pc_host_skm_plan(int k, int64_t n_sub_total, int32_t* m_out);
+int pc_host_skm_records(const uint64_t* words, const uint32_t* nmask, int64_t n_words, int k, int m, int nmax, int pb,
+                        int nb2, uint64_t* recs, int64_t cap, int64_t* n_records);
+int pc_host_skm_expand(const uint64_t* recs, int64_t n_records, int k, uint64_t* keys, uint32_t* dest, int64_t cap,
+                       int64_t* n_keys);
 /* kmer <-> text */
 int pc_kmer_decode(const uint64_t* keys, int64_t n, int k, char* out /* n*k bytes, no separators */);
 int pc_kmer_encode(const char* text, int64_t n, int k, uint64_t* keys /* ~0 when not acgtACGT */);

@@ -11,10 +11,10 @@ import numpy as np
 from . import build as _build
 
 PC_HOST, PC_DEVICE = 0, 1
-PC_N_STAGES = 20
+PC_N_STAGES = 24
 STAGE_NAMES = ["h2d", "pack", "table_init", "count", "select", "sort", "rep_table", "probe", "row_sort", "emit",
                "tfidf", "d2h", "export", "merge", "part_hist", "part_scatter", "sub_dict", "sub_compare", "sub_mapback",
-               "part2"]
+               "part2", "count_fallback", "gram", "expand", "spare23"]
 PC_MAX_GROUPS, PC_MAX_SUB_K = 8, 8
 
 
@@ -33,13 +33,17 @@ class SynthParams(C.Structure):
 
 def _load():
     path = _build.LIB
-    if not os.path.exists(path):
-        # on the dev box nvcc is present: build in-tree; on a GPU box the prebuilt .so travels with the snapshot
+    # on the dev box (no GPU, the read-only reference tree is mounted) a library older than its sources is rebuilt
+    # in-tree; on a GPU box the prebuilt .so travels with the snapshot and is used as is (file times do not survive the
+    # copy, and N ranks must not race to rebuild it)
+    dev_box = os.path.isdir("/root/reference") or os.environ.get("PC_DEV_REBUILD") == "1"
+    if not os.path.exists(path) or (dev_box and _build.is_stale()):
         try:
             _build.build()
         except Exception as exc:  # pragma: no cover
-            raise ImportError("libpolycracker_b200.so is missing and could not be built: %s "
-                              "(the CUDA extension is mandatory, there is no CPU fallback)" % exc)
+            if not os.path.exists(path):
+                raise ImportError("libpolycracker_b200.so is missing and could not be built: %s "
+                                  "(the CUDA extension is mandatory, there is no CPU fallback)" % exc)
     return C.CDLL(path)
 
 
@@ -80,6 +84,13 @@ _SIGS = {
     "pc_peer_open": (C.c_int, [_vp, _vp, _P(_vp)]),
     "pc_peer_close": (C.c_int, [_vp, _vp]),
     "pc_count_buckets_from": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _i64]),
+    "pc_skm_plan": (C.c_int, [_vp, C.c_int, _i64, C.c_int, _vp]),
+    "pc_skm_partition": (C.c_int, [_vp, C.c_int, _vp, _vp, _P(_vp), _P(_vp)]),
+    "pc_skm_export": (C.c_int, [_vp, _i64, _vp]),
+    "pc_skm_count_from": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "pc_host_skm_plan": (C.c_int, [C.c_int, _i64, _P(_i32)]),
+    "pc_host_skm_records": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _i64, _P(_i64)]),
+    "pc_host_skm_expand": (C.c_int, [_vp, _i64, C.c_int, _vp, _vp, _i64, _P(_i64)]),
     "pc_export_by_owner": (C.c_int, [_vp, C.c_int, _vp, _vp, _i64, _vp]),
     "pc_merge_counts": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, _i64, C.c_int]),
     "pc_release": (C.c_int, [_vp, C.c_int]),
@@ -260,6 +271,36 @@ def host_extract(words, nmask, k):
     return keys, valid.astype(bool)
 
 
+def host_skm_m(k, n_sub_total):
+    """minimizer length the super-k-mer count picks for k and a number of sub-buckets (0: k too short)"""
+    m = _i32()
+    check(lib.pc_host_skm_plan(int(k), int(n_sub_total), C.byref(m)), "pc_host_skm_plan")
+    return m.value
+
+
+def host_skm_records(words, nmask, k, m, nmax, pb, nb2):
+    """Host run of the super-k-mer extraction (the device's own inline routines).  words/nmask include the trailing
+    guard word.  -> uint64[n_records, 2] (hi, lo)"""
+    n_words = len(words) - 1
+    n = _i64()
+    args = (words.ctypes.data, nmask.ctypes.data, n_words, int(k), int(m), int(nmax), int(pb), int(nb2))
+    check(lib.pc_host_skm_records(*args, None, 0, C.byref(n)), "pc_host_skm_records")
+    recs = np.zeros((n.value, 2), np.uint64)
+    check(lib.pc_host_skm_records(*args, recs.ctypes.data, n.value, C.byref(n)), "pc_host_skm_records")
+    return recs
+
+
+def host_skm_expand(recs, k):
+    """-> (canonical k-mers uint64[n], destination uint32[n]) of the records, in record order"""
+    recs = np.ascontiguousarray(recs, dtype=np.uint64)
+    n = _i64()
+    check(lib.pc_host_skm_expand(recs.ctypes.data, len(recs), int(k), None, None, 0, C.byref(n)), "pc_host_skm_expand")
+    keys = np.zeros(n.value, np.uint64); dest = np.zeros(n.value, np.uint32)
+    check(lib.pc_host_skm_expand(recs.ctypes.data, len(recs), int(k), keys.ctypes.data, dest.ctypes.data, n.value,
+                                 C.byref(n)), "pc_host_skm_expand")
+    return keys, dest
+
+
 def host_canonical(kmer, k):
     out = _u64()
     check(lib.pc_host_canonical(int(kmer), k, C.byref(out)), "pc_host_canonical")
@@ -406,7 +447,7 @@ class Context:
         d = np.zeros(8, np.int64)
         check(lib.pc_count_detail(self._h, d.ctypes.data), "pc_count_detail")
         return dict(kind="list" if d[0] == 1 else "table", kept=int(d[1]), keep_min=int(d[2]), sub_buckets=int(d[3]),
-                    sub_per_bucket=int(d[4]), overflowed=int(d[5]))
+                    sub_per_bucket=int(d[4]), overflowed=int(d[5]), skm_records=int(d[6]), skm_m=int(d[7]))
 
     def dump_counts(self, min_count=1, max_count=0xFFFFFFFF):
         n = _i64()
@@ -499,6 +540,43 @@ class Context:
         assert sp.shape == sb.shape == sl.shape and sb.ndim == 2
         check(lib.pc_count_buckets_from(self._h, int(k), int(pb), sb.shape[0], sp.ctypes.data, sb.ctypes.data,
                                         sl.ctypes.data, sb.shape[1], int(capacity)), "pc_count_buckets_from")
+
+    # super-k-mer variant of the multi-GPU count (pc_skm_*)
+    def skm_plan(self, k, windows_global, world=1):
+        """-> int32[8] plan shared by all ranks (plan[5] == 0: not usable for this k / part_mode)"""
+        plan = np.zeros(8, np.int32)
+        check(lib.pc_skm_plan(self._h, int(k), int(windows_global), int(world), plan.ctypes.data), "pc_skm_plan")
+        return plan
+
+    def skm_partition(self, k, plan):
+        """-> (bucket_off int64[2^pb + 1] in records, device pointer of the bucket-sorted records, device pointer of the
+        packed sub-bucket histogram uint64[2^pb * nb2])"""
+        plan = np.ascontiguousarray(plan, dtype=np.int32)
+        off = np.zeros((1 << int(plan[0])) + 1, np.int64)
+        recs, hist = _vp(), _vp()
+        check(lib.pc_skm_partition(self._h, int(k), plan.ctypes.data, off.ctypes.data, C.byref(recs), C.byref(hist)),
+              "pc_skm_partition")
+        return off, recs.value, hist.value
+
+    def skm_export(self, n_records):
+        h = np.zeros(64, np.uint8)
+        check(lib.pc_skm_export(self._h, int(n_records), h.ctypes.data), "pc_skm_export")
+        return h
+
+    def skm_count_from(self, k, plan, seg_base, seg_begin, seg_len, hist, recs=None):
+        """seg_base: uint64[n_buckets, n_seg] device pointers of the senders' record buffers (None: all segments are
+        relative to `recs`); hist: torch CUDA int64 tensor / device pointer of the packed histogram of these buckets."""
+        plan = np.ascontiguousarray(plan, dtype=np.int32)
+        sb = np.ascontiguousarray(seg_begin, dtype=np.int64); sl = np.ascontiguousarray(seg_len, dtype=np.int64)
+        assert sb.ndim == 2 and sb.shape == sl.shape
+        sp = None
+        if seg_base is not None:
+            sp = np.ascontiguousarray(seg_base, dtype=np.uint64)
+            assert sp.shape == sb.shape
+        hp = hist if isinstance(hist, int) else hist.data_ptr()
+        rp = recs if (recs is None or isinstance(recs, int)) else recs.data_ptr()
+        check(lib.pc_skm_count_from(self._h, int(k), plan.ctypes.data, sb.shape[0], rp, None if sp is None else sp.ctypes.data,
+                                    sb.ctypes.data, sl.ctypes.data, sb.shape[1], hp), "pc_skm_count_from")
 
     def export_by_owner(self, world, keys_t, counts_t):
         """keys_t (int64/uint64 view) and counts_t (int32) are torch CUDA tensors with >= distinct elements."""

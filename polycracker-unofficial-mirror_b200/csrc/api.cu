@@ -15,6 +15,7 @@
 #include "../../include/polycracker_b200.h"
 #include "kernels.cuh"
 #include "kernels_smem.cuh"
+#include "kernels_skm.cuh"
 
 namespace {
 
@@ -41,7 +42,7 @@ int fail(int code, const char* fmt, ...) {
 
 enum Stage { ST_H2D = 0, ST_PACK, ST_TABLE_INIT, ST_COUNT, ST_SELECT, ST_SORT, ST_REPTABLE, ST_PROBE,
              ST_ROWSORT, ST_EMIT, ST_TFIDF, ST_D2H, ST_EXPORT, ST_MERGE, ST_PART_HIST, ST_PART_SCATTER,
-             ST_SUB_DICT, ST_SUB_COMPARE, ST_SUB_MAPBACK, ST_PART2, ST_N };
+             ST_SUB_DICT, ST_SUB_COMPARE, ST_SUB_MAPBACK, ST_PART2, ST_COUNT_FALLBACK, ST_GRAM, ST_EXPAND, ST_N };
 static_assert(ST_N <= PC_N_STAGES, "stage table too small");
 static_assert(pc::kMaxGroups == PC_MAX_GROUPS && pc::kMaxSubK == PC_MAX_SUB_K, "header and kernels disagree");
 
@@ -114,6 +115,7 @@ struct pc_ctx {
     int64_t part_bytes = 64ll << 20;            // target size of one L2-resident sub-table
     int probe_mode = -1;                        // -1 auto (stream when available), 0 roller, 1 stream
     int probe_batch = 4;
+    int probe_roll = 1;                         // roller probe: 1 = filtered kernels of kernels_skm.cuh, 0 = the plain round-1 kernel
     int probe_threads = 0;                      // filtered probe: 0 auto, 512 (two CTAs per SM) or 1024
     // probe_filter: -1 auto, 0 off, 1 shared-memory bitmap, 2 L2-resident bitmap
     int probe_filter = -1;                      // shared-memory bitmap filter in front of the repeat table: -1 auto, 0 off, 1 on
@@ -142,7 +144,7 @@ struct pc_ctx {
     int count_kind = 0;                         // 0 global table, 1 compact list
     uint32_t keep_min = 1;                      // tunable: lowest count worth keeping (the reference dumps mincount=3)
     int64_t smem_target = 0;                    // tunable: mean k-mer instances per sub-bucket (0 = half the table slots: an all-distinct sub-bucket loads its table to 0.5)
-    int smem_slots() const { return smem_variant == 1 ? 4096 : smem_variant == 2 ? 16384 : 8192; }
+    int smem_slots() const { return (smem_variant == 1 || smem_variant == 5) ? 4096 : smem_variant == 2 ? 16384 : 8192; }
     int64_t smem_mean() const { return smem_target > 0 ? smem_target : (int64_t)smem_slots() / 2; }
     bool kbuf_shared = false;                   // the bucket buffer has been exported to peer processes (pc_kbuf_export)
     int rowsort_warps = 16;                     // tunable: warps per CTA in the per-row sort (8 or 16)
@@ -156,6 +158,19 @@ struct pc_ctx {
     int64_t n_list = 0, n_sub = 0, n_ovf = 0; uint32_t list_min = 1; unsigned int sub_nb2 = 0;
     // multi-GPU: level-2 histogram computed by the senders (pc_sub_hist), summed by the owner and staged for the next count
     const unsigned long long* staged_hist = nullptr; int64_t staged_n = 0; unsigned int staged_nb2 = 0;
+
+    // super-k-mer count (part_mode 3, kernels_skm.cuh): the flat record stream of the extraction (later the level-2
+    // output), the sub-bucket histogram ((k-mers << 32) | records per sub-bucket), its scan, the scatter cursors
+    DevBuf<ulonglong2> rec_a, rec_b; DevBuf<unsigned long long> d_skm_hist, d_skm_off, d_skm_cur, d_skm_n;
+    int64_t skm_cap_records = 0, skm_n_records = 0, skm_n_kmers = 0;
+    int skm_m = 0, skm_w = 0, skm_nmax_used = 0;
+    int skm_nmax = 16;                          // tunable: longest run (k-mers) one record carries (lane balance of the count kernel)
+    int skm_expand = 0;                         // tunable: 1 = expand the records into 8-byte k-mers (k_rec_expand) and count them with k_count_smem; 0 = expand inside the count kernel (k_count_skm)
+    DevBuf<unsigned long long> d_skm_koff;      // skm_expand 1: k-mer offsets of the sub-buckets + expansion cursors
+    int skm_grp = 2;                            // tunable: k-mers of a record in flight per thread in the count kernel (2, 4, 8)
+    int skm_min_k = 17;                         // auto mode: shortest k that takes the super-k-mer path
+    int skm_stage = 2560;                       // tunable: records staged per CTA of the extraction (x 16 bytes of shared memory)
+    bool skm_used = false;
 
     // N1 subgenome-extraction session (pc_sub_*): per-subgenome dictionaries of the k being compared, then per k the
     // differential sets and their union mask table
@@ -359,6 +374,7 @@ int pc_destroy(pc_ctx* c) {
     c->kbuf.release(); c->kstream.release(); c->d_part_hist.release(); c->d_seg.release(); c->cross_keys.release(); c->d_cross_n.release();
     c->d_scaled.release(); c->d_colstat.release(); c->d_rowscale.release();
     c->kbuf2.release(); c->list_keys.release(); c->list_counts.release(); c->d_sub.release(); c->d_tile.release(); c->d_ovf.release();
+    c->rec_a.release(); c->rec_b.release(); c->d_skm_hist.release(); c->d_skm_off.release(); c->d_skm_cur.release(); c->d_skm_n.release(); c->d_skm_koff.release();
     c->sel_a.release(); c->sel_b.release(); c->rs_hist.release(); c->d_counter.release(); c->rtable.release(); c->rfp.release(); c->rfilter.release();
     c->d_chunk_row.release(); c->d_row_base.release(); c->d_row_cursor.release(); c->hits_a.release();
     c->hits_b.release(); c->d_row_nnz.release(); c->d_indptr.release(); c->d_indices.release();
@@ -848,7 +864,337 @@ static int count_buckets_smem(pc_ctx* c, int k, int pb, int n_buckets, const uin
     return PC_OK;
 }
 
-static bool smem_mode(const pc_ctx* c) { return c->part_mode == 2 || c->part_mode < 0; }
+static bool smem_mode(const pc_ctx* c) { return c->part_mode == 2 || c->part_mode == 3 || c->part_mode < 0; }
+
+// ---------------------------------------------------------------------------------------------- K3, super-k-mer path
+// plan[0] = pb (level-1 bucket bits), [1] = nb2 (sub-buckets per level-1 bucket), [2] = m (minimizer length),
+// [3] = W = k - m + 1, [4] = nmax (k-mers per record), [5] = 1 when the path can run for this k
+struct SkmPlan { int pb; unsigned int nb2; int m, W, nmax; bool ok; };
+
+static SkmPlan skm_plan(const pc_ctx* c, int k, int64_t windows_global, int world) {
+    SkmPlan pl{1, 1u, 0, 0, 0, false};
+    const int64_t nb_total = std::max<int64_t>(1, windows_global / c->smem_mean());
+    // level 1 takes the smaller half of the bits, as in the k-mer path (the short runs of a wide scatter cost more at level 1)
+    int pb = 1;
+    while (pb < 12 && ((int64_t)2 << (2 * pb)) < nb_total) ++pb;
+    if (c->smem_pb > 0) pb = std::min(12, c->smem_pb);
+    while ((1 << pb) < world && pb < 12) ++pb;
+    const int64_t P = (int64_t)1 << pb;
+    pl.pb = pb;
+    pl.nb2 = (unsigned int)std::min<int64_t>(PC_SUB_MAX, std::max<int64_t>(1, (nb_total + P - 1) / P));
+    pl.m = pc::skm_choose_m(k, P * (int64_t)pl.nb2);
+    if (pl.m == 0 || k > 32) return pl;
+    pl.W = k - pl.m + 1;
+    pl.nmax = std::max(1, std::min(std::min(c->skm_nmax, PC_SKM_COUNT_NMAX), PC_SKM_BASES - k + 1));
+    pl.ok = true;
+    return pl;
+}
+
+static void skm_plan_store(const SkmPlan& pl, int32_t plan[8]) {
+    memset(plan, 0, 8 * sizeof(int32_t));
+    plan[0] = pl.pb; plan[1] = (int32_t)pl.nb2; plan[2] = pl.m; plan[3] = pl.W; plan[4] = pl.nmax; plan[5] = pl.ok ? 1 : 0;
+}
+static int skm_plan_load(const int32_t plan[8], int k, SkmPlan* pl) {
+    if (!plan || !plan[5]) return fail(PC_EINVAL, "super-k-mer plan is not usable for k = %d", k);
+    pl->pb = plan[0]; pl->nb2 = (unsigned int)plan[1]; pl->m = plan[2]; pl->W = plan[3]; pl->nmax = plan[4]; pl->ok = true;
+    if (pl->pb < 0 || pl->pb > 12 || pl->nb2 < 1 || pl->nb2 > PC_SUB_MAX || pl->m < 1 || pl->m > 16 || pl->W != k - pl->m + 1 ||
+        pl->W < PC_SKM_WMIN || pl->W > PC_SKM_WMAX || (pl->W & 1) || pl->nmax < 1 || pl->nmax > PC_SKM_COUNT_NMAX || pl->nmax + k - 1 > PC_SKM_BASES)
+        return fail(PC_EINVAL, "bad super-k-mer plan (pb %d nb2 %u m %d W %d nmax %d) for k = %d", pl->pb, pl->nb2, pl->m, pl->W, pl->nmax, k);
+    return PC_OK;
+}
+
+__global__ void __launch_bounds__(256)
+k_skm_hist_split(const unsigned long long* __restrict__ raw, int64_t n, unsigned long long* __restrict__ rec_counts,
+                 unsigned long long* __restrict__ kmer_total)
+{
+    unsigned long long s = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long v = raw[i];
+        rec_counts[i] = v & 0xFFFFFFFFull;
+        s += v >> 32;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(kmer_total, s);
+}
+
+__global__ void __launch_bounds__(256)
+k_skm_hist_kmers(const unsigned long long* __restrict__ raw, int64_t n, unsigned long long* __restrict__ kmer_counts)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) kmer_counts[i] = raw[i] >> 32;
+}
+
+extern "C++" {
+template <int W>
+static int launch_skm_extract(pc_ctx* c, int k, const SkmPlan& pl, unsigned int stage_cap) {
+    const size_t smem = (size_t)32 * PC_SKM_THREADS * sizeof(uint32_t) + (size_t)stage_cap * sizeof(pc::SkmRec);
+    CU(cudaFuncSetAttribute(pc::k_skm_extract<W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    c->launches++;
+    pc::k_skm_extract<W><<<blocks_for(c->n_words, PC_SKM_THREADS), PC_SKM_THREADS, smem, c->stream>>>(
+        c->words.p, c->nmask.p, c->n_words, k, pl.m, pl.nmax, pl.pb, pl.nb2, c->rec_a.p, (unsigned long long)c->skm_cap_records,
+        c->d_skm_n.p, c->d_skm_hist.p, stage_cap, c->d_stats.p);
+    CU(cudaGetLastError());
+    return PC_OK;
+}
+template <int TILE, int LEVEL>
+static int launch_rec_scatter(pc_ctx* c, const pc::SkmRec* recs, const pc::SkmRec* const* d_base, const int64_t* d_beg,
+                              const int64_t* d_len, const int64_t* d_tile, int n_pairs, int n_seg, int64_t n_tiles_hint,
+                              unsigned int F, unsigned int nb2, const unsigned long long* off, unsigned long long* cursor,
+                              pc::SkmRec* out) {
+    const size_t smem = (size_t)TILE * 16 + (size_t)F * 8 + (size_t)F * 4 + ((size_t)F + 2) * 4 + (size_t)TILE * 2 + 16;
+    CU(cudaFuncSetAttribute((pc::k_rec_scatter<TILE, LEVEL>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per_sm = std::max(1, std::min(TILE <= 2048 ? 3 : 2, (int)((size_t)(220 << 10) / (smem + 1024))));
+    const unsigned int grid = (unsigned int)std::max<int64_t>(1, std::min<int64_t>(148 * per_sm, n_tiles_hint));
+    c->launches++;
+    pc::k_rec_scatter<TILE, LEVEL><<<grid, 256, smem, c->stream>>>(recs, d_base, d_beg, d_len, d_tile, n_pairs, n_seg,
+                                                                    c->d_skm_n.p, (unsigned long long)c->skm_cap_records, F, nb2,
+                                                                    off, cursor, out);
+    CU(cudaGetLastError());
+    return PC_OK;
+}
+template <int SLOTS, int THREADS, int GRP>
+static int launch_count_skm(pc_ctx* c, const pc::SkmRec* recs, const unsigned long long* sub_off, unsigned int n_sub, int k,
+                            unsigned long long list_cap, unsigned long long* d_nlist, unsigned int* d_novf) {
+    const size_t smem = (size_t)SLOTS * 12 + (size_t)THREADS * PC_SKM_COUNT_NMAX;      // table + one k-mer -> lane map per warp
+    CU(cudaFuncSetAttribute((pc::k_count_skm<SLOTS, THREADS, GRP>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = std::max(1, (int)((size_t)(220 << 10) / (smem + 1024)));
+    per_sm = std::min(per_sm, 2048 / THREADS);
+    const unsigned int grid = std::min<unsigned int>(n_sub, 148u * (unsigned int)per_sm);
+    c->launches++;
+    pc::k_count_skm<SLOTS, THREADS, GRP><<<grid, THREADS, smem, c->stream>>>(
+        recs, sub_off, n_sub, k, c->keep_min, c->list_keys.p, c->list_counts.p, list_cap, d_nlist, c->d_ovf.p, d_novf, c->d_stats.p);
+    CU(cudaGetLastError());
+    return PC_OK;
+}
+}  // extern "C++"
+
+// extraction + level-1 scatter of the local chunks.  Leaves the bucket-sorted records in rec_b, the raw packed
+// histogram ((k-mers << 32) | records per sub-bucket, P * nb2 entries) in d_skm_hist and the level-1 bucket offsets (in
+// records) in h_bucket_off.  d_stats must have been reset by the caller.
+static int do_skm_partition(pc_ctx* c, int k, const SkmPlan& pl) {
+    int rc;
+    const int64_t P = (int64_t)1 << pl.pb;
+    const int64_t n_sub = P * (int64_t)pl.nb2;
+    int64_t windows = 0;
+    for (int64_t i = 0; i < c->n_chunks; ++i) windows += std::max<int64_t>(0, c->h_len[i] - k + 1);
+    // records: one per minimizer change (~2 / (W + 1) per window in random sequence), one per word boundary inside a
+    // run, one per nmax windows of a long run; 30 % head-room.  A genome that needs more (adversarial minimizer order)
+    // is reported and the caller falls back to the k-mer path.
+    const double per_window = std::min(1.0, 2.0 / (pl.W + 1) * 1.3 + 1.0 / 32.0 + 1.0 / pl.nmax);
+    int64_t cap = (int64_t)((double)windows * per_window) + c->n_words + 65536;
+    cap = std::min<int64_t>(cap, windows + 1024);
+    cap = std::max<int64_t>(cap, c->skm_cap_records);             // never shrink (the level-1 buffer may be exported to peers)
+    rc = c->rec_a.alloc((size_t)cap); if (rc) return rc;
+    rc = c->rec_b.alloc((size_t)cap); if (rc) return rc;
+    c->skm_cap_records = cap;
+    rc = c->d_skm_hist.alloc((size_t)n_sub + 8); if (rc) return rc;
+    rc = c->d_skm_off.alloc((size_t)n_sub + 8); if (rc) return rc;
+    rc = c->d_skm_cur.alloc((size_t)std::max<int64_t>(n_sub, P) + 8); if (rc) return rc;
+    rc = c->d_skm_n.alloc(4); if (rc) return rc;
+    c->skm_m = pl.m; c->skm_w = pl.W; c->skm_nmax_used = pl.nmax;
+    c->stream_valid = false;
+    unsigned long long h_n[4] = {0, 0, 0, 0};
+    {
+        StageTimer t(c, ST_PART_HIST);
+        CU(cudaMemsetAsync(c->d_skm_hist.p, 0, ((size_t)n_sub + 8) * sizeof(unsigned long long), c->stream));
+        CU(cudaMemsetAsync(c->d_skm_n.p, 0, 4 * sizeof(unsigned long long), c->stream));
+        CU(cudaMemsetAsync(c->d_skm_cur.p, 0, ((size_t)std::max<int64_t>(n_sub, P) + 8) * sizeof(unsigned long long), c->stream));
+        if (c->n_words > 0) {
+            const unsigned int stage_cap = (unsigned int)std::max(256, std::min(c->skm_stage, 8192));
+            switch (pl.W) {
+#define SKM_CASE(W_) case W_: rc = launch_skm_extract<W_>(c, k, pl, stage_cap); break;
+                SKM_CASE(4) SKM_CASE(6) SKM_CASE(8) SKM_CASE(10) SKM_CASE(12) SKM_CASE(14) SKM_CASE(16) SKM_CASE(18) SKM_CASE(20) SKM_CASE(22)
+#undef SKM_CASE
+                default: return fail(PC_EINVAL, "no extraction kernel for W = %d", pl.W);
+            }
+            if (rc) return rc;
+        }
+        // record counts per sub-bucket -> exclusive scan: off[q * nb2 + x]; the level-1 bucket q starts at off[q * nb2]
+        LAUNCH(c, k_skm_hist_split, (unsigned int)std::min<int64_t>(148 * 4, (n_sub + 255) / 256), 256, c->d_skm_hist.p, n_sub,
+               c->d_skm_off.p, c->d_skm_n.p + 2);
+        LAUNCH(c, pc::k_rs_scan<unsigned long long>, 1, 1024, c->d_skm_off.p, n_sub);
+    }
+    if (c->n_words > 0) {
+        StageTimer t(c, ST_PART_SCATTER);
+        const int64_t hint = (cap + 2047) / 2048;
+        if (P <= 1024) rc = launch_rec_scatter<4096, 1>(c, c->rec_a.p, nullptr, nullptr, nullptr, nullptr, 1, 1, hint, (unsigned int)P, pl.nb2, c->d_skm_off.p, c->d_skm_cur.p, c->rec_b.p);
+        else rc = launch_rec_scatter<2048, 1>(c, c->rec_a.p, nullptr, nullptr, nullptr, nullptr, 1, 1, hint, (unsigned int)P, pl.nb2, c->d_skm_off.p, c->d_skm_cur.p, c->rec_b.p);
+        if (rc) return rc;
+    }
+    // bucket offsets (every nb2-th entry of the scan) to the host
+    rc = c->d_tile.alloc((size_t)P + 1); if (rc) return rc;
+    LAUNCH(c, pc::k_stride_gather, blocks_for(P + 1, 256), 256, reinterpret_cast<const uint64_t*>(c->d_skm_off.p), P + 1, (int64_t)pl.nb2,
+           reinterpret_cast<uint64_t*>(c->d_tile.p));
+    c->h_bucket_off.assign(P + 1, 0);
+    READ_SMALL(c, c->h_bucket_off.data(), c->d_tile.p, (size_t)(P + 1) * sizeof(int64_t));
+    READ_SMALL(c, h_n, c->d_skm_n.p, sizeof h_n);
+    READ_SMALL(c, &c->h_stats, c->d_stats.p, sizeof(pc::CountStats));
+    SYNC(c);
+    c->skm_n_records = (int64_t)h_n[0]; c->skm_n_kmers = (int64_t)h_n[2];
+    if (h_n[1] != 0 || (int64_t)h_n[0] > cap)
+        return fail(PC_ENOMEM, "super-k-mer records overflow their buffer (%llu records for %lld slots)", h_n[0], (long long)cap);
+    if ((int64_t)h_n[0] != c->h_bucket_off[P])
+        return fail(PC_ESTATE, "super-k-mer histogram (%lld) and record stream (%llu) disagree", (long long)c->h_bucket_off[P], h_n[0]);
+    return PC_OK;
+}
+
+// level-2 scatter + shared-memory count of n_buckets level-1 buckets given as record segments (one per sender), with
+// the packed histogram of exactly those buckets (n_buckets * nb2 entries, summed over the senders) in hist_dev.
+static int count_buckets_skm(pc_ctx* c, int k, const SkmPlan& pl, int n_buckets, const pc::SkmRec* recs_dev, const int64_t* seg_begin,
+                             const int64_t* seg_len, int n_seg, const pc::SkmRec* const* seg_base_host, const unsigned long long* hist_dev) {
+    int rc;
+    const unsigned int NB2 = pl.nb2;
+    const int64_t n_pairs = (int64_t)n_buckets * n_seg;
+    const int64_t n_sub = (int64_t)n_buckets * NB2;
+    const int TILE = NB2 <= 1024 ? 4096 : 2048;
+    std::vector<int64_t> tile_start(n_pairs + 1, 0);
+    int64_t total = 0;
+    for (int64_t p = 0; p < n_pairs; ++p) {
+        if (seg_len[p] < 0 || seg_begin[p] < 0) return fail(PC_EINVAL, "bad segment");
+        total += seg_len[p];
+        tile_start[p + 1] = tile_start[p] + (seg_len[p] + TILE - 1) / TILE;
+    }
+    if (c->keep_min < 1) c->keep_min = 1;
+    const int64_t n_tiles = tile_start[n_pairs];
+    c->k = k; c->pb = pl.pb; c->sub_nb2 = NB2; c->n_sub = n_sub; c->cross_valid = false;
+    c->part_S = 0; c->capacity = (uint64_t)n_sub * (uint64_t)c->smem_slots();
+
+    rc = c->d_seg.alloc((size_t)3 * n_pairs); if (rc) return rc;
+    rc = c->d_tile.alloc((size_t)n_pairs + 1); if (rc) return rc;
+    rc = c->d_sub.alloc((size_t)2 * n_sub + 8); if (rc) return rc;
+    rc = c->d_ovf.alloc((size_t)n_sub + 2); if (rc) return rc;
+    rc = c->rec_a.alloc((size_t)std::max<int64_t>(total, 1)); if (rc) return rc;
+    rc = c->d_skm_n.alloc(4); if (rc) return rc;
+    CU(cudaMemcpyAsync(c->d_seg.p, seg_begin, (size_t)n_pairs * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_seg.p + n_pairs, seg_len, (size_t)n_pairs * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    const int64_t* d_beg = c->d_seg.p;
+    const int64_t* d_len = c->d_seg.p + n_pairs;
+    const pc::SkmRec* const* d_base = nullptr;
+    if (seg_base_host) {
+        CU(cudaMemcpyAsync(c->d_seg.p + 2 * n_pairs, seg_base_host, (size_t)n_pairs * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+        d_base = reinterpret_cast<const pc::SkmRec* const*>(c->d_seg.p + 2 * n_pairs);
+    }
+    CU(cudaMemcpyAsync(c->d_tile.p, tile_start.data(), (size_t)(n_pairs + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
+    unsigned long long* sub_off = c->d_sub.p;                              // [n_sub + 1] record counts, then offsets
+    unsigned long long* sub_cur = c->d_sub.p + n_sub + 1;                  // [n_sub] scatter cursors
+    unsigned long long* d_nlist = c->d_sub.p + 2 * n_sub + 2;              // [1]
+    unsigned int* d_novf = reinterpret_cast<unsigned int*>(c->d_sub.p + 2 * n_sub + 3);
+    unsigned long long* d_kmers = c->d_sub.p + 2 * n_sub + 4;              // [1] k-mer instances in these buckets
+    CU(cudaMemsetAsync(c->d_sub.p, 0, ((size_t)2 * n_sub + 8) * sizeof(unsigned long long), c->stream));
+    unsigned long long h_kmers = 0;
+    {
+        StageTimer t(c, ST_PART2);
+        LAUNCH(c, k_skm_hist_split, (unsigned int)std::min<int64_t>(148 * 4, (n_sub + 255) / 256), 256, hist_dev, n_sub, sub_off, d_kmers);
+        LAUNCH(c, pc::k_rs_scan<unsigned long long>, 1, 1024, sub_off, n_sub);
+        READ_SMALL(c, &h_kmers, d_kmers, sizeof h_kmers);
+        if (total > 0) {
+            if (TILE == 4096) rc = launch_rec_scatter<4096, 2>(c, recs_dev, d_base, d_beg, d_len, c->d_tile.p, (int)n_pairs, n_seg, n_tiles, NB2, NB2, sub_off, sub_cur, c->rec_a.p);
+            else rc = launch_rec_scatter<2048, 2>(c, recs_dev, d_base, d_beg, d_len, c->d_tile.p, (int)n_pairs, n_seg, n_tiles, NB2, NB2, sub_off, sub_cur, c->rec_a.p);
+            if (rc) return rc;
+        }
+    }
+    SYNC(c);                                                   // k-mer total: sizes the list
+    const unsigned long long list_cap = h_kmers / c->keep_min + 1024ull;
+    rc = c->list_keys.alloc((size_t)list_cap); if (rc) return rc;
+    rc = c->list_counts.alloc((size_t)list_cap); if (rc) return rc;
+    const bool expand = c->skm_expand != 0;
+    if (expand) {
+        // records -> 8-byte k-mers in sub-bucket order (kbuf2), then the k-mer path's count kernel and fall-back
+        rc = c->d_skm_koff.alloc((size_t)2 * n_sub + 8); if (rc) return rc;
+        rc = c->kbuf2.alloc((size_t)std::max<unsigned long long>(h_kmers, 1ull)); if (rc) return rc;
+        unsigned long long* koff = c->d_skm_koff.p;                         // [n_sub + 1]
+        unsigned long long* kcur = c->d_skm_koff.p + n_sub + 1;             // [n_sub]
+        if (total > 0) {
+            {
+                StageTimer t(c, ST_EXPAND);
+                CU(cudaMemsetAsync(kcur, 0, (size_t)n_sub * sizeof(unsigned long long), c->stream));
+                LAUNCH(c, k_skm_hist_kmers, (unsigned int)std::min<int64_t>(148 * 4, (n_sub + 255) / 256), 256, hist_dev, n_sub, koff);
+                LAUNCH(c, pc::k_rs_scan<unsigned long long>, 1, 1024, koff, n_sub);
+                LAUNCH(c, pc::k_rec_expand<512>, (unsigned int)std::min<int64_t>(n_sub, 148 * 4), 512, c->rec_a.p, sub_off, koff, kcur,
+                       (unsigned int)n_sub, k, c->kbuf2.p);
+            }
+            StageTimer t(c, ST_COUNT);
+            // k_count_smem reads c->d_sub as the k-mer offsets: hand it the expansion's
+            CU(cudaMemcpyAsync(sub_off, koff, ((size_t)n_sub + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
+            if (c->smem_variant == 1) rc = launch_count_smem<4096, 256, 4, false>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
+            else rc = launch_count_smem<8192, 512, 4, false>(c, (unsigned int)n_sub, list_cap, d_nlist, d_novf);
+            if (rc) return rc;
+        }
+    } else if (total > 0) {
+        StageTimer t(c, ST_COUNT);
+        if (c->smem_variant == 1) rc = launch_count_skm<4096, 256, 2>(c, c->rec_a.p, sub_off, (unsigned int)n_sub, k, list_cap, d_nlist, d_novf);
+        else if (c->smem_variant == 5) rc = launch_count_skm<4096, 512, 2>(c, c->rec_a.p, sub_off, (unsigned int)n_sub, k, list_cap, d_nlist, d_novf);
+        else if (c->skm_grp == 4) rc = launch_count_skm<8192, 512, 4>(c, c->rec_a.p, sub_off, (unsigned int)n_sub, k, list_cap, d_nlist, d_novf);
+        else rc = launch_count_skm<8192, 512, 2>(c, c->rec_a.p, sub_off, (unsigned int)n_sub, k, list_cap, d_nlist, d_novf);
+        if (rc) return rc;
+    }
+    unsigned long long h_nlist = 0; unsigned int h_novf = 0;
+    READ_SMALL(c, &h_nlist, d_nlist, sizeof h_nlist);
+    READ_SMALL(c, &h_novf, d_novf, sizeof h_novf);
+    rc = fetch_stats(c); if (rc) return rc;                   // synchronises
+    c->n_ovf = h_novf;
+    if (h_novf > 0 && expand) {
+        // as in count_buckets_smem: the overflowed sub-buckets are k-mer segments of kbuf2
+        std::vector<unsigned int> ids(h_novf);
+        std::vector<unsigned long long> off(n_sub + 1);
+        READ_SMALL(c, ids.data(), c->d_ovf.p, (size_t)h_novf * sizeof(unsigned int));
+        READ_SMALL(c, off.data(), sub_off, (size_t)(n_sub + 1) * sizeof(unsigned long long));
+        SYNC(c);
+        std::sort(ids.begin(), ids.end());
+        std::vector<int64_t> fb_begin(h_novf), fb_len(h_novf);
+        int64_t fb_total = 0;
+        for (unsigned int i = 0; i < h_novf; ++i) {
+            fb_begin[i] = (int64_t)off[ids[i]]; fb_len[i] = (int64_t)(off[ids[i] + 1] - off[ids[i]]); fb_total += fb_len[i];
+        }
+        const uint32_t keep_watch = c->watch_low; c->watch_low = 0;
+        {
+            // count_buckets_table times itself as ST_COUNT: keep the shared-memory count's time, report this one apart
+            cudaEvent_t k0 = c->ev[ST_COUNT][0], k1 = c->ev[ST_COUNT][1];
+            c->ev[ST_COUNT][0] = c->ev[ST_COUNT_FALLBACK][0]; c->ev[ST_COUNT][1] = c->ev[ST_COUNT_FALLBACK][1];
+            rc = count_buckets_table(c, k, 0, 1, c->kbuf2.p, fb_begin.data(), fb_len.data(), (int)h_novf,
+                                     (int64_t)(fb_total / c->table_load) + 1024);
+            c->ev[ST_COUNT_FALLBACK][0] = c->ev[ST_COUNT][0]; c->ev[ST_COUNT_FALLBACK][1] = c->ev[ST_COUNT][1];
+            c->ev[ST_COUNT][0] = k0; c->ev[ST_COUNT][1] = k1;
+            c->ev_used[ST_COUNT_FALLBACK] = true;
+        }
+        c->watch_low = keep_watch;
+        if (rc) return rc;
+        unsigned int grid = (unsigned int)std::min<uint64_t>((c->capacity + 1023) / 1024, 148ull * 64);
+        LAUNCH(c, pc::k_select, grid, 256, c->table(), c->capacity, c->keep_min, 0xFFFFFFFFu, c->list_keys.p, c->list_counts.p,
+               list_cap, d_nlist);
+        READ_SMALL(c, &h_nlist, d_nlist, sizeof h_nlist);
+        SYNC(c);
+        c->pb = pl.pb; c->part_S = 0; c->capacity = (uint64_t)n_sub * (uint64_t)c->smem_slots();
+    } else if (h_novf > 0) {
+        // sub-buckets whose distinct k-mers did not fit a shared-memory table: one global table for all of them
+        LAUNCH(c, pc::k_hist_kmer_total, std::min<unsigned int>((h_novf + 255u) / 256u, 148u), 256, hist_dev, c->d_ovf.p, h_novf, d_kmers + 1);
+        unsigned long long fb_total = 0;
+        READ_SMALL(c, &fb_total, d_kmers + 1, sizeof fb_total);
+        SYNC(c);
+        rc = table_prepare(c, k, (int64_t)((double)fb_total / c->table_load) + 1024, /*reset_stats=*/false); if (rc) return rc;
+        {
+            StageTimer t(c, ST_COUNT_FALLBACK);
+            // a heavy minimizer (one m-mer inside a high-copy repeat family carries the mutated k-mers of every copy) can put
+            // millions of records into one sub-bucket: 32 CTAs per listed sub-bucket
+            dim3 fgrid(std::min<unsigned int>(h_novf, 65535u), 32u);
+            c->launches++;
+            pc::k_count_rec_table<<<fgrid, 256, 0, c->stream>>>(c->rec_a.p, sub_off, c->d_ovf.p, h_novf, k, c->table(), c->capacity, c->d_stats.p);
+            CU(cudaGetLastError());
+        }
+        rc = fetch_stats(c); if (rc) return rc;
+        unsigned int grid = (unsigned int)std::min<uint64_t>((c->capacity + 1023) / 1024, 148ull * 64);
+        LAUNCH(c, pc::k_select, grid, 256, c->table(), c->capacity, c->keep_min, 0xFFFFFFFFu, c->list_keys.p, c->list_counts.p,
+               list_cap, d_nlist);
+        READ_SMALL(c, &h_nlist, d_nlist, sizeof h_nlist);
+        SYNC(c);
+        c->part_S = 0; c->capacity = (uint64_t)n_sub * (uint64_t)c->smem_slots();
+    }
+    if (h_nlist > list_cap) return fail(PC_ESTATE, "k-mer list overflow: %llu entries for %llu slots", h_nlist, list_cap);
+    c->n_list = (int64_t)h_nlist; c->list_min = c->keep_min;
+    c->skm_n_kmers = (int64_t)h_kmers;
+    c->counted = true; c->count_kind = 1; c->skm_used = true;
+    return PC_OK;
+}
 
 static int do_count_buckets(pc_ctx* c, int k, int pb, int n_buckets, const uint64_t* keys_dev, const int64_t* seg_begin,
                             const int64_t* seg_len, int n_seg, int64_t capacity, const uint64_t* const* seg_base_host = nullptr) {
@@ -863,7 +1209,7 @@ int pc_release(pc_ctx* c, int what) {
     SYNC(c);
     if (c->zeroed_slots > 0) { CU(cudaStreamSynchronize(c->aux_stream)); c->zeroed_slots = 0; }
     if (what & PC_REL_ASCII) { c->ascii.release(); c->ascii_padded = 0; }
-    if (what & PC_REL_BUCKETS) { c->kbuf.release(); c->kbuf2.release(); c->kbuf_shared = false; }
+    if (what & PC_REL_BUCKETS) { c->kbuf.release(); c->kbuf2.release(); c->kbuf_shared = false; c->rec_a.release(); c->rec_b.release(); c->skm_cap_records = 0; }
     if (what & PC_REL_TABLE) {
         c->table_keys.release(); c->table_counts.release(); c->counted = false; c->cross_valid = false; c->cross_keys.release();
         c->list_keys.release(); c->list_counts.release(); c->n_list = 0;
@@ -901,6 +1247,11 @@ int pc_tune(pc_ctx* c, const char* key, int64_t value) {
     else if (k == "smem_variant") c->smem_variant = (int)value;
     else if (k == "scatter_variant") c->scatter_variant = (int)value;
     else if (k == "smem_pb") c->smem_pb = (int)value;
+    else if (k == "skm_nmax") c->skm_nmax = (int)std::max<int64_t>(1, std::min<int64_t>(PC_SKM_COUNT_NMAX, value));
+    else if (k == "skm_min_k") c->skm_min_k = (int)value;
+    else if (k == "skm_grp") c->skm_grp = (int)value;
+    else if (k == "skm_expand") c->skm_expand = (int)value;
+    else if (k == "skm_stage") c->skm_stage = (int)value;
     else if (k == "scatter_tile") c->scatter_tile = (int)value;
     else if (k == "scatter_pack") c->scatter_pack = (int)value;
     else if (k == "rowsort_warps") c->rowsort_warps = (int)value;
@@ -912,6 +1263,7 @@ int pc_tune(pc_ctx* c, const char* key, int64_t value) {
     else if (k == "part_casfirst") c->part_casfirst = (int)value;
     else if (k == "part_minb") c->part_minb = (int)value;
     else if (k == "probe_batch") c->probe_batch = (int)value;
+    else if (k == "probe_roll") c->probe_roll = (int)value;
     else if (k == "rep_load_inv") c->rep_load_inv = (int)value;
     else if (k == "part_mbytes") c->part_bytes = std::max<int64_t>(1, value) << 20;
     else if (k == "part_blocks") c->part_blocks = (int)std::max<int64_t>(0, value);
@@ -937,7 +1289,27 @@ int pc_count(pc_ctx* c, int k, int64_t capacity) {
     }
     // partition plan: P = 2^pb sub-tables of S slots, each about part_bytes so that it stays L2 resident
     int pb = 0;
-    bool partitioned = c->part_mode == 1 || c->part_mode == 2 || (c->part_mode < 0 && (size_t)capacity * (size_t)PC_SLOT_BYTES > (size_t)(64ll << 20));
+    bool partitioned = c->part_mode == 1 || c->part_mode == 2 || c->part_mode == 3 ||
+                       (c->part_mode < 0 && (size_t)capacity * (size_t)PC_SLOT_BYTES > (size_t)(64ll << 20));
+    c->skm_used = false;
+    if (partitioned && c->n_words > 0 && (c->part_mode == 3 || (c->part_mode < 0 && k >= c->skm_min_k))) {
+        // super-k-mer path: records instead of k-mers through the two scatters, expansion inside the count kernel
+        SkmPlan pl = skm_plan(c, k, windows, 1);
+        if (!pl.ok && c->part_mode == 3)
+            return fail(PC_EINVAL, "k = %d is too short for the super-k-mer count (part_mode 3): use part_mode 2", k);
+        if (pl.ok) {
+            CU(cudaMemsetAsync(c->d_stats.p, 0, sizeof(pc::CountStats), c->stream));
+            rc = do_skm_partition(c, k, pl);
+            if (rc == PC_OK) {
+                const int64_t Pn = (int64_t)1 << pl.pb;
+                std::vector<int64_t> seg_begin(Pn), seg_len(Pn);
+                for (int64_t q = 0; q < Pn; ++q) { seg_begin[q] = c->h_bucket_off[q]; seg_len[q] = c->h_bucket_off[q + 1] - c->h_bucket_off[q]; }
+                return count_buckets_skm(c, k, pl, (int)Pn, c->rec_b.p, seg_begin.data(), seg_len.data(), 1, nullptr, c->d_skm_hist.p);
+            }
+            if (rc != PC_ENOMEM || c->part_mode == 3) return rc;
+            // more records than the buffer plans for (adversarial minimizer order): the k-mer path below always works
+        }
+    }
     if (partitioned && smem_mode(c)) {
         // two-level split into about windows / smem_target sub-buckets: level 1 takes the square root, rounded to a
         // power of two, the level-2 fan-out is fixed once the exact number of valid windows is known
@@ -1098,13 +1470,64 @@ int pc_sub_hist_set(pc_ctx* c, int nb2, const uint64_t* hist_dev, int64_t n) {
     return PC_OK;
 }
 
+// ---- super-k-mer building blocks for several GPUs (same roles as pc_partition / pc_kbuf_export / pc_count_buckets_from)
+int pc_skm_plan(pc_ctx* c, int k, int64_t windows_global, int world, int32_t plan[8]) {
+    if (!c || !plan || k < 1 || k > 32 || windows_global < 0 || world < 1) return fail(PC_EINVAL, "bad pc_skm_plan arguments");
+    SkmPlan pl = skm_plan(c, k, windows_global, world);
+    if (!smem_mode(c) || c->part_mode == 2) pl.ok = false;
+    skm_plan_store(pl, plan);
+    return PC_OK;
+}
+
+int pc_skm_partition(pc_ctx* c, int k, const int32_t plan[8], int64_t* bucket_off, uint64_t** recs_dev, uint64_t** hist_dev) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!c->loaded) return fail(PC_ESTATE, "pc_skm_partition before pc_load_sequences");
+    if (k < 1 || k > 32 || !bucket_off || !recs_dev || !hist_dev) return fail(PC_EINVAL, "bad pc_skm_partition arguments");
+    SkmPlan pl; rc = skm_plan_load(plan, k, &pl); if (rc) return rc;
+    c->counted = c->selected = c->built = c->tfidf_done = false;
+    CU(cudaMemsetAsync(c->d_stats.p, 0, sizeof(pc::CountStats), c->stream));
+    rc = do_skm_partition(c, k, pl); if (rc) return rc;
+    memcpy(bucket_off, c->h_bucket_off.data(), ((size_t)(1u << pl.pb) + 1) * sizeof(int64_t));
+    *recs_dev = reinterpret_cast<uint64_t*>(c->rec_b.p);
+    *hist_dev = reinterpret_cast<uint64_t*>(c->d_skm_hist.p);
+    return PC_OK;
+}
+
+int pc_skm_export(pc_ctx* c, int64_t n_records, void* ipc_handle) {
+    int rc = use_device(c); if (rc) return rc;
+    if (n_records < 1 || !ipc_handle) return fail(PC_EINVAL, "bad pc_skm_export arguments");
+    rc = c->rec_b.alloc((size_t)n_records); if (rc) return rc;       // kept (and re-used by pc_skm_partition) while it is big enough
+    rc = c->rec_a.alloc((size_t)n_records); if (rc) return rc;
+    c->skm_cap_records = std::max<int64_t>(c->skm_cap_records, n_records);
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, c->rec_b.p));
+    memcpy(ipc_handle, &h, sizeof h);
+    return PC_OK;
+}
+
+int pc_skm_count_from(pc_ctx* c, int k, const int32_t plan[8], int n_buckets, const uint64_t* recs_dev,
+                      const uint64_t* const* seg_base, const int64_t* seg_begin, const int64_t* seg_len, int n_seg,
+                      const uint64_t* hist_dev) {
+    int rc = use_device(c); if (rc) return rc;
+    SkmPlan pl; rc = skm_plan_load(plan, k, &pl); if (rc) return rc;
+    if (n_buckets < 1 || n_buckets > (1 << pl.pb) || n_seg < 1 || (!seg_base && !recs_dev) || !seg_begin || !seg_len || !hist_dev)
+        return fail(PC_EINVAL, "bad pc_skm_count_from arguments");
+    c->counted = c->selected = c->built = c->tfidf_done = false;
+    unsigned long long keep = c->h_stats.valid_windows;        // pc_skm_partition already counted the local windows
+    pc::CountStats z{}; z.valid_windows = keep;
+    CU(cudaMemcpyAsync(c->d_stats.p, &z, sizeof z, cudaMemcpyHostToDevice, c->stream));
+    SYNC(c);
+    return count_buckets_skm(c, k, pl, n_buckets, reinterpret_cast<const pc::SkmRec*>(recs_dev), seg_begin, seg_len, n_seg,
+                             reinterpret_cast<const pc::SkmRec* const*>(seg_base), reinterpret_cast<const unsigned long long*>(hist_dev));
+}
+
 int pc_count_info(pc_ctx* c, int64_t info[8]) {
     if (!c || !c->counted) return fail(PC_ESTATE, "no count table");
     memset(info, 0, 8 * sizeof(int64_t));
     info[0] = (int64_t)c->capacity; info[1] = (int64_t)c->h_stats.distinct; info[2] = (int64_t)c->h_stats.valid_windows;
     info[3] = (int64_t)(c->capacity * (size_t)PC_SLOT_BYTES); info[4] = (int64_t)c->h_stats.max_probe; info[5] = c->k;
     info[6] = c->count_kind == 1 ? c->n_list : 0; info[7] = c->pb;
-    if (c->count_kind == 1) info[3] = (int64_t)((size_t)c->list_keys.n * 12 + (size_t)c->kbuf2.n * 8);
+    if (c->count_kind == 1) info[3] = (int64_t)((size_t)c->list_keys.n * 12 + (c->skm_used ? (size_t)c->rec_a.n * 16 : (size_t)c->kbuf2.n * 8));
     return PC_OK;
 }
 
@@ -1114,6 +1537,7 @@ int pc_count_detail(pc_ctx* c, int64_t detail[8]) {
     detail[0] = c->count_kind;
     if (c->count_kind == 1) {
         detail[1] = c->n_list; detail[2] = c->list_min; detail[3] = c->n_sub; detail[4] = c->sub_nb2; detail[5] = c->n_ovf;
+        if (c->skm_used) { detail[6] = c->skm_n_records; detail[7] = c->skm_m; }
     }
     return PC_OK;
 }
@@ -1469,8 +1893,17 @@ int pc_set_selected(pc_ctx* c, const uint64_t* keys, int64_t n, int k, int loc, 
     unsigned long long nu = 0;
     uint64_t* result = sorted;
     if (n > 0) {
+        // entries that are not k-mers (the sentinel pc_kmer_encode returns for a name with N or any non-ACGT character)
+        // are dropped: canonicalising them would turn every one into poly-A and match windows the query never named
+        unsigned long long sent = 0;
+        CU(cudaMemsetAsync(c->d_counter.p, 0, 2 * sizeof(unsigned long long), c->stream));
+        LAUNCH(c, pc::k_count_sentinel, blocks_for(n, 256), 256, sorted, n, c->d_counter.p + 1);
+        READ_SMALL(c, &sent, c->d_counter.p + 1, sizeof sent);
+        SYNC(c);
+        n -= (int64_t)sent;                                    // sorted last
+    }
+    if (n > 0) {
         unsigned long long dups = 0;
-        CU(cudaMemsetAsync(c->d_counter.p, 0, sizeof(unsigned long long), c->stream));
         LAUNCH(c, pc::k_count_dups, blocks_for(n, 256), 256, sorted, n, c->d_counter.p);
         READ_SMALL(c, &dups, c->d_counter.p, sizeof dups);
         SYNC(c);
@@ -1611,9 +2044,24 @@ int pc_build_matrix(pc_ctx* c, const int32_t* chunk_row, int64_t n_rows, int64_t
                     LAUNCH(c, (pc::k_probe_stream<8>), grid, 256, c->kstream.p, c->n_words, c->d_word0.p, c->n_chunks,
                            c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, use_fp ? c->rfp.p : nullptr,
                            c->gfilter_bits ? c->rfilter.p : nullptr, c->gfilter_bits, c->hits_a.p, c->d_row_cursor.p);
-            } else {
+            } else if (c->probe_roll == 0) {
                 LAUNCH(c, (pc::k_probe<8>), grid, 256, c->words.p, c->nmask.p, c->n_words, k, c->d_word0.p, c->n_chunks,
                        c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, use_fp ? c->rfp.p : nullptr, c->hits_a.p, c->d_row_cursor.p);
+            } else if (c->rfilter_bits > 0 && !use_fp) {
+                // no k-mer stream (super-k-mer count): roller + shared-memory bitmap, one persistent CTA of 1024 threads per SM
+                size_t smem = (size_t)(c->rfilter_bits / 32 + 4) * sizeof(unsigned int);
+                unsigned int pgrid = (unsigned int)std::min<int64_t>(148, (c->n_words + 1023) / 1024);
+                c->launches++;
+                CU(cudaFuncSetAttribute((pc::k_probe_roll_filt<4, 1024, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                pc::k_probe_roll_filt<4, 1024, true><<<pgrid, 1024, smem, c->stream>>>(c->words.p, c->nmask.p, c->n_words, k, c->d_word0.p,
+                    c->n_chunks, c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, nullptr, c->rfilter.p, c->rfilter_bits,
+                    c->hits_a.p, c->d_row_cursor.p);
+                CU(cudaGetLastError());
+            } else {
+                unsigned int pgrid = (unsigned int)std::min<int64_t>(148 * 8, (c->n_words + 255) / 256);
+                LAUNCH(c, (pc::k_probe_roll_filt<8, 256, false>), pgrid, 256, c->words.p, c->nmask.p, c->n_words, k, c->d_word0.p,
+                       c->n_chunks, c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, use_fp ? c->rfp.p : nullptr,
+                       c->gfilter_bits ? c->rfilter.p : nullptr, c->gfilter_bits, c->hits_a.p, c->d_row_cursor.p);
             }
         }
     }
@@ -1894,6 +2342,73 @@ int pc_host_extract(const uint64_t* words, const uint32_t* nmask, int64_t n_word
             if (b < 31) r.step(b);
         }
     }
+    return PC_OK;
+}
+
+// host run of the super-k-mer extraction (the SAME inline routines as k_skm_extract: SkmThread, skm_run_length, skm_dest,
+// skm_record) over packed words, and of the record expansion (RecRoller): unit tests of the bit logic without a GPU
+extern "C++" {
+template <int W>
+static int64_t host_skm_records(const uint64_t* words, const uint32_t* nmask, int64_t n_words, int k, int m, int nmax, int pb,
+                                unsigned int nb2, uint64_t* recs, int64_t cap) {
+    int64_t n_out = 0;
+    for (int64_t w = 0; w < n_words; ++w) {
+        if (nmask[w] == 0xFFFFFFFFu) continue;
+        pc::SkmThread<W> th;
+        th.run(words[w], words[w + 1], nmask[w], nmask[w + 1], k, m, nmax);      // word n_words is the guard word
+        uint32_t rem = th.starts;
+        while (rem) {
+            const int b = __builtin_ctz(rem);
+            rem &= rem - 1;
+            const int n = pc::skm_run_length(th.vmask, th.starts, b);
+            const uint32_t dest = pc::skm_dest(th.hmin[b], pb, nb2);
+            uint64_t hi, lo;
+            pc::skm_record(words[w], words[w + 1], b, n, k, dest, hi, lo);
+            if (recs && n_out < cap) { recs[2 * n_out] = hi; recs[2 * n_out + 1] = lo; }
+            ++n_out;
+        }
+    }
+    return n_out;
+}
+}  // extern "C++"
+
+int pc_host_skm_plan(int k, int64_t n_sub_total, int32_t* m_out) {
+    if (!m_out) return fail(PC_EINVAL, "m_out is null");
+    *m_out = pc::skm_choose_m(k, n_sub_total);
+    return PC_OK;
+}
+
+int pc_host_skm_records(const uint64_t* words, const uint32_t* nmask, int64_t n_words, int k, int m, int nmax, int pb,
+                        int nb2, uint64_t* recs, int64_t cap, int64_t* n_records) {
+    if (!words || !nmask || !n_records || k < 1 || k > 32 || m < 1 || m > 16 || m > k || nmax < 1 || nmax + k - 1 > PC_SKM_BASES ||
+        pb < 0 || pb > 12 || nb2 < 1 || nb2 > PC_SUB_MAX)
+        return fail(PC_EINVAL, "bad pc_host_skm_records arguments");
+    const int W = k - m + 1;
+    int64_t n = -1;
+    switch (W) {
+#define SKM_CASE(W_) case W_: n = host_skm_records<W_>(words, nmask, n_words, k, m, nmax, pb, (unsigned int)nb2, recs, cap); break;
+        SKM_CASE(4) SKM_CASE(6) SKM_CASE(8) SKM_CASE(10) SKM_CASE(12) SKM_CASE(14) SKM_CASE(16) SKM_CASE(18) SKM_CASE(20) SKM_CASE(22)
+#undef SKM_CASE
+        default: return fail(PC_EINVAL, "W = k - m + 1 = %d is not an even value in [4, 22]", W);
+    }
+    *n_records = n;
+    return PC_OK;
+}
+
+int pc_host_skm_expand(const uint64_t* recs, int64_t n_records, int k, uint64_t* keys, uint32_t* dest, int64_t cap, int64_t* n_keys) {
+    if (!recs || !n_keys || k < 1 || k > 32) return fail(PC_EINVAL, "bad pc_host_skm_expand arguments");
+    int64_t out = 0;
+    for (int64_t i = 0; i < n_records; ++i) {
+        pc::RecRoller r;
+        r.init(recs[2 * i], recs[2 * i + 1], k);
+        const int n = pc::skm_rec_n(recs[2 * i + 1]);
+        for (int j = 0; j < n; ++j) {
+            if (keys && out < cap) { keys[out] = r.canonical(); if (dest) dest[out] = pc::skm_rec_dest(recs[2 * i + 1]); }
+            ++out;
+            r.step();
+        }
+    }
+    *n_keys = out;
     return PC_OK;
 }
 

@@ -967,9 +967,20 @@ k_canonicalize(uint64_t* __restrict__ keys, int64_t n, int k)
 {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (keys[i] == PC_KEY_SENTINEL) return;                   // "not a k-mer" (pc_kmer_encode of a name with N): stays the sentinel
     uint64_t x = keys[i] & kmer_mask(k);
     uint64_t rc = revcomp_bits(x, k);
     keys[i] = x < rc ? x : rc;
+}
+
+// number of sentinel entries (the radix sort over 2k bits puts them last: no canonical-min k-mer has all 2k bits set)
+__global__ void __launch_bounds__(256)
+k_count_sentinel(const uint64_t* __restrict__ keys, int64_t n, unsigned long long* __restrict__ n_sent)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool s = i < n && keys[i] == PC_KEY_SENTINEL;
+    unsigned int bal = __ballot_sync(0xFFFFFFFFu, s);
+    if ((threadIdx.x & 31) == 0 && bal) atomicAdd(n_sent, (unsigned long long)__popc(bal));
 }
 
 __global__ void __launch_bounds__(256)

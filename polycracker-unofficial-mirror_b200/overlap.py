@@ -84,7 +84,7 @@ class StepPipeline:
     def close(self):
         """Hand the context back to its private stream."""
         self.s_main.synchronize()
-        self.ctx.set_stream(0)
+        self.ctx.set_stream(None)                             # None = the context's own stream (0 would mean cudaStreamLegacy)
 
     def _dev(self, slot, name, n, dtype):
         torch = self.torch

@@ -277,7 +277,7 @@ def _cols_of(names_list, kmers, kmer_idx):
         order = np.argsort(keys)
         pos = np.searchsorted(keys[order], q)
         pos[pos >= len(keys)] = 0
-        hit = keys[order][pos] == q
+        hit = (keys[order][pos] == q) & (q != np.uint64(0xFFFFFFFFFFFFFFFF))   # ~0 = "not a k-mer" (N, other letters)
         return np.where(hit, order[pos], -1).astype(np.int32)
     return np.array([kmer_idx.get(n, -1) for n in names_list], np.int32)
 

@@ -202,6 +202,91 @@ def test_shared_memory_count(ctx, k):
         ctx.tune(part_mode=-1, smem_variant=0, scatter_variant=0, smem_target=0, keep_min=1)
 
 
+@pytest.mark.parametrize("k", [12, 17, 23, 26, 31, 32])
+def test_super_kmer_count(ctx, k):
+    """The super-k-mer count (part_mode 3: minimizer-partitioned 16-byte records through both scatters, k-mers expanded
+    inside the count kernel): record lengths, staging overflow, tiny and huge sub-buckets (the latter overflow their
+    shared-memory table and take the record fall-back through a global table), keep_min floors, forced level-1 widths,
+    all against the oracle."""
+    p = synth.small_params(seed=500 + k, genome_size=2_000_000, n_fraction=0.01)
+    seq, off, names = synth.generate(p)
+    lay = ChunkLayout(names, off, 20000)
+    ctx.load_sequences(seq, lay.chunk_begin_abs, lay.chunk_end_abs)
+    want_keys, want_counts, n_windows = c_oracle.count(seq, lay.chunk_begin_abs, lay.chunk_end_abs, k)
+    distinct = len(want_keys)
+
+    def check(keep_min, expect_overflow=None):
+        ctx.count(k)
+        d = ctx.count_detail()
+        assert d["kind"] == "list" and d["keep_min"] == keep_min and d["skm_records"] > 0 and d["skm_m"] >= 9, d
+        if expect_overflow is not None:
+            assert (d["overflowed"] > 0) == expect_overflow, d
+        keys, counts = ctx.dump_counts(keep_min)
+        order = np.argsort(keys)
+        m = want_counts >= keep_min
+        assert d["kept"] == int(m.sum())
+        assert np.array_equal(keys[order], want_keys[m]) and np.array_equal(counts[order].astype(np.uint64), want_counts[m])
+        info = ctx.count_info()
+        assert info["valid_windows"] == n_windows and info["distinct"] == distinct
+        return d
+
+    try:
+        # (no "no overflow" expectation here: one minimizer inside a high-copy repeat family collects the mutated k-mers
+        # of every copy, so a few sub-buckets outgrow their table on any repeat-rich genome and take the fall-back)
+        ctx.tune(part_mode=3, smem_target=0, keep_min=1, skm_nmax=16, skm_stage=2560, smem_pb=0)
+        d0 = check(1)
+        for nmax in (1, 5, 32):                                  # one k-mer per record ... as long as a record can hold
+            ctx.tune(skm_nmax=nmax)
+            d = check(1)
+            assert (d["skm_records"] == n_windows) if nmax == 1 else (d["skm_records"] < n_windows)
+        ctx.tune(skm_nmax=16, skm_stage=256)                     # staging area too small: records leave one by one
+        assert check(1)["skm_records"] == d0["skm_records"]
+        ctx.tune(skm_stage=2560, keep_min=3)
+        check(3)
+        with pytest.raises(binding.PolycrackerError, match="not kept"):
+            ctx.dump_counts(2)
+        for pb in (1, 5, 11):                                    # 2 ... 2048 level-1 buckets
+            ctx.tune(smem_pb=pb)
+            assert check(3)["skm_records"] == d0["skm_records"]
+        ctx.tune(smem_pb=0, smem_target=100, keep_min=2)         # hundreds of tiny sub-buckets per bucket
+        d = check(2)
+        assert d["sub_per_bucket"] > 50
+        ctx.tune(smem_target=200_000, keep_min=1)                # sub-buckets far larger than a table: record fall-back
+        check(1, expect_overflow=distinct > 100_000)
+        ctx.tune(keep_min=4)
+        check(4)
+        ctx.tune(smem_target=0, keep_min=3)
+        _check_against_c_oracle(ctx, seq, off, names, 20000, k, 5)
+        assert ctx.count_detail()["skm_records"] > 0
+    finally:
+        ctx.tune(part_mode=-1, smem_target=0, keep_min=1, skm_nmax=16, skm_stage=2560, smem_pb=0)
+
+
+def test_super_kmer_count_odd_shapes(ctx):
+    """part_mode 3 on inputs that unbalance the minimizer buckets (poly-A, tandem repeats: every window of 300 kb shares
+    ONE minimizer), on thousands of tiny scaffolds (chunks shorter than k, words that hold several chunks) and on a chunk
+    with 2 % N; and too short a k is refused loudly."""
+    rng = np.random.default_rng(3)
+    tiny = [("t%d" % i, "".join(rng.choice(list("ACGT"), int(rng.integers(1, 90))))) for i in range(3000)]
+    seqs = [("polyA", "A" * 300000), ("at", "AT" * 100000), ("unit", "ACGTTGCAAC" * 30000)] + tiny + \
+           [("big", "".join(rng.choice(list("ACGTN"), 400000, p=[.245, .245, .245, .245, .02])))]
+    seq, off, names = util.from_sequences(seqs)
+    try:
+        for target in (0, 300):
+            ctx.tune(part_mode=3, smem_target=target)
+            _check_against_c_oracle(ctx, seq, off, names, 50000, 23, 3, remove_non_chunk=0)
+            assert ctx.count_detail()["skm_records"] > 0
+            _check_against_c_oracle(ctx, seq, off, names, 1000000, 16, 3, remove_non_chunk=0)
+            _check_against_c_oracle(ctx, seq, off, names, 1000000, 32, 3, remove_non_chunk=0)
+        ctx.tune(smem_target=0)
+        lay = ChunkLayout(names, off, 50000)
+        ctx.load_sequences(seq, lay.chunk_begin_abs, lay.chunk_end_abs)
+        with pytest.raises(binding.PolycrackerError, match="too short"):
+            ctx.count(9)
+    finally:
+        ctx.tune(part_mode=-1, smem_target=0)
+
+
 def test_small_table_reports_overflow_not_garbage(ctx):
     p = synth.small_params(seed=9, genome_size=100_000)
     seq, off, names = synth.generate(p)
@@ -543,7 +628,9 @@ def test_cfg2_full_size_parity(ctx):
     res, want = _check_against_c_oracle(ctx, seq, off, names, cfg["chunk_size"], cfg["k"], cfg["kmer_low_count"])
     assert res.stats["valid_windows"] > 490_000_000 and res.shape[1] > 500_000 and len(want["data"]) > 90_000_000
     d = ctx.count_detail()
-    assert d["kind"] == "list" and d["overflowed"] == 0
+    # the super-k-mer count ran; a handful of sub-buckets (heavy minimizers inside high-copy repeat families) may take the
+    # global-table fall-back, never more than a fraction of a percent
+    assert d["kind"] == "list" and d["skm_records"] > 50_000_000 and d["overflowed"] < d["sub_buckets"] // 500
     ctx.release(ctx.REL_BUCKETS | ctx.REL_TABLE | ctx.REL_STREAM | ctx.REL_HITS | ctx.REL_ASCII)   # 20 GB back for the next tests
 
 

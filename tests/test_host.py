@@ -182,3 +182,36 @@ def test_n2_file_stage_writers(tmp_path):
     got = stages.number_repeatmers_per_subsequence(str(bed), out_file=str(tmp_path / "per"))
     assert got.tolist() == [3, 1]
     assert open(str(tmp_path / "per.png.tsv")).read() == "1\t1\n3\t1"
+
+
+@pytest.mark.parametrize("k,chunk", [(23, 20000), (31, 7777), (32, 5000), (17, 20000), (12, 3000), (26, 50000)])
+def test_super_kmer_records_partition_the_kmers_exactly(k, chunk):
+    """Host run of the device's own super-k-mer routines (kmer_skm.cuh: window validity, rolling m-mer hashes, sliding
+    minimum, record boundaries, record assembly, rolling and direct expansion): the records hold exactly the multiset of
+    canonical k-mers of the packed genome, every k-mer goes to ONE destination (so counting bucket by bucket is exact),
+    destinations and record lengths respect the plan."""
+    from polycracker_b200 import synth
+    from polycracker_b200.pipeline import ChunkLayout
+    p = synth.small_params(seed=11, genome_size=200_000)
+    seq, off, names = synth.generate(p)
+    lay = ChunkLayout(names, off, chunk)
+    words, nmask, _ = binding.host_pack_chunks(seq, lay.chunk_begin_abs, lay.chunk_end_abs)
+    keys, valid = binding.host_extract(words, nmask, k)
+    want = np.sort(keys[valid])
+    for nsub, pb, nb2, nmax in [(10, 1, 5, 16), (121000, 8, 473, 16), (1_090_000, 10, 1065, 8), (4000, 2, 2048, 1)]:
+        m = binding.host_skm_m(k, nsub)
+        assert 9 <= m <= 16 and (k - m + 1) % 2 == 0 and 4 <= k - m + 1 <= 22
+        nmax = min(nmax, 49 - k + 1)
+        recs = binding.host_skm_records(words, nmask, k, m, nmax, pb, nb2)
+        got, dest = binding.host_skm_expand(recs, k)
+        assert np.array_equal(np.sort(got), want)
+        order = np.lexsort((dest, got))
+        g, d = got[order], dest[order]
+        same = g[1:] == g[:-1]
+        assert np.all(d[1:][same] == d[:-1][same]), "a canonical k-mer went to two destinations"
+        assert (d >> 11).max() < (1 << pb) and (d & 2047).max() < nb2
+        n = (recs[:, 1] & np.uint64(63)).astype(np.int64) + 1
+        assert n.max() <= nmax and n.sum() == len(want)
+        if nmax == 1:
+            assert len(recs) == len(want)
+    assert binding.host_skm_m(9, 1000) == 0                     # too short for a minimizer window

@@ -54,8 +54,8 @@ def main():
                 t = ctx.timings()
                 ctx.select(max(a.low, int(v.get("keep_min", 1))))
                 t2 = ctx.timings()
-                ts.append((t["count"] + t["part_hist"] + t["part_scatter"] + t["part2"] + t["table_init"] + t2["select"],
-                           t["table_init"], t["count"], t["part_hist"], t["part_scatter"], t["part2"], t2["select"]))
+                ts.append((t["count"] + t["part_hist"] + t["part_scatter"] + t["part2"] + t["table_init"] + t["count_fallback"] + t["expand"] + t2["select"],
+                           t["table_init"], t["count"], t["part_hist"], t["part_scatter"], t["part2"], t2["select"], t["count_fallback"], t["expand"]))
             info = ctx.count_info()
             det = ctx.count_detail()
             sig = (info["distinct"], info["valid_windows"])
@@ -64,7 +64,7 @@ def main():
             best = min(ts)
             print(json.dumps(dict(variant=v, total_ms=round(best[0], 3), init_ms=round(best[1], 3), count_ms=round(best[2], 3),
                                   hist_ms=round(best[3], 3), scatter_ms=round(best[4], 3), part2_ms=round(best[5], 3),
-                                  select_ms=round(best[6], 3), detail=det,
+                                  select_ms=round(best[6], 3), fallback_ms=round(best[7], 3), expand_ms=round(best[8], 3), detail=det,
                                   ginserts_per_s=round(info["valid_windows"] / best[0] / 1e6, 2),
                                   load=round(info["distinct"] / info["capacity"], 3), max_probe=info["max_probe"],
                                   ok=(sig == base))), flush=True)
