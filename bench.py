@@ -38,11 +38,10 @@ METRIC = "matrix_build_gbp_per_s_k23"
 UNIT = "Gbp/s"
 WORKLOAD = "cfg2_500Mbp_allotetraploid"
 FALLBACK_HBM_GBS = 6650.0
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed `ncu --set full`
-# capture of this workload (profiles/); None until a capture of the current kernel exists
-NCU_TRAFFIC = {"K3_count": 4.048e9,   # k_count_smem: 3.978 GB read + 0.070 GB written (= one read of the 8-byte k-mers)
-               "K5_probe": 4.409e9}   # k_probe_stream_filt: 4.028 GB read + 0.382 GB written
-# (profiles/r01_ncu_full_bench_500Mbp_top_kernels_raw.csv: `ncu --set full` of this file's default workload)
+# dram__bytes_read.sum + dram__bytes_write.sum per step of the dominant unit (K3 = every kernel of the count), summed over
+# its launches, from the committed `ncu --set full` capture of THIS workload with THIS kernel variant
+# (profiles/r02_ncu_k3_500Mbp.md).  Keyed by (count kind, super-k-mer minimizer length); anything else reports null.
+NCU_TRAFFIC = {}
 
 
 def parse_args():
@@ -52,9 +51,11 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--genome-size", type=int, default=0, help="override bases per GPU (testing only)")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="override the CPU-baseline sample size in bases")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="bases of the genome the CPU legs run on (0 = reference arm: the "
+                    "whole genome; cpu_baseline leg of the GPU arm: a bounded sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the 3 Mbp oracle check that precedes the timed loops")
     return ap.parse_args()
 
 
@@ -197,37 +198,23 @@ def algorithmic_bytes_count(n_bases_packed, n_windows):
 
 # ------------------------------------------------------------------------------------------------ CPU arm
 def cpu_reference_pass(seq, off, names, cfg):
-    """The C restatement of the reference path (oracle/oracle.c) over one in-memory genome; returns seconds."""
-    from oracle import c_oracle
-    from tests import util
+    """The C restatement of the reference path (oracle/ref_path.py -> oracle.c) over one in-memory genome; seconds."""
+    from oracle import ref_path
     t0 = time.perf_counter()
-    out = util.c_oracle_path(seq, off, names, cfg["chunk_size"], cfg["k"], cfg["kmer_low_count"])
-    dt = time.perf_counter() - t0
-    return dt, out
-
-
-def cpu_sample(params, target_bases):
-    from polycracker_b200 import synth
-    lay = synth.layout(params)
-    chroms, total = [], 0
-    for c, (_, ln) in enumerate(lay):
-        if total >= target_bases:
-            break
-        chroms.append(c); total += ln
-    seq, off, names = synth.generate(params, chroms=chroms, threads=8)
-    if total > target_bases and len(chroms) == 1:          # a single huge chromosome: cut it
-        seq = seq[:target_bases].copy(); off = np.array([0, target_bases], np.int64)
-    return seq, off, names
+    out = ref_path.run(seq, off, names, cfg["chunk_size"], cfg["k"], cfg["kmer_low_count"])
+    return time.perf_counter() - t0, out
 
 
 def run_reference_arm(args):
+    """The reference's own path restated on the CPU, on the SAME genome and config as the GPU arm (the full cfg2 genome:
+    every step is one whole pass), all host cores.  Nothing of the product is imported or mapped here: the genome comes
+    from oracle/libpcsynth.so, geometry and row order from the literal oracle, the arithmetic from oracle.c."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from oracle import c_oracle
-    cfg, params, per_gpu = workload_params(1, args.genome_size)
-    sample_bases = args.cpu_sample or min(per_gpu, 72_000_000)
-    seq, off, names = cpu_sample(params, sample_bases)
+    from oracle import c_oracle, ref_path
+    cfg, params = ref_path.workload(WORKLOAD, args.genome_size)
+    seq, off, names = ref_path.generate(params, max_bases=args.cpu_sample, threads=8)
     times = []
     for i in range(args.warmup + args.steps):
         dt, out = cpu_reference_pass(seq, off, names, cfg)
@@ -236,15 +223,20 @@ def run_reference_arm(args):
     sec = float(np.mean(times))
     val = len(seq) / sec / 1e9
     cores = c_oracle.threads()
-    sample = "%d bp (first %d chromosomes of the %s genome), full path count->select->match->CSR->TF-IDF" % (
-        len(seq), len(names), WORKLOAD)
+    sample = "%d bp = %s of the %s genome, full path count->select->match->CSR->TF-IDF" % (
+        len(seq), "all %d chromosomes" % len(names) if not args.cpu_sample else "the first %d chromosomes" % len(names), WORKLOAD)
+    mapped = [l.split()[-1] for l in open("/proc/self/maps") if ".so" in l and ("polycracker" in l or "oracle" in l)]
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "k": cfg["k"], "chunk_size": cfg["chunk_size"],
-                       "kmer_low_count": cfg["kmer_low_count"], "sample_bases": int(len(seq))},
+            "config": {"workload": WORKLOAD, "genome_bases": int(len(seq)), "bases_per_gpu": int(len(seq)), "k": cfg["k"],
+                       "chunk_size": cfg["chunk_size"], "kmer_low_count": cfg["kmer_low_count"],
+                       "n_subgenomes": cfg["n_subgenomes"]},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "result": {"n_selected": int(len(out["sel"])), "nnz": int(len(out["data"])), "rows": int(len(out["scaffolds"])),
+                       "valid_windows": int(out["n_windows"]), "distinct_kmers": int(len(out["keys"]))},
+            "native_libraries_mapped": sorted(set(os.path.basename(m) for m in mapped)),
             "note": "oracle/oracle.c (C+OpenMP restatement): the reference's kmercountexact/bbmap/bedtools/py2 chain "
                     "cannot run here (SURVEY.md F8)"}
     print(json.dumps(line))
@@ -252,6 +244,57 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def parity_check(ctx, device, world, rank, dist):
+    """Before anything is timed: a 3 Mbp genome through the SAME entry points the timed steps use (run_hot_path, or
+    run_hot_path_distributed + gather_rows over NCCL at N > 1) against the CPU oracle -- repeat set, CSR bit-exact, TF-IDF
+    within 1e-6 relative.  A bench line is only printed when this holds."""
+    from polycracker_b200 import synth
+    from polycracker_b200.pipeline import ChunkLayout, run_hot_path
+    p = synth.small_params(seed=191, genome_size=3_000_000, n_chrom=3, n_shared_families=6, n_specific_families=8)
+    k, chunk, low = 23, 20000, 10
+    lay_all = synth.layout(p)
+    names = [n for n, _ in lay_all]
+    offs = np.concatenate([[0], np.cumsum([l for _, l in lay_all])]).astype(np.int64)
+    layout = ChunkLayout(names, offs, chunk)
+    seq, _, _ = synth.generate(p)
+    if world == 1:
+        full = run_hot_path(ctx, seq, offs, names, chunk_size=chunk, k=k, kmer_low_count=low, layout=layout)
+    else:
+        from polycracker_b200 import distributed as pcd
+
+        def fetch(ids, begins, ends, total):
+            buf = np.empty(total, np.uint8)
+            for j, i in enumerate(ids.tolist()):
+                a = int(offs[layout.chunk_seq[i]])
+                buf[begins[j]:ends[j]] = seq[a + layout.chunk_start[i]:a + layout.chunk_end[i]]
+            return buf
+        res = pcd.run_hot_path_distributed(ctx, layout, fetch, device, chunk_size=chunk, k=k, kmer_low_count=low,
+                                           exchange=os.environ.get("PC_EXCHANGE", "auto"))
+        full = pcd.gather_rows(res)
+    out = None
+    if rank == 0:
+        from oracle import ref_path
+        want = ref_path.run(seq, offs, names, chunk, k, low)
+        tf_err = 0.0
+        if len(want["tfidf"]):
+            tf_err = float(np.max(np.abs(np.asarray(full.tfidf, np.float64) - want["tfidf"]) / np.maximum(np.abs(want["tfidf"]), 1e-30)))
+        ok = (np.array_equal(full.kmer_keys, want["sel"]) and full.scaffolds == want["scaffolds"]
+              and np.array_equal(full.indptr, want["indptr"]) and np.array_equal(full.indices, want["indices"])
+              and np.array_equal(full.data, want["data"]) and tf_err <= 1e-6)
+        out = {"n_gpus": world, "ok": bool(ok), "genome_bases": int(len(seq)), "k": k, "n_selected": int(len(want["sel"])),
+               "nnz": int(len(want["data"])), "rows": int(len(want["scaffolds"])), "tfidf_max_rel_err": tf_err,
+               "checker": "oracle/ref_path.py (oracle.c)", "entry": "run_hot_path" if world == 1 else
+               "run_hot_path_distributed + gather_rows (%s)" % full.stats.get("exchange")}
+    if dist is not None:
+        flag = [out["ok"] if rank == 0 else None]
+        dist.broadcast_object_list(flag, src=0)
+        if not flag[0]:
+            raise SystemExit("parity check failed: %r" % (out,))
+    elif not out["ok"]:
+        raise SystemExit("parity check failed: %r" % (out,))
+    return out
+
+
 def run_b200_arm(args):
     import torch
     from polycracker_b200 import binding, synth
@@ -324,6 +367,7 @@ def run_b200_arm(args):
                                             exchange=os.environ.get("PC_EXCHANGE", "auto"))
 
     layout.rows()                                          # host-side row order: cached, reused by every step
+    parity = None if args.no_parity else parity_check(ctx, device, world, rank, dist)
 
     def barrier():
         if dist is not None:
@@ -444,7 +488,9 @@ def run_b200_arm(args):
                "sequential_ms_per_step": ms_lat / args.steps,
                "sequential_value": genome_bases / (ms_lat / args.steps * 1e-3) / 1e9,
                "note": "K back-to-back steps through the public API, host buffers: pinned host genome -> H2D -> "
-                       "pc_load_sequences ... pc_csr_get/pc_tfidf_get -> D2H into pinned host memory, every step; copies "
+                       "pc_load_sequences ... pc_csr_get16/pc_tfidf_factors_get -> D2H into pinned host memory, every step "
+                       "(compact hand-off: int32 column ids + uint16 counts + idf + row norms, 6 B per entry; the float32 "
+                       "count / tf-idf arrays are rebuilt on the host bit for bit, outside the timed region); copies "
                        "of neighbouring steps overlap this step's kernels (StepPipeline).  sequential_* = the same "
                        "with nothing overlapped (latency of one call)" + ("; bytes per rank" if world > 1 else "")}
 
@@ -468,11 +514,14 @@ def run_b200_arm(args):
     # K4 scans the count result: 12 B x table slots, or 12 B x list entries when the shared-memory count left a
     # compact (k-mer, count) list instead of a table
     scan_units = detail["kept"] if detail["kind"] == "list" else cap
-    k3_ms = stage_ms["part_hist"] + stage_ms["part_scatter"] + stage_ms["part2"] + stage_ms["table_init"] + stage_ms["count"]
+    k3_parts = {"extract": stage_ms["part_hist"], "scatter_level1": stage_ms["part_scatter"], "scatter_level2": stage_ms["part2"],
+                "table_init": stage_ms["table_init"], "expand": stage_ms.get("expand", 0.0), "count": stage_ms["count"],
+                "count_fallback": stage_ms.get("count_fallback", 0.0)}
+    k3_ms = sum(k3_parts.values())
+    # one entry per unit of SURVEY.md 8d; K3 is ONE unit (0.375 G + 24 T) over all of its launches
     model = {
         "K1_pack": (1.375 * G, stage_ms["pack"]),
-        "K3_partition(extract,scatter,level2)": (0.375 * G, stage_ms["part_hist"] + stage_ms["part_scatter"] + stage_ms["part2"]),
-        "K3_count": (24.0 * T, stage_ms["count"]),
+        "K3_count": (0.375 * G + 24.0 * T, k3_ms),
         "K4_select+sort": (12.0 * scan_units + 12.0 * Ds, stage_ms["select"] + stage_ms["sort"] + stage_ms["rep_table"]),
         "K5_probe": (0.375 * G + 12.0 * T + 8.0 * nnz, stage_ms["probe"]),
         "K6_rows_to_csr": (16.0 * nnz + 8.0 * R, stage_ms["row_sort"] + stage_ms["emit"]),
@@ -482,36 +531,41 @@ def run_b200_arm(args):
     for name, (nbytes, ms) in model.items():
         gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
         kernels[name] = {"algorithmic_bytes": nbytes, "ms": ms, "achieved_gbs": gbs, "frac": gbs / peak}
-    dom = max((n for n in kernels if not n.startswith("K3_partition")), key=lambda n: kernels[n]["ms"])
+    kernels["K3_count"]["launch_ms"] = {k_: round(v, 4) for k_, v in k3_parts.items()}
+    dom = max(kernels, key=lambda n: kernels[n]["ms"])
     d = kernels[dom]
     path_bytes = sum(v[0] for v in model.values())
-    k3_bytes = 0.375 * G + 24.0 * T
-    kernels["K3_whole(partition+count)"] = {"algorithmic_bytes": k3_bytes, "ms": k3_ms,
-                                            "achieved_gbs": k3_bytes / (k3_ms * 1e-3) / 1e9 if k3_ms > 0 else 0.0,
-                                            "frac": (k3_bytes / (k3_ms * 1e-3) / 1e9 / peak) if k3_ms > 0 else 0.0}
-    count_kernel = "k_count_smem (shared-memory sub-bucket count)" if detail["kind"] == "list" else "k_count_part (bucket count)"
-    roofline = {"bound": "hbm", "kernel": {"K3_count": count_kernel, "K5_probe": "k_probe_stream (repeat-table probe)"}.get(dom, dom),
+    skm = detail.get("skm_m", 0) > 0
+    unit_kernels = {
+        "K3_count": ("k_skm_extract + k_rec_scatter<1> + k_rec_scatter<2> + k_count_skm (super-k-mer count)" if skm else
+                     "k_extract + k_tile_scatter + k_sub_scatter + k_count_smem (k-mer count)") if detail["kind"] == "list"
+        else "k_extract + k_tile_scatter + k_count_part (table count)",
+        "K5_probe": "k_probe_roll_filt" if skm else "k_probe_stream_filt", "K6_rows_to_csr": "k_row_sort + k_row_emit"}
+    roofline = {"bound": "hbm", "kernel": unit_kernels.get(dom, dom),
                 "achieved": d["achieved_gbs"],
-                "peak": peak, "unit": "GB/s", "frac": d["frac"], "traffic": NCU_TRAFFIC.get(dom), "peak_source": peak_src,
+                "peak": peak, "unit": "GB/s", "frac": d["frac"],
+                "traffic": NCU_TRAFFIC.get((dom, detail["kind"], detail.get("skm_m", 0), int(genome_bases))),
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": d["algorithmic_bytes"], "launch_ms": d["ms"],
                 "whole_path": {"algorithmic_bytes": path_bytes, "ms": ms_per_step,
                                "achieved_gbs": path_bytes / (ms_per_step * 1e-3) / 1e9,
                                "frac": path_bytes / (ms_per_step * 1e-3) / 1e9 / peak},
                 "per_kernel": kernels, "stage_ms": stage_ms,
                 "count": detail,
-                "model": "SURVEY.md 8d per-unit bytes x units of this launch, per rank (K3 = 0.375 G + 24 T is split: the "
-                         "count kernel owns the 24 T, the partition passes the packed-genome read; K3_whole puts the whole "
-                         "K3 model over all of its passes).  The probe and the count are L2 / shared-memory-atomic bound, "
-                         "not HBM-stream bound (profiles/)"}
+                "model": "SURVEY.md 8d per-unit bytes x units of this step, per rank; the dominant unit is the one with the "
+                         "largest CUDA-event time over ALL of its launches (K3 = extraction + both scatters + count + "
+                         "fall-back, one unit with 0.375 G + 24 T).  `traffic` is null unless a committed ncu capture of this "
+                         "workload and kernel variant exists (NCU_TRAFFIC)"}
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:            # the CPU baseline is reported at N = 1 only
-        from oracle import c_oracle
-        sample_bases = args.cpu_sample or min(per_gpu, 72_000_000)
-        s_seq, s_off, s_names = cpu_sample(workload_params(1, args.genome_size)[1], sample_bases)
-        dt, _ = cpu_reference_pass(s_seq, s_off, s_names, cfg)
+        from oracle import c_oracle, ref_path
+        sample_bases = args.cpu_sample or min(per_gpu, 250_000_000)     # ~10 s of CPU work on 16 cores
+        r_cfg, r_params = ref_path.workload(WORKLOAD, args.genome_size)
+        s_seq, s_off, s_names = ref_path.generate(r_params, max_bases=sample_bases, threads=8)
+        dt, _ = cpu_reference_pass(s_seq, s_off, s_names, r_cfg)
         cpu_baseline = {"value": len(s_seq) / dt / 1e9, "unit": UNIT, "cores": c_oracle.threads(), "kind": "port",
-                        "sample": "%d bp (first %d chromosomes of the 1-GPU %s genome), full path, %.1f s wall" % (
+                        "sample": "%d bp (first %d chromosomes of the %s genome), full path, %.1f s wall" % (
                             len(s_seq), len(s_names), WORKLOAD, dt)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -519,17 +573,22 @@ def run_b200_arm(args):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "genome_bases": genome_bases, "bases_per_gpu": per_gpu, "k": k,
                        "chunk_size": chunk, "kmer_low_count": low, "n_subgenomes": cfg["n_subgenomes"],
-                       "l2_policy": "inputs larger than L2 (ASCII %.0f MB, k-mer stream %.1f GB, count %s %.1f GB per rank)" % (
-                           local_bases / 1e6, 8.0 * T / 1e9, "buffers" if detail["kind"] == "list" else "table",
+                       "l2_policy": "inputs larger than L2 (ASCII %.0f MB, %s, count %s %.1f GB per rank)" % (
+                           local_bases / 1e6,
+                           "super-k-mer records %.1f GB" % (16.0 * detail.get("skm_records", 0) / 1e9) if skm else
+                           "k-mer stream %.1f GB" % (8.0 * T / 1e9), "buffers" if detail["kind"] == "list" else "table",
                            info["table_bytes"] / 1e9),
                        "parallelism": ("one GPU" if world == 1 else
                                        "chunks sharded over %d ranks; k-mers hash-partitioned by owner, owners read the "
                                        "senders' bucket buffers over NVLink peer memory (level-2 histograms exchanged), "
                                        "all-gather of the repeat set, all-reduce of df" % world)},
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "parity_check": parity,
+            "gpu_launches": int(launches),
             "numa_binding_rank0": numa, "clocks": clocks, "step_wall_ms": [round(x, 2) for x in step_wall], "quiet_gpu_wait_s": round(quiet_wait, 2),
             "result": {"distinct_kmers_rank0": info["distinct"], "valid_windows_rank0": info["valid_windows"],
-                       "table_capacity": info["capacity"], "load_factor": info["distinct"] / max(1, info["capacity"]),
+                       "shared_tables": detail.get("sub_buckets"), "shared_table_slots": info["capacity"] // max(1, detail.get("sub_buckets") or 1),
+                       "mean_shared_table_load": info["distinct"] / max(1, info["capacity"]),
+                       "overflowed_sub_buckets": detail.get("overflowed"),
                        "n_selected": (res.stats["n_selected"] if res is not None else None),
                        "nnz_rank0": (res.stats["nnz"] if res is not None else None),
                        "rows_rank0": (res.stats["n_rows"] if res is not None else None),

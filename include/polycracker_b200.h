@@ -176,12 +176,25 @@ int pc_matrix_from_hits(pc_ctx* ctx, const int64_t* row_offsets, const int32_t* 
                         int64_t* nnz);
 int pc_csr_get(pc_ctx* ctx, int64_t* indptr, int32_t* indices, float* data, int loc);
 int pc_df_get(pc_ctx* ctx, int32_t* df, int loc);                      /* stored entries per column */
+/* Compact hand-off of the same matrix (what crosses PCIe in the end-to-end path): the counts are integers bounded by the
+ * windows of a chunk, so they travel as uint16 (6 bytes per entry with the int32 column id instead of 12 with the float32
+ * count and tf-idf arrays).  An entry >= 65535 (one k-mer filling a chunk of >= 65535 windows: poly-A) is stored as 65535
+ * and returned by pc_csr_escapes_get as (position in the CSR arrays, value); *n_escapes says how many there are.
+ * The float32 arrays a consumer of clusteringMatrix.npz wants are rebuilt on the host (data = float32(data16), escapes
+ * patched in). */
+int pc_csr_get16(pc_ctx* ctx, int64_t* indptr, int32_t* indices, uint16_t* data16, int loc, int64_t* n_escapes);
+int pc_csr_escapes_get(pc_ctx* ctx, int64_t* pos, float* val, int loc);
 
 /* ---- K7  TF-IDF + L2 rows (replaces sklearn TfidfTransformer().fit_transform, polycracker.py:395-396) -------
  * idf_j = ln((1+n)/(1+df_j)) + 1 in float32; rows divided by their L2 norm (double accumulation), zero rows
  * untouched.  n_rows_global / df_global (device or host, may be NULL = use local) let ranks share a global idf. */
 int pc_tfidf(pc_ctx* ctx, int64_t n_rows_global, const int32_t* df_global, int df_loc);
 int pc_tfidf_get(pc_ctx* ctx, float* data, int loc);                   /* nnz values, CSR order */
+/* the two vectors the tf-idf values are a function of: idf[n_selected] (float32) and the L2 norm of every row (double,
+ * 0 for an empty row).  value(i in row r, column j) = float32(double(float32(count_i) * idf_j) / row_norm_r) -- the
+ * kernel's own arithmetic (one float32 multiply, one double divide rounded once), so a host rebuilds the array bit for
+ * bit from 4 * n_selected + 8 * n_rows bytes instead of reading 4 * nnz. */
+int pc_tfidf_factors_get(pc_ctx* ctx, float* idf, double* row_norm, int loc);
 
 /* ---- N1  subgenome extraction inner loop (scope row N1; replaces the external-tool chain of
  * subgenomeExtraction, polycracker.py:991-1020: kmercountexact per subgenome 692-719, compareKmers 735-783,

@@ -14,9 +14,11 @@ LIB = os.path.join(HERE, "liboracle.so")
 
 
 def build(force=False):
+    """liboracle.so (this checker) and libpcsynth.so (the workload generator as a library of its own, for ref_path.py)."""
     src = os.path.join(HERE, "oracle.c")
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(src):
-        subprocess.run(["make", "-C", HERE, "-B", "liboracle.so"], check=True, capture_output=True)
+    synth = os.path.join(HERE, "libpcsynth.so")
+    if force or not os.path.exists(LIB) or not os.path.exists(synth) or os.path.getmtime(LIB) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", HERE, "-B", "all"], check=True, capture_output=True)
     return LIB
 
 

@@ -109,6 +109,9 @@ _SIGS = {
     "pc_matrix_from_hits": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _P(_i64)]),
     "pc_csr_get": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int]),
     "pc_df_get": (C.c_int, [_vp, _vp, C.c_int]),
+    "pc_csr_get16": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _P(_i64)]),
+    "pc_csr_escapes_get": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "pc_tfidf_factors_get": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "pc_tfidf": (C.c_int, [_vp, _i64, _vp, C.c_int]),
     "pc_tfidf_get": (C.c_int, [_vp, _vp, C.c_int]),
     "pc_timings": (C.c_int, [_vp, _vp]),
@@ -646,6 +649,32 @@ class Context:
             raise ValueError("all CSR outputs must live in the same place")
         check(lib.pc_csr_get(self._h, ptr(indptr)[0], ptr(indices)[0], ptr(data)[0], locs.pop() if locs else PC_HOST),
               "pc_csr_get")
+
+    def csr16_into(self, indptr=None, indices=None, data16=None):
+        """Compact hand-off: counts as uint16 (any 2-byte container: numpy uint16 / torch int16).  -> number of entries
+        >= 65535 (stored as 65535; fetch them with csr_escapes)."""
+        locs = {ptr(x)[1] for x in (indptr, indices, data16) if x is not None}
+        if len(locs) > 1:
+            raise ValueError("all CSR outputs must live in the same place")
+        n = _i64()
+        check(lib.pc_csr_get16(self._h, ptr(indptr)[0], ptr(indices)[0], ptr(data16)[0], locs.pop() if locs else PC_HOST,
+                               C.byref(n)), "pc_csr_get16")
+        return n.value
+
+    def csr_escapes(self, n):
+        pos = np.empty(n, np.int64); val = np.empty(n, np.float32)
+        if n:
+            check(lib.pc_csr_escapes_get(self._h, pos.ctypes.data, val.ctypes.data, PC_HOST), "pc_csr_escapes_get")
+        return pos, val
+
+    def tfidf_factors_into(self, idf=None, row_norm=None):
+        """idf float32[n_selected], row_norm float64[n_rows] (same location): everything a host needs to rebuild the
+        tf-idf values bit for bit (pipeline.rebuild_tfidf)."""
+        locs = {ptr(x)[1] for x in (idf, row_norm) if x is not None}
+        if len(locs) > 1:
+            raise ValueError("idf and row_norm must live in the same place")
+        check(lib.pc_tfidf_factors_get(self._h, ptr(idf)[0], ptr(row_norm)[0], locs.pop() if locs else PC_HOST),
+              "pc_tfidf_factors_get")
 
     def df(self, n_cols):
         out = np.empty(n_cols, np.int32)

@@ -104,6 +104,8 @@ struct pc_ctx {
     DevBuf<int32_t> d_chunk_row; DevBuf<int64_t> d_row_base; DevBuf<unsigned int> d_row_cursor;
     DevBuf<int32_t> hits_a, hits_b; DevBuf<int64_t> d_row_nnz, d_indptr;
     DevBuf<int32_t> d_indices; DevBuf<float> d_data, d_idf, d_tfidf; DevBuf<int> d_df, d_df_global;
+    DevBuf<double> d_row_norm; DevBuf<unsigned short> d_data16; DevBuf<int64_t> d_esc_pos; DevBuf<float> d_esc_val;
+    int64_t n_esc = -1;                          // escapes of the last pc_csr_get16 (-1: none taken)
     int64_t n_rows = 0, nnz = 0;
     bool built = false, tfidf_done = false, scaled_done = false;
     DevBuf<float> d_scaled; DevBuf<double> d_colstat, d_rowscale;   // N3: StandardScaler(with_mean=False) values
@@ -379,6 +381,7 @@ int pc_destroy(pc_ctx* c) {
     c->d_chunk_row.release(); c->d_row_base.release(); c->d_row_cursor.release(); c->hits_a.release();
     c->hits_b.release(); c->d_row_nnz.release(); c->d_indptr.release(); c->d_indices.release();
     c->d_data.release(); c->d_idf.release(); c->d_tfidf.release(); c->d_df.release(); c->d_df_global.release();
+    c->d_row_norm.release(); c->d_data16.release(); c->d_esc_pos.release(); c->d_esc_val.release();
     c->sub_clear();
     for (int i = 0; i < ST_N; ++i) { cudaEventDestroy(c->ev[i][0]); cudaEventDestroy(c->ev[i][1]); }
     if (c->mailbox) cudaFreeHost(c->mailbox);
@@ -1981,7 +1984,7 @@ int pc_build_matrix(pc_ctx* c, const int32_t* chunk_row, int64_t n_rows, int64_t
     if (!c->loaded || !c->selected) return fail(PC_ESTATE, "pc_build_matrix needs loaded sequences and a repeat set");
     if (n_rows < 0 || (c->n_chunks > 0 && !chunk_row)) return fail(PC_EINVAL, "bad build_matrix arguments");
     if (n_rows > 0x7FFFFFFF) return fail(PC_EINVAL, "too many rows");
-    c->built = c->tfidf_done = false;
+    c->built = c->tfidf_done = false; c->n_esc = -1;
     const int k = c->k;
     std::vector<int64_t> row_base(n_rows + 1, 0), row_windows(std::max<int64_t>(n_rows, 1), -1);
     for (int64_t i = 0; i < c->n_chunks; ++i) {
@@ -2114,6 +2117,53 @@ int pc_csr_get(pc_ctx* c, int64_t* indptr, int32_t* indices, float* data, int lo
     return PC_OK;
 }
 
+// compact hand-off (6 bytes per entry instead of 12 with the float32 tf-idf array): counts as uint16 + escapes
+int pc_csr_get16(pc_ctx* c, int64_t* indptr, int32_t* indices, uint16_t* data16, int loc, int64_t* n_escapes) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!c->built) return fail(PC_ESTATE, "no matrix built");
+    if (!n_escapes) return fail(PC_EINVAL, "n_escapes is null");
+    StageTimer t(c, ST_D2H);
+    // an entry >= 65535 needs a chunk with >= 65535 windows holding ONE k-mer: at most one per 65535 hits
+    int64_t hits = 0;
+    const int64_t esc_cap = c->nnz / 65535 + c->n_rows + 16;
+    rc = c->d_data16.alloc(std::max<int64_t>(c->nnz, 1)); if (rc) return rc;
+    rc = c->d_esc_pos.alloc(esc_cap); if (rc) return rc;
+    rc = c->d_esc_val.alloc(esc_cap); if (rc) return rc;
+    (void)hits;
+    unsigned long long ne = 0;
+    CU(cudaMemsetAsync(c->d_counter.p + 8, 0, sizeof(unsigned long long), c->stream));
+    if (c->nnz > 0)
+        LAUNCH(c, pc::k_data_u16, (unsigned int)std::min<int64_t>(148 * 8, (c->nnz + 255) / 256), 256, c->d_data.p, c->nnz, c->d_data16.p,
+               c->d_counter.p + 8, c->d_esc_pos.p, c->d_esc_val.p, (unsigned long long)esc_cap);
+    READ_SMALL(c, &ne, c->d_counter.p + 8, sizeof ne);
+    if (indptr) { rc = copy_out(c, indptr, c->d_indptr.p, (c->n_rows + 1) * sizeof(int64_t), loc); if (rc) return rc; }
+    if (indices) { rc = copy_out(c, indices, c->d_indices.p, c->nnz * sizeof(int32_t), loc); if (rc) return rc; }
+    if (data16) { rc = copy_out(c, data16, c->d_data16.p, c->nnz * sizeof(uint16_t), loc); if (rc) return rc; }
+    SYNC(c);
+    if ((int64_t)ne > esc_cap) return fail(PC_ESTATE, "%llu matrix entries >= 65535 for %lld escape slots", ne, (long long)esc_cap);
+    c->n_esc = (int64_t)ne;
+    *n_escapes = c->n_esc;
+    return PC_OK;
+}
+
+int pc_csr_escapes_get(pc_ctx* c, int64_t* pos, float* val, int loc) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!c->built || c->n_esc < 0) return fail(PC_ESTATE, "pc_csr_escapes_get before pc_csr_get16");
+    if (c->n_esc == 0) return PC_OK;
+    if (!pos || !val) return fail(PC_EINVAL, "null escape buffers");
+    rc = copy_out(c, pos, c->d_esc_pos.p, c->n_esc * sizeof(int64_t), loc); if (rc) return rc;
+    return copy_out(c, val, c->d_esc_val.p, c->n_esc * sizeof(float), loc);
+}
+
+int pc_tfidf_factors_get(pc_ctx* c, float* idf, double* row_norm, int loc) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!c->tfidf_done) return fail(PC_ESTATE, "no tf-idf computed");
+    StageTimer t(c, ST_D2H);
+    if (idf) { rc = copy_out(c, idf, c->d_idf.p, c->n_sel * sizeof(float), loc); if (rc) return rc; }
+    if (row_norm) { rc = copy_out(c, row_norm, c->d_row_norm.p, c->n_rows * sizeof(double), loc); if (rc) return rc; }
+    return PC_OK;
+}
+
 int pc_df_get(pc_ctx* c, int32_t* df, int loc) {
     int rc = use_device(c); if (rc) return rc;
     if (!c->built) return fail(PC_ESTATE, "no matrix built");
@@ -2140,8 +2190,11 @@ int pc_tfidf(pc_ctx* c, int64_t n_rows_global, const int32_t* df_global, int df_
     {
         StageTimer t(c, ST_TFIDF);
         if (c->n_sel > 0) LAUNCH(c, pc::k_idf, blocks_for(c->n_sel, 256), 256, df, c->n_sel, (float)(n_rows_global + 1), c->d_idf.p);
+        rc = c->d_row_norm.alloc(std::max<int64_t>(c->n_rows, 1)); if (rc) return rc;
+        CU(cudaMemsetAsync(c->d_row_norm.p, 0, std::max<int64_t>(c->n_rows, 1) * sizeof(double), c->stream));
         if (c->n_rows > 0 && c->nnz > 0)
-            LAUNCH(c, (pc::k_tfidf<256>), (unsigned int)c->n_rows, 256, c->d_indptr.p, c->d_indices.p, c->d_data.p, c->d_idf.p, c->d_tfidf.p);
+            LAUNCH(c, (pc::k_tfidf<256>), (unsigned int)c->n_rows, 256, c->d_indptr.p, c->d_indices.p, c->d_data.p, c->d_idf.p, c->d_tfidf.p,
+                   c->d_row_norm.p);
     }
     SYNC(c);
     c->tfidf_done = true;

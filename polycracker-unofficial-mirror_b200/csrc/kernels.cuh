@@ -1458,7 +1458,7 @@ k_idf(const int* __restrict__ df, int64_t n_cols, float n_plus_1, float* __restr
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_tfidf(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ data,
-        const float* __restrict__ idf, float* __restrict__ out)
+        const float* __restrict__ idf, float* __restrict__ out, double* __restrict__ row_norm)
 {
     __shared__ double red[THREADS / 32];
     __shared__ double norm_s;
@@ -1479,11 +1479,29 @@ k_tfidf(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices,
         double s = 0.0;
         for (int q = 0; q < THREADS / 32; ++q) s += red[q];
         norm_s = sqrt(s);
+        if (row_norm) row_norm[row] = norm_s;                 // with idf, all a host needs to rebuild the values (pc_tfidf_factors_get)
     }
     __syncthreads();
     double nrm = norm_s;
     if (nrm == 0.0) return;
     for (int64_t i = beg + t; i < end; i += THREADS) out[i] = (float)((double)out[i] / nrm);
+}
+
+// Compact hand-off of the matrix over PCIe: the counts are small integers (at most the windows of a chunk), so they travel
+// as uint16 instead of float32; the rare entry >= 65535 (a poly-A chunk) is stored as 65535 and listed apart.
+__global__ void __launch_bounds__(256)
+k_data_u16(const float* __restrict__ data, int64_t n, unsigned short* __restrict__ out, unsigned long long* __restrict__ n_esc,
+           int64_t* __restrict__ esc_pos, float* __restrict__ esc_val, unsigned long long esc_cap)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float v = data[i];
+        if (v >= 65535.0f) {
+            const unsigned long long p = atomicAdd(n_esc, 1ull);
+            if (p < esc_cap) { esc_pos[p] = i; esc_val[p] = v; }
+            out[i] = 65535;
+        } else out[i] = (unsigned short)v;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------ N1 subgenome extraction

@@ -116,8 +116,6 @@ class StepPipeline:
         d_keys = self._dev(slot, "keys", n_sel, torch.int64)
         d_indptr = self._dev(slot, "indptr", n_rows + 1, torch.int64)
         d_indices = self._dev(slot, "indices", nnz, torch.int32)
-        d_data = self._dev(slot, "data", nnz, torch.float32)
-        d_tf = self._dev(slot, "tfidf", nnz, torch.float32) if tfidf else None
         d_df = self._dev(slot, "df", n_sel, torch.int32)
         if n_sel:
             self.ctx.selected_into(d_keys)
@@ -125,41 +123,53 @@ class StepPipeline:
                 self.ctx.df_into(d_df)
             else:
                 d_df.copy_(df[:n_sel])
-        self.ctx.csr_into(d_indptr, d_indices if nnz else None, d_data if nnz else None)
-        if tfidf and nnz:
-            self.ctx.tfidf_into(d_tf)
+        # compact hand-off (pc_csr_get16 / pc_tfidf_factors_get): counts as uint16, idf + row norms instead of the tf-idf
+        # array -- 6 bytes per matrix entry cross PCIe instead of 12; the host rebuilds the float32 arrays bit for bit
+        d_data = self._dev(slot, "data16", nnz, torch.int16)                  # 2-byte container for uint16
+        n_esc = self.ctx.csr16_into(d_indptr, d_indices if nnz else None, d_data if nnz else None)
+        escapes = self.ctx.csr_escapes(n_esc) if n_esc else None             # a handful of entries, read back at once
+        d_idf = d_norm = None
+        if tfidf:
+            d_idf = self._dev(slot, "idf", n_sel, torch.float32)
+            d_norm = self._dev(slot, "row_norm", n_rows, torch.float64)
+            self.ctx.tfidf_factors_into(d_idf if n_sel else None, d_norm if n_rows else None)
         ev = torch.cuda.Event()
         ev.record(main)
         # D2H on the copy-out stream into this slot's page-locked arena
         a = self.arena[slot]
         h = dict(keys=a.get("keys", n_sel, np.uint64), indptr=a.get("indptr", n_rows + 1, np.int64),
-                 indices=a.get("indices", nnz, np.int32), data=a.get("data", nnz, np.float32),
-                 tfidf=a.get("tfidf", nnz, np.float32) if tfidf else None, df=a.get("df", n_sel, np.int32))
+                 indices=a.get("indices", nnz, np.int32), data16=a.get("data16", nnz, np.uint16),
+                 idf=a.get("idf", n_sel, np.float32) if tfidf else None,
+                 row_norm=a.get("row_norm", n_rows, np.float64) if tfidf else None, df=a.get("df", n_sel, np.int32))
         with torch.cuda.stream(self.s_d2h):
             self.s_d2h.wait_event(ev)
-            for name, src in (("keys", d_keys), ("indptr", d_indptr), ("indices", d_indices), ("data", d_data),
-                              ("tfidf", d_tf), ("df", d_df)):
+            for name, src in (("keys", d_keys), ("indptr", d_indptr), ("indices", d_indices), ("data16", d_data),
+                              ("idf", d_idf), ("row_norm", d_norm), ("df", d_df)):
                 if src is None or src.numel() == 0:
                     continue
-                dst = torch.from_numpy(h[name].view(np.int64) if name == "keys" else h[name])
+                view = {"keys": np.int64, "data16": np.int16}.get(name)
+                dst = torch.from_numpy(h[name].view(view) if view else h[name])
                 self._copy_pieces(dst, src)
                 self.d2h_bytes += src.numel() * src.element_size()
             done = torch.cuda.Event()
             done.record(self.s_d2h)
         self.snap_free[slot] = done
         previous = self._collect()
-        self.pending = (done, res, h)
+        self.pending = (done, res, h, escapes)
         self.n_steps += 1
         return previous
 
     def _collect(self):
+        """Host result of the pending step.  Its arrays are views into this pipeline's page-locked arena: they stay valid
+        until the step() after next reuses the slot (depth = 2) -- copy what must live longer."""
         if self.pending is None:
             return None
-        done, res, h = self.pending
+        done, res, h, escapes = self.pending
         done.synchronize()
         self.pending = None
-        return HotPathResult(res.layout, res.k, res.scaffolds, h["keys"], h["indptr"], h["indices"], h["data"],
-                             h["tfidf"], h["df"], res.stats, res.timings)
+        return HotPathResult(res.layout, res.k, res.scaffolds, h["keys"], h["indptr"], h["indices"], None, None, h["df"],
+                             res.stats, res.timings, data16=h["data16"], escapes=escapes, idf=h["idf"],
+                             row_norm=h["row_norm"])
 
     def flush(self):
         """Host result of the last step."""

@@ -4,8 +4,6 @@ the C ABI.  The file-based stage functions (stages.py / cli.py) and bench.py are
 Host code here is integer bookkeeping only (chunk names, row order, row filter: polycracker.py:129-156, 284-287,
 322-327); it never touches a base or a k-mer.
 """
-from dataclasses import dataclass, field
-
 import numpy as np
 
 from . import binding
@@ -64,19 +62,54 @@ class ChunkLayout:
         return self._rows_cache[key]
 
 
-@dataclass
+def rebuild_counts(data16, escapes=None):
+    """float32 counts (what clusteringMatrix.npz holds, polycracker.py:355) from the compact uint16 hand-off; entries
+    >= 65535 come from the escape list (positions, values)."""
+    data = np.asarray(data16).view(np.uint16).astype(np.float32)
+    if escapes is not None and len(escapes[0]):
+        data[np.asarray(escapes[0])] = np.asarray(escapes[1], dtype=np.float32)
+    return data
+
+
+def rebuild_tfidf(indptr, indices, data, idf, row_norm):
+    """TF-IDF values from the two vectors they are a function of, with the kernel's own arithmetic (k_tfidf: one float32
+    multiply, the float32 product divided by the row norm in double and rounded once; rows with norm 0 untouched) --
+    bit-identical to pc_tfidf_get, from 4 * n_selected + 8 * n_rows bytes instead of 4 * nnz over PCIe."""
+    indptr = np.asarray(indptr); indices = np.asarray(indices)
+    x = np.asarray(data, dtype=np.float32) * np.asarray(idf, dtype=np.float32)[indices]          # float32 product
+    nrm = np.repeat(np.asarray(row_norm, dtype=np.float64), np.diff(indptr))
+    out = x.copy()
+    nz = nrm > 0
+    out[nz] = (x[nz].astype(np.float64) / nrm[nz]).astype(np.float32)
+    return out
+
+
 class HotPathResult:
-    layout: ChunkLayout
-    k: int
-    scaffolds: list            # row labels (scaffolds.p)
-    kmer_keys: np.ndarray      # uint64, ascending == sorted k-mer strings (kmers.p)
-    indptr: object             # CSR of raw counts (numpy, or torch CUDA tensors when device_out)
-    indices: object
-    data: object
-    tfidf: object              # TF-IDF values in CSR order (or None)
-    df: object = None
-    stats: dict = field(default_factory=dict)
-    timings: dict = field(default_factory=dict)
+    """Result of one pass.  The matrix values can arrive compact (data16 + escapes, idf + row_norm: 6 bytes per entry over
+    PCIe instead of 12); `data` and `tfidf` then rebuild the float32 arrays on first use, bit-identical to the full
+    hand-off.  Views into a StepPipeline arena are valid until the pipeline's next step() -- copy what must live longer."""
+
+    def __init__(self, layout, k, scaffolds, kmer_keys, indptr, indices, data, tfidf, df=None, stats=None, timings=None,
+                 data16=None, escapes=None, idf=None, row_norm=None):
+        self.layout, self.k, self.scaffolds, self.kmer_keys = layout, k, scaffolds, kmer_keys
+        self.indptr, self.indices = indptr, indices           # CSR of raw counts (numpy, or torch CUDA tensors)
+        self._data, self._tfidf = data, tfidf
+        self.df = df
+        self.stats = {} if stats is None else stats
+        self.timings = {} if timings is None else timings
+        self.data16, self.escapes, self.idf, self.row_norm = data16, escapes, idf, row_norm
+
+    @property
+    def data(self):
+        if self._data is None and self.data16 is not None:
+            self._data = rebuild_counts(self.data16, self.escapes)
+        return self._data
+
+    @property
+    def tfidf(self):
+        if self._tfidf is None and self.idf is not None and self.row_norm is not None and self.indptr is not None:
+            self._tfidf = rebuild_tfidf(self.indptr, self.indices, self.data, self.idf, self.row_norm)
+        return self._tfidf
 
     @property
     def shape(self):
@@ -137,7 +170,7 @@ def dump_floor(k):
 def run_hot_path(ctx, seq, seq_offsets, names, chunk_size=75000, k=23, kmer_low_count=100, high_bool=0,
                  kmer_high_count=2000000, sampling_sensitivity=1, remove_non_chunk=1, min_chunk_threshold=0,
                  min_chunk_size=0, prefilter=0, tfidf=True, table_capacity=0, fetch=True, layout=None, arena=None,
-                 fuse_select=False, low_memory=False):
+                 fuse_select=False, low_memory=False, compact=True):
     """One pass of the hot path on one GPU.  fuse_select: record threshold crossings during the count instead of
     re-scanning the table (pc_watch_threshold); measured slower on B200 (returning atomics cost more than the scan).
 
@@ -170,33 +203,50 @@ def run_hot_path(ctx, seq, seq_offsets, names, chunk_size=75000, k=23, kmer_low_
     if not fetch:
         return HotPathResult(layout, k, scaffolds, np.empty(0, np.uint64), None, None, None, None, None, stats,
                              ctx.timings())
-    return fetch_result(ctx, layout, k, scaffolds, n_sel, nnz, tfidf, stats, arena)
+    return fetch_result(ctx, layout, k, scaffolds, n_sel, nnz, tfidf, stats, arena, compact=compact)
 
 
-def fetch_result(ctx, layout, k, scaffolds, n_sel, nnz, tfidf, stats, arena=None, df=None):
-    """D2H of the repeat set, CSR and TF-IDF values (into page-locked buffers when an arena is given)."""
+def fetch_result(ctx, layout, k, scaffolds, n_sel, nnz, tfidf, stats, arena=None, df=None, compact=True):
+    """D2H of the repeat set and the matrix (into page-locked buffers when an arena is given).  compact (default): counts
+    as uint16 + escapes, and idf + row norms instead of the tf-idf array -- 6 bytes per entry instead of 12; the float32
+    arrays are rebuilt on the host on first use (HotPathResult.data / .tfidf), bit-identical.  compact=False reads the
+    float32 arrays themselves (pc_csr_get / pc_tfidf_get)."""
     n_rows = len(scaffolds)
-    if arena is None:
+    compact = compact and hasattr(ctx, "csr16_into")         # (test stand-ins of the context only know the plain getters)
+    if not hasattr(ctx, "csr_into"):
         keys = ctx.selected(n_sel)
         indptr, indices, data = ctx.csr(n_rows, nnz)
-        tf = ctx.tfidf_values(nnz) if tfidf else None
-        if df is None:
-            df = ctx.df(n_sel)
-    else:
-        keys = arena.get("keys", n_sel, np.uint64)
-        indptr = arena.get("indptr", n_rows + 1, np.int64)
-        indices = arena.get("indices", nnz, np.int32)
-        data = arena.get("data", nnz, np.float32)
+        return HotPathResult(layout, k, scaffolds, keys, indptr, indices, data, ctx.tfidf_values(nnz) if tfidf else None,
+                             ctx.df(n_sel) if df is None and hasattr(ctx, "df") else df, stats, ctx.timings())
+
+    def buf(name, n, dtype):
+        return np.empty(n, dtype) if arena is None else arena.get(name, n, dtype)
+
+    keys = buf("keys", n_sel, np.uint64)
+    indptr = buf("indptr", n_rows + 1, np.int64)
+    indices = buf("indices", nnz, np.int32)
+    if n_sel:
+        ctx.selected_into(keys)
+    if df is None:
+        df = buf("df", n_sel, np.int32)
         if n_sel:
-            ctx.selected_into(keys)
+            ctx.df_into(df)
+    if not compact:
+        data = buf("data", nnz, np.float32)
         ctx.csr_into(indptr, indices if nnz else None, data if nnz else None)
         tf = None
         if tfidf:
-            tf = arena.get("tfidf", nnz, np.float32)
+            tf = buf("tfidf", nnz, np.float32)
             if nnz:
                 ctx.tfidf_into(tf)
-        if df is None:
-            df = arena.get("df", n_sel, np.int32)
-            if n_sel:
-                ctx.df_into(df)
-    return HotPathResult(layout, k, scaffolds, keys, indptr, indices, data, tf, df, stats, ctx.timings())
+        return HotPathResult(layout, k, scaffolds, keys, indptr, indices, data, tf, df, stats, ctx.timings())
+    data16 = buf("data16", nnz, np.uint16)
+    n_esc = ctx.csr16_into(indptr, indices if nnz else None, data16 if nnz else None)
+    escapes = ctx.csr_escapes(n_esc) if n_esc else None
+    idf = row_norm = None
+    if tfidf:
+        idf = buf("idf", n_sel, np.float32)
+        row_norm = buf("row_norm", n_rows, np.float64)
+        ctx.tfidf_factors_into(idf if n_sel else None, row_norm if n_rows else None)
+    return HotPathResult(layout, k, scaffolds, keys, indptr, indices, None, None, df, stats, ctx.timings(),
+                         data16=data16, escapes=escapes, idf=idf, row_norm=row_norm)

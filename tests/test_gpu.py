@@ -407,6 +407,28 @@ def test_probe_filters(ctx):
         ctx.tune(part_mode=-1, probe_filter=-1, probe_fp=-1, probe_mode=-1, filter_bits=1310720)
 
 
+def test_compact_handoff_matches_full_arrays(ctx):
+    """What crosses PCIe in the end-to-end path (pc_csr_get16 + escapes, pc_tfidf_factors_get: 6 bytes per entry) rebuilds
+    on the host to exactly the float32 arrays of pc_csr_get / pc_tfidf_get (12 bytes per entry) -- bit for bit, including a
+    count >= 65535 (a poly-A chunk of 70 000 windows) that does not fit uint16 and an all-N row with norm 0."""
+    p = synth.small_params(seed=77, genome_size=600_000)
+    seq, off, names = synth.generate(p)
+    seqs = util.to_sequences(seq, off, names) + [("polyA", "A" * 70000), ("allN", "N" * 70000), ("at", "AT" * 35000)]
+    seq, off, names = util.from_sequences(seqs)
+    for k, chunk in ((23, 70000), (31, 20000)):
+        full = run_hot_path(ctx, seq, off, names, chunk_size=chunk, k=k, kmer_low_count=5, remove_non_chunk=0, compact=False)
+        comp = run_hot_path(ctx, seq, off, names, chunk_size=chunk, k=k, kmer_low_count=5, remove_non_chunk=0, compact=True)
+        assert comp.data16 is not None and comp.data16.dtype == np.uint16 and full.data16 is None
+        assert np.array_equal(comp.indptr, full.indptr) and np.array_equal(comp.indices, full.indices)
+        assert np.array_equal(comp.kmer_keys, full.kmer_keys) and np.array_equal(comp.df, full.df)
+        assert comp.data.dtype == np.float32 and np.array_equal(comp.data, full.data)
+        assert comp.tfidf.dtype == np.float32 and np.array_equal(comp.tfidf.view(np.uint32), full.tfidf.view(np.uint32))
+        if chunk == 70000:
+            assert comp.escapes is not None and len(comp.escapes[0]) >= 1 and full.data.max() >= 65535
+            assert (np.asarray(comp.data16) == 65535).sum() == len(comp.escapes[0])
+        assert (comp.row_norm == 0).any()                              # the all-N chunks: empty rows stay zero
+
+
 def test_n2_diagnostics(ctx):
     """Scope row N2: the data of kcount_hist (Counter over the dumped counts) and of number_repeatmers_per_subsequence
     (k-mer names per merged-bed line), from the table count, the list count and against the literal oracle."""
