@@ -130,13 +130,13 @@ int pc_sub_hist_set(pc_ctx* ctx, int nb2, const uint64_t* hist_dev, int64_t n);
  *   bucket, [2] = minimizer length m, [3] = W = k - m + 1, [4] = k-mers per record at most, [5] = 1 when usable for this k.
  * pc_skm_partition: K1 must have run.  bucket_off[2^pb + 1] (host) = level-1 bucket offsets in RECORDS into *recs_dev
  *   (device, 16 bytes per record); *hist_dev (device, uint64[2^pb * nb2]) = (k-mers << 32) | records of every sub-bucket.
- * pc_skm_export: pins the record buffer at >= n_records and returns its CUDA IPC handle (peers open it with
- *   pc_peer_open).  pc_skm_count_from: counts n_buckets buckets given as record segments (seg_base[i * n_seg + s] device
+ * pc_skm_export: after pc_load_sequences; sizes the record buffer for the loaded chunks (it only ever grows, so the handle
+ *   stays valid from step to step) and returns its CUDA IPC handle (peers open it with pc_peer_open).  pc_skm_count_from: counts n_buckets buckets given as record segments (seg_base[i * n_seg + s] device
  *   pointers, or all relative to recs_dev when seg_base is NULL; begin / length in records) with hist_dev = the packed
  *   histogram of exactly these buckets summed over the senders (device, uint64[n_buckets * nb2]). */
 int pc_skm_plan(pc_ctx* ctx, int k, int64_t windows_global, int world, int32_t plan[8]);
 int pc_skm_partition(pc_ctx* ctx, int k, const int32_t plan[8], int64_t* bucket_off, uint64_t** recs_dev, uint64_t** hist_dev);
-int pc_skm_export(pc_ctx* ctx, int64_t n_records, void* ipc_handle_64);
+int pc_skm_export(pc_ctx* ctx, int k, const int32_t plan[8], void* ipc_handle_64);
 int pc_skm_count_from(pc_ctx* ctx, int k, const int32_t plan[8], int n_buckets, const uint64_t* recs_dev,
                       const uint64_t* const* seg_base, const int64_t* seg_begin, const int64_t* seg_len, int n_seg,
                       const uint64_t* hist_dev);
@@ -148,6 +148,13 @@ int pc_export_by_owner(pc_ctx* ctx, int world, uint64_t* keys_dev, uint32_t* cou
                        int64_t* offsets);
 int pc_merge_counts(pc_ctx* ctx, const uint64_t* keys_dev, const uint32_t* counts_dev, int64_t n,
                     int k, int64_t capacity, int fresh);
+
+/* ---- N4  externally counted k-mers (scope row N4, second half; polycracker/format.py:123-133 hipmer_output_to_kcount and
+ * any other .kcount the reference's kmer2Fasta would read, polycracker.py:220-238).  The (k-mer, count) pairs of such a file
+ * become the count result of the context, exactly as if pc_count had produced them, so pc_select / pc_dump_counts /
+ * pc_count_histogram and everything after them (K4..K7) run unchanged on k-mers the GPU never counted.  Keys are
+ * strand-collapsed on entry; a k-mer named twice (or by both strands) and an entry that is no k-mer are refused. */
+int pc_load_counts(pc_ctx* ctx, const uint64_t* keys, const uint32_t* counts, int64_t n, int k, int loc);
 
 /* ---- K4  repeat-k-mer selection (replaces kmer2Fasta, polycracker.py:220-238) ------------------------------
  * keep count >= low (and <= high when use_high); sort ascending; keep every `sampling`-th survivor

@@ -67,6 +67,7 @@ _SIGS = {
     "pc_packed_get": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int]),
     "pc_count": (C.c_int, [_vp, C.c_int, _i64]),
     "pc_count_info": (C.c_int, [_vp, _vp]),
+    "pc_load_counts": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, C.c_int]),
     "pc_count_detail": (C.c_int, [_vp, _vp]),
     "pc_copy_async": (C.c_int, [_vp, _vp, _vp, _i64, _vp, C.c_int]),
     "pc_read_back": (C.c_int, [_vp, _vp, _vp, _i64]),
@@ -86,7 +87,7 @@ _SIGS = {
     "pc_count_buckets_from": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _i64]),
     "pc_skm_plan": (C.c_int, [_vp, C.c_int, _i64, C.c_int, _vp]),
     "pc_skm_partition": (C.c_int, [_vp, C.c_int, _vp, _vp, _P(_vp), _P(_vp)]),
-    "pc_skm_export": (C.c_int, [_vp, _i64, _vp]),
+    "pc_skm_export": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "pc_skm_count_from": (C.c_int, [_vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp]),
     "pc_host_skm_plan": (C.c_int, [C.c_int, _i64, _P(_i32)]),
     "pc_host_skm_records": (C.c_int, [_vp, _vp, _i64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _i64, _P(_i64)]),
@@ -378,6 +379,15 @@ class Context:
     def count(self, k, capacity=0):
         check(lib.pc_count(self._h, int(k), int(capacity)), "pc_count")
 
+    def load_counts(self, keys, counts, k):
+        """Install externally counted k-mers (uint64 keys, uint32 counts; numpy or torch) as the count result."""
+        pk, loc = ptr(keys)
+        pc_, loc2 = ptr(counts)
+        if loc != loc2:
+            raise ValueError("keys and counts must live in the same place")
+        n = int(keys.numel() if _is_torch(keys) else len(keys))
+        check(lib.pc_load_counts(self._h, pk if n else None, pc_ if n else None, n, int(k), loc), "pc_load_counts")
+
     def count_info(self):
         info = np.zeros(8, np.int64)
         check(lib.pc_count_info(self._h, info.ctypes.data), "pc_count_info")
@@ -561,10 +571,15 @@ class Context:
               "pc_skm_partition")
         return off, recs.value, hist.value
 
-    def skm_export(self, n_records):
+    def skm_export(self, k, plan):
+        """-> 64-byte CUDA IPC handle of the record buffer, sized for the loaded chunks"""
+        plan = np.ascontiguousarray(plan, dtype=np.int32)
         h = np.zeros(64, np.uint8)
-        check(lib.pc_skm_export(self._h, int(n_records), h.ctypes.data), "pc_skm_export")
+        check(lib.pc_skm_export(self._h, int(k), plan.ctypes.data, h.ctypes.data), "pc_skm_export")
         return h
+
+    def peer_close(self, dev_ptr):
+        check(lib.pc_peer_close(self._h, _vp(int(dev_ptr))), "pc_peer_close")
 
     def skm_count_from(self, k, plan, seg_base, seg_begin, seg_len, hist, recs=None):
         """seg_base: uint64[n_buckets, n_seg] device pointers of the senders' record buffers (None: all segments are

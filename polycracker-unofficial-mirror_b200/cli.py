@@ -170,6 +170,15 @@ def kcount_hist(kcount_directory, out_file, log, kcount_range, low_count, kmer_l
          low_count=low_count, kmer_lengths=kmer_lengths, sample_speed=sample_speed)
 
 
+@polycracker.command(name="hipmer_output_to_kcount")
+@click.option("-i", "--hipmer_input", default="test.txt", help="Input file or directory from hipmer kmer counting run.", show_default=True, type=click.Path(exists=False))
+@click.option("-o", "--kcount_output", default="test.final.kcount", help="Output kmer count file.", show_default=True, type=click.Path(exists=False))
+@click.option("-d", "--run_on_dir", is_flag=True, help="Choose to run on all files in hipmer_input if you have specified a directory for the hipmer input. Directory can only contain hipmer files.")
+def hipmer_output_to_kcount(hipmer_input, kcount_output, run_on_dir):
+    """Converts hipmer kmer count output into a kmer count, kcount, file (polycracker/format.py:123-133)."""
+    _run(stages.hipmer_output_to_kcount, hipmer_input=hipmer_input, kcount_output=kcount_output, run_on_dir=run_on_dir)
+
+
 def main():
     polycracker()
 

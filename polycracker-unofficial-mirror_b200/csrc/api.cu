@@ -971,6 +971,14 @@ static int launch_count_skm(pc_ctx* c, const pc::SkmRec* recs, const unsigned lo
 }
 }  // extern "C++"
 
+static int64_t skm_record_cap(const pc_ctx* c, int k, const SkmPlan& pl, int64_t windows) {
+    (void)k;
+    const double per_window = std::min(1.0, 2.0 / (pl.W + 1) * 1.3 + 1.0 / 32.0 + 1.0 / pl.nmax);
+    int64_t cap = (int64_t)((double)windows * per_window) + c->n_words + 65536;
+    cap = std::min<int64_t>(cap, windows + 1024);
+    return std::max<int64_t>(cap, c->skm_cap_records);           // never shrink (the level-1 buffer may be exported to peers)
+}
+
 // extraction + level-1 scatter of the local chunks.  Leaves the bucket-sorted records in rec_b, the raw packed
 // histogram ((k-mers << 32) | records per sub-bucket, P * nb2 entries) in d_skm_hist and the level-1 bucket offsets (in
 // records) in h_bucket_off.  d_stats must have been reset by the caller.
@@ -983,10 +991,7 @@ static int do_skm_partition(pc_ctx* c, int k, const SkmPlan& pl) {
     // records: one per minimizer change (~2 / (W + 1) per window in random sequence), one per word boundary inside a
     // run, one per nmax windows of a long run; 30 % head-room.  A genome that needs more (adversarial minimizer order)
     // is reported and the caller falls back to the k-mer path.
-    const double per_window = std::min(1.0, 2.0 / (pl.W + 1) * 1.3 + 1.0 / 32.0 + 1.0 / pl.nmax);
-    int64_t cap = (int64_t)((double)windows * per_window) + c->n_words + 65536;
-    cap = std::min<int64_t>(cap, windows + 1024);
-    cap = std::max<int64_t>(cap, c->skm_cap_records);             // never shrink (the level-1 buffer may be exported to peers)
+    const int64_t cap = skm_record_cap(c, k, pl, windows);
     rc = c->rec_a.alloc((size_t)cap); if (rc) return rc;
     rc = c->rec_b.alloc((size_t)cap); if (rc) return rc;
     c->skm_cap_records = cap;
@@ -1477,7 +1482,7 @@ int pc_sub_hist_set(pc_ctx* c, int nb2, const uint64_t* hist_dev, int64_t n) {
 int pc_skm_plan(pc_ctx* c, int k, int64_t windows_global, int world, int32_t plan[8]) {
     if (!c || !plan || k < 1 || k > 32 || windows_global < 0 || world < 1) return fail(PC_EINVAL, "bad pc_skm_plan arguments");
     SkmPlan pl = skm_plan(c, k, windows_global, world);
-    if (!smem_mode(c) || c->part_mode == 2) pl.ok = false;
+    if (!(c->part_mode == 3 || (c->part_mode < 0 && k >= c->skm_min_k))) pl.ok = false;      // the rule of pc_count
     skm_plan_store(pl, plan);
     return PC_OK;
 }
@@ -1496,12 +1501,17 @@ int pc_skm_partition(pc_ctx* c, int k, const int32_t plan[8], int64_t* bucket_of
     return PC_OK;
 }
 
-int pc_skm_export(pc_ctx* c, int64_t n_records, void* ipc_handle) {
+int pc_skm_export(pc_ctx* c, int k, const int32_t plan[8], void* ipc_handle) {
     int rc = use_device(c); if (rc) return rc;
-    if (n_records < 1 || !ipc_handle) return fail(PC_EINVAL, "bad pc_skm_export arguments");
-    rc = c->rec_b.alloc((size_t)n_records); if (rc) return rc;       // kept (and re-used by pc_skm_partition) while it is big enough
-    rc = c->rec_a.alloc((size_t)n_records); if (rc) return rc;
-    c->skm_cap_records = std::max<int64_t>(c->skm_cap_records, n_records);
+    if (!c->loaded) return fail(PC_ESTATE, "pc_skm_export before pc_load_sequences");
+    if (!ipc_handle) return fail(PC_EINVAL, "bad pc_skm_export arguments");
+    SkmPlan pl; rc = skm_plan_load(plan, k, &pl); if (rc) return rc;
+    int64_t windows = 0;
+    for (int64_t i = 0; i < c->n_chunks; ++i) windows += std::max<int64_t>(0, c->h_len[i] - k + 1);
+    const int64_t cap = skm_record_cap(c, k, pl, windows);       // what pc_skm_partition will need: kept while it is big enough
+    rc = c->rec_b.alloc((size_t)cap); if (rc) return rc;
+    rc = c->rec_a.alloc((size_t)cap); if (rc) return rc;
+    c->skm_cap_records = cap;
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, c->rec_b.p));
     memcpy(ipc_handle, &h, sizeof h);
@@ -1522,6 +1532,43 @@ int pc_skm_count_from(pc_ctx* c, int k, const int32_t plan[8], int n_buckets, co
     SYNC(c);
     return count_buckets_skm(c, k, pl, n_buckets, reinterpret_cast<const pc::SkmRec*>(recs_dev), seg_begin, seg_len, n_seg,
                              reinterpret_cast<const pc::SkmRec* const*>(seg_base), reinterpret_cast<const unsigned long long*>(hist_dev));
+}
+
+// ---- N4: externally counted k-mers (a .kcount from HipMer / jellyfish / kmercountexact, format.py:123-133) become the
+// count result, so that K4..K7 run on them unchanged
+int pc_load_counts(pc_ctx* c, const uint64_t* keys, const uint32_t* counts, int64_t n, int k, int loc) {
+    int rc = use_device(c); if (rc) return rc;
+    if (k < 1 || k > 32) return fail(PC_EINVAL, "k = %d unsupported: this path handles 1 <= k <= 32 (uint64 k-mers)", k);
+    if (n < 0 || (n > 0 && (!keys || !counts))) return fail(PC_EINVAL, "bad pc_load_counts arguments");
+    c->counted = c->selected = c->built = c->tfidf_done = false;
+    c->skm_used = false; c->cross_valid = false;
+    rc = c->list_keys.alloc((size_t)std::max<int64_t>(n, 1)); if (rc) return rc;
+    rc = c->list_counts.alloc((size_t)std::max<int64_t>(n, 1)); if (rc) return rc;
+    rc = c->sel_a.alloc(std::max<int64_t>(n, 1)); if (rc) return rc;
+    rc = c->sel_b.alloc(std::max<int64_t>(n, 1)); if (rc) return rc;
+    const cudaMemcpyKind kind = loc == PC_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    unsigned long long bad[2] = {0, 0};
+    if (n > 0) {
+        CU(cudaMemcpyAsync(c->list_keys.p, keys, (size_t)n * sizeof(uint64_t), kind, c->stream));
+        CU(cudaMemcpyAsync(c->list_counts.p, counts, (size_t)n * sizeof(uint32_t), kind, c->stream));
+        LAUNCH(c, pc::k_canonicalize, blocks_for(n, 256), 256, c->list_keys.p, n, k);
+        // every k-mer once: a list that names a k-mer twice (or both of its strands) would double its matrix column
+        CU(cudaMemcpyAsync(c->sel_a.p, c->list_keys.p, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToDevice, c->stream));
+        uint64_t* sorted = nullptr;
+        rc = radix_sort_u64(c, c->sel_a.p, c->sel_b.p, n, 2 * k, &sorted); if (rc) return rc;
+        CU(cudaMemsetAsync(c->d_counter.p, 0, 2 * sizeof(unsigned long long), c->stream));
+        LAUNCH(c, pc::k_count_dups, blocks_for(n, 256), 256, sorted, n, c->d_counter.p);
+        LAUNCH(c, pc::k_count_sentinel, blocks_for(n, 256), 256, c->list_keys.p, n, c->d_counter.p + 1);
+        READ_SMALL(c, bad, c->d_counter.p, sizeof bad);
+    }
+    SYNC(c);
+    if (bad[1]) return fail(PC_EINVAL, "%llu entries are not k-mers of length %d (N or other letters)", bad[1], k);
+    if (bad[0]) return fail(PC_EINVAL, "%llu k-mers are listed more than once after strand collapse: merge their counts first", bad[0]);
+    c->k = k; c->n_list = n; c->list_min = 1; c->keep_min = 1;
+    c->h_stats = pc::CountStats{}; c->h_stats.distinct = (unsigned long long)n;
+    c->capacity = (uint64_t)std::max<int64_t>(n, 1); c->pb = 0; c->n_sub = 0; c->sub_nb2 = 0; c->n_ovf = 0;
+    c->counted = true; c->count_kind = 1;
+    return PC_OK;
 }
 
 int pc_count_info(pc_ctx* c, int64_t info[8]) {

@@ -125,6 +125,28 @@ def plan_partition_bits(windows_global, world, part_bytes=64 << 20, table_load=0
     return pb
 
 
+def owner_ranges(P, world):
+    """rank r owns the level-1 buckets [q_lo[r], q_lo[r + 1])"""
+    return [(r * P + world - 1) // world for r in range(world + 1)]
+
+
+def owner_segments(sizes_all, q_lo, rank):
+    """sizes_all[sender, bucket] = units (k-mers or records) every sender holds per bucket, bucket-sorted in its buffer.
+    -> (seg_begin, seg_len), both [my bucket, sender]: where the owner `rank` finds each sender's slice of its buckets
+    inside that sender's buffer."""
+    sizes_all = np.asarray(sizes_all, dtype=np.int64)
+    sender_off = np.cumsum(sizes_all, axis=1) - sizes_all
+    lo, hi = q_lo[rank], q_lo[rank + 1]
+    return sender_off[:, lo:hi].T.copy(), sizes_all[:, lo:hi].T.copy()
+
+
+def bind_context_stream(ctx, torch, device):
+    """The context must compute on torch's current stream: its small read-backs (Context.to_host) are ordered on the context
+    stream, so only then do they wait for the collective that produced their input.  Idempotent."""
+    if getattr(device, "type", "cpu") == "cuda" and hasattr(ctx, "set_stream"):
+        ctx.set_stream(torch.cuda.current_stream(device).cuda_stream)
+
+
 class _DevView:
     def __init__(self, ptr, n):
         self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<i8", "data": (int(ptr), False), "version": 2}
@@ -137,18 +159,19 @@ def device_view(torch, ptr, n, device):
     return torch.as_tensor(_DevView(ptr, n), device=device)
 
 
-def peer_pointers(ctx, torch, dist, device, kbuf_keys, own_ptr):
-    """Device pointers of every rank's bucket buffer in THIS process (own buffer: own pointer).  The 64-byte CUDA IPC
+def peer_pointers(ctx, torch, dist, device, handle, own_ptr, cache_name="_pc_peers"):
+    """Device pointers of every rank's exported buffer in THIS process (own buffer: own pointer).  The 64-byte CUDA IPC
     handles are all-gathered every step (a 64-byte collective) and a peer buffer is (re)opened only when its handle
-    changed, i.e. when that rank had to grow its buffer."""
+    changed, i.e. when that rank had to grow its buffer; the mapping it replaces is closed."""
     world, rank = dist.get_world_size(), dist.get_rank()
-    mine = torch.from_numpy(ctx._pc_handle.copy()).to(device)
+    mine = torch.from_numpy(np.ascontiguousarray(handle).copy()).to(device)
     allh = [torch.empty(64, dtype=torch.uint8, device=device) for _ in range(world)]
     dist.all_gather(allh, mine)
     handles = [h.tobytes() for h in _to_host(ctx, torch.stack(allh), torch, device)]
-    cache = getattr(ctx, "_pc_peers", None)
+    cache = getattr(ctx, cache_name, None)
     if cache is None:
-        cache = ctx._pc_peers = {}
+        cache = {}
+        setattr(ctx, cache_name, cache)
     ptrs = []
     for r in range(world):
         if r == rank:
@@ -156,6 +179,8 @@ def peer_pointers(ctx, torch, dist, device, kbuf_keys, own_ptr):
             continue
         ent = cache.get(r)
         if ent is None or ent[0] != handles[r]:
+            if ent is not None and hasattr(ctx, "peer_close"):
+                ctx.peer_close(ent[1])
             ent = cache[r] = (handles[r], ctx.peer_open(np.frombuffer(handles[r], dtype=np.uint8)))
         ptrs.append(ent[1])
     return ptrs
@@ -182,6 +207,7 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
     import torch
     import torch.distributed as dist
     world, rank = dist.get_world_size(), dist.get_rank()
+    bind_context_stream(ctx, torch, device)
     phase, t_last = {}, [time.perf_counter()]
 
     def mark(name):
@@ -213,76 +239,130 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
     if hasattr(ctx, "sub_plan"):
         per = ctx.sub_plan(1 << 40, 1 << 20)                 # sub-buckets per bucket for 2^20 k-mers per bucket ...
         smem_mean = (1 << 20) // per if per > 0 else 0        # ... = the mean sub-bucket size (0: table count in use)
-    pb = plan_partition_bits(windows_global, world, smem_mean=smem_mean)
+    # super-k-mer path (pc_tune part_mode 3 / auto for k >= 17): 16-byte records -- runs of windows that share a minimizer --
+    # travel instead of one 8-byte k-mer per window, so the owners read ~4x fewer bytes from their peers
+    skm = None
+    if hasattr(ctx, "skm_plan") and exchange != "kmers":
+        plan = ctx.skm_plan(k, windows_global, world)
+        if int(plan[5]) == 1:
+            skm = plan
+    pb = int(skm[0]) if skm is not None else plan_partition_bits(windows_global, world, smem_mean=smem_mean)
     P = 1 << pb
+    q_lo = owner_ranges(P, world)
     mark("host_plan")
     ctx.load_sequences(buf, begins, ends)
-    kbuf_keys = int((ends - begins).sum()) if len(ends) else 1            # >= local windows: pins the bucket buffer
-    if hasattr(ctx, "kbuf_export") and getattr(device, "type", "cpu") == "cuda" and exchange != "nccl":
-        ctx._pc_handle = ctx.kbuf_export(max(kbuf_keys, getattr(ctx, "_pc_kbuf_keys", 1)))
-        ctx._pc_kbuf_keys = max(kbuf_keys, getattr(ctx, "_pc_kbuf_keys", 1))
-    off, keys = ctx.partition(k, pb)
-    mark("pack+partition")
-    n_local = int(off[-1])
-    sizes = torch.from_numpy(np.diff(off).astype(np.int64)).to(device)
-    gathered = [torch.empty(P, dtype=torch.int64, device=device) for _ in range(world)]
-    dist.all_gather(gathered, sizes)
-    sizes_all = _to_host(ctx, torch.stack(gathered), torch, device)       # [sender, bucket]
-    q_lo = [(r * P + world - 1) // world for r in range(world + 1)]      # rank r owns buckets [q_lo[r], q_lo[r+1])
-    send_counts = [int(sizes_all[rank, q_lo[r]:q_lo[r + 1]].sum()) for r in range(world)]
-    recv_counts = [int(sizes_all[s, q_lo[rank]:q_lo[rank + 1]].sum()) for s in range(world)]
-    mine = sizes_all[:, q_lo[rank]:q_lo[rank + 1]]                        # [sender, my bucket]
+    on_gpu = getattr(device, "type", "cpu") == "cuda"
     if hasattr(ctx, "watch_threshold"):
         ctx.watch_threshold(0)
-    use_peer = exchange == "peer" or (exchange == "auto" and getattr(device, "type", "cpu") == "cuda"
-                                      and hasattr(ctx, "kbuf_export") and not torch.is_tensor(keys))
-    mark("bucket_sizes_allgather")
     if hasattr(ctx, "tune"):
         ctx.tune(keep_min=dump_floor(k))                                  # the owners keep what the reference's counter dumps
-    staged_hist = None
-    if use_peer and hasattr(ctx, "sub_plan"):
-        # shared-memory count: the owner needs the sizes of its sub-buckets before it scatters.  Every sender histograms
-        # its own bucket buffer (local HBM) and the small histograms travel, instead of the owner streaming every peer
-        # segment over NVLink a second time.  One fan-out for all ranks, from the all-gathered bucket sizes.
-        nb2 = max(ctx.sub_plan(int(sizes_all[:, q_lo[r]:q_lo[r + 1]].sum()), max(1, q_lo[r + 1] - q_lo[r]))
-                  for r in range(world))
-        if nb2 > 0 and all(q_lo[r + 1] > q_lo[r] for r in range(world)):
-            h_local = torch.empty(P * nb2, dtype=torch.int64, device=device)
-            ctx.sub_hist(pb, nb2, h_local)
-            n_mine = (q_lo[rank + 1] - q_lo[rank]) * nb2
-            h_recv = torch.empty(world * n_mine, dtype=torch.int64, device=device)
-            dist.all_to_all_single(h_recv, h_local, output_split_sizes=[n_mine] * world,
-                                   input_split_sizes=[(q_lo[r + 1] - q_lo[r]) * nb2 for r in range(world)])
-            staged_hist = h_recv.view(world, n_mine).sum(dim=0).contiguous()
+    if skm is not None:
+        nb2 = int(skm[1])
+        use_peer = exchange in ("peer", "auto") and on_gpu and hasattr(ctx, "skm_export")
+        handle = ctx.skm_export(k, skm) if use_peer else None
+        off, recs, hist = ctx.skm_partition(k, skm)
+        mark("pack+partition")
+        n_local_records = int(off[-1])
+        n_local = ctx.count_info_windows() if hasattr(ctx, "count_info_windows") else None
+        sizes = torch.from_numpy(np.diff(off).astype(np.int64)).to(device)
+        gathered = [torch.empty(P, dtype=torch.int64, device=device) for _ in range(world)]
+        dist.all_gather(gathered, sizes)
+        sizes_all = _to_host(ctx, torch.stack(gathered), torch, device)   # [sender, bucket], in records
+        mark("bucket_sizes_allgather")
+        # every sender's packed sub-bucket histogram ((k-mers << 32) | records) of MY buckets, summed: the owner's scatter
+        # offsets and the size of its k-mer list, without reading any record twice
+        h_local = hist if torch.is_tensor(hist) else device_view(torch, hist, P * nb2, device)
+        n_mine = (q_lo[rank + 1] - q_lo[rank]) * nb2
+        h_recv = torch.empty(world * n_mine, dtype=torch.int64, device=device)
+        dist.all_to_all_single(h_recv, h_local.contiguous(), output_split_sizes=[n_mine] * world,
+                               input_split_sizes=[(q_lo[r + 1] - q_lo[r]) * nb2 for r in range(world)])
+        staged_hist = h_recv.view(world, n_mine).sum(dim=0).contiguous()
+        _stream_sync(torch, device)
+        mark("sub_hist_exchange")
+        seg_begin, seg_len = owner_segments(sizes_all, q_lo, rank)
+        recv_records = int(seg_len.sum())
+        if use_peer:
+            peers = peer_pointers(ctx, torch, dist, device, handle, recs, cache_name="_pc_skm_peers")
+            mark("peer_handles")
+            seg_base = np.repeat(np.asarray(peers, dtype=np.uint64)[None, :], seg_len.shape[0], axis=0)
+            ctx.skm_count_from(k, skm, seg_base, seg_begin, seg_len, staged_hist)
+            exchanged = 16 * (recv_records - int(sizes_all[rank, q_lo[rank]:q_lo[rank + 1]].sum()))
+        else:
+            # all-to-all of the records themselves (two int64 per record), then count from the receive buffer
+            send = recs if torch.is_tensor(recs) else device_view(torch, recs, 2 * n_local_records, device)
+            send_counts = [2 * int(sizes_all[rank, q_lo[r]:q_lo[r + 1]].sum()) for r in range(world)]
+            recv_counts = [2 * int(sizes_all[s_, q_lo[rank]:q_lo[rank + 1]].sum()) for s_ in range(world)]
+            recv = torch.empty(int(sum(recv_counts)), dtype=torch.int64, device=device)
+            dist.all_to_all_single(recv, send[:2 * n_local_records], output_split_sizes=recv_counts, input_split_sizes=send_counts)
             _stream_sync(torch, device)
-            ctx.sub_hist_set(nb2, staged_hist)
-            mark("sub_hist_exchange")
-    if use_peer:
-        # 2a. fused exchange: the owner's count kernel reads every sender's slice straight out of that sender's bucket
-        # buffer over NVLink (CUDA IPC mapping).  The all-gather of the bucket sizes above is the barrier that says
-        # "every rank has finished its partition"; the repeat-set all-gather below says "every rank has finished
-        # reading", so the next step may overwrite the buffers.
-        peers = peer_pointers(ctx, torch, dist, device, kbuf_keys, keys)
-        mark("peer_handles")
-        sender_off = np.cumsum(sizes_all, axis=1) - sizes_all             # bucket offsets inside each sender's buffer
-        seg_begin = sender_off[:, q_lo[rank]:q_lo[rank + 1]].T.copy()     # [my bucket, sender]
-        seg_len = mine.T.copy()
-        seg_base = np.repeat(np.asarray(peers, dtype=np.uint64)[None, :], seg_len.shape[0], axis=0)
-        ctx.count_buckets_from(k, pb, seg_base, seg_begin, seg_len)
-        exchanged = 8 * (int(sum(recv_counts)) - recv_counts[rank])    # bytes read from peers' HBM over NVLink
+            mark("record_all_to_all")
+            mine = sizes_all[:, q_lo[rank]:q_lo[rank + 1]]
+            recv_off = np.concatenate([[0], np.cumsum(recv_counts)])[:-1] // 2
+            within = np.cumsum(mine, axis=1) - mine
+            ctx.skm_count_from(k, skm, None, (recv_off[:, None] + within).T.copy(), mine.T.copy(), staged_hist, recs=recv)
+            del recv
+            exchanged = 8 * (int(sum(send_counts)) - send_counts[rank])
+        n_local = int(ctx.count_info()["valid_windows"]) if n_local is None else n_local
     else:
-        # 2b. all-to-all of the raw k-mers over NVLink (NCCL); count at the owner
-        send = keys if torch.is_tensor(keys) else device_view(torch, keys, n_local, device)
-        recv = torch.empty(int(sum(recv_counts)), dtype=torch.int64, device=device)
-        dist.all_to_all_single(recv, send[:n_local], output_split_sizes=recv_counts, input_split_sizes=send_counts)
-        mark("kmer_all_to_all")
-        recv_off = np.concatenate([[0], np.cumsum(recv_counts)])[:-1]
-        within = np.cumsum(mine, axis=1) - mine                           # offset of bucket q inside sender s's slice
-        seg_begin = (recv_off[:, None] + within).T.copy()                 # [my bucket, sender]
-        seg_len = mine.T.copy()
-        ctx.count_buckets(k, pb, recv, seg_begin, seg_len)
-        del recv
-        exchanged = 8 * (n_local - send_counts[rank])
+        kbuf_keys = int((ends - begins).sum()) if len(ends) else 1        # >= local windows: pins the bucket buffer
+        if hasattr(ctx, "kbuf_export") and on_gpu and exchange != "nccl":
+            ctx._pc_handle = ctx.kbuf_export(max(kbuf_keys, getattr(ctx, "_pc_kbuf_keys", 1)))
+            ctx._pc_kbuf_keys = max(kbuf_keys, getattr(ctx, "_pc_kbuf_keys", 1))
+        off, keys = ctx.partition(k, pb)
+        mark("pack+partition")
+        n_local = int(off[-1])
+        sizes = torch.from_numpy(np.diff(off).astype(np.int64)).to(device)
+        gathered = [torch.empty(P, dtype=torch.int64, device=device) for _ in range(world)]
+        dist.all_gather(gathered, sizes)
+        sizes_all = _to_host(ctx, torch.stack(gathered), torch, device)   # [sender, bucket]
+        send_counts = [int(sizes_all[rank, q_lo[r]:q_lo[r + 1]].sum()) for r in range(world)]
+        recv_counts = [int(sizes_all[s_, q_lo[rank]:q_lo[rank + 1]].sum()) for s_ in range(world)]
+        mine = sizes_all[:, q_lo[rank]:q_lo[rank + 1]]                    # [sender, my bucket]
+        use_peer = exchange in ("peer", "kmers") and on_gpu or (exchange == "auto" and on_gpu
+                                                                 and hasattr(ctx, "kbuf_export") and not torch.is_tensor(keys))
+        mark("bucket_sizes_allgather")
+        staged_hist = None
+        if use_peer and hasattr(ctx, "sub_plan"):
+            # shared-memory count: the owner needs the sizes of its sub-buckets before it scatters.  Every sender histograms
+            # its own bucket buffer (local HBM) and the small histograms travel, instead of the owner streaming every peer
+            # segment over NVLink a second time.  One fan-out for all ranks, from the all-gathered bucket sizes.
+            nb2 = max(ctx.sub_plan(int(sizes_all[:, q_lo[r]:q_lo[r + 1]].sum()), max(1, q_lo[r + 1] - q_lo[r]))
+                      for r in range(world))
+            if nb2 > 0 and all(q_lo[r + 1] > q_lo[r] for r in range(world)):
+                h_local = torch.empty(P * nb2, dtype=torch.int64, device=device)
+                ctx.sub_hist(pb, nb2, h_local)
+                n_mine = (q_lo[rank + 1] - q_lo[rank]) * nb2
+                h_recv = torch.empty(world * n_mine, dtype=torch.int64, device=device)
+                dist.all_to_all_single(h_recv, h_local, output_split_sizes=[n_mine] * world,
+                                       input_split_sizes=[(q_lo[r + 1] - q_lo[r]) * nb2 for r in range(world)])
+                staged_hist = h_recv.view(world, n_mine).sum(dim=0).contiguous()
+                _stream_sync(torch, device)
+                ctx.sub_hist_set(nb2, staged_hist)
+                mark("sub_hist_exchange")
+        if use_peer:
+            # 2a. fused exchange: the owner's count kernel reads every sender's slice straight out of that sender's bucket
+            # buffer over NVLink (CUDA IPC mapping).  The all-gather of the bucket sizes above is the barrier that says
+            # "every rank has finished its partition"; the repeat-set all-gather below says "every rank has finished
+            # reading", so the next step may overwrite the buffers.
+            peers = peer_pointers(ctx, torch, dist, device, ctx._pc_handle, keys)
+            mark("peer_handles")
+            seg_begin, seg_len = owner_segments(sizes_all, q_lo, rank)
+            seg_base = np.repeat(np.asarray(peers, dtype=np.uint64)[None, :], seg_len.shape[0], axis=0)
+            ctx.count_buckets_from(k, pb, seg_base, seg_begin, seg_len)
+            exchanged = 8 * (int(sum(recv_counts)) - recv_counts[rank])    # bytes read from peers' HBM over NVLink
+        else:
+            # 2b. all-to-all of the raw k-mers over NVLink (NCCL); count at the owner
+            send = keys if torch.is_tensor(keys) else device_view(torch, keys, n_local, device)
+            recv = torch.empty(int(sum(recv_counts)), dtype=torch.int64, device=device)
+            dist.all_to_all_single(recv, send[:n_local], output_split_sizes=recv_counts, input_split_sizes=send_counts)
+            mark("kmer_all_to_all")
+            recv_off = np.concatenate([[0], np.cumsum(recv_counts)])[:-1]
+            within = np.cumsum(mine, axis=1) - mine                           # offset of bucket q inside sender s's slice
+            seg_begin = (recv_off[:, None] + within).T.copy()                 # [my bucket, sender]
+            seg_len = mine.T.copy()
+            ctx.count_buckets(k, pb, recv, seg_begin, seg_len)
+            del recv
+            exchanged = 8 * (n_local - send_counts[rank])
     if hasattr(ctx, "tune"):
         ctx.tune(keep_min=1)
     owner_info = ctx.count_info()
@@ -324,7 +404,8 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
     stats.update(n_selected=n_sel, nnz=nnz, n_rows=n_local_rows, n_rows_global=len(scaffolds_all), row0=row0,
                  valid_windows_global=int(t[0]), distinct_global=int(t[1]), nnz_global=int(t[2]),
                  owner_distinct=owner_info["distinct"], local_bases=int(ends[-1]) if len(ends) else 0,
-                 phase_ms={k_: round(v, 2) for k_, v in phase.items()}, exchange_bytes_sent=exchanged, exchange="peer" if use_peer else "nccl_all_to_all")
+                 phase_ms={k_: round(v, 2) for k_, v in phase.items()}, exchange_bytes_sent=exchanged,
+                 exchange=("peer" if use_peer else "nccl_all_to_all") + ("/super-k-mers" if skm is not None else ""))
     scaffolds = scaffolds_all[row0:row0 + n_local_rows]
     if not fetch:
         return HotPathResult(layout, k, scaffolds, np.empty(0, np.uint64), None, None, None, None, None, stats,
@@ -339,6 +420,7 @@ def rerun_threshold(ctx, layout, ids, device, k=23, kmer_low_count=100, high_boo
     this context are kept; only K4 -> all-gather of the repeat set -> K5..K7 are repeated for the new threshold."""
     import torch
     import torch.distributed as dist
+    bind_context_stream(ctx, torch, device)
     scaffolds_all, chunk_row_all = layout.rows(remove_non_chunk, min_chunk_threshold, min_chunk_size, prefilter)
     my_rows_global = chunk_row_all[ids]
     kept = np.flatnonzero(my_rows_global >= 0)

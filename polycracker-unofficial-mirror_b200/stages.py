@@ -9,6 +9,7 @@ GPU produced).  `blast2bed` and `generate_Kmer_Matrix` use it when it sits next 
 the text artefacts otherwise (e.g. after Nextflow's collectFile concatenated several SAM files, polycracker.nf:286-290).
 """
 import os
+import re
 import pickle
 
 import numpy as np
@@ -236,6 +237,10 @@ def blast2bed(blast_file="./blast_files/results.sam", bb=1, low_memory=0, output
             csr = sps.csr_matrix((data, indices, indptr), shape=(len(names), len(keys)))[order]
             binding.write_hit_lines(output_merged_bed_file, "merged", csr.indptr, csr.indices, csr.data, keys, int(k),
                                     [names[i] for i in order], row_len[order])
+            # binary twin of the merged bed for generate_Kmer_Matrix (at Gbp scale the text is hundreds of GB of k-mer
+            # names; the stage that reads it back only needs (chunk, k-mer, multiplicity))
+            np.savez(output_merged_bed_file + ".pcb200.npz", k=np.array(int(k)), keys=keys, names=np.array([names[i] for i in order]),
+                     indptr=csr.indptr.astype(np.int64), indices=csr.indices.astype(np.int32), data=csr.data.astype(np.float32))
         else:
             per_chunk = {}
             with open(output_bed_file) as f:
@@ -310,6 +315,25 @@ def generate_Kmer_Matrix(kmercount_path="./kmercount_files/", genome=None, chunk
     scaffold_idx = {s: i for i, s in enumerate(scaffolds)}
     kmer_idx = {km: i for i, km in enumerate(kmers)}
     per_row = [[] for _ in scaffolds]
+    side = None if low_memory else _load_merged_sidecar(input_merged_bed_file, kmers)
+    if side is not None:
+        # blast2bed left the merged bed's content in binary form: no text parsing, no Python lists of names
+        col_of_key, names_s, indptr_s, indices_s, data_s = side
+        row_of_name = {n: i for i, n in enumerate(names_s)}
+        src = np.array([row_of_name.get(sc, -1) for sc in scaffolds], np.int64)
+        csr_s = sps.csr_matrix((data_s, indices_s, indptr_s), shape=(len(names_s), len(col_of_key)))
+        pick = csr_s[np.where(src >= 0, src, 0)]
+        lens_r = np.diff(pick.indptr) * (src >= 0)
+        mult = pick.data.astype(np.int64)
+        valid = np.repeat(src >= 0, np.diff(pick.indptr)) & (col_of_key[pick.indices] >= 0)
+        cols = np.repeat(col_of_key[pick.indices][valid], mult[valid]).astype(np.int32)
+        row_id = np.repeat(np.repeat(np.arange(len(scaffolds)), np.diff(pick.indptr))[valid], mult[valid])
+        del lens_r
+        row_offsets = np.zeros(len(scaffolds) + 1, np.int64)
+        np.cumsum(np.bincount(row_id, minlength=len(scaffolds)), out=row_offsets[1:])
+        order = np.argsort(row_id, kind="stable")
+        return _finish_matrix(scaffolds, original_scaffolds, kmers, row_offsets, cols[order], output_sparse_matrix,
+                              output_kmer_file, tfidf)
     if low_memory:
         with open(input_bed_file) as f:
             for line in f:
@@ -330,6 +354,29 @@ def generate_Kmer_Matrix(kmercount_path="./kmercount_files/", genome=None, chunk
     cols, row_of = cols[keep], row_of[keep]
     row_offsets = np.zeros(len(scaffolds) + 1, np.int64)
     np.cumsum(np.bincount(row_of, minlength=len(scaffolds)), out=row_offsets[1:])
+    return _finish_matrix(scaffolds, original_scaffolds, kmers, row_offsets, cols, output_sparse_matrix, output_kmer_file, tfidf)
+
+
+def _load_merged_sidecar(merged_bed, kmers):
+    """(column id of every side-car k-mer or -1, row names, CSR) when blast2bed left a binary twin next to the merged bed that
+    is at least as new as the text, and every column label has the side-car's k; else None (the text is parsed)."""
+    side = merged_bed + ".pcb200.npz"
+    if not (os.path.exists(side) and os.path.exists(merged_bed)) or os.path.getmtime(side) + 1 < os.path.getmtime(merged_bed):
+        return None
+    z = np.load(side)
+    k = int(z["k"])
+    if not kmers or {len(x) for x in kmers} != {k}:
+        return None
+    col_keys = binding.kmer_encode(kmers, k)                  # column j = kmers[j] (already string-sorted = key-sorted)
+    order = np.argsort(col_keys)
+    pos = np.searchsorted(col_keys[order], z["keys"])
+    pos[pos >= len(col_keys)] = 0
+    hit = col_keys[order][pos] == z["keys"]
+    return np.where(hit, order[pos], -1).astype(np.int64), z["names"].tolist(), z["indptr"], z["indices"], z["data"]
+
+
+def _finish_matrix(scaffolds, original_scaffolds, kmers, row_offsets, cols, output_sparse_matrix, output_kmer_file, tfidf):
+    """K6 (+ K7) on the GPU from per-row hit lists, then the reference's artefacts (polycracker.py:355-367)."""
     ctx = context()
     nnz = ctx.matrix_from_hits(row_offsets, cols, len(kmers))
     indptr, indices, data = ctx.csr(len(scaffolds), nnz)
@@ -355,6 +402,73 @@ def generate_Kmer_Matrix(kmercount_path="./kmercount_files/", genome=None, chunk
     pickle.dump(original_scaffolds, open("originalScaffolds.p", "wb"), protocol=2)
     pickle.dump(kmers, open(output_kmer_file, "wb"), protocol=2)
     return mat
+
+
+# --------------------------------------------------------------------------------------------------- N4 external counts
+def hipmer_output_to_kcount(hipmer_input="test.txt", kcount_output="test.final.kcount", run_on_dir=False):
+    """polycracker/format.py:123-133: `cat files | awk '{OFS="\t"; sum=0; for (i=2;i<=7;i++) sum+=$i; if (sum>=3) print $1, sum}'`.
+    HipMer's k-mer count files carry the k-mer and six count columns; the .kcount line is the k-mer and their sum, kept
+    when the sum is at least 3.  awk semantics: fields split on runs of blanks, a missing or non-numeric field counts 0
+    (its leading number, if any), sums print as integers when integral."""
+    files = [os.path.join(hipmer_input, f) for f in os.listdir(hipmer_input)] if run_on_dir else [hipmer_input]
+
+    def num(tok):
+        m = re.match(r"[ \t]*[-+]?(\d+\.?\d*([eE][-+]?\d+)?|\.\d+([eE][-+]?\d+)?)", tok)
+        return float(m.group(0)) if m else 0.0
+
+    with open(kcount_output, "w") as out:
+        for path in files:
+            with open(path) as f:
+                for line in f:
+                    p = line.split()
+                    total = sum(num(x) for x in p[1:7])
+                    if total >= 3:
+                        out.write("%s\t%s\n" % (p[0] if p else "", ("%d" % total) if total == int(total) else ("%.6g" % total)))
+    return kcount_output
+
+
+def read_kcount(path):
+    """A .kcount text file (`KMER<blank or tab>COUNT` per line, polycracker.py:199-208) -> (k, uint64 canonical keys,
+    uint32 counts).  Lines whose k-mer has another length than the first line's, or letters other than ACGT, are skipped
+    like the reference's downstream mapping would never place them; both strands of one k-mer are merged (counts add)."""
+    names, counts = [], []
+    with open(path) as f:
+        for line in f:
+            p = line.split()
+            if len(p) >= 2:
+                names.append(p[0]); counts.append(int(float(p[-1])))
+    if not names:
+        return 0, np.zeros(0, np.uint64), np.zeros(0, np.uint32)
+    k = len(names[0])
+    keep = [i for i, n in enumerate(names) if len(n) == k]
+    keys = binding.kmer_encode([names[i] for i in keep], k)
+    cnt = np.asarray(counts, np.int64)[keep]
+    ok = keys != np.uint64(0xFFFFFFFFFFFFFFFF)
+    keys, cnt = keys[ok], cnt[ok]
+    canon = np.array([binding.host_canonical(int(x), k) for x in keys.tolist()], np.uint64) if len(keys) < 4096 else _canonical_np(keys, k)
+    uniq, inv = np.unique(canon, return_inverse=True)
+    total = np.bincount(inv, weights=cnt.astype(np.float64), minlength=len(uniq)).astype(np.int64)
+    return k, uniq, np.minimum(total, 0xFFFFFFFF).astype(np.uint32)
+
+
+def _canonical_np(keys, k):
+    """strand collapse of uint64 k-mers in numpy (min of the k-mer and its reverse complement)"""
+    x = keys.astype(np.uint64)
+    for sh, m in ((2, 0x3333333333333333), (4, 0x0F0F0F0F0F0F0F0F), (8, 0x00FF00FF00FF00FF), (16, 0x0000FFFF0000FFFF)):
+        x = ((x >> np.uint64(sh)) & np.uint64(m)) | ((x & np.uint64(m)) << np.uint64(sh))
+    x = (x >> np.uint64(32)) | (x << np.uint64(32))
+    rc = (~x) >> np.uint64(64 - 2 * k)
+    return np.minimum(keys, rc)
+
+
+def load_kcount(ctx, path):
+    """Install the k-mers of a .kcount file (HipMer via hipmer_output_to_kcount, jellyfish dump, kmercountexact) as the
+    context's count result: select / build_matrix / tfidf then run on externally counted k-mers (pc_load_counts)."""
+    k, keys, counts = read_kcount(path)
+    if k == 0:
+        raise PolycrackerError("%s holds no k-mers" % path)
+    ctx.load_counts(keys, counts, k)
+    return k, len(keys)
 
 
 # --------------------------------------------------------------------------------------------------- N2 diagnostics

@@ -122,7 +122,47 @@ class OracleContext:
         return {}
 
 
-def _worker(rank, world, port, tmpdir, sampling):
+class SkmOracleContext(OracleContext):
+    """Adds the super-k-mer entry points (pc_skm_*): the records come from the device's own extraction routines run on the
+    host (binding.host_skm_records), bucketed like pc_skm_partition; the owner expands and counts what it received."""
+
+    def skm_plan(self, k, windows_global, world):
+        from polycracker_b200 import binding
+        pb, nb2 = 2, 3
+        m = binding.host_skm_m(k, (1 << pb) * nb2)
+        return np.array([pb, nb2, m, k - m + 1, min(16, 49 - k + 1), 1 if m else 0, 0, 0], np.int32)
+
+    def skm_partition(self, k, plan):
+        import torch
+        from polycracker_b200 import binding
+        pb, nb2, m, nmax = int(plan[0]), int(plan[1]), int(plan[2]), int(plan[4])
+        words, nmask, _ = binding.host_pack_chunks(self.seq, self.begins, self.ends)
+        recs = binding.host_skm_records(words, nmask, k, m, nmax, pb, nb2)
+        dest = ((recs[:, 1] >> np.uint64(6)) & np.uint64(0xFFFFFF)).astype(np.int64)
+        q, sub = dest >> 11, dest & 2047
+        n = (recs[:, 1] & np.uint64(63)).astype(np.int64) + 1
+        order = np.argsort(q, kind="stable")
+        hist = np.zeros((1 << pb) * nb2, np.int64)
+        np.add.at(hist, q * nb2 + sub, (n << 32) | 1)
+        self.k, self.n_windows = k, int(n.sum())
+        off = np.concatenate([[0], np.cumsum(np.bincount(q, minlength=1 << pb))]).astype(np.int64)
+        return off, torch.from_numpy(recs[order].reshape(-1).view(np.int64).copy()), torch.from_numpy(hist)
+
+    def skm_count_from(self, k, plan, seg_base, seg_begin, seg_len, hist, recs=None):
+        from polycracker_b200 import binding
+        assert seg_base is None and recs is not None            # CPU: the all-to-all variant of the exchange
+        arr = recs.numpy().view(np.uint64).reshape(-1, 2)
+        parts = [arr[b:b + n] for b, n in zip(np.asarray(seg_begin).ravel().tolist(), np.asarray(seg_len).ravel().tolist())]
+        mine = np.concatenate(parts) if parts else np.empty((0, 2), np.uint64)
+        h = hist.numpy()
+        assert int((h & 0xFFFFFFFF).sum()) == len(mine)         # the summed histogram describes exactly what arrived
+        keys, _ = binding.host_skm_expand(mine, k)
+        assert int((h >> 32).sum()) == len(keys)
+        self.keys, cnt = np.unique(keys, return_counts=True)
+        self.counts = cnt.astype(np.uint64)
+
+
+def _worker(rank, world, port, tmpdir, sampling, skm=False):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -146,8 +186,10 @@ def _worker(rank, world, port, tmpdir, sampling):
                     buf[begins[j]:ends[j]] = chrom[layout.chunk_start[i]:layout.chunk_end[i]]
             return buf
 
-        res = pcd.run_hot_path_distributed(OracleContext(), layout, fetch, torch.device("cpu"), chunk_size=20000, k=23,
-                                           kmer_low_count=10, sampling_sensitivity=sampling)
+        res = pcd.run_hot_path_distributed(SkmOracleContext() if skm else OracleContext(), layout, fetch,
+                                           torch.device("cpu"), chunk_size=20000, k=23, kmer_low_count=10,
+                                           sampling_sensitivity=sampling)
+        assert res.stats["exchange"] == ("nccl_all_to_all/super-k-mers" if skm else "nccl_all_to_all")
         full = pcd.gather_rows(res)
         if rank == 0:
             np.savez(os.path.join(tmpdir, "out.npz"), keys=full.kmer_keys, indptr=full.indptr, indices=full.indices,
@@ -158,13 +200,13 @@ def _worker(rank, world, port, tmpdir, sampling):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("sampling", [1, 3])
-def test_two_rank_gloo_matches_single_process_oracle(tmp_path, sampling):
+@pytest.mark.parametrize("sampling,skm", [(1, False), (3, False), (1, True)])
+def test_two_rank_gloo_matches_single_process_oracle(tmp_path, sampling, skm):
     import torch.multiprocessing as mp
     from polycracker_b200 import synth
     from tests import util
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
-    mp.spawn(_worker, args=(2, port, str(tmp_path), sampling), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, port, str(tmp_path), sampling, skm), nprocs=2, join=True)
     got = np.load(tmp_path / "out.npz")
     p = synth.small_params(seed=91, genome_size=600_000, n_chrom=3)
     seq, off, names = synth.generate(p)

@@ -43,7 +43,8 @@ def _worker(rank, world, port, tmpdir, part_mode, exchange):
         for _ in range(2):                                    # twice: the peer mappings and buffers are re-used
             res = pcd.run_hot_path_distributed(ctx, layout, fetch, dev, chunk_size=20000, k=23, kmer_low_count=10,
                                                exchange=exchange)
-        assert res.stats["exchange"] == ("peer" if exchange == "peer" else "nccl_all_to_all")
+        skm = part_mode in (3, -1)                            # k = 23: the automatic mode takes the super-k-mer path
+        assert res.stats["exchange"] == ("nccl_all_to_all" if exchange == "nccl" else "peer") + ("/super-k-mers" if skm else "")
         if exchange == "peer":                                # threshold sweep on the kept count tables (config 4)
             blocks = pcd.shard_chunks(layout, world)
             ids = pcd.local_buffer_plan(layout, blocks[rank])[0]
@@ -63,7 +64,8 @@ def _worker(rank, world, port, tmpdir, part_mode, exchange):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("part_mode,exchange", [(0, "nccl"), (1, "nccl"), (1, "peer"), (2, "nccl"), (2, "peer"), (-1, "peer")])
+@pytest.mark.parametrize("part_mode,exchange", [(0, "nccl"), (1, "nccl"), (1, "peer"), (2, "nccl"), (2, "peer"), (-1, "peer"),
+                                                (3, "peer"), (3, "nccl"), (-1, "auto")])
 def test_two_gpus_nccl_match_oracle(tmp_path, part_mode, exchange):
     from polycracker_b200 import binding, synth
     from tests import util

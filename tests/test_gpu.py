@@ -429,6 +429,43 @@ def test_compact_handoff_matches_full_arrays(ctx):
         assert (comp.row_norm == 0).any()                              # the all-N chunks: empty rows stay zero
 
 
+def test_external_kcount_ingest(ctx, tmp_path):
+    """Scope row N4, second half (format.py:123-133): a .kcount written by ANOTHER counter (here: the oracle's counts, with
+    half of the k-mers named by their reverse-complement strand, as a non-canonical counter would) is installed as the count
+    result (pc_load_counts) and K4..K7 run on it: same repeat set, matrix and TF-IDF as counting on the GPU."""
+    from polycracker_b200 import stages
+    p = synth.small_params(seed=123, genome_size=400_000)
+    seq, off, names = synth.generate(p)
+    k, chunk, low = 23, 20000, 6
+    want = util.c_oracle_path(seq, off, names, chunk, k, low)
+    keep = want["counts"] >= 3
+    kmers = binding.kmer_decode(want["keys"][keep], k)
+    comp = str.maketrans("ACGT", "TGCA")
+    path = str(tmp_path / "ext.kcount")
+    with open(path, "w") as f:
+        for i, (km, c) in enumerate(zip(kmers, want["counts"][keep].tolist())):
+            f.write("%s%s%d\n" % (km.translate(comp)[::-1] if i % 2 else km, "\t" if i % 3 else " ", c))
+        f.write("ACGTNNNNNNNNNNNNNNNNNNN\t50\n")                      # not a k-mer: skipped
+    lay = ChunkLayout(names, off, chunk)
+    scaffolds, chunk_row = lay.rows()
+    ctx.load_sequences(seq, lay.chunk_begin_abs, lay.chunk_end_abs)
+    kk, n = stages.load_kcount(ctx, path)
+    assert kk == k and n == int(keep.sum()) and ctx.count_info()["distinct"] == n
+    n_sel = ctx.select(low)
+    assert ctx.selected(n_sel).tolist() == want["sel"].tolist()
+    nnz = ctx.build_matrix(chunk_row, len(scaffolds))
+    indptr, indices, data = ctx.csr(len(scaffolds), nnz)
+    assert np.array_equal(indptr, want["indptr"]) and np.array_equal(indices, want["indices"]) and np.array_equal(data, want["data"])
+    ctx.tfidf(len(scaffolds))
+    util.assert_tfidf_close(ctx.tfidf_values(nnz), want["tfidf"])
+    values, freq, above = ctx.count_histogram(3, 1000)
+    assert freq.sum() + above == n
+    with pytest.raises(binding.PolycrackerError, match="more than once"):
+        ctx.load_counts(np.array([5, 5], np.uint64), np.array([3, 4], np.uint32), k)
+    with pytest.raises(binding.PolycrackerError, match="not k-mers"):
+        ctx.load_counts(np.array([5, 0xFFFFFFFFFFFFFFFF], np.uint64), np.array([3, 4], np.uint32), k)
+
+
 def test_n2_diagnostics(ctx):
     """Scope row N2: the data of kcount_hist (Counter over the dumped counts) and of number_repeatmers_per_subsequence
     (k-mer names per merged-bed line), from the table count, the list count and against the literal oracle."""
@@ -622,6 +659,110 @@ def test_owner_partitioned_counts_two_ranks_on_one_gpu(ctx):
     assert total_distinct == len(want["keys"])
     union = np.sort(np.concatenate(selected))
     assert union.tolist() == want["sel"].tolist()
+
+
+@pytest.mark.parametrize("world,part_mode", [(2, 3), (4, 3), (3, -1), (2, 2), (4, 2)])
+def test_emulated_ranks_end_to_end_on_one_gpu(world, part_mode):
+    """The multi-GPU path with every rank emulated by its own context on ONE device, end to end and with the driver's own
+    helpers (shard_chunks, local_buffer_plan, owner_ranges, owner_segments): shard the chunks, partition locally, exchange
+    the bucket sizes and sub-bucket histograms (summed on the host here instead of all-gather / all-to-all), every owner
+    counts its buckets straight out of ALL ranks' buffers (pointer segments, as over NVLink peer memory), thresholds its
+    share, the union of the repeat sets is installed everywhere, local matrices, global df, TF-IDF, row blocks
+    concatenated -- against the single-process C oracle.  part_mode 3 / -1: super-k-mer records; 2: 8-byte k-mers."""
+    import torch
+    from polycracker_b200 import distributed as pcd
+    from polycracker_b200.pipeline import dump_floor, effective_low_count
+    p = synth.small_params(seed=191, genome_size=3_000_000, n_chrom=3, n_shared_families=6, n_specific_families=8)
+    seq, off, names = synth.generate(p)
+    k, chunk, low = 23, 20000, 10
+    want = util.c_oracle_path(seq, off, names, chunk, k, low)
+    layout = ChunkLayout(names, off, chunk)
+    scaffolds_all, chunk_row_all = layout.rows()
+    windows_global = int(np.maximum(0, (layout.chunk_end - layout.chunk_start) - k + 1).sum())
+    blocks = pcd.shard_chunks(layout, world)
+    ctxs = [binding.Context(0) for _ in range(world)]
+    dev = torch.device("cuda", 0)
+    try:
+        plans, shard = [], []
+        for r, c in enumerate(ctxs):
+            c.tune(part_mode=part_mode, keep_min=dump_floor(k))
+            ids, begins, ends, total = pcd.local_buffer_plan(layout, blocks[r])
+            buf = np.empty(total, np.uint8)
+            for j, i in enumerate(ids.tolist()):
+                a = int(off[layout.chunk_seq[i]])
+                buf[begins[j]:ends[j]] = seq[a + layout.chunk_start[i]:a + layout.chunk_end[i]]
+            c.load_sequences(buf, begins, ends)
+            shard.append((ids, begins, ends))
+            plans.append(c.skm_plan(k, windows_global, world))
+        skm = int(plans[0][5]) == 1
+        assert skm == (part_mode != 2) and all(np.array_equal(pl, plans[0]) for pl in plans)
+        plan = plans[0]
+        if skm:
+            pb, nb2 = int(plan[0]), int(plan[1])
+            parts = [c.skm_partition(k, plan) for c in ctxs]                # (off, records ptr, hist ptr)
+            hists = [pcd.device_view(torch, h, (1 << pb) * nb2, dev) for _, _, h in parts]
+        else:
+            smem_mean = (1 << 20) // ctxs[0].sub_plan(1 << 40, 1 << 20)
+            pb = pcd.plan_partition_bits(windows_global, world, smem_mean=smem_mean)
+            parts = [c.partition(k, pb) for c in ctxs]                      # (off, k-mer ptr)
+        P = 1 << pb
+        q_lo = pcd.owner_ranges(P, world)
+        sizes_all = np.stack([np.diff(pt[0]) for pt in parts])              # [sender, bucket]
+        ptrs = np.asarray([pt[1] for pt in parts], dtype=np.uint64)
+        n_windows = 0
+        selected, distinct = [], 0
+        for r, c in enumerate(ctxs):
+            seg_begin, seg_len = pcd.owner_segments(sizes_all, q_lo, r)
+            seg_base = np.repeat(ptrs[None, :], seg_len.shape[0], axis=0)
+            if skm:
+                mine = slice(q_lo[r] * nb2, q_lo[r + 1] * nb2)
+                staged = torch.stack([h[mine] for h in hists]).sum(dim=0).contiguous()
+                torch.cuda.synchronize()
+                c.skm_count_from(k, plan, seg_base, seg_begin, seg_len, staged)
+            else:
+                nb2 = max(c.sub_plan(int(sizes_all[:, q_lo[x]:q_lo[x + 1]].sum()), max(1, q_lo[x + 1] - q_lo[x])) for x in range(world))
+                hs = []
+                for c2 in ctxs:
+                    h = torch.empty(P * nb2, dtype=torch.int64, device=dev)
+                    c2.sub_hist(pb, nb2, h)
+                    hs.append(h[q_lo[r] * nb2:q_lo[r + 1] * nb2])
+                staged = torch.stack(hs).sum(dim=0).contiguous()
+                torch.cuda.synchronize()
+                c.sub_hist_set(nb2, staged)
+                c.count_buckets_from(k, pb, seg_base, seg_begin, seg_len)
+            info = c.count_info()
+            n_windows += info["valid_windows"]; distinct += info["distinct"]
+            n = c.select(effective_low_count(k, low))
+            selected.append(c.selected(n))
+        assert n_windows == want["n_windows"] and distinct == len(want["keys"])
+        sel_all = np.concatenate(selected)
+        assert len(np.unique(sel_all)) == len(sel_all)                       # owners select disjoint sets
+        rows, dfs = [], []
+        for r, c in enumerate(ctxs):
+            ids = shard[r][0]
+            my = chunk_row_all[ids]
+            kept = my[my >= 0]
+            row0 = int(kept.min()) if len(kept) else 0
+            assert len(kept) == 0 or int(kept.max()) - row0 + 1 == len(kept)
+            n_sel = c.set_selected(sel_all, k)
+            nnz = c.build_matrix(np.where(my >= 0, my - row0, -1).astype(np.int32), len(kept))
+            rows.append((row0, len(kept), nnz))
+            dfs.append(c.df(n_sel))
+        df = np.sum(dfs, axis=0).astype(np.int32)
+        keys = ctxs[0].selected(len(sel_all))
+        assert keys.tolist() == want["sel"].tolist()
+        indptr, indices, data, tf = [np.zeros(1, np.int64)], [], [], []
+        for r, c in sorted(enumerate(ctxs), key=lambda x: rows[x[0]][0] if rows[x[0]][1] else 1 << 60):
+            row0, n_rows, nnz = rows[r]
+            c.tfidf(len(scaffolds_all), df)
+            ip, ix, dt = c.csr(n_rows, nnz)
+            indptr.append(ip[1:] + int(indptr[-1][-1])); indices.append(ix); data.append(dt); tf.append(c.tfidf_values(nnz))
+        assert np.array_equal(np.concatenate(indptr), want["indptr"])
+        assert np.array_equal(np.concatenate(indices), want["indices"]) and np.array_equal(np.concatenate(data), want["data"])
+        util.assert_tfidf_close(np.concatenate(tf), want["tfidf"])
+    finally:
+        for c in ctxs:
+            c.close()
 
 
 def test_cfg1_full_size_parity(ctx):

@@ -215,3 +215,35 @@ def test_super_kmer_records_partition_the_kmers_exactly(k, chunk):
         if nmax == 1:
             assert len(recs) == len(want)
     assert binding.host_skm_m(9, 1000) == 0                     # too short for a minimizer window
+
+
+def test_hipmer_output_to_kcount_matches_the_reference_awk_line(tmp_path):
+    """format.py:123-133 shells out to `cat <files> | awk '{OFS="\\t"; sum=0; for (i=2; i<=7; i++) { sum+= $i }; if (sum >= 3)
+    print $1, sum}'`; the host mirror must write the same bytes (run against the real awk when the box has one)."""
+    import shutil
+    import subprocess
+    from polycracker_b200 import stages
+    rng = np.random.default_rng(5)
+    d = tmp_path / "hip"
+    d.mkdir()
+    for f in range(3):
+        with open(d / ("part%d.txt" % f), "w") as out:
+            for _ in range(400):
+                kmer = "".join(rng.choice(list("ACGT"), 21))
+                cols = rng.integers(0, 3, size=int(rng.integers(4, 9))).tolist()      # fewer or more than six count columns
+                sep = "\t" if rng.random() < 0.5 else "  "
+                out.write(kmer + sep + sep.join(str(c) for c in cols) + "\n")
+            out.write("ACGTACGTACGTACGTACGTA\t2\t0.5\t0.5\tx\t0\t0\n")                     # fractional sum, a non-numeric field
+            out.write("\n")
+    stages.hipmer_output_to_kcount(str(d), str(tmp_path / "mine.kcount"), run_on_dir=True)
+    stages.hipmer_output_to_kcount(str(d / "part0.txt"), str(tmp_path / "one.kcount"))
+    lines = open(tmp_path / "mine.kcount").read().splitlines()
+    assert lines and all(float(l.split("\t")[1]) >= 3 for l in lines)
+    if shutil.which("awk"):
+        files = " ".join(str(d / f) for f in os.listdir(d))
+        cmd = "cat %s | awk '{OFS = \"\\t\"; sum=0; for (i=2; i<=7; i++) { sum+= $i }; if (sum >= 3) print $1, sum}' > %s" % (
+            files, tmp_path / "awk.kcount")
+        subprocess.check_call(cmd, shell=True)
+        assert open(tmp_path / "mine.kcount").read() == open(tmp_path / "awk.kcount").read()
+    k, keys, counts = stages.read_kcount(str(tmp_path / "mine.kcount"))
+    assert k == 21 and len(keys) == len(np.unique(keys)) and counts.min() >= 3
