@@ -85,6 +85,13 @@ int pc_count_info(pc_ctx* ctx, int64_t info[8]);
  * distinct k-mers did not fit the shared-memory table; super-k-mer count: detail[6] = records, detail[7] = minimizer
  * length m (both 0 when the k-mers themselves were partitioned). */
 int pc_count_detail(pc_ctx* ctx, int64_t detail[8]);
+/* Counters are uint32.  A counting unit (one shared-memory table, one sub-table, the direct table) that received >= 2^32
+ * k-mer instances could wrap one (one k-mer with > 4.29e9 occurrences on one GPU): such a count is REFUSED with PC_ENOMEM,
+ * never returned wrapped (SURVEY 8c "counts saturate / flag at 2^32 - 1").  flags[0] = 1 if the last count could have
+ * wrapped (always 0 for a count that was returned), flags[1] = k-mer instances of the largest counting unit (upper bound for
+ * the super-k-mer count), flags[2] = sub-buckets that overflowed their shared-memory table and were re-counted through a
+ * global table, flags[3] = slots per table. */
+int pc_count_flags(pc_ctx* ctx, int64_t flags[4]);
 /* dump (kmer, count) with min_count <= count <= max_count (the .kcount file: `mincount=3` for k<=31,
  * polycracker.py:199).  keys == NULL -> only *n is written.  Unordered, like the tools' dumps. */
 int pc_dump_counts(pc_ctx* ctx, uint32_t min_count, uint32_t max_count,

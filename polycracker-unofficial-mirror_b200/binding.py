@@ -69,6 +69,7 @@ _SIGS = {
     "pc_count_info": (C.c_int, [_vp, _vp]),
     "pc_load_counts": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int, C.c_int]),
     "pc_count_detail": (C.c_int, [_vp, _vp]),
+    "pc_count_flags": (C.c_int, [_vp, _vp]),
     "pc_copy_async": (C.c_int, [_vp, _vp, _vp, _i64, _vp, C.c_int]),
     "pc_read_back": (C.c_int, [_vp, _vp, _vp, _i64]),
     "pc_count_histogram": (C.c_int, [_vp, _u32, _u32, _vp, C.c_int]),
@@ -461,6 +462,11 @@ class Context:
         check(lib.pc_count_detail(self._h, d.ctypes.data), "pc_count_detail")
         return dict(kind="list" if d[0] == 1 else "table", kept=int(d[1]), keep_min=int(d[2]), sub_buckets=int(d[3]),
                     sub_per_bucket=int(d[4]), overflowed=int(d[5]), skm_records=int(d[6]), skm_m=int(d[7]))
+
+    def count_flags(self):
+        f = np.zeros(4, np.int64)
+        check(lib.pc_count_flags(self._h, f.ctypes.data), "pc_count_flags")
+        return dict(could_wrap=bool(f[0]), largest_unit=int(f[1]), overflowed_sub_buckets=int(f[2]), slots_per_table=int(f[3]))
 
     def dump_counts(self, min_count=1, max_count=0xFFFFFFFF):
         n = _i64()

@@ -173,6 +173,7 @@ struct pc_ctx {
     int skm_min_k = 17;                         // auto mode: shortest k that takes the super-k-mer path
     int skm_stage = 2560;                       // tunable: records staged per CTA of the extraction (x 16 bytes of shared memory)
     bool skm_used = false;
+    uint64_t max_unit = 0;                      // k-mer instances of the largest counting unit (sub-bucket / bucket / table) of the last count
 
     // N1 subgenome-extraction session (pc_sub_*): per-subgenome dictionaries of the k being compared, then per k the
     // differential sets and their union mask table
@@ -566,6 +567,17 @@ static int table_prepare(pc_ctx* c, int k, int64_t capacity, bool reset_stats = 
     return PC_OK;
 }
 
+// counts are uint32: a counting unit (one shared-memory table, one sub-table, the whole direct table) that received 2^32 or
+// more k-mer instances could have wrapped a counter.  That needs one k-mer with > 4.29e9 occurrences on one GPU (a
+// multi-Gbp homopolymer); it is refused loudly instead of returning a wrapped count ("counts saturate / flag").
+static int check_unit_size(pc_ctx* c, uint64_t instances) {
+    c->max_unit = std::max<uint64_t>(c->max_unit, instances);
+    if (instances >= (1ull << 32))
+        return fail(PC_ENOMEM, "a counting unit holds %llu k-mer instances: a uint32 counter could wrap -- shard the genome over "
+                    "more GPUs (counts are never returned wrapped)", (unsigned long long)instances);
+    return PC_OK;
+}
+
 static int fetch_stats(pc_ctx* c) {
     READ_SMALL(c, &c->h_stats, c->d_stats.p, sizeof(pc::CountStats));
     SYNC(c);
@@ -656,6 +668,7 @@ static int count_buckets_table(pc_ctx* c, int k, int pb, int n_buckets, const ui
         }
         total += t; max_bucket = std::max(max_bucket, t);
     }
+    { int rc_u = check_unit_size(c, (uint64_t)max_bucket); if (rc_u) return rc_u; }
     if (capacity <= 0) {
         double space = k >= 31 ? 9.3e18 : (double)(1ull << (2 * k));
         capacity = (int64_t)(std::min((double)total, space) / c->table_load) + 1024;
@@ -801,6 +814,7 @@ static int count_buckets_smem(pc_ctx* c, int k, int pb, int n_buckets, const uin
                 CU(cudaGetLastError());
             }
             LAUNCH(c, pc::k_rs_scan<unsigned long long>, 1, 1024, sub_off, n_sub);
+            LAUNCH(c, pc::k_max_diff, (unsigned int)std::min<int64_t>(148, (n_sub + 255) / 256), 256, sub_off, n_sub, c->d_sub.p + 2 * n_sub + 5);
             size_t smem = (size_t)TILE * 8 + (size_t)NB2 * 8 + (size_t)NB2 * 4 + ((size_t)NB2 + 2) * 4 + (size_t)TILE * 2 + 16;
             CU(cudaFuncSetAttribute((pc::k_sub_scatter<TILE, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             CU(cudaFuncSetAttribute((pc::k_sub_scatter<TILE, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -830,10 +844,13 @@ static int count_buckets_smem(pc_ctx* c, int k, int pb, int n_buckets, const uin
             if (rc) return rc;
         }
     }
-    unsigned long long h_nlist = 0; unsigned int h_novf = 0;
+    unsigned long long h_nlist = 0, h_maxunit = 0; unsigned int h_novf = 0;
     READ_SMALL(c, &h_nlist, d_nlist, sizeof h_nlist);
     READ_SMALL(c, &h_novf, d_novf, sizeof h_novf);
+    READ_SMALL(c, &h_maxunit, c->d_sub.p + 2 * n_sub + 5, sizeof h_maxunit);
     rc = fetch_stats(c); if (rc) return rc;                   // synchronises
+    c->max_unit = 0;
+    rc = check_unit_size(c, h_maxunit); if (rc) return rc;
     c->n_ovf = h_novf;
     if (h_novf > 0) {
         // sub-buckets whose distinct k-mers did not fit a shared-memory table: count them in one global table and
@@ -1089,11 +1106,13 @@ static int count_buckets_skm(pc_ctx* c, int k, const SkmPlan& pl, int n_buckets,
     unsigned int* d_novf = reinterpret_cast<unsigned int*>(c->d_sub.p + 2 * n_sub + 3);
     unsigned long long* d_kmers = c->d_sub.p + 2 * n_sub + 4;              // [1] k-mer instances in these buckets
     CU(cudaMemsetAsync(c->d_sub.p, 0, ((size_t)2 * n_sub + 8) * sizeof(unsigned long long), c->stream));
-    unsigned long long h_kmers = 0;
+    unsigned long long h_kmers = 0, h_maxrec = 0;
     {
         StageTimer t(c, ST_PART2);
         LAUNCH(c, k_skm_hist_split, (unsigned int)std::min<int64_t>(148 * 4, (n_sub + 255) / 256), 256, hist_dev, n_sub, sub_off, d_kmers);
         LAUNCH(c, pc::k_rs_scan<unsigned long long>, 1, 1024, sub_off, n_sub);
+        LAUNCH(c, pc::k_max_diff, (unsigned int)std::min<int64_t>(148, (n_sub + 255) / 256), 256, sub_off, n_sub, c->d_sub.p + 2 * n_sub + 6);
+        READ_SMALL(c, &h_maxrec, c->d_sub.p + 2 * n_sub + 6, sizeof h_maxrec);
         READ_SMALL(c, &h_kmers, d_kmers, sizeof h_kmers);
         if (total > 0) {
             if (TILE == 4096) rc = launch_rec_scatter<4096, 2>(c, recs_dev, d_base, d_beg, d_len, c->d_tile.p, (int)n_pairs, n_seg, n_tiles, NB2, NB2, sub_off, sub_cur, c->rec_a.p);
@@ -1102,6 +1121,11 @@ static int count_buckets_skm(pc_ctx* c, int k, const SkmPlan& pl, int n_buckets,
         }
     }
     SYNC(c);                                                   // k-mer total: sizes the list
+    c->max_unit = 0;
+    // (the sub-bucket's own k-mer count travels in 32 bits of the packed histogram: bound it by its records)
+    rc = check_unit_size(c, (uint64_t)h_maxrec * (uint64_t)pl.nmax >= (1ull << 32) ? (uint64_t)h_maxrec * (uint64_t)pl.nmax
+                                                                                     : std::min<uint64_t>((uint64_t)h_maxrec * (uint64_t)pl.nmax, h_kmers));
+    if (rc) return rc;
     const unsigned long long list_cap = h_kmers / c->keep_min + 1024ull;
     rc = c->list_keys.alloc((size_t)list_cap); if (rc) return rc;
     rc = c->list_counts.alloc((size_t)list_cap); if (rc) return rc;
@@ -1332,7 +1356,9 @@ int pc_count(pc_ctx* c, int k, int64_t capacity) {
         if (pb == 0) pb = 1;
     }
     uint64_t P = 1ull << pb;
+    c->max_unit = 0;
     if (!partitioned || c->n_words == 0) {
+        rc = check_unit_size(c, (uint64_t)windows); if (rc) return rc;
         uint64_t S = std::max<uint64_t>(64, (uint64_t)capacity);
         rc = table_prepare(c, k, (int64_t)S); if (rc) return rc;
         c->pb = 0; c->part_S = S;
@@ -1578,6 +1604,15 @@ int pc_count_info(pc_ctx* c, int64_t info[8]) {
     info[3] = (int64_t)(c->capacity * (size_t)PC_SLOT_BYTES); info[4] = (int64_t)c->h_stats.max_probe; info[5] = c->k;
     info[6] = c->count_kind == 1 ? c->n_list : 0; info[7] = c->pb;
     if (c->count_kind == 1) info[3] = (int64_t)((size_t)c->list_keys.n * 12 + (c->skm_used ? (size_t)c->rec_a.n * 16 : (size_t)c->kbuf2.n * 8));
+    return PC_OK;
+}
+
+int pc_count_flags(pc_ctx* c, int64_t flags[4]) {
+    if (!c || !c->counted || !flags) return fail(PC_ESTATE, "no count result");
+    flags[0] = c->max_unit >= (1ull << 32) ? 1 : 0;            // always 0 for a count that was returned: see check_unit_size
+    flags[1] = (int64_t)c->max_unit;
+    flags[2] = c->count_kind == 1 ? c->n_ovf : 0;
+    flags[3] = c->count_kind == 1 && c->n_sub > 0 ? (int64_t)(c->capacity / (uint64_t)c->n_sub) : (int64_t)c->capacity;
     return PC_OK;
 }
 

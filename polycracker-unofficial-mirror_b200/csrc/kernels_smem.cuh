@@ -477,6 +477,19 @@ k_count_smem(const uint64_t* __restrict__ kbuf2, const unsigned long long* __res
     }
 }
 
+// largest counting unit: max over i of off[i + 1] - off[i] (the uint32 counters of a unit cannot wrap while the unit holds
+// fewer than 2^32 k-mer instances; the host refuses to return counts otherwise)
+__global__ void __launch_bounds__(256)
+k_max_diff(const unsigned long long* __restrict__ off, int64_t n, unsigned long long* __restrict__ out)
+{
+    unsigned long long m = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m = max(m, off[i + 1] - off[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
+}
+
 // K4 over the compact list: survivors appended with one atomic per warp (same contract as k_select)
 __global__ void __launch_bounds__(256)
 k_select_list(const uint64_t* __restrict__ keys, const uint32_t* __restrict__ counts, int64_t n, unsigned int low,

@@ -228,6 +228,8 @@ def test_super_kmer_count(ctx, k):
         assert np.array_equal(keys[order], want_keys[m]) and np.array_equal(counts[order].astype(np.uint64), want_counts[m])
         info = ctx.count_info()
         assert info["valid_windows"] == n_windows and info["distinct"] == distinct
+        f = ctx.count_flags()                                    # uint32 counters: no counting unit anywhere near 2^32 instances
+        assert not f["could_wrap"] and 0 < f["largest_unit"] <= n_windows and f["overflowed_sub_buckets"] == d["overflowed"]
         return d
 
     try:
