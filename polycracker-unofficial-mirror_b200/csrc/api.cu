@@ -98,6 +98,8 @@ struct pc_ctx {
     DevBuf<unsigned int> rs_hist;
     DevBuf<unsigned long long> d_counter;
     DevBuf<pc::RepSlot> rtable; DevBuf<unsigned short> rfp; uint64_t rcap = 0;
+    DevBuf<unsigned long long> rtable8; uint64_t rcap8 = 0;     // compact 8-byte slots (large repeat sets, roller probe)
+    int probe_table8 = -1;                      // tunable: -1 auto (repeat sets beyond the shared-memory filter, no k-mer stream), 0 off, 1 on
     bool selected = false;
 
     // matrix
@@ -298,8 +300,10 @@ int build_rep_table(pc_ctx* c) {
         LAUNCH(c, pc::k_rep_build, blocks_for(c->n_sel, 256), 256, c->sel, c->n_sel, c->rtable.p, c->rcap, c->rfp.p);
     // shared-memory filter of the probe: worth it while the bitmap stays sparse (>= 1.2 bits per repeat k-mer: fill < 57 %)
     c->rfilter_bits = 0; c->gfilter_bits = 0;
+    // (the roller probe -- no k-mer stream -- measured better with the L2 bitmap than with the shared-memory one at every size:
+    // 3.79 vs 3.91 ms at 673 k repeat k-mers; the shared-memory bitmap stays the choice of the stream probe)
     const bool smem_filter = c->n_sel > 0 && c->probe_filter != 0 && c->probe_filter != 2 &&
-                             (c->probe_filter == 1 || c->filter_bits * 5 >= c->n_sel * 6);
+                             (c->probe_filter == 1 || (c->stream_valid && c->filter_bits * 5 >= c->n_sel * 6));
     // (not in front of the fingerprint walk, which already keeps misses away from the table: measured on 8 GPUs with
     // 5.6 M repeat k-mers, probe 7.4 ms with fingerprints alone, 8.8 ms with the bitmap in front of them)
     const bool fp_walk = c->probe_fp == 1 || (c->probe_fp < 0 && c->rcap * sizeof(pc::RepSlot) > (size_t)(256ull << 20));
@@ -313,6 +317,16 @@ int build_rep_table(pc_ctx* c) {
         CU(cudaMemsetAsync(c->rfilter.p, 0, ((size_t)nbits / 32 + 4) * sizeof(unsigned int), c->stream));
         LAUNCH(c, pc::k_filter_build, blocks_for(c->n_sel, 256), 256, c->sel, c->n_sel, nbits, c->rfilter.p);
         c->gfilter_bits = nbits;
+    }
+    c->rcap8 = 0;
+    // compact table only where the 16-byte slots (64 bytes per repeat k-mer at load 0.25) would leave L2: measured at 673 k
+    // repeat k-mers, where both fit, the inline keys win (3.79 ms against 5.78: no verification read, shorter probe chains)
+    if (c->n_sel > 0 && (c->probe_table8 == 1 || (c->probe_table8 < 0 && !smem_filter && !c->stream_valid && c->probe_roll != 0 &&
+                                                   c->rcap * sizeof(pc::RepSlot) > (size_t)(96ull << 20)))) {
+        c->rcap8 = std::max<uint64_t>(64, (uint64_t)c->n_sel * 2);
+        rc = c->rtable8.alloc(c->rcap8); if (rc) return rc;
+        CU(cudaMemsetAsync(c->rtable8.p, 0, c->rcap8 * sizeof(unsigned long long), c->stream));
+        LAUNCH(c, pc::k_rep8_build, blocks_for(c->n_sel, 256), 256, c->sel, c->n_sel, c->rtable8.p, c->rcap8);
     }
     if (smem_filter) {
         unsigned int nbits = (unsigned int)std::min<int64_t>(std::max<int64_t>(c->filter_bits, 1024), 1744896) & ~127u;
@@ -378,7 +392,7 @@ int pc_destroy(pc_ctx* c) {
     c->d_scaled.release(); c->d_colstat.release(); c->d_rowscale.release();
     c->kbuf2.release(); c->list_keys.release(); c->list_counts.release(); c->d_sub.release(); c->d_tile.release(); c->d_ovf.release();
     c->rec_a.release(); c->rec_b.release(); c->d_skm_hist.release(); c->d_skm_off.release(); c->d_skm_cur.release(); c->d_skm_n.release(); c->d_skm_koff.release();
-    c->sel_a.release(); c->sel_b.release(); c->rs_hist.release(); c->d_counter.release(); c->rtable.release(); c->rfp.release(); c->rfilter.release();
+    c->sel_a.release(); c->sel_b.release(); c->rs_hist.release(); c->d_counter.release(); c->rtable.release(); c->rfp.release(); c->rfilter.release(); c->rtable8.release();
     c->d_chunk_row.release(); c->d_row_base.release(); c->d_row_cursor.release(); c->hits_a.release();
     c->hits_b.release(); c->d_row_nnz.release(); c->d_indptr.release(); c->d_indices.release();
     c->d_data.release(); c->d_idf.release(); c->d_tfidf.release(); c->d_df.release(); c->d_df_global.release();
@@ -1296,6 +1310,7 @@ int pc_tune(pc_ctx* c, const char* key, int64_t value) {
     else if (k == "part_minb") c->part_minb = (int)value;
     else if (k == "probe_batch") c->probe_batch = (int)value;
     else if (k == "probe_roll") c->probe_roll = (int)value;
+    else if (k == "probe_table8") c->probe_table8 = (int)value;
     else if (k == "rep_load_inv") c->rep_load_inv = (int)value;
     else if (k == "part_mbytes") c->part_bytes = std::max<int64_t>(1, value) << 20;
     else if (k == "part_blocks") c->part_blocks = (int)std::max<int64_t>(0, value);
@@ -2137,16 +2152,31 @@ int pc_build_matrix(pc_ctx* c, const int32_t* chunk_row, int64_t n_rows, int64_t
                 size_t smem = (size_t)(c->rfilter_bits / 32 + 4) * sizeof(unsigned int);
                 unsigned int pgrid = (unsigned int)std::min<int64_t>(148, (c->n_words + 1023) / 1024);
                 c->launches++;
-                CU(cudaFuncSetAttribute((pc::k_probe_roll_filt<4, 1024, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                pc::k_probe_roll_filt<4, 1024, true><<<pgrid, 1024, smem, c->stream>>>(c->words.p, c->nmask.p, c->n_words, k, c->d_word0.p,
-                    c->n_chunks, c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, nullptr, c->rfilter.p, c->rfilter_bits,
-                    c->hits_a.p, c->d_row_cursor.p);
+                if (c->rcap8 > 0) {
+                    CU(cudaFuncSetAttribute((pc::k_probe_roll_filt<4, 1024, true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    pc::k_probe_roll_filt<4, 1024, true, true><<<pgrid, 1024, smem, c->stream>>>(c->words.p, c->nmask.p, c->n_words, k, c->d_word0.p,
+                        c->n_chunks, c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, nullptr, c->rfilter.p, c->rfilter_bits,
+                        c->rtable8.p, c->rcap8, c->sel, c->hits_a.p, c->d_row_cursor.p);
+                } else {
+                    CU(cudaFuncSetAttribute((pc::k_probe_roll_filt<4, 1024, true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                    pc::k_probe_roll_filt<4, 1024, true, false><<<pgrid, 1024, smem, c->stream>>>(c->words.p, c->nmask.p, c->n_words, k, c->d_word0.p,
+                        c->n_chunks, c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, nullptr, c->rfilter.p, c->rfilter_bits,
+                        nullptr, 0, nullptr, c->hits_a.p, c->d_row_cursor.p);
+                }
                 CU(cudaGetLastError());
             } else {
-                unsigned int pgrid = (unsigned int)std::min<int64_t>(148 * 8, (c->n_words + 255) / 256);
-                LAUNCH(c, (pc::k_probe_roll_filt<8, 256, false>), pgrid, 256, c->words.p, c->nmask.p, c->n_words, k, c->d_word0.p,
-                       c->n_chunks, c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, use_fp ? c->rfp.p : nullptr,
-                       c->gfilter_bits ? c->rfilter.p : nullptr, c->gfilter_bits, c->hits_a.p, c->d_row_cursor.p);
+                // (64 registers: 4 CTAs of 256 threads per SM; the first version ran BATCH = 8 at 136 registers and one CTA
+                // per SM: 9.1 ms instead of ~4 for 1.3 M repeat k-mers)
+                unsigned int pgrid = (unsigned int)std::min<int64_t>(148 * 4, (c->n_words + 255) / 256);
+                if (c->rcap8 > 0)
+                    LAUNCH(c, (pc::k_probe_roll_filt<4, 256, false, true>), pgrid, 256, c->words.p, c->nmask.p, c->n_words, k, c->d_word0.p,
+                           c->n_chunks, c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, nullptr,
+                           c->gfilter_bits ? c->rfilter.p : nullptr, c->gfilter_bits, c->rtable8.p, c->rcap8, c->sel,
+                           c->hits_a.p, c->d_row_cursor.p);
+                else
+                    LAUNCH(c, (pc::k_probe_roll_filt<4, 256, false, false>), pgrid, 256, c->words.p, c->nmask.p, c->n_words, k, c->d_word0.p,
+                           c->n_chunks, c->d_chunk_row.p, c->d_row_base.p, c->rtable.p, c->rcap, use_fp ? c->rfp.p : nullptr,
+                           c->gfilter_bits ? c->rfilter.p : nullptr, c->gfilter_bits, nullptr, 0, nullptr, c->hits_a.p, c->d_row_cursor.p);
             }
         }
     }

@@ -529,18 +529,56 @@ k_count_rec_table(const SkmRec* __restrict__ recs, const unsigned long long* __r
     }
 }
 
+// ------------------------------------------------------------------------------------------------ K5 compact repeat table
+// 8-byte slots for large repeat sets: (32-bit fingerprint << 32) | (column + 1), 0 = empty, load 0.5 -> 16 bytes per repeat
+// k-mer instead of 64 (16-byte slots at load 0.25), so the 5.6 M repeat k-mers of the 8-GPU run stay L2 resident (90 MB
+// instead of 358 MB).  A fingerprint match is verified against the sorted key array (column = rank), so the look-up is
+// exact; only real hits (and one in 2^32 of the other slots met) pay that second read.
+__device__ __forceinline__ unsigned int rep_fp32(uint64_t key) { return (unsigned int)((key * 0xC2B2AE3D27D4EB4Full) >> 32); }
+
+__global__ void __launch_bounds__(256)
+k_rep8_build(const uint64_t* __restrict__ sorted_keys, int64_t n, unsigned long long* __restrict__ table8, uint64_t cap8)
+{
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t key = sorted_keys[i];
+    const unsigned long long val = ((unsigned long long)rep_fp32(key) << 32) | (unsigned long long)(i + 1);
+    uint64_t s = rep_slot(key, cap8);
+    for (;;) {                                               // keys are unique and cap8 >= 2 n: terminates
+        if (atomicCAS(&table8[s], 0ull, val) == 0ull) break;
+        if (++s == cap8) s = 0;
+    }
+}
+
+// column of `key` or -1
+__device__ __forceinline__ int rep8_find(const unsigned long long* __restrict__ table8, uint64_t cap8,
+                                         const uint64_t* __restrict__ sorted_keys, uint64_t key, uint64_t s, unsigned long long v)
+{
+    const unsigned int fp = rep_fp32(key);
+    while (v != 0ull) {
+        if ((unsigned int)(v >> 32) == fp) {
+            const int col = (int)(unsigned int)v - 1;
+            if (__ldg(sorted_keys + col) == key) return col;
+        }
+        if (++s == cap8) s = 0;
+        v = __ldg(table8 + s);
+    }
+    return -1;
+}
+
 // ------------------------------------------------------------------------------------------------ K5 without a k-mer stream
 // The super-k-mer count never materialises one 8-byte k-mer per window, so the probe re-derives the canonical k-mers
 // from the packed genome (0.375 B per base, L2 resident) with the roller instead of streaming 8 B per window from HBM.
 // Same structure as k_probe_stream_filt: persistent CTAs hold the bitmap filter in shared memory, ~2/3 of the windows
 // that are no repeat k-mers never leave the SM, the rest probes the 16-byte repeat-table slot in L2.
 // SMEMF: the bitmap lives in shared memory (loaded once per CTA); otherwise `bitmap` (may be null) is read through L2.
-template <int BATCH, int THREADS, bool SMEMF>
-__global__ void __launch_bounds__(THREADS, SMEMF ? 1024 / THREADS : 1)
+template <int BATCH, int THREADS, bool SMEMF, bool TABLE8>
+__global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 k_probe_roll_filt(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, int64_t n_words, int k,
                   const int64_t* __restrict__ chunk_word0, int64_t n_chunks, const int32_t* __restrict__ chunk_row,
                   const int64_t* __restrict__ row_hit_base, const RepSlot* __restrict__ rtable, uint64_t rcap,
                   const unsigned short* __restrict__ fp, const unsigned int* __restrict__ bitmap, unsigned int nbits,
+                  const unsigned long long* __restrict__ table8, uint64_t cap8, const uint64_t* __restrict__ sorted_keys,
                   int32_t* __restrict__ hits, unsigned int* __restrict__ row_cursor)
 {
     extern __shared__ __align__(16) unsigned int sbits[];
@@ -588,7 +626,7 @@ k_probe_roll_filt(const uint64_t* __restrict__ words, const uint32_t* __restrict
                     }
                     vmask |= (unsigned int)maybe << j;
                     skey[j] = ~key;
-                    slot[j] = rep_slot(key, rcap);
+                    slot[j] = rep_slot(key, TABLE8 ? cap8 : rcap);
                     if (b < 31) r.step(b);
                 }
                 if (!SMEMF && bitmap != nullptr) {               // L2-resident bitmap (repeat sets too large for shared memory)
@@ -602,7 +640,19 @@ k_probe_roll_filt(const uint64_t* __restrict__ words, const uint32_t* __restrict
                     for (int j = 0; j < BATCH; ++j)
                         if (!((wbits[j] >> (fb[j] & 31)) & 1u)) vmask &= ~(1u << j);
                 }
-                if (fp != nullptr) {                             // fingerprint-first walk (tables far beyond L2)
+                if (TABLE8) {                                    // compact 8-byte slots, verified against the key array
+                    unsigned long long v8[BATCH];
+#pragma unroll
+                    for (int j = 0; j < BATCH; ++j) v8[j] = ((vmask >> j) & 1u) ? __ldg(table8 + slot[j]) : 0ull;
+#pragma unroll
+                    for (int j = 0; j < BATCH; ++j) {
+                        cols[j] = 0;
+                        if (v8[j] == 0ull) continue;
+                        const int col = rep8_find(table8, cap8, sorted_keys, ~skey[j], slot[j], v8[j]);
+                        if (col >= 0) { cols[j] = col; hmask |= 1u << j; }
+                    }
+                    vmask = 0;
+                } else if (fp != nullptr) {                      // fingerprint-first walk (tables far beyond L2)
                     unsigned short f[BATCH];
 #pragma unroll
                     for (int j = 0; j < BATCH; ++j) f[j] = ((vmask >> j) & 1u) ? __ldg(fp + slot[j]) : (unsigned short)0;
@@ -630,7 +680,7 @@ k_probe_roll_filt(const uint64_t* __restrict__ words, const uint32_t* __restrict
                     cur[j] = ((vmask >> j) & 1u) ? __ldg(reinterpret_cast<const uint4*>(rtable + slot[j])) : make_uint4(0, 0, 0, 0);
 #pragma unroll
                 for (int j = 0; j < BATCH; ++j) {
-                    if (fp == nullptr) cols[j] = 0;
+                    if (fp == nullptr && !TABLE8) cols[j] = 0;
                     if (!((vmask >> j) & 1u)) continue;
                     unsigned long long ck = ((unsigned long long)cur[j].y << 32) | cur[j].x;
                     int col = (int)cur[j].z;

@@ -405,8 +405,17 @@ def test_probe_filters(ctx):
             ctx.tune(**kw)
             res, want = _check_against_c_oracle(ctx, seq, off, names, 20000, 23, 5)
             assert len(want["sel"]) > 1000
+        # no k-mer stream (super-k-mer count): the roller probe with the shared-memory bitmap, the L2 bitmap, the compact
+        # 8-byte-slot repeat table (verified against the key array), the fingerprint walk, and the plain round-1 kernel
+        for kw in (dict(), dict(probe_table8=1), dict(probe_filter=2), dict(probe_filter=2, probe_table8=0),
+                   dict(probe_filter=0, probe_table8=1), dict(probe_filter=0, probe_table8=0, probe_fp=1),
+                   dict(probe_filter=1, filter_bits=4096, probe_table8=1), dict(probe_roll=0)):
+            ctx.tune(part_mode=3, probe_mode=-1, probe_fp=-1, filter_bits=1310720, probe_filter=-1, probe_table8=-1, probe_roll=1)
+            ctx.tune(**kw)
+            res, want = _check_against_c_oracle(ctx, seq, off, names, 20000, 23, 5)
+            assert ctx.count_detail()["skm_records"] > 0
     finally:
-        ctx.tune(part_mode=-1, probe_filter=-1, probe_fp=-1, probe_mode=-1, filter_bits=1310720)
+        ctx.tune(part_mode=-1, probe_filter=-1, probe_fp=-1, probe_mode=-1, filter_bits=1310720, probe_table8=-1, probe_roll=1)
 
 
 def test_compact_handoff_matches_full_arrays(ctx):
@@ -797,6 +806,94 @@ def test_cfg2_full_size_parity(ctx):
     # global-table fall-back, never more than a fraction of a percent
     assert d["kind"] == "list" and d["skm_records"] > 50_000_000 and d["overflowed"] < d["sub_buckets"] // 500
     ctx.release(ctx.REL_BUCKETS | ctx.REL_TABLE | ctx.REL_STREAM | ctx.REL_HITS | ctx.REL_ASCII)   # 20 GB back for the next tests
+
+
+def _sampled_rows_match(ctx, seq, lay, scaffolds, chunk_row, k, sel, rng, n_sample=600):
+    """matrix of the current repeat set on the GPU against the oracle on a random sample of rows (bit-exact), and the
+    size-independent invariants on all rows"""
+    nnz = ctx.build_matrix(chunk_row, len(scaffolds))
+    indptr, indices, data = ctx.csr(len(scaffolds), nnz)
+    rows = np.sort(rng.choice(len(scaffolds), size=min(n_sample, len(scaffolds)), replace=False))
+    chunk_of_row = np.full(len(scaffolds), -1, np.int64)
+    chunk_of_row[chunk_row[chunk_row >= 0]] = np.flatnonzero(chunk_row >= 0)
+    w_indptr, w_indices, w_data = c_oracle.matrix(seq, lay.chunk_begin_abs, lay.chunk_end_abs, chunk_of_row[rows], k, sel)
+    for j, r in enumerate(rows.tolist()):
+        a, b = indptr[r], indptr[r + 1]
+        assert np.array_equal(indices[a:b], w_indices[w_indptr[j]:w_indptr[j + 1]]), r
+        assert np.array_equal(data[a:b], w_data[w_indptr[j]:w_indptr[j + 1]]), r
+    assert np.array_equal(ctx.df(len(sel)), np.bincount(indices, minlength=len(sel)))
+    return nnz
+
+
+def test_scale_1gbp_threshold_100_parity(ctx):
+    """BASELINE configs[2]/[3] regime on one GPU (the oracle would need minutes at 4.5 Gbp): a 1 Gbp genome of the cfg3
+    shape, k = 23, threshold 100.  Repeat set bit-exact against the C oracle; CSR bit-exact on 600 random rows for every
+    probe variant that only appears at scale (L2 bitmap, compact 8-byte table, fingerprint walk, forced level-1 width
+    pb = 10); then a threshold sweep (100 -> 300 -> 1000) on the kept count list, as rerun_threshold does per rank."""
+    cfg = synth.CONFIGS["cfg3_4.5Gbp_tobacco"]
+    p = synth.make_params(cfg["seed"], 1_000_000_000, n_subgenomes=cfg["n_subgenomes"])
+    seq, off, names = synth.generate(p, threads=8)
+    k, chunk = cfg["k"], cfg["chunk_size"]
+    lay = ChunkLayout(names, off, chunk)
+    scaffolds, chunk_row = lay.rows()
+    rng = np.random.default_rng(1)
+    want_keys, want_counts, n_windows = c_oracle.count(seq, lay.chunk_begin_abs, lay.chunk_end_abs, k)
+    try:
+        ctx.tune(part_mode=-1, smem_pb=10, keep_min=3)
+        ctx.load_sequences(seq, lay.chunk_begin_abs, lay.chunk_end_abs)
+        ctx.count(k)
+        info, d = ctx.count_info(), ctx.count_detail()
+        assert info["valid_windows"] == n_windows > 990_000_000 and info["distinct"] == len(want_keys)
+        assert d["skm_records"] > 100_000_000 and info["partition_bits"] == 10 and not ctx.count_flags()["could_wrap"]
+        for low, variants in ((100, (dict(), dict(probe_table8=1), dict(probe_filter=0, probe_table8=0, probe_fp=1), dict(probe_filter=2, probe_table8=0))),
+                              (300, (dict(),)), (1000, (dict(),))):
+            sel = c_oracle.select(want_keys, want_counts, k, low)
+            for kw in variants:
+                ctx.tune(probe_filter=-1, probe_table8=-1, probe_fp=-1)
+                ctx.tune(**kw)
+                n_sel = ctx.select(low)                            # (re)builds the look-up structures for this variant
+                assert n_sel == len(sel) and np.array_equal(ctx.selected(n_sel), sel)
+                nnz = _sampled_rows_match(ctx, seq, lay, scaffolds, chunk_row, k, sel, rng)
+            assert len(sel) > 1000 and nnz > 1_000_000
+    finally:
+        ctx.tune(part_mode=-1, smem_pb=0, keep_min=1, probe_filter=-1, probe_table8=-1, probe_fp=-1)
+        ctx.release(ctx.REL_BUCKETS | ctx.REL_TABLE | ctx.REL_STREAM | ctx.REL_HITS | ctx.REL_ASCII)
+
+
+@pytest.mark.parametrize("k", [15, 31])
+def test_k_sweep_300mbp_parity(ctx, k):
+    """BASELINE configs[4] (k = 15 / 31 next to the k = 23 of the other tests) at 300 Mbp: k = 15 takes the k-mer partition
+    (4^15 / 2 distinct k-mers at most), k = 31 the super-k-mer one with the longest minimizer window; counts of everything
+    the reference's counter would dump (>= 3), repeat set and 600 sampled CSR rows bit-exact, TF-IDF rows unit length."""
+    p = synth.make_params(20260005, 300_000_000)
+    seq, off, names = synth.generate(p, threads=8)
+    chunk, low = 75000, 100
+    lay = ChunkLayout(names, off, chunk)
+    scaffolds, chunk_row = lay.rows()
+    want_keys, want_counts, n_windows = c_oracle.count(seq, lay.chunk_begin_abs, lay.chunk_end_abs, k)
+    try:
+        ctx.tune(keep_min=3)
+        ctx.load_sequences(seq, lay.chunk_begin_abs, lay.chunk_end_abs)
+        ctx.count(k)
+        info, d = ctx.count_info(), ctx.count_detail()
+        assert info["valid_windows"] == n_windows and info["distinct"] == len(want_keys)
+        assert (d["skm_m"] > 0) == (k >= 17)
+        keys, counts = ctx.dump_counts(3)
+        order = np.argsort(keys)
+        m = want_counts >= 3
+        assert np.array_equal(keys[order], want_keys[m]) and np.array_equal(counts[order].astype(np.uint64), want_counts[m])
+        sel = c_oracle.select(want_keys, want_counts, k, low)
+        n_sel = ctx.select(low)
+        assert np.array_equal(ctx.selected(n_sel), sel) and n_sel > 100
+        nnz = _sampled_rows_match(ctx, seq, lay, scaffolds, chunk_row, k, sel, np.random.default_rng(k))
+        ctx.tfidf(len(scaffolds))
+        indptr, _, _ = ctx.csr(len(scaffolds), nnz)
+        tf = ctx.tfidf_values(nnz).astype(np.float64)
+        norms = np.sqrt(np.add.reduceat(tf * tf, indptr[:-1][np.diff(indptr) > 0]))
+        np.testing.assert_allclose(norms, 1.0, rtol=1e-6)
+    finally:
+        ctx.tune(keep_min=1)
+        ctx.release(ctx.REL_BUCKETS | ctx.REL_TABLE | ctx.REL_STREAM | ctx.REL_HITS | ctx.REL_ASCII)
 
 
 def test_properties_at_scale(ctx):
