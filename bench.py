@@ -106,7 +106,7 @@ class ClockSampler:
                                              {n for n, b in names.items() if bits & b}))
                     except Exception:
                         pass
-                    time.sleep(0.1)
+                    time.sleep(0.2)
             threading.Thread(target=loop, daemon=True).start()
             self.how = "nvml"
             return
@@ -447,7 +447,10 @@ def run_b200_arm(args):
                                                 fetch=False, staged=(dev_src, ids, begins, ends),
                                                 exchange=os.environ.get("PC_EXCHANGE", "auto"))
 
+        e2e_wall = []
+
         def piped(n_steps):
+            del e2e_wall[:]
             gc.disable()
             try:
                 barrier()
@@ -456,10 +459,12 @@ def run_b200_arm(args):
                 pipe.prefetch(host_in)
                 out = None
                 for i in range(n_steps):
+                    t_s = time.perf_counter()
                     if i + 1 < n_steps:
                         pipe.prefetch(host_in)
                     got = pipe.step(run_dev)
                     out = got if got is not None else out
+                    e2e_wall.append((time.perf_counter() - t_s) * 1e3)
                 last = pipe.flush()
                 e1.record()
                 barrier()
@@ -488,8 +493,8 @@ def run_b200_arm(args):
                "sequential_ms_per_step": ms_lat / args.steps,
                "sequential_value": genome_bases / (ms_lat / args.steps * 1e-3) / 1e9,
                "note": "K back-to-back steps through the public API, host buffers: pinned host genome -> H2D -> "
-                       "pc_load_sequences ... pc_csr_get16/pc_tfidf_factors_get -> D2H into pinned host memory, every step "
-                       "(compact hand-off: int32 column ids + uint16 counts + idf + row norms, 6 B per entry; the float32 "
+                       "pc_load_sequences ... pc_csr_get8/pc_tfidf_factors_get -> D2H into pinned host memory, every step "
+                       "(compact hand-off: one byte per column gap + one per count + escape lists + idf + row norms, ~2 B per entry; the int32 / float32 "
                        "count / tf-idf arrays are rebuilt on the host bit for bit, outside the timed region); copies "
                        "of neighbouring steps overlap this step's kernels (StepPipeline).  sequential_* = the same "
                        "with nothing overlapped (latency of one call)" + ("; bytes per rank" if world > 1 else "")}
@@ -584,7 +589,8 @@ def run_b200_arm(args):
                                        "all-gather of the repeat set, all-reduce of df" % world)},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "parity_check": parity,
             "gpu_launches": int(launches),
-            "numa_binding_rank0": numa, "clocks": clocks, "step_wall_ms": [round(x, 2) for x in step_wall], "quiet_gpu_wait_s": round(quiet_wait, 2),
+            "numa_binding_rank0": numa, "clocks": clocks, "step_wall_ms": [round(x, 2) for x in step_wall],
+            "e2e_step_wall_ms": [round(x, 2) for x in (e2e_wall if not args.no_e2e else [])], "quiet_gpu_wait_s": round(quiet_wait, 2),
             "result": {"distinct_kmers_rank0": info["distinct"], "valid_windows_rank0": info["valid_windows"],
                        "shared_tables": detail.get("sub_buckets"), "shared_table_slots": info["capacity"] // max(1, detail.get("sub_buckets") or 1),
                        "mean_shared_table_load": info["distinct"] / max(1, info["capacity"]),

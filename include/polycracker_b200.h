@@ -198,6 +198,13 @@ int pc_df_get(pc_ctx* ctx, int32_t* df, int loc);                      /* stored
  * patched in). */
 int pc_csr_get16(pc_ctx* ctx, int64_t* indptr, int32_t* indices, uint16_t* data16, int loc, int64_t* n_escapes);
 int pc_csr_escapes_get(pc_ctx* ctx, int64_t* pos, float* val, int loc);
+/* Densest hand-off, 2 bytes per entry: dcol8[i] = column(i) - column(i - 1) inside a row and cnt8[i] = count, one byte each;
+ * 255 marks an escape -- the first entry of every row and every gap >= 255 carry their ABSOLUTE column in the column escape
+ * list, counts >= 255 their value in the count escape list (positions index the CSR arrays; lists are unordered).
+ * n_escapes[0] / [1] = entries of the two lists, fetched with pc_csr_escapes8_get.  pipeline.rebuild_indices / rebuild_counts
+ * restore the int32 / float32 arrays on the host. */
+int pc_csr_get8(pc_ctx* ctx, int64_t* indptr, uint8_t* dcol8, uint8_t* cnt8, int loc, int64_t n_escapes[2]);
+int pc_csr_escapes8_get(pc_ctx* ctx, int64_t* col_pos, int32_t* col_val, int64_t* cnt_pos, float* cnt_val, int loc);
 
 /* ---- K7  TF-IDF + L2 rows (replaces sklearn TfidfTransformer().fit_transform, polycracker.py:395-396) -------
  * idf_j = ln((1+n)/(1+df_j)) + 1 in float32; rows divided by their L2 norm (double accumulation), zero rows

@@ -113,6 +113,8 @@ _SIGS = {
     "pc_df_get": (C.c_int, [_vp, _vp, C.c_int]),
     "pc_csr_get16": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _P(_i64)]),
     "pc_csr_escapes_get": (C.c_int, [_vp, _vp, _vp, C.c_int]),
+    "pc_csr_get8": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "pc_csr_escapes8_get": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int]),
     "pc_tfidf_factors_get": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "pc_tfidf": (C.c_int, [_vp, _i64, _vp, C.c_int]),
     "pc_tfidf_get": (C.c_int, [_vp, _vp, C.c_int]),
@@ -681,6 +683,34 @@ class Context:
         check(lib.pc_csr_get16(self._h, ptr(indptr)[0], ptr(indices)[0], ptr(data16)[0], locs.pop() if locs else PC_HOST,
                                C.byref(n)), "pc_csr_get16")
         return n.value
+
+    def csr8_into(self, indptr=None, dcol8=None, cnt8=None):
+        """Densest hand-off (2 bytes per entry).  -> (column escapes, count escapes) counts; see csr8_escapes."""
+        locs = {ptr(x)[1] for x in (indptr, dcol8, cnt8) if x is not None}
+        if len(locs) > 1:
+            raise ValueError("all CSR outputs must live in the same place")
+        n = np.zeros(2, np.int64)
+        check(lib.pc_csr_get8(self._h, ptr(indptr)[0], ptr(dcol8)[0], ptr(cnt8)[0], locs.pop() if locs else PC_HOST,
+                              n.ctypes.data), "pc_csr_get8")
+        return int(n[0]), int(n[1])
+
+    def csr8_escapes(self, n_col, n_cnt):
+        """-> ((positions int64, absolute columns int32), (positions int64, counts float32))"""
+        cp, cv = np.empty(n_col, np.int64), np.empty(n_col, np.int32)
+        kp, kv = np.empty(n_cnt, np.int64), np.empty(n_cnt, np.float32)
+        if n_col or n_cnt:
+            check(lib.pc_csr_escapes8_get(self._h, cp.ctypes.data, cv.ctypes.data, kp.ctypes.data, kv.ctypes.data, PC_HOST),
+                  "pc_csr_escapes8_get")
+        return (cp, cv), (kp, kv)
+
+    def csr8_escapes_into(self, col_pos, col_val, cnt_pos, cnt_val):
+        """Escape lists of the last csr8_into into caller buffers (torch tensors on the device: a device-to-device copy on
+        the context stream, so a pipeline can move them to the host with its other bulk copies)."""
+        locs = {ptr(x)[1] for x in (col_pos, col_val, cnt_pos, cnt_val) if x is not None}
+        if len(locs) > 1:
+            raise ValueError("all escape buffers must live in the same place")
+        check(lib.pc_csr_escapes8_get(self._h, ptr(col_pos)[0], ptr(col_val)[0], ptr(cnt_pos)[0], ptr(cnt_val)[0],
+                                      locs.pop() if locs else PC_HOST), "pc_csr_escapes8_get")
 
     def csr_escapes(self, n):
         pos = np.empty(n, np.int64); val = np.empty(n, np.float32)

@@ -108,6 +108,8 @@ struct pc_ctx {
     DevBuf<int32_t> d_indices; DevBuf<float> d_data, d_idf, d_tfidf; DevBuf<int> d_df, d_df_global;
     DevBuf<double> d_row_norm; DevBuf<unsigned short> d_data16; DevBuf<int64_t> d_esc_pos; DevBuf<float> d_esc_val;
     int64_t n_esc = -1;                          // escapes of the last pc_csr_get16 (-1: none taken)
+    DevBuf<unsigned char> d_dcol8, d_cnt8; DevBuf<int64_t> d_esc8_pos; DevBuf<int32_t> d_esc8_val;
+    int64_t n_esc8_col = -1, n_esc8_cnt = -1, esc8_col_cap = 0;    // escapes of the last pc_csr_get8
     int64_t n_rows = 0, nnz = 0;
     bool built = false, tfidf_done = false, scaled_done = false;
     DevBuf<float> d_scaled; DevBuf<double> d_colstat, d_rowscale;   // N3: StandardScaler(with_mean=False) values
@@ -397,6 +399,7 @@ int pc_destroy(pc_ctx* c) {
     c->hits_b.release(); c->d_row_nnz.release(); c->d_indptr.release(); c->d_indices.release();
     c->d_data.release(); c->d_idf.release(); c->d_tfidf.release(); c->d_df.release(); c->d_df_global.release();
     c->d_row_norm.release(); c->d_data16.release(); c->d_esc_pos.release(); c->d_esc_val.release();
+    c->d_dcol8.release(); c->d_cnt8.release(); c->d_esc8_pos.release(); c->d_esc8_val.release();
     c->sub_clear();
     for (int i = 0; i < ST_N; ++i) { cudaEventDestroy(c->ev[i][0]); cudaEventDestroy(c->ev[i][1]); }
     if (c->mailbox) cudaFreeHost(c->mailbox);
@@ -2081,7 +2084,7 @@ int pc_build_matrix(pc_ctx* c, const int32_t* chunk_row, int64_t n_rows, int64_t
     if (!c->loaded || !c->selected) return fail(PC_ESTATE, "pc_build_matrix needs loaded sequences and a repeat set");
     if (n_rows < 0 || (c->n_chunks > 0 && !chunk_row)) return fail(PC_EINVAL, "bad build_matrix arguments");
     if (n_rows > 0x7FFFFFFF) return fail(PC_EINVAL, "too many rows");
-    c->built = c->tfidf_done = false; c->n_esc = -1;
+    c->built = c->tfidf_done = false; c->n_esc = -1; c->n_esc8_col = c->n_esc8_cnt = -1;
     const int k = c->k;
     std::vector<int64_t> row_base(n_rows + 1, 0), row_windows(std::max<int64_t>(n_rows, 1), -1);
     for (int64_t i = 0; i < c->n_chunks; ++i) {
@@ -2255,6 +2258,57 @@ int pc_csr_get16(pc_ctx* c, int64_t* indptr, int32_t* indices, uint16_t* data16,
     if ((int64_t)ne > esc_cap) return fail(PC_ESTATE, "%llu matrix entries >= 65535 for %lld escape slots", ne, (long long)esc_cap);
     c->n_esc = (int64_t)ne;
     *n_escapes = c->n_esc;
+    return PC_OK;
+}
+
+// densest hand-off: 2 bytes per entry (column gap + count, one byte each) + escape lists
+int pc_csr_get8(pc_ctx* c, int64_t* indptr, uint8_t* dcol8, uint8_t* cnt8, int loc, int64_t n_escapes[2]) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!c->built) return fail(PC_ESTATE, "no matrix built");
+    if (!n_escapes) return fail(PC_EINVAL, "n_escapes is null");
+    StageTimer t(c, ST_D2H);
+    // column escapes: the first entry of every row + gaps >= 255 (at most n_selected / 255 per row); count escapes: entries
+    // >= 255 (a k-mer that fills >= 255 windows of one chunk)
+    // (sized so that they cannot overflow: low-complexity genomes put a count >= 255 into most entries)
+    const int64_t col_cap = c->n_rows * (1 + c->n_sel / 255) + 16, cnt_cap = c->nnz + 16;
+    const int64_t col_cap_used = std::min<int64_t>(col_cap, c->nnz + 16);
+    rc = c->d_dcol8.alloc(std::max<int64_t>(c->nnz, 1)); if (rc) return rc;
+    rc = c->d_cnt8.alloc(std::max<int64_t>(c->nnz, 1)); if (rc) return rc;
+    rc = c->d_esc8_pos.alloc(col_cap_used); if (rc) return rc;
+    rc = c->d_esc8_val.alloc(col_cap_used); if (rc) return rc;
+    rc = c->d_esc_pos.alloc(cnt_cap); if (rc) return rc;
+    rc = c->d_esc_val.alloc(cnt_cap); if (rc) return rc;
+    unsigned long long ne[2] = {0, 0};
+    CU(cudaMemsetAsync(c->d_counter.p + 8, 0, 2 * sizeof(unsigned long long), c->stream));
+    if (c->nnz > 0 && c->n_rows > 0)
+        LAUNCH(c, (pc::k_csr_pack8<256>), (unsigned int)c->n_rows, 256, c->d_indptr.p, c->d_indices.p, c->d_data.p, c->d_dcol8.p,
+               c->d_cnt8.p, c->d_counter.p + 8, c->d_esc8_pos.p, c->d_esc8_val.p, (unsigned long long)col_cap_used, c->d_esc_pos.p,
+               c->d_esc_val.p, (unsigned long long)cnt_cap);
+    READ_SMALL(c, ne, c->d_counter.p + 8, sizeof ne);
+    if (indptr) { rc = copy_out(c, indptr, c->d_indptr.p, (c->n_rows + 1) * sizeof(int64_t), loc); if (rc) return rc; }
+    if (dcol8) { rc = copy_out(c, dcol8, c->d_dcol8.p, c->nnz, loc); if (rc) return rc; }
+    if (cnt8) { rc = copy_out(c, cnt8, c->d_cnt8.p, c->nnz, loc); if (rc) return rc; }
+    SYNC(c);
+    if ((int64_t)ne[0] > col_cap_used || (int64_t)ne[1] > cnt_cap)
+        return fail(PC_ESTATE, "escape lists of the 8-bit hand-off overflow (%llu columns, %llu counts): use pc_csr_get16", ne[0], ne[1]);
+    c->n_esc8_col = (int64_t)ne[0]; c->n_esc8_cnt = (int64_t)ne[1]; c->n_esc = (int64_t)ne[1];
+    n_escapes[0] = c->n_esc8_col; n_escapes[1] = c->n_esc8_cnt;
+    return PC_OK;
+}
+
+int pc_csr_escapes8_get(pc_ctx* c, int64_t* col_pos, int32_t* col_val, int64_t* cnt_pos, float* cnt_val, int loc) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!c->built || c->n_esc8_col < 0) return fail(PC_ESTATE, "pc_csr_escapes8_get before pc_csr_get8");
+    if (c->n_esc8_col > 0) {
+        if (!col_pos || !col_val) return fail(PC_EINVAL, "null column escape buffers");
+        rc = copy_out(c, col_pos, c->d_esc8_pos.p, c->n_esc8_col * sizeof(int64_t), loc); if (rc) return rc;
+        rc = copy_out(c, col_val, c->d_esc8_val.p, c->n_esc8_col * sizeof(int32_t), loc); if (rc) return rc;
+    }
+    if (c->n_esc8_cnt > 0) {
+        if (!cnt_pos || !cnt_val) return fail(PC_EINVAL, "null count escape buffers");
+        rc = copy_out(c, cnt_pos, c->d_esc_pos.p, c->n_esc8_cnt * sizeof(int64_t), loc); if (rc) return rc;
+        rc = copy_out(c, cnt_val, c->d_esc_val.p, c->n_esc8_cnt * sizeof(float), loc); if (rc) return rc;
+    }
     return PC_OK;
 }
 

@@ -115,7 +115,6 @@ class StepPipeline:
             main.wait_event(self.snap_free[slot])
         d_keys = self._dev(slot, "keys", n_sel, torch.int64)
         d_indptr = self._dev(slot, "indptr", n_rows + 1, torch.int64)
-        d_indices = self._dev(slot, "indices", nnz, torch.int32)
         d_df = self._dev(slot, "df", n_sel, torch.int32)
         if n_sel:
             self.ctx.selected_into(d_keys)
@@ -123,11 +122,19 @@ class StepPipeline:
                 self.ctx.df_into(d_df)
             else:
                 d_df.copy_(df[:n_sel])
-        # compact hand-off (pc_csr_get16 / pc_tfidf_factors_get): counts as uint16, idf + row norms instead of the tf-idf
-        # array -- 6 bytes per matrix entry cross PCIe instead of 12; the host rebuilds the float32 arrays bit for bit
-        d_data = self._dev(slot, "data16", nnz, torch.int16)                  # 2-byte container for uint16
-        n_esc = self.ctx.csr16_into(d_indptr, d_indices if nnz else None, d_data if nnz else None)
-        escapes = self.ctx.csr_escapes(n_esc) if n_esc else None             # a handful of entries, read back at once
+        # densest hand-off (pc_csr_get8 / pc_tfidf_factors_get): one byte per column gap, one per count, idf + row norms
+        # instead of the tf-idf array -- 2 bytes per matrix entry cross PCIe instead of 12; the host rebuilds the int32 /
+        # float32 arrays bit for bit (HotPathResult.indices / .data / .tfidf)
+        d_dcol = self._dev(slot, "dcol8", nnz, torch.uint8)
+        d_cnt = self._dev(slot, "cnt8", nnz, torch.uint8)
+        n_col, n_cnt = self.ctx.csr8_into(d_indptr, d_dcol if nnz else None, d_cnt if nnz else None)
+        # the escape lists (a few MB) leave with the bulk copies on the copy-out stream: a host-synchronous read here would
+        # queue on the copy engine behind the previous step's D2H and stall the pipeline
+        d_ecp, d_ecv = self._dev(slot, "esc_col_pos", n_col, torch.int64), self._dev(slot, "esc_col_val", n_col, torch.int32)
+        d_ekp, d_ekv = self._dev(slot, "esc_cnt_pos", n_cnt, torch.int64), self._dev(slot, "esc_cnt_val", n_cnt, torch.float32)
+        if n_col or n_cnt:
+            self.ctx.csr8_escapes_into(d_ecp if n_col else None, d_ecv if n_col else None, d_ekp if n_cnt else None,
+                                       d_ekv if n_cnt else None)
         d_idf = d_norm = None
         if tfidf:
             d_idf = self._dev(slot, "idf", n_sel, torch.float32)
@@ -138,24 +145,26 @@ class StepPipeline:
         # D2H on the copy-out stream into this slot's page-locked arena
         a = self.arena[slot]
         h = dict(keys=a.get("keys", n_sel, np.uint64), indptr=a.get("indptr", n_rows + 1, np.int64),
-                 indices=a.get("indices", nnz, np.int32), data16=a.get("data16", nnz, np.uint16),
+                 dcol8=a.get("dcol8", nnz, np.uint8), cnt8=a.get("cnt8", nnz, np.uint8),
                  idf=a.get("idf", n_sel, np.float32) if tfidf else None,
-                 row_norm=a.get("row_norm", n_rows, np.float64) if tfidf else None, df=a.get("df", n_sel, np.int32))
+                 row_norm=a.get("row_norm", n_rows, np.float64) if tfidf else None, df=a.get("df", n_sel, np.int32),
+                 esc_col_pos=a.get("esc_col_pos", n_col, np.int64), esc_col_val=a.get("esc_col_val", n_col, np.int32),
+                 esc_cnt_pos=a.get("esc_cnt_pos", n_cnt, np.int64), esc_cnt_val=a.get("esc_cnt_val", n_cnt, np.float32))
         with torch.cuda.stream(self.s_d2h):
             self.s_d2h.wait_event(ev)
-            for name, src in (("keys", d_keys), ("indptr", d_indptr), ("indices", d_indices), ("data16", d_data),
-                              ("idf", d_idf), ("row_norm", d_norm), ("df", d_df)):
+            for name, src in (("keys", d_keys), ("indptr", d_indptr), ("dcol8", d_dcol), ("cnt8", d_cnt),
+                              ("idf", d_idf), ("row_norm", d_norm), ("df", d_df), ("esc_col_pos", d_ecp),
+                              ("esc_col_val", d_ecv), ("esc_cnt_pos", d_ekp), ("esc_cnt_val", d_ekv)):
                 if src is None or src.numel() == 0:
                     continue
-                view = {"keys": np.int64, "data16": np.int16}.get(name)
-                dst = torch.from_numpy(h[name].view(view) if view else h[name])
+                dst = torch.from_numpy(h[name].view(np.int64) if name == "keys" else h[name])
                 self._copy_pieces(dst, src)
                 self.d2h_bytes += src.numel() * src.element_size()
             done = torch.cuda.Event()
             done.record(self.s_d2h)
         self.snap_free[slot] = done
         previous = self._collect()
-        self.pending = (done, res, h, escapes)
+        self.pending = (done, res, h)
         self.n_steps += 1
         return previous
 
@@ -164,12 +173,13 @@ class StepPipeline:
         until the step() after next reuses the slot (depth = 2) -- copy what must live longer."""
         if self.pending is None:
             return None
-        done, res, h, escapes = self.pending
+        done, res, h = self.pending
         done.synchronize()
         self.pending = None
-        return HotPathResult(res.layout, res.k, res.scaffolds, h["keys"], h["indptr"], h["indices"], None, None, h["df"],
-                             res.stats, res.timings, data16=h["data16"], escapes=escapes, idf=h["idf"],
-                             row_norm=h["row_norm"])
+        escapes8 = ((h["esc_col_pos"], h["esc_col_val"]), (h["esc_cnt_pos"], h["esc_cnt_val"]))
+        return HotPathResult(res.layout, res.k, res.scaffolds, h["keys"], h["indptr"], None, None, None, h["df"],
+                             res.stats, res.timings, idf=h["idf"], row_norm=h["row_norm"], dcol8=h["dcol8"], cnt8=h["cnt8"],
+                             escapes8=escapes8)
 
     def flush(self):
         """Host result of the last step."""

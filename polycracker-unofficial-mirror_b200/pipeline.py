@@ -71,6 +71,31 @@ def rebuild_counts(data16, escapes=None):
     return data
 
 
+def rebuild_indices(indptr, dcol8, col_escapes):
+    """int32 column ids from the one-byte gaps of pc_csr_get8: an escape (first entry of a row, gap >= 255) carries its
+    absolute column, every other entry adds its gap to the entry before it."""
+    d = np.asarray(dcol8).view(np.uint8).astype(np.int64)
+    n = len(d)
+    if n == 0:
+        return np.zeros(0, np.int32)
+    pos, val = np.asarray(col_escapes[0], np.int64), np.asarray(col_escapes[1], np.int64)
+    is_esc = np.zeros(n, bool)
+    is_esc[pos] = True
+    d[pos] = 0
+    c = np.cumsum(d)
+    absval = np.zeros(n, np.int64)
+    absval[pos] = val
+    last = np.maximum.accumulate(np.where(is_esc, np.arange(n), 0))      # entry 0 starts a row, so it is an escape
+    return (c - c[last] + absval[last]).astype(np.int32)
+
+
+def rebuild_counts8(cnt8, cnt_escapes):
+    data = np.asarray(cnt8).view(np.uint8).astype(np.float32)
+    if cnt_escapes is not None and len(cnt_escapes[0]):
+        data[np.asarray(cnt_escapes[0])] = np.asarray(cnt_escapes[1], dtype=np.float32)
+    return data
+
+
 def rebuild_tfidf(indptr, indices, data, idf, row_norm):
     """TF-IDF values from the two vectors they are a function of, with the kernel's own arithmetic (k_tfidf: one float32
     multiply, the float32 product divided by the row norm in double and rounded once; rows with norm 0 untouched) --
@@ -90,19 +115,28 @@ class HotPathResult:
     hand-off.  Views into a StepPipeline arena are valid until the pipeline's next step() -- copy what must live longer."""
 
     def __init__(self, layout, k, scaffolds, kmer_keys, indptr, indices, data, tfidf, df=None, stats=None, timings=None,
-                 data16=None, escapes=None, idf=None, row_norm=None):
+                 data16=None, escapes=None, idf=None, row_norm=None, dcol8=None, cnt8=None, escapes8=None):
         self.layout, self.k, self.scaffolds, self.kmer_keys = layout, k, scaffolds, kmer_keys
-        self.indptr, self.indices = indptr, indices           # CSR of raw counts (numpy, or torch CUDA tensors)
+        self.indptr, self._indices = indptr, indices          # CSR of raw counts (numpy, or torch CUDA tensors)
         self._data, self._tfidf = data, tfidf
         self.df = df
         self.stats = {} if stats is None else stats
         self.timings = {} if timings is None else timings
         self.data16, self.escapes, self.idf, self.row_norm = data16, escapes, idf, row_norm
+        self.dcol8, self.cnt8, self.escapes8 = dcol8, cnt8, escapes8      # 2-byte hand-off (pc_csr_get8)
+
+    @property
+    def indices(self):
+        if self._indices is None and self.dcol8 is not None:
+            self._indices = rebuild_indices(self.indptr, self.dcol8, self.escapes8[0])
+        return self._indices
 
     @property
     def data(self):
         if self._data is None and self.data16 is not None:
             self._data = rebuild_counts(self.data16, self.escapes)
+        if self._data is None and self.cnt8 is not None:
+            self._data = rebuild_counts8(self.cnt8, self.escapes8[1])
         return self._data
 
     @property
@@ -207,12 +241,13 @@ def run_hot_path(ctx, seq, seq_offsets, names, chunk_size=75000, k=23, kmer_low_
 
 
 def fetch_result(ctx, layout, k, scaffolds, n_sel, nnz, tfidf, stats, arena=None, df=None, compact=True):
-    """D2H of the repeat set and the matrix (into page-locked buffers when an arena is given).  compact (default): counts
-    as uint16 + escapes, and idf + row norms instead of the tf-idf array -- 6 bytes per entry instead of 12; the float32
-    arrays are rebuilt on the host on first use (HotPathResult.data / .tfidf), bit-identical.  compact=False reads the
-    float32 arrays themselves (pc_csr_get / pc_tfidf_get)."""
+    """D2H of the repeat set and the matrix (into page-locked buffers when an arena is given).  compact=True (default): one
+    byte per column gap and one per count plus escape lists (pc_csr_get8), and idf + row norms instead of the tf-idf array
+    -- 2 bytes per entry instead of 12; compact=16: int32 columns + uint16 counts (6 bytes).  The int32 / float32 arrays are
+    rebuilt on the host on first use (HotPathResult.indices / .data / .tfidf), bit-identical.  compact=False reads the
+    arrays themselves (pc_csr_get / pc_tfidf_get)."""
     n_rows = len(scaffolds)
-    compact = compact and hasattr(ctx, "csr16_into")         # (test stand-ins of the context only know the plain getters)
+    compact = compact if hasattr(ctx, "csr8_into") else False   # (test stand-ins of the context only know the plain getters)
     if not hasattr(ctx, "csr_into"):
         keys = ctx.selected(n_sel)
         indptr, indices, data = ctx.csr(n_rows, nnz)
@@ -224,7 +259,7 @@ def fetch_result(ctx, layout, k, scaffolds, n_sel, nnz, tfidf, stats, arena=None
 
     keys = buf("keys", n_sel, np.uint64)
     indptr = buf("indptr", n_rows + 1, np.int64)
-    indices = buf("indices", nnz, np.int32)
+    indices = buf("indices", nnz, np.int32) if compact in (False, 16) else None
     if n_sel:
         ctx.selected_into(keys)
     if df is None:
@@ -240,13 +275,18 @@ def fetch_result(ctx, layout, k, scaffolds, n_sel, nnz, tfidf, stats, arena=None
             if nnz:
                 ctx.tfidf_into(tf)
         return HotPathResult(layout, k, scaffolds, keys, indptr, indices, data, tf, df, stats, ctx.timings())
-    data16 = buf("data16", nnz, np.uint16)
-    n_esc = ctx.csr16_into(indptr, indices if nnz else None, data16 if nnz else None)
-    escapes = ctx.csr_escapes(n_esc) if n_esc else None
     idf = row_norm = None
     if tfidf:
         idf = buf("idf", n_sel, np.float32)
         row_norm = buf("row_norm", n_rows, np.float64)
         ctx.tfidf_factors_into(idf if n_sel else None, row_norm if n_rows else None)
-    return HotPathResult(layout, k, scaffolds, keys, indptr, indices, None, None, df, stats, ctx.timings(),
-                         data16=data16, escapes=escapes, idf=idf, row_norm=row_norm)
+    if compact == 16:
+        data16 = buf("data16", nnz, np.uint16)
+        n_esc = ctx.csr16_into(indptr, indices if nnz else None, data16 if nnz else None)
+        escapes = ctx.csr_escapes(n_esc) if n_esc else None
+        return HotPathResult(layout, k, scaffolds, keys, indptr, indices, None, None, df, stats, ctx.timings(),
+                             data16=data16, escapes=escapes, idf=idf, row_norm=row_norm)
+    dcol8, cnt8 = buf("dcol8", nnz, np.uint8), buf("cnt8", nnz, np.uint8)
+    n_col, n_cnt = ctx.csr8_into(indptr, dcol8 if nnz else None, cnt8 if nnz else None)
+    return HotPathResult(layout, k, scaffolds, keys, indptr, None, None, None, df, stats, ctx.timings(), idf=idf,
+                         row_norm=row_norm, dcol8=dcol8, cnt8=cnt8, escapes8=ctx.csr8_escapes(n_col, n_cnt))

@@ -419,16 +419,23 @@ def test_probe_filters(ctx):
 
 
 def test_compact_handoff_matches_full_arrays(ctx):
-    """What crosses PCIe in the end-to-end path (pc_csr_get16 + escapes, pc_tfidf_factors_get: 6 bytes per entry) rebuilds
-    on the host to exactly the float32 arrays of pc_csr_get / pc_tfidf_get (12 bytes per entry) -- bit for bit, including a
-    count >= 65535 (a poly-A chunk of 70 000 windows) that does not fit uint16 and an all-N row with norm 0."""
+    """What crosses PCIe in the end-to-end path (pc_csr_get8: one byte per column gap and per count + escapes, 2 bytes per
+    entry; or pc_csr_get16: 6 bytes; both with pc_tfidf_factors_get) rebuilds on the host to exactly the int32 / float32 arrays
+    of pc_csr_get / pc_tfidf_get (12 bytes per entry) -- bit for bit, including a count >= 65535 (a poly-A chunk of 70 000
+    windows), column gaps >= 255, and an all-N row with norm 0."""
     p = synth.small_params(seed=77, genome_size=600_000)
     seq, off, names = synth.generate(p)
     seqs = util.to_sequences(seq, off, names) + [("polyA", "A" * 70000), ("allN", "N" * 70000), ("at", "AT" * 35000)]
     seq, off, names = util.from_sequences(seqs)
     for k, chunk in ((23, 70000), (31, 20000)):
         full = run_hot_path(ctx, seq, off, names, chunk_size=chunk, k=k, kmer_low_count=5, remove_non_chunk=0, compact=False)
-        comp = run_hot_path(ctx, seq, off, names, chunk_size=chunk, k=k, kmer_low_count=5, remove_non_chunk=0, compact=True)
+        comp = run_hot_path(ctx, seq, off, names, chunk_size=chunk, k=k, kmer_low_count=5, remove_non_chunk=0, compact=16)
+        c8 = run_hot_path(ctx, seq, off, names, chunk_size=chunk, k=k, kmer_low_count=5, remove_non_chunk=0, compact=True)
+        assert c8.dcol8.dtype == np.uint8 and c8.cnt8.dtype == np.uint8 and c8._indices is None and c8._data is None
+        assert np.array_equal(c8.indptr, full.indptr) and np.array_equal(c8.indices, full.indices) and c8.indices.dtype == np.int32
+        assert np.array_equal(c8.data, full.data) and np.array_equal(c8.tfidf.view(np.uint32), full.tfidf.view(np.uint32))
+        assert len(c8.escapes8[0][0]) >= (np.diff(full.indptr) > 0).sum()   # every non-empty row starts with an absolute column
+        assert (np.asarray(c8.cnt8) == 255).sum() == len(c8.escapes8[1][0]) == (full.data >= 255).sum()
         assert comp.data16 is not None and comp.data16.dtype == np.uint16 and full.data16 is None
         assert np.array_equal(comp.indptr, full.indptr) and np.array_equal(comp.indices, full.indices)
         assert np.array_equal(comp.kmer_keys, full.kmer_keys) and np.array_equal(comp.df, full.df)
