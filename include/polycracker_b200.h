@@ -259,6 +259,14 @@ int pc_sub_mapback(pc_ctx* ctx, int32_t* coverage, int loc);
 int pc_standard_scale(pc_ctx* ctx, const double* row_scale, int loc);
 int pc_scaled_get(pc_ctx* ctx, float* data, int loc);
 
+/* ---- N3, second half: the Gram matrix X X^T that KernelPCA(kernel = 'linear' | 'cosine') forms from the matrix rows
+ * (polycracker.py:387 and 398-399: sklearn pairwise linear_kernel / cosine_similarity on the TF-IDF or standard-scaled rows).
+ * The contraction runs over column panels densified on the fly: pc_densify_panel writes rows [0, n_rows) x columns
+ * [col0, col0 + ncols) of the built matrix (which = 0 raw counts, 1 TF-IDF, 2 standard-scaled) as dense float32 into
+ * out_dev (device, row-major, leading dimension ld >= ncols), asynchronously on the ctx stream.  polycracker_b200/gram.py
+ * accumulates G += P P^T over the panels (a plain GEMM: cuBLAS through torch) and applies the cosine normalisation. */
+int pc_densify_panel(pc_ctx* ctx, int which, int64_t col0, int ncols, float* out_dev, int64_t ld);
+
 /* ---- N2  diagnostics (scope row N2) ------------------------------------------------------------------------
  * pc_count_histogram: the data of `kcount_hist` (polycracker.py:1419-1496: Counter over the second column of a
  * .kcount): hist[c - min_count] = number of distinct k-mers that occur exactly c times, min_count <= c <= max_count;

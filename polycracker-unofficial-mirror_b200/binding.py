@@ -76,6 +76,7 @@ _SIGS = {
     "pc_standard_scale": (C.c_int, [_vp, _vp, C.c_int]),
     "pc_scaled_get": (C.c_int, [_vp, _vp, C.c_int]),
     "pc_row_hits": (C.c_int, [_vp, _vp, C.c_int]),
+    "pc_densify_panel": (C.c_int, [_vp, C.c_int, _i64, C.c_int, _vp, _i64]),
     "pc_sub_plan": (C.c_int, [_vp, _i64, C.c_int]),
     "pc_sub_hist": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
     "pc_sub_hist_set": (C.c_int, [_vp, C.c_int, _vp, _i64]),
@@ -421,6 +422,13 @@ class Context:
         if nnz:
             check(lib.pc_scaled_get(self._h, out.ctypes.data, PC_HOST), "pc_scaled_get")
         return out
+
+    def densify_panel(self, which, col0, ncols, out_t):
+        """Columns [col0, col0 + ncols) of the built matrix as dense float32 into a torch CUDA tensor [n_rows, >= ncols]
+        (which: 'counts' | 'tfidf' | 'scaled'); asynchronous on the context stream."""
+        assert out_t.is_cuda and out_t.dim() == 2 and out_t.stride(1) == 1 and out_t.shape[1] >= ncols
+        check(lib.pc_densify_panel(self._h, {"counts": 0, "tfidf": 1, "scaled": 2}[which], int(col0), int(ncols),
+                                   _vp(out_t.data_ptr()), int(out_t.stride(0))), "pc_densify_panel")
 
     # N2 diagnostics
     def count_histogram(self, min_count=3, max_count=10000):

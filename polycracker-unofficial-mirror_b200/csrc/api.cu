@@ -308,7 +308,9 @@ int build_rep_table(pc_ctx* c) {
                              (c->probe_filter == 1 || (c->stream_valid && c->filter_bits * 5 >= c->n_sel * 6));
     // (not in front of the fingerprint walk, which already keeps misses away from the table: measured on 8 GPUs with
     // 5.6 M repeat k-mers, probe 7.4 ms with fingerprints alone, 8.8 ms with the bitmap in front of them)
-    const bool fp_walk = c->probe_fp == 1 || (c->probe_fp < 0 && c->rcap * sizeof(pc::RepSlot) > (size_t)(256ull << 20));
+    // (stream probe only; the roller probe measured best with the L2 bitmap in front of the plain 16-byte table at every size:
+    // 6.8 M repeat k-mers, 438 MB table: 5.1 ms, against 7.9 with the fingerprint walk and 12.1 with the compact 8-byte table)
+    const bool fp_walk = c->probe_fp == 1 || (c->probe_fp < 0 && c->stream_valid && c->rcap * sizeof(pc::RepSlot) > (size_t)(256ull << 20));
     if (c->n_sel > 0 && !smem_filter && (c->probe_filter == 2 || (c->probe_filter < 0 && !fp_walk))) {
         // L2-resident bitmap, 16 bits per repeat k-mer (false positives ~6 %): for repeat sets too large for the
         // shared-memory filter (measured at 673 k repeat k-mers: no filter 5.16 ms, this 4.04 ms, shared-memory filter
@@ -321,10 +323,11 @@ int build_rep_table(pc_ctx* c) {
         c->gfilter_bits = nbits;
     }
     c->rcap8 = 0;
-    // compact table only where the 16-byte slots (64 bytes per repeat k-mer at load 0.25) would leave L2: measured at 673 k
-    // repeat k-mers, where both fit, the inline keys win (3.79 ms against 5.78: no verification read, shorter probe chains)
-    if (c->n_sel > 0 && (c->probe_table8 == 1 || (c->probe_table8 < 0 && !smem_filter && !c->stream_valid && c->probe_roll != 0 &&
-                                                   c->rcap * sizeof(pc::RepSlot) > (size_t)(96ull << 20)))) {
+    // compact 8-byte-slot table: opt-in only (pc_tune probe_table8 1).  Measured slower than the 16-byte slots with inline
+    // keys both where everything fits L2 (673 k repeat k-mers: 5.78 ms against 3.79) and where the 16-byte table is 438 MB
+    // (6.8 M: 12.1 against 5.1): the verification read of the key array and the longer probe chains at load 0.5 cost more
+    // than the DRAM sectors of the hits, once the L2 bitmap keeps the misses away from the table
+    if (c->n_sel > 0 && c->probe_table8 == 1) {
         c->rcap8 = std::max<uint64_t>(64, (uint64_t)c->n_sel * 2);
         rc = c->rtable8.alloc(c->rcap8); if (rc) return rc;
         CU(cudaMemsetAsync(c->rtable8.p, 0, c->rcap8 * sizeof(unsigned long long), c->stream));
@@ -2120,7 +2123,7 @@ int pc_build_matrix(pc_ctx* c, const int32_t* chunk_row, int64_t n_rows, int64_t
             if (c->probe_mode == 1 && !use_stream) return fail(PC_ESTATE, "probe_mode=1 needs the k-mer stream of a partitioned pc_count");
             unsigned int grid = blocks_for(c->n_words, 256);
             // fingerprint-first walk when the 16 B/slot table is far beyond L2 (measured: +17 % at 43 MB, -9 % at 650 MB)
-            const bool use_fp = c->probe_fp == 1 || (c->probe_fp < 0 && c->rcap * sizeof(pc::RepSlot) > (size_t)(256ull << 20));
+            const bool use_fp = c->probe_fp == 1 || (c->probe_fp < 0 && use_stream && c->rcap * sizeof(pc::RepSlot) > (size_t)(256ull << 20));
             if (use_stream && c->rfilter_bits > 0 && !use_fp) {
                 // one persistent CTA of 1024 threads per SM, or two of 512 when two copies of the bitmap fit
                 size_t smem = (size_t)(c->rfilter_bits / 32 + 4) * sizeof(unsigned int);
@@ -2409,6 +2412,24 @@ int pc_scaled_get(pc_ctx* c, float* data, int loc) {
     int rc = use_device(c); if (rc) return rc;
     if (!c->scaled_done) return fail(PC_ESTATE, "no standard-scaled values computed");
     return copy_out(c, data, c->d_scaled.p, c->nnz * sizeof(float), loc);
+}
+
+// ---------------------------------------------------------------------------------------------- N3 Gram matrix panels
+int pc_densify_panel(pc_ctx* c, int which, int64_t col0, int ncols, float* out_dev, int64_t ld) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!c->built) return fail(PC_ESTATE, "pc_densify_panel before pc_build_matrix");
+    if (col0 < 0 || ncols < 1 || ld < ncols || !out_dev) return fail(PC_EINVAL, "bad pc_densify_panel arguments");
+    const float* values = nullptr;
+    if (which == 0) values = c->d_data.p;
+    else if (which == 1) { if (!c->tfidf_done) return fail(PC_ESTATE, "no tf-idf computed"); values = c->d_tfidf.p; }
+    else if (which == 2) { if (!c->scaled_done) return fail(PC_ESTATE, "no standard-scaled values computed"); values = c->d_scaled.p; }
+    else return fail(PC_EINVAL, "which must be 0 (counts), 1 (tf-idf) or 2 (standard-scaled)");
+    if (c->n_rows > 0) {
+        StageTimer t(c, ST_GRAM);
+        LAUNCH(c, (pc::k_densify_panel<float, 256>), (unsigned int)c->n_rows, 256, c->d_indptr.p, c->d_indices.p, values, col0, ncols,
+               out_dev, ld);
+    }
+    return PC_OK;
 }
 
 // ---------------------------------------------------------------------------------------------- N2 diagnostics

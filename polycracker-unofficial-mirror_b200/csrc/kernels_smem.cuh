@@ -757,4 +757,32 @@ k_col_apply(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indi
         out[i] = (float)((double)scaled_value(data[i], row_scale, row) * factor[indices[i]]);
 }
 
+// ------------------------------------------------------------------------------------------------ N3 Gram matrix, panels
+// X X^T of the (TF-IDF / scaled / count) matrix for the linear and cosine kernels of KernelPCA (polycracker.py:387, 398-399)
+// is the first dense contraction behind the hot path.  X is R x D with ~2 % of its entries stored; the contraction runs
+// over column panels that are densified on the fly: row r of the panel = the entries of CSR row r with col0 <= column <
+// col0 + ncols (a binary search finds the first), everything else 0.  One CTA per row.
+template <typename T>
+__device__ __forceinline__ T gram_cast(float v);
+template <> __device__ __forceinline__ float gram_cast<float>(float v) { return v; }
+
+template <typename T, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_densify_panel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
+                int64_t col0, int ncols, T* __restrict__ out, int64_t ld)
+{
+    const int64_t row = blockIdx.x;
+    T* o = out + row * ld;
+    for (int i = threadIdx.x; i < ncols; i += THREADS) o[i] = gram_cast<T>(0.0f);
+    __syncthreads();
+    const int64_t beg = indptr[row], end = indptr[row + 1];
+    int64_t lo = beg, hi = end;                               // first entry with column >= col0
+    while (lo < hi) { const int64_t mid = (lo + hi) >> 1; if ((int64_t)indices[mid] < col0) lo = mid + 1; else hi = mid; }
+    for (int64_t i = lo + threadIdx.x; i < end; i += THREADS) {
+        const int64_t c = (int64_t)indices[i] - col0;
+        if (c >= ncols) break;                                // columns ascend inside a row
+        o[c] = gram_cast<T>(values[i]);
+    }
+}
+
 }  // namespace pc

@@ -562,6 +562,30 @@ def test_n3_standard_scaler(ctx):
     assert m2.nnz > 0 and np.array_equal(got2, m2.data)
 
 
+def test_n3_gram_matrix(ctx):
+    """Scope row N3, second half: K = X X^T for KernelPCA(kernel='linear' | 'cosine') (polycracker.py:387, 398-399) from the
+    matrix on the device, against sklearn's linear_kernel / cosine_similarity on the same sparse TF-IDF matrix."""
+    from sklearn.metrics.pairwise import cosine_similarity, linear_kernel
+    from polycracker_b200 import gram
+    p = synth.small_params(seed=42, genome_size=1_500_000)
+    seq, off, names = synth.generate(p)
+    seqs = util.to_sequences(seq, off, names) + [("allN", "N" * 30000)]
+    seq, off, names = util.from_sequences(seqs)
+    res = run_hot_path(ctx, seq, off, names, chunk_size=15000, k=23, kmer_low_count=5, remove_non_chunk=0, compact=False)
+    X = res.csr_matrix("tfidf")
+    assert X.shape[0] > 80 and X.shape[1] > 1000
+    want = linear_kernel(X)
+    for panel in (257, 8192):
+        got = gram.gram_matrix_numpy(ctx, X.shape[0], X.shape[1], values="tfidf", kernel="linear", panel_cols=panel)
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-6)
+    got = gram.gram_matrix_numpy(ctx, X.shape[0], X.shape[1], values="tfidf", kernel="linear", tf32=True)
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-3)                  # TF32 products: <= 1e-3 of the unit diagonal
+    C = res.csr_matrix("counts")
+    got = gram.gram_matrix_numpy(ctx, C.shape[0], C.shape[1], values="counts", kernel="cosine")
+    np.testing.assert_allclose(got, cosine_similarity(C), rtol=1e-4, atol=1e-6)
+    assert np.all(got[-1] == 0)                                               # the all-N chunk: an empty row stays zero
+
+
 def test_threshold_watch_fused_select(ctx):
     """pc_watch_threshold (K4 fused into the table count through returning atomics on threshold crossings): same repeat
     set and matrix as the scan; a no-op for the shared-memory count, whose list already is the thresholded dump."""
