@@ -1002,7 +1002,8 @@ static int launch_count_skm(pc_ctx* c, const pc::SkmRec* recs, const unsigned lo
     const unsigned int grid = std::min<unsigned int>(n_sub, 148u * (unsigned int)per_sm);
     c->launches++;
     pc::k_count_skm<SLOTS, THREADS, GRP><<<grid, THREADS, smem, c->stream>>>(
-        recs, sub_off, n_sub, k, c->keep_min, c->list_keys.p, c->list_counts.p, list_cap, d_nlist, c->d_ovf.p, d_novf, c->d_stats.p);
+        recs, sub_off, n_sub, k, c->keep_min, c->list_keys.p, c->list_counts.p, list_cap, d_nlist, c->d_ovf.p, d_novf, c->d_stats.p,
+        reinterpret_cast<unsigned int*>(c->d_sub.p + 2 * (size_t)n_sub + 7));
     CU(cudaGetLastError());
     return PC_OK;
 }

@@ -234,12 +234,16 @@ k_skm_tile_plan(const unsigned long long* __restrict__ sub_off, unsigned int P, 
 // sub-bucket, the table is re-zeroed; a sub-bucket that does not fit is listed in ovf_ids and re-counted through a
 // global table by k_count_rec_table.
 #define PC_SKM_COUNT_NMAX 16                                   // records of at most 16 k-mers: 32 x 16 map entries per warp
+// a probe sequence this long means the table is > 90 % full: give the sub-bucket to the global-table fall-back now instead of
+// crawling through the last slots (minimizer buckets overflow for real: heavy minimizers of repeat families)
+#define PC_SKM_PROBE_LIMIT 128u
 template <int SLOTS, int THREADS, int GRP>
 __global__ void __launch_bounds__(THREADS, (2048 / THREADS) < (int)((220u << 10) / (SLOTS * 12u + THREADS * 16u + 1024u)) ? (2048 / THREADS) : (int)((220u << 10) / (SLOTS * 12u + THREADS * 16u + 1024u)))
 k_count_skm(const SkmRec* __restrict__ recs, const unsigned long long* __restrict__ sub_off, unsigned int n_sub, int k,
             unsigned int keep_min, uint64_t* __restrict__ list_keys, uint32_t* __restrict__ list_counts,
             unsigned long long list_cap, unsigned long long* __restrict__ n_list,
-            unsigned int* __restrict__ ovf_ids, unsigned int* __restrict__ n_ovf, CountStats* __restrict__ stats)
+            unsigned int* __restrict__ ovf_ids, unsigned int* __restrict__ n_ovf, CountStats* __restrict__ stats,
+            unsigned int* __restrict__ queue /* zeroed: next sub-bucket to hand out */)
 {
     constexpr int WARPS = THREADS / 32;
     constexpr int SPW = SLOTS / WARPS;
@@ -248,19 +252,22 @@ k_count_skm(const SkmRec* __restrict__ recs, const unsigned long long* __restric
     extern __shared__ __align__(16) unsigned long long skeys[];  // [SLOTS]
     unsigned int* scnt = reinterpret_cast<unsigned int*>(skeys + SLOTS);   // [SLOTS]
     unsigned char* smap = reinterpret_cast<unsigned char*>(scnt + SLOTS);  // [WARPS][32 * PC_SKM_COUNT_NMAX]
-    __shared__ unsigned int s_total, s_ovf;
+    __shared__ unsigned int s_total, s_ovf, s_next;
     __shared__ unsigned long long s_gbase;
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
-    const unsigned int G = gridDim.x;
     unsigned char* wmap = smap + wid * (32 * PC_SKM_COUNT_NMAX);
 
     for (int i = t; i < SLOTS; i += THREADS) { skeys[i] = 0ull; scnt[i] = 0u; }
-    if (t == 0) { s_total = 0; s_ovf = 0; }
+    // Sub-buckets are handed out by a global counter, not by a fixed stride: minimizer buckets are skewed (one m-mer inside
+    // a high-copy repeat family collects the k-mers of every copy), and with static striding the CTA that drew the heavy
+    // ones finished long after the others.  A CTA knows the ids of its current, next and next-but-one sub-bucket, so the
+    // offsets and the first records of the next one are still requested before the current one is finished.
+    if (t == 0) { s_total = 0; s_ovf = 0; s_next = atomicAdd(queue, 3u); }
     __syncthreads();
 
     unsigned long long distinct = 0;
     unsigned int max_probe = 0;
-    unsigned int cur_sb = blockIdx.x;
+    unsigned int cur_sb = s_next, next_sb = cur_sb + 1, next2_sb = cur_sb + 2;
     if (cur_sb >= n_sub) return;
     // Every warp owns an equal slice of the sub-bucket's records (+-1) and walks it 32 records at a time: with one
     // record per THREAD per pass, a 740-record sub-bucket left half of the CTA's warps without work in its second pass
@@ -274,7 +281,7 @@ k_count_skm(const SkmRec* __restrict__ recs, const unsigned long long* __restric
     slice(__ldg(sub_off + cur_sb), __ldg(sub_off + cur_sb + 1));
     unsigned long long cur_i0 = wbeg;
     unsigned long long nbeg = 0, nend = 0;
-    if (cur_sb + G < n_sub) { nbeg = __ldg(sub_off + cur_sb + G); nend = __ldg(sub_off + cur_sb + G + 1); }
+    if (next_sb < n_sub) { nbeg = __ldg(sub_off + next_sb); nend = __ldg(sub_off + next_sb + 1); }
     SkmRec nrec = make_ulonglong2(0ull, 0ull);
     bool nhave = false;
     {
@@ -287,13 +294,16 @@ k_count_skm(const SkmRec* __restrict__ recs, const unsigned long long* __restric
         const SkmRec rec = nrec;
         const bool have = nhave;
         const unsigned int this_sb = cur_sb;
-        const bool last_batch = cur_i0 + 32 >= wend;             // last pass of this warp over the current sub-bucket
+        // (a sub-bucket that has overflowed its table is abandoned at once: the fall-back re-counts all of it, and a heavy
+        // minimizer can put millions of records into one sub-bucket -- measured on 4 GPUs: one CTA streaming such a
+        // sub-bucket to its end stretched the whole kernel from 6.5 to 11 ms)
+        const bool last_batch = cur_i0 + 32 >= wend || *(volatile unsigned int*)&s_ovf != 0u;
         if (!last_batch) cur_i0 += 32;
         else {
-            cur_sb += G;
+            cur_sb = next_sb; next_sb = next2_sb;              // (next2_sb is refreshed after this sub-bucket's epilogue)
             slice(nbeg, nend);
             cur_i0 = wbeg;
-            if (cur_sb + G < n_sub) { nbeg = __ldg(sub_off + cur_sb + G); nend = __ldg(sub_off + cur_sb + G + 1); }
+            if (next_sb < n_sub) { nbeg = __ldg(sub_off + next_sb); nend = __ldg(sub_off + next_sb + 1); }
         }
         const bool more = cur_sb < n_sub;
         nhave = false;
@@ -342,7 +352,7 @@ k_count_skm(const SkmRec* __restrict__ recs, const unsigned long long* __restric
                     for (;;) {
                         if (o == 0ull) { ++nk; break; }
                         if (o == skey[u]) { atomicAdd(&scnt[s], 1u); break; }
-                        if (++probes > PC_SMEM_PROBE_LIMIT) { s_ovf = 1u; break; }
+                        if (++probes > PC_SKM_PROBE_LIMIT) { s_ovf = 1u; break; }
                         s = (s + 1) & (SLOTS - 1);
                         o = atomicCAS(&skeys[s], 0ull, skey[u]);
                     }
@@ -390,8 +400,10 @@ k_count_skm(const SkmRec* __restrict__ recs, const unsigned long long* __restric
             s_gbase = tot ? atomicAdd(n_list, (unsigned long long)tot) : 0ull;
             s_total = 0; s_ovf = 0;
             if (ovf) ovf_ids[atomicAdd(n_ovf, 1u)] = this_sb;
+            s_next = atomicAdd(queue, 1u);
         }
         __syncthreads();
+        next2_sb = s_next;
         unsigned long long pos = s_gbase + wbase + (incl - n_emit);
 #pragma unroll
         for (int i = 0; i < IT4; ++i) {
