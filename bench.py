@@ -41,7 +41,11 @@ FALLBACK_HBM_GBS = 6650.0
 # dram__bytes_read.sum + dram__bytes_write.sum per step of the dominant unit (K3 = every kernel of the count), summed over
 # its launches, from the committed `ncu --set full` capture of THIS workload with THIS kernel variant
 # (profiles/r02_ncu_k3_500Mbp.md).  Keyed by (count kind, super-k-mer minimizer length); anything else reports null.
-NCU_TRAFFIC = {}
+NCU_TRAFFIC = {
+    # (unit, count kind, minimizer length, genome bases): 1.56 (k_skm_extract) + 2.81 (k_rec_scatter<1>) + 2.81 (k_rec_scatter<2>)
+    # + 1.51 (k_count_skm) GB, profiles/r02_ncu_summary.md section 2
+    ("K3_count", "list", 12, 497057026): 8.692e9,
+}
 
 
 def parse_args():

@@ -349,6 +349,8 @@ k_count_skm(const SkmRec* __restrict__ recs, const unsigned long long* __restric
                     if (!on[u]) continue;
                     unsigned long long o = old[u];
                     unsigned int s = slot[u], probes = 0;
+                    // (ptxas unrolls this loop up to the probe limit -- 261 ATOMS, 5 600 instructions -- and that is the faster
+                    // code: with `#pragma unroll 1` the kernel took 6.7 ms instead of 5.25)
                     for (;;) {
                         if (o == 0ull) { ++nk; break; }
                         if (o == skey[u]) { atomicAdd(&scnt[s], 1u); break; }

@@ -222,6 +222,9 @@ def run_hot_path(ctx, seq, seq_offsets, names, chunk_size=75000, k=23, kmer_low_
     finally:
         ctx.tune(keep_min=1)
     stats = ctx.count_info()
+    if hasattr(ctx, "count_detail"):                      # how the count is held (before low_memory releases it)
+        stats["count_detail"] = ctx.count_detail()
+        stats["count_flags"] = ctx.count_flags()
     if low_memory:                                        # Gbp-scale genomes on one GPU: see pc_release
         ctx.release(ctx.REL_BUCKETS | ctx.REL_ASCII)
     n_sel = ctx.select(effective_low_count(k, kmer_low_count), kmer_high_count, bool(high_bool),

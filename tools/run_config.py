@@ -17,6 +17,16 @@ from polycracker_b200 import binding, synth  # noqa: E402
 from polycracker_b200.pipeline import ChunkLayout, HostArena, run_hot_path  # noqa: E402
 
 
+def _hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6650.0
+
+
+HBM_PEAK_GBS = _hbm_peak()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--config", default="cfg3_4.5Gbp_tobacco", choices=sorted(synth.CONFIGS))
@@ -60,13 +70,32 @@ def run_k(a, cfg, k, ctx, dev, off, names, layout, arena, seq, t_gen, torch):
         torch.cuda.synchronize(); dt = time.perf_counter() - t0
         out["pass%d_s" % it] = round(dt, 4)
     st = res.stats
-    try:
-        out["count"] = ctx.count_detail()
-    except Exception as exc:                               # low-memory mode has released the count result
-        out["count"] = str(exc)[:60]
+    det, flags = st.get("count_detail", {}), st.get("count_flags", {})
+    out["count"] = det
+    # BASELINE configs[4]: hash-table occupancy and achieved HBM GB/s.  The count has no global table: every sub-bucket is
+    # counted in its own shared-memory table, so "occupancy" = distinct k-mers / (tables x slots), plus the sub-buckets whose
+    # k-mers did not fit and went through the global-table fall-back.
+    if det.get("kind") == "list" and det.get("sub_buckets"):
+        slots = flags.get("slots_per_table", 8192)
+        out["occupancy"] = {"shared_tables": det["sub_buckets"], "slots_per_table": slots,
+                            "mean_load": round(st["distinct"] / (det["sub_buckets"] * slots), 4),
+                            "overflowed_sub_buckets": det["overflowed"],
+                            "overflowed_fraction": round(det["overflowed"] / det["sub_buckets"], 5),
+                            "largest_unit_kmers": flags.get("largest_unit"), "kept_kmers": det["kept"],
+                            "super_kmer_records": det.get("skm_records"), "minimizer_length": det.get("skm_m")}
+    tm = res.timings
+    G = sum(int(l // 32 + 1) for l in (layout.chunk_end - layout.chunk_start).tolist()) * 32
+    T, nnz, Ds, R = st["valid_windows"], st["nnz"], st["n_selected"], st["n_rows"]
+    k3_ms = sum(tm.get(x, 0.0) for x in ("part_hist", "part_scatter", "part2", "table_init", "expand", "count", "count_fallback"))
+    units = {"K1_pack": (1.375 * G, tm.get("pack", 0.0)), "K3_count": (0.375 * G + 24.0 * T, k3_ms),
+             "K5_probe": (0.375 * G + 12.0 * T + 8.0 * nnz, tm.get("probe", 0.0)),
+             "K6_rows_to_csr": (16.0 * nnz + 8.0 * R, tm.get("row_sort", 0.0) + tm.get("emit", 0.0)),
+             "K7_tfidf": (12.0 * nnz + 4.0 * Ds, tm.get("tfidf", 0.0))}
+    out["achieved_gbs"] = {n: round(b / (ms * 1e-3) / 1e9, 1) for n, (b, ms) in units.items() if ms > 0}
+    out["achieved_frac_of_hbm_peak"] = {n: round(v / HBM_PEAK_GBS, 3) for n, v in out["achieved_gbs"].items()}
     free_b, total_b = torch.cuda.mem_get_info()
     out.update(config=a.config, genome_bases=int(len(seq)), gen_s=round(t_gen, 1), gbp_per_s=round(len(seq) / dt / 1e9, 2),
-               stats={k_: int(v) for k_, v in st.items() if isinstance(v, (int, np.integer))},
+               stats={k_: int(v) for k_, v in st.items() if isinstance(v, (int, np.integer)) and not isinstance(v, bool)},
                stage_ms={k_: round(v, 2) for k_, v in res.timings.items() if v > 0},
                hbm_used_gb=round((total_b - free_b) / 1e9, 1), hbm_total_gb=round(total_b / 1e9, 1),
                torch_peak_gb=round(torch.cuda.max_memory_allocated() / 1e9, 1))
