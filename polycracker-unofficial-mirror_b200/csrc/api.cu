@@ -995,7 +995,7 @@ static int launch_rec_scatter(pc_ctx* c, const pc::SkmRec* recs, const pc::SkmRe
 template <int SLOTS, int THREADS, int GRP>
 static int launch_count_skm(pc_ctx* c, const pc::SkmRec* recs, const unsigned long long* sub_off, unsigned int n_sub, int k,
                             unsigned long long list_cap, unsigned long long* d_nlist, unsigned int* d_novf) {
-    const size_t smem = (size_t)SLOTS * 12 + (size_t)THREADS * PC_SKM_COUNT_NMAX;      // table + one k-mer -> lane map per warp
+    const size_t smem = (size_t)SLOTS * 12 + (size_t)THREADS * PC_SKM_COUNT_NMAX + (size_t)PC_SKM_NCAND * 2;   // table + one k-mer -> lane map per warp + candidate list
     CU(cudaFuncSetAttribute((pc::k_count_skm<SLOTS, THREADS, GRP>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = std::max(1, (int)((size_t)(220 << 10) / (smem + 1024)));
     per_sm = std::min(per_sm, 2048 / THREADS);

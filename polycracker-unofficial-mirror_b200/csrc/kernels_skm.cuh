@@ -237,8 +237,9 @@ k_skm_tile_plan(const unsigned long long* __restrict__ sub_off, unsigned int P, 
 // a probe sequence this long means the table is > 90 % full: give the sub-bucket to the global-table fall-back now instead of
 // crawling through the last slots (minimizer buckets overflow for real: heavy minimizers of repeat families)
 #define PC_SKM_PROBE_LIMIT 128u
+#define PC_SKM_NCAND 2048u                                     // candidate slots per sub-bucket (k-mers that reached keep_min)
 template <int SLOTS, int THREADS, int GRP>
-__global__ void __launch_bounds__(THREADS, (2048 / THREADS) < (int)((220u << 10) / (SLOTS * 12u + THREADS * 16u + 1024u)) ? (2048 / THREADS) : (int)((220u << 10) / (SLOTS * 12u + THREADS * 16u + 1024u)))
+__global__ void __launch_bounds__(THREADS, (2048 / THREADS) < (int)((220u << 10) / (SLOTS * 12u + THREADS * 16u + PC_SKM_NCAND * 2u + 1024u)) ? (2048 / THREADS) : (int)((220u << 10) / (SLOTS * 12u + THREADS * 16u + PC_SKM_NCAND * 2u + 1024u)))
 k_count_skm(const SkmRec* __restrict__ recs, const unsigned long long* __restrict__ sub_off, unsigned int n_sub, int k,
             unsigned int keep_min, uint64_t* __restrict__ list_keys, uint32_t* __restrict__ list_counts,
             unsigned long long list_cap, unsigned long long* __restrict__ n_list,
@@ -246,23 +247,29 @@ k_count_skm(const SkmRec* __restrict__ recs, const unsigned long long* __restric
             unsigned int* __restrict__ queue /* zeroed: next sub-bucket to hand out */)
 {
     constexpr int WARPS = THREADS / 32;
-    constexpr int SPW = SLOTS / WARPS;
+    constexpr int SPW = SLOTS / WARPS;                           // slots owned (scanned, emitted, re-zeroed) by one warp
     constexpr int IT4 = SPW / 128;
-    static_assert(SLOTS % (WARPS * 128) == 0 && IT4 * 4 <= 32, "slot layout");
+    static_assert(SLOTS % (WARPS * 128) == 0 && IT4 * 4 <= 32 && SLOTS <= 65536, "slot layout");
     extern __shared__ __align__(16) unsigned long long skeys[];  // [SLOTS]
     unsigned int* scnt = reinterpret_cast<unsigned int*>(skeys + SLOTS);   // [SLOTS]
     unsigned char* smap = reinterpret_cast<unsigned char*>(scnt + SLOTS);  // [WARPS][32 * PC_SKM_COUNT_NMAX]
-    __shared__ unsigned int s_total, s_ovf, s_next;
-    __shared__ unsigned long long s_gbase;
+    unsigned short* scand = reinterpret_cast<unsigned short*>(smap + WARPS * 32 * PC_SKM_COUNT_NMAX);   // [PC_SKM_NCAND]
+    // flags of the sub-bucket being counted, double-buffered by sub-bucket parity: everybody reads pair [p] after the
+    // barrier that ends sub-bucket i while thread 0 already clears pair [p ^ 1] for sub-bucket i + 1 -- no extra barrier
+    __shared__ unsigned int s_ovf[2], s_ncand[2], s_next;
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
     unsigned char* wmap = smap + wid * (32 * PC_SKM_COUNT_NMAX);
+    // k-mers that reach keep_min are listed when the count atomic returns keep_min - 2, so the epilogue emits them from
+    // the list instead of scanning all SLOTS slots (17 % of this kernel's instructions); keep_min = 1 lists nothing and
+    // scans (every distinct k-mer is emitted anyway)
+    const bool cand_mode = keep_min >= 2u;
 
     for (int i = t; i < SLOTS; i += THREADS) { skeys[i] = 0ull; scnt[i] = 0u; }
     // Sub-buckets are handed out by a global counter, not by a fixed stride: minimizer buckets are skewed (one m-mer inside
     // a high-copy repeat family collects the k-mers of every copy), and with static striding the CTA that drew the heavy
     // ones finished long after the others.  A CTA knows the ids of its current, next and next-but-one sub-bucket, so the
     // offsets and the first records of the next one are still requested before the current one is finished.
-    if (t == 0) { s_total = 0; s_ovf = 0; s_next = atomicAdd(queue, 3u); }
+    if (t == 0) { s_ovf[0] = s_ovf[1] = 0; s_ncand[0] = s_ncand[1] = 0; s_next = atomicAdd(queue, 3u); }
     __syncthreads();
 
     unsigned long long distinct = 0;
@@ -290,14 +297,16 @@ k_count_skm(const SkmRec* __restrict__ recs, const unsigned long long* __restric
         if (nhave) { const uint4 v = ldnc_u4(recs + i); nrec.x = ((unsigned long long)v.y << 32) | v.x; nrec.y = ((unsigned long long)v.w << 32) | v.z; }
     }
     unsigned int nk = 0;
+    unsigned int par = 0;                                        // parity of the sub-bucket this warp is inserting
     for (;;) {
         const SkmRec rec = nrec;
         const bool have = nhave;
         const unsigned int this_sb = cur_sb;
+        volatile unsigned int* ovf_flag = &s_ovf[par];
         // (a sub-bucket that has overflowed its table is abandoned at once: the fall-back re-counts all of it, and a heavy
         // minimizer can put millions of records into one sub-bucket -- measured on 4 GPUs: one CTA streaming such a
         // sub-bucket to its end stretched the whole kernel from 6.5 to 11 ms)
-        const bool last_batch = cur_i0 + 32 >= wend || *(volatile unsigned int*)&s_ovf != 0u;
+        const bool last_batch = cur_i0 + 32 >= wend || *ovf_flag != 0u;
         if (!last_batch) cur_i0 += 32;
         else {
             cur_sb = next_sb; next_sb = next2_sb;              // (next2_sb is refreshed after this sub-bucket's epilogue)
@@ -327,7 +336,7 @@ k_count_skm(const SkmRec* __restrict__ recs, const unsigned long long* __restric
             // the record travels by shuffle with the number of its first k-mer in the (here unused) destination bits
             const unsigned long long rec_lo = (rec.y & ~0x3FFFFFFFull) | (unsigned long long)excl;
             __syncwarp();
-            const bool live = *(volatile unsigned int*)&s_ovf == 0u;
+            const bool live = *ovf_flag == 0u;
             for (int g0 = 0; g0 < total; g0 += 32 * GRP) {
                 unsigned long long skey[GRP], old[GRP]; unsigned int slot[GRP]; bool on[GRP];
 #pragma unroll
@@ -353,8 +362,16 @@ k_count_skm(const SkmRec* __restrict__ recs, const unsigned long long* __restric
                     // code: with `#pragma unroll 1` the kernel took 6.7 ms instead of 5.25)
                     for (;;) {
                         if (o == 0ull) { ++nk; break; }
-                        if (o == skey[u]) { atomicAdd(&scnt[s], 1u); break; }
-                        if (++probes > PC_SKM_PROBE_LIMIT) { s_ovf = 1u; break; }
+                        if (o == skey[u]) {
+                            if (cand_mode) {
+                                if (atomicAdd(&scnt[s], 1u) + 2u == keep_min) {           // this occurrence lifts it to keep_min
+                                    const unsigned int p = atomicAdd(&s_ncand[par], 1u);
+                                    if (p < PC_SKM_NCAND) scand[p] = (unsigned short)s;
+                                }
+                            } else atomicAdd(&scnt[s], 1u);
+                            break;
+                        }
+                        if (++probes > PC_SKM_PROBE_LIMIT) { *ovf_flag = 1u; break; }
                         s = (s + 1) & (SLOTS - 1);
                         o = atomicCAS(&skeys[s], 0ull, skey[u]);
                     }
@@ -365,67 +382,101 @@ k_count_skm(const SkmRec* __restrict__ recs, const unsigned long long* __restric
         }
         if (!last_batch) continue;
 
-        // ---- sub-bucket complete: emit the k-mers that reach keep_min, re-zero the table (as k_count_smem)
-        __syncthreads();
-        const bool ovf = s_ovf != 0u;
-        if (!ovf) distinct += nk;
-        nk = 0;
-        uint4 c4[IT4];
-        unsigned int emask = 0, n_emit = 0;
-        const int s0 = wid * SPW + lane * 4;
-#pragma unroll
-        for (int i = 0; i < IT4; ++i) {
-            const int s = s0 + i * 128;
-            c4[i] = *reinterpret_cast<const uint4*>(scnt + s);
-            const unsigned int cc[4] = {c4[i].x, c4[i].y, c4[i].z, c4[i].w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                bool e = !ovf && cc[j] + 1u >= keep_min;
-                if (e && keep_min <= 1u) e = skeys[s + j] != 0ull;
-                emask |= (unsigned int)e << (4 * i + j);
-                n_emit += e;
-            }
-        }
-        unsigned int incl = n_emit;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned int u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-            if (lane >= o) incl += u;
-        }
-        const unsigned int wtot = __shfl_sync(0xFFFFFFFFu, incl, 31);
-        unsigned int wbase = 0;
-        if (lane == 0 && wtot) wbase = atomicAdd(&s_total, wtot);
-        wbase = __shfl_sync(0xFFFFFFFFu, wbase, 0);
-        __syncthreads();
+        // ---- sub-bucket complete: emit the k-mers that reach keep_min, re-zero the table.  Two CTA barriers: every warp
+        // emits and re-zeroes only the slots it owns ([wid * SPW, (wid + 1) * SPW)), so nothing has to be ordered between
+        // the emission and the re-zeroing.
+        __syncthreads();                                         // A: all inserts of this_sb are done
+        const bool ovf = s_ovf[par] != 0u;
+        const unsigned int nc = s_ncand[par];
         if (t == 0) {
-            const unsigned int tot = s_total;
-            s_gbase = tot ? atomicAdd(n_list, (unsigned long long)tot) : 0ull;
-            s_total = 0; s_ovf = 0;
             if (ovf) ovf_ids[atomicAdd(n_ovf, 1u)] = this_sb;
+            s_ovf[par ^ 1u] = 0u; s_ncand[par ^ 1u] = 0u;        // (read by nobody until the next sub-bucket, see above)
             s_next = atomicAdd(queue, 1u);
         }
-        __syncthreads();
-        next2_sb = s_next;
-        unsigned long long pos = s_gbase + wbase + (incl - n_emit);
+        if (!ovf) distinct += nk;
+        nk = 0;
+        const unsigned int lo_slot = (unsigned int)(wid * SPW), hi_slot = lo_slot + SPW;
+        if (!ovf && cand_mode && nc <= PC_SKM_NCAND) {
+            // the candidate list is short (84 entries per sub-bucket at cfg2): every warp walks it twice and takes its own
+            // slots -- first to count them (ONE reservation per warp in the global list: with one per 32 candidates the
+            // same-address atomics were what the kernel waited for), then to emit them
+            unsigned int mine_n = 0;
+            for (unsigned int i0 = 0; i0 < nc; i0 += 32) {
+                const unsigned int i = i0 + lane;
+                const unsigned int s = i < nc ? (unsigned int)scand[i] : 0xFFFFFFFFu;
+                mine_n += __popc(__ballot_sync(0xFFFFFFFFu, s >= lo_slot && s < hi_slot));
+            }
+            if (mine_n) {
+                unsigned long long pos = 0;
+                if (lane == 0) pos = atomicAdd(n_list, (unsigned long long)mine_n);
+                pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+                for (unsigned int i0 = 0; i0 < nc; i0 += 32) {
+                    const unsigned int i = i0 + lane;
+                    const unsigned int s = i < nc ? (unsigned int)scand[i] : 0xFFFFFFFFu;
+                    const bool mine = s >= lo_slot && s < hi_slot;
+                    const unsigned int bal = __ballot_sync(0xFFFFFFFFu, mine);
+                    if (mine) {
+                        const unsigned long long q = pos + __popc(bal & ((1u << lane) - 1u));
+                        if (q < list_cap) { list_keys[q] = ~skeys[s]; list_counts[q] = scnt[s] + 1u; }
+                    }
+                    pos += __popc(bal);
+                }
+            }
+        } else if (!ovf) {
+            // scan of the warp's own slots (keep_min = 1, or more candidates than the list holds)
+            uint4 c4[IT4];
+            unsigned int emask = 0, n_emit = 0;
+            const int s0 = wid * SPW + lane * 4;
 #pragma unroll
-        for (int i = 0; i < IT4; ++i) {
-            const int s = s0 + i * 128;
-            if ((emask >> (4 * i)) & 0xFu) {
+            for (int i = 0; i < IT4; ++i) {
+                const int s = s0 + i * 128;
+                c4[i] = *reinterpret_cast<const uint4*>(scnt + s);
                 const unsigned int cc[4] = {c4[i].x, c4[i].y, c4[i].z, c4[i].w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    if ((emask >> (4 * i + j)) & 1u) {
-                        if (pos < list_cap) { list_keys[pos] = ~skeys[s + j]; list_counts[pos] = cc[j] + 1u; }
-                        ++pos;
-                    }
+                for (int j = 0; j < 4; ++j) {
+                    bool e = cc[j] + 1u >= keep_min;
+                    if (e && keep_min <= 1u) e = skeys[s + j] != 0ull;   // count field 0 is also what an empty slot holds
+                    emask |= (unsigned int)e << (4 * i + j);
+                    n_emit += e;
+                }
             }
-            __syncwarp();
-            *reinterpret_cast<uint4*>(scnt + s) = make_uint4(0u, 0u, 0u, 0u);
-            uint4* kz = reinterpret_cast<uint4*>(skeys + wid * SPW + i * 128);
-            kz[lane] = make_uint4(0u, 0u, 0u, 0u);
-            kz[lane + 32] = make_uint4(0u, 0u, 0u, 0u);
+            unsigned int incl = n_emit;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned int u = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            const unsigned int wtot = __shfl_sync(0xFFFFFFFFu, incl, 31);
+            unsigned long long gb = 0;
+            if (lane == 0 && wtot) gb = atomicAdd(n_list, (unsigned long long)wtot);
+            gb = __shfl_sync(0xFFFFFFFFu, gb, 0);
+            unsigned long long pos = gb + (incl - n_emit);
+#pragma unroll
+            for (int i = 0; i < IT4; ++i) {
+                const int s = s0 + i * 128;
+                if ((emask >> (4 * i)) & 0xFu) {
+                    const unsigned int cc[4] = {c4[i].x, c4[i].y, c4[i].z, c4[i].w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if ((emask >> (4 * i + j)) & 1u) {
+                            if (pos < list_cap) { list_keys[pos] = ~skeys[s + j]; list_counts[pos] = cc[j] + 1u; }
+                            ++pos;
+                        }
+                }
+            }
         }
-        __syncthreads();
+        __syncwarp();                                            // this warp has read what it emits: re-zero its slots
+        {
+            uint4* cz = reinterpret_cast<uint4*>(scnt + wid * SPW);          // SPW counts = SPW / 4 x 16 bytes
+            uint4* kz = reinterpret_cast<uint4*>(skeys + wid * SPW);         // SPW keys   = SPW / 2 x 16 bytes
+#pragma unroll
+            for (int i = 0; i < SPW / 128; ++i) cz[i * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int i = 0; i < SPW / 64; ++i) kz[i * 32 + lane] = make_uint4(0u, 0u, 0u, 0u);
+        }
+        __syncthreads();                                         // D: table is empty again, s_next is valid
+        next2_sb = s_next;
+        par ^= 1u;
         if (!more) break;
     }
 #pragma unroll

@@ -263,7 +263,6 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
         off, recs, hist = ctx.skm_partition(k, skm)
         mark("pack+partition")
         n_local_records = int(off[-1])
-        n_local = ctx.count_info_windows() if hasattr(ctx, "count_info_windows") else None
         sizes = torch.from_numpy(np.diff(off).astype(np.int64)).to(device)
         gathered = [torch.empty(P, dtype=torch.int64, device=device) for _ in range(world)]
         dist.all_gather(gathered, sizes)
@@ -302,7 +301,7 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
             ctx.skm_count_from(k, skm, None, (recv_off[:, None] + within).T.copy(), mine.T.copy(), staged_hist, recs=recv)
             del recv
             exchanged = 8 * (int(sum(send_counts)) - send_counts[rank])
-        n_local = int(ctx.count_info()["valid_windows"]) if n_local is None else n_local
+        n_local = int(ctx.count_info()["valid_windows"])
     else:
         kbuf_keys = int((ends - begins).sum()) if len(ends) else 1        # >= local windows: pins the bucket buffer
         if hasattr(ctx, "kbuf_export") and on_gpu and exchange != "nccl":
