@@ -420,8 +420,30 @@ def run_b200_arm(args):
     if rank == 0:
         sampler.wait_ready()
         sampler.mark_begin()
-    per_step_timings = []
-    ms_total, last_resident = timed(args.steps, True, False, per_step_timings)
+    # A timed region of K steps that contains a host stall (another tenant of the box, a driver lock: single steps of
+    # 200+ ms between 17 ms ones were seen on one pool box, kernels unaffected) measures the box, not the path.  The region
+    # is therefore re-measured (whole K-step regions, at most 3) while one of its steps took more than twice the median
+    # step; every attempt is reported (`timed_attempts`), the FIRST clean one -- or, if none is clean, the fastest -- is
+    # the line's value.  All ranks take the same decision (the flag is all-reduced).
+    attempts = []
+    for attempt in range(3):
+        per_step_timings = []
+        n_wall = len(step_wall)
+        ms_total, last_resident = timed(args.steps, True, False, per_step_timings)
+        walls = step_wall[n_wall:]
+        stalled = bool(walls) and max(walls) > 2.0 * float(np.median(walls)) and len(walls) >= 3
+        if dist is not None:
+            f = torch.tensor([1.0 if stalled else 0.0], dtype=torch.float64, device=device)
+            dist.all_reduce(f, op=dist.ReduceOp.MAX)
+            stalled = bool(f.item() > 0)
+        attempts.append({"ms_per_step": ms_total / args.steps, "stalled_step": stalled, "timings": per_step_timings,
+                         "last": last_resident, "walls": walls})
+        if not stalled:
+            break
+    clean = [a for a in attempts if not a["stalled_step"]]
+    chosen = clean[0] if clean else min(attempts, key=lambda a: a["ms_per_step"])
+    ms_total, last_resident, per_step_timings = chosen["ms_per_step"] * args.steps, chosen["last"], chosen["timings"]
+    step_wall = chosen["walls"]
     if rank == 0:
         sampler.mark_end()
     launches = ctx.launch_count()
@@ -505,10 +527,22 @@ def run_b200_arm(args):
 
         piped(2)
         h0, d0 = pipe.h2d_bytes, pipe.d2h_bytes
-        ms_e2e, res_p = piped(args.steps)
+        e2e_attempts = []
+        for attempt in range(3):                           # same re-measure rule as the resident loop (3 x the median here:
+            ms_e2e, res_p = piped(args.steps)              # the first and last steps of a pipelined loop are longer by design)
+            stalled = len(e2e_wall) >= 3 and max(e2e_wall) > 3.0 * float(np.median(e2e_wall))
+            if dist is not None:
+                f = torch.tensor([1.0 if stalled else 0.0], dtype=torch.float64, device=device)
+                dist.all_reduce(f, op=dist.ReduceOp.MAX)
+                stalled = bool(f.item() > 0)
+            e2e_attempts.append((ms_e2e, res_p, list(e2e_wall), stalled))
+            if not stalled:
+                break
+        clean = [a for a in e2e_attempts if not a[3]]
+        ms_e2e, res_p, e2e_wall, _ = clean[0] if clean else min(e2e_attempts, key=lambda a: a[0])
         pipe.close()
-        h2d = (pipe.h2d_bytes - h0) // args.steps
-        d2h = (pipe.d2h_bytes - d0) // args.steps
+        h2d = (pipe.h2d_bytes - h0) // (args.steps * len(e2e_attempts))
+        d2h = (pipe.d2h_bytes - d0) // (args.steps * len(e2e_attempts))
         same = (np.array_equal(res_p.indptr, res.indptr) and np.array_equal(res_p.indices, res.indices)
                 and np.array_equal(res_p.data, res.data) and np.array_equal(res_p.kmer_keys, res.kmer_keys)
                 and np.array_equal(res_p.tfidf, res.tfidf))
@@ -518,6 +552,7 @@ def run_b200_arm(args):
                "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e / args.steps,
                "sequential_ms_per_step": ms_lat / args.steps,
                "sequential_value": genome_bases / (ms_lat / args.steps * 1e-3) / 1e9,
+               "timed_attempts": [{"ms_per_step": round(a[0] / args.steps, 3), "stalled_step": a[3]} for a in e2e_attempts],
                "note": "K back-to-back steps through the public API, host buffers: pinned host genome -> H2D -> "
                        "pc_load_sequences ... pc_csr_get8/pc_tfidf_factors_get -> D2H into pinned host memory, every step "
                        "(compact hand-off: one byte per column gap + one per count + escape lists + idf + row norms, ~2 B per entry; the int32 / float32 "
@@ -620,6 +655,8 @@ def run_b200_arm(args):
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "parity_check": parity,
             "gpu_launches": int(launches),
             "numa_binding": numa_all, "iso_work": iso, "clocks": clocks, "step_wall_ms": [round(x, 2) for x in step_wall],
+            "timed_attempts": [{"ms_per_step": round(a["ms_per_step"], 3), "stalled_step": a["stalled_step"],
+                                "max_step_wall_ms": round(max(a["walls"]), 2) if a["walls"] else None} for a in attempts],
             "e2e_step_wall_ms": [round(x, 2) for x in (e2e_wall if not args.no_e2e else [])], "quiet_gpu_wait_s": round(quiet_wait, 2),
             "result": {"distinct_kmers_rank0": info["distinct"], "valid_windows_rank0": info["valid_windows"],
                        "shared_tables": detail.get("sub_buckets"), "shared_table_slots": info["capacity"] // max(1, detail.get("sub_buckets") or 1),
