@@ -610,7 +610,7 @@ def run_b200_arm(args):
         "K3_count": ("k_skm_extract + k_rec_scatter<1> + k_rec_scatter<2> + k_count_skm (super-k-mer count)" if skm else
                      "k_extract + k_tile_scatter + k_sub_scatter + k_count_smem (k-mer count)") if detail["kind"] == "list"
         else "k_extract + k_tile_scatter + k_count_part (table count)",
-        "K5_probe": "k_probe_roll_filt" if skm else "k_probe_stream_filt", "K6_rows_to_csr": "k_row_sort + k_row_emit"}
+        "K5_probe": "k_probe_roll_filt" if skm else "k_probe_stream_filt", "K6_rows_to_csr": "k_row_bitmap_csr"}
     roofline = {"bound": "hbm", "kernel": unit_kernels.get(dom, dom),
                 "achieved": d["achieved_gbs"],
                 "peak": peak, "unit": "GB/s", "frac": d["frac"],

@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 #include "kernels_smem.cuh"
 #include "kernels_skm.cuh"
+#include "kernels_csr.cuh"
 
 namespace {
 
@@ -154,6 +155,9 @@ struct pc_ctx {
     int64_t smem_mean() const { return smem_target > 0 ? smem_target : (int64_t)smem_slots() / 2; }
     bool kbuf_shared = false;                   // the bucket buffer has been exported to peer processes (pc_kbuf_export)
     int rowsort_warps = 16;                     // tunable: warps per CTA in the per-row sort (8 or 16)
+    int csr_mode = -1;                          // tunable: rows -> CSR by -1 auto, 0 per-row radix sort, 1 shared-memory column bitmap (kernels_csr.cuh)
+    int64_t csr_range_bits = 0, csr_ncap = 0;   // tunables (tests): columns per bitmap range / shared count slots (0 = as many as fit)
+    DevBuf<unsigned long long> d_row_state;
     int scatter_pack = 1;                       // tunable: carry the bucket id in the spare top bits of the k-mer word (k <= 26)
     int scatter_tile = 0;                       // tunable: k-mers per tile of the level-1 scatter (0 auto, 8192: 2 CTAs/SM, 4096: 4 CTAs/SM)
     int smem_pb = 0;                            // tunable: level-1 bucket bits of the shared-memory count (0 = auto)
@@ -399,7 +403,7 @@ int pc_destroy(pc_ctx* c) {
     c->rec_a.release(); c->rec_b.release(); c->d_skm_hist.release(); c->d_skm_off.release(); c->d_skm_cur.release(); c->d_skm_n.release(); c->d_skm_koff.release();
     c->sel_a.release(); c->sel_b.release(); c->rs_hist.release(); c->d_counter.release(); c->rtable.release(); c->rfp.release(); c->rfilter.release(); c->rtable8.release();
     c->d_chunk_row.release(); c->d_row_base.release(); c->d_row_cursor.release(); c->hits_a.release();
-    c->hits_b.release(); c->d_row_nnz.release(); c->d_indptr.release(); c->d_indices.release();
+    c->hits_b.release(); c->d_row_nnz.release(); c->d_row_state.release(); c->d_indptr.release(); c->d_indices.release();
     c->d_data.release(); c->d_idf.release(); c->d_tfidf.release(); c->d_df.release(); c->d_df_global.release();
     c->d_row_norm.release(); c->d_data16.release(); c->d_esc_pos.release(); c->d_esc_val.release();
     c->d_dcol8.release(); c->d_cnt8.release(); c->d_esc8_pos.release(); c->d_esc8_val.release();
@@ -1308,6 +1312,9 @@ int pc_tune(pc_ctx* c, const char* key, int64_t value) {
     else if (k == "scatter_tile") c->scatter_tile = (int)value;
     else if (k == "scatter_pack") c->scatter_pack = (int)value;
     else if (k == "rowsort_warps") c->rowsort_warps = (int)value;
+    else if (k == "csr_mode") c->csr_mode = (int)value;
+    else if (k == "csr_range_bits") c->csr_range_bits = value <= 0 ? 0 : ((std::max<int64_t>(1024, value) + 1023) / 1024) * 1024;
+    else if (k == "csr_ncap") c->csr_ncap = std::max<int64_t>(0, value);
     else if (k == "prezero") c->prezero = (int)value;
     else if (k == "probe_fp") c->probe_fp = (int)value;
     else if (k == "probe_filter") c->probe_filter = (int)value;
@@ -2032,8 +2039,67 @@ int pc_set_selected(pc_ctx* c, const uint64_t* keys, int64_t n, int k, int loc, 
 // ---------------------------------------------------------------------------------------------- K5 + K6
 // K6: sort every row's hit list, run-length encode it into CSR and accumulate df.  Expects hits_a / d_row_base /
 // d_row_cursor / d_df / d_indptr prepared on the device and c->n_sel = number of columns.
+// bitmap plan: columns per range (multiple of 1024) and the shared count slots that fit one CTA's 227 KB next to the
+// bitmap (4 B per 32 columns), its per-word prefixes (2 B per 32 columns) and per-chunk prefixes
+struct CsrPlan { bool bitmap; unsigned int range_bits, ncap, n_ranges; size_t smem; };
+static CsrPlan csr_plan(const pc_ctx* c) {
+    CsrPlan p{};
+    const int64_t budget = 231424;                             // dynamic shared memory (static: < 1 KB)
+    int64_t rb = ((std::max<int64_t>(c->n_sel, 1) + 1023) / 1024) * 1024;
+    rb = std::min<int64_t>(rb, 768 * 1024);                    // 96 KB of bits + 48 KB of prefixes, 21 k count slots
+    if (c->csr_range_bits > 0) rb = std::min<int64_t>(rb, c->csr_range_bits);
+    const int64_t nchunks = rb / 1024, NC = nchunks | 1;
+    const int64_t fixed = 32 * NC * 4 + (nchunks + 1) * 4 + 32 * NC * 2;
+    int64_t ncap = (budget - fixed) / 4;
+    if (c->csr_ncap > 0) ncap = std::min<int64_t>(ncap, c->csr_ncap);
+    p.range_bits = (unsigned int)rb; p.ncap = (unsigned int)ncap;
+    p.n_ranges = (unsigned int)((std::max<int64_t>(c->n_sel, 1) + rb - 1) / rb);
+    p.smem = (size_t)(fixed + ncap * 4);
+    p.bitmap = c->csr_mode == 1 ? p.n_ranges <= PC_CSR_MAXR : (c->csr_mode < 0 && p.n_ranges <= 16);
+    return p;
+}
+
+static int rows_to_csr_bitmap(pc_ctx* c, int64_t n_rows, const CsrPlan& plan) {
+    int rc;
+    c->nnz = 0;
+    if (n_rows > 0) {
+        StageTimer t(c, ST_ROWSORT);
+        // capacity of indices / data: the hits of all rows (their distinct count is only known row by row)
+        unsigned long long total_hits = 0;
+        CU(cudaMemsetAsync(c->d_counter.p, 0, 2 * sizeof(unsigned long long), c->stream));
+        LAUNCH(c, pc::k_sum_u32, (unsigned int)std::min<int64_t>(148 * 4, (n_rows + 255) / 256), 256, c->d_row_cursor.p, n_rows, c->d_counter.p);
+        READ_SMALL(c, &total_hits, c->d_counter.p, sizeof total_hits);
+        SYNC(c);
+        rc = c->d_indices.alloc(std::max<int64_t>((int64_t)total_hits, 1)); if (rc) return rc;
+        rc = c->d_data.alloc(std::max<int64_t>((int64_t)total_hits, 1)); if (rc) return rc;
+        rc = c->d_row_state.alloc(n_rows + 1); if (rc) return rc;
+        CU(cudaMemsetAsync(c->d_row_state.p, 0, (n_rows + 1) * sizeof(unsigned long long), c->stream));
+        unsigned int* queue = reinterpret_cast<unsigned int*>(c->d_row_state.p + n_rows);
+        CU(cudaFuncSetAttribute(pc::k_row_bitmap_csr, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+        c->launches++;
+        pc::k_row_bitmap_csr<<<(unsigned int)std::min<int64_t>(148, n_rows), PC_CSR_THREADS, plan.smem, c->stream>>>(
+            c->hits_a.p, c->d_row_base.p, c->d_row_cursor.p, (int)n_rows, (unsigned int)c->n_sel, plan.range_bits, plan.ncap,
+            c->d_row_state.p, queue, c->d_indptr.p, c->d_indices.p, c->d_data.p, c->d_df.p);
+        CU(cudaGetLastError());
+        int64_t total = 0;
+        READ_SMALL(c, &total, c->d_indptr.p + n_rows, sizeof(int64_t));
+        SYNC(c);
+        c->nnz = total;
+    }
+    SYNC(c);                      // host staging vectors no longer needed
+    c->n_rows = n_rows;
+    c->built = true;
+    return PC_OK;
+}
+
 static int rows_to_csr(pc_ctx* c, int64_t n_rows) {
     int rc;
+    {
+        const CsrPlan plan = csr_plan(c);
+        if (plan.bitmap && c->n_sel > 0) return rows_to_csr_bitmap(c, n_rows, plan);
+    }
+    rc = c->hits_b.alloc(std::max<int64_t>(c->hits_a.n, 1)); if (rc) return rc;
+    rc = c->d_row_nnz.alloc(std::max<int64_t>(n_rows, 1)); if (rc) return rc;
     int bits = 1; while (((int64_t)1 << bits) < c->n_sel) ++bits;
     // digit width: fewest passes, then the narrowest digit (smem = 17 * 2^DB * 4 bytes)
     int db = 8;
@@ -2107,10 +2173,8 @@ int pc_build_matrix(pc_ctx* c, const int32_t* chunk_row, int64_t n_rows, int64_t
     rc = c->d_chunk_row.alloc(c->n_chunks); if (rc) return rc;
     rc = c->d_row_base.alloc(n_rows + 1); if (rc) return rc;
     rc = c->d_row_cursor.alloc(n_rows); if (rc) return rc;
-    rc = c->d_row_nnz.alloc(n_rows); if (rc) return rc;
     rc = c->d_indptr.alloc(n_rows + 1); if (rc) return rc;
     rc = c->hits_a.alloc(total_windows); if (rc) return rc;
-    rc = c->hits_b.alloc(total_windows); if (rc) return rc;
     rc = c->d_df.alloc(std::max<int64_t>(c->n_sel, 1)); if (rc) return rc;
     if (c->n_chunks) CU(cudaMemcpyAsync(c->d_chunk_row.p, chunk_row, c->n_chunks * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->d_row_base.p, row_base.data(), (n_rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
@@ -2207,14 +2271,14 @@ int pc_matrix_from_hits(pc_ctx* c, const int64_t* row_offsets, const int32_t* co
         if (n < 0 || n > 0xFFFFFFFFll) return fail(PC_EINVAL, "row %lld has a bad hit count", (long long)r);
         cursor[r] = (unsigned int)n;
     }
+    for (int64_t i = 0; i < total; ++i)
+        if (cols[i] < 0 || (int64_t)cols[i] >= n_cols) return fail(PC_EINVAL, "hit %lld names column %d, the matrix has %lld", (long long)i, cols[i], (long long)n_cols);
     c->built = c->tfidf_done = false;
     c->n_sel = n_cols;                                         // column universe of this matrix
     rc = c->d_row_base.alloc(n_rows + 1); if (rc) return rc;
     rc = c->d_row_cursor.alloc(n_rows); if (rc) return rc;
-    rc = c->d_row_nnz.alloc(n_rows); if (rc) return rc;
     rc = c->d_indptr.alloc(n_rows + 1); if (rc) return rc;
     rc = c->hits_a.alloc(total); if (rc) return rc;
-    rc = c->hits_b.alloc(total); if (rc) return rc;
     rc = c->d_df.alloc(std::max<int64_t>(n_cols, 1)); if (rc) return rc;
     CU(cudaMemcpyAsync(c->d_row_base.p, row_offsets, (n_rows + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, c->stream));
     if (n_rows) CU(cudaMemcpyAsync(c->d_row_cursor.p, cursor.data(), n_rows * sizeof(unsigned int), cudaMemcpyHostToDevice, c->stream));

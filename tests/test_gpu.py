@@ -418,6 +418,47 @@ def test_probe_filters(ctx):
         ctx.tune(part_mode=-1, probe_filter=-1, probe_fp=-1, probe_mode=-1, filter_bits=1310720, probe_table8=-1, probe_roll=1)
 
 
+def test_rows_to_csr_bitmap_equals_sort_and_scipy(ctx):
+    """K6: the shared-memory column-bitmap kernel (kernels_csr.cuh) against the per-row radix sort and against scipy, on
+    raw hit lists (pc_matrix_from_hits): empty rows, one heavy column, more rows than resident CTAs x 32 (the chained scan
+    looks back over several windows), several column ranges per row (csr_range_bits) and rows with more distinct columns
+    than shared count slots (csr_ncap: the counts of the tail live in global memory)."""
+    rng = np.random.default_rng(7)
+    for n_rows, n_cols, mean_hits in ((1, 1, 5), (700, 5000, 300), (5200, 40000, 40), (300, 2_500_000, 3000)):
+        lens = rng.poisson(mean_hits, n_rows).astype(np.int64)
+        lens[rng.random(n_rows) < 0.1] = 0
+        ro = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        cols = rng.integers(0, n_cols, int(ro[-1])).astype(np.int32)
+        cols[rng.random(len(cols)) < 0.3] = n_cols // 2            # a heavy column: counts far above 1
+        if len(cols) > 10:
+            cols[:5] = n_cols - 1                                  # the last column of the last range
+        rows = np.repeat(np.arange(n_rows), lens)
+        want = sps.coo_matrix((np.ones(len(cols), np.float32), (rows, cols)), shape=(n_rows, n_cols)).tocsr()
+        want.sort_indices()
+        got = {}
+        try:
+            for name, kw in (("sort", dict(csr_mode=0)), ("bitmap", dict(csr_mode=1)),
+                             ("ranges", dict(csr_mode=1, csr_range_bits=1024)),
+                             ("ncap", dict(csr_mode=1, csr_ncap=3)),
+                             ("ranges+ncap", dict(csr_mode=1, csr_range_bits=2048, csr_ncap=1))):
+                if name.startswith("ranges") and n_cols > 64 * 2048:
+                    continue                                       # more ranges than the kernel takes (it would fall back to the sort)
+                ctx.tune(csr_mode=-1, csr_range_bits=0, csr_ncap=0)
+                ctx.tune(**kw)
+                nnz = ctx.matrix_from_hits(ro, cols, n_cols)
+                got[name] = ctx.csr(n_rows, nnz)
+                df = ctx.df(n_cols)
+                assert nnz == want.nnz, name
+                assert np.array_equal(got[name][0], want.indptr), name
+                assert np.array_equal(got[name][1], want.indices), name
+                assert np.array_equal(got[name][2], want.data), name
+                assert np.array_equal(df, np.bincount(want.indices, minlength=n_cols)), name
+        finally:
+            ctx.tune(csr_mode=-1, csr_range_bits=0, csr_ncap=0)
+    with pytest.raises(Exception):
+        ctx.matrix_from_hits(np.array([0, 1]), np.array([7], np.int32), 7)       # column out of range
+
+
 def test_compact_handoff_matches_full_arrays(ctx):
     """What crosses PCIe in the end-to-end path (pc_csr_get8: one byte per column gap and per count + escapes, 2 bytes per
     entry; or pc_csr_get16: 6 bytes; both with pc_tfidf_factors_get) rebuilds on the host to exactly the int32 / float32 arrays
