@@ -310,6 +310,9 @@ int pc_copy_async(pc_ctx* ctx, void* dst, const void* src, int64_t bytes, void* 
  * launches: kernels launched by this ctx since the last pc_reset_counters. */
 #define PC_N_STAGES 24
 int pc_timings(pc_ctx* ctx, float ms[PC_N_STAGES]);
+/* start / end of every timed stage of the last step, ms after the earliest stage start (-1 = stage not used): shows the
+ * device idle time between stages (host read-backs, the caller's own code between two calls) */
+int pc_stage_timeline(pc_ctx* ctx, float start_ms[PC_N_STAGES], float end_ms[PC_N_STAGES]);
 int pc_launch_count(pc_ctx* ctx, int64_t* launches);
 int pc_reset_counters(pc_ctx* ctx);
 /* kernel tunables (measurement / tuning only; defaults are the shipped configuration):

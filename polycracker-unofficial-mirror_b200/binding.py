@@ -120,6 +120,7 @@ _SIGS = {
     "pc_tfidf": (C.c_int, [_vp, _i64, _vp, C.c_int]),
     "pc_tfidf_get": (C.c_int, [_vp, _vp, C.c_int]),
     "pc_timings": (C.c_int, [_vp, _vp]),
+    "pc_stage_timeline": (C.c_int, [_vp, _vp, _vp]),
     "pc_launch_count": (C.c_int, [_vp, _P(_i64)]),
     "pc_reset_counters": (C.c_int, [_vp]),
     "pc_tune": (C.c_int, [_vp, C.c_char_p, _i64]),
@@ -765,6 +766,13 @@ class Context:
         ms = np.zeros(PC_N_STAGES, np.float32)
         check(lib.pc_timings(self._h, ms.ctypes.data), "pc_timings")
         return {name: float(ms[i]) for i, name in enumerate(STAGE_NAMES)}
+
+    def stage_timeline(self):
+        """-> [(stage, start_ms, end_ms)] of the last step in start order (device idle time = the holes in between)"""
+        a = np.zeros(PC_N_STAGES, np.float32); b = np.zeros(PC_N_STAGES, np.float32)
+        check(lib.pc_stage_timeline(self._h, a.ctypes.data, b.ctypes.data), "pc_stage_timeline")
+        out = [(name, float(a[i]), float(b[i])) for i, name in enumerate(STAGE_NAMES) if a[i] >= 0]
+        return sorted(out, key=lambda x: x[1])
 
     def launch_count(self):
         n = _i64()

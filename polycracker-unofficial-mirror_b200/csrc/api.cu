@@ -539,6 +539,8 @@ int pc_packed_get(pc_ctx* c, uint64_t* words, uint32_t* nmask, int64_t* chunk_wo
 // ---------------------------------------------------------------------------------------------- K3
 static int table_alloc(pc_ctx* c, int k, int64_t capacity) {
     if (k < 1 || k > 32) return fail(PC_EINVAL, "k = %d unsupported: this path handles 1 <= k <= 32 (uint64 k-mers)", k);
+    // (no driver query when the table does not have to grow: this runs in the middle of every step)
+    if (c->table_keys.p && c->table_counts.p && c->table_keys.n >= (size_t)capacity && c->table_counts.n >= (size_t)capacity) return PC_OK;
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
     size_t need = (size_t)capacity * (size_t)PC_SLOT_BYTES;
@@ -1186,9 +1188,11 @@ static int count_buckets_skm(pc_ctx* c, int k, const SkmPlan& pl, int n_buckets,
         if (rc) return rc;
     }
     unsigned long long h_nlist = 0; unsigned int h_novf = 0;
+    TRACE("skm count: launched");
     READ_SMALL(c, &h_nlist, d_nlist, sizeof h_nlist);
     READ_SMALL(c, &h_novf, d_novf, sizeof h_novf);
     rc = fetch_stats(c); if (rc) return rc;                   // synchronises
+    TRACE("skm count: done, sizes read");
     c->n_ovf = h_novf;
     if (h_novf > 0 && expand) {
         // as in count_buckets_smem: the overflowed sub-buckets are k-mer segments of kbuf2
@@ -1228,7 +1232,9 @@ static int count_buckets_skm(pc_ctx* c, int k, const SkmPlan& pl, int n_buckets,
         unsigned long long fb_total = 0;
         READ_SMALL(c, &fb_total, d_kmers + 1, sizeof fb_total);
         SYNC(c);
+        TRACE("skm fall-back: size read");
         rc = table_prepare(c, k, (int64_t)((double)fb_total / c->table_load) + 1024, /*reset_stats=*/false); if (rc) return rc;
+        TRACE("skm fall-back: table ready");
         {
             StageTimer t(c, ST_COUNT_FALLBACK);
             // a heavy minimizer (one m-mer inside a high-copy repeat family carries the mutated k-mers of every copy) can put
@@ -2064,14 +2070,10 @@ static int rows_to_csr_bitmap(pc_ctx* c, int64_t n_rows, const CsrPlan& plan) {
     c->nnz = 0;
     if (n_rows > 0) {
         StageTimer t(c, ST_ROWSORT);
-        // capacity of indices / data: the hits of all rows (their distinct count is only known row by row)
-        unsigned long long total_hits = 0;
-        CU(cudaMemsetAsync(c->d_counter.p, 0, 2 * sizeof(unsigned long long), c->stream));
-        LAUNCH(c, pc::k_sum_u32, (unsigned int)std::min<int64_t>(148 * 4, (n_rows + 255) / 256), 256, c->d_row_cursor.p, n_rows, c->d_counter.p);
-        READ_SMALL(c, &total_hits, c->d_counter.p, sizeof total_hits);
-        SYNC(c);
-        rc = c->d_indices.alloc(std::max<int64_t>((int64_t)total_hits, 1)); if (rc) return rc;
-        rc = c->d_data.alloc(std::max<int64_t>((int64_t)total_hits, 1)); if (rc) return rc;
+        // capacity of indices / data: a row has at most as many entries as hits, and the hit buffer is sized by the rows'
+        // windows -- an upper bound that needs no read-back (the exact entry count is only known when the kernel is done)
+        rc = c->d_indices.alloc(std::max<size_t>(c->hits_a.n, 1)); if (rc) return rc;
+        rc = c->d_data.alloc(std::max<size_t>(c->hits_a.n, 1)); if (rc) return rc;
         rc = c->d_row_state.alloc(n_rows + 1); if (rc) return rc;
         CU(cudaMemsetAsync(c->d_row_state.p, 0, (n_rows + 1) * sizeof(unsigned long long), c->stream));
         unsigned int* queue = reinterpret_cast<unsigned int*>(c->d_row_state.p + n_rows);
@@ -2578,6 +2580,32 @@ int pc_timings(pc_ctx* c, float ms[PC_N_STAGES]) {
     for (int i = 0; i < PC_N_STAGES; ++i) ms[i] = 0.f;
     for (int i = 0; i < ST_N; ++i)
         if (c->ev_used[i]) { float v = 0.f; if (cudaEventElapsedTime(&v, c->ev[i][0], c->ev[i][1]) == cudaSuccess) ms[i] = v; else cudaGetLastError(); }
+    return PC_OK;
+}
+
+// Start and end of every timed stage of the last step, in ms after the earliest stage start (-1: stage not used).  What
+// the per-stage durations cannot show -- the device idling between stages while the host reads a size back or Python
+// returns from one C call and enters the next -- is the difference between consecutive entries.
+int pc_stage_timeline(pc_ctx* c, float start_ms[PC_N_STAGES], float end_ms[PC_N_STAGES]) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!start_ms || !end_ms) return fail(PC_EINVAL, "null output");
+    SYNC(c);
+    for (int i = 0; i < PC_N_STAGES; ++i) start_ms[i] = end_ms[i] = -1.f;
+    int first = -1;
+    for (int i = 0; i < ST_N; ++i) {
+        if (!c->ev_used[i]) continue;
+        if (first < 0) { first = i; continue; }
+        float v = 0.f;
+        if (cudaEventElapsedTime(&v, c->ev[first][0], c->ev[i][0]) == cudaSuccess && v < 0.f) first = i; else cudaGetLastError();
+    }
+    if (first < 0) return PC_OK;
+    for (int i = 0; i < ST_N; ++i) {
+        if (!c->ev_used[i]) continue;
+        float a = 0.f, b = 0.f;
+        if (cudaEventElapsedTime(&a, c->ev[first][0], c->ev[i][0]) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (cudaEventElapsedTime(&b, c->ev[first][0], c->ev[i][1]) != cudaSuccess) { cudaGetLastError(); continue; }
+        start_ms[i] = a; end_ms[i] = b;
+    }
     return PC_OK;
 }
 
