@@ -30,8 +30,11 @@ __device__ __forceinline__ uint64_t rep_slot(uint64_t key, uint64_t rcap) {
 }
 
 // bit of a k-mer in the probe's bitmap filters (shared-memory or L2 resident): an independent multiplicative hash
+// (three 32-bit multiplies: the 64-bit product used here first was 6 % of the roller probe's instructions, ncu source page;
+// a filter only needs an even spread, and every bit of the k-mer still reaches the top bits of h)
 __device__ __forceinline__ unsigned int gbit_of(uint64_t key, unsigned int nbits) {
-    return (unsigned int)((((key * 0xA24BAED4963EE407ull) >> 32) * (uint64_t)nbits) >> 32);
+    const unsigned int h = ((unsigned int)key ^ ((unsigned int)(key >> 32) * 0x85EBCA77u)) * 0x9E3779B1u;
+    return __umulhi(h ^ (h >> 15), nbits);
 }
 
 // 16-bit fingerprint of a k-mer (never 0), from a third independent multiplicative hash

@@ -637,6 +637,38 @@ __device__ __forceinline__ int rep8_find(const unsigned long long* __restrict__ 
 // Same structure as k_probe_stream_filt: persistent CTAs hold the bitmap filter in shared memory, ~2/3 of the windows
 // that are no repeat k-mers never leave the SM, the rest probes the 16-byte repeat-table slot in L2.
 // SMEMF: the bitmap lives in shared memory (loaded once per CTA); otherwise `bitmap` (may be null) is read through L2.
+// Roller of this kernel: the validity of the 32 windows is ONE 32-bit mask (masked-base bits dilated by k - 1, as in the
+// super-k-mer extraction) instead of two 64-bit variable shifts per window, and the incoming bases come off the top of a
+// shifting register instead of being located in (w0, w1) by index (ncu source page: 11 % of the kernel's instructions).
+struct ProbeRoller {
+    uint64_t fwd, rc, kmask, t;
+    uint32_t vmsb;                                             // bit 31: current window valid (shifted left every step)
+    int rcshift;
+    __device__ __forceinline__ void init(uint64_t w0, uint64_t w1, uint32_t m0, uint32_t m1, int k) {
+        kmask = kmer_mask(k);
+        rcshift = 2 * (k - 1);
+        fwd = w0 >> (64 - 2 * k);
+        rc = revcomp_bits(fwd, k);
+        t = k >= 32 ? w1 : ((w0 << (2 * k)) | (w1 >> (64 - 2 * k)));      // bases k, k + 1, ... at the top
+        uint64_t r = ((uint64_t)m0 << 32) | (uint64_t)m1;                   // bit (63 - j): base j is masked
+        int width = 1;
+#pragma unroll
+        for (int s = 1; s <= 16; s <<= 1)
+            if (2 * s <= k) { r |= r << s; width = 2 * s; }
+        r |= r << (k - width);                                              // k - width < width
+        vmsb = ~(uint32_t)(r >> 32);
+    }
+    __device__ __forceinline__ bool valid() const { return (vmsb >> 31) != 0u; }
+    __device__ __forceinline__ uint64_t canonical() const { return fwd < rc ? fwd : rc; }
+    __device__ __forceinline__ void step() {
+        const uint64_t nb = t >> 62;
+        t <<= 2;
+        vmsb <<= 1;
+        fwd = ((fwd << 2) | nb) & kmask;
+        rc = (rc >> 2) | ((3ull - nb) << rcshift);
+    }
+};
+
 template <int BATCH, int THREADS, bool SMEMF, bool TABLE8>
 __global__ void __launch_bounds__(THREADS, 1024 / THREADS)
 k_probe_roll_filt(const uint64_t* __restrict__ words, const uint32_t* __restrict__ nmask, int64_t n_words, int k,
@@ -671,7 +703,7 @@ k_probe_roll_filt(const uint64_t* __restrict__ words, const uint32_t* __restrict
         if (on_mask == 0u) continue;
         const int row0 = __shfl_sync(0xFFFFFFFFu, row, __ffs(on_mask) - 1);
         const bool uniform = __all_sync(0xFFFFFFFFu, !lane_on || row == row0);
-        Roller r;
+        ProbeRoller r;
         if (lane_on) r.init(p.w0, p.w1, p.m0, p.m1, k);
 #pragma unroll 1
         for (int b0 = 0; b0 < 32; b0 += BATCH) {
@@ -682,9 +714,8 @@ k_probe_roll_filt(const uint64_t* __restrict__ words, const uint32_t* __restrict
                 unsigned int vmask = 0;
 #pragma unroll
                 for (int j = 0; j < BATCH; ++j) {
-                    const int b = b0 + j;
                     const uint64_t key = r.canonical();
-                    bool maybe = r.valid(b);
+                    bool maybe = r.valid();
                     if (SMEMF) {
                         const unsigned int fb = filt_bit(key, nbits);
                         maybe = maybe && ((sbits[fb >> 5] >> (fb & 31)) & 1u);
@@ -692,7 +723,7 @@ k_probe_roll_filt(const uint64_t* __restrict__ words, const uint32_t* __restrict
                     vmask |= (unsigned int)maybe << j;
                     skey[j] = ~key;
                     slot[j] = rep_slot(key, TABLE8 ? cap8 : rcap);
-                    if (b < 31) r.step(b);
+                    r.step();                                    // (the step after window 31 shifts in zeros: never used)
                 }
                 if (!SMEMF && bitmap != nullptr) {               // L2-resident bitmap (repeat sets too large for shared memory)
                     unsigned int wbits[BATCH], fb[BATCH];
