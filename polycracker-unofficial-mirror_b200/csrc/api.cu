@@ -129,7 +129,7 @@ struct pc_ctx {
     int64_t filter_bits = 1310720;              // 160 KB of shared memory (measured best: 1.0 M bits 3.58 ms, 1.31 M 3.49, 1.74 M 3.89 -- the
                                                 // largest bitmap leaves the SM no L1 for the chunk / row look-ups)
     DevBuf<unsigned int> rfilter; unsigned int rfilter_bits = 0, gfilter_bits = 0;   // shared-memory / L2-resident bitmap
-    int rep_load_inv = 4;                       // repeat table capacity = rep_load_inv * n_selected
+    int rep_load_inv = 0;                       // repeat table capacity = rep_load_inv * n_selected (0 = auto, see build_rep_table)
     bool stream_valid = false; int stream_k = 0;
     int part_blocks = 0;                        // blocks per bucket in k_count_part (0 = from the bucket size)
 
@@ -294,7 +294,11 @@ int radix_sort_u64(pc_ctx* c, uint64_t* a, uint64_t* b, int64_t n, int bits, uin
 
 int build_rep_table(pc_ctx* c) {
     StageTimer t(c, ST_REPTABLE);
-    c->rcap = std::max<uint64_t>(64, (uint64_t)c->n_sel * (uint64_t)std::max(2, c->rep_load_inv));
+    // load 1/8 while the table stays L2 resident (<= 96 MB), 1/4 beyond: the chain walk -- dependent L2 reads in a
+    // divergent loop -- is what the probe pays for a fuller table (cfg2, no filter: load 1/2 8.1 ms, 1/4 4.1, 1/8 3.6)
+    const int inv = c->rep_load_inv > 0 ? std::max(2, c->rep_load_inv)
+                                        : ((uint64_t)c->n_sel * 8 * sizeof(pc::RepSlot) <= (96ull << 20) ? 8 : 4);
+    c->rcap = std::max<uint64_t>(64, (uint64_t)c->n_sel * (uint64_t)inv);
     if (c->rcap >= (1ull << 32)) return fail(PC_EINVAL, "repeat set of %lld k-mers is too large for the repeat table", (long long)c->n_sel);
     int rc = c->rtable.alloc(c->rcap);
     if (rc) return rc;
