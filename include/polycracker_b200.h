@@ -266,6 +266,13 @@ int pc_scaled_get(pc_ctx* ctx, float* data, int loc);
  * out_dev (device, row-major, leading dimension ld >= ncols), asynchronously on the ctx stream.  polycracker_b200/gram.py
  * accumulates G += P P^T over the panels (a plain GEMM: cuBLAS through torch) and applies the cosine normalisation. */
 int pc_densify_panel(pc_ctx* ctx, int which, int64_t col0, int ncols, float* out_dev, int64_t ld);
+/* The contraction itself on the 5th-generation tensor cores (csrc/gram_tc.cuh: TMA-fed tcgen05.mma kind::tf32, TMEM
+ * accumulators): K += P P^T for the tiles on and above the diagonal, P = panel_dev (n_rows x ncols, leading dimension ld a
+ * multiple of 4 floats, 16-byte aligned; rounded to TF32 in place), K = k_dev (n_rows x n_rows float32, leading dimension
+ * ldk, zeroed by the caller before the first panel).  pc_gram_finish mirrors the upper triangle once all panels are in.
+ * Replaces the X X^T inside sklearn's linear_kernel / cosine_similarity (polycracker.py:387, 398-399); <= 1e-3 relative. */
+int pc_gram_accumulate(pc_ctx* ctx, float* panel_dev, int64_t n_rows, int ncols, int64_t ld, float* k_dev, int64_t ldk);
+int pc_gram_finish(pc_ctx* ctx, float* k_dev, int64_t n_rows, int64_t ldk);
 
 /* ---- N2  diagnostics (scope row N2) ------------------------------------------------------------------------
  * pc_count_histogram: the data of `kcount_hist` (polycracker.py:1419-1496: Counter over the second column of a

@@ -119,6 +119,8 @@ _SIGS = {
     "pc_tfidf_factors_get": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "pc_tfidf": (C.c_int, [_vp, _i64, _vp, C.c_int]),
     "pc_tfidf_get": (C.c_int, [_vp, _vp, C.c_int]),
+    "pc_gram_accumulate": (C.c_int, [_vp, _vp, C.c_int64, C.c_int, C.c_int64, _vp, C.c_int64]),
+    "pc_gram_finish": (C.c_int, [_vp, _vp, C.c_int64, C.c_int64]),
     "pc_timings": (C.c_int, [_vp, _vp]),
     "pc_stage_timeline": (C.c_int, [_vp, _vp, _vp]),
     "pc_launch_count": (C.c_int, [_vp, _P(_i64)]),
@@ -430,6 +432,16 @@ class Context:
         assert out_t.is_cuda and out_t.dim() == 2 and out_t.stride(1) == 1 and out_t.shape[1] >= ncols
         check(lib.pc_densify_panel(self._h, {"counts": 0, "tfidf": 1, "scaled": 2}[which], int(col0), int(ncols),
                                    _vp(out_t.data_ptr()), int(out_t.stride(0))), "pc_densify_panel")
+
+    def gram_accumulate(self, panel_t, ncols, k_t):
+        """K += P P^T (tiles on and above the diagonal) on the tensor cores: panel_t = torch CUDA float32 [n_rows, >= ncols]
+        (rounded to TF32 in place), k_t = torch CUDA float32 [n_rows, n_rows]; asynchronous on the context stream."""
+        assert panel_t.is_cuda and k_t.is_cuda and panel_t.stride(1) == 1 and k_t.stride(1) == 1
+        check(lib.pc_gram_accumulate(self._h, _vp(panel_t.data_ptr()), int(panel_t.shape[0]), int(ncols), int(panel_t.stride(0)),
+                                     _vp(k_t.data_ptr()), int(k_t.stride(0))), "pc_gram_accumulate")
+
+    def gram_finish(self, k_t):
+        check(lib.pc_gram_finish(self._h, _vp(k_t.data_ptr()), int(k_t.shape[0]), int(k_t.stride(0))), "pc_gram_finish")
 
     # N2 diagnostics
     def count_histogram(self, min_count=3, max_count=10000):

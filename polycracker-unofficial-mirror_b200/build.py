@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpolycracker_b200.so")
 SOURCES = ["api.cu", "host.cpp", "synth.cpp"]
-HEADERS = ["kernels.cuh", "kernels_smem.cuh", "kernels_skm.cuh", "kernels_csr.cuh", "kmer_device.cuh", "kmer_skm.cuh",
+HEADERS = ["kernels.cuh", "kernels_smem.cuh", "kernels_skm.cuh", "kernels_csr.cuh", "gram_tc.cuh", "kmer_device.cuh", "kmer_skm.cuh",
            os.path.join("..", "..", "include", "polycracker_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fopenmp,-O3", "-shared", "-lgomp"]

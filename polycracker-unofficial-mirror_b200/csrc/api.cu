@@ -17,6 +17,7 @@
 #include "kernels_smem.cuh"
 #include "kernels_skm.cuh"
 #include "kernels_csr.cuh"
+#include "gram_tc.cuh"
 
 namespace {
 
@@ -2502,6 +2503,59 @@ int pc_densify_panel(pc_ctx* c, int which, int64_t col0, int ncols, float* out_d
         LAUNCH(c, (pc::k_densify_panel<float, 256>), (unsigned int)c->n_rows, 256, c->d_indptr.p, c->d_indices.p, values, col0, ncols,
                out_dev, ld);
     }
+    return PC_OK;
+}
+
+// K += P P^T on the tensor cores (gram_tc.cuh): P = panel_dev, n_rows x ncols float32, row-major with leading dimension
+// ld (a multiple of 4 elements, 16-byte aligned base); K = k_dev, n_rows x n_rows float32, leading dimension ldk.  Only
+// the tiles on and above the diagonal are updated; pc_gram_finish mirrors them.  The panel is rounded to TF32 in place.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else cudaGetLastError();
+    }
+    return fn;
+}
+
+int pc_gram_accumulate(pc_ctx* c, float* panel_dev, int64_t n_rows, int ncols, int64_t ld, float* k_dev, int64_t ldk) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!panel_dev || !k_dev || n_rows < 1 || n_rows > 0x7FFFFFFF || ncols < 1 || ld < ncols || ldk < n_rows)
+        return fail(PC_EINVAL, "bad pc_gram_accumulate arguments");
+    if ((ld & 3) || (reinterpret_cast<uintptr_t>(panel_dev) & 15))
+        return fail(PC_EINVAL, "the panel must be 16-byte aligned with a leading dimension that is a multiple of 4 floats (TMA)");
+    EncodeTiledFn encode = encode_tiled_fn();
+    if (!encode) return fail(PC_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    CUtensorMap tm;
+    const cuuint64_t dims[2] = {(cuuint64_t)ncols, (cuuint64_t)n_rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)pc::gram::BK, (cuuint32_t)pc::gram::BM};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, panel_dev, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(PC_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    const int nt = (int)((n_rows + pc::gram::BM - 1) / pc::gram::BM);
+    const int n_kblocks = (ncols + pc::gram::BK - 1) / pc::gram::BK;
+    StageTimer t(c, ST_GRAM);
+    LAUNCH(c, pc::gram::k_round_tf32, (unsigned int)std::min<int64_t>(148 * 16, (n_rows * ncols + 255) / 256), 256, panel_dev, n_rows, ncols, ld);
+    CU(cudaFuncSetAttribute(pc::gram::k_gram_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pc::gram::SMEM_BYTES));
+    c->launches++;
+    pc::gram::k_gram_tf32<<<(unsigned int)(nt * (nt + 1) / 2), pc::gram::THREADS, pc::gram::SMEM_BYTES, c->stream>>>(
+        tm, k_dev, (int)n_rows, ldk, n_kblocks, nt);
+    CU(cudaGetLastError());
+    return PC_OK;
+}
+
+int pc_gram_finish(pc_ctx* c, float* k_dev, int64_t n_rows, int64_t ldk) {
+    int rc = use_device(c); if (rc) return rc;
+    if (!k_dev || n_rows < 1 || n_rows > 0x7FFFFFFF || ldk < n_rows) return fail(PC_EINVAL, "bad pc_gram_finish arguments");
+    LAUNCH(c, pc::gram::k_gram_mirror, (unsigned int)std::min<int64_t>(148 * 16, (n_rows * n_rows + 255) / 256), 256, k_dev, (int)n_rows, ldk);
     return PC_OK;
 }
 
