@@ -333,7 +333,11 @@ class Context:
             lib.pc_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:            # interpreter shutdown: the library handle may already be gone
+            pass
 
     def __enter__(self):
         return self
