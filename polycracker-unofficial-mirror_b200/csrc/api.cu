@@ -2052,23 +2052,35 @@ int pc_set_selected(pc_ctx* c, const uint64_t* keys, int64_t n, int k, int loc, 
 // d_row_cursor / d_df / d_indptr prepared on the device and c->n_sel = number of columns.
 // bitmap plan: columns per range (multiple of 1024) and the shared count slots that fit one CTA's 227 KB next to the
 // bitmap (4 B per 32 columns), its per-word prefixes (2 B per 32 columns) and per-chunk prefixes
-struct CsrPlan { bool bitmap; unsigned int range_bits, ncap, n_ranges; size_t smem; };
+struct CsrPlan { bool bitmap; unsigned int range_bits, range_shift, ncap, cnt_alloc, n_ranges; size_t smem; };
 static CsrPlan csr_plan(const pc_ctx* c) {
     CsrPlan p{};
-    const int64_t budget = 231424;                             // dynamic shared memory (static: < 1 KB)
-    int64_t rb = ((std::max<int64_t>(c->n_sel, 1) + 1023) / 1024) * 1024;
-    rb = std::min<int64_t>(rb, 768 * 1024);                    // 96 KB of bits + 48 KB of prefixes, 21 k count slots
+    const int64_t budget = 231424;                             // dynamic shared memory (static: < 2 KB)
+    const int64_t n_cols = std::max<int64_t>(c->n_sel, 1);
+    int64_t rb = ((n_cols + 1023) / 1024) * 1024;
     if (c->csr_range_bits > 0) rb = std::min<int64_t>(rb, c->csr_range_bits);
+    if (rb > 768 * 1024 || rb < n_cols) {
+        // several ranges: a power of two (the range of a column is a shift), at most 512 K columns = 64 KB of bits + 32 KB
+        // of prefixes, which leaves 32 k count slots
+        int64_t pow2 = 1024;
+        while (pow2 * 2 <= std::min<int64_t>(rb, 512 * 1024)) pow2 *= 2;
+        rb = pow2;
+    }
+    unsigned int shift = 0; while (((int64_t)1 << shift) < rb) ++shift;
     const int64_t nchunks = rb / 1024, NC = nchunks | 1;
     const int64_t fixed = 32 * NC * 4 + (nchunks + 1) * 4 + 32 * NC * 2;
-    int64_t ncap = (budget - fixed) / 4;
+    const int64_t n_ranges = (n_cols + rb - 1) / rb;
+    const int64_t cnt_alloc = (budget - fixed) / 4;
+    int64_t ncap = cnt_alloc;
     if (c->csr_ncap > 0) ncap = std::min<int64_t>(ncap, c->csr_ncap);
-    p.range_bits = (unsigned int)rb; p.ncap = (unsigned int)ncap;
-    p.n_ranges = (unsigned int)((std::max<int64_t>(c->n_sel, 1) + rb - 1) / rb);
-    p.smem = (size_t)(fixed + ncap * 4);
-    // auto: every range sweeps all of the row's hits twice, so the bitmap wins while the repeat set spans few ranges
-    // (measured at cfg2: 0.67 M columns 1.17 vs 2.39 ms for the sort, 2.5 M 3.78 vs 3.97, 6.8 M 8.65 vs 4.78)
-    p.bitmap = c->csr_mode == 1 ? p.n_ranges <= PC_CSR_MAXR : (c->csr_mode < 0 && p.n_ranges <= 3);
+    p.range_bits = (unsigned int)rb; p.range_shift = shift; p.ncap = (unsigned int)ncap; p.cnt_alloc = (unsigned int)cnt_alloc;
+    p.n_ranges = (unsigned int)n_ranges;
+    p.smem = (size_t)(fixed + cnt_alloc * 4);
+    const bool fits = n_ranges <= PC_CSR_MAXR && 32 * n_ranges <= cnt_alloc;
+    // auto: the bitmap while the repeat set spans at most 6 ranges (3 M columns), the per-row radix sort beyond: every
+    // range of every row pays its own prefix passes and barriers (measured at cfg2, bitmap / sort: 0.67 M columns
+    // 1.17 / 2.39 ms, 2.5 M (5 ranges) 3.32 / 3.97, 6.8 M (14 ranges) 7.05 / 4.78)
+    p.bitmap = fits && (c->csr_mode == 1 || (c->csr_mode < 0 && n_ranges <= 6));
     return p;
 }
 
@@ -2081,6 +2093,7 @@ static int rows_to_csr_bitmap(pc_ctx* c, int64_t n_rows, const CsrPlan& plan) {
         // windows -- an upper bound that needs no read-back (the exact entry count is only known when the kernel is done)
         rc = c->d_indices.alloc(std::max<size_t>(c->hits_a.n, 1)); if (rc) return rc;
         rc = c->d_data.alloc(std::max<size_t>(c->hits_a.n, 1)); if (rc) return rc;
+        if (plan.n_ranges > 1) { rc = c->hits_b.alloc(std::max<size_t>(c->hits_a.n, 1)); if (rc) return rc; }
         rc = c->d_row_state.alloc(n_rows + 1); if (rc) return rc;
         CU(cudaMemsetAsync(c->d_row_state.p, 0, (n_rows + 1) * sizeof(unsigned long long), c->stream));
         unsigned int* queue = reinterpret_cast<unsigned int*>(c->d_row_state.p + n_rows);
@@ -2088,7 +2101,8 @@ static int rows_to_csr_bitmap(pc_ctx* c, int64_t n_rows, const CsrPlan& plan) {
         c->launches++;
         pc::k_row_bitmap_csr<<<(unsigned int)std::min<int64_t>(148, n_rows), PC_CSR_THREADS, plan.smem, c->stream>>>(
             c->hits_a.p, c->d_row_base.p, c->d_row_cursor.p, (int)n_rows, (unsigned int)c->n_sel, plan.range_bits, plan.ncap,
-            c->d_row_state.p, queue, c->d_indptr.p, c->d_indices.p, c->d_data.p, c->d_df.p);
+            c->d_row_state.p, queue, c->d_indptr.p, c->d_indices.p, c->d_data.p, c->d_df.p,
+            plan.n_ranges > 1 ? c->hits_b.p : nullptr, plan.range_shift, plan.cnt_alloc);
         CU(cudaGetLastError());
         int64_t total = 0;
         READ_SMALL(c, &total, c->d_indptr.p + n_rows, sizeof(int64_t));

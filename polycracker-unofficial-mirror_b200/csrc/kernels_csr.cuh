@@ -77,18 +77,18 @@ k_sum_u32(const unsigned int* __restrict__ v, int64_t n, unsigned long long* __r
 // that follows keeps the compiler from hoisting the next one) a 45 k-hit row cost 44 dependent DRAM round trips per
 // sweep -- measured 41 us per row, 1.84 ms for the 6 621 rows of cfg2.
 #define PC_CSR_U 8
-#define PC_CSR_FOR_HITS(...)                                                                                   \
-    for (unsigned int i0_ = t; i0_ < n; i0_ += T * PC_CSR_U) {                                                 \
+#define PC_CSR_FOR_HITS(PTR, N, C0, LIMIT, ...)                                                                \
+    for (unsigned int i0_ = t; i0_ < (N); i0_ += T * PC_CSR_U) {                                               \
         unsigned int cc_[PC_CSR_U];                                                                            \
         _Pragma("unroll")                                                                                      \
         for (int u_ = 0; u_ < PC_CSR_U; ++u_) {                                                                \
             const unsigned int i_ = i0_ + u_ * T;                                                              \
-            cc_[u_] = i_ < n ? (unsigned int)__ldg(a + i_) - c0 : 0xFFFFFFFFu;                                 \
+            cc_[u_] = i_ < (N) ? (unsigned int)__ldcg((PTR) + i_) - (C0) : 0xFFFFFFFFu;                         \
         }                                                                                                      \
         _Pragma("unroll")                                                                                      \
         for (int u_ = 0; u_ < PC_CSR_U; ++u_) {                                                                \
             const unsigned int c = cc_[u_];                                                                    \
-            if (c < range_bits) { __VA_ARGS__ }                                                                \
+            if (c < (LIMIT)) { __VA_ARGS__ }                                                                   \
         }                                                                                                      \
     }
 
@@ -97,7 +97,9 @@ k_row_bitmap_csr(const int32_t* __restrict__ hits, const int64_t* __restrict__ r
                  const unsigned int* __restrict__ row_cursor, int n_rows, unsigned int n_cols,
                  unsigned int range_bits /* multiple of 1024, <= 1024 * PC_CSR_THREADS */, unsigned int ncap /* shared count slots */,
                  unsigned long long* row_state /* [n_rows], zeroed */, unsigned int* queue /* zeroed */,
-                 int64_t* __restrict__ indptr, int32_t* __restrict__ indices, float* data, int* __restrict__ df)
+                 int64_t* __restrict__ indptr, int32_t* __restrict__ indices, float* data, int* __restrict__ df,
+                 int32_t* scratch /* several ranges: a second hit buffer, same row regions; range_bits = 1 << range_shift */,
+                 unsigned int range_shift, unsigned int cnt_alloc /* count slots laid out: >= ncap and >= 32 * ranges */)
 {
     constexpr int T = PC_CSR_THREADS, WARPS = T / 32;
     // Bitmap layout: the range is cut into chunks of 32 words (1024 columns); word j of chunk g lives at j * NC + g with
@@ -110,9 +112,10 @@ k_row_bitmap_csr(const int32_t* __restrict__ hits, const int64_t* __restrict__ r
     unsigned int* bits = csr_smem;                               // [32 * NC]
     unsigned int* cpre = bits + 32 * NC;                         // [nchunks + 1]
     unsigned int* cnt = cpre + nchunks + 1;                      // [ncap]
-    unsigned short* rel = reinterpret_cast<unsigned short*>(cnt + ncap);   // [32 * NC]
+    unsigned short* rel = reinterpret_cast<unsigned short*>(cnt + cnt_alloc);   // [32 * NC]
     __shared__ unsigned int part[32];
     __shared__ unsigned int s_nnzp[PC_CSR_MAXR];
+    __shared__ unsigned int s_rstart[PC_CSR_MAXR + 1];           // several ranges: where each range's hits start in the scratch row
     __shared__ int s_row;
     __shared__ unsigned long long s_base;
     const int t = threadIdx.x, lane = t & 31, wid = t >> 5;
@@ -129,13 +132,45 @@ k_row_bitmap_csr(const int32_t* __restrict__ hits, const int64_t* __restrict__ r
         const unsigned int n = __ldg(row_cursor + row);
         const int32_t* a = hits + __ldg(row_hit_base + row);
 
+        // ---- several ranges: group the row's hits by range first (counting sort into the scratch row; per-warp counters
+        // in the not yet used count array), so that every range sweeps only its own hits.  Without it every sweep walked
+        // all hits of the row: 6.8 M columns (9 ranges) took 8.65 ms against 4.78 ms for the per-row radix sort.
+        if (nr > 1 && n) {
+            unsigned int* wc = cnt;                              // [WARPS][nr]
+            for (unsigned int i = t; i < WARPS * nr; i += T) wc[i] = 0u;
+            __syncthreads();
+            PC_CSR_FOR_HITS(a, n, 0u, 0xFFFFFFFFu, atomicAdd(&wc[wid * nr + (c >> range_shift)], 1u);)
+            __syncthreads();
+            if ((unsigned int)t < nr) {                          // hits of range t, then the per-warp cursors
+                unsigned int sum = 0;
+                for (int w = 0; w < WARPS; ++w) { const unsigned int v = wc[w * nr + t]; wc[w * nr + t] = sum; sum += v; }
+                s_nnzp[t] = sum;                                 // (borrowed: overwritten with the entry counts below)
+            }
+            __syncthreads();
+            if (t == 0) {
+                unsigned int run = 0;
+                for (unsigned int r = 0; r < nr; ++r) { s_rstart[r] = run; run += s_nnzp[r]; }
+                s_rstart[nr] = run;
+            }
+            __syncthreads();
+            int32_t* sr = scratch + (a - hits);
+            PC_CSR_FOR_HITS(a, n, 0u, 0xFFFFFFFFu,
+                const unsigned int r = c >> range_shift;
+                sr[s_rstart[r] + atomicAdd(&wc[wid * nr + r], 1u)] = (int32_t)c;
+            )
+            __syncthreads();
+            a = sr;
+        }
+
         // ---- sweep A: distinct columns per range (the bitmap is all-zero here)
         unsigned int total = 0;
         for (unsigned int p = 0; p < nr; ++p) {
             unsigned int np = 0;
-            if (n) {
+            const int32_t* ap = nr > 1 ? a + s_rstart[p] : a;
+            const unsigned int npn = nr > 1 ? (n ? s_rstart[p + 1] - s_rstart[p] : 0u) : n;
+            if (npn) {
                 const unsigned int c0 = p * range_bits;
-                PC_CSR_FOR_HITS(atomicOr(&bits[PC_CSR_PHYS(c)], 1u << (c & 31u));)
+                PC_CSR_FOR_HITS(ap, npn, c0, range_bits, atomicOr(&bits[PC_CSR_PHYS(c)], 1u << (c & 31u));)
                 __syncthreads();
                 unsigned int s = 0;
                 if ((unsigned int)t < nchunks) {
@@ -153,6 +188,7 @@ k_row_bitmap_csr(const int32_t* __restrict__ hits, const int64_t* __restrict__ r
                 __syncthreads();
                 np = cpre[nchunks];
             }
+            __syncthreads();                                     // (s_nnzp[p] held the hit count of range p until here)
             if (t == 0) s_nnzp[p] = np;
             total += np;
         }
@@ -197,8 +233,10 @@ k_row_bitmap_csr(const int32_t* __restrict__ hits, const int64_t* __restrict__ r
             const unsigned int np = s_nnzp[p];
             if (np == 0) continue;                               // (uniform; the bitmap is still all-zero)
             const unsigned int c0 = p * range_bits;
+            const int32_t* ap = nr > 1 ? a + s_rstart[p] : a;
+            const unsigned int npn = nr > 1 ? s_rstart[p + 1] - s_rstart[p] : n;
             if (nr > 1) {
-                PC_CSR_FOR_HITS(atomicOr(&bits[PC_CSR_PHYS(c)], 1u << (c & 31u));)
+                PC_CSR_FOR_HITS(ap, npn, c0, range_bits, atomicOr(&bits[PC_CSR_PHYS(c)], 1u << (c & 31u));)
                 __syncthreads();
                 unsigned int s = 0;
                 if ((unsigned int)t < nchunks) {
@@ -215,7 +253,7 @@ k_row_bitmap_csr(const int32_t* __restrict__ hits, const int64_t* __restrict__ r
             for (unsigned int i = t; i < m; i += T) cnt[i] = 0u;
             for (unsigned int i = ncap + t; i < np; i += T) idata[run + i] = 0;
             __syncthreads();
-            PC_CSR_FOR_HITS(
+            PC_CSR_FOR_HITS(ap, npn, c0, range_bits,
                 const unsigned int ph = PC_CSR_PHYS(c);
                 const unsigned int pos = cpre[c >> 10] + rel[ph] + __popc(bits[ph] & ((1u << (c & 31u)) - 1u));
                 if (pos < ncap) atomicAdd(&cnt[pos], 1u);
