@@ -48,6 +48,12 @@ enum Stage { ST_H2D = 0, ST_PACK, ST_TABLE_INIT, ST_COUNT, ST_SELECT, ST_SORT, S
 static_assert(ST_N <= PC_N_STAGES, "stage table too small");
 static_assert(pc::kMaxGroups == PC_MAX_GROUPS && pc::kMaxSubK == PC_MAX_SUB_K, "header and kernels disagree");
 
+// Memory pressure: buffers are cached across calls (a step allocates nothing in steady state), so a later pass with a
+// different shape -- another k on a 4.5 Gbp genome -- can find HBM full of buffers nobody needs any more.  While pc_count
+// runs, a failed cudaMalloc frees what is stale by construction (the previous pass's repeat set and matrix, the other
+// count path's partition buffers) and tries once more.  Defined after pc_ctx.
+bool relieve_pressure();
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr; size_t n = 0;
@@ -56,7 +62,11 @@ struct DevBuf {
         release();
         if (count == 0) count = 1;
         cudaError_t e = cudaMalloc(&p, count * sizeof(T));
-        if (e != cudaSuccess) { p = nullptr; n = 0; return fail(PC_ENOMEM, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e)); }
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            if (relieve_pressure()) e = cudaMalloc(&p, count * sizeof(T));
+        }
+        if (e != cudaSuccess) { cudaGetLastError(); p = nullptr; n = 0; return fail(PC_ENOMEM, "cudaMalloc(%zu bytes): %s", count * sizeof(T), cudaGetErrorString(e)); }
         n = count;
         return PC_OK;
     }
@@ -156,6 +166,8 @@ struct pc_ctx {
     int64_t smem_mean() const { return smem_target > 0 ? smem_target : (int64_t)smem_slots() / 2; }
     bool kbuf_shared = false;                   // the bucket buffer has been exported to peer processes (pc_kbuf_export)
     int rowsort_warps = 16;                     // tunable: warps per CTA in the per-row sort (8 or 16)
+    int relief_path = 0;                        // set while pc_count runs: 1 = k-mer partition, 2 = super-k-mer records (see relieve_pressure)
+    bool rec_shared = false;                    // the record buffer has been exported to peer processes (pc_skm_export)
     int csr_mode = -1;                          // tunable: rows -> CSR by -1 auto, 0 per-row radix sort, 1 shared-memory column bitmap (kernels_csr.cuh)
     int64_t csr_range_bits = 0, csr_ncap = 0;   // tunables (tests): columns per bitmap range / shared count slots (0 = as many as fit)
     DevBuf<unsigned long long> d_row_state;
@@ -207,6 +219,29 @@ struct pc_ctx {
 };
 
 namespace {
+
+thread_local pc_ctx* g_relief_ctx = nullptr;
+bool relieve_pressure() {
+    pc_ctx* c = g_relief_ctx;
+    if (!c || c->relief_path == 0) return false;
+    const int path = c->relief_path;
+    c->relief_path = 0;                                        // once per count
+    cudaStreamSynchronize(c->stream);
+    // a new count invalidates the previous pass's repeat set and matrix (pc_count clears selected / built first)
+    c->hits_a.release(); c->hits_b.release(); c->d_indices.release(); c->d_data.release(); c->d_tfidf.release(); c->d_row_state.release();
+    c->d_data16.release(); c->d_dcol8.release(); c->d_cnt8.release(); c->d_esc_pos.release(); c->d_esc_val.release();
+    c->d_esc8_pos.release(); c->d_esc8_val.release(); c->esc8_col_cap = 0; c->d_scaled.release();
+    c->rtable.release(); c->rfp.release(); c->rfilter.release(); c->rtable8.release(); c->sel_a.release(); c->sel_b.release(); c->sel = nullptr;
+    // the partition buffers of the path that is NOT running (never buffers peers may have mapped)
+    if (path == 1 && !c->rec_shared) { c->rec_a.release(); c->rec_b.release(); c->skm_cap_records = 0; }
+    if (path == 2) { c->kstream.release(); if (!c->kbuf_shared) { c->kbuf.release(); c->kbuf2.release(); } }
+    return true;
+}
+struct ReliefScope {                                           // arms the relief for the duration of a pc_count
+    pc_ctx* c;
+    explicit ReliefScope(pc_ctx* c_) : c(c_) { g_relief_ctx = c; }
+    ~ReliefScope() { c->relief_path = 0; g_relief_ctx = nullptr; }
+};
 
 struct StageTimer {
     pc_ctx* c; int st;
@@ -1277,7 +1312,7 @@ int pc_release(pc_ctx* c, int what) {
     SYNC(c);
     if (c->zeroed_slots > 0) { CU(cudaStreamSynchronize(c->aux_stream)); c->zeroed_slots = 0; }
     if (what & PC_REL_ASCII) { c->ascii.release(); c->ascii_padded = 0; }
-    if (what & PC_REL_BUCKETS) { c->kbuf.release(); c->kbuf2.release(); c->kbuf_shared = false; c->rec_a.release(); c->rec_b.release(); c->skm_cap_records = 0; }
+    if (what & PC_REL_BUCKETS) { c->kbuf.release(); c->kbuf2.release(); c->kbuf_shared = false; c->rec_a.release(); c->rec_b.release(); c->skm_cap_records = 0; c->rec_shared = false; }
     if (what & PC_REL_TABLE) {
         c->table_keys.release(); c->table_counts.release(); c->counted = false; c->cross_valid = false; c->cross_keys.release();
         c->list_keys.release(); c->list_counts.release(); c->n_list = 0;
@@ -1351,6 +1386,7 @@ int pc_count(pc_ctx* c, int k, int64_t capacity) {
     if (k < 1 || k > 32) return fail(PC_EINVAL, "k = %d unsupported: this path handles 1 <= k <= 32 (uint64 k-mers)", k);
     c->counted = c->selected = c->built = c->tfidf_done = false;
     c->stream_valid = false;
+    ReliefScope relief(c);
     int64_t windows = 0;
     for (int64_t i = 0; i < c->n_chunks; ++i) windows += std::max<int64_t>(0, c->h_len[i] - k + 1);
     if (capacity <= 0) {
@@ -1371,6 +1407,7 @@ int pc_count(pc_ctx* c, int k, int64_t capacity) {
             return fail(PC_EINVAL, "k = %d is too short for the super-k-mer count (part_mode 3): use part_mode 2", k);
         if (pl.ok) {
             CU(cudaMemsetAsync(c->d_stats.p, 0, sizeof(pc::CountStats), c->stream));
+            c->relief_path = 2;
             rc = do_skm_partition(c, k, pl);
             if (rc == PC_OK) {
                 const int64_t Pn = (int64_t)1 << pl.pb;
@@ -1412,6 +1449,7 @@ int pc_count(pc_ctx* c, int k, int64_t capacity) {
     }
 
     // ---- partitioned path: extract -> tile scatter -> bucket-by-bucket count ----------------------------------
+    c->relief_path = 1;
     CU(cudaMemsetAsync(c->d_stats.p, 0, sizeof(pc::CountStats), c->stream));
     if (!smem_mode(c)) { rc = table_prezero(c, k, (int64_t)(((uint64_t)capacity + P - 1) / P * P)); if (rc) return rc; }
     rc = do_partition(c, k, pb); if (rc) return rc;
@@ -1581,6 +1619,7 @@ int pc_skm_export(pc_ctx* c, int k, const int32_t plan[8], void* ipc_handle) {
     cudaIpcMemHandle_t h;
     CU(cudaIpcGetMemHandle(&h, c->rec_b.p));
     memcpy(ipc_handle, &h, sizeof h);
+    c->rec_shared = true;
     return PC_OK;
 }
 
@@ -2089,10 +2128,16 @@ static int rows_to_csr_bitmap(pc_ctx* c, int64_t n_rows, const CsrPlan& plan) {
     c->nnz = 0;
     if (n_rows > 0) {
         StageTimer t(c, ST_ROWSORT);
-        // capacity of indices / data: a row has at most as many entries as hits, and the hit buffer is sized by the rows'
-        // windows -- an upper bound that needs no read-back (the exact entry count is only known when the kernel is done)
-        rc = c->d_indices.alloc(std::max<size_t>(c->hits_a.n, 1)); if (rc) return rc;
-        rc = c->d_data.alloc(std::max<size_t>(c->hits_a.n, 1)); if (rc) return rc;
+        // capacity of indices / data: a row has at most as many entries as hits.  The exact hit total costs one tiny kernel
+        // and a read-back (~30 us); sizing by the rows' windows instead needs no read-back but 36 GB at 4.5 Gbp, which no
+        // longer fits next to the k-mer buffers of a following k < 17 pass on one GPU.
+        unsigned long long total_hits = 0;
+        CU(cudaMemsetAsync(c->d_counter.p, 0, 2 * sizeof(unsigned long long), c->stream));
+        LAUNCH(c, pc::k_sum_u32, (unsigned int)std::min<int64_t>(148 * 4, (n_rows + 255) / 256), 256, c->d_row_cursor.p, n_rows, c->d_counter.p);
+        READ_SMALL(c, &total_hits, c->d_counter.p, sizeof total_hits);
+        SYNC(c);
+        rc = c->d_indices.alloc(std::max<size_t>((size_t)total_hits, 1)); if (rc) return rc;
+        rc = c->d_data.alloc(std::max<size_t>((size_t)total_hits, 1)); if (rc) return rc;
         if (plan.n_ranges > 1) { rc = c->hits_b.alloc(std::max<size_t>(c->hits_a.n, 1)); if (rc) return rc; }
         rc = c->d_row_state.alloc(n_rows + 1); if (rc) return rc;
         CU(cudaMemsetAsync(c->d_row_state.p, 0, (n_rows + 1) * sizeof(unsigned long long), c->stream));
