@@ -204,6 +204,10 @@ int pc_csr_escapes_get(pc_ctx* ctx, int64_t* pos, float* val, int loc);
  * n_escapes[0] / [1] = entries of the two lists, fetched with pc_csr_escapes8_get.  pipeline.rebuild_indices / rebuild_counts
  * restore the int32 / float32 arrays on the host. */
 int pc_csr_get8(pc_ctx* ctx, int64_t* indptr, uint8_t* dcol8, uint8_t* cnt8, int loc, int64_t n_escapes[2]);
+/* The same hand-off with TWO-byte column gaps (escape 65535): for a large column universe (mean gap of a row n_selected /
+ * entries per row beyond ~100: the 8-GPU weak-scaling run has 257) half of the one-byte gaps would escape at 12 bytes each;
+ * 3 bytes per entry instead.  Escapes are fetched with pc_csr_escapes8_get as for pc_csr_get8. */
+int pc_csr_get_gap16(pc_ctx* ctx, int64_t* indptr, uint16_t* dcol16, uint8_t* cnt8, int loc, int64_t n_escapes[2]);
 int pc_csr_escapes8_get(pc_ctx* ctx, int64_t* col_pos, int32_t* col_val, int64_t* cnt_pos, float* cnt_val, int loc);
 
 /* ---- K7  TF-IDF + L2 rows (replaces sklearn TfidfTransformer().fit_transform, polycracker.py:395-396) -------

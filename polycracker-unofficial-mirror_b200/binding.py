@@ -115,6 +115,7 @@ _SIGS = {
     "pc_csr_get16": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _P(_i64)]),
     "pc_csr_escapes_get": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "pc_csr_get8": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "pc_csr_get_gap16": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp]),
     "pc_csr_escapes8_get": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int]),
     "pc_tfidf_factors_get": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "pc_tfidf": (C.c_int, [_vp, _i64, _vp, C.c_int]),
@@ -715,9 +716,17 @@ class Context:
         if len(locs) > 1:
             raise ValueError("all CSR outputs must live in the same place")
         n = np.zeros(2, np.int64)
-        check(lib.pc_csr_get8(self._h, ptr(indptr)[0], ptr(dcol8)[0], ptr(cnt8)[0], locs.pop() if locs else PC_HOST,
-                              n.ctypes.data), "pc_csr_get8")
+        # the gap width follows the buffer: one byte (pc_csr_get8) or two (pc_csr_get_gap16; see gap_dtype)
+        wide = dcol8 is not None and (dcol8.element_size() if hasattr(dcol8, "element_size") else dcol8.dtype.itemsize) == 2
+        fn, name = (lib.pc_csr_get_gap16, "pc_csr_get_gap16") if wide else (lib.pc_csr_get8, "pc_csr_get8")
+        check(fn(self._h, ptr(indptr)[0], ptr(dcol8)[0], ptr(cnt8)[0], locs.pop() if locs else PC_HOST, n.ctypes.data), name)
         return int(n[0]), int(n[1])
+
+    @staticmethod
+    def gap_dtype(n_selected, n_rows, nnz):
+        """Width of the column gaps of the compact hand-off: one byte while the mean gap of a row (columns / entries per
+        row) stays below ~100, two bytes for a large column universe (where half of the one-byte gaps would escape)."""
+        return np.uint16 if nnz > 0 and n_selected * max(n_rows, 1) > 96 * nnz else np.uint8
 
     def csr8_escapes(self, n_col, n_cnt):
         """-> ((positions int64, absolute columns int32), (positions int64, counts float32))"""

@@ -1511,10 +1511,13 @@ k_data_u16(const float* __restrict__ data, int64_t n, unsigned short* __restrict
 // Densest hand-off: one byte per column id (the gap to the previous column of the row; the first entry of a row and any gap
 // >= 255 are listed apart with their absolute column) and one byte per count (>= 255 listed apart).  Column ids of a row
 // ascend with a mean gap of n_selected / (entries per row) ~ 50, counts are mostly 1-3: 2 bytes per entry instead of 12.
-template <int THREADS>
+// GT = unsigned char (escape 255) or unsigned short (escape 65535): with a large column universe the mean gap of a row
+// passes 255 (8 ranks, 5.6 M columns, 21 k entries per row: mean gap 257) and half of the one-byte gaps would escape at 12
+// bytes each -- measured 0.99 GB per rank and step instead of 0.29; two-byte gaps then cost 3 bytes per entry.
+template <int THREADS, typename GT>
 __global__ void __launch_bounds__(THREADS)
 k_csr_pack8(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ data,
-            unsigned char* __restrict__ dcol, unsigned char* __restrict__ cnt8,
+            GT* __restrict__ dcol, unsigned char* __restrict__ cnt8,
             unsigned long long* __restrict__ n_esc /* [0] columns, [1] counts */, int64_t* __restrict__ col_pos,
             int32_t* __restrict__ col_val, unsigned long long col_cap, int64_t* __restrict__ cnt_pos,
             float* __restrict__ cnt_val, unsigned long long cnt_cap)
@@ -1523,12 +1526,13 @@ k_csr_pack8(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indi
     const int64_t beg = indptr[row], end = indptr[row + 1];
     for (int64_t i = beg + threadIdx.x; i < end; i += THREADS) {
         const int32_t c = indices[i];
-        const int64_t gap = i == beg ? 255 : (int64_t)c - (int64_t)indices[i - 1];
-        if (gap >= 255) {
+        constexpr int64_t ESC = sizeof(GT) == 1 ? 255 : 65535;
+        const int64_t gap = i == beg ? ESC : (int64_t)c - (int64_t)indices[i - 1];
+        if (gap >= ESC) {
             const unsigned long long p = atomicAdd(&n_esc[0], 1ull);
             if (p < col_cap) { col_pos[p] = i; col_val[p] = c; }
-            dcol[i] = 255;
-        } else dcol[i] = (unsigned char)gap;
+            dcol[i] = (GT)ESC;
+        } else dcol[i] = (GT)gap;
         const float v = data[i];
         if (v >= 255.0f) {
             const unsigned long long p = atomicAdd(&n_esc[1], 1ull);

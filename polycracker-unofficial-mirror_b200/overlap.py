@@ -125,7 +125,9 @@ class StepPipeline:
         # densest hand-off (pc_csr_get8 / pc_tfidf_factors_get): one byte per column gap, one per count, idf + row norms
         # instead of the tf-idf array -- 2 bytes per matrix entry cross PCIe instead of 12; the host rebuilds the int32 /
         # float32 arrays bit for bit (HotPathResult.indices / .data / .tfidf)
-        d_dcol = self._dev(slot, "dcol8", nnz, torch.uint8)
+        gdt = self.ctx.gap_dtype(n_sel, n_rows, nnz)         # one-byte column gaps, two for a large column universe
+        wide = gdt == np.uint16
+        d_dcol = self._dev(slot, "dcol16" if wide else "dcol8", nnz, torch.int16 if wide else torch.uint8)
         d_cnt = self._dev(slot, "cnt8", nnz, torch.uint8)
         n_col, n_cnt = self.ctx.csr8_into(d_indptr, d_dcol if nnz else None, d_cnt if nnz else None)
         # the escape lists (a few MB) leave with the bulk copies on the copy-out stream: a host-synchronous read here would
@@ -145,7 +147,7 @@ class StepPipeline:
         # D2H on the copy-out stream into this slot's page-locked arena
         a = self.arena[slot]
         h = dict(keys=a.get("keys", n_sel, np.uint64), indptr=a.get("indptr", n_rows + 1, np.int64),
-                 dcol8=a.get("dcol8", nnz, np.uint8), cnt8=a.get("cnt8", nnz, np.uint8),
+                 dcol8=a.get("dcol16" if wide else "dcol8", nnz, gdt), cnt8=a.get("cnt8", nnz, np.uint8),
                  idf=a.get("idf", n_sel, np.float32) if tfidf else None,
                  row_norm=a.get("row_norm", n_rows, np.float64) if tfidf else None, df=a.get("df", n_sel, np.int32),
                  esc_col_pos=a.get("esc_col_pos", n_col, np.int64), esc_col_val=a.get("esc_col_val", n_col, np.int32),
@@ -157,7 +159,8 @@ class StepPipeline:
                               ("esc_col_val", d_ecv), ("esc_cnt_pos", d_ekp), ("esc_cnt_val", d_ekv)):
                 if src is None or src.numel() == 0:
                     continue
-                dst = torch.from_numpy(h[name].view(np.int64) if name == "keys" else h[name])
+                hv = h[name]
+                dst = torch.from_numpy(hv.view(np.int64) if name == "keys" else hv.view(np.int16) if hv.dtype == np.uint16 else hv)
                 self._copy_pieces(dst, src)
                 self.d2h_bytes += src.numel() * src.element_size()
             done = torch.cuda.Event()

@@ -74,7 +74,8 @@ def rebuild_counts(data16, escapes=None):
 def rebuild_indices(indptr, dcol8, col_escapes):
     """int32 column ids from the one-byte gaps of pc_csr_get8: an escape (first entry of a row, gap >= 255) carries its
     absolute column, every other entry adds its gap to the entry before it."""
-    d = np.asarray(dcol8).view(np.uint8).astype(np.int64)
+    d = np.asarray(dcol8)
+    d = d.view(np.uint16 if d.dtype.itemsize == 2 else np.uint8).astype(np.int64)      # one- or two-byte gaps
     n = len(d)
     if n == 0:
         return np.zeros(0, np.int32)
@@ -289,7 +290,8 @@ def fetch_result(ctx, layout, k, scaffolds, n_sel, nnz, tfidf, stats, arena=None
         escapes = ctx.csr_escapes(n_esc) if n_esc else None
         return HotPathResult(layout, k, scaffolds, keys, indptr, indices, None, None, df, stats, ctx.timings(),
                              data16=data16, escapes=escapes, idf=idf, row_norm=row_norm)
-    dcol8, cnt8 = buf("dcol8", nnz, np.uint8), buf("cnt8", nnz, np.uint8)
+    gdt = ctx.gap_dtype(n_sel, n_rows, nnz) if hasattr(ctx, "gap_dtype") else np.uint8
+    dcol8, cnt8 = buf("dcol8" if gdt == np.uint8 else "dcol16", nnz, gdt), buf("cnt8", nnz, np.uint8)
     n_col, n_cnt = ctx.csr8_into(indptr, dcol8 if nnz else None, cnt8 if nnz else None)
     return HotPathResult(layout, k, scaffolds, keys, indptr, None, None, None, df, stats, ctx.timings(), idf=idf,
                          row_norm=row_norm, dcol8=dcol8, cnt8=cnt8, escapes8=ctx.csr8_escapes(n_col, n_cnt))

@@ -477,6 +477,18 @@ def test_compact_handoff_matches_full_arrays(ctx):
         assert np.array_equal(c8.data, full.data) and np.array_equal(c8.tfidf.view(np.uint32), full.tfidf.view(np.uint32))
         assert len(c8.escapes8[0][0]) >= (np.diff(full.indptr) > 0).sum()   # every non-empty row starts with an absolute column
         assert (np.asarray(c8.cnt8) == 255).sum() == len(c8.escapes8[1][0]) == (full.data >= 255).sum()
+        # two-byte column gaps (pc_csr_get_gap16: what gap_dtype picks for a large column universe), forced here
+        keep = binding.Context.__dict__["gap_dtype"]             # (the staticmethod object, not the function it wraps)
+        try:
+            binding.Context.gap_dtype = staticmethod(lambda n_sel, n_rows, nnz: np.uint16)
+            c16 = run_hot_path(ctx, seq, off, names, chunk_size=chunk, k=k, kmer_low_count=5, remove_non_chunk=0, compact=True)
+        finally:
+            binding.Context.gap_dtype = keep
+        assert c16.dcol8.dtype == np.uint16 and c16._indices is None
+        assert np.array_equal(c16.indices, full.indices) and np.array_equal(c16.data, full.data)
+        assert len(c16.escapes8[0][0]) <= len(c8.escapes8[0][0]) and (np.asarray(c16.dcol8) == 65535).sum() == len(c16.escapes8[0][0])
+        assert binding.Context.gap_dtype(5_600_000, 6600, 143_000_000) == np.uint16      # the 8-GPU weak-scaling shape
+        assert binding.Context.gap_dtype(673_070, 6621, 96_226_654) == np.uint8          # the bench workload
         assert comp.data16 is not None and comp.data16.dtype == np.uint16 and full.data16 is None
         assert np.array_equal(comp.indptr, full.indptr) and np.array_equal(comp.indices, full.indices)
         assert np.array_equal(comp.kmer_keys, full.kmer_keys) and np.array_equal(comp.df, full.df)
