@@ -208,6 +208,9 @@ int pc_csr_get8(pc_ctx* ctx, int64_t* indptr, uint8_t* dcol8, uint8_t* cnt8, int
  * entries per row beyond ~100: the 8-GPU weak-scaling run has 257) half of the one-byte gaps would escape at 12 bytes each;
  * 3 bytes per entry instead.  Escapes are fetched with pc_csr_escapes8_get as for pc_csr_get8. */
 int pc_csr_get_gap16(pc_ctx* ctx, int64_t* indptr, uint16_t* dcol16, uint8_t* cnt8, int loc, int64_t n_escapes[2]);
+/* ... and with gap and count sharing one uint16 ((gap << 4) | count; gap >= 4095 / count >= 15 escape as above): 2 bytes per
+ * entry for a large column universe too.  What the end-to-end path ships when pc gap_dtype picks the wide form. */
+int pc_csr_get_g12c4(pc_ctx* ctx, int64_t* indptr, uint16_t* packed, int loc, int64_t n_escapes[2]);
 int pc_csr_escapes8_get(pc_ctx* ctx, int64_t* col_pos, int32_t* col_val, int64_t* cnt_pos, float* cnt_val, int loc);
 
 /* ---- K7  TF-IDF + L2 rows (replaces sklearn TfidfTransformer().fit_transform, polycracker.py:395-396) -------

@@ -116,6 +116,7 @@ _SIGS = {
     "pc_csr_escapes_get": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "pc_csr_get8": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp]),
     "pc_csr_get_gap16": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, _vp]),
+    "pc_csr_get_g12c4": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
     "pc_csr_escapes8_get": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int]),
     "pc_tfidf_factors_get": (C.c_int, [_vp, _vp, _vp, C.c_int]),
     "pc_tfidf": (C.c_int, [_vp, _i64, _vp, C.c_int]),
@@ -718,8 +719,12 @@ class Context:
         n = np.zeros(2, np.int64)
         # the gap width follows the buffer: one byte (pc_csr_get8) or two (pc_csr_get_gap16; see gap_dtype)
         wide = dcol8 is not None and (dcol8.element_size() if hasattr(dcol8, "element_size") else dcol8.dtype.itemsize) == 2
+        loc = locs.pop() if locs else PC_HOST
+        if wide and cnt8 is None:                              # gap and count share the uint16 (pc_csr_get_g12c4)
+            check(lib.pc_csr_get_g12c4(self._h, ptr(indptr)[0], ptr(dcol8)[0], loc, n.ctypes.data), "pc_csr_get_g12c4")
+            return int(n[0]), int(n[1])
         fn, name = (lib.pc_csr_get_gap16, "pc_csr_get_gap16") if wide else (lib.pc_csr_get8, "pc_csr_get8")
-        check(fn(self._h, ptr(indptr)[0], ptr(dcol8)[0], ptr(cnt8)[0], locs.pop() if locs else PC_HOST, n.ctypes.data), name)
+        check(fn(self._h, ptr(indptr)[0], ptr(dcol8)[0], ptr(cnt8)[0], loc, n.ctypes.data), name)
         return int(n[0]), int(n[1])
 
     @staticmethod

@@ -2405,6 +2405,9 @@ int pc_csr_get8(pc_ctx* c, int64_t* indptr, uint8_t* dcol8, uint8_t* cnt8, int l
 int pc_csr_get_gap16(pc_ctx* c, int64_t* indptr, uint16_t* dcol16, uint8_t* cnt8, int loc, int64_t n_escapes[2]) {
     return csr_get_packed(c, indptr, dcol16, cnt8, loc, n_escapes, 2);
 }
+int pc_csr_get_g12c4(pc_ctx* c, int64_t* indptr, uint16_t* packed, int loc, int64_t n_escapes[2]) {
+    return csr_get_packed(c, indptr, packed, nullptr, loc, n_escapes, 3);       // 3 = 12-bit gap + 4-bit count in one uint16
+}
 static int csr_get_packed(pc_ctx* c, int64_t* indptr, void* dcol8, uint8_t* cnt8, int loc, int64_t n_escapes[2], int gap_bytes) {
     int rc = use_device(c); if (rc) return rc;
     if (!c->built) return fail(PC_ESTATE, "no matrix built");
@@ -2413,7 +2416,9 @@ static int csr_get_packed(pc_ctx* c, int64_t* indptr, void* dcol8, uint8_t* cnt8
     // column escapes: the first entry of every row + gaps >= 255 (at most n_selected / 255 per row); count escapes: entries
     // >= 255 (a k-mer that fills >= 255 windows of one chunk)
     // (sized so that they cannot overflow: low-complexity genomes put a count >= 255 into most entries)
-    const int64_t esc_gap = gap_bytes == 1 ? 255 : 65535;
+    const bool g12c4 = gap_bytes == 3;
+    if (g12c4) gap_bytes = 2;
+    const int64_t esc_gap = g12c4 ? 4095 : gap_bytes == 1 ? 255 : 65535;
     const int64_t col_cap = c->n_rows * (1 + c->n_sel / esc_gap) + 16, cnt_cap = c->nnz + 16;
     const int64_t col_cap_used = std::min<int64_t>(col_cap, c->nnz + 16);
     rc = c->d_dcol8.alloc(std::max<int64_t>(c->nnz * gap_bytes, 1)); if (rc) return rc;
@@ -2425,7 +2430,11 @@ static int csr_get_packed(pc_ctx* c, int64_t* indptr, void* dcol8, uint8_t* cnt8
     unsigned long long ne[2] = {0, 0};
     CU(cudaMemsetAsync(c->d_counter.p + 8, 0, 2 * sizeof(unsigned long long), c->stream));
     if (c->nnz > 0 && c->n_rows > 0) {
-        if (gap_bytes == 1)
+        if (g12c4)
+            LAUNCH(c, (pc::k_csr_pack_g12c4<256>), (unsigned int)c->n_rows, 256, c->d_indptr.p, c->d_indices.p, c->d_data.p,
+                   reinterpret_cast<unsigned short*>(c->d_dcol8.p), c->d_counter.p + 8, c->d_esc8_pos.p, c->d_esc8_val.p,
+                   (unsigned long long)col_cap_used, c->d_esc_pos.p, c->d_esc_val.p, (unsigned long long)cnt_cap);
+        else if (gap_bytes == 1)
             LAUNCH(c, (pc::k_csr_pack8<256, unsigned char>), (unsigned int)c->n_rows, 256, c->d_indptr.p, c->d_indices.p, c->d_data.p, c->d_dcol8.p,
                    c->d_cnt8.p, c->d_counter.p + 8, c->d_esc8_pos.p, c->d_esc8_val.p, (unsigned long long)col_cap_used, c->d_esc_pos.p,
                    c->d_esc_val.p, (unsigned long long)cnt_cap);
@@ -2437,7 +2446,7 @@ static int csr_get_packed(pc_ctx* c, int64_t* indptr, void* dcol8, uint8_t* cnt8
     READ_SMALL(c, ne, c->d_counter.p + 8, sizeof ne);
     if (indptr) { rc = copy_out(c, indptr, c->d_indptr.p, (c->n_rows + 1) * sizeof(int64_t), loc); if (rc) return rc; }
     if (dcol8) { rc = copy_out(c, dcol8, c->d_dcol8.p, c->nnz * gap_bytes, loc); if (rc) return rc; }
-    if (cnt8) { rc = copy_out(c, cnt8, c->d_cnt8.p, c->nnz, loc); if (rc) return rc; }
+    if (cnt8 && !g12c4) { rc = copy_out(c, cnt8, c->d_cnt8.p, c->nnz, loc); if (rc) return rc; }
     SYNC(c);
     if ((int64_t)ne[0] > col_cap_used || (int64_t)ne[1] > cnt_cap)
         return fail(PC_ESTATE, "escape lists of the 8-bit hand-off overflow (%llu columns, %llu counts): use pc_csr_get16", ne[0], ne[1]);

@@ -1542,6 +1542,36 @@ k_csr_pack8(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indi
     }
 }
 
+// Two bytes per entry for a large column universe: (gap << 4) | count, gap < 4095 and count < 15, else the field holds
+// its maximum and the value is listed apart (column escapes: absolute column; count escapes: the count).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k_csr_pack_g12c4(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ data,
+                 unsigned short* __restrict__ packed, unsigned long long* __restrict__ n_esc /* [0] columns, [1] counts */,
+                 int64_t* __restrict__ col_pos, int32_t* __restrict__ col_val, unsigned long long col_cap,
+                 int64_t* __restrict__ cnt_pos, float* __restrict__ cnt_val, unsigned long long cnt_cap)
+{
+    const int64_t row = blockIdx.x;
+    const int64_t beg = indptr[row], end = indptr[row + 1];
+    for (int64_t i = beg + threadIdx.x; i < end; i += THREADS) {
+        const int32_t c = indices[i];
+        int64_t gap = i == beg ? 4095 : (int64_t)c - (int64_t)indices[i - 1];
+        if (gap >= 4095) {
+            const unsigned long long p = atomicAdd(&n_esc[0], 1ull);
+            if (p < col_cap) { col_pos[p] = i; col_val[p] = c; }
+            gap = 4095;
+        }
+        const float v = data[i];
+        unsigned int cn = (unsigned int)v;
+        if (v >= 15.0f) {
+            const unsigned long long p = atomicAdd(&n_esc[1], 1ull);
+            if (p < cnt_cap) { cnt_pos[p] = i; cnt_val[p] = v; }
+            cn = 15u;
+        }
+        packed[i] = (unsigned short)(((unsigned int)gap << 4) | cn);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ N1 subgenome extraction
 // Row N1 of the scope table (polycracker.py:692-865): per-subgenome k-mer dictionaries, the differential-k-mer ratio
 // test, and the map-back of the differential k-mers onto every chunk.  All dictionaries are RepSlot tables (key -> int).

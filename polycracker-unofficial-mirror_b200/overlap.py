@@ -128,8 +128,8 @@ class StepPipeline:
         gdt = self.ctx.gap_dtype(n_sel, n_rows, nnz)         # one-byte column gaps, two for a large column universe
         wide = gdt == np.uint16
         d_dcol = self._dev(slot, "dcol16" if wide else "dcol8", nnz, torch.int16 if wide else torch.uint8)
-        d_cnt = self._dev(slot, "cnt8", nnz, torch.uint8)
-        n_col, n_cnt = self.ctx.csr8_into(d_indptr, d_dcol if nnz else None, d_cnt if nnz else None)
+        d_cnt = None if wide else self._dev(slot, "cnt8", nnz, torch.uint8)   # wide: gap << 4 | count in one uint16
+        n_col, n_cnt = self.ctx.csr8_into(d_indptr, d_dcol if (nnz or wide) else None, d_cnt if nnz else None)
         # the escape lists (a few MB) leave with the bulk copies on the copy-out stream: a host-synchronous read here would
         # queue on the copy engine behind the previous step's D2H and stall the pipeline
         d_ecp, d_ecv = self._dev(slot, "esc_col_pos", n_col, torch.int64), self._dev(slot, "esc_col_val", n_col, torch.int32)
@@ -147,7 +147,7 @@ class StepPipeline:
         # D2H on the copy-out stream into this slot's page-locked arena
         a = self.arena[slot]
         h = dict(keys=a.get("keys", n_sel, np.uint64), indptr=a.get("indptr", n_rows + 1, np.int64),
-                 dcol8=a.get("dcol16" if wide else "dcol8", nnz, gdt), cnt8=a.get("cnt8", nnz, np.uint8),
+                 dcol8=a.get("dcol16" if wide else "dcol8", nnz, gdt), cnt8=None if wide else a.get("cnt8", nnz, np.uint8),
                  idf=a.get("idf", n_sel, np.float32) if tfidf else None,
                  row_norm=a.get("row_norm", n_rows, np.float64) if tfidf else None, df=a.get("df", n_sel, np.int32),
                  esc_col_pos=a.get("esc_col_pos", n_col, np.int64), esc_col_val=a.get("esc_col_val", n_col, np.int32),

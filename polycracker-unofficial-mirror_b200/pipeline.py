@@ -71,11 +71,13 @@ def rebuild_counts(data16, escapes=None):
     return data
 
 
-def rebuild_indices(indptr, dcol8, col_escapes):
+def rebuild_indices(indptr, dcol8, col_escapes, packed_counts=False):
     """int32 column ids from the one-byte gaps of pc_csr_get8: an escape (first entry of a row, gap >= 255) carries its
     absolute column, every other entry adds its gap to the entry before it."""
     d = np.asarray(dcol8)
     d = d.view(np.uint16 if d.dtype.itemsize == 2 else np.uint8).astype(np.int64)      # one- or two-byte gaps
+    if packed_counts:                                           # pc_csr_get_g12c4: (gap << 4) | count
+        d >>= 4
     n = len(d)
     if n == 0:
         return np.zeros(0, np.int32)
@@ -90,8 +92,11 @@ def rebuild_indices(indptr, dcol8, col_escapes):
     return (c - c[last] + absval[last]).astype(np.int32)
 
 
-def rebuild_counts8(cnt8, cnt_escapes):
-    data = np.asarray(cnt8).view(np.uint8).astype(np.float32)
+def rebuild_counts8(cnt8, cnt_escapes, packed=None):
+    if cnt8 is None:                                            # pc_csr_get_g12c4: the low 4 bits of the packed uint16
+        data = (np.asarray(packed).view(np.uint16) & 15).astype(np.float32)
+    else:
+        data = np.asarray(cnt8).view(np.uint8).astype(np.float32)
     if cnt_escapes is not None and len(cnt_escapes[0]):
         data[np.asarray(cnt_escapes[0])] = np.asarray(cnt_escapes[1], dtype=np.float32)
     return data
@@ -129,15 +134,16 @@ class HotPathResult:
     @property
     def indices(self):
         if self._indices is None and self.dcol8 is not None:
-            self._indices = rebuild_indices(self.indptr, self.dcol8, self.escapes8[0])
+            # (a two-byte dcol8 without a cnt8 array is the packed form of pc_csr_get_g12c4: gap << 4 | count)
+            self._indices = rebuild_indices(self.indptr, self.dcol8, self.escapes8[0], packed_counts=self.cnt8 is None)
         return self._indices
 
     @property
     def data(self):
         if self._data is None and self.data16 is not None:
             self._data = rebuild_counts(self.data16, self.escapes)
-        if self._data is None and self.cnt8 is not None:
-            self._data = rebuild_counts8(self.cnt8, self.escapes8[1])
+        if self._data is None and (self.cnt8 is not None or self.dcol8 is not None):
+            self._data = rebuild_counts8(self.cnt8, self.escapes8[1], packed=self.dcol8)
         return self._data
 
     @property
@@ -291,7 +297,8 @@ def fetch_result(ctx, layout, k, scaffolds, n_sel, nnz, tfidf, stats, arena=None
         return HotPathResult(layout, k, scaffolds, keys, indptr, indices, None, None, df, stats, ctx.timings(),
                              data16=data16, escapes=escapes, idf=idf, row_norm=row_norm)
     gdt = ctx.gap_dtype(n_sel, n_rows, nnz) if hasattr(ctx, "gap_dtype") else np.uint8
-    dcol8, cnt8 = buf("dcol8" if gdt == np.uint8 else "dcol16", nnz, gdt), buf("cnt8", nnz, np.uint8)
-    n_col, n_cnt = ctx.csr8_into(indptr, dcol8 if nnz else None, cnt8 if nnz else None)
+    wide = gdt == np.uint16                                     # gap and count then share one uint16 (pc_csr_get_g12c4)
+    dcol8, cnt8 = buf("dcol16" if wide else "dcol8", nnz, gdt), (None if wide else buf("cnt8", nnz, np.uint8))
+    n_col, n_cnt = ctx.csr8_into(indptr, dcol8 if (nnz or wide) else None, cnt8 if nnz else None)
     return HotPathResult(layout, k, scaffolds, keys, indptr, None, None, None, df, stats, ctx.timings(), idf=idf,
                          row_norm=row_norm, dcol8=dcol8, cnt8=cnt8, escapes8=ctx.csr8_escapes(n_col, n_cnt))

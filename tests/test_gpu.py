@@ -484,9 +484,20 @@ def test_compact_handoff_matches_full_arrays(ctx):
             c16 = run_hot_path(ctx, seq, off, names, chunk_size=chunk, k=k, kmer_low_count=5, remove_non_chunk=0, compact=True)
         finally:
             binding.Context.gap_dtype = keep
-        assert c16.dcol8.dtype == np.uint16 and c16._indices is None
+        # ... which ships gap and count in ONE uint16 (pc_csr_get_g12c4: gap << 4 | count, 4095 / 15 escape)
+        assert c16.dcol8.dtype == np.uint16 and c16.cnt8 is None and c16._indices is None and c16._data is None
         assert np.array_equal(c16.indices, full.indices) and np.array_equal(c16.data, full.data)
-        assert len(c16.escapes8[0][0]) <= len(c8.escapes8[0][0]) and (np.asarray(c16.dcol8) == 65535).sum() == len(c16.escapes8[0][0])
+        assert np.array_equal(c16.tfidf.view(np.uint32), full.tfidf.view(np.uint32))
+        assert len(c16.escapes8[0][0]) <= len(c8.escapes8[0][0]) and ((np.asarray(c16.dcol8) >> 4) == 4095).sum() == len(c16.escapes8[0][0])
+        assert ((np.asarray(c16.dcol8) & 15) == 15).sum() == len(c16.escapes8[1][0]) == (full.data >= 15).sum()
+        # two-byte gaps next to one-byte counts (pc_csr_get_gap16), straight through the binding on the matrix just built
+        from polycracker_b200.pipeline import rebuild_counts8, rebuild_indices
+        nnz = len(full.indices)
+        g16, k8, ip = np.empty(nnz, np.uint16), np.empty(nnz, np.uint8), np.empty(len(full.indptr), np.int64)
+        n_col, n_cnt = ctx.csr8_into(ip, g16, k8)
+        esc = ctx.csr8_escapes(n_col, n_cnt)
+        assert np.array_equal(ip, full.indptr) and np.array_equal(rebuild_indices(ip, g16, esc[0]), full.indices)
+        assert np.array_equal(rebuild_counts8(k8, esc[1]), full.data) and (g16 == 65535).sum() == n_col
         assert binding.Context.gap_dtype(5_600_000, 6600, 143_000_000) == np.uint16      # the 8-GPU weak-scaling shape
         assert binding.Context.gap_dtype(673_070, 6621, 96_226_654) == np.uint8          # the bench workload
         assert comp.data16 is not None and comp.data16.dtype == np.uint16 and full.data16 is None
