@@ -685,7 +685,10 @@ def test_overlap_pipeline_and_sm_copy():
         genomes.append((torch.from_numpy(seq).pin_memory(), seq, off, names))
     with binding.Context(0) as plain:
         want = [run_hot_path(plain, seq, off, names, chunk_size=20000, k=23, kmer_low_count=5) for _, seq, off, names in genomes]
-    for ctas in (0, 8):
+    keep = binding.Context.__dict__["gap_dtype"]
+    for ctas, wide in ((0, False), (8, False), (0, True)):     # wide: the packed two-byte hand-off of a large column universe
+      binding.Context.gap_dtype = staticmethod(lambda n_sel, n_rows, nnz: np.uint16) if wide else keep
+      try:
         with binding.Context(0) as c2:
             pipe = StepPipeline(c2, dev, sm_copy_ctas=ctas)
             got = []
@@ -717,6 +720,8 @@ def test_overlap_pipeline_and_sm_copy():
                 c2.copy_async(back, d, stream=st.cuda_stream, n_ctas=4)
                 st.synchronize()
                 assert torch.equal(back, src)
+      finally:
+        binding.Context.gap_dtype = keep
 
 
 def test_external_repeat_set(ctx):
