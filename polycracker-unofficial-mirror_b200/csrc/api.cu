@@ -190,7 +190,8 @@ struct pc_ctx {
     int skm_nmax = 16;                          // tunable: longest run (k-mers) one record carries (lane balance of the count kernel)
     int skm_expand = 0;                         // tunable: 1 = expand the records into 8-byte k-mers (k_rec_expand) and count them with k_count_smem; 0 = expand inside the count kernel (k_count_skm)
     DevBuf<unsigned long long> d_skm_koff;      // skm_expand 1: k-mer offsets of the sub-buckets + expansion cursors
-    int skm_grp = 2;                            // tunable: k-mers of a record in flight per thread in the count kernel (2, 4, 8)
+    int skm_grp = 2;
+    int skm_m_force = 0;                        // tunable: minimizer length (0 = skm_choose_m)                            // tunable: k-mers of a record in flight per thread in the count kernel (2, 4, 8)
     int skm_min_k = 17;                         // auto mode: shortest k that takes the super-k-mer path
     int skm_stage = 2560;                       // tunable: records staged per CTA of the extraction (x 16 bytes of shared memory)
     bool skm_used = false;
@@ -969,6 +970,9 @@ static SkmPlan skm_plan(const pc_ctx* c, int k, int64_t windows_global, int worl
     pl.pb = pb;
     pl.nb2 = (unsigned int)std::min<int64_t>(PC_SUB_MAX, std::max<int64_t>(1, (nb_total + P - 1) / P));
     pl.m = pc::skm_choose_m(k, P * (int64_t)pl.nb2);
+    if (c->skm_m_force > 0 && c->skm_m_force <= k && ((k - c->skm_m_force + 1) & 1) == 0 && k - c->skm_m_force + 1 >= PC_SKM_WMIN &&
+        k - c->skm_m_force + 1 <= PC_SKM_WMAX && c->skm_m_force >= 9 && c->skm_m_force <= 16)
+        pl.m = c->skm_m_force;                                   // tunable (experiments): minimizer length
     if (pl.m == 0 || k > 32) return pl;
     pl.W = k - pl.m + 1;
     pl.nmax = std::max(1, std::min(std::min(c->skm_nmax, PC_SKM_COUNT_NMAX), PC_SKM_BASES - k + 1));
@@ -1353,6 +1357,7 @@ int pc_tune(pc_ctx* c, const char* key, int64_t value) {
     else if (k == "skm_nmax") c->skm_nmax = (int)std::max<int64_t>(1, std::min<int64_t>(PC_SKM_COUNT_NMAX, value));
     else if (k == "skm_min_k") c->skm_min_k = (int)value;
     else if (k == "skm_grp") c->skm_grp = (int)value;
+    else if (k == "skm_m") c->skm_m_force = (int)value;
     else if (k == "skm_expand") c->skm_expand = (int)value;
     else if (k == "skm_stage") c->skm_stage = (int)value;
     else if (k == "scatter_tile") c->scatter_tile = (int)value;

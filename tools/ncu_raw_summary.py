@@ -23,5 +23,14 @@ def conv(i, v):
         m = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
         return "%.3f" % (x * m / 1e9)
     return "%.1f" % x if "." in v else v
+PEAK = 6533.8                                                  # measured HBM copy bandwidth, GB/s (MEASURED_PEAKS.json)
 for r in rows[2:]:
-    print("| " + " | ".join(conv(i, r[i]) for i, _ in idx) + " |")
+    cells = [conv(i, r[i]) for i, _ in idx]
+    labs = [l for _, l in idx]
+    if "DRAM % of peak" in labs and not cells[labs.index("DRAM % of peak")].strip():
+        try:
+            gb = float(cells[labs.index("DRAM read GB")]) + float(cells[labs.index("DRAM write GB")])
+            cells[labs.index("DRAM % of peak")] = "%.1f" % (100.0 * gb / (float(cells[labs.index("ms")]) * 1e-3) / PEAK)
+        except ValueError:
+            pass
+    print("| " + " | ".join(cells) + " |")
