@@ -247,3 +247,40 @@ def test_hipmer_output_to_kcount_matches_the_reference_awk_line(tmp_path):
         assert open(tmp_path / "mine.kcount").read() == open(tmp_path / "awk.kcount").read()
     k, keys, counts = stages.read_kcount(str(tmp_path / "mine.kcount"))
     assert k == 21 and len(keys) == len(np.unique(keys)) and counts.min() >= 3
+
+
+def test_compact_handoff_rebuild_is_exact_for_every_packing():
+    """Host side of the compact matrix hand-off (pipeline.rebuild_indices / rebuild_counts8): the three packings the device
+    ships -- one-byte gaps + one-byte counts (pc_csr_get8), two-byte gaps (pc_csr_get_gap16), 12-bit gap + 4-bit count in one
+    uint16 (pc_csr_get_g12c4) -- restated in numpy, rebuild the int32 columns and float32 counts exactly; the width rule
+    (Context.gap_dtype) picks the wide form only for a large column universe."""
+    from polycracker_b200.pipeline import rebuild_counts8, rebuild_indices
+    rng = np.random.default_rng(3)
+    n_rows, n_cols = 300, 100_000                               # mean column gap of a row: 500
+    lens = rng.poisson(200, n_rows); lens[::7] = 0
+    indptr = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+    indices = np.concatenate([np.sort(rng.choice(n_cols, l, replace=False)) for l in lens] + [np.zeros(0, np.int64)]).astype(np.int32)
+    data = rng.geometric(0.4, len(indices)).astype(np.float32)
+    data[rng.random(len(data)) < 0.01] = 70000.0                   # counts beyond every field width
+    first = np.zeros(len(indices), bool); first[indptr[:-1][lens > 0]] = True
+    gap = np.where(first, 1 << 40, np.diff(indices.astype(np.int64), prepend=0))
+
+    def pack(gap_esc, cnt_esc):
+        g = np.minimum(gap, gap_esc); cn = np.minimum(data, cnt_esc)
+        ce = np.flatnonzero(gap >= gap_esc); ke = np.flatnonzero(data >= cnt_esc)
+        order = rng.permutation(len(ce))                        # the device appends escapes in no particular order
+        return g, cn, (ce[order], indices[ce[order]]), (ke, data[ke])
+
+    g, cn, ce, ke = pack(255, 255)
+    assert np.array_equal(rebuild_indices(indptr, g.astype(np.uint8), ce), indices)
+    assert np.array_equal(rebuild_counts8(cn.astype(np.uint8), ke), data)
+    g, cn, ce, ke = pack(65535, 255)
+    assert np.array_equal(rebuild_indices(indptr, g.astype(np.uint16), ce), indices)
+    g, cn, ce, ke = pack(4095, 15)
+    packed = ((g.astype(np.uint32) << 4) | cn.astype(np.uint32)).astype(np.uint16)
+    assert np.array_equal(rebuild_indices(indptr, packed, ce, packed_counts=True), indices)
+    assert np.array_equal(rebuild_counts8(None, ke, packed=packed), data)
+    assert len(ce[0]) < 0.01 * len(indices) < 0.4 * len(indices) < (gap >= 255).sum()   # what the wide form is for
+    assert binding.Context.gap_dtype(n_cols, n_rows, len(indices)) == np.uint16
+    assert binding.Context.gap_dtype(673_070, 6621, 96_226_654) == np.uint8
+    assert binding.Context.gap_dtype(10, 5, 0) == np.uint8
