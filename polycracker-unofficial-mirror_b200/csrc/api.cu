@@ -168,6 +168,8 @@ struct pc_ctx {
     int rowsort_warps = 16;                     // tunable: warps per CTA in the per-row sort (8 or 16)
     int relief_path = 0;                        // set while pc_count runs: 1 = k-mer partition, 2 = super-k-mer records (see relieve_pressure)
     bool rec_shared = false;                    // the record buffer has been exported to peer processes (pc_skm_export)
+    int select_raw = 0;                         // tunable: pc_select leaves the survivors unsorted and builds no repeat table (multi-GPU owners)
+    bool sel_unsorted = false;
     int csr_mode = -1;                          // tunable: rows -> CSR by -1 auto, 0 per-row radix sort, 1 shared-memory column bitmap (kernels_csr.cuh)
     int64_t csr_range_bits = 0, csr_ncap = 0;   // tunables (tests): columns per bitmap range / shared count slots (0 = as many as fit)
     DevBuf<unsigned long long> d_row_state;
@@ -1363,6 +1365,7 @@ int pc_tune(pc_ctx* c, const char* key, int64_t value) {
     else if (k == "scatter_tile") c->scatter_tile = (int)value;
     else if (k == "scatter_pack") c->scatter_pack = (int)value;
     else if (k == "rowsort_warps") c->rowsort_warps = (int)value;
+    else if (k == "select_raw") c->select_raw = (int)value;
     else if (k == "csr_mode") c->csr_mode = (int)value;
     else if (k == "csr_range_bits") c->csr_range_bits = value <= 0 ? 0 : ((std::max<int64_t>(1024, value) + 1023) / 1024) * 1024;
     else if (k == "csr_ncap") c->csr_ncap = std::max<int64_t>(0, value);
@@ -2017,6 +2020,15 @@ int pc_select(pc_ctx* c, uint32_t low, uint32_t high, int use_high, int64_t samp
             rc = select_into(c, low, high, c->sel_a.p, nullptr, cap, &n); if (rc) return rc;
         }
     }
+    if (c->select_raw && sampling <= 1) {
+        // multi-GPU owners (pc_tune select_raw 1): the survivors leave unsorted -- every rank sorts the all-gathered set in
+        // pc_set_selected anyway, so the owner's own sort and repeat table (0.45 ms per step) would be thrown away
+        c->sel = c->sel_a.p; c->n_sel = n;
+        c->selected = true; c->sel_unsorted = true;
+        if (n_selected) *n_selected = n;
+        return PC_OK;
+    }
+    c->sel_unsorted = false;
     {
         StageTimer t(c, ST_SORT);
         rc = c->sel_b.alloc(std::max<int64_t>(n, 1)); if (rc) return rc;
@@ -2084,7 +2096,7 @@ int pc_set_selected(pc_ctx* c, const uint64_t* keys, int64_t n, int k, int loc, 
             result = other;
         }
     }
-    c->sel = result; c->n_sel = (int64_t)nu;
+    c->sel = result; c->n_sel = (int64_t)nu; c->sel_unsorted = false;
     rc = build_rep_table(c); if (rc) return rc;
     c->selected = true;
     if (n_unique) *n_unique = c->n_sel;
@@ -2225,6 +2237,7 @@ static int rows_to_csr(pc_ctx* c, int64_t n_rows) {
 int pc_build_matrix(pc_ctx* c, const int32_t* chunk_row, int64_t n_rows, int64_t* nnz) {
     int rc = use_device(c); if (rc) return rc;
     if (!c->loaded || !c->selected) return fail(PC_ESTATE, "pc_build_matrix needs loaded sequences and a repeat set");
+    if (c->sel_unsorted) return fail(PC_ESTATE, "the repeat set was selected raw (pc_tune select_raw): install the gathered set with pc_set_selected first");
     if (n_rows < 0 || (c->n_chunks > 0 && !chunk_row)) return fail(PC_EINVAL, "bad build_matrix arguments");
     if (n_rows > 0x7FFFFFFF) return fail(PC_EINVAL, "too many rows");
     c->built = c->tfidf_done = false; c->n_esc = -1; c->n_esc8_col = c->n_esc8_cnt = -1;

@@ -51,6 +51,22 @@ def _to_host(ctx, t, torch, device):
     return t.cpu().numpy()
 
 
+def _select_raw(ctx, low, high, use_high):
+    """The owner's share of the repeat set, unsorted and without a repeat table of its own: every rank sorts the all-gathered
+    set in pc_set_selected anyway."""
+    raw = hasattr(ctx, "tune")
+    if raw:
+        try:
+            ctx.tune(select_raw=1)
+        except Exception:
+            raw = False                                        # (stand-in contexts of the CPU tests)
+    try:
+        return ctx.select(low, high, use_high, 1)
+    finally:
+        if raw:
+            ctx.tune(select_raw=0)
+
+
 def shard_chunks(layout, world):
     """Contiguous blocks of the string-sorted chunk list, balanced by bases.  Returns a list (per rank) of chunk
     index arrays, each in sorted-name order."""
@@ -367,7 +383,7 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
     owner_info = ctx.count_info()
     info = dict(owner_info, valid_windows=n_local)
     mark("count_buckets")
-    n_owner_sel = ctx.select(effective_low_count(k, kmer_low_count), kmer_high_count, bool(high_bool), 1)
+    n_owner_sel = _select_raw(ctx, effective_low_count(k, kmer_low_count), kmer_high_count, bool(high_bool))
     mark("select")
     if hasattr(ctx, "timings"):
         tm = ctx.timings()
@@ -426,7 +442,7 @@ def rerun_threshold(ctx, layout, ids, device, k=23, kmer_low_count=100, high_boo
     row0 = int(my_rows_global[kept].min()) if len(kept) else 0
     local_chunk_row = np.where(my_rows_global >= 0, my_rows_global - row0, -1).astype(np.int32)
     n_local_rows = len(kept)
-    n_owner_sel = ctx.select(effective_low_count(k, kmer_low_count), kmer_high_count, bool(high_bool), 1)
+    n_owner_sel = _select_raw(ctx, effective_low_count(k, kmer_low_count), kmer_high_count, bool(high_bool))
     sel_local = torch.empty(max(n_owner_sel, 1), dtype=torch.int64, device=device)
     if n_owner_sel:
         ctx.selected_into(sel_local)
