@@ -13,9 +13,10 @@
 //             with more distinct columns than fit -- count in the row's own slice of `data` in global memory)
 //   emit      the bitmap is walked one chunk (32 words) per warp: columns and df += 1 leave in ascending order and the
 //             words are cleared on the way; the counts follow as one coalesced copy.
-// Repeat sets larger than the bitmap (range_bits columns) are handled range by range (both sweeps walk the row's hits
-// once per range; the hits of one row are <= 300 KB and stay in L2).  The row's hits are read from the probe's hit
-// buffer; the second hit buffer and the two global ping-pong passes of the sort are gone.
+// Repeat sets larger than one bitmap are handled in power-of-two column ranges: the row's hits are first grouped by range
+// (a counting sort into the second hit buffer, which exists only then), and every range runs both sweeps over its own
+// hits.  The hits of one row are <= 300 KB and stay in L2 between the sweeps.  For a single range the row's hits are
+// read straight from the probe's hit buffer: no second buffer, none of the sort's global ping-pong passes.
 #pragma once
 #include "kernels.cuh"
 
