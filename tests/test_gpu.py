@@ -459,6 +459,38 @@ def test_rows_to_csr_bitmap_equals_sort_and_scipy(ctx):
         ctx.matrix_from_hits(np.array([0, 1]), np.array([7], np.int32), 7)       # column out of range
 
 
+def test_stage_timeline_and_raw_select(ctx):
+    """pc_stage_timeline: the stages of the last step in start order, each as long as pc_timings says, inside the step;
+    pc_tune select_raw (what multi-GPU owners use): the survivors leave unsorted, the matrix refuses to build on them until
+    the (gathered) set is installed with pc_set_selected -- and then equals the plain path's."""
+    p = synth.small_params(seed=91, genome_size=1_500_000)
+    seq, off, names = synth.generate(p)
+    ctx.reset_counters()
+    res = run_hot_path(ctx, seq, off, names, chunk_size=20000, k=23, kmer_low_count=5)
+    tl = ctx.stage_timeline()
+    tm = ctx.timings()
+    assert [n for n, _, _ in tl][:2] == ["h2d", "pack"] and {"count", "probe", "row_sort", "tfidf"} <= {n for n, _, _ in tl}
+    assert all(b >= a >= 0 for _, a, b in tl) and all(tl[i][1] <= tl[i + 1][1] for i in range(len(tl) - 1))
+    for name, a, b in tl:
+        assert abs((b - a) - tm[name]) < 0.05, (name, a, b, tm[name])
+    lay = ChunkLayout(names, off, 20000)
+    scaffolds, chunk_row = lay.rows()
+    try:
+        ctx.tune(select_raw=1)
+        n = ctx.select(5, 2000000, False, 1)
+        raw = ctx.selected(n)
+        assert n == len(res.kmer_keys) and not np.array_equal(raw, res.kmer_keys) and np.array_equal(np.sort(raw), res.kmer_keys)
+        with pytest.raises(binding.PolycrackerError, match="select_raw"):
+            ctx.build_matrix(chunk_row, len(scaffolds))
+        ctx.tune(select_raw=0)
+        assert ctx.set_selected(raw, 23) == n
+        nnz = ctx.build_matrix(chunk_row, len(scaffolds))
+        indptr, indices, data = ctx.csr(len(scaffolds), nnz)
+        assert np.array_equal(indptr, res.indptr) and np.array_equal(indices, res.indices) and np.array_equal(data, res.data)
+    finally:
+        ctx.tune(select_raw=0)
+
+
 def test_compact_handoff_matches_full_arrays(ctx):
     """What crosses PCIe in the end-to-end path (pc_csr_get8: one byte per column gap and per count + escapes, 2 bytes per
     entry; or pc_csr_get16: 6 bytes; both with pc_tfidf_factors_get) rebuilds on the host to exactly the int32 / float32 arrays
