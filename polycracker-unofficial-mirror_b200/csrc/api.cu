@@ -170,6 +170,8 @@ struct pc_ctx {
     bool rec_shared = false;                    // the record buffer has been exported to peer processes (pc_skm_export)
     int select_raw = 0;                         // tunable: pc_select leaves the survivors unsorted and builds no repeat table (multi-GPU owners)
     bool sel_unsorted = false;
+    int gram_preround = 0;                      // tunable: pc_densify_panel rounds the values to TF32, pc_gram_accumulate does not round again
+    int gram_variant = 1;                       // tunable: Gram kernel, 0 = one CTA per 128 x 128 tile, 1 = persistent 128 x 256 tiles with two TMEM accumulators
     int csr_mode = -1;                          // tunable: rows -> CSR by -1 auto, 0 per-row radix sort, 1 shared-memory column bitmap (kernels_csr.cuh)
     int64_t csr_range_bits = 0, csr_ncap = 0;   // tunables (tests): columns per bitmap range / shared count slots (0 = as many as fit)
     DevBuf<unsigned long long> d_row_state;
@@ -1366,6 +1368,8 @@ int pc_tune(pc_ctx* c, const char* key, int64_t value) {
     else if (k == "scatter_pack") c->scatter_pack = (int)value;
     else if (k == "rowsort_warps") c->rowsort_warps = (int)value;
     else if (k == "select_raw") c->select_raw = (int)value;
+    else if (k == "gram_variant") c->gram_variant = (int)value;
+    else if (k == "gram_preround") c->gram_preround = value ? 1 : 0;
     else if (k == "csr_mode") c->csr_mode = (int)value;
     else if (k == "csr_range_bits") c->csr_range_bits = value <= 0 ? 0 : ((std::max<int64_t>(1024, value) + 1023) / 1024) * 1024;
     else if (k == "csr_ncap") c->csr_ncap = std::max<int64_t>(0, value);
@@ -2601,7 +2605,7 @@ int pc_densify_panel(pc_ctx* c, int which, int64_t col0, int ncols, float* out_d
     if (c->n_rows > 0) {
         StageTimer t(c, ST_GRAM);
         LAUNCH(c, (pc::k_densify_panel<float, 256>), (unsigned int)c->n_rows, 256, c->d_indptr.p, c->d_indices.p, values, col0, ncols,
-               out_dev, ld);
+               out_dev, ld, c->gram_preround);
     }
     return PC_OK;
 }
@@ -2643,7 +2647,25 @@ int pc_gram_accumulate(pc_ctx* c, float* panel_dev, int64_t n_rows, int ncols, i
     const int nt = (int)((n_rows + pc::gram::BM - 1) / pc::gram::BM);
     const int n_kblocks = (ncols + pc::gram::BK - 1) / pc::gram::BK;
     StageTimer t(c, ST_GRAM);
-    LAUNCH(c, pc::gram::k_round_tf32, (unsigned int)std::min<int64_t>(148 * 16, (n_rows * ncols + 255) / 256), 256, panel_dev, n_rows, ncols, ld);
+    if (!c->gram_preround)                                     // (pc_tune gram_preround 1: pc_densify_panel already rounded the panel)
+        LAUNCH(c, pc::gram::k_round_tf32, (unsigned int)std::min<int64_t>(148 * 16, (n_rows * ncols + 255) / 256), 256, panel_dev, n_rows, ncols, ld);
+    if (c->gram_variant == 1) {
+        // persistent 128 x 256 tiles, two TMEM accumulators (gram_tc.cuh, namespace v2): a second tensor map with a 256-row box
+        CUtensorMap tm_b;
+        const cuuint32_t box_b[2] = {(cuuint32_t)pc::gram::BK, (cuuint32_t)pc::gram::v2::BN2};
+        r = encode(&tm_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, panel_dev, dims, strides, box_b, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(PC_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+        const int ntn = (int)((n_rows + pc::gram::v2::BN2 - 1) / pc::gram::v2::BN2);
+        int n_tiles = 0;
+        for (int ti = 0; ti < nt; ++ti) n_tiles += ntn - (ti >> 1);
+        CU(cudaFuncSetAttribute(pc::gram::v2::k_gram_tf32_p, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pc::gram::v2::SMEM_BYTES2));
+        c->launches++;
+        pc::gram::v2::k_gram_tf32_p<<<(unsigned int)std::min(n_tiles, 148), pc::gram::THREADS, pc::gram::v2::SMEM_BYTES2, c->stream>>>(
+            tm, tm_b, k_dev, (int)n_rows, ldk, n_kblocks, ntn, n_tiles);
+        CU(cudaGetLastError());
+        return PC_OK;
+    }
     CU(cudaFuncSetAttribute(pc::gram::k_gram_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pc::gram::SMEM_BYTES));
     c->launches++;
     pc::gram::k_gram_tf32<<<(unsigned int)(nt * (nt + 1) / 2), pc::gram::THREADS, pc::gram::SMEM_BYTES, c->stream>>>(
@@ -2655,7 +2677,7 @@ int pc_gram_accumulate(pc_ctx* c, float* panel_dev, int64_t n_rows, int ncols, i
 int pc_gram_finish(pc_ctx* c, float* k_dev, int64_t n_rows, int64_t ldk) {
     int rc = use_device(c); if (rc) return rc;
     if (!k_dev || n_rows < 1 || n_rows > 0x7FFFFFFF || ldk < n_rows) return fail(PC_EINVAL, "bad pc_gram_finish arguments");
-    LAUNCH(c, pc::gram::k_gram_mirror, (unsigned int)std::min<int64_t>(148 * 16, (n_rows * n_rows + 255) / 256), 256, k_dev, (int)n_rows, ldk);
+    LAUNCH(c, pc::gram::v2::k_gram_mirror_all, (unsigned int)std::min<int64_t>(148 * 16, (n_rows * n_rows + 255) / 256), 256, k_dev, (int)n_rows, ldk);
     return PC_OK;
 }
 

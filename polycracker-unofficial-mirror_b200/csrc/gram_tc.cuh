@@ -12,7 +12,7 @@
 // Only tiles with j >= i are computed (K is symmetric); k_gram_mirror copies the upper triangle down at the end.
 // Warp roles: 0 = TMA producer, 1 = TMEM allocation + MMA issue, 2..5 = epilogue.  Two CTAs fit one SM (97 KB of shared
 // memory, 128 TMEM columns each), so one CTA's epilogue overlaps the other's main loop.
-// TF32 keeps 10 mantissa bits: the panel is rounded to nearest TF32 first (k_round_tf32) so the products are unbiased;
+// TF32 keeps 10 mantissa bits: the panel is rounded to nearest TF32 first (by the panel kernel, or k_round_tf32) so the products are unbiased;
 // K is within 1e-3 relative of the float64 result (tests/test_gpu.py::test_n3_gram_matrix).
 #pragma once
 #include <cuda.h>
@@ -208,6 +208,165 @@ k_gram_tf32(const __grid_constant__ CUtensorMap tm, float* __restrict__ K, int n
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
+
+// ------------------------------------------------------------------------------------------------ persistent variant
+// The kernel above pulls 32 KB of operands from L2 for every 128 x 128 x 32 block of products: 32 flop per byte, and ncu shows
+// the tensor pipe only 22 % busy while the CTAs wait for their tiles.  This variant raises the reuse and overlaps the
+// epilogue: one persistent CTA per SM walks 128 x 256 tiles (one tcgen05.mma of N = 256 per K step: 48 KB per block of
+// products, 43.7 flop per byte), four stages, and TWO accumulators of 256 TMEM columns -- the epilogue warps drain one
+// while the MMA thread fills the other (tmem_full / tmem_empty barriers).  Tiles with any column on or above the diagonal
+// are computed: column block tJ >= ti / 2.
+namespace v2 {
+constexpr int BN2 = 256;
+constexpr int STAGES2 = 4;
+constexpr uint32_t A_BYTES = BM * BK * 4, B_BYTES = BN2 * BK * 4;          // 16 KB + 32 KB per stage
+constexpr uint32_t TMEM_COLS2 = 512;                                          // two 128 x 256 float32 accumulators
+constexpr size_t SMEM_BYTES2 = 1024 + (size_t)STAGES2 * (A_BYTES + B_BYTES) + 256;
+constexpr uint32_t IDESC2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN2 >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void umma_tf32_n256(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC2), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory");
+}
+// tile t of the trapezoid: row block ti (128 rows), column block tJ (256 columns), tJ >= ti / 2
+__device__ __forceinline__ void tile_of2(int t, int ntn, int& ti, int& tj) {
+    int i = 0, rowlen = ntn;
+    while (t >= rowlen) { t -= rowlen; ++i; rowlen = ntn - (i >> 1); }
+    ti = i; tj = (i >> 1) + t;
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+k_gram_tf32_p(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, float* __restrict__ K, int n_rows,
+              int64_t ldk, int n_kblocks, int ntn, int n_tiles)
+{
+    extern __shared__ uint8_t gram_smem_raw[];
+    uint8_t* smem = gram_smem_raw + ((1024u - (smem_u32(gram_smem_raw) & 1023u)) & 1023u);
+    uint8_t* tiles = smem;                                      // [STAGES2][A 16 KB | B 32 KB]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES2 * (A_BYTES + B_BYTES));
+    uint64_t* empty = full + STAGES2;
+    uint64_t* tfull = empty + STAGES2;                          // [2] accumulator complete
+    uint64_t* tempty = tfull + 2;                               // [2] accumulator drained (4 epilogue warps arrive)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_a)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tm_b)) : "memory");
+        for (int s = 0; s < STAGES2; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS2) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                        // ---- TMA producer
+            uint32_t it = 0;                                    // k-blocks issued so far (stage = it % STAGES2)
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                int ti, tj;
+                tile_of2(tile, ntn, ti, tj);
+                for (int kb = 0; kb < n_kblocks; ++kb, ++it) {
+                    const uint32_t s = it % STAGES2, ph = (it / STAGES2) & 1u;
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    mbar_expect_tx(&full[s], A_BYTES + B_BYTES);
+                    uint8_t* a = tiles + (size_t)s * (A_BYTES + B_BYTES);
+                    tma_load_2d(a, &tm_a, &full[s], kb * BK, ti * BM);
+                    tma_load_2d(a + A_BYTES, &tm_b, &full[s], kb * BK, tj * BN2);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {                                        // ---- MMA issue
+            uint32_t it = 0, nt = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++nt) {
+                const uint32_t acc = nt & 1u, aph = (nt >> 1) & 1u;
+                mbar_wait(&tempty[acc], aph ^ 1u);              // the epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tacc = tmem_base + acc * (uint32_t)BN2;
+                for (int kb = 0; kb < n_kblocks; ++kb, ++it) {
+                    const uint32_t s = it % STAGES2, ph = (it / STAGES2) & 1u;
+                    mbar_wait(&full[s], ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = smem_u32(tiles + (size_t)s * (A_BYTES + B_BYTES));
+                    const uint64_t adesc = smem_desc(a_addr), bdesc = smem_desc(a_addr + A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma_tf32_n256(tacc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), (uint32_t)((kb | k) != 0));
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&tfull[acc]);
+            }
+        }
+    } else {                                                    // ---- epilogue warps 2..5
+        const int g = warp & 3;
+        uint32_t nt = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++nt) {
+            int ti, tj;
+            tile_of2(tile, ntn, ti, tj);
+            const uint32_t acc = nt & 1u, aph = (nt >> 1) & 1u;
+            mbar_wait(&tfull[acc], aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int row = ti * BM + g * 32 + lane;
+#pragma unroll 1
+            for (int c = 0; c < BN2 / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(g * 32) << 16) + acc * (uint32_t)BN2 + (uint32_t)(c * 32), v);
+                const int col0 = tj * BN2 + c * 32;
+                if (row < n_rows && col0 < n_rows) {
+                    float* out = K + (int64_t)row * ldk + col0;
+                    if (col0 + 32 <= n_rows && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            float4 o = *reinterpret_cast<float4*>(out + 4 * q);
+                            o.x += __uint_as_float(v[4 * q]); o.y += __uint_as_float(v[4 * q + 1]);
+                            o.z += __uint_as_float(v[4 * q + 2]); o.w += __uint_as_float(v[4 * q + 3]);
+                            *reinterpret_cast<float4*>(out + 4 * q) = o;
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q)
+                            if (col0 + q < n_rows) out[q] += __uint_as_float(v[q]);
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty[acc]);           // this warp's 32 lanes of the accumulator are free again
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS2) : "memory");
+    }
+}
+
+// K[j][i] = K[i][j] for every j > i (the persistent kernel computes every entry on or above the diagonal, and a few below
+// it inside the tiles that straddle it: those are overwritten with their mirror image)
+__global__ void __launch_bounds__(256)
+k_gram_mirror_all(float* __restrict__ K, int n, int64_t ldk)
+{
+    const int64_t total = (int64_t)n * n;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx / n), j = (int)(idx - (int64_t)i * n);
+        if (j > i) K[(int64_t)j * ldk + i] = K[(int64_t)i * ldk + j];
+    }
+}
+}  // namespace v2
 
 // K[j][i] = K[i][j] for j > i (the kernel above fills the upper triangle of every tile pair ti <= tj; inside a
 // diagonal tile both halves are computed)

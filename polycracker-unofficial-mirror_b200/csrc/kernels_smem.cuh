@@ -769,7 +769,7 @@ template <> __device__ __forceinline__ float gram_cast<float>(float v) { return 
 template <typename T, int THREADS>
 __global__ void __launch_bounds__(THREADS)
 k_densify_panel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ indices, const float* __restrict__ values,
-                int64_t col0, int ncols, T* __restrict__ out, int64_t ld)
+                int64_t col0, int ncols, T* __restrict__ out, int64_t ld, int round_tf32 /* float panels for the tensor-core Gram kernel */)
 {
     const int64_t row = blockIdx.x;
     T* o = out + row * ld;
@@ -781,7 +781,13 @@ k_densify_panel(const int64_t* __restrict__ indptr, const int32_t* __restrict__ 
     for (int64_t i = lo + threadIdx.x; i < end; i += THREADS) {
         const int64_t c = (int64_t)indices[i] - col0;
         if (c >= ncols) break;                                // columns ascend inside a row
-        o[c] = gram_cast<T>(values[i]);
+        float v = values[i];
+        if (round_tf32) {                                       // round to nearest TF32 here instead of in a pass of its own
+            uint32_t r;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+            v = __uint_as_float(r);
+        }
+        o[c] = gram_cast<T>(v);
     }
 }
 

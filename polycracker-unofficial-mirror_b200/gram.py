@@ -35,6 +35,8 @@ def gram_matrix(ctx, n_rows, n_cols, values="tfidf", kernel="linear", panel_cols
     bufs = [torch.empty((n_rows, panel_cols), dtype=torch.float32, device=device) for _ in range(2)]
     old_tf32 = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = bool(tf32)
+    if engine == "tcgen05":
+        ctx.tune(gram_preround=1)                              # the panel kernel rounds to TF32: no pass of its own
     try:
         with torch.cuda.stream(stream):
             ctx.set_stream(stream.cuda_stream)               # panel kernels and GEMMs are ordered on one stream
@@ -57,6 +59,8 @@ def gram_matrix(ctx, n_rows, n_cols, values="tfidf", kernel="linear", panel_cols
                 raise ValueError("kernel must be 'linear' or 'cosine'")
         stream.synchronize()
     finally:
+        if engine == "tcgen05":
+            ctx.tune(gram_preround=0)
         torch.backends.cuda.matmul.allow_tf32 = old_tf32
         ctx.set_stream(ctx_stream_before)
     return K

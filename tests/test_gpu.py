@@ -678,14 +678,39 @@ def test_n3_gram_matrix(ctx):
     np.testing.assert_allclose(got, want, rtol=0, atol=2e-3)                  # TF32 products: <= 1e-3 of the unit diagonal
     # the hand-written tcgen05 kernel (TF32 operands rounded to nearest, float32 accumulation in TMEM): 1e-3 relative;
     # panel widths that leave a partial K block, a partial last panel, one panel for everything
-    for panel in (100, 1000, 4096, 1 << 20):
-        got = gram.gram_matrix_numpy(ctx, X.shape[0], X.shape[1], values="tfidf", kernel="linear", panel_cols=panel)
-        np.testing.assert_allclose(got, want, rtol=1e-3, atol=1e-5)
-        assert np.array_equal(got, got.T)
+    # (gram_variant 0: one CTA per 128 x 128 tile; 1, the default: persistent CTAs, 128 x 256 tiles, two TMEM accumulators)
+    try:
+        for variant in (0, 1):
+            ctx.tune(gram_variant=variant)
+            for panel in (100, 1000, 4096, 1 << 20):
+                got = gram.gram_matrix_numpy(ctx, X.shape[0], X.shape[1], values="tfidf", kernel="linear", panel_cols=panel)
+                np.testing.assert_allclose(got, want, rtol=1e-3, atol=1e-5)
+                assert np.array_equal(got, got.T)
+    finally:
+        ctx.tune(gram_variant=1)
     C = res.csr_matrix("counts")
     got = gram.gram_matrix_numpy(ctx, C.shape[0], C.shape[1], values="counts", kernel="cosine")
     np.testing.assert_allclose(got, cosine_similarity(C), rtol=1e-3, atol=1e-6)
     assert np.all(got[-1] == 0)                                               # the all-N chunk: an empty row stays zero
+    try:
+        # several tiles per persistent CTA (3 000 rows: 156 tiles of 128 x 256 on 148 SMs, so the two accumulators alternate),
+        # ragged last row / column blocks, small integer counts: TF32 products and float32 sums are exact here
+        rng = np.random.default_rng(5)
+        n_rows, n_cols = 3000, 5000
+        lens = rng.poisson(40, n_rows).astype(np.int64); lens[::11] = 0
+        ro = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        cols = rng.integers(0, n_cols, int(ro[-1])).astype(np.int32)
+        nnz = ctx.matrix_from_hits(ro, cols, n_cols)
+        ip, ix, dt = ctx.csr(n_rows, nnz)
+        M = sps.csr_matrix((dt, ix, ip), shape=(n_rows, n_cols))
+        exact = (M @ M.T).toarray().astype(np.float32)
+        for variant in (0, 1):
+            ctx.tune(gram_variant=variant)
+            for panel in (512, 5000):
+                got = gram.gram_matrix_numpy(ctx, n_rows, n_cols, values="counts", kernel="linear", panel_cols=panel)
+                assert np.array_equal(got, exact), (variant, panel, np.abs(got - exact).max())
+    finally:
+        ctx.tune(gram_variant=1)
 
 
 def test_threshold_watch_fused_select(ctx):
