@@ -271,7 +271,8 @@ int pc_scaled_get(pc_ctx* ctx, float* data, int loc);
  * The contraction runs over column panels densified on the fly: pc_densify_panel writes rows [0, n_rows) x columns
  * [col0, col0 + ncols) of the built matrix (which = 0 raw counts, 1 TF-IDF, 2 standard-scaled) as dense float32 into
  * out_dev (device, row-major, leading dimension ld >= ncols), asynchronously on the ctx stream.  polycracker_b200/gram.py
- * accumulates G += P P^T over the panels (a plain GEMM: cuBLAS through torch) and applies the cosine normalisation. */
+ * accumulates G += P P^T over the panels (pc_gram_accumulate below; or, as a cross-check, a plain cuBLAS GEMM through torch) and
+ * applies the cosine normalisation.  pc_tune gram_preround 1 makes this call round the values to nearest TF32 for the tensor cores. */
 int pc_densify_panel(pc_ctx* ctx, int which, int64_t col0, int ncols, float* out_dev, int64_t ld);
 /* The contraction itself on the 5th-generation tensor cores (csrc/gram_tc.cuh: TMA-fed tcgen05.mma kind::tf32, TMEM
  * accumulators): K += P P^T for the tiles on and above the diagonal, P = panel_dev (n_rows x ncols, leading dimension ld a
