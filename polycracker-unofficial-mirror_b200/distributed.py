@@ -175,15 +175,17 @@ def device_view(torch, ptr, n, device):
     return torch.as_tensor(_DevView(ptr, n), device=device)
 
 
-def peer_pointers(ctx, torch, dist, device, handle, own_ptr, cache_name="_pc_peers"):
+def peer_pointers(ctx, torch, dist, device, handle, own_ptr, cache_name="_pc_peers", handles=None):
     """Device pointers of every rank's exported buffer in THIS process (own buffer: own pointer).  The 64-byte CUDA IPC
-    handles are all-gathered every step (a 64-byte collective) and a peer buffer is (re)opened only when its handle
-    changed, i.e. when that rank had to grow its buffer; the mapping it replaces is closed."""
+    handles are all-gathered every step (a 64-byte collective -- or they arrive in `handles`, piggy-backed on a collective
+    the caller needed anyway) and a peer buffer is (re)opened only when its handle changed, i.e. when that rank had to grow
+    its buffer; the mapping it replaces is closed."""
     world, rank = dist.get_world_size(), dist.get_rank()
-    mine = torch.from_numpy(np.ascontiguousarray(handle).copy()).to(device)
-    allh = [torch.empty(64, dtype=torch.uint8, device=device) for _ in range(world)]
-    dist.all_gather(allh, mine)
-    handles = [h.tobytes() for h in _to_host(ctx, torch.stack(allh), torch, device)]
+    if handles is None:
+        mine = torch.from_numpy(np.ascontiguousarray(handle).copy()).to(device)
+        allh = [torch.empty(64, dtype=torch.uint8, device=device) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        handles = [h.tobytes() for h in _to_host(ctx, torch.stack(allh), torch, device)]
     cache = getattr(ctx, cache_name, None)
     if cache is None:
         cache = {}
@@ -279,11 +281,14 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
         off, recs, hist = ctx.skm_partition(k, skm)
         mark("pack+partition")
         n_local_records = int(off[-1])
-        sizes = torch.from_numpy(np.diff(off).astype(np.int64)).to(device)
-        gathered = [torch.empty(P, dtype=torch.int64, device=device) for _ in range(world)]
+        # one all-gather carries the bucket sizes AND the 64-byte IPC handle of the record buffer (8 more int64), and the
+        # histogram all-to-all below is queued behind it before the host looks at either: one read-back instead of three
+        payload = np.diff(off).astype(np.int64)
+        if use_peer:
+            payload = np.concatenate([payload, np.frombuffer(np.ascontiguousarray(handle).tobytes(), dtype=np.int64)])
+        sizes = torch.from_numpy(payload).to(device)
+        gathered = [torch.empty(len(payload), dtype=torch.int64, device=device) for _ in range(world)]
         dist.all_gather(gathered, sizes)
-        sizes_all = _to_host(ctx, torch.stack(gathered), torch, device)   # [sender, bucket], in records
-        mark("bucket_sizes_allgather")
         # every sender's packed sub-bucket histogram ((k-mers << 32) | records) of MY buckets, summed: the owner's scatter
         # offsets and the size of its k-mer list, without reading any record twice
         h_local = hist if torch.is_tensor(hist) else device_view(torch, hist, P * nb2, device)
@@ -292,12 +297,15 @@ def run_hot_path_distributed(ctx, layout, fetch_chunks, device, chunk_size=75000
         dist.all_to_all_single(h_recv, h_local.contiguous(), output_split_sizes=[n_mine] * world,
                                input_split_sizes=[(q_lo[r + 1] - q_lo[r]) * nb2 for r in range(world)])
         staged_hist = h_recv.view(world, n_mine).sum(dim=0).contiguous()
+        gathered_all = _to_host(ctx, torch.stack(gathered), torch, device)
+        sizes_all = np.ascontiguousarray(gathered_all[:, :P])          # [sender, bucket], in records
         _stream_sync(torch, device)
-        mark("sub_hist_exchange")
+        mark("sizes+sub_hist_exchange")
         seg_begin, seg_len = owner_segments(sizes_all, q_lo, rank)
         recv_records = int(seg_len.sum())
         if use_peer:
-            peers = peer_pointers(ctx, torch, dist, device, handle, recs, cache_name="_pc_skm_peers")
+            all_handles = [np.ascontiguousarray(gathered_all[r, P:]).tobytes() for r in range(world)]
+            peers = peer_pointers(ctx, torch, dist, device, handle, recs, cache_name="_pc_skm_peers", handles=all_handles)
             mark("peer_handles")
             seg_base = np.repeat(np.asarray(peers, dtype=np.uint64)[None, :], seg_len.shape[0], axis=0)
             ctx.skm_count_from(k, skm, seg_base, seg_begin, seg_len, staged_hist)
